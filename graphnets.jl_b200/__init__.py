@@ -1,0 +1,18 @@
+"""graphnets.jl_b200 - B200-native GNBlock / GNCore forward path behind GraphNets.jl's API.
+
+Exports mirror the reference module (src/GraphNets.jl:12-50).  The directory name carries a dot,
+so import it through the repo-root shim:  `import graphnets_b200 as gn`.
+"""
+from ._lib import lib, LIB_PATH, GnbError
+from .engine import get_engine
+from .api import (GNData, GNGraphBatch, Padded, batch, batch_compact, unbatch, checks, efview, nfview, gfview,
+                  flatunpaddednf, flatunpaddedef, collapsef, unpaddedcollapsedef, flatunpaddedcollapsedef)
+from .layers import (GNBlock, GNCore, GNCoreList, GNSequential, GNFeedForward, GNGraphNorm, Dense, Chain,
+                     LayerNorm, Dropout, set_precision, get_precision)
+from .shard import shard_ranges, shard_batch
+
+__all__ = [
+    "GNGraphBatch", "batch", "batch_compact", "unbatch", "GNBlock", "GNCore", "GNCoreList", "GNSequential", "efview", "nfview",
+    "gfview", "flatunpaddednf", "flatunpaddedef", "collapsef", "unpaddedcollapsedef", "flatunpaddedcollapsedef",
+    "GNData", "Padded", "set_precision", "get_precision", "get_engine", "shard_ranges", "shard_batch",
+]

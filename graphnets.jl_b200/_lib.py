@@ -1,0 +1,105 @@
+"""ctypes binding of libgnb200.so - the C ABI declared in include/gnb200.h.
+
+There is no CPU fallback: if the library is missing the import fails, and every compute entry
+point fails with the library's own error when no B200 is present."""
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libgnb200.so")
+
+GNB_OK, GNB_ERR_INVALID, GNB_ERR_CUDA, GNB_ERR_OOM, GNB_ERR_UNSUPPORTED = 0, -1, -2, -3, -4
+PREC_FP32, PREC_BF16, PREC_AUTO = 0, 2, 3
+ADJ_F32, ADJ_U8, ADJ_I32 = 0, 1, 2
+LAYER_BLOCK, LAYER_CORE = 0, 1
+PRECISIONS = {"fp32": PREC_FP32, "bf16": PREC_BF16, "auto": PREC_AUTO}
+
+f32p = C.POINTER(C.c_float)
+i32p = C.POINTER(C.c_int32)
+
+
+class BlockParams(C.Structure):
+    _fields_ = [("in_e", C.c_int32), ("in_n", C.c_int32), ("in_g", C.c_int32),
+                ("out_e", C.c_int32), ("out_n", C.c_int32), ("out_g", C.c_int32),
+                ("We", C.c_void_p), ("be", C.c_void_p), ("Wn", C.c_void_p), ("bn", C.c_void_p),
+                ("Wg", C.c_void_p), ("bg", C.c_void_p)]
+
+
+class FfnParams(C.Structure):
+    _fields_ = [("W1", C.c_void_p), ("b1", C.c_void_p), ("W2", C.c_void_p), ("b2", C.c_void_p)]
+
+
+class LnParams(C.Structure):
+    _fields_ = [("gamma", C.c_void_p), ("beta", C.c_void_p), ("eps", C.c_float), ("eps_mode", C.c_int32)]
+
+
+class CoreParams(C.Structure):
+    _fields_ = [("block", BlockParams), ("ffn", FfnParams * 3), ("ln1", LnParams * 3), ("ln2", LnParams * 3)]
+
+
+class Layer(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("_pad", C.c_int32), ("block", BlockParams), ("core", CoreParams)]
+
+
+# name -> (restype, argtypes); must list every symbol include/gnb200.h declares
+SIGNATURES = {
+    "gnb_version": (C.c_int, []),
+    "gnb_last_error": (C.c_char_p, []),
+    "gnb_ctx_create": (C.c_void_p, [C.c_int, C.POINTER(C.c_int)]),
+    "gnb_ctx_destroy": (C.c_int, [C.c_void_p]),
+    "gnb_ctx_set_stream": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "gnb_sync": (C.c_int, [C.c_void_p]),
+    "gnb_ctx_launch_count": (C.c_int64, [C.c_void_p]),
+    "gnb_graph_lower": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, i32p, C.c_int, C.c_int, C.c_int,
+                                  C.POINTER(C.c_void_p)]),
+    "gnb_graph_destroy": (C.c_int, [C.c_void_p]),
+    "gnb_graph_counts": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64), i32p, i32p]),
+    "gnb_graph_export_host": (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_void_p] * 7),
+    "gnb_pad_edges": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
+    "gnb_unpad_edges": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
+    "gnb_pad_nodes": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
+    "gnb_unpad_nodes": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
+    "gnb_collapse_edges": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
+    "gnb_model_create": (C.c_int, [C.c_void_p, C.POINTER(Layer), C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
+    "gnb_model_destroy": (C.c_int, [C.c_void_p]),
+    "gnb_model_out_dims": (C.c_int, [C.c_void_p, i32p, i32p, i32p]),
+    "gnb_model_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p] + [C.c_void_p] * 6 + [C.c_int]),
+    "gnb_model_forward_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p] + [C.c_void_p] * 6 + [C.c_int]),
+    "gnb_block_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(BlockParams)] + [C.c_void_p] * 6 + [C.c_int]),
+    "gnb_core_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(CoreParams)] + [C.c_void_p] * 6 + [C.c_int]),
+    "gnb_corelist_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(CoreParams), C.c_int] + [C.c_void_p] * 6
+                             + [C.c_int]),
+}
+
+
+class GnbError(RuntimeError):
+    pass
+
+
+def _load():
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            "libgnb200.so is not built (%s). Run `python graphnets.jl_b200/build.py` "
+            "(or __graft_entry__.build()); there is no CPU fallback." % LIB_PATH)
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)   # AttributeError if a declared symbol is not exported
+        fn.restype = res
+        fn.argtypes = args
+    return lib
+
+
+lib = _load()
+
+
+def check(rc):
+    """Map ABI error codes onto the reference's error behaviour: invalid input is an
+    AssertionError (the reference uses @assert everywhere, src/checks.jl)."""
+    if rc == GNB_OK:
+        return
+    msg = (lib.gnb_last_error() or b"").decode()
+    if rc == GNB_ERR_INVALID:
+        raise AssertionError(msg)
+    if rc == GNB_ERR_OOM:
+        raise MemoryError(msg)
+    raise GnbError("gnb200 error %d: %s" % (rc, msg))

@@ -1,0 +1,88 @@
+// Internal structures shared by the gnb200 translation units (not part of the ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+#include <string.h>
+#include <vector>
+#include <string>
+#include "../../include/gnb200.h"
+
+void gnb_set_error(const char* fmt, ...);
+
+#define GNB_CUDA(call)                                                                   \
+  do {                                                                                   \
+    cudaError_t _e = (call);                                                             \
+    if (_e != cudaSuccess) {                                                             \
+      gnb_set_error("CUDA error %s at %s:%d (%s)", cudaGetErrorString(_e), __FILE__,     \
+                    __LINE__, #call);                                                    \
+      return (_e == cudaErrorMemoryAllocation) ? GNB_ERR_OOM : GNB_ERR_CUDA;             \
+    }                                                                                    \
+  } while (0)
+
+#define GNB_CHECK(cond, ...)                                                             \
+  do {                                                                                   \
+    if (!(cond)) {                                                                       \
+      gnb_set_error(__VA_ARGS__);                                                        \
+      return GNB_ERR_INVALID;                                                            \
+    }                                                                                    \
+  } while (0)
+
+#define GNB_TRY(expr)                                                                    \
+  do {                                                                                   \
+    int _r = (expr);                                                                     \
+    if (_r != GNB_OK) return _r;                                                         \
+  } while (0)
+
+// Scratch arena: bump allocation out of cudaMalloc'd chunks, reset at the start of every
+// forward.  Chunks persist across calls so steady-state forwards do no cudaMalloc.
+struct Arena {
+  struct Chunk { char* base; size_t cap; size_t used; };
+  std::vector<Chunk> chunks;
+  size_t min_chunk = (size_t)64 << 20;
+  int alloc(size_t bytes, void** out);
+  void reset();
+  void release();
+};
+
+struct gnb_ctx {
+  int device = 0;
+  int sm_count = 148;
+  cudaStream_t stream = nullptr;
+  Arena arena;
+  int64_t launches = 0;
+  // host-variant staging (device side), grown on demand
+  Arena staging;
+};
+
+struct gnb_graph {
+  int device = 0;
+  int32_t B = 0, PN = 0;
+  int64_t E = 0, N = 0;
+  // device arrays
+  int32_t* edge_src = nullptr;    // [E] global compact node id of the sender (row i)
+  int32_t* edge_dst = nullptr;    // [E] global compact node id of the receiver (column j)
+  int32_t* edge_slot = nullptr;   // [E] padded slot i + PN*j within the graph
+  int32_t* edge_graph = nullptr;  // [E]
+  int32_t* node_graph = nullptr;  // [N]
+  int32_t* graph_edge_ptr = nullptr;  // [B+1]
+  int32_t* graph_node_ptr = nullptr;  // [B+1]
+  int32_t* node_in_ptr = nullptr;     // [N+1] CSR over receivers (edges are receiver-sorted)
+  // tensor-core path: 128-edge tiles; per tile, per distinct receiver one partial row.
+  // node v sums partial rows [node_part_ptr[v], node_part_ptr[v+1])  (deterministic, no atomics)
+  int32_t* edge_part = nullptr;       // [E]   partial-row id of each edge
+  int32_t* node_part_ptr = nullptr;   // [N+1]
+  int64_t n_parts = 0;
+  void* all = nullptr;  // single allocation backing everything above
+};
+
+template <typename T>
+static inline T* arena_ptr(Arena& a, size_t n, int* rc) {
+  void* p = nullptr;
+  int r = a.alloc(n * sizeof(T), &p);
+  if (r != GNB_OK) *rc = r;
+  return (T*)p;
+}
+
+static inline int ceil_div(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }

@@ -1,0 +1,271 @@
+// fp32 CUDA-core path: fused linear layer + deterministic segmented sums.
+//
+// One kernel template covers every Dense of the reference forward:
+//   out = act( sum_s LN_s(x_s) W_s + bias + sum_j add_j[idx_j] )
+// The reference builds [e | v_src | v_dst | u] with dense batched_mul gathers and a
+// materialised vcat (src/edgefninput.jl:1-8) and then applies one Dense (src/gnblock.jl:65).
+// Dense is linear, so W [e;v_s;v_r;u] = W_e e + (W_s v)[src] + (W_r v)[dst] + (W_u u)[graph]:
+// nodes / graphs are projected once (N, B << E rows) and the gather becomes an indexed ADD in
+// the epilogue of the per-edge GEMM - the concat never exists.  LayerNorm (src/gngraphnorm.jl)
+// is applied on the fly while the A tile is staged in shared memory.
+#include "kernels.cuh"
+
+namespace {
+
+constexpr int TK = 32;
+
+__device__ __forceinline__ float ln_rstd(float var, float eps, int mode) {
+  if (mode == GNB_EPS_SQRT_VAR_EPS2) return 1.0f / sqrtf(var + eps * eps);
+  if (mode == GNB_EPS_STD_PLUS_EPS) return 1.0f / (sqrtf(var) + eps);
+  return 1.0f / sqrtf(var + eps);
+}
+
+// Thread tile: QM x QN quads of 4x4; quads are strided by TM/QM rows and TN/QN columns so
+// every shared-memory read is a conflict-free LDS.128.
+template <int TM, int TN, int QM, int QN>
+__global__ void __launch_bounds__((TM / (4 * QM)) * (TN / (4 * QN)))
+k_linear(const LinArgs a) {
+  constexpr int TXN = TN / (4 * QN);
+  constexpr int TYN = TM / (4 * QM);
+  constexpr int NT = TXN * TYN;
+  constexpr int LDA = TM + 4;
+  constexpr int LDB = TN + 4;
+  __shared__ __align__(16) float As[TK * LDA];
+  __shared__ __align__(16) float Ws[TK * LDB];
+  __shared__ float s_mu[3][TM];
+  __shared__ float s_rs[3][TM];
+
+  const int tid = threadIdx.x;
+  const int tx = tid % TXN, ty = tid / TXN;
+  const int64_t row0 = (int64_t)blockIdx.x * TM;
+  const int col0 = blockIdx.y * TN;
+  const int lane = tid & 31, warp = tid >> 5;
+  constexpr int NW = NT / 32;
+
+  // ---- LayerNorm statistics of this CTA's rows (two-pass, fp32) -------------------------
+  for (int s = 0; s < a.nsrc; s++) {
+    const LinSrc& S = a.src[s];
+    if (S.gamma == nullptr || S.d == 0) continue;
+    for (int r = warp; r < TM; r += NW) {
+      int64_t row = row0 + r;
+      float mu = 0.f, rs = 0.f;
+      if (row < a.R) {
+        const float* xr = S.x + (size_t)row * S.ldx;
+        float sum = 0.f;
+        for (int k = lane; k < S.d; k += 32) sum += xr[k];
+        for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        mu = sum / (float)S.d;
+        float sq = 0.f;
+        for (int k = lane; k < S.d; k += 32) {
+          float t = xr[k] - mu;
+          sq += t * t;
+        }
+        for (int o = 16; o; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+        rs = ln_rstd(sq / (float)S.d, S.eps, S.eps_mode);
+      }
+      if (lane == 0) {
+        s_mu[s][r] = mu;
+        s_rs[s][r] = rs;
+      }
+    }
+  }
+  __syncthreads();
+
+  float acc[QM * 4][QN * 4];
+#pragma unroll
+  for (int i = 0; i < QM * 4; i++)
+#pragma unroll
+    for (int j = 0; j < QN * 4; j++) acc[i][j] = 0.f;
+
+  for (int s = 0; s < a.nsrc; s++) {
+    const LinSrc& S = a.src[s];
+    const bool has_ln = S.gamma != nullptr;
+    const bool xvec = ((S.ldx & 3) == 0) && ((((uintptr_t)S.x) & 15) == 0);
+    const bool wvec = ((a.ldw & 3) == 0) && ((((uintptr_t)S.W) & 15) == 0) && ((col0 & 3) == 0);
+    for (int k0 = 0; k0 < S.d; k0 += TK) {
+      // A tile: TM rows x TK k, stored transposed As[k][r]
+      for (int idx = tid; idx < TM * (TK / 4); idx += NT) {
+        int r = idx / (TK / 4);
+        int k = k0 + (idx % (TK / 4)) * 4;
+        int64_t row = row0 + r;
+        float v[4] = {0.f, 0.f, 0.f, 0.f};
+        if (row < a.R && k < S.d) {
+          const float* p = S.x + (size_t)row * S.ldx + k;
+          if (xvec && k + 3 < S.d) {
+            float4 t = *reinterpret_cast<const float4*>(p);
+            v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+          } else {
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+              if (k + i < S.d) v[i] = p[i];
+          }
+          if (has_ln) {
+            float mu = s_mu[s][r], rs = s_rs[s][r];
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+              if (k + i < S.d) v[i] = (v[i] - mu) * rs * S.gamma[k + i] + S.beta[k + i];
+          }
+        }
+        int kk = k - k0;
+#pragma unroll
+        for (int i = 0; i < 4; i++) As[(kk + i) * LDA + r] = v[i];
+      }
+      // W tile: TK k x TN n
+      for (int idx = tid; idx < TK * (TN / 4); idx += NT) {
+        int kk = idx / (TN / 4);
+        int n = (idx % (TN / 4)) * 4;
+        int k = k0 + kk;
+        float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (k < S.d) {
+          const float* p = S.W + (size_t)k * a.ldw + col0 + n;
+          if (wvec && col0 + n + 3 < a.Nout) {
+            t = *reinterpret_cast<const float4*>(p);
+          } else {
+            if (col0 + n + 0 < a.Nout) t.x = p[0];
+            if (col0 + n + 1 < a.Nout) t.y = p[1];
+            if (col0 + n + 2 < a.Nout) t.z = p[2];
+            if (col0 + n + 3 < a.Nout) t.w = p[3];
+          }
+        }
+        *reinterpret_cast<float4*>(&Ws[kk * LDB + n]) = t;
+      }
+      __syncthreads();
+#pragma unroll 8
+      for (int kk = 0; kk < TK; kk++) {
+        float av[QM * 4], bv[QN * 4];
+#pragma unroll
+        for (int q = 0; q < QM; q++) {
+          float4 t = *reinterpret_cast<const float4*>(&As[kk * LDA + q * (TM / QM) + ty * 4]);
+          av[q * 4 + 0] = t.x; av[q * 4 + 1] = t.y; av[q * 4 + 2] = t.z; av[q * 4 + 3] = t.w;
+        }
+#pragma unroll
+        for (int q = 0; q < QN; q++) {
+          float4 t = *reinterpret_cast<const float4*>(&Ws[kk * LDB + q * (TN / QN) + tx * 4]);
+          bv[q * 4 + 0] = t.x; bv[q * 4 + 1] = t.y; bv[q * 4 + 2] = t.z; bv[q * 4 + 3] = t.w;
+        }
+#pragma unroll
+        for (int i = 0; i < QM * 4; i++)
+#pragma unroll
+          for (int j = 0; j < QN * 4; j++) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+      }
+      __syncthreads();
+    }
+  }
+
+  // ---- epilogue: bias + gathered addends + activation + store ---------------------------
+  const bool ovec = ((a.ldo & 3) == 0) && ((((uintptr_t)a.out) & 15) == 0);
+#pragma unroll
+  for (int qi = 0; qi < QM; qi++) {
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      int r = qi * (TM / QM) + ty * 4 + i;
+      int64_t row = row0 + r;
+      if (row >= a.R) continue;
+      const float* addrow[4];
+      for (int j = 0; j < a.nadd; j++) {
+        int64_t ar = a.add[j].idx ? (int64_t)a.add[j].idx[row] : row;
+        addrow[j] = a.add[j].a + (size_t)ar * a.add[j].lda;
+      }
+#pragma unroll
+      for (int qj = 0; qj < QN; qj++) {
+        int n = col0 + qj * (TN / QN) + tx * 4;
+        if (n >= a.Nout) continue;
+        float v[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) v[j] = acc[qi * 4 + i][qj * 4 + j];
+        const bool full = n + 3 < a.Nout;
+        if (a.bias) {
+#pragma unroll
+          for (int j = 0; j < 4; j++)
+            if (n + j < a.Nout) v[j] += a.bias[n + j];
+        }
+        for (int t = 0; t < a.nadd; t++) {
+          const float* p = addrow[t] + n;
+          if (full && ((a.add[t].lda & 3) == 0) && ((((uintptr_t)a.add[t].a) & 15) == 0)) {
+            float4 q = *reinterpret_cast<const float4*>(p);
+            v[0] += q.x; v[1] += q.y; v[2] += q.z; v[3] += q.w;
+          } else {
+#pragma unroll
+            for (int j = 0; j < 4; j++)
+              if (n + j < a.Nout) v[j] += p[j];
+          }
+        }
+        if (a.relu) {
+#pragma unroll
+          for (int j = 0; j < 4; j++) v[j] = fmaxf(v[j], 0.f);
+        }
+        float* o = a.out + (size_t)row * a.ldo + n;
+        if (full && ovec) {
+          *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 4; j++)
+            if (n + j < a.Nout) o[j] = v[j];
+        }
+      }
+    }
+  }
+}
+
+// One warp per segment, lanes over feature columns, rows in ascending order.
+__global__ void k_segsum(const float* __restrict__ x, int D, const int32_t* __restrict__ ptr, int64_t S,
+                         float* __restrict__ out) {
+  int64_t seg = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  int lane = threadIdx.x & 31;
+  if (seg >= S) return;
+  int64_t r0 = ptr[seg], r1 = ptr[seg + 1];
+  if (((D & 3) == 0) && ((((uintptr_t)x) & 15) == 0) && ((((uintptr_t)out) & 15) == 0)) {
+    int D4 = D >> 2;
+    for (int c = lane; c < D4; c += 32) {
+      float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+      const float4* p = reinterpret_cast<const float4*>(x) + c;
+      int64_t r = r0;
+      for (; r + 3 < r1; r += 4) {
+        float4 t0 = p[(size_t)r * D4], t1 = p[(size_t)(r + 1) * D4];
+        float4 t2 = p[(size_t)(r + 2) * D4], t3 = p[(size_t)(r + 3) * D4];
+        s.x += t0.x; s.y += t0.y; s.z += t0.z; s.w += t0.w;
+        s.x += t1.x; s.y += t1.y; s.z += t1.z; s.w += t1.w;
+        s.x += t2.x; s.y += t2.y; s.z += t2.z; s.w += t2.w;
+        s.x += t3.x; s.y += t3.y; s.z += t3.z; s.w += t3.w;
+      }
+      for (; r < r1; r++) {
+        float4 t = p[(size_t)r * D4];
+        s.x += t.x; s.y += t.y; s.z += t.z; s.w += t.w;
+      }
+      reinterpret_cast<float4*>(out)[(size_t)seg * D4 + c] = s;
+    }
+  } else {
+    for (int c = lane; c < D; c += 32) {
+      float s = 0.f;
+      for (int64_t r = r0; r < r1; r++) s += x[(size_t)r * D + c];
+      out[(size_t)seg * D + c] = s;
+    }
+  }
+}
+
+}  // namespace
+
+int launch_linear_fp32(gnb_ctx* ctx, const LinArgs& a) {
+  if (a.R <= 0 || a.Nout <= 0) return GNB_OK;
+  if (a.Nout > 64) {
+    dim3 grid((unsigned)ceil_div(a.R, 128), (unsigned)ceil_div(a.Nout, 128));
+    k_linear<128, 128, 2, 2><<<grid, 256, 0, ctx->stream>>>(a);
+  } else if (a.Nout > 16) {
+    dim3 grid((unsigned)ceil_div(a.R, 64), (unsigned)ceil_div(a.Nout, 64));
+    k_linear<64, 64, 1, 1><<<grid, 256, 0, ctx->stream>>>(a);
+  } else {
+    dim3 grid((unsigned)ceil_div(a.R, 256), (unsigned)ceil_div(a.Nout, 16));
+    k_linear<256, 16, 1, 1><<<grid, 256, 0, ctx->stream>>>(a);
+  }
+  ctx->launches++;
+  GNB_CUDA(cudaGetLastError());
+  return GNB_OK;
+}
+
+int launch_segsum(gnb_ctx* ctx, const float* x, int D, const int32_t* ptr, int64_t S, float* out) {
+  if (S <= 0 || D <= 0) return GNB_OK;
+  k_segsum<<<ceil_div(S * 32, 256), 256, 0, ctx->stream>>>(x, D, ptr, S, out);
+  ctx->launches++;
+  GNB_CUDA(cudaGetLastError());
+  return GNB_OK;
+}

@@ -1,0 +1,48 @@
+// Launch interfaces of the compute kernels (internal).
+#pragma once
+#include "common.cuh"
+
+// One direct (un-gathered) row source of a fused linear layer:
+//   contribution[r][n] = sum_k  LN?(x[r][:])[k] * W[k][n]
+// W is a k-major sub-block of a Flux Dense.weight ((out,in) column-major == [in][out]),
+// i.e. rows [koff, koff+d) of the full matrix: W = Wfull + koff*ldw.
+struct LinSrc {
+  const float* x;      // [R][ldx]
+  int d;               // width of this source (number of k rows)
+  int ldx;
+  const float* W;      // [d][ldw]
+  const float* gamma;  // LayerNorm affine, nullptr = no LayerNorm on this source
+  const float* beta;
+  float eps;
+  int eps_mode;
+};
+
+// Row-gathered addend of the epilogue: out[r][:] += a[idx ? idx[r] : r][:]
+struct LinAdd {
+  const float* a;
+  const int32_t* idx;
+  int lda;
+};
+
+struct LinArgs {
+  int64_t R;      // rows
+  int Nout;       // output width
+  int ldw;        // leading dim of every W block (= out dim of the Dense layer)
+  int nsrc;
+  LinSrc src[3];
+  const float* bias;  // [Nout] or nullptr
+  int nadd;
+  LinAdd add[4];
+  int relu;
+  float* out;     // [R][ldo]
+  int ldo;
+};
+
+// out = act( sum_s LN_s(x_s) W_s + bias + sum_j add_j[idx_j] )     fp32 CUDA cores
+int launch_linear_fp32(gnb_ctx* ctx, const LinArgs& a);
+
+// out[s][:] = sum_{r in [ptr[s], ptr[s+1])} x[r][:]  in ascending r (deterministic)
+int launch_segsum(gnb_ctx* ctx, const float* x, int D, const int32_t* ptr, int64_t S, float* out);
+
+// ---- tensor-core (tcgen05) path, tc.cu ---------------------------------------------
+struct TcWeights;  // packed bf16 weights of one core (tc.cu)

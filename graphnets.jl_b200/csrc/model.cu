@@ -1,0 +1,564 @@
+// Context, model (weights) and forward orchestration of the GNBlock / GNCore path.
+// Reference: src/gnblock.jl:63-69, src/gncore.jl:56-68, src/gncorelist.jl:43-45,
+// src/gnfeedforward.jl:27-40, src/gngraphnorm.jl:19-26.
+#include "kernels.cuh"
+#include "tc.cuh"
+
+// ------------------------------------------------------------------ errors / arena / ctx
+static thread_local char g_err[1024] = "";
+
+void gnb_set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+extern "C" const char* gnb_last_error(void) { return g_err; }
+extern "C" int gnb_version(void) { return 100; }
+
+int Arena::alloc(size_t bytes, void** out) {
+  bytes = (bytes + 255) / 256 * 256;
+  if (bytes == 0) bytes = 256;
+  for (auto& c : chunks) {
+    // only the most recent chunks with space are tried in order; chunks are never interleaved
+    if (c.cap - c.used >= bytes) {
+      *out = c.base + c.used;
+      c.used += bytes;
+      return GNB_OK;
+    }
+  }
+  size_t cap = bytes > min_chunk ? bytes : min_chunk;
+  void* p = nullptr;
+  cudaError_t e = cudaMalloc(&p, cap);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    gnb_set_error("workspace cudaMalloc(%zu bytes) failed: %s", cap, cudaGetErrorString(e));
+    return GNB_ERR_OOM;
+  }
+  chunks.push_back({(char*)p, cap, bytes});
+  *out = p;
+  return GNB_OK;
+}
+void Arena::reset() {
+  // Coalesce: if the previous use spilled over several chunks, replace them by one big chunk so
+  // that steady-state forwards bump-allocate out of a single region.
+  if (chunks.size() > 1) {
+    size_t total = 0;
+    for (auto& c : chunks) total += c.cap;
+    void* p = nullptr;
+    for (auto& c : chunks) cudaFree(c.base);
+    chunks.clear();
+    if (cudaMalloc(&p, total) == cudaSuccess) chunks.push_back({(char*)p, total, 0});
+    else cudaGetLastError();
+  }
+  for (auto& c : chunks) c.used = 0;
+}
+void Arena::release() {
+  for (auto& c : chunks) cudaFree(c.base);
+  chunks.clear();
+}
+
+extern "C" gnb_ctx* gnb_ctx_create(int device, int* err) {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || device < 0 || device >= n) {
+    gnb_set_error("gnb_ctx_create: no CUDA device %d (%s)", device,
+                  e != cudaSuccess ? cudaGetErrorString(e) : "index out of range");
+    if (err) *err = GNB_ERR_CUDA;
+    return nullptr;
+  }
+  cudaSetDevice(device);
+  gnb_ctx* c = new gnb_ctx();
+  c->device = device;
+  cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device);
+  if (err) *err = GNB_OK;
+  return c;
+}
+extern "C" int gnb_ctx_destroy(gnb_ctx* c) {
+  if (!c) return GNB_OK;
+  cudaSetDevice(c->device);
+  c->arena.release();
+  c->staging.release();
+  delete c;
+  return GNB_OK;
+}
+extern "C" int gnb_ctx_set_stream(gnb_ctx* c, void* s) {
+  GNB_CHECK(c, "gnb_ctx_set_stream: null ctx");
+  c->stream = (cudaStream_t)s;
+  return GNB_OK;
+}
+extern "C" int gnb_sync(gnb_ctx* c) {
+  GNB_CHECK(c, "gnb_sync: null ctx");
+  GNB_CUDA(cudaSetDevice(c->device));
+  GNB_CUDA(cudaStreamSynchronize(c->stream));
+  return GNB_OK;
+}
+extern "C" int64_t gnb_ctx_launch_count(const gnb_ctx* c) { return c ? c->launches : 0; }
+
+// ------------------------------------------------------------------ model
+struct LayerW {
+  int kind;
+  gnb_block_params blk;
+  gnb_ffn_params ffn[3];
+  gnb_ln_params ln1[3], ln2[3];
+  TcCorePack* tc = nullptr;  // packed bf16 weights (cores the tensor path supports)
+};
+
+struct gnb_model {
+  int device = 0;
+  std::vector<LayerW> layers;
+  float* wbuf = nullptr;  // owned device copy of every weight (nullptr: weights by reference)
+  int in_dims[3] = {0, 0, 0};
+  int out_dims[3] = {0, 0, 0};
+};
+
+static int check_block(const gnb_block_params& b, int li) {
+  GNB_CHECK(b.in_e >= 0 && b.in_n >= 0 && b.in_g >= 0 && b.out_e >= 0 && b.out_n >= 0 && b.out_g >= 0,
+            "layer %d: negative dimension", li);
+  GNB_CHECK(b.in_e > 0 || b.in_n > 0 || b.in_g > 0, "layer %d: GNBlock needs any(in .> 0) (src/gnblock.jl:48)", li);
+  GNB_CHECK(b.out_e > 0 || b.out_n > 0 || b.out_g > 0, "layer %d: GNBlock needs any(out .> 0) (src/gnblock.jl:49)", li);
+  int ke = b.in_e + 2 * b.in_n + b.in_g, kn = b.out_e + b.in_n + b.in_g, kg = b.out_e + b.out_n + b.in_g;
+  GNB_CHECK(b.out_e == 0 || (b.be && (ke == 0 || b.We)), "layer %d: edgefn weights missing", li);
+  GNB_CHECK(b.out_n == 0 || (b.bn && (kn == 0 || b.Wn)), "layer %d: nodefn weights missing", li);
+  GNB_CHECK(b.out_g == 0 || (b.bg && (kg == 0 || b.Wg)), "layer %d: graphfn weights missing", li);
+  return GNB_OK;
+}
+
+static int build_model(gnb_ctx* ctx, const gnb_layer* layers, int n_layers, int mode /*0 host copy,1 dev copy,2 by reference*/,
+                       gnb_model** out) {
+  GNB_CHECK(ctx && layers && out && n_layers > 0, "gnb_model_create: bad argument");
+  GNB_CUDA(cudaSetDevice(ctx->device));
+  gnb_model* m = new gnb_model();
+  m->device = ctx->device;
+  int cur[3] = {-1, -1, -1};
+  size_t total = 0;
+  auto cnt = [&](size_t n) { total += (n + 63) / 64 * 64; };
+  int rc = GNB_OK;
+  for (int li = 0; li < n_layers && rc == GNB_OK; li++) {
+    const gnb_layer& L = layers[li];
+    LayerW w;
+    w.kind = L.kind;
+    if (L.kind == GNB_LAYER_BLOCK) {
+      w.blk = L.block;
+    } else if (L.kind == GNB_LAYER_CORE) {
+      w.blk = L.core.block;
+      for (int i = 0; i < 3; i++) { w.ffn[i] = L.core.ffn[i]; w.ln1[i] = L.core.ln1[i]; w.ln2[i] = L.core.ln2[i]; }
+    } else {
+      gnb_set_error("layer %d: unknown kind %d", li, L.kind);
+      rc = GNB_ERR_INVALID;
+      break;
+    }
+    if ((rc = check_block(w.blk, li)) != GNB_OK) break;
+    const gnb_block_params& b = w.blk;
+    if (L.kind == GNB_LAYER_CORE) {
+      // GNFeedForward / GNGraphNorm assert all(dims .> 0) (src/gnfeedforward.jl:18, src/gngraphnorm.jl:10)
+      if (!(b.in_e > 0 && b.in_n > 0 && b.in_g > 0 && b.in_e == b.out_e && b.in_n == b.out_n && b.in_g == b.out_g)) {
+        gnb_set_error("layer %d: GNCore needs all(dims .> 0) and in == out", li);
+        rc = GNB_ERR_INVALID;
+        break;
+      }
+      for (int i = 0; i < 3; i++) {
+        if (!(w.ffn[i].W1 && w.ffn[i].b1 && w.ffn[i].W2 && w.ffn[i].b2 && w.ln1[i].gamma && w.ln1[i].beta &&
+              w.ln2[i].gamma && w.ln2[i].beta)) {
+          gnb_set_error("layer %d: GNCore parameter pointer missing (kind %d)", li, i);
+          rc = GNB_ERR_INVALID;
+          break;
+        }
+      }
+      if (rc != GNB_OK) break;
+    }
+    if (cur[0] >= 0 && (cur[0] != b.in_e || cur[1] != b.in_n || cur[2] != b.in_g)) {
+      gnb_set_error("layer %d: input dims (%d,%d,%d) do not match previous output (%d,%d,%d)", li, b.in_e, b.in_n,
+                    b.in_g, cur[0], cur[1], cur[2]);
+      rc = GNB_ERR_INVALID;
+      break;
+    }
+    if (li == 0) { m->in_dims[0] = b.in_e; m->in_dims[1] = b.in_n; m->in_dims[2] = b.in_g; }
+    cur[0] = b.out_e; cur[1] = b.out_n; cur[2] = b.out_g;
+    m->layers.push_back(w);
+  }
+  if (rc != GNB_OK) { delete m; return rc; }
+  m->out_dims[0] = cur[0]; m->out_dims[1] = cur[1]; m->out_dims[2] = cur[2];
+
+  if (mode != 2) {
+    // size pass
+    for (auto& w : m->layers) {
+      const gnb_block_params& b = w.blk;
+      cnt((size_t)b.out_e * (b.in_e + 2 * b.in_n + b.in_g)); cnt(b.out_e);
+      cnt((size_t)b.out_n * (b.out_e + b.in_n + b.in_g)); cnt(b.out_n);
+      cnt((size_t)b.out_g * (b.out_e + b.out_n + b.in_g)); cnt(b.out_g);
+      if (w.kind == GNB_LAYER_CORE) {
+        int d[3] = {b.in_e, b.in_n, b.in_g};
+        for (int i = 0; i < 3; i++) { cnt((size_t)4 * d[i] * d[i]); cnt(4 * d[i]); cnt((size_t)4 * d[i] * d[i]); cnt(d[i]); cnt(d[i]); cnt(d[i]); cnt(d[i]); cnt(d[i]); }
+      }
+    }
+    cudaError_t e = cudaMalloc((void**)&m->wbuf, (total ? total : 64) * sizeof(float));
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      delete m;
+      gnb_set_error("gnb_model_create: cudaMalloc failed: %s", cudaGetErrorString(e));
+      return GNB_ERR_OOM;
+    }
+    size_t off = 0;
+    cudaError_t ce = cudaSuccess;
+    auto put = [&](const float*& p, size_t n) {
+      if (n == 0 || p == nullptr) { p = nullptr; return; }
+      float* dst = m->wbuf + off;
+      off += (n + 63) / 64 * 64;
+      cudaError_t r = cudaMemcpyAsync(dst, p, n * sizeof(float), mode == 0 ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice, ctx->stream);
+      if (r != cudaSuccess && ce == cudaSuccess) ce = r;
+      p = dst;
+    };
+    for (auto& w : m->layers) {
+      gnb_block_params& b = w.blk;
+      put(b.We, (size_t)b.out_e * (b.in_e + 2 * b.in_n + b.in_g)); put(b.be, b.out_e);
+      put(b.Wn, (size_t)b.out_n * (b.out_e + b.in_n + b.in_g)); put(b.bn, b.out_n);
+      put(b.Wg, (size_t)b.out_g * (b.out_e + b.out_n + b.in_g)); put(b.bg, b.out_g);
+      if (w.kind == GNB_LAYER_CORE) {
+        int d[3] = {b.in_e, b.in_n, b.in_g};
+        for (int i = 0; i < 3; i++) {
+          put(w.ffn[i].W1, (size_t)4 * d[i] * d[i]); put(w.ffn[i].b1, 4 * d[i]);
+          put(w.ffn[i].W2, (size_t)4 * d[i] * d[i]); put(w.ffn[i].b2, d[i]);
+          put(w.ln1[i].gamma, d[i]); put(w.ln1[i].beta, d[i]);
+          put(w.ln2[i].gamma, d[i]); put(w.ln2[i].beta, d[i]);
+        }
+      }
+    }
+    if (ce == cudaSuccess) ce = cudaStreamSynchronize(ctx->stream);
+    if (ce != cudaSuccess) {
+      gnb_set_error("gnb_model_create: weight upload failed: %s", cudaGetErrorString(ce));
+      cudaFree(m->wbuf);
+      delete m;
+      return GNB_ERR_CUDA;
+    }
+    // tensor-core packs for the cores the tcgen05 path supports
+    for (auto& w : m->layers) {
+      if (w.kind == GNB_LAYER_CORE && tc_core_supported(w.blk.in_e, w.blk.in_n, w.blk.in_g)) {
+        int r = tc_core_pack(ctx, w.blk, w.ffn, w.ln1, w.ln2, &w.tc);
+        if (r != GNB_OK) {
+          gnb_model_destroy(m);
+          return r;
+        }
+      }
+    }
+  }
+  *out = m;
+  return GNB_OK;
+}
+
+extern "C" int gnb_model_create(gnb_ctx* ctx, const gnb_layer* layers, int n_layers, int weights_on_device, gnb_model** out) {
+  return build_model(ctx, layers, n_layers, weights_on_device ? 1 : 0, out);
+}
+extern "C" int gnb_model_destroy(gnb_model* m) {
+  if (!m) return GNB_OK;
+  cudaSetDevice(m->device);
+  for (auto& w : m->layers)
+    if (w.tc) tc_core_pack_free(w.tc);
+  if (m->wbuf) cudaFree(m->wbuf);
+  delete m;
+  return GNB_OK;
+}
+extern "C" int gnb_model_out_dims(const gnb_model* m, int32_t* e, int32_t* n, int32_t* g) {
+  GNB_CHECK(m, "gnb_model_out_dims: null model");
+  if (e) *e = m->out_dims[0];
+  if (n) *n = m->out_dims[1];
+  if (g) *g = m->out_dims[2];
+  return GNB_OK;
+}
+
+// ------------------------------------------------------------------ fp32 forward
+namespace {
+
+struct Feat { const float* e; const float* n; const float* g; };
+struct FeatOut { float* e; float* n; float* g; };
+
+LinSrc mk_src(const float* x, int d, const float* W, const gnb_ln_params* ln) {
+  LinSrc s;
+  s.x = x; s.d = d; s.ldx = d; s.W = W;
+  s.gamma = ln ? ln->gamma : nullptr;
+  s.beta = ln ? ln->beta : nullptr;
+  s.eps = ln ? ln->eps : 0.f;
+  s.eps_mode = ln ? ln->eps_mode : 0;
+  return s;
+}
+
+// GNBlock forward (optionally with LayerNorm `ln[3]` applied to the inputs = block(gn1(x))).
+// Writes h_e [E][p], h_v [N][q], h_u [B][r].
+int run_block_fp32(gnb_ctx* ctx, const gnb_graph* g, const gnb_block_params& b, const gnb_ln_params* ln,
+                   Feat x, FeatOut h) {
+  const int a = b.in_e, bn_ = b.in_n, c = b.in_g, p = b.out_e, q = b.out_n, r = b.out_g;
+  const int64_t E = g->E, N = g->N, B = g->B;
+  const gnb_ln_params* lne = ln ? &ln[0] : nullptr;
+  const gnb_ln_params* lnn = ln ? &ln[1] : nullptr;
+  const gnb_ln_params* lng = ln ? &ln[2] : nullptr;
+  int rc = GNB_OK;
+  float* agg = nullptr;
+  if (p > 0) {
+    float *Ps = nullptr, *Pr = nullptr, *Pu = nullptr;
+    if (bn_ > 0) {
+      Ps = arena_ptr<float>(ctx->arena, (size_t)N * p, &rc);
+      Pr = arena_ptr<float>(ctx->arena, (size_t)N * p, &rc);
+      if (rc != GNB_OK) return rc;
+      LinArgs la{};
+      la.R = N; la.Nout = p; la.ldw = p; la.nsrc = 1; la.ldo = p;
+      la.src[0] = mk_src(x.n, bn_, b.We + (size_t)a * p, lnn);
+      la.out = Ps;
+      GNB_TRY(launch_linear_fp32(ctx, la));
+      la.src[0] = mk_src(x.n, bn_, b.We + (size_t)(a + bn_) * p, lnn);
+      la.out = Pr;
+      GNB_TRY(launch_linear_fp32(ctx, la));
+    }
+    if (c > 0) {
+      Pu = arena_ptr<float>(ctx->arena, (size_t)B * p, &rc);
+      if (rc != GNB_OK) return rc;
+      LinArgs la{};
+      la.R = B; la.Nout = p; la.ldw = p; la.nsrc = 1; la.ldo = p;
+      la.src[0] = mk_src(x.g, c, b.We + (size_t)(a + 2 * bn_) * p, lng);
+      la.bias = b.be;
+      la.out = Pu;
+      GNB_TRY(launch_linear_fp32(ctx, la));
+    }
+    LinArgs la{};
+    la.R = E; la.Nout = p; la.ldw = p; la.ldo = p; la.out = h.e;
+    if (a > 0) { la.nsrc = 1; la.src[0] = mk_src(x.e, a, b.We, lne); }
+    if (Ps) {
+      la.add[la.nadd++] = LinAdd{Ps, g->edge_src, p};
+      la.add[la.nadd++] = LinAdd{Pr, g->edge_dst, p};
+    }
+    if (Pu) la.add[la.nadd++] = LinAdd{Pu, g->edge_graph, p};
+    else la.bias = b.be;
+    GNB_TRY(launch_linear_fp32(ctx, la));
+    // edge -> node aggregation over the receiver CSR (src/nodefninput.jl:3)
+    if (q > 0 || r > 0) {
+      agg = arena_ptr<float>(ctx->arena, (size_t)N * p, &rc);
+      if (rc != GNB_OK) return rc;
+      GNB_TRY(launch_segsum(ctx, h.e, p, g->node_in_ptr, N, agg));
+    }
+  }
+  if (q > 0) {
+    float* Pu = nullptr;
+    if (c > 0) {
+      Pu = arena_ptr<float>(ctx->arena, (size_t)B * q, &rc);
+      if (rc != GNB_OK) return rc;
+      LinArgs la{};
+      la.R = B; la.Nout = q; la.ldw = q; la.nsrc = 1; la.ldo = q;
+      la.src[0] = mk_src(x.g, c, b.Wn + (size_t)(p + bn_) * q, lng);
+      la.bias = b.bn;
+      la.out = Pu;
+      GNB_TRY(launch_linear_fp32(ctx, la));
+    }
+    LinArgs la{};
+    la.R = N; la.Nout = q; la.ldw = q; la.ldo = q; la.out = h.n;
+    if (p > 0) la.src[la.nsrc++] = mk_src(agg, p, b.Wn, nullptr);
+    if (bn_ > 0) la.src[la.nsrc++] = mk_src(x.n, bn_, b.Wn + (size_t)p * q, lnn);
+    if (Pu) la.add[la.nadd++] = LinAdd{Pu, g->node_graph, q};
+    else la.bias = b.bn;
+    GNB_TRY(launch_linear_fp32(ctx, la));
+  }
+  if (r > 0) {
+    float *se = nullptr, *sv = nullptr;
+    if (p > 0) {
+      // sum of a graph's edges == sum of its nodes' incoming-edge aggregates (src/graphfninput.jl:3)
+      se = arena_ptr<float>(ctx->arena, (size_t)B * p, &rc);
+      if (rc != GNB_OK) return rc;
+      GNB_TRY(launch_segsum(ctx, agg, p, g->graph_node_ptr, B, se));
+    }
+    if (q > 0) {
+      sv = arena_ptr<float>(ctx->arena, (size_t)B * q, &rc);
+      if (rc != GNB_OK) return rc;
+      GNB_TRY(launch_segsum(ctx, h.n, q, g->graph_node_ptr, B, sv));
+    }
+    LinArgs la{};
+    la.R = B; la.Nout = r; la.ldw = r; la.ldo = r; la.out = h.g; la.bias = b.bg;
+    if (p > 0) la.src[la.nsrc++] = mk_src(se, p, b.Wg, nullptr);
+    if (q > 0) la.src[la.nsrc++] = mk_src(sv, q, b.Wg + (size_t)p * r, nullptr);
+    if (c > 0) la.src[la.nsrc++] = mk_src(x.g, c, b.Wg + (size_t)(p + q) * r, lng);
+    GNB_TRY(launch_linear_fp32(ctx, la));
+  }
+  return GNB_OK;
+}
+
+// y = (x + h) + W2 relu(W1 LN2(x) + b1) + b2       (src/gncore.jl:56-68, src/gnfeedforward.jl:27-31)
+int run_ffn_residual_fp32(gnb_ctx* ctx, int64_t R, int d, const gnb_ffn_params& f, const gnb_ln_params& ln2,
+                          const float* x, const float* h, float* y) {
+  if (R <= 0) return GNB_OK;
+  const size_t cap_bytes = (size_t)1 << 30;  // hidden scratch per chunk
+  int64_t chunk = (int64_t)(cap_bytes / ((size_t)4 * d * sizeof(float)));
+  if (chunk < 1024) chunk = 1024;
+  if (chunk > R) chunk = R;
+  int rc = GNB_OK;
+  float* hid = arena_ptr<float>(ctx->arena, (size_t)chunk * 4 * d, &rc);
+  if (rc != GNB_OK) return rc;
+  for (int64_t r0 = 0; r0 < R; r0 += chunk) {
+    int64_t rows = R - r0 < chunk ? R - r0 : chunk;
+    LinArgs l1{};
+    l1.R = rows; l1.Nout = 4 * d; l1.ldw = 4 * d; l1.nsrc = 1; l1.ldo = 4 * d;
+    l1.src[0] = mk_src(x + (size_t)r0 * d, d, f.W1, &ln2);
+    l1.bias = f.b1; l1.relu = 1; l1.out = hid;
+    GNB_TRY(launch_linear_fp32(ctx, l1));
+    LinArgs l2{};
+    l2.R = rows; l2.Nout = d; l2.ldw = d; l2.nsrc = 1; l2.ldo = d;
+    l2.src[0] = mk_src(hid, 4 * d, f.W2, nullptr);
+    l2.bias = f.b2;
+    l2.add[l2.nadd++] = LinAdd{x + (size_t)r0 * d, nullptr, d};
+    l2.add[l2.nadd++] = LinAdd{h + (size_t)r0 * d, nullptr, d};
+    l2.out = y + (size_t)r0 * d;
+    GNB_TRY(launch_linear_fp32(ctx, l2));
+  }
+  return GNB_OK;
+}
+
+int run_core_fp32(gnb_ctx* ctx, const gnb_graph* g, const LayerW& w, Feat x, FeatOut y) {
+  const int d[3] = {w.blk.in_e, w.blk.in_n, w.blk.in_g};
+  int rc = GNB_OK;
+  FeatOut h;
+  h.e = arena_ptr<float>(ctx->arena, (size_t)g->E * d[0], &rc);
+  h.n = arena_ptr<float>(ctx->arena, (size_t)g->N * d[1], &rc);
+  h.g = arena_ptr<float>(ctx->arena, (size_t)g->B * d[2], &rc);
+  if (rc != GNB_OK) return rc;
+  GNB_TRY(run_block_fp32(ctx, g, w.blk, w.ln1, x, h));
+  GNB_TRY(run_ffn_residual_fp32(ctx, g->E, d[0], w.ffn[0], w.ln2[0], x.e, h.e, y.e));
+  GNB_TRY(run_ffn_residual_fp32(ctx, g->N, d[1], w.ffn[1], w.ln2[1], x.n, h.n, y.n));
+  GNB_TRY(run_ffn_residual_fp32(ctx, g->B, d[2], w.ffn[2], w.ln2[2], x.g, h.g, y.g));
+  return GNB_OK;
+}
+
+struct ArenaMark { size_t nchunks; std::vector<size_t> used; };
+ArenaMark arena_mark(Arena& a) {
+  ArenaMark m;
+  m.nchunks = a.chunks.size();
+  for (auto& c : a.chunks) m.used.push_back(c.used);
+  return m;
+}
+void arena_rewind(Arena& a, const ArenaMark& m) {
+  for (size_t i = 0; i < a.chunks.size(); i++) a.chunks[i].used = i < m.nchunks ? m.used[i] : 0;
+}
+
+int forward_device(gnb_ctx* ctx, const gnb_model* m, const gnb_graph* g, const float* ef, const float* nf,
+                   const float* gf, float* out_ef, float* out_nf, float* out_gf, int precision, bool reset_arena) {
+  GNB_CHECK(ctx && m && g, "gnb_model_forward: null argument");
+  GNB_CHECK(ctx->device == m->device && ctx->device == g->device, "gnb_model_forward: ctx/model/graph on different devices");
+  GNB_CHECK(precision == GNB_PREC_FP32 || precision == GNB_PREC_BF16 || precision == GNB_PREC_AUTO,
+            "gnb_model_forward: unknown precision %d", precision);
+  GNB_CHECK(m->in_dims[0] == 0 || g->E == 0 || ef, "gnb_model_forward: ef is NULL but the model expects in_e=%d", m->in_dims[0]);
+  GNB_CHECK(m->in_dims[1] == 0 || g->N == 0 || nf, "gnb_model_forward: nf is NULL but the model expects in_n=%d", m->in_dims[1]);
+  GNB_CHECK(m->in_dims[2] == 0 || gf, "gnb_model_forward: gf is NULL but the model expects in_g=%d", m->in_dims[2]);
+  GNB_CHECK(m->out_dims[0] == 0 || g->E == 0 || out_ef, "gnb_model_forward: out_ef is NULL");
+  GNB_CHECK(m->out_dims[1] == 0 || g->N == 0 || out_nf, "gnb_model_forward: out_nf is NULL");
+  GNB_CHECK(m->out_dims[2] == 0 || out_gf, "gnb_model_forward: out_gf is NULL");
+  GNB_CUDA(cudaSetDevice(ctx->device));
+  if (reset_arena) ctx->arena.reset();
+  const int L = (int)m->layers.size();
+  // ping-pong activation buffers sized for the widest intermediate layer output
+  size_t me = 0, mn = 0, mg = 0;
+  for (int i = 0; i + 1 < L; i++) {
+    const gnb_block_params& b = m->layers[i].blk;
+    if ((size_t)b.out_e > me) me = b.out_e;
+    if ((size_t)b.out_n > mn) mn = b.out_n;
+    if ((size_t)b.out_g > mg) mg = b.out_g;
+  }
+  int rc = GNB_OK;
+  FeatOut pp[2] = {{nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr}};
+  int nbuf = L > 2 ? 2 : (L > 1 ? 1 : 0);
+  for (int i = 0; i < nbuf; i++) {
+    pp[i].e = arena_ptr<float>(ctx->arena, (size_t)g->E * me, &rc);
+    pp[i].n = arena_ptr<float>(ctx->arena, (size_t)g->N * mn, &rc);
+    pp[i].g = arena_ptr<float>(ctx->arena, (size_t)g->B * mg, &rc);
+  }
+  if (rc != GNB_OK) return rc;
+  Feat x{ef, nf, gf};
+  ArenaMark mark = arena_mark(ctx->arena);
+  for (int li = 0; li < L; li++) {
+    const LayerW& w = m->layers[li];
+    FeatOut y = (li == L - 1) ? FeatOut{out_ef, out_nf, out_gf} : pp[li & 1];
+    if (w.blk.in_e == 0) x.e = nullptr;
+    if (w.blk.in_n == 0) x.n = nullptr;
+    if (w.blk.in_g == 0) x.g = nullptr;
+    arena_rewind(ctx->arena, mark);
+    if (w.kind == GNB_LAYER_BLOCK) {
+      GNB_TRY(run_block_fp32(ctx, g, w.blk, nullptr, x, y));
+    } else {
+      bool use_tc = (precision != GNB_PREC_FP32) && w.tc != nullptr;
+      if (precision == GNB_PREC_BF16 && !w.tc) {
+        gnb_set_error("layer %d: GNCore dims (%d,%d,%d) are not supported by the tcgen05 bf16 path "
+                      "(use GNB_PREC_AUTO or GNB_PREC_FP32)", li, w.blk.in_e, w.blk.in_n, w.blk.in_g);
+        return GNB_ERR_UNSUPPORTED;
+      }
+      if (use_tc) GNB_TRY(tc_core_forward(ctx, g, w.tc, w.blk, w.ffn, w.ln1, w.ln2, x.e, x.n, x.g, y.e, y.n, y.g));
+      else GNB_TRY(run_core_fp32(ctx, g, w, x, y));
+    }
+    x = Feat{y.e, y.n, y.g};
+  }
+  return GNB_OK;
+}
+
+}  // namespace
+
+extern "C" int gnb_model_forward(gnb_ctx* ctx, const gnb_model* m, const gnb_graph* g, const float* ef,
+                                 const float* nf, const float* gf, float* out_ef, float* out_nf, float* out_gf,
+                                 int precision) {
+  return forward_device(ctx, m, g, ef, nf, gf, out_ef, out_nf, out_gf, precision, true);
+}
+
+extern "C" int gnb_model_forward_host(gnb_ctx* ctx, const gnb_model* m, const gnb_graph* g, const float* ef,
+                                      const float* nf, const float* gf, float* out_ef, float* out_nf,
+                                      float* out_gf, int precision) {
+  GNB_CHECK(ctx && m && g, "gnb_model_forward_host: null argument");
+  GNB_CUDA(cudaSetDevice(ctx->device));
+  ctx->staging.reset();
+  int rc = GNB_OK;
+  const size_t ie = (size_t)g->E * m->in_dims[0], in = (size_t)g->N * m->in_dims[1], ig = (size_t)g->B * m->in_dims[2];
+  const size_t oe = (size_t)g->E * m->out_dims[0], on = (size_t)g->N * m->out_dims[1], og = (size_t)g->B * m->out_dims[2];
+  float* d_ie = ie && ef ? arena_ptr<float>(ctx->staging, ie, &rc) : nullptr;
+  float* d_in = in && nf ? arena_ptr<float>(ctx->staging, in, &rc) : nullptr;
+  float* d_ig = ig && gf ? arena_ptr<float>(ctx->staging, ig, &rc) : nullptr;
+  float* d_oe = oe ? arena_ptr<float>(ctx->staging, oe, &rc) : nullptr;
+  float* d_on = on ? arena_ptr<float>(ctx->staging, on, &rc) : nullptr;
+  float* d_og = og ? arena_ptr<float>(ctx->staging, og, &rc) : nullptr;
+  if (rc != GNB_OK) return rc;
+  if (d_ie) GNB_CUDA(cudaMemcpyAsync(d_ie, ef, ie * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+  if (d_in) GNB_CUDA(cudaMemcpyAsync(d_in, nf, in * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+  if (d_ig) GNB_CUDA(cudaMemcpyAsync(d_ig, gf, ig * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+  GNB_TRY(forward_device(ctx, m, g, d_ie, d_in, d_ig, d_oe, d_on, d_og, precision, true));
+  if (d_oe && out_ef) GNB_CUDA(cudaMemcpyAsync(out_ef, d_oe, oe * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+  if (d_on && out_nf) GNB_CUDA(cudaMemcpyAsync(out_nf, d_on, on * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+  if (d_og && out_gf) GNB_CUDA(cudaMemcpyAsync(out_gf, d_og, og * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+  GNB_CUDA(cudaStreamSynchronize(ctx->stream));
+  return GNB_OK;
+}
+
+static int forward_by_reference(gnb_ctx* ctx, const gnb_graph* g, const gnb_layer* layers, int n, const float* ef,
+                                const float* nf, const float* gf, float* oe, float* on, float* og, int precision) {
+  GNB_CHECK(precision == GNB_PREC_FP32 || precision == GNB_PREC_AUTO,
+            "single-layer forward runs the fp32 path on caller-owned weights; create a gnb_model for the bf16 tensor path");
+  gnb_model* m = nullptr;
+  GNB_TRY(build_model(ctx, layers, n, 2, &m));
+  int r = forward_device(ctx, m, g, ef, nf, gf, oe, on, og, GNB_PREC_FP32, true);
+  gnb_model_destroy(m);
+  return r;
+}
+
+extern "C" int gnb_block_forward(gnb_ctx* ctx, const gnb_graph* g, const gnb_block_params* p, const float* ef,
+                                 const float* nf, const float* gf, float* oe, float* on, float* og, int precision) {
+  GNB_CHECK(p, "gnb_block_forward: null params");
+  gnb_layer L{};
+  L.kind = GNB_LAYER_BLOCK;
+  L.block = *p;
+  return forward_by_reference(ctx, g, &L, 1, ef, nf, gf, oe, on, og, precision);
+}
+extern "C" int gnb_core_forward(gnb_ctx* ctx, const gnb_graph* g, const gnb_core_params* p, const float* ef,
+                                const float* nf, const float* gf, float* oe, float* on, float* og, int precision) {
+  return gnb_corelist_forward(ctx, g, p, 1, ef, nf, gf, oe, on, og, precision);
+}
+extern "C" int gnb_corelist_forward(gnb_ctx* ctx, const gnb_graph* g, const gnb_core_params* cores, int n_cores,
+                                    const float* ef, const float* nf, const float* gf, float* oe, float* on,
+                                    float* og, int precision) {
+  GNB_CHECK(cores && n_cores > 0, "gnb_corelist_forward: no cores");
+  std::vector<gnb_layer> L(n_cores);
+  for (int i = 0; i < n_cores; i++) {
+    memset(&L[i], 0, sizeof(gnb_layer));
+    L[i].kind = GNB_LAYER_CORE;
+    L[i].core = cores[i];
+  }
+  return forward_by_reference(ctx, g, L.data(), n_cores, ef, nf, gf, oe, on, og, precision);
+}

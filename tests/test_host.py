@@ -1,0 +1,101 @@
+"""CPU-side tests: the C-ABI library loads and exports every symbol include/gnb200.h declares,
+the host mirror raises the reference's AssertionErrors (src/checks.jl), sharding logic."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ADJ = np.array([[1, 0, 1], [1, 1, 0], [0, 0, 1]])
+
+
+def _header_symbols():
+    src = open(os.path.join(ROOT, "include", "gnb200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(gnb_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol(gn):
+    names = _header_symbols()
+    assert len(names) >= 24
+    lib = ctypes.CDLL(gn.LIB_PATH)
+    for n in names:
+        assert hasattr(lib, n), "libgnb200.so does not export %s" % n
+    # and the ctypes binding covers the same set
+    assert set(names) == set(gn.pkg._lib.SIGNATURES.keys())
+    assert lib.gnb_version() >= 100
+
+
+def test_struct_layout_matches_header(gn):
+    L = gn.pkg._lib
+    assert ctypes.sizeof(L.BlockParams) == 6 * 4 + 6 * 8
+    assert ctypes.sizeof(L.FfnParams) == 32 and ctypes.sizeof(L.LnParams) == 24
+    assert ctypes.sizeof(L.CoreParams) == 72 + 3 * 32 + 6 * 24
+    assert ctypes.sizeof(L.Layer) == 8 + 72 + ctypes.sizeof(L.CoreParams)
+
+
+def test_no_cpu_fallback_without_device(gn):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    x = dict(graphs=ADJ, ef=np.zeros((10, 5, 2), np.float32), nf=np.zeros((5, 3, 2), np.float32), gf=None)
+    with pytest.raises(gn.pkg.GnbError):
+        gn.batch(x)
+
+
+def test_checks_assertions(gn):
+    f = lambda *s: np.zeros(s, np.float32)
+    bad = [
+        dict(graphs=ADJ, ef=f(10, 4, 2), nf=f(5, 3, 2), gf=None),          # wrong edge count
+        dict(graphs=ADJ, ef=f(10, 5, 2), nf=f(5, 4, 2), gf=None),          # wrong node count
+        dict(graphs=ADJ, ef=f(10, 5, 2), nf=f(5, 3, 3), gf=None),          # batch sizes differ
+        dict(graphs=ADJ, ef=f(10, 5), nf=f(5, 3, 2), gf=None),             # ef not 3-D
+        dict(graphs=ADJ, ef=f(10, 5, 2), nf=f(5, 3, 2), gf=f(4, 2, 1)),    # gf not 2-D
+        dict(graphs=ADJ, ef=None, nf=None, gf=None),                       # nothing at all
+        dict(graphs=[ADJ, ADJ], ef=[f(10, 5)], nf=[f(5, 3), f(5, 3)], gf=None),   # list lengths
+        dict(graphs=[ADJ], ef=[f(10, 5, 1)], nf=[f(5, 3)], gf=None),       # ef[i] not 2-D
+        dict(graphs=[ADJ], ef=[f(10, 5)], nf=[f(5, 3)], gf=[f(4, 1)]),     # gf[i] not 1-D
+        dict(graphs=[], ef=[], nf=[], gf=None),
+    ]
+    for x in bad:
+        with pytest.raises(AssertionError):
+            gn.batch(x)
+    with pytest.raises(AssertionError):
+        gn.batch(dict(graphs=ADJ, ef=f(10, 5, 2), nf=f(5, 3, 2)))          # missing key (src/batch.jl:54)
+    with pytest.raises(AssertionError):
+        gn.GNBlock((0, 0, 0), (1, 1, 1))
+    with pytest.raises(AssertionError):
+        gn.GNBlock((1, 1, 1), (0, 0, 0))
+    with pytest.raises(AssertionError):
+        gn.GNCore((3, 0, 5))        # GNFeedForward: all(dims .> 0) (src/gnfeedforward.jl:18)
+
+
+def test_layer_fields_and_shapes(gn):
+    b = gn.GNBlock((10, 5, 0), (3, 4, 5))
+    assert b.edgefn[0].weight.shape == (3, 20) and b.nodefn[0].weight.shape == (4, 8)
+    assert b.graphfn[0].weight.shape == (5, 7) and b.dropout.p == 0
+    assert (b.edgefn[0].bias == 0).all()
+    lim = np.sqrt(6 / 23)
+    assert np.abs(b.edgefn[0].weight).max() <= lim
+    c = gn.GNCore((3, 4, 5))
+    assert c.block.edgefn[0].weight.shape == (3, 3 + 8 + 5)
+    assert c.ffwd.eff[0].weight.shape == (12, 3) and c.ffwd.eff[1].weight.shape == (3, 12)
+    assert c.gn1.nodeln.scale.shape == (4,) and c.gn2.graphln.eps == pytest.approx(1e-5)
+    cl = gn.GNCoreList([c, gn.GNCore((3, 4, 5))])
+    assert len(cl.list) == 2
+
+
+def test_shard_ranges(gn):
+    r = gn.shard_ranges([512] * 4096, 8)
+    assert r == [(i * 512, (i + 1) * 512) for i in range(8)]
+    rng = np.random.default_rng(0)
+    m = rng.integers(64, 4097, size=1000)
+    for ws in (1, 2, 3, 4, 8):
+        r = gn.shard_ranges(m, ws)
+        assert r[0][0] == 0 and r[-1][1] == 1000 and all(r[i][1] == r[i + 1][0] for i in range(ws - 1))
+        tot = [m[a:b].sum() for a, b in r]
+        assert max(tot) - min(tot) <= 2 * m.max()
+    assert gn.shard_ranges([], 2) == [(0, 0), (0, 0)]
+    assert gn.shard_ranges([0, 0, 0, 0], 2) == [(0, 2), (2, 4)]
