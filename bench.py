@@ -1,0 +1,324 @@
+#!/usr/bin/env python
+"""bench.py - GNCore-model forward throughput (edges/s, graphs/s) on 1..8 B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config cfg4]
+                    [--precision auto|fp32|bf16] [--graphs B]
+
+A "step" is one forward of the whole model (encoder GNBlock -> n x GNCore -> decoder GNBlock,
+BASELINE.json config 4 by default: hidden 128, 4 cores, 4096 random graphs of 64 nodes / 512 edges)
+over one batch of synthetic inputs that are already resident in HBM (`value`), and the same call
+through the host-buffer C-ABI entry points with the H2D / D2H copies and the batch lowering inside
+the timed region (`e2e`).  N > 1: one process per GPU under torchrun, every rank owns its own
+contiguous shard of the graph batch (4096 graphs per GPU: weak scaling), no data-path collective;
+time = max over ranks.  Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+import workloads as W  # noqa: E402
+
+METRIC = "edges/sec, GNCore-model forward (graphs/sec alongside)"
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=d["hbm_gbs"], bf16=d["bf16_tflops"], bf16_sustained=d.get("bf16_tflops_sustained", d["bf16_tflops"]),
+                    src="measured")
+    return dict(hbm=6650.0, bf16=1590.0, bf16_sustained=1400.0, src="fallback")
+
+
+class ClockSampler:
+    """Samples SM clock / throttle reasons of one GPU during the timed region (NVML)."""
+
+    def __init__(self, index):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._t = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _loop(self):
+        nv = self.nv
+        names = {"hw_slowdown": getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8),
+                 "hw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+                 "sw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
+                 "sw_power_cap": getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4),
+                 "hw_power_brake": getattr(nv, "nvmlClocksEventReasonHwPowerBrakeSlowdown", 0x80)}
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, bit in names.items():
+                    if mask & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            time.sleep(0.02)
+
+    def start(self):
+        if self.nv is not None:
+            self._t = threading.Thread(target=self._loop, daemon=True)
+            self._t.start()
+
+    def stop(self):
+        self._stop.set()
+        if self._t is not None:
+            self._t.join(1.0)
+        med = float(np.median(self.samples)) if self.samples else None
+        return dict(sm_mhz=med, sm_max_mhz=self.max_mhz, reasons=sorted(self.reasons), samples=len(self.samples))
+
+
+def synth(name, B, seed):
+    """Compact synthetic inputs of a vector-mode config (cfg4 / cfg5 shape), no per-graph Python."""
+    cfg = W.CONFIGS[name]
+    rng = np.random.default_rng(seed)
+    n, m = 64, 512
+    adj = W.random_cells_adj(rng, B, n, m)
+    ef = rng.random((B * m, cfg["enc"][0]), dtype=np.float32)
+    nf = rng.random((B * n, cfg["enc"][1]), dtype=np.float32)
+    return adj, ef, nf
+
+
+# ------------------------------------------------------------------------------------ reference
+def cpu_reference_time(name, Bs, steps, warmup, seed=123):
+    """Times the reference formulation (dense broadcasters, padded slots) on the host cores."""
+    import torch
+    from oracle import gn_oracle as O, ref_cpu as R
+    torch.set_num_threads(os.cpu_count())
+    layers = R.to_torch_params(W.model_params(name))
+    adj, ef, nf = synth(name, Bs, seed)
+    adjs = [adj[b] for b in range(Bs)]
+    g = O.lower(adjs)
+    d = R.TorchDenseBatch(adjs)
+    efp, nfp, gfp = R.pad_inputs(adjs, ef, nf, None, g)
+    times = []
+    with torch.no_grad():
+        for i in range(warmup + steps):
+            t0 = time.perf_counter()
+            R.forward(layers, d, efp, nfp, gfp)
+            t1 = time.perf_counter()
+            if i >= warmup:
+                times.append(t1 - t0)
+    return float(np.mean(times)), g["E"], Bs, torch.get_num_threads()
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    Bs = args.ref_graphs
+    t, E, B, threads = cpu_reference_time(args.config, Bs, args.steps, args.warmup)
+    val = E / t
+    sample = "%d graphs of the %s workload per step (reference formulation holds (4H,PN^2,B) in memory; scaled linearly, graphs are independent)" % (Bs, args.config)
+    out = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": "edges/s", "graphs_per_sec": B / t,
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(args), "sample_graphs": Bs},
+        "cpu_baseline": {"value": val, "unit": "edges/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": "edges/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(out))
+
+
+def workload_name(args):
+    c = W.CONFIGS[args.config]
+    return "%s: enc%s -> %dx GNCore%s -> dec%s, %d random graphs/GPU of 64 nodes / 512 edges" % (
+        args.config, c["enc"], c["cores"], c["hidden"], c["dec"], args.graphs)
+
+
+# ------------------------------------------------------------------------------------ ours
+def run_ours(args, rank, world, local_rank):
+    import ctypes as C
+    import torch
+    import torch.distributed as dist
+    import graphnets_b200 as gn
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    peaks = load_peaks()
+    B = args.graphs
+    adj, ef, nf = synth(args.config, B, 1000 + rank)
+    layers = W.model_params(args.config)
+    model = W.to_gn_model(gn, layers)
+    x = gn.batch_compact(adj, ef, nf, device=local_rank)
+    g = x.graphs
+    eng = g.engine
+    E, N = g.E, g.N
+    in_bytes = (ef.nbytes + nf.nbytes)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident throughput (`value`) -----------------------------------------------
+    y = None
+    for _ in range(args.warmup):
+        y = model(x, precision=args.precision)
+    barrier()
+    launches0 = eng.launches
+    eng.set_profiling(True)
+    eng.read_profile()
+    sampler = ClockSampler(local_rank)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sampler.start()
+    ev0.record()
+    for _ in range(args.steps):
+        y = model(x, precision=args.precision)
+    ev1.record()
+    barrier()
+    clocks = sampler.stop()
+    ms = ev0.elapsed_time(ev1) / args.steps
+    prof = eng.read_profile()
+    eng.set_profiling(False)
+    launches = eng.launches - launches0
+    out_bytes = sum(int(f.compact.numel()) * 4 for f in (y.ef, y.nf, y.gf) if f is not None)
+
+    # ---- end to end through the host-buffer ABI (`e2e`): H2D adjacency + lowering + H2D features
+    #      + forward + D2H outputs, every step, from pinned host memory ---------------------------
+    mask = torch.from_numpy(np.ascontiguousarray((adj == 1).transpose(0, 2, 1)).astype(np.uint8)).pin_memory()
+    h_ef, h_nf = torch.from_numpy(ef).pin_memory(), torch.from_numpy(nf).pin_memory()
+    dout = model._out_dims()
+    h_oe = torch.empty((E, dout[0]), dtype=torch.float32).pin_memory()
+    h_on = torch.empty((N, dout[1]), dtype=torch.float32).pin_memory()
+    h_og = torch.empty((B, dout[2]), dtype=torch.float32).pin_memory()
+    nn = (C.c_int32 * B)(*([64] * B))
+    mh = model._model(eng)
+    prec = gn.pkg._lib.PRECISIONS[args.precision]
+    P = lambda t: C.c_void_p(t.data_ptr())
+
+    def e2e_step():
+        h = C.c_void_p()
+        gn.pkg._lib.check(gn.lib.gnb_graph_lower(eng.ctx, P(mask), 1, 0, nn, 64, B, B, C.byref(h)))
+        gn.pkg._lib.check(gn.lib.gnb_model_forward_host(eng.ctx, mh, h, P(h_ef), P(h_nf), None, P(h_oe), P(h_on),
+                                                       P(h_og), prec))
+        gn.lib.gnb_graph_destroy(h)
+    e2e_steps = max(3, min(args.steps, 10))
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()
+    barrier()
+    e2e_s = (time.perf_counter() - t0) / e2e_steps
+    # the host path must agree with the device path
+    assert torch.equal(h_og, y.gf.compact.cpu()), "host-ABI result differs from the device-resident result"
+
+    # ---- reduce over ranks (max time) ----------------------------------------------------------
+    t = torch.tensor([ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
+    tot = torch.tensor([float(E), float(B), float(launches)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+    ms_max, e2e_ms_max = float(t[0]), float(t[1])
+    E_all, B_all = float(tot[0]), float(tot[1])
+    if rank != 0:
+        return
+
+    # ---- roofline of the dominant kernel ---------------------------------------------------------
+    top = max(prof.items(), key=lambda kv: kv[1]["ms"]) if prof else (None, None)
+    roof = None
+    if top[0] is not None:
+        name, p = top
+        per_ms = p["ms"] / p["launches"]
+        if name.startswith("tc_"):
+            peak = peaks["bf16_sustained"]
+            ach = p["alg_flops"] / p["launches"] / (per_ms * 1e-3) / 1e12
+            roof = {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak}
+        else:
+            peak = peaks["hbm"]
+            ach = p["alg_bytes"] / p["launches"] / (per_ms * 1e-3) / 1e9
+            roof = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak}
+        roof.update({"traffic": None, "kernel": name, "launches_per_step": p["launches"] / args.steps,
+                     "avg_launch_ms": per_ms, "share_of_step": p["ms"] / (ms * args.steps),
+                     "peak_source": "of " + peaks["src"],
+                     "kernel_tflops": p["alg_flops"] / p["launches"] / (per_ms * 1e-3) / 1e12})
+    fl, by = W.canonical_work(layers, E, N, B)
+    model_roof = {"canonical_flops": fl, "canonical_bytes": by,
+                  "hbm_frac": by / (ms * 1e-3) / 1e9 / peaks["hbm"],
+                  "tensor_frac": fl / (ms * 1e-3) / 1e12 / peaks["bf16_sustained"], "peak_source": "of " + peaks["src"]}
+    kern = {k: {"ms_per_step": v["ms"] / args.steps, "launches_per_step": v["launches"] / args.steps}
+            for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])}
+
+    # ---- CPU baseline: reference formulation on the host cores, bounded sample -------------------
+    cpu = None
+    if not args.no_cpu_baseline:
+        tcpu, Ecpu, Bcpu, threads = cpu_reference_time(args.config, args.ref_graphs, 2, 1)
+        cpu = {"value": Ecpu / tcpu, "unit": "edges/s", "cores": threads, "kind": "port",
+               "graphs_per_sec": Bcpu / tcpu,
+               "sample": "%d graphs of the same workload, dense-broadcaster formulation on torch CPU, mean of 2 passes" % Bcpu}
+
+    out = {
+        "metric": METRIC, "value": E_all / (ms_max * 1e-3), "unit": "edges/s",
+        "graphs_per_sec": B_all / (ms_max * 1e-3),
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_max,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16" if (args.precision != "fp32" and any(k.startswith("tc_") for k in prof)) else "f32",
+        "data": "synthetic",
+        "config": {"workload": workload_name(args), "precision": args.precision, "graphs_per_gpu": B,
+                   "edges_per_gpu": E, "nodes_per_gpu": N, "l2": "inputs (%.0f MB/step) exceed the 126 MB L2" % (in_bytes / 1e6),
+                   "parallelism": "graph-sharded x%d, no data-path collective" % world},
+        "e2e": {"value": E_all / (e2e_ms_max * 1e-3), "unit": "edges/s", "ms_per_step": e2e_ms_max,
+                "h2d_bytes_per_step": int(mask.numel() + in_bytes), "d2h_bytes_per_step": int(out_bytes),
+                "includes": "H2D adjacency + GPU lowering + H2D features + forward + D2H outputs (gnb_graph_lower + gnb_model_forward_host)"},
+        "gpu_launches": int(float(tot[2])),
+        "clocks": clocks, "roofline": roof, "model_roofline": model_roof, "kernels": kern, "cpu_baseline": cpu,
+    }
+    print(json.dumps(out))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="cfg4", choices=["cfg4", "cfg5"])
+    ap.add_argument("--precision", default="auto", choices=["auto", "fp32", "bf16"])
+    ap.add_argument("--graphs", type=int, default=4096, help="graphs per GPU")
+    ap.add_argument("--ref-graphs", type=int, default=32, help="graphs per step of the CPU reference sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    try:
+        run_ours(args, rank, world, local_rank)
+    finally:
+        if world > 1:
+            import torch.distributed as dist
+            dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

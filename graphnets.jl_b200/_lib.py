@@ -72,6 +72,15 @@ SIGNATURES = {
 }
 
 
+class ProfEntry(C.Structure):
+    _fields_ = [("name", C.c_char * 48), ("launches", C.c_int64), ("ms", C.c_double),
+                ("alg_bytes", C.c_double), ("alg_flops", C.c_double)]
+
+
+SIGNATURES["gnb_ctx_set_profiling"] = (C.c_int, [C.c_void_p, C.c_int])
+SIGNATURES["gnb_ctx_profile_read"] = (C.c_int, [C.c_void_p, C.POINTER(ProfEntry), C.c_int, C.POINTER(C.c_int)])
+
+
 class GnbError(RuntimeError):
     pass
 

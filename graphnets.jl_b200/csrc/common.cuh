@@ -46,8 +46,15 @@ struct Arena {
   void release();
 };
 
+struct ProfRec { int tag; cudaEvent_t a, b; double bytes, flops; };
+struct ProfTag { const char* name; int64_t launches; double ms, bytes, flops; };
+
 struct gnb_ctx {
   int device = 0;
+  bool profiling = false;
+  std::vector<ProfRec> prof_recs;
+  std::vector<ProfTag> prof_tags;
+  std::vector<cudaEvent_t> ev_pool;
   int sm_count = 148;
   cudaStream_t stream = nullptr;
   Arena arena;
@@ -75,6 +82,14 @@ struct gnb_graph {
   int32_t* node_part_ptr = nullptr;   // [N+1]
   int64_t n_parts = 0;
   void* all = nullptr;  // single allocation backing everything above
+};
+
+// RAII bracket of one kernel launch: counts it and, when profiling, times it with CUDA events.
+struct Launch {
+  gnb_ctx* c;
+  int rec = -1;
+  Launch(gnb_ctx* ctx, const char* name, double alg_bytes = 0, double alg_flops = 0);
+  ~Launch();
 };
 
 template <typename T>

@@ -247,6 +247,15 @@ __global__ void k_segsum(const float* __restrict__ x, int D, const int32_t* __re
 
 int launch_linear_fp32(gnb_ctx* ctx, const LinArgs& a) {
   if (a.R <= 0 || a.Nout <= 0) return GNB_OK;
+  // algorithmic traffic: every source row and gathered addend read once, the output written once,
+  // the weights once; flops = 2 R K Nout
+  double K = 0, bytes = 0;
+  for (int s = 0; s < a.nsrc; s++) K += a.src[s].d;
+  bytes = 4.0 * ((double)a.R * (K + (double)a.Nout * (1 + a.nadd)) + K * a.Nout);
+  for (int j = 0; j < a.nadd; j++)
+    if (a.add[j].idx) bytes += 4.0 * a.R;
+  Launch L(ctx, a.Nout > 64 ? "linear_fp32_128x128" : (a.Nout > 16 ? "linear_fp32_64x64" : "linear_fp32_256x16"), bytes,
+           2.0 * a.R * K * a.Nout);
   if (a.Nout > 64) {
     dim3 grid((unsigned)ceil_div(a.R, 128), (unsigned)ceil_div(a.Nout, 128));
     k_linear<128, 128, 2, 2><<<grid, 256, 0, ctx->stream>>>(a);
@@ -257,15 +266,14 @@ int launch_linear_fp32(gnb_ctx* ctx, const LinArgs& a) {
     dim3 grid((unsigned)ceil_div(a.R, 256), (unsigned)ceil_div(a.Nout, 16));
     k_linear<256, 16, 1, 1><<<grid, 256, 0, ctx->stream>>>(a);
   }
-  ctx->launches++;
   GNB_CUDA(cudaGetLastError());
   return GNB_OK;
 }
 
 int launch_segsum(gnb_ctx* ctx, const float* x, int D, const int32_t* ptr, int64_t S, float* out) {
   if (S <= 0 || D <= 0) return GNB_OK;
+  Launch L(ctx, "segsum_fp32", 0, 0);   // row count is data dependent; bytes accounted by the caller's model
   k_segsum<<<ceil_div(S * 32, 256), 256, 0, ctx->stream>>>(x, D, ptr, S, out);
-  ctx->launches++;
   GNB_CUDA(cudaGetLastError());
   return GNB_OK;
 }

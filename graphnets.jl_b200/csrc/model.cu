@@ -79,6 +79,8 @@ extern "C" int gnb_ctx_destroy(gnb_ctx* c) {
   cudaSetDevice(c->device);
   c->arena.release();
   c->staging.release();
+  for (auto& r : c->prof_recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+  for (auto e : c->ev_pool) cudaEventDestroy(e);
   delete c;
   return GNB_OK;
 }
@@ -94,6 +96,62 @@ extern "C" int gnb_sync(gnb_ctx* c) {
   return GNB_OK;
 }
 extern "C" int64_t gnb_ctx_launch_count(const gnb_ctx* c) { return c ? c->launches : 0; }
+
+Launch::Launch(gnb_ctx* ctx, const char* name, double alg_bytes, double alg_flops) : c(ctx) {
+  c->launches++;
+  if (!c->profiling) return;
+  int tag = -1;
+  for (size_t i = 0; i < c->prof_tags.size(); i++)
+    if (c->prof_tags[i].name == name || strcmp(c->prof_tags[i].name, name) == 0) { tag = (int)i; break; }
+  if (tag < 0) { c->prof_tags.push_back({name, 0, 0, 0, 0}); tag = (int)c->prof_tags.size() - 1; }
+  ProfRec r;
+  r.tag = tag; r.bytes = alg_bytes; r.flops = alg_flops;
+  auto get = [&]() {
+    cudaEvent_t e;
+    if (!c->ev_pool.empty()) { e = c->ev_pool.back(); c->ev_pool.pop_back(); }
+    else cudaEventCreate(&e);
+    return e;
+  };
+  r.a = get(); r.b = get();
+  cudaEventRecord(r.a, c->stream);
+  c->prof_recs.push_back(r);
+  rec = (int)c->prof_recs.size() - 1;
+}
+Launch::~Launch() {
+  if (rec >= 0) cudaEventRecord(c->prof_recs[rec].b, c->stream);
+}
+
+extern "C" int gnb_ctx_set_profiling(gnb_ctx* c, int on) {
+  GNB_CHECK(c, "gnb_ctx_set_profiling: null ctx");
+  c->profiling = on != 0;
+  return GNB_OK;
+}
+extern "C" int gnb_ctx_profile_read(gnb_ctx* c, gnb_prof_entry* out, int cap, int* n) {
+  GNB_CHECK(c && n, "gnb_ctx_profile_read: null argument");
+  GNB_CUDA(cudaSetDevice(c->device));
+  GNB_CUDA(cudaStreamSynchronize(c->stream));
+  for (auto& r : c->prof_recs) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, r.a, r.b);
+    ProfTag& t = c->prof_tags[r.tag];
+    t.launches++; t.ms += ms; t.bytes += r.bytes; t.flops += r.flops;
+    c->ev_pool.push_back(r.a); c->ev_pool.push_back(r.b);
+  }
+  c->prof_recs.clear();
+  int k = 0;
+  for (auto& t : c->prof_tags) {
+    if (t.launches == 0) continue;
+    if (out && k < cap) {
+      memset(&out[k], 0, sizeof(gnb_prof_entry));
+      strncpy(out[k].name, t.name, sizeof(out[k].name) - 1);
+      out[k].launches = t.launches; out[k].ms = t.ms; out[k].alg_bytes = t.bytes; out[k].alg_flops = t.flops;
+    }
+    k++;
+    t.launches = 0; t.ms = t.bytes = t.flops = 0;
+  }
+  *n = k;
+  return GNB_OK;
+}
 
 // ------------------------------------------------------------------ model
 struct LayerW {

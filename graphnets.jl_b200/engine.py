@@ -34,6 +34,17 @@ class Engine:
     def launches(self):
         return int(lib.gnb_ctx_launch_count(self.ctx))
 
+    def set_profiling(self, on):
+        check(lib.gnb_ctx_set_profiling(self.ctx, 1 if on else 0))
+
+    def read_profile(self):
+        """{kernel kind: dict(launches, ms, alg_bytes, alg_flops)} since the last read."""
+        arr = (_lib.ProfEntry * 64)()
+        n = C.c_int(0)
+        check(lib.gnb_ctx_profile_read(self.ctx, arr, 64, C.byref(n)))
+        return {arr[i].name.decode(): dict(launches=arr[i].launches, ms=arr[i].ms, alg_bytes=arr[i].alg_bytes,
+                                           alg_flops=arr[i].alg_flops) for i in range(min(n.value, 64))}
+
     def empty(self, *shape):
         return torch.empty(*shape, dtype=torch.float32, device=self.torch_device)
 

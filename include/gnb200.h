@@ -83,6 +83,12 @@ int         gnb_ctx_set_stream(gnb_ctx*, void* cuda_stream);
 int         gnb_sync(gnb_ctx*);
 /* number of kernels this ctx has launched since creation (bench `gpu_launches`) */
 int64_t     gnb_ctx_launch_count(const gnb_ctx*);
+/* Per-kernel CUDA-event profile (bench.py roofline): when on, every launch is bracketed by events
+ * on the ctx stream; gnb_ctx_profile_read synchronises, returns the totals per kernel kind since the
+ * last read (algorithmic bytes / flops as stated in DESIGN.md) and clears them. */
+typedef struct { char name[48]; int64_t launches; double ms; double alg_bytes; double alg_flops; } gnb_prof_entry;
+int         gnb_ctx_set_profiling(gnb_ctx*, int on);
+int         gnb_ctx_profile_read(gnb_ctx*, gnb_prof_entry* out, int cap, int* n);
 
 /* ---------------------------------------------------------------- lowering ---------- */
 /* Replaces GNGraphBatch(adj_mats) (src/gngraphbatch.jl:33-54) and padadjmats (src/pad.jl:1-10):

@@ -56,16 +56,16 @@ def test_readme_example_1(gn):
 def test_readme_example_2(gn):
     # test/runtests.jl:218-271: graphs of different structure
     block = gn.GNBlock((10, 5, 0), (3, 4, 5))
-    x = gn.batch(dict(graphs=[ADJ, ADJ2], ef=[rand(10, 5), rand(10, 8)], nf=[rand(5, 3), rand(5, 4)], gf=None))
+    x = gn.batch(dict(graphs=[ADJ, ADJ2], ef=[rand(10, 5), rand(10, 9)], nf=[rand(5, 3), rand(5, 4)], gf=None))
     assert x.ef.shape == (10, 16, 2) and x.nf.shape == (5, 4, 2)
     yb = block(x)
     y = gn.unbatch(yb)
     assert gn.efview(yb, ALL, ALL, 0).shape == (3, 5) and gn.nfview(yb, ALL, ALL, 0).shape == (4, 3)
     assert gn.gfview(yb, ALL, 0).shape == (5,)
-    assert gn.efview(yb, ALL, ALL, 1).shape == (3, 8) and gn.nfview(yb, ALL, ALL, 1).shape == (4, 4)
+    assert gn.efview(yb, ALL, ALL, 1).shape == (3, 9) and gn.nfview(yb, ALL, ALL, 1).shape == (4, 4)
     assert gn.gfview(yb, ALL, 1).shape == (5,)
     assert y.ef[0].shape == (3, 5) and y.nf[0].shape == (4, 3) and y.gf[0].shape == (5,)
-    assert y.ef[1].shape == (3, 8) and y.nf[1].shape == (4, 4) and y.gf[1].shape == (5,)
+    assert y.ef[1].shape == (3, 9) and y.nf[1].shape == (4, 4) and y.gf[1].shape == (5,)
     assert yb.gf.shape == (5, 1, 2) and yb.ef.shape == (3, 16, 2)
     # views alias the batched storage (src/views.jl uses @view)
     v = gn.efview(yb, ALL, ALL, 1)
@@ -134,8 +134,8 @@ def test_single_graph_vector_unbatches_in_single_form(gn):
 
 
 def test_flat_unpadded_views(gn):
-    x = gn.batch(dict(graphs=[ADJ, ADJ2], ef=[rand(10, 5), rand(10, 8)], nf=[rand(5, 3), rand(5, 4)], gf=None))
-    assert gn.flatunpaddedef(x).shape == (10, 13) and gn.flatunpaddednf(x).shape == (5, 7)
+    x = gn.batch(dict(graphs=[ADJ, ADJ2], ef=[rand(10, 5), rand(10, 9)], nf=[rand(5, 3), rand(5, 4)], gf=None))
+    assert gn.flatunpaddedef(x).shape == (10, 14) and gn.flatunpaddednf(x).shape == (5, 7)
     # same content as masking the padded tensor with the unpadders (src/views.jl:80-98)
     pe = x.ef.padded().permute(2, 1, 0).reshape(-1, 10).cpu().numpy()
     assert np.array_equal(pe[x.graphs.flat_edge_unpadder], gn.flatunpaddedef(x).t().cpu().numpy())
