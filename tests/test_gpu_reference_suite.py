@@ -88,7 +88,7 @@ def test_readme_example_3(gn):
 
 def test_batch_inverse_2d(gn):
     # test/runtests.jl:328-366
-    efs, nfs = [rand(10, 5), rand(10, 8)], [rand(5, 3), rand(5, 4)]
+    efs, nfs = [rand(10, 5), rand(10, 9)], [rand(5, 3), rand(5, 4)]
     x = dict(graphs=[ADJ, ADJ2], ef=efs, nf=nfs, gf=None)
     xh = gn.unbatch(gn.batch(x))
     assert xh.graphs is not None and all(np.array_equal(a, b) for a, b in zip(xh.graphs, x["graphs"]))
