@@ -80,6 +80,7 @@ struct gnb_graph {
   // node v sums partial rows [node_part_ptr[v], node_part_ptr[v+1])  (deterministic, no atomics)
   int32_t* edge_part = nullptr;       // [E]   partial-row id of each edge
   int32_t* node_part_ptr = nullptr;   // [N+1]
+  int32_t* graph_part_ptr = nullptr;  // [B+1] partial rows of graph b = [graph_part_ptr[b], graph_part_ptr[b+1])
   int64_t n_parts = 0;
   void* all = nullptr;  // single allocation backing everything above
 };

@@ -44,5 +44,11 @@ int launch_linear_fp32(gnb_ctx* ctx, const LinArgs& a);
 // out[s][:] = sum_{r in [ptr[s], ptr[s+1])} x[r][:]  in ascending r (deterministic)
 int launch_segsum(gnb_ctx* ctx, const float* x, int D, const int32_t* ptr, int64_t S, float* out);
 
-// ---- tensor-core (tcgen05) path, tc.cu ---------------------------------------------
-struct TcWeights;  // packed bf16 weights of one core (tc.cu)
+
+
+
+// shared between model.cu (fp32 orchestration) and tc.cu (graph-level pieces of the tensor path)
+LinSrc mk_src(const float* x, int d, const float* W, const gnb_ln_params* ln);
+// y = (x + h) + W2 relu(W1 LN2(x) + b1) + b2   on the fp32 CUDA-core path
+int run_ffn_residual_fp32(gnb_ctx* ctx, int64_t R, int d, const gnb_ffn_params& f, const gnb_ln_params& ln2,
+                          const float* x, const float* h, float* y);

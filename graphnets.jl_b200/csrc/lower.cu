@@ -168,6 +168,12 @@ __global__ void k_node_part_ptr(const int32_t* __restrict__ node_in_ptr, const i
   if (v <= N) node_part_ptr[v] = excl[node_in_ptr[v]];
 }
 
+__global__ void k_graph_part_ptr(const int32_t* __restrict__ gnp, const int32_t* __restrict__ npp, int B,
+                                 int32_t* __restrict__ out) {
+  int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b <= B) out[b] = npp[gnp[b]];
+}
+
 // ---- pad / unpad / collapse ---------------------------------------------------------
 __global__ void k_pad_edges(const float* __restrict__ src, const int32_t* __restrict__ edge_slot,
                             const int32_t* __restrict__ edge_graph, int64_t E, int D, int64_t PE,
@@ -310,6 +316,7 @@ extern "C" int gnb_graph_lower(gnb_ctx* ctx, const void* adj, int adj_dtype, int
   auto take = [&](size_t n) { size_t o = off; off += align_up(n * sizeof(int32_t)); return o; };
   size_t o_src = take(E), o_dst = take(E), o_slot = take(E), o_eg = take(E), o_ng = take(N);
   size_t o_gep = take(B + 1), o_gnp = take(B + 1), o_nip = take(N + 1), o_ep = take(E), o_npp = take(N + 1);
+  size_t o_gpp = take(B + 1);
   cudaError_t ce = cudaMalloc(&g->all, off ? off : 256);
   if (ce != cudaSuccess) {
     delete g;
@@ -322,6 +329,7 @@ extern "C" int gnb_graph_lower(gnb_ctx* ctx, const void* adj, int adj_dtype, int
   g->node_graph = (int32_t*)(base + o_ng); g->graph_edge_ptr = (int32_t*)(base + o_gep);
   g->graph_node_ptr = (int32_t*)(base + o_gnp); g->node_in_ptr = (int32_t*)(base + o_nip);
   g->edge_part = (int32_t*)(base + o_ep); g->node_part_ptr = (int32_t*)(base + o_npp);
+  g->graph_part_ptr = (int32_t*)(base + o_gpp);
   int ret = GNB_OK;
   do {
     if (cudaMemcpyAsync(g->graph_node_ptr, gnp.data(), sizeof(int32_t) * (B + 1), cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) { ret = GNB_ERR_CUDA; break; }
@@ -352,6 +360,8 @@ extern "C" int gnb_graph_lower(gnb_ctx* ctx, const void* adj, int adj_dtype, int
     } else {
       cudaMemsetAsync(g->node_part_ptr, 0, sizeof(int32_t) * (N + 1), ctx->stream);
     }
+    k_graph_part_ptr<<<ceil_div(B + 1, 256), 256, 0, ctx->stream>>>(g->graph_node_ptr, g->node_part_ptr, B, g->graph_part_ptr);
+    ctx->launches++;
     cudaError_t e2 = cudaStreamSynchronize(ctx->stream);
     if (e2 == cudaSuccess) e2 = cudaGetLastError();
     if (e2 != cudaSuccess) { gnb_set_error("gnb_graph_lower: %s", cudaGetErrorString(e2)); ret = GNB_ERR_CUDA; }

@@ -325,7 +325,7 @@ extern "C" int gnb_model_out_dims(const gnb_model* m, int32_t* e, int32_t* n, in
 }
 
 // ------------------------------------------------------------------ fp32 forward
-namespace {
+// (internal linkage via static where not shared with tc.cu)
 
 struct Feat { const float* e; const float* n; const float* g; };
 struct FeatOut { float* e; float* n; float* g; };
@@ -342,7 +342,7 @@ LinSrc mk_src(const float* x, int d, const float* W, const gnb_ln_params* ln) {
 
 // GNBlock forward (optionally with LayerNorm `ln[3]` applied to the inputs = block(gn1(x))).
 // Writes h_e [E][p], h_v [N][q], h_u [B][r].
-int run_block_fp32(gnb_ctx* ctx, const gnb_graph* g, const gnb_block_params& b, const gnb_ln_params* ln,
+static int run_block_fp32(gnb_ctx* ctx, const gnb_graph* g, const gnb_block_params& b, const gnb_ln_params* ln,
                    Feat x, FeatOut h) {
   const int a = b.in_e, bn_ = b.in_n, c = b.in_g, p = b.out_e, q = b.out_n, r = b.out_g;
   const int64_t E = g->E, N = g->N, B = g->B;
@@ -466,7 +466,7 @@ int run_ffn_residual_fp32(gnb_ctx* ctx, int64_t R, int d, const gnb_ffn_params& 
   return GNB_OK;
 }
 
-int run_core_fp32(gnb_ctx* ctx, const gnb_graph* g, const LayerW& w, Feat x, FeatOut y) {
+static int run_core_fp32(gnb_ctx* ctx, const gnb_graph* g, const LayerW& w, Feat x, FeatOut y) {
   const int d[3] = {w.blk.in_e, w.blk.in_n, w.blk.in_g};
   int rc = GNB_OK;
   FeatOut h;
@@ -482,17 +482,17 @@ int run_core_fp32(gnb_ctx* ctx, const gnb_graph* g, const LayerW& w, Feat x, Fea
 }
 
 struct ArenaMark { size_t nchunks; std::vector<size_t> used; };
-ArenaMark arena_mark(Arena& a) {
+static ArenaMark arena_mark(Arena& a) {
   ArenaMark m;
   m.nchunks = a.chunks.size();
   for (auto& c : a.chunks) m.used.push_back(c.used);
   return m;
 }
-void arena_rewind(Arena& a, const ArenaMark& m) {
+static void arena_rewind(Arena& a, const ArenaMark& m) {
   for (size_t i = 0; i < a.chunks.size(); i++) a.chunks[i].used = i < m.nchunks ? m.used[i] : 0;
 }
 
-int forward_device(gnb_ctx* ctx, const gnb_model* m, const gnb_graph* g, const float* ef, const float* nf,
+static int forward_device(gnb_ctx* ctx, const gnb_model* m, const gnb_graph* g, const float* ef, const float* nf,
                    const float* gf, float* out_ef, float* out_nf, float* out_gf, int precision, bool reset_arena) {
   GNB_CHECK(ctx && m && g, "gnb_model_forward: null argument");
   GNB_CHECK(ctx->device == m->device && ctx->device == g->device, "gnb_model_forward: ctx/model/graph on different devices");
@@ -550,7 +550,7 @@ int forward_device(gnb_ctx* ctx, const gnb_model* m, const gnb_graph* g, const f
   return GNB_OK;
 }
 
-}  // namespace
+
 
 extern "C" int gnb_model_forward(gnb_ctx* ctx, const gnb_model* m, const gnb_graph* g, const float* ef,
                                  const float* nf, const float* gf, float* out_ef, float* out_nf, float* out_gf,
