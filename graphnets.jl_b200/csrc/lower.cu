@@ -347,7 +347,7 @@ extern "C" int gnb_graph_lower(gnb_ctx* ctx, const void* adj, int adj_dtype, int
       int32_t* sums2 = arena_ptr<int32_t>(ctx->arena, ceil_div(E, SCAN_ITEMS) + 2, &rc2);
       if (rc2 != GNB_OK) { ret = rc2; break; }
       int eb = ceil_div(E, 256);
-      k_part_flags<<<eb, 256, 0, ctx->stream>>>(g->edge_dst, E, 128, flag);
+      k_part_flags<<<eb, 256, 0, ctx->stream>>>(g->edge_dst, E, 32, flag);
       ctx->launches++;
       if ((ret = exclusive_scan(ctx, flag, E, excl, 1, sums2)) != GNB_OK) break;
       k_part_finish<<<eb, 256, 0, ctx->stream>>>(flag, excl, E, g->edge_part);

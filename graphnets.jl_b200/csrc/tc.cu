@@ -29,11 +29,11 @@ constexpr int TM = 128;            // rows per tile (UMMA M)
 constexpr int BLK_BYTES = 32768;   // one 128x128 bf16 operand block
 constexpr int KB_BYTES = 16384;    // one 64-wide K half of a block: 128 rows x 128 B
 
-enum { MODE_EDGE = 0, MODE_NODE = 1, MODE_PROJ = 2 };
+enum { MODE_EDGE = 0, MODE_NODE = 1 };
 
 struct TcArgs {
   const float* x;   // [R][H] rows (input features of this entity kind)
-  float* y;         // EDGE/NODE: [R][H] core output;  PROJ: [R][2H] projections (P_s | P_r)
+  float* y;         // [R][H] core output
   int64_t R;
   int num_tiles;
   const __nv_bfloat16* wpack;   // weight blocks in consumption order
@@ -48,8 +48,8 @@ struct TcArgs {
   const int32_t* dst;           // EDGE: edge_dst
   const int32_t* gid;           // EDGE: edge_graph, NODE: node_graph
   const int32_t* part;          // EDGE: partial-row id per edge
-  float* agg_part;              // EDGE out / NODE in: [n_parts][H]
-  const int32_t* node_part_ptr; // NODE: [N+1]
+  float* agg_part;              // EDGE out: [n_parts][H] per-32-row-block partial receiver sums
+  const float* Pagg;            // NODE: [N][H] W_na . (edge aggregate)
   float* h_out;                 // NODE: [N][H] block output h_v (for the node -> graph sum)
 };
 
@@ -140,6 +140,12 @@ __device__ __forceinline__ float warp_sum(float v) {
   for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
 }
+// relu fused into the conversion: {lo, hi} = bf16(max(lo,0)), bf16(max(hi,0))
+__device__ __forceinline__ uint32_t pack_bf16_relu(float lo, float hi) {
+  uint32_t d;
+  asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  return d;
+}
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&t);
@@ -154,296 +160,439 @@ __device__ __forceinline__ void issue_block(uint32_t d_tmem, uint32_t a_base, ui
   }
 }
 
-template <int MODE>
-struct Cfg {
-  static constexpr int NA = (MODE == MODE_NODE) ? 2 : 1;       // A operand blocks (node: [x_hat | agg])
-  static constexpr int NSTAGE = (MODE == MODE_NODE) ? 2 : 3;   // weight ring stages
-  static constexpr int NCHUNK = (MODE == MODE_PROJ) ? 0 : 4;   // FFN hidden chunks of 128
-  static constexpr int NBLK0 = (MODE == MODE_EDGE) ? 1 : 2;    // blocks of the first GEMM
-  static constexpr int NBLK = NBLK0 + 2 * NCHUNK;              // weight blocks per tile
-  static constexpr int OFF_A = 0;
-  static constexpr int OFF_H = OFF_A + NA * BLK_BYTES;
-  static constexpr int OFF_W = OFF_H + 2 * BLK_BYTES;
-  static constexpr int OFF_MISC = OFF_W + NSTAGE * BLK_BYTES;
-  // misc: b1f[512] b2[128] pid[132] barriers[32] tmem slot
-  static constexpr int MISC_BYTES = 512 * 4 + 128 * 4 + 132 * 4 + 32 * 8 + 16;
-  static constexpr int SMEM_BYTES = OFF_MISC + MISC_BYTES + 1024;  // + slack for 1024 B alignment
+// =====================================================================================================
+// Projection kernel: out = A . W for 1 or 2 weight blocks (N = 128 or 256), fp32 out.
+//   SRC_LN : A = LayerNorm-normalised rows of x (affine folded into W)   -> P_s | P_r of the nodes
+//   SRC_AGG: A = per-node edge aggregate (ordered sum of its partial rows) -> W_na . agg
+// 6 warps: 0-3 prologue/epilogue, 4 MMA issuer, 5 weight loader.  One 128-row tile per iteration.
+// =====================================================================================================
+enum { SRC_LN = 0, SRC_AGG = 1 };
+
+struct ProjArgs {
+  const float* x;                 // SRC_LN: [R][H];  SRC_AGG: partial rows [n_parts][H]
+  const int32_t* part_ptr;        // SRC_AGG: [R+1]
+  float* out;                     // [R][nblk*H]
+  int64_t R;
+  int num_tiles;
+  int nblk;                       // weight blocks (1 or 2)
+  const __nv_bfloat16* wpack;
+  float eps;
+  int eps_mode;
 };
 
-// barrier indices
-enum { B_WFULL = 0, B_WEMPTY = 3, B_AREADY = 6, B_ACCFREE = 7, B_HIDFULL = 8, B_HSREADY = 10, B_HSFREE = 12, B_OUTDONE = 14, B_COUNT = 15 };
+constexpr int PJ_OFF_A = 0;
+constexpr int PJ_OFF_W = BLK_BYTES;
+constexpr int PJ_OFF_MISC = 3 * BLK_BYTES;
+constexpr int PJ_SMEM = PJ_OFF_MISC + 256 + 1024;
+enum { PB_WFULL = 0, PB_AREADY = 2, PB_ACCFREE = 3, PB_OUTDONE = 4 };
 
-template <int MODE>
-__global__ void __launch_bounds__(192, 1) k_tc_core(const TcArgs a) {
-  using C = Cfg<MODE>;
+template <int SRC>
+__global__ void __launch_bounds__(192, 1) k_tc_proj(const ProjArgs a) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
   uint8_t* sm = smem_raw + (base - raw);
-  const uint32_t sA = base + C::OFF_A, sH = base + C::OFF_H, sW = base + C::OFF_W;
-  float* sB1 = reinterpret_cast<float*>(sm + C::OFF_MISC);
-  float* sB2 = sB1 + 512;
-  int* sPid = reinterpret_cast<int*>(sB2 + 128);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sPid + 132);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 32);
+  const uint32_t sA = base + PJ_OFF_A, sW = base + PJ_OFF_W;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sm + PJ_OFF_MISC);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
   const uint32_t bar0 = smem_u32(bars);
   auto BAR = [&](int i) { return bar0 + 8u * (uint32_t)i; };
-
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-
   if (tid == 0) {
-    for (int i = 0; i < 3; i++) { mbar_init(BAR(B_WFULL + i), 1); mbar_init(BAR(B_WEMPTY + i), 1); }
-    mbar_init(BAR(B_AREADY), 128);
-    mbar_init(BAR(B_ACCFREE), 128);
-    for (int i = 0; i < 2; i++) { mbar_init(BAR(B_HIDFULL + i), 1); mbar_init(BAR(B_HSREADY + i), 128); mbar_init(BAR(B_HSFREE + i), 1); }
-    mbar_init(BAR(B_OUTDONE), 1);
+    mbar_init(BAR(PB_WFULL), 1); mbar_init(BAR(PB_WFULL + 1), 1);
+    mbar_init(BAR(PB_AREADY), 128); mbar_init(BAR(PB_ACCFREE), 128); mbar_init(BAR(PB_OUTDONE), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 4) {  // TMEM: all 512 columns (D_blk 0..127 | D_out 128..255 | D_hid 256..511)
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+  if (warp == 4) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(256u) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-  }
-  if (MODE != MODE_PROJ) {
-    for (int i = tid; i < 512; i += 192) sB1[i] = a.b1f[i];
-    for (int i = tid; i < 128; i += 192) sB2[i] = a.b2[i];
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
-  const uint32_t T_BLK = tmem, T_OUT = tmem + 128, T_HID = tmem + 256;
 
   if (warp == 5) {
-    // ===================================================== weight loader (one thread)
+    // the (at most 2) weight blocks stay resident in shared memory for the whole kernel
     if (lane == 0) {
-      uint32_t it = 0;
-      for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
-        for (int b = 0; b < C::NBLK; b++, it++) {
-          const uint32_t s = it % C::NSTAGE, ph = (it / C::NSTAGE) & 1;
-          mbar_wait(BAR(B_WEMPTY + s), ph ^ 1);
-          mbar_expect_tx(BAR(B_WFULL + s), BLK_BYTES);
-          bulk_g2s(sW + s * BLK_BYTES, reinterpret_cast<const uint8_t*>(a.wpack) + (size_t)b * BLK_BYTES, BLK_BYTES,
-                   BAR(B_WFULL + s));
-        }
+      for (int b = 0; b < a.nblk; b++) {
+        mbar_expect_tx(BAR(PB_WFULL + b), BLK_BYTES);
+        bulk_g2s(sW + b * BLK_BYTES, reinterpret_cast<const uint8_t*>(a.wpack) + (size_t)b * BLK_BYTES, BLK_BYTES, BAR(PB_WFULL + b));
       }
     }
   } else if (warp == 4) {
-    // ===================================================== MMA issuer (one thread)
     if (lane == 0) {
-      uint32_t it = 0, tl = 0;
-      auto next_w = [&](uint32_t& s) {
-        s = it % C::NSTAGE;
-        mbar_wait(BAR(B_WFULL + s), (it / C::NSTAGE) & 1);
-        it++;
-      };
+      uint32_t tl = 0;
+      for (int b = 0; b < a.nblk; b++) mbar_wait(BAR(PB_WFULL + b), 0);
       for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, tl++) {
-        uint32_t s;
-        mbar_wait(BAR(B_AREADY), tl & 1);
-        mbar_wait(BAR(B_ACCFREE), (tl & 1) ^ 1);
+        mbar_wait(BAR(PB_AREADY), tl & 1);
+        mbar_wait(BAR(PB_ACCFREE), (tl & 1) ^ 1);
         tc_fence_after();
-        if (MODE == MODE_PROJ) {
-          // D[0..127] = A . W_s', D[128..255] = A . W_r'
-          for (int j = 0; j < 2; j++) {
-            next_w(s);
-            issue_block(tmem + 128 * j, sA, sW + s * BLK_BYTES, false);
-            tc_commit(BAR(B_WEMPTY + s));
-          }
-          tc_commit(BAR(B_OUTDONE));
-        } else {
-          for (int j = 0; j < C::NBLK0; j++) {
-            next_w(s);
-            issue_block(T_BLK, sA + j * BLK_BYTES, sW + s * BLK_BYTES, j > 0);
-            tc_commit(BAR(B_WEMPTY + s));
-          }
-          for (int c = 0; c <= C::NCHUNK; c++) {
-            if (c < C::NCHUNK) {  // D_hid[c&1] = A . W1_c
-              next_w(s);
-              issue_block(T_HID + 128 * (c & 1), sA, sW + s * BLK_BYTES, false);
-              tc_commit(BAR(B_WEMPTY + s));
-              tc_commit(BAR(B_HIDFULL + (c & 1)));
-            }
-            if (c >= 1) {  // D_out += relu(hidden chunk c-1) . W2_{c-1}
-              const int cc = c - 1, b = cc & 1;
-              mbar_wait(BAR(B_HSREADY + b), (cc >> 1) & 1);
-              tc_fence_after();
-              next_w(s);
-              issue_block(T_OUT, sH + b * BLK_BYTES, sW + s * BLK_BYTES, cc > 0);
-              tc_commit(BAR(B_WEMPTY + s));
-              if (cc < 2) tc_commit(BAR(B_HSFREE + b));
-            }
-          }
-          tc_commit(BAR(B_OUTDONE));
-        }
+        for (int b = 0; b < a.nblk; b++) issue_block(tmem + 128 * b, sA, sW + b * BLK_BYTES, false);
+        tc_commit(BAR(PB_OUTDONE));
       }
     }
   } else {
-    // ===================================================== compute warps: prologue + epilogues
-    const int t = tid;  // 0..127: row of the tile owned in the epilogues (TMEM lane)
+    const int t = tid;
     const uint32_t lane_base = ((uint32_t)(warp * 32)) << 16;
+    const int l8 = lane & 7, rsub = lane >> 3;
     uint32_t tl = 0;
     for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, tl++) {
       const int64_t row0 = (int64_t)tile * TM;
       const int rows = (int)((a.R - row0) < TM ? (a.R - row0) : TM);
-      // ---------------- prologue: LayerNorm -> bf16 A operand (warp per row, lanes over features)
-#pragma unroll 1
-      for (int i0 = 0; i0 < 32; i0 += 4) {
-        float4 v[4];
+      if (tl > 0) mbar_wait(BAR(PB_OUTDONE), (tl - 1) & 1);   // previous MMAs have finished reading A
+      if (SRC == SRC_LN) {
+        // 8 lanes per row, 4 rows per warp step: every load instruction covers full 128 B lines
+#pragma unroll 2
+        for (int i = 0; i < 8; i++) {
+          const int r = warp * 32 + i * 4 + rsub;
+          float4 v[4];
+          const float4* xr = reinterpret_cast<const float4*>(a.x + (size_t)(row0 + r) * H) + l8;
 #pragma unroll
-        for (int u = 0; u < 4; u++) {
-          const int r = warp * 32 + i0 + u;
-          v[u] = (r < rows) ? __ldg(reinterpret_cast<const float4*>(a.x + (size_t)(row0 + r) * H) + lane)
-                            : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
+          for (int j = 0; j < 4; j++) v[j] = (r < rows) ? __ldg(xr + 8 * j) : make_float4(0.f, 0.f, 0.f, 0.f);
+          float s = 0.f;
 #pragma unroll
-        for (int u = 0; u < 4; u++) {
-          const int r = warp * 32 + i0 + u;
-          const float mu = warp_sum(v[u].x + v[u].y + v[u].z + v[u].w) * (1.0f / H);
-          const float d0 = v[u].x - mu, d1 = v[u].y - mu, d2 = v[u].z - mu, d3 = v[u].w - mu;
-          const float var = warp_sum(d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3) * (1.0f / H);
-          const float rs = (r < rows) ? ln_rstd(var, a.eps, a.eps_mode) : 0.f;
-          uint2 pk;
-          pk.x = pack_bf16(d0 * rs, d1 * rs);
-          pk.y = pack_bf16(d2 * rs, d3 * rs);
-          *reinterpret_cast<uint2*>(sm + C::OFF_A + sw_off(r, lane * 4)) = pk;
+          for (int j = 0; j < 4; j++) s += (v[j].x + v[j].y) + (v[j].z + v[j].w);
+          s += __shfl_xor_sync(0xffffffffu, s, 1); s += __shfl_xor_sync(0xffffffffu, s, 2); s += __shfl_xor_sync(0xffffffffu, s, 4);
+          const float mu = s * (1.0f / H);
+          float q = 0.f;
+#pragma unroll
+          for (int j = 0; j < 4; j++) {
+            v[j].x -= mu; v[j].y -= mu; v[j].z -= mu; v[j].w -= mu;
+            q += (v[j].x * v[j].x + v[j].y * v[j].y) + (v[j].z * v[j].z + v[j].w * v[j].w);
+          }
+          q += __shfl_xor_sync(0xffffffffu, q, 1); q += __shfl_xor_sync(0xffffffffu, q, 2); q += __shfl_xor_sync(0xffffffffu, q, 4);
+          const float rs = (r < rows) ? ln_rstd(q * (1.0f / H), a.eps, a.eps_mode) : 0.f;
+#pragma unroll
+          for (int j = 0; j < 4; j++) {
+            uint2 pk;
+            pk.x = pack_bf16(v[j].x * rs, v[j].y * rs);
+            pk.y = pack_bf16(v[j].z * rs, v[j].w * rs);
+            *reinterpret_cast<uint2*>(sm + PJ_OFF_A + sw_off(r, 32 * j + 4 * l8)) = pk;
+          }
         }
-      }
-      if (MODE == MODE_NODE) {
-        // second A block: edge aggregate of each node = ordered sum of its partial rows
+      } else {
 #pragma unroll 1
         for (int i = 0; i < 32; i++) {
           const int r = warp * 32 + i;
           float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
           if (r < rows) {
-            const int p0 = a.node_part_ptr[row0 + r], p1 = a.node_part_ptr[row0 + r + 1];
+            const int p0 = a.part_ptr[row0 + r], p1 = a.part_ptr[row0 + r + 1];
             for (int p = p0; p < p1; p++) {
-              const float4 q = __ldg(reinterpret_cast<const float4*>(a.agg_part + (size_t)p * H) + lane);
+              const float4 q = __ldg(reinterpret_cast<const float4*>(a.x + (size_t)p * H) + lane);
               s.x += q.x; s.y += q.y; s.z += q.z; s.w += q.w;
             }
           }
           uint2 pk;
           pk.x = pack_bf16(s.x, s.y);
           pk.y = pack_bf16(s.z, s.w);
-          *reinterpret_cast<uint2*>(sm + C::OFF_A + BLK_BYTES + sw_off(r, lane * 4)) = pk;
+          *reinterpret_cast<uint2*>(sm + PJ_OFF_A + sw_off(r, lane * 4)) = pk;
         }
-      }
-      int e_src = 0, e_dst = 0, e_gid = 0;
-      if (t < rows) {
-        if (MODE == MODE_EDGE) {
-          e_src = a.src[row0 + t];
-          e_dst = a.dst[row0 + t];
-          sPid[t] = a.part[row0 + t];
-        }
-        if (MODE != MODE_PROJ) e_gid = a.gid[row0 + t];
       }
       fence_async_smem();
-      mbar_arrive(BAR(B_AREADY));
-
-      // ---------------- FFN hidden chunks: TMEM -> +b1 -> relu -> bf16 -> swizzled smem A operand
-      if (MODE != MODE_PROJ) {
-#pragma unroll 1
-        for (int c = 0; c < C::NCHUNK; c++) {
-          const int b = c & 1;
-          mbar_wait(BAR(B_HIDFULL + b), (c >> 1) & 1);
-          tc_fence_after();
-          if (c >= 2) mbar_wait(BAR(B_HSFREE + b), tl & 1);
-#pragma unroll 1
-          for (int j = 0; j < 4; j++) {
-            float v[32];
-            tc_ld32(T_HID + 128 * b + 32 * j + lane_base, v);
-            const float* bb = sB1 + c * 128 + j * 32;
-#pragma unroll
-            for (int q = 0; q < 4; q++) {
-              uint4 pk;
-              pk.x = pack_bf16(fmaxf(v[q * 8 + 0] + bb[q * 8 + 0], 0.f), fmaxf(v[q * 8 + 1] + bb[q * 8 + 1], 0.f));
-              pk.y = pack_bf16(fmaxf(v[q * 8 + 2] + bb[q * 8 + 2], 0.f), fmaxf(v[q * 8 + 3] + bb[q * 8 + 3], 0.f));
-              pk.z = pack_bf16(fmaxf(v[q * 8 + 4] + bb[q * 8 + 4], 0.f), fmaxf(v[q * 8 + 5] + bb[q * 8 + 5], 0.f));
-              pk.w = pack_bf16(fmaxf(v[q * 8 + 6] + bb[q * 8 + 6], 0.f), fmaxf(v[q * 8 + 7] + bb[q * 8 + 7], 0.f));
-              *reinterpret_cast<uint4*>(sm + C::OFF_H + b * BLK_BYTES + sw_off(t, j * 32 + q * 8)) = pk;
-            }
-          }
-          tc_fence_before();
-          fence_async_smem();
-          mbar_arrive(BAR(B_HSREADY + b));
-        }
-      }
-
-      // ---------------- final epilogue
-      mbar_wait(BAR(B_OUTDONE), tl & 1);
+      mbar_arrive(BAR(PB_AREADY));
+      mbar_wait(BAR(PB_OUTDONE), tl & 1);
       tc_fence_after();
       const bool valid = t < rows;
-      const size_t grow = (size_t)(row0 + t);
-      if (MODE == MODE_PROJ) {
+      const int ld = a.nblk * H;
 #pragma unroll 1
-        for (int j = 0; j < 8; j++) {
-          float v[32];
-          tc_ld32(tmem + 32 * j + lane_base, v);
-          if (valid) {
-            float4* o = reinterpret_cast<float4*>(a.y + grow * (2 * H) + j * 32);
+      for (int j = 0; j < a.nblk * 4; j++) {
+        float v[32];
+        tc_ld32(tmem + 32 * j + lane_base, v);
+        if (valid) {
+          float4* o = reinterpret_cast<float4*>(a.out + (size_t)(row0 + t) * ld + j * 32);
 #pragma unroll
-            for (int q = 0; q < 8; q++) o[q] = make_float4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
-          }
-        }
-      } else {
-        float* stage = reinterpret_cast<float*>(sm + C::OFF_H);   // fp32 [128][128] h_e tile, float4-swizzled
-#pragma unroll 1
-        for (int j = 0; j < 4; j++) {
-          float hb[32], ob[32];
-          tc_ld32(T_BLK + 32 * j + lane_base, hb);
-          tc_ld32(T_OUT + 32 * j + lane_base, ob);
-          if (valid) {
-            const float4* pu = reinterpret_cast<const float4*>(a.Pu + (size_t)e_gid * H + j * 32);
-            const float4* xs = reinterpret_cast<const float4*>(a.x + grow * H + j * 32);
-            float4* yo = reinterpret_cast<float4*>(a.y + grow * H + j * 32);
-#pragma unroll
-            for (int q = 0; q < 8; q++) {
-              float4 h = __ldg(pu + q);
-              h.x += hb[q * 4]; h.y += hb[q * 4 + 1]; h.z += hb[q * 4 + 2]; h.w += hb[q * 4 + 3];
-              if (MODE == MODE_EDGE) {
-                const float4 ps = __ldg(reinterpret_cast<const float4*>(a.Psr + (size_t)e_src * (2 * H) + j * 32) + q);
-                const float4 pr = __ldg(reinterpret_cast<const float4*>(a.Psr + (size_t)e_dst * (2 * H) + H + j * 32) + q);
-                h.x += ps.x + pr.x; h.y += ps.y + pr.y; h.z += ps.z + pr.z; h.w += ps.w + pr.w;
-                const int f4 = j * 8 + q;
-                *reinterpret_cast<float4*>(stage + t * H + ((f4 ^ (t & 31)) << 2)) = h;
-              } else {
-                reinterpret_cast<float4*>(a.h_out + grow * H + j * 32)[q] = h;
-              }
-              const float4 xv = __ldg(xs + q);
-              const float* b2 = sB2 + j * 32 + q * 4;
-              float4 y;
-              y.x = (xv.x + h.x) + (ob[q * 4] + b2[0]);
-              y.y = (xv.y + h.y) + (ob[q * 4 + 1] + b2[1]);
-              y.z = (xv.z + h.z) + (ob[q * 4 + 2] + b2[2]);
-              y.w = (xv.w + h.w) + (ob[q * 4 + 3] + b2[3]);
-              yo[q] = y;
-            }
-          }
-        }
-        if (MODE == MODE_EDGE) {
-          // edge -> receiver segmented sum of h_e, column per thread, rows in order (deterministic)
-          asm volatile("bar.sync 1, 128;" ::: "memory");
-          float s = 0.f;
-          const int c4 = t >> 2, cw = t & 3;
-          for (int r = 0; r < rows; r++) {
-            s += stage[r * H + (((c4 ^ (r & 31)) << 2) | cw)];
-            const int pid = sPid[r];
-            if (r == rows - 1 || sPid[r + 1] != pid) {
-              a.agg_part[(size_t)pid * H + t] = s;
-              s = 0.f;
-            }
-          }
-          asm volatile("bar.sync 1, 128;" ::: "memory");
+          for (int q = 0; q < 8; q++) o[q] = make_float4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
         }
       }
       tc_fence_before();
-      mbar_arrive(BAR(B_ACCFREE));
+      mbar_arrive(BAR(PB_ACCFREE));
     }
   }
-
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+  if (warp == 4) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(256u) : "memory");
+}
+
+// =====================================================================================================
+// Fused GNCore kernel for edges (MODE_EDGE) and nodes (MODE_NODE).
+// A CTA owns a PAIR of 128-row sub-tiles that run in lock step, so every streamed weight block feeds
+// two UMMA tiles (halves the L2 -> SMEM weight traffic).  10 warps:
+//   warps 0-3 : compute group of sub-tile 0      warps 4-7 : compute group of sub-tile 1
+//   warp  8   : MMA issuer (one thread)          warp  9   : weight loader (one thread)
+// TMEM per sub-tile s: D_s   (cols 256s .. +127)      FFN output accumulator
+//                      Hd_s  (cols 256s+128 .. +127)  FFN hidden chunk, finally the GNBlock GEMM D_blk
+// Block order per pair: W1_0 W2_0 W1_1 W2_1 W1_2 W2_2 W1_3 W2_3 W_blk, each block used by s = 0 then 1.
+// =====================================================================================================
+constexpr int HALF_BYTES = KB_BYTES;     // weight ring stage = one 64-wide K half of a block (16 KB)
+constexpr int NWS = 5;                   // ring stages
+constexpr int P_OFF_A = 0;                          // A_s: s * 32 KB
+constexpr int P_OFF_H = 2 * BLK_BYTES;              // Hs_s (hidden chunk bf16; epilogue staging)
+constexpr int P_OFF_W = 4 * BLK_BYTES;
+constexpr int P_OFF_MISC = P_OFF_W + NWS * HALF_BYTES;
+// misc: b1f[512] b2[128] seg masks[8] seg pid0[8] barriers[32] tmem slot
+constexpr int P_MISC = 512 * 4 + 128 * 4 + 8 * 4 + 8 * 4 + 32 * 8 + 16;
+constexpr int P_SMEM = P_OFF_MISC + P_MISC + 1024;
+enum { QB_WFULL = 0, QB_WEMPTY = 5, QB_AREADY = 10, QB_ACCFREE = 12, QB_HIDFULL = 14, QB_HSREADY = 16, QB_HSFREE = 18, QB_OUTDONE = 20 };
+
+// 4 UMMAs (K = 64): one 16 KB half block
+__device__ __forceinline__ void issue_half(uint32_t d_tmem, uint32_t a_half, uint32_t b_half, bool accumulate) {
+#pragma unroll
+  for (int ks = 0; ks < 4; ks++)
+    tc_mma(d_tmem, umma_desc(a_half + ks * 32), umma_desc(b_half + ks * 32), IDESC, (accumulate || ks > 0) ? 1u : 0u);
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(320, 1) k_tc_pair(const TcArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* sm = smem_raw + (base - raw);
+  const uint32_t sW = base + P_OFF_W;
+  float* sB1 = reinterpret_cast<float*>(sm + P_OFF_MISC);
+  float* sB2 = sB1 + 512;
+  uint32_t* sMask = reinterpret_cast<uint32_t*>(sB2 + 128);   // [2][4] segment-end bit masks of 32-row blocks
+  int* sPid0 = reinterpret_cast<int*>(sMask + 8);             // [2][4] first partial-row id of each 32-row block
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sPid0 + 8);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 32);
+  const uint32_t bar0 = smem_u32(bars);
+  auto BAR = [&](int i) { return bar0 + 8u * (uint32_t)i; };
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  if (tid == 0) {
+    for (int i = 0; i < NWS; i++) { mbar_init(BAR(QB_WFULL + i), 1); mbar_init(BAR(QB_WEMPTY + i), 1); }
+    for (int s = 0; s < 2; s++) {
+      mbar_init(BAR(QB_AREADY + s), 128); mbar_init(BAR(QB_ACCFREE + s), 128);
+      mbar_init(BAR(QB_HIDFULL + s), 1); mbar_init(BAR(QB_HSREADY + s), 128);
+      mbar_init(BAR(QB_HSFREE + s), 1); mbar_init(BAR(QB_OUTDONE + s), 1);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  if (warp == 8) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  for (int i = tid; i < 512; i += 320) sB1[i] = a.b1f[i];
+  for (int i = tid; i < 128; i += 320) sB2[i] = a.b2[i];
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const int num_pairs = (a.num_tiles + 1) >> 1;
+
+  if (warp == 9) {
+    // ===================================================== weight loader
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int pair = blockIdx.x; pair < num_pairs; pair += gridDim.x) {
+        for (int hb = 0; hb < 18; hb++, it++) {
+          const uint32_t st = it % NWS, ph = (it / NWS) & 1;
+          mbar_wait(BAR(QB_WEMPTY + st), ph ^ 1);
+          mbar_expect_tx(BAR(QB_WFULL + st), HALF_BYTES);
+          bulk_g2s(sW + st * HALF_BYTES, reinterpret_cast<const uint8_t*>(a.wpack) + (size_t)hb * HALF_BYTES, HALF_BYTES,
+                   BAR(QB_WFULL + st));
+        }
+      }
+    }
+  } else if (warp == 8) {
+    // ===================================================== MMA issuer
+    if (lane == 0) {
+      uint32_t it = 0, tl = 0;
+      for (int pair = blockIdx.x; pair < num_pairs; pair += gridDim.x, tl++) {
+        for (int b = 0; b < 9; b++) {
+          const uint32_t st0 = it % NWS, ph0 = (it / NWS) & 1;
+          const uint32_t st1 = (it + 1) % NWS, ph1 = ((it + 1) / NWS) & 1;
+          it += 2;
+          mbar_wait(BAR(QB_WFULL + st0), ph0);
+          mbar_wait(BAR(QB_WFULL + st1), ph1);
+          const uint32_t w0 = sW + st0 * HALF_BYTES, w1 = sW + st1 * HALF_BYTES;
+          const int c = b >> 1;
+          for (int s = 0; s < 2; s++) {
+            const uint32_t A_s = base + P_OFF_A + s * BLK_BYTES, H_s = base + P_OFF_H + s * BLK_BYTES;
+            const uint32_t D_s = tmem + 256 * s, Hd_s = D_s + 128;
+            if (b == 0) {
+              mbar_wait(BAR(QB_AREADY + s), tl & 1);
+              mbar_wait(BAR(QB_ACCFREE + s), (tl & 1) ^ 1);
+              tc_fence_after();
+            }
+            if (b == 8) {                 // D_blk = A . W_blk  (into the drained hidden columns)
+              issue_half(Hd_s, A_s, w0, false);
+              issue_half(Hd_s, A_s + KB_BYTES, w1, true);
+              tc_commit(BAR(QB_OUTDONE + s));
+            } else if ((b & 1) == 0) {    // hidden chunk c = A . W1_c
+              issue_half(Hd_s, A_s, w0, false);
+              issue_half(Hd_s, A_s + KB_BYTES, w1, true);
+              tc_commit(BAR(QB_HIDFULL + s));
+            } else {                      // D_s += relu(hidden chunk c) . W2_c
+              mbar_wait(BAR(QB_HSREADY + s), c & 1);
+              tc_fence_after();
+              issue_half(D_s, H_s, w0, c > 0);
+              issue_half(D_s, H_s + KB_BYTES, w1, true);
+              if (c < 3) tc_commit(BAR(QB_HSFREE + s));
+            }
+          }
+          tc_commit(BAR(QB_WEMPTY + st0));
+          tc_commit(BAR(QB_WEMPTY + st1));
+        }
+      }
+    }
+  } else {
+    // ===================================================== compute groups
+    const int s = warp >> 2;              // sub-tile of this group
+    const int w4 = warp & 3;              // warp within the group == TMEM lane quadrant
+    const int t = tid & 127;              // row of the sub-tile owned in thread-per-row phases
+    const uint32_t lane_base = ((uint32_t)(w4 * 32)) << 16;
+    const uint32_t D_s = tmem + 256 * s, Hd_s = D_s + 128;
+    uint8_t* A_s = sm + P_OFF_A + s * BLK_BYTES;
+    uint8_t* H_s = sm + P_OFF_H + s * BLK_BYTES;
+    float* S_h = reinterpret_cast<float*>(H_s);            // [128][32] fp32 staging (swizzled float4)
+    float* S_f = S_h + 128 * 32;
+    const int l8 = lane & 7, rsub = lane >> 3;
+    uint32_t tl = 0;
+    for (int pair = blockIdx.x; pair < num_pairs; pair += gridDim.x, tl++) {
+      const int64_t row0 = ((int64_t)pair * 2 + s) * TM;
+      int rows = (int)(a.R - row0);
+      rows = rows < 0 ? 0 : (rows > TM ? TM : rows);
+      // ---------------- prologue: LayerNorm -> bf16 A operand (8 lanes per row)
+#pragma unroll 2
+      for (int i = 0; i < 8; i++) {
+        const int r = w4 * 32 + i * 4 + rsub;
+        float4 v[4];
+        const float4* xr = reinterpret_cast<const float4*>(a.x + (size_t)(row0 + r) * H) + l8;
+#pragma unroll
+        for (int j = 0; j < 4; j++) v[j] = (r < rows) ? __ldg(xr + 8 * j) : make_float4(0.f, 0.f, 0.f, 0.f);
+        float sum = 0.f;
+#pragma unroll
+        for (int j = 0; j < 4; j++) sum += (v[j].x + v[j].y) + (v[j].z + v[j].w);
+        sum += __shfl_xor_sync(0xffffffffu, sum, 1); sum += __shfl_xor_sync(0xffffffffu, sum, 2); sum += __shfl_xor_sync(0xffffffffu, sum, 4);
+        const float mu = sum * (1.0f / H);
+        float q = 0.f;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          v[j].x -= mu; v[j].y -= mu; v[j].z -= mu; v[j].w -= mu;
+          q += (v[j].x * v[j].x + v[j].y * v[j].y) + (v[j].z * v[j].z + v[j].w * v[j].w);
+        }
+        q += __shfl_xor_sync(0xffffffffu, q, 1); q += __shfl_xor_sync(0xffffffffu, q, 2); q += __shfl_xor_sync(0xffffffffu, q, 4);
+        const float rs = (r < rows) ? ln_rstd(q * (1.0f / H), a.eps, a.eps_mode) : 0.f;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          uint2 pk;
+          pk.x = pack_bf16(v[j].x * rs, v[j].y * rs);
+          pk.y = pack_bf16(v[j].z * rs, v[j].w * rs);
+          *reinterpret_cast<uint2*>(A_s + sw_off(r, 32 * j + 4 * l8)) = pk;
+        }
+      }
+      if (MODE == MODE_EDGE) {
+        // segment structure of this warp's 32 rows: bit i set = row i closes a partial row
+        const int r = w4 * 32 + lane;
+        const int pid = (r < rows) ? a.part[row0 + r] : -1;
+        const int nxt = __shfl_down_sync(0xffffffffu, pid, 1);
+        const bool endb = (r < rows) && (lane == 31 || nxt != pid);
+        const uint32_t m = __ballot_sync(0xffffffffu, endb);
+        if (lane == 0) { sMask[s * 4 + w4] = m; sPid0[s * 4 + w4] = pid; }
+      }
+      fence_async_smem();
+      mbar_arrive(BAR(QB_AREADY + s));
+
+      // ---------------- FFN hidden chunks: TMEM -> +b1 -> relu -> bf16 -> swizzled smem A operand
+#pragma unroll 1
+      for (int c = 0; c < 4; c++) {
+        mbar_wait(BAR(QB_HIDFULL + s), c & 1);
+        tc_fence_after();
+        if (c >= 1) mbar_wait(BAR(QB_HSFREE + s), (3 * tl + (c - 1)) & 1);
+#pragma unroll 1
+        for (int j = 0; j < 4; j++) {
+          float v[32];
+          tc_ld32(Hd_s + 32 * j + lane_base, v);
+          const float* bb = sB1 + c * 128 + j * 32;
+#pragma unroll
+          for (int q = 0; q < 4; q++) {
+            uint4 pk;
+            pk.x = pack_bf16_relu(v[q * 8 + 0] + bb[q * 8 + 0], v[q * 8 + 1] + bb[q * 8 + 1]);
+            pk.y = pack_bf16_relu(v[q * 8 + 2] + bb[q * 8 + 2], v[q * 8 + 3] + bb[q * 8 + 3]);
+            pk.z = pack_bf16_relu(v[q * 8 + 4] + bb[q * 8 + 4], v[q * 8 + 5] + bb[q * 8 + 5]);
+            pk.w = pack_bf16_relu(v[q * 8 + 6] + bb[q * 8 + 6], v[q * 8 + 7] + bb[q * 8 + 7]);
+            *reinterpret_cast<uint4*>(H_s + sw_off(t, j * 32 + q * 8)) = pk;
+          }
+        }
+        tc_fence_before();
+        fence_async_smem();
+        mbar_arrive(BAR(QB_HSREADY + s));
+      }
+
+      // ---------------- final epilogue, 32 columns at a time through the staging tiles
+      mbar_wait(BAR(QB_OUTDONE + s), tl & 1);
+      tc_fence_after();
+#pragma unroll 1
+      for (int qq = 0; qq < 4; qq++) {
+        {  // A: thread per row, TMEM -> staging (D_blk and FFN out + b2)
+          float v[32];
+          tc_ld32(Hd_s + 32 * qq + lane_base, v);
+#pragma unroll
+          for (int q = 0; q < 8; q++)
+            *reinterpret_cast<float4*>(S_h + t * 32 + ((q ^ (t & 7)) << 2)) = make_float4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
+          tc_ld32(D_s + 32 * qq + lane_base, v);
+          const float* b2 = sB2 + 32 * qq;
+#pragma unroll
+          for (int q = 0; q < 8; q++)
+            *reinterpret_cast<float4*>(S_f + t * 32 + ((q ^ (t & 7)) << 2)) =
+                make_float4(v[q * 4] + b2[q * 4], v[q * 4 + 1] + b2[q * 4 + 1], v[q * 4 + 2] + b2[q * 4 + 2], v[q * 4 + 3] + b2[q * 4 + 3]);
+        }
+        __syncwarp();   // every epilogue step touches only this warp's own 32 rows
+        // C: 8 lanes per row (full 128 B lines): gathers + residual, coalesced y store
+#pragma unroll 2
+        for (int i = 0; i < 8; i++) {
+          const int r = w4 * 32 + i * 4 + rsub;
+          if (r < rows) {
+            const size_t grow = (size_t)(row0 + r);
+            const int col = 32 * qq + 4 * l8;
+            const int sidx = r * 32 + ((l8 ^ (r & 7)) << 2);
+            float4 h = *reinterpret_cast<const float4*>(S_h + sidx);
+            const float4 f = *reinterpret_cast<const float4*>(S_f + sidx);
+            const float4 xv = __ldg(reinterpret_cast<const float4*>(a.x + grow * H + col));
+            const float4 pu = __ldg(reinterpret_cast<const float4*>(a.Pu + (size_t)a.gid[grow] * H + col));
+            if (MODE == MODE_EDGE) {
+              const float4 ps = __ldg(reinterpret_cast<const float4*>(a.Psr + (size_t)a.src[grow] * (2 * H) + col));
+              const float4 pr = __ldg(reinterpret_cast<const float4*>(a.Psr + (size_t)a.dst[grow] * (2 * H) + H + col));
+              h.x += (ps.x + pr.x) + pu.x; h.y += (ps.y + pr.y) + pu.y; h.z += (ps.z + pr.z) + pu.z; h.w += (ps.w + pr.w) + pu.w;
+              *reinterpret_cast<float4*>(S_h + sidx) = h;
+            } else {
+              const float4 pa = __ldg(reinterpret_cast<const float4*>(a.Pagg + grow * H + col));
+              h.x += pa.x + pu.x; h.y += pa.y + pu.y; h.z += pa.z + pu.z; h.w += pa.w + pu.w;
+              *reinterpret_cast<float4*>(a.h_out + grow * H + col) = h;
+            }
+            float4 y;
+            y.x = (xv.x + h.x) + f.x; y.y = (xv.y + h.y) + f.y; y.z = (xv.z + h.z) + f.z; y.w = (xv.w + h.w) + f.w;
+            *reinterpret_cast<float4*>(a.y + grow * H + col) = y;
+          }
+        }
+        if (MODE == MODE_EDGE) {
+          __syncwarp();   // every epilogue step touches only this warp's own 32 rows
+          // E: edge -> receiver segmented sum; thread = (column lane, 32-row block w4), rows in order
+          uint32_t m = sMask[s * 4 + w4];
+          int pid = sPid0[s * 4 + w4];
+          float acc = 0.f;
+          const int cc = lane >> 2, cw = lane & 3;
+#pragma unroll 8
+          for (int i = 0; i < 32; i++) {
+            const int r = w4 * 32 + i;
+            acc += S_h[r * 32 + (((cc ^ (r & 7)) << 2) | cw)];
+            if ((m >> i) & 1u) {
+              a.agg_part[(size_t)pid * H + 32 * qq + lane] = acc;
+              acc = 0.f;
+              pid++;
+            }
+          }
+        }
+        __syncwarp();   // every epilogue step touches only this warp's own 32 rows
+      }
+      tc_fence_before();
+      mbar_arrive(BAR(QB_ACCFREE + s));
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 8) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
 }
 
 // ------------------------------------------------------------------ weight packing
@@ -471,9 +620,9 @@ __global__ void k_fold_bias(const float* __restrict__ W, int ldw, int n0, int k0
 }  // namespace
 
 struct TcCorePack {
-  __nv_bfloat16* w = nullptr;   // [proj 2 | edge 9 | node 10] blocks
+  __nv_bfloat16* w = nullptr;   // [proj 2 | aggproj 1 | edge 9 | node 9] blocks of 32 KB
   float* f = nullptr;           // folded fp32 vectors: cu_e[128] cu_n[128] b1f_e[512] b1f_n[512]
-  const __nv_bfloat16 *w_proj, *w_edge, *w_node;
+  const __nv_bfloat16 *w_proj, *w_agg, *w_edge, *w_node;
   float *cu_e, *cu_n, *b1f_e, *b1f_n;
 };
 
@@ -494,8 +643,9 @@ int tc_core_pack(gnb_ctx* ctx, const gnb_block_params& blk, const gnb_ffn_params
   for (int i = 0; i < 2; i++)
     if (ln1[i].eps != ln2[i].eps || ln1[i].eps_mode != ln2[i].eps_mode) return GNB_OK;
   TcCorePack* p = new TcCorePack();
-  const size_t nblk = 2 + 9 + 10;
-  if (cudaMalloc((void**)&p->w, nblk * BLK_BYTES) != cudaSuccess || cudaMalloc((void**)&p->f, (128 + 128 + 512 + 512) * sizeof(float)) != cudaSuccess) {
+  const size_t nblk = 2 + 1 + 9 + 9;
+  if (cudaMalloc((void**)&p->w, nblk * BLK_BYTES) != cudaSuccess ||
+      cudaMalloc((void**)&p->f, (128 + 128 + 512 + 512) * sizeof(float)) != cudaSuccess) {
     cudaGetLastError();
     tc_core_pack_free(p);
     gnb_set_error("tc_core_pack: cudaMalloc failed");
@@ -503,39 +653,28 @@ int tc_core_pack(gnb_ctx* ctx, const gnb_block_params& blk, const gnb_ffn_params
   }
   __nv_bfloat16* w = p->w;
   const size_t BE = BLK_BYTES / 2;   // elements per block
-  p->w_proj = w; p->w_edge = w + 2 * BE; p->w_node = w + 11 * BE;
+  p->w_proj = w; p->w_agg = w + 2 * BE; p->w_edge = w + 3 * BE; p->w_node = w + 12 * BE;
   p->cu_e = p->f; p->cu_n = p->f + 128; p->b1f_e = p->f + 256; p->b1f_n = p->f + 768;
   cudaStream_t st = ctx->stream;
   auto pack = [&](const float* W, int ldw, int n0, int k0, const float* gamma, __nv_bfloat16* dst) {
     k_pack_block<<<64, 256, 0, st>>>(W, ldw, n0, k0, gamma, dst);
   };
-  // We: (128, 4*128) rows [e | v_src | v_dst | u]; Wn: (128, 3*128) rows [agg | v | u]
+  // We: (128, 4*128) input rows [e | v_src | v_dst | u]; Wn: (128, 3*128) input rows [agg | v | u]
   const float *g1e = ln1[0].gamma, *g1n = ln1[1].gamma, *b1e = ln1[0].beta, *b1n = ln1[1].beta;
-  // projections P_s | P_r
-  pack(blk.We, H, 0, H, g1n, w + 0 * BE);
-  pack(blk.We, H, 0, 2 * H, g1n, w + 1 * BE);
-  // edge: W_blk, then W1_0 W1_1 W2_0 W1_2 W2_1 W1_3 W2_2 W2_3
-  __nv_bfloat16* we = w + 2 * BE;
-  pack(blk.We, H, 0, 0, g1e, we);
-  {
-    const int order1[4] = {1, 2, 4, 6}, order2[4] = {3, 5, 7, 8};
+  pack(blk.We, H, 0, H, g1n, w + 0 * BE);          // P_s
+  pack(blk.We, H, 0, 2 * H, g1n, w + 1 * BE);      // P_r
+  pack(blk.Wn, H, 0, 0, nullptr, w + 2 * BE);      // W_na (aggregate rows, no LayerNorm)
+  // fused kernels: W1_0 W2_0 W1_1 W2_1 W1_2 W2_2 W1_3 W2_3 W_blk
+  for (int kind = 0; kind < 2; kind++) {
+    __nv_bfloat16* dst = w + (kind == 0 ? 3 : 12) * BE;
     for (int c = 0; c < 4; c++) {
-      pack(ffn[0].W1, 4 * H, c * H, 0, ln2[0].gamma, we + order1[c] * BE);   // W1 (4H, H): hidden unit c*128+n
-      pack(ffn[0].W2, H, 0, c * H, nullptr, we + order2[c] * BE);            // W2 (H, 4H): k = hidden index
+      pack(ffn[kind].W1, 4 * H, c * H, 0, ln2[kind].gamma, dst + (2 * c) * BE);   // W1 (4H, H): hidden unit c*128+n
+      pack(ffn[kind].W2, H, 0, c * H, nullptr, dst + (2 * c + 1) * BE);           // W2 (H, 4H): k = hidden index
     }
+    if (kind == 0) pack(blk.We, H, 0, 0, g1e, dst + 8 * BE);
+    else pack(blk.Wn, H, 0, H, g1n, dst + 8 * BE);
   }
-  // node: [W_nv' (x_hat block), W_na (agg block)], then the FFN blocks in the same order
-  __nv_bfloat16* wn = w + 11 * BE;
-  pack(blk.Wn, H, 0, H, g1n, wn);
-  pack(blk.Wn, H, 0, 0, nullptr, wn + BE);
-  {
-    const int order1[4] = {2, 3, 5, 7}, order2[4] = {4, 6, 8, 9};
-    for (int c = 0; c < 4; c++) {
-      pack(ffn[1].W1, 4 * H, c * H, 0, ln2[1].gamma, wn + order1[c] * BE);
-      pack(ffn[1].W2, H, 0, c * H, nullptr, wn + order2[c] * BE);
-    }
-  }
-  // folded constants
+  // constants folded into the per-graph rows / FFN bias
   k_fold_bias<<<1, 128, 0, st>>>(blk.We, H, 0, 0, H, b1e, blk.be, H, p->cu_e, 0);
   k_fold_bias<<<1, 128, 0, st>>>(blk.We, H, 0, H, H, b1n, nullptr, H, p->cu_e, 1);
   k_fold_bias<<<1, 128, 0, st>>>(blk.We, H, 0, 2 * H, H, b1n, nullptr, H, p->cu_e, 1);
@@ -554,17 +693,32 @@ int tc_core_pack(gnb_ctx* ctx, const gnb_block_params& blk, const gnb_ffn_params
 }
 
 template <int MODE>
-static int launch_tc(gnb_ctx* ctx, const TcArgs& a, const char* name, double flops, double bytes) {
-  using C = Cfg<MODE>;
+static int launch_pair(gnb_ctx* ctx, const TcArgs& a, const char* name, double flops, double bytes) {
   if (a.num_tiles <= 0) return GNB_OK;
   static bool attr_set = false;
   if (!attr_set) {
-    GNB_CUDA(cudaFuncSetAttribute(k_tc_core<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    GNB_CUDA(cudaFuncSetAttribute(k_tc_pair<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, P_SMEM));
     attr_set = true;
   }
-  int grid = a.num_tiles < ctx->sm_count ? a.num_tiles : ctx->sm_count;
+  const int pairs = (a.num_tiles + 1) / 2;
+  const int grid = pairs < ctx->sm_count ? pairs : ctx->sm_count;
   Launch L(ctx, name, bytes, flops);
-  k_tc_core<MODE><<<grid, 192, C::SMEM_BYTES, ctx->stream>>>(a);
+  k_tc_pair<MODE><<<grid, 320, P_SMEM, ctx->stream>>>(a);
+  GNB_CUDA(cudaGetLastError());
+  return GNB_OK;
+}
+
+template <int SRC>
+static int launch_proj(gnb_ctx* ctx, const ProjArgs& a, const char* name, double flops, double bytes) {
+  if (a.num_tiles <= 0) return GNB_OK;
+  static bool attr_set = false;
+  if (!attr_set) {
+    GNB_CUDA(cudaFuncSetAttribute(k_tc_proj<SRC>, cudaFuncAttributeMaxDynamicSharedMemorySize, PJ_SMEM));
+    attr_set = true;
+  }
+  const int grid = a.num_tiles < ctx->sm_count ? a.num_tiles : ctx->sm_count;
+  Launch L(ctx, name, bytes, flops);
+  k_tc_proj<SRC><<<grid, 192, PJ_SMEM, ctx->stream>>>(a);
   GNB_CUDA(cudaGetLastError());
   return GNB_OK;
 }
@@ -578,6 +732,7 @@ int tc_core_forward(gnb_ctx* ctx, const gnb_graph* g, const TcCorePack* pk, cons
   float* Pun = arena_ptr<float>(ctx->arena, (size_t)B * H, &rc);
   float* Psr = arena_ptr<float>(ctx->arena, (size_t)N * 2 * H, &rc);
   float* aggp = arena_ptr<float>(ctx->arena, (size_t)(g->n_parts > 0 ? g->n_parts : 1) * H, &rc);
+  float* Pagg = arena_ptr<float>(ctx->arena, (size_t)N * H, &rc);
   float* hv = arena_ptr<float>(ctx->arena, (size_t)N * H, &rc);
   float* se = arena_ptr<float>(ctx->arena, (size_t)B * H, &rc);
   float* sv = arena_ptr<float>(ctx->arena, (size_t)B * H, &rc);
@@ -596,30 +751,34 @@ int tc_core_forward(gnb_ctx* ctx, const gnb_graph* g, const TcCorePack* pk, cons
     GNB_TRY(launch_linear_fp32(ctx, la));
   }
   const double HH = (double)H * H;
-  // node projections P_s | P_r
-  {
-    TcArgs a{};
-    a.x = xn; a.y = Psr; a.R = N; a.num_tiles = ceil_div(N, TM); a.wpack = pk->w_proj;
+  {  // node projections P_s | P_r
+    ProjArgs a{};
+    a.x = xn; a.out = Psr; a.R = N; a.num_tiles = ceil_div(N, TM); a.nblk = 2; a.wpack = pk->w_proj;
     a.eps = ln1[1].eps; a.eps_mode = ln1[1].eps_mode;
-    GNB_TRY(launch_tc<MODE_PROJ>(ctx, a, "tc_node_proj", 2.0 * N * 2 * HH, 4.0 * N * 3 * H));
+    GNB_TRY(launch_proj<SRC_LN>(ctx, a, "tc_node_proj", 2.0 * N * 2 * HH, 4.0 * N * 3 * H));
   }
-  // edges: block update + FFN + residual + receiver aggregation
-  {
+  {  // edges: GNBlock edge update + FFN + residual + receiver aggregation
     TcArgs a{};
     a.x = xe; a.y = ye; a.R = E; a.num_tiles = ceil_div(E, TM); a.wpack = pk->w_edge;
     a.b1f = pk->b1f_e; a.b2 = ffn[0].b2; a.eps = ln1[0].eps; a.eps_mode = ln1[0].eps_mode;
     a.Psr = Psr; a.Pu = Pue; a.src = g->edge_src; a.dst = g->edge_dst; a.gid = g->edge_graph; a.part = g->edge_part;
     a.agg_part = aggp;
-    // canonical work of the reference's edge update + edge FFN: 24 H^2 flops, 8H bytes (+12 B index) per edge
-    GNB_TRY(launch_tc<MODE_EDGE>(ctx, a, "tc_edge_core", 24.0 * HH * E, (8.0 * H + 12.0) * E));
+    // canonical work of the reference's edge update + edge FFN: 24 H^2 flops and
+    // 8H bytes of features + 12 B of index per edge
+    GNB_TRY(launch_pair<MODE_EDGE>(ctx, a, "tc_edge_core", 24.0 * HH * E, (8.0 * H + 12.0) * E));
   }
-  // nodes
-  {
+  {  // W_na . (edge aggregate of each node)
+    ProjArgs a{};
+    a.x = aggp; a.part_ptr = g->node_part_ptr; a.out = Pagg; a.R = N; a.num_tiles = ceil_div(N, TM); a.nblk = 1;
+    a.wpack = pk->w_agg;
+    GNB_TRY(launch_proj<SRC_AGG>(ctx, a, "tc_agg_proj", 2.0 * N * HH, 4.0 * N * 2 * H));
+  }
+  {  // nodes
     TcArgs a{};
     a.x = xn; a.y = yn; a.R = N; a.num_tiles = ceil_div(N, TM); a.wpack = pk->w_node;
     a.b1f = pk->b1f_n; a.b2 = ffn[1].b2; a.eps = ln1[1].eps; a.eps_mode = ln1[1].eps_mode;
-    a.Pu = Pun; a.gid = g->node_graph; a.agg_part = aggp; a.node_part_ptr = g->node_part_ptr; a.h_out = hv;
-    GNB_TRY(launch_tc<MODE_NODE>(ctx, a, "tc_node_core", 22.0 * HH * N, (8.0 * H + 4.0 * H + 8.0) * N));
+    a.Pu = Pun; a.gid = g->node_graph; a.Pagg = Pagg; a.h_out = hv;
+    GNB_TRY(launch_pair<MODE_NODE>(ctx, a, "tc_node_core", 20.0 * HH * N, (8.0 * H + 8.0) * N));
   }
   // graphs (B rows, fp32 CUDA cores): sums, graph update, graph FFN + residual
   GNB_TRY(launch_segsum(ctx, aggp, H, g->graph_part_ptr, B, se));
