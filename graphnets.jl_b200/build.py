@@ -17,7 +17,7 @@ BUILD = os.path.join(HERE, "build")
 SOURCES = ["model.cu", "lower.cu", "fp32.cu", "tc.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-         "-Xcompiler", "-fPIC", "-Xptxas=-v"]
+         "-Xcompiler", "-fPIC", "-Xptxas=-v"] + os.environ.get("GNB_EXTRA_NVCC_FLAGS", "").split()
 
 
 def _digest():
