@@ -1,23 +1,23 @@
 // tcgen05 / TMEM / bulk-async (TMA engine) bf16 path for GNCore layers with hidden width 128.
 //
-// One persistent, warp-specialised kernel template processes 128-row tiles of edges (or nodes):
+// Algebra (all exact rewrites of src/gnblock.jl:63-69 + src/gncore.jl:56-59 by linearity of Dense):
+//   h_e   = We_e' ê + Ps[src] + Pr[dst] + Pu[g]           ê = LayerNorm-normalised edge row, affine folded into W
+//   y_e   = x_e + h_e + W2 relu(W1' ê + b1') + b2          one TMEM accumulator: D = ê We_e' + relu(.) W2
+//   agg_v = sum_{e->v} h_e = We_e' (sum ê) + sum (Ps+Pr+Pu)   "aggregate, then transform": the edge kernel only
+//                                                          emits per-32-row partial sums of ê and of the gathered
+//                                                          addends (deterministic order, no atomics)
 //
-//   prologue   (4 compute warps)  LayerNorm statistics of the fp32 rows, normalised rows written as the
-//                                 bf16 A operand into 128B-swizzled K-major shared memory (the LayerNorm
-//                                 affine is folded into the packed weights, so LN1 and LN2 share one A tile)
-//   MMA        (1 thread)         tcgen05.mma kind::f16, M=128 N=128 K=16, accumulators in TMEM:
-//                                   D_blk  = A . W_blk                      (GNBlock edge / node update)
-//                                   D_hid  = A . W1[chunk]                  (FFN up-projection, 4 chunks of 128)
-//                                   D_out += relu(D_hid + b1) . W2[chunk]   (FFN down-projection)
-//   loader     (1 thread)         streams the packed bf16 weight blocks (32 KB each, already in the
-//                                 swizzled shared-memory image) with cp.async.bulk + mbarrier
-//   epilogue   (4 compute warps)  tcgen05.ld; hidden chunk: bias + relu -> bf16 -> swizzled smem A operand;
-//                                 final: gather-add of the projected sender / receiver / graph rows
-//                                 (src/edgefninput.jl:1-8 by linearity), residual adds (src/gncore.jl:56-59),
-//                                 store y, and the deterministic edge -> receiver segmented sum
-//                                 (src/nodefninput.jl:3) written as per-tile partial rows (no atomics).
-//
-// The 4H-wide FFN hidden activation never leaves the SM (TMEM -> registers -> shared memory).
+// k_core (persistent, warp specialised, one CTA per SM, a PAIR of 128-row tiles in lock step so that every
+// streamed weight block feeds two UMMA tiles):
+//   warps 0-3 / 4-7   drain + epilogue group of sub-tile 0 / 1 (TMEM lane quadrant = warp & 3)
+//   warps 8-15        prologue, one pair AHEAD of the MMAs: coalesced row loads, LayerNorm, bf16 A operand into
+//                     128B-swizzled K-major smem (double buffered), gathered addends + residual written as y0,
+//                     partial receiver sums
+//   warp 16           MMA issuer: converged warp, one elected lane, descriptors in uniform registers
+//   warp 17           weight loader: cp.async.bulk of pre-swizzled 16 KB half blocks through a 5-stage ring
+// TMEM per sub-tile: D (128 cols, fp32 accumulator) | Hd (128 cols: FFN hidden chunk fp32, rewritten IN PLACE as
+// bf16 by the drain warps and consumed as the TMEM A operand of the down-projection; the 4H hidden activation
+// never touches shared or global memory).
 #include <cuda_bf16.h>
 #include "kernels.cuh"
 #include "tc.cuh"
@@ -30,28 +30,6 @@ constexpr int BLK_BYTES = 32768;   // one 128x128 bf16 operand block
 constexpr int KB_BYTES = 16384;    // one 64-wide K half of a block: 128 rows x 128 B
 
 enum { MODE_EDGE = 0, MODE_NODE = 1 };
-
-struct TcArgs {
-  const float* x;   // [R][H] rows (input features of this entity kind)
-  float* y;         // [R][H] core output
-  int64_t R;
-  int num_tiles;
-  const __nv_bfloat16* wpack;   // weight blocks in consumption order
-  const float* b1f;             // [4H] FFN bias with the LN2 shift folded in
-  const float* b2;              // [H]
-  float eps;
-  int eps_mode;
-  // gather addends of the block update
-  const float* Psr;             // EDGE: [N][2H] sender (cols 0..H) / receiver (cols H..2H) projections
-  const float* Pu;              // [B][H] per-graph row (graph projection + every folded bias)
-  const int32_t* src;           // EDGE: edge_src
-  const int32_t* dst;           // EDGE: edge_dst
-  const int32_t* gid;           // EDGE: edge_graph, NODE: node_graph
-  const int32_t* part;          // EDGE: partial-row id per edge
-  float* agg_part;              // EDGE out: [n_parts][H] per-32-row-block partial receiver sums
-  const float* Pagg;            // NODE: [N][H] W_na . (edge aggregate)
-  float* h_out;                 // NODE: [N][H] block output h_v (for the node -> graph sum)
-};
 
 // ------------------------------------------------------------------ PTX helpers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -90,7 +68,16 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
-__device__ __forceinline__ void tc_mma(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+// One lane of a CONVERGED warp.  tcgen05.mma / commit take their operands from uniform registers; issuing
+// them from divergent code (if (lane == 0)) makes ptxas wrap every instruction in an ELECT/branch loop,
+// which costs ~2x the tensor-pipe time of a 128x128x16 UMMA (scratch/hwprobe.cu, T3).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+// D[tmem] (+)= A[smem] . B[smem]
+__device__ __forceinline__ void mma_ss(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
@@ -98,23 +85,51 @@ __device__ __forceinline__ void tc_mma(uint32_t d_tmem, uint64_t adesc, uint64_t
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
       : "memory");
 }
-// 32 lanes x 32 consecutive fp32 columns: thread i of the warp receives row (lane base + i)
-__device__ __forceinline__ void tc_ld32(uint32_t taddr, float* v) {
-  uint32_t r[32];
+// D[tmem] (+)= A[tmem, bf16 pairs packed per 32-bit column] . B[smem]
+__device__ __forceinline__ void mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
   asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,"
-      "%29,%30,%31}, [%32];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr)
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accum)
       : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-  for (int i = 0; i < 32; i++) v[i] = __uint_as_float(r[i]);
 }
+// 32 lanes x 32 consecutive fp32 columns: thread i of the warp receives row (lane base + i)
+#define TC_LD32(taddr, r)                                                                                             \
+  asm volatile(                                                                                                       \
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "                                                                       \
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,"   \
+      "%29,%30,%31}, [%32];"                                                                                          \
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),   \
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),        \
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),       \
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])                     \
+      : "r"(taddr)                                                                                                    \
+      : "memory")
+// 16 lanes x 64 fp32 columns in the accumulator-fragment layout (verified by scratch/hwprobe.cu, T1):
+//   r[4n + 2h + c] of lane l = TMEM[lane base + l/4 + 8h][col base + 8n + 2(l%4) + c]
+// four consecutive lanes cover one 32-byte sector of a row: sector-exact global loads / stores from registers.
+#define TC_LD_FRAG64(taddr, r)                                                                                        \
+  asm volatile(                                                                                                       \
+      "tcgen05.ld.sync.aligned.16x256b.x8.b32 "                                                                       \
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,"   \
+      "%29,%30,%31}, [%32];"                                                                                          \
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),   \
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),        \
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),       \
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])                     \
+      : "r"(taddr)                                                                                                    \
+      : "memory")
+// 32 lanes x 16 columns store (thread i writes row lane base + i)
+#define TC_ST16(taddr, r)                                                                                             \
+  asm volatile(                                                                                                       \
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%16], {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15};" ::"r"( \
+          r[0]),                                                                                                      \
+      "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]),  \
+      "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(taddr)                                          \
+      : "memory")
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tc_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 // K-major, 128B-swizzled shared-memory matrix descriptor (cute::UMMA::SmemDescriptor layout):
 // start address >> 4 | LBO (unused for swizzled K-major, 1) | SBO = 1024 B between 8-row groups |
@@ -150,27 +165,38 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&t);
 }
+__device__ __forceinline__ float4 f4add(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
+__device__ __forceinline__ float4 f4zero() { return make_float4(0.f, 0.f, 0.f, 0.f); }
 
-// issue one 128x128x128 block: 8 UMMAs of K=16
-__device__ __forceinline__ void issue_block(uint32_t d_tmem, uint32_t a_base, uint32_t b_base, bool accumulate) {
+// one 128x128x128 block = 8 UMMAs of K=16; A block = two 64-wide K halves 16 KB apart, B = two ring stages.
+// Call from ONE elected lane of a converged warp.
+__device__ __forceinline__ void issue_ss(uint32_t d_tmem, uint64_t adesc, uint64_t w0, uint64_t w1, bool accumulate) {
 #pragma unroll
-  for (int ks = 0; ks < 8; ks++) {
-    uint32_t off = (uint32_t)((ks >> 2) * KB_BYTES + (ks & 3) * 32);
-    tc_mma(d_tmem, umma_desc(a_base + off), umma_desc(b_base + off), IDESC, (accumulate || ks > 0) ? 1u : 0u);
-  }
+  for (int ks = 0; ks < 4; ks++) mma_ss(d_tmem, adesc + 2 * ks, w0 + 2 * ks, IDESC, (accumulate || ks > 0) ? 1u : 0u);
+#pragma unroll
+  for (int ks = 0; ks < 4; ks++) mma_ss(d_tmem, adesc + (KB_BYTES >> 4) + 2 * ks, w1 + 2 * ks, IDESC, 1u);
+}
+// A operand in TMEM: bf16 pairs, 8 columns per K=16 step
+__device__ __forceinline__ void issue_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t w0, uint64_t w1, bool accumulate) {
+#pragma unroll
+  for (int ks = 0; ks < 4; ks++) mma_ts(d_tmem, a_tmem + 8 * ks, w0 + 2 * ks, IDESC, (accumulate || ks > 0) ? 1u : 0u);
+#pragma unroll
+  for (int ks = 0; ks < 4; ks++) mma_ts(d_tmem, a_tmem + 32 + 8 * ks, w1 + 2 * ks, IDESC, 1u);
 }
 
 // =====================================================================================================
 // Projection kernel: out = A . W for 1 or 2 weight blocks (N = 128 or 256), fp32 out.
 //   SRC_LN : A = LayerNorm-normalised rows of x (affine folded into W)   -> P_s | P_r of the nodes
-//   SRC_AGG: A = per-node edge aggregate (ordered sum of its partial rows) -> W_na . agg
+//   SRC_AGG: A = ordered sum of the partial rows [part_ptr[r], part_ptr[r+1]) of x (part_ptr == nullptr: row r
+//            itself); `addend` (optional, [R][H]) is added to the single-block output
 // 6 warps: 0-3 prologue/epilogue, 4 MMA issuer, 5 weight loader.  One 128-row tile per iteration.
 // =====================================================================================================
 enum { SRC_LN = 0, SRC_AGG = 1 };
 
 struct ProjArgs {
   const float* x;                 // SRC_LN: [R][H];  SRC_AGG: partial rows [n_parts][H]
-  const int32_t* part_ptr;        // SRC_AGG: [R+1]
+  const int32_t* part_ptr;        // SRC_AGG: [R+1] or nullptr
+  const float* addend;            // optional [R][H] (nblk == 1)
   float* out;                     // [R][nblk*H]
   int64_t R;
   int num_tiles;
@@ -214,95 +240,112 @@ __global__ void __launch_bounds__(192, 1) k_tc_proj(const ProjArgs a) {
 
   if (warp == 5) {
     // the (at most 2) weight blocks stay resident in shared memory for the whole kernel
-    if (lane == 0) {
+    if (elect_one()) {
       for (int b = 0; b < a.nblk; b++) {
         mbar_expect_tx(BAR(PB_WFULL + b), BLK_BYTES);
         bulk_g2s(sW + b * BLK_BYTES, reinterpret_cast<const uint8_t*>(a.wpack) + (size_t)b * BLK_BYTES, BLK_BYTES, BAR(PB_WFULL + b));
       }
     }
+    __syncwarp();
   } else if (warp == 4) {
-    if (lane == 0) {
-      uint32_t tl = 0;
-      for (int b = 0; b < a.nblk; b++) mbar_wait(BAR(PB_WFULL + b), 0);
-      for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, tl++) {
-        mbar_wait(BAR(PB_AREADY), tl & 1);
-        mbar_wait(BAR(PB_ACCFREE), (tl & 1) ^ 1);
-        tc_fence_after();
-        for (int b = 0; b < a.nblk; b++) issue_block(tmem + 128 * b, sA, sW + b * BLK_BYTES, false);
+    uint32_t tl = 0;
+    for (int b = 0; b < a.nblk; b++) mbar_wait(BAR(PB_WFULL + b), 0);
+    const uint64_t adesc = umma_desc(sA);
+    for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, tl++) {
+      mbar_wait(BAR(PB_AREADY), tl & 1);
+      mbar_wait(BAR(PB_ACCFREE), (tl & 1) ^ 1);
+      tc_fence_after();
+      if (elect_one()) {
+        for (int b = 0; b < a.nblk; b++) {
+          const uint64_t w = umma_desc(sW + b * BLK_BYTES);
+          issue_ss(tmem + 128 * b, adesc, w, w + (KB_BYTES >> 4), false);
+        }
         tc_commit(BAR(PB_OUTDONE));
       }
+      __syncwarp();
     }
   } else {
-    const int t = tid;
     const uint32_t lane_base = ((uint32_t)(warp * 32)) << 16;
-    const int l8 = lane & 7, rsub = lane >> 3;
     uint32_t tl = 0;
     for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, tl++) {
       const int64_t row0 = (int64_t)tile * TM;
       const int rows = (int)((a.R - row0) < TM ? (a.R - row0) : TM);
+      const int wrows = rows - warp * 32 < 0 ? 0 : (rows - warp * 32 > 32 ? 32 : rows - warp * 32);
       if (tl > 0) mbar_wait(BAR(PB_OUTDONE), (tl - 1) & 1);   // previous MMAs have finished reading A
+      // 32 lanes per row (512 B, fully coalesced), 4 rows in flight
       if (SRC == SRC_LN) {
-        // 8 lanes per row, 4 rows per warp step: every load instruction covers full 128 B lines
-#pragma unroll 2
-        for (int i = 0; i < 8; i++) {
-          const int r = warp * 32 + i * 4 + rsub;
+#pragma unroll 1
+        for (int i0 = 0; i0 < 32; i0 += 4) {
           float4 v[4];
-          const float4* xr = reinterpret_cast<const float4*>(a.x + (size_t)(row0 + r) * H) + l8;
 #pragma unroll
-          for (int j = 0; j < 4; j++) v[j] = (r < rows) ? __ldg(xr + 8 * j) : make_float4(0.f, 0.f, 0.f, 0.f);
-          float s = 0.f;
+          for (int u = 0; u < 4; u++)
+            v[u] = (i0 + u < wrows) ? __ldg(reinterpret_cast<const float4*>(a.x + (size_t)(row0 + warp * 32 + i0 + u) * H) + lane) : f4zero();
 #pragma unroll
-          for (int j = 0; j < 4; j++) s += (v[j].x + v[j].y) + (v[j].z + v[j].w);
-          s += __shfl_xor_sync(0xffffffffu, s, 1); s += __shfl_xor_sync(0xffffffffu, s, 2); s += __shfl_xor_sync(0xffffffffu, s, 4);
-          const float mu = s * (1.0f / H);
-          float q = 0.f;
-#pragma unroll
-          for (int j = 0; j < 4; j++) {
-            v[j].x -= mu; v[j].y -= mu; v[j].z -= mu; v[j].w -= mu;
-            q += (v[j].x * v[j].x + v[j].y * v[j].y) + (v[j].z * v[j].z + v[j].w * v[j].w);
-          }
-          q += __shfl_xor_sync(0xffffffffu, q, 1); q += __shfl_xor_sync(0xffffffffu, q, 2); q += __shfl_xor_sync(0xffffffffu, q, 4);
-          const float rs = (r < rows) ? ln_rstd(q * (1.0f / H), a.eps, a.eps_mode) : 0.f;
-#pragma unroll
-          for (int j = 0; j < 4; j++) {
+          for (int u = 0; u < 4; u++) {
+            const int r = warp * 32 + i0 + u;
+            const float mu = warp_sum((v[u].x + v[u].y) + (v[u].z + v[u].w)) * (1.0f / H);
+            const float dx = v[u].x - mu, dy = v[u].y - mu, dz = v[u].z - mu, dw = v[u].w - mu;
+            const float var = warp_sum((dx * dx + dy * dy) + (dz * dz + dw * dw)) * (1.0f / H);
+            const float rs = (i0 + u < wrows) ? ln_rstd(var, a.eps, a.eps_mode) : 0.f;
             uint2 pk;
-            pk.x = pack_bf16(v[j].x * rs, v[j].y * rs);
-            pk.y = pack_bf16(v[j].z * rs, v[j].w * rs);
-            *reinterpret_cast<uint2*>(sm + PJ_OFF_A + sw_off(r, 32 * j + 4 * l8)) = pk;
+            pk.x = pack_bf16(dx * rs, dy * rs);
+            pk.y = pack_bf16(dz * rs, dw * rs);
+            *reinterpret_cast<uint2*>(sm + PJ_OFF_A + sw_off(r, 4 * lane)) = pk;
           }
         }
       } else {
+        int p0 = 0, p1 = 0;
+        if (lane < wrows) {
+          const int64_t r = row0 + warp * 32 + lane;
+          if (a.part_ptr) { p0 = a.part_ptr[r]; p1 = a.part_ptr[r + 1]; }
+          else { p0 = (int)r; p1 = (int)r + 1; }
+        }
 #pragma unroll 1
-        for (int i = 0; i < 32; i++) {
-          const int r = warp * 32 + i;
-          float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (r < rows) {
-            const int p0 = a.part_ptr[row0 + r], p1 = a.part_ptr[row0 + r + 1];
-            for (int p = p0; p < p1; p++) {
-              const float4 q = __ldg(reinterpret_cast<const float4*>(a.x + (size_t)p * H) + lane);
-              s.x += q.x; s.y += q.y; s.z += q.z; s.w += q.w;
-            }
+        for (int i0 = 0; i0 < 32; i0 += 4) {
+          float4 s[4];
+          int q0[4], q1[4];
+#pragma unroll
+          for (int u = 0; u < 4; u++) {
+            q0[u] = __shfl_sync(0xffffffffu, p0, i0 + u);
+            q1[u] = __shfl_sync(0xffffffffu, p1, i0 + u);
+            s[u] = (q0[u] < q1[u]) ? __ldg(reinterpret_cast<const float4*>(a.x + (size_t)q0[u] * H) + lane) : f4zero();
           }
-          uint2 pk;
-          pk.x = pack_bf16(s.x, s.y);
-          pk.y = pack_bf16(s.z, s.w);
-          *reinterpret_cast<uint2*>(sm + PJ_OFF_A + sw_off(r, lane * 4)) = pk;
+#pragma unroll
+          for (int u = 0; u < 4; u++) {
+            for (int p = q0[u] + 1; p < q1[u]; p++) s[u] = f4add(s[u], __ldg(reinterpret_cast<const float4*>(a.x + (size_t)p * H) + lane));
+            uint2 pk;
+            pk.x = pack_bf16(s[u].x, s[u].y);
+            pk.y = pack_bf16(s[u].z, s[u].w);
+            *reinterpret_cast<uint2*>(sm + PJ_OFF_A + sw_off(warp * 32 + i0 + u, 4 * lane)) = pk;
+          }
         }
       }
       fence_async_smem();
       mbar_arrive(BAR(PB_AREADY));
       mbar_wait(BAR(PB_OUTDONE), tl & 1);
       tc_fence_after();
-      const bool valid = t < rows;
+      // epilogue in the accumulator-fragment layout: every 4 lanes write one full 32 B sector
       const int ld = a.nblk * H;
+      const int q = lane >> 2, cq = 2 * (lane & 3);
 #pragma unroll 1
-      for (int j = 0; j < a.nblk * 4; j++) {
-        float v[32];
-        tc_ld32(tmem + 32 * j + lane_base, v);
-        if (valid) {
-          float4* o = reinterpret_cast<float4*>(a.out + (size_t)(row0 + t) * ld + j * 32);
+      for (int st = 0; st < 4 * a.nblk; st++) {
+        const int hh = st & 1, ch = st >> 1;
+        uint32_t d[32];
+        TC_LD_FRAG64(tmem + lane_base + ((uint32_t)(16 * hh) << 16) + 64 * ch, d);
+        tc_wait_ld();
 #pragma unroll
-          for (int q = 0; q < 8; q++) o[q] = make_float4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
+        for (int h2 = 0; h2 < 2; h2++) {
+          const int r = warp * 32 + 16 * hh + q + 8 * h2;
+          if (r < rows) {
+            float* o = a.out + (size_t)(row0 + r) * ld + 64 * ch + cq;
+            const float* ad = a.addend ? a.addend + (size_t)(row0 + r) * H + 64 * ch + cq : nullptr;
+#pragma unroll
+            for (int n = 0; n < 8; n++) {
+              float2 v = make_float2(__uint_as_float(d[4 * n + 2 * h2]), __uint_as_float(d[4 * n + 2 * h2 + 1]));
+              if (ad) { const float2 t = *reinterpret_cast<const float2*>(ad + 8 * n); v.x += t.x; v.y += t.y; }
+              *reinterpret_cast<float2*>(o + 8 * n) = v;
+            }
+          }
         }
       }
       tc_fence_before();
@@ -315,284 +358,346 @@ __global__ void __launch_bounds__(192, 1) k_tc_proj(const ProjArgs a) {
 }
 
 // =====================================================================================================
-// Fused GNCore kernel for edges (MODE_EDGE) and nodes (MODE_NODE).
-// A CTA owns a PAIR of 128-row sub-tiles that run in lock step, so every streamed weight block feeds
-// two UMMA tiles (halves the L2 -> SMEM weight traffic).  10 warps:
-//   warps 0-3 : compute group of sub-tile 0      warps 4-7 : compute group of sub-tile 1
-//   warp  8   : MMA issuer (one thread)          warp  9   : weight loader (one thread)
-// TMEM per sub-tile s: D_s   (cols 256s .. +127)      FFN output accumulator
-//                      Hd_s  (cols 256s+128 .. +127)  FFN hidden chunk, finally the GNBlock GEMM D_blk
-// Block order per pair: W1_0 W2_0 W1_1 W2_1 W1_2 W2_2 W1_3 W2_3 W_blk, each block used by s = 0 then 1.
+// Fused GNCore kernel for edges (MODE_EDGE) and nodes (MODE_NODE); see the file header.
+// Weight block order per pair, each block used by sub-tile 0 then 1:
+//   EDGE: W1_0  W_blk  W2_0  W1_1  W2_1  W1_2  W2_2  W1_3  W2_3      (W_blk accumulates into D)
+//   NODE: W1_0  W2_0  W1_1  W2_1  W1_2  W2_2  W1_3  W2_3  W_blk      (W_blk -> Hd: the block output h_v is needed
+//                                                                     separately for the node -> graph sum)
 // =====================================================================================================
+struct CoreArgs {
+  const float* x;   // [R][H] rows (input features of this entity kind)
+  float* y;         // [R][H] core output
+  int64_t R;
+  int num_tiles;
+  const __nv_bfloat16* wpack;   // weight blocks in consumption order
+  const float* b1f;             // [4H] FFN bias with the LN2 shift folded in
+  const float* b2;              // [H]
+  float eps;
+  int eps_mode;
+  const float* Pu;              // [B][H] per-graph row (graph projection + every folded bias)
+  const int32_t* gid;           // EDGE: edge_graph, NODE: node_graph
+  // EDGE
+  const float* Psr;             // [N][2H] sender (cols 0..H) / receiver (cols H..2H) projections
+  const int32_t* src;
+  const int32_t* dst;
+  const int32_t* part;          // partial-row id per edge (32-row blocks, receiver runs)
+  float* Epart;                 // out [n_parts][H] partial sums of the normalised edge rows
+  float* Gpart;                 // out [n_parts][H] partial sums of the gathered addends Ps+Pr+Pu
+  // NODE
+  const float* Pagg;            // [N][H] W_na . (edge aggregate)
+  float* h_out;                 // [N][H] block output h_v
+};
+
 constexpr int HALF_BYTES = KB_BYTES;     // weight ring stage = one 64-wide K half of a block (16 KB)
 constexpr int NWS = 5;                   // ring stages
-constexpr int P_OFF_A = 0;                          // A_s: s * 32 KB
-constexpr int P_OFF_H = 2 * BLK_BYTES;              // Hs_s (hidden chunk bf16; epilogue staging)
-constexpr int P_OFF_W = 4 * BLK_BYTES;
-constexpr int P_OFF_MISC = P_OFF_W + NWS * HALF_BYTES;
-// misc: b1f[512] b2[128] seg masks[8] seg pid0[8] barriers[32] tmem slot
-constexpr int P_MISC = 512 * 4 + 128 * 4 + 8 * 4 + 8 * 4 + 32 * 8 + 16;
-constexpr int P_SMEM = P_OFF_MISC + P_MISC + 1024;
-enum { QB_WFULL = 0, QB_WEMPTY = 5, QB_AREADY = 10, QB_ACCFREE = 12, QB_HIDFULL = 14, QB_HSREADY = 16, QB_HSFREE = 18, QB_OUTDONE = 20 };
-
-// 4 UMMAs (K = 64): one 16 KB half block
-__device__ __forceinline__ void issue_half(uint32_t d_tmem, uint32_t a_half, uint32_t b_half, bool accumulate) {
-#pragma unroll
-  for (int ks = 0; ks < 4; ks++)
-    tc_mma(d_tmem, umma_desc(a_half + ks * 32), umma_desc(b_half + ks * 32), IDESC, (accumulate || ks > 0) ? 1u : 0u);
-}
+constexpr int C_OFF_A = 0;                           // [stage 2][sub-tile 2] x 32 KB
+constexpr int C_OFF_W = 4 * BLK_BYTES;
+constexpr int C_OFF_MISC = C_OFF_W + NWS * HALF_BYTES;
+constexpr int C_MISC = 512 * 4 + 32 * 8 + 16;        // b1f[512], barriers[32], tmem slot
+constexpr int C_SMEM = C_OFF_MISC + C_MISC + 1024;
+constexpr int C_THREADS = 18 * 32;
+enum { CB_WFULL = 0, CB_WEMPTY = 5, CB_AFULL = 10, CB_AEMPTY = 14, CB_HIDFULL = 18, CB_HSREADY = 20, CB_OUTDONE = 22, CB_ACCFREE = 24 };
 
 template <int MODE>
-__global__ void __launch_bounds__(320, 1) k_tc_pair(const TcArgs a) {
+__global__ void __launch_bounds__(C_THREADS, 1) k_core(const CoreArgs a) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
   uint8_t* sm = smem_raw + (base - raw);
-  const uint32_t sW = base + P_OFF_W;
-  float* sB1 = reinterpret_cast<float*>(sm + P_OFF_MISC);
-  float* sB2 = sB1 + 512;
-  uint32_t* sMask = reinterpret_cast<uint32_t*>(sB2 + 128);   // [2][4] segment-end bit masks of 32-row blocks
-  int* sPid0 = reinterpret_cast<int*>(sMask + 8);             // [2][4] first partial-row id of each 32-row block
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sPid0 + 8);
+  const uint32_t sW = base + C_OFF_W;
+  float* sB1 = reinterpret_cast<float*>(sm + C_OFF_MISC);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sB1 + 512);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 32);
   const uint32_t bar0 = smem_u32(bars);
   auto BAR = [&](int i) { return bar0 + 8u * (uint32_t)i; };
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
   if (tid == 0) {
-    for (int i = 0; i < NWS; i++) { mbar_init(BAR(QB_WFULL + i), 1); mbar_init(BAR(QB_WEMPTY + i), 1); }
+    for (int i = 0; i < NWS; i++) { mbar_init(BAR(CB_WFULL + i), 1); mbar_init(BAR(CB_WEMPTY + i), 1); }
+    for (int i = 0; i < 4; i++) { mbar_init(BAR(CB_AFULL + i), 128); mbar_init(BAR(CB_AEMPTY + i), 1); }
     for (int s = 0; s < 2; s++) {
-      mbar_init(BAR(QB_AREADY + s), 128); mbar_init(BAR(QB_ACCFREE + s), 128);
-      mbar_init(BAR(QB_HIDFULL + s), 1); mbar_init(BAR(QB_HSREADY + s), 128);
-      mbar_init(BAR(QB_HSFREE + s), 1); mbar_init(BAR(QB_OUTDONE + s), 1);
+      mbar_init(BAR(CB_HIDFULL + s), 1); mbar_init(BAR(CB_HSREADY + s), 128);
+      mbar_init(BAR(CB_OUTDONE + s), 1); mbar_init(BAR(CB_ACCFREE + s), 128);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 8) {
+  if (warp == 16) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
-  for (int i = tid; i < 512; i += 320) sB1[i] = a.b1f[i];
-  for (int i = tid; i < 128; i += 320) sB2[i] = a.b2[i];
+  for (int i = tid; i < 512; i += C_THREADS) sB1[i] = a.b1f[i];
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
   const int num_pairs = (a.num_tiles + 1) >> 1;
 
-  if (warp == 9) {
+  if (warp == 17) {
     // ===================================================== weight loader
-    if (lane == 0) {
-      uint32_t it = 0;
-      for (int pair = blockIdx.x; pair < num_pairs; pair += gridDim.x) {
-        for (int hb = 0; hb < 18; hb++, it++) {
-          const uint32_t st = it % NWS, ph = (it / NWS) & 1;
-          mbar_wait(BAR(QB_WEMPTY + st), ph ^ 1);
-          mbar_expect_tx(BAR(QB_WFULL + st), HALF_BYTES);
+    uint32_t it = 0;
+    for (int pair = blockIdx.x; pair < num_pairs; pair += gridDim.x) {
+      for (int hb = 0; hb < 18; hb++, it++) {
+        const uint32_t st = it % NWS, ph = (it / NWS) & 1;
+        mbar_wait(BAR(CB_WEMPTY + st), ph ^ 1);
+        if (elect_one()) {
+          mbar_expect_tx(BAR(CB_WFULL + st), HALF_BYTES);
           bulk_g2s(sW + st * HALF_BYTES, reinterpret_cast<const uint8_t*>(a.wpack) + (size_t)hb * HALF_BYTES, HALF_BYTES,
-                   BAR(QB_WFULL + st));
+                   BAR(CB_WFULL + st));
         }
+        __syncwarp();
       }
     }
-  } else if (warp == 8) {
-    // ===================================================== MMA issuer
-    if (lane == 0) {
-      uint32_t it = 0, tl = 0;
-      for (int pair = blockIdx.x; pair < num_pairs; pair += gridDim.x, tl++) {
-        for (int b = 0; b < 9; b++) {
-          const uint32_t st0 = it % NWS, ph0 = (it / NWS) & 1;
-          const uint32_t st1 = (it + 1) % NWS, ph1 = ((it + 1) / NWS) & 1;
-          it += 2;
-          mbar_wait(BAR(QB_WFULL + st0), ph0);
-          mbar_wait(BAR(QB_WFULL + st1), ph1);
-          const uint32_t w0 = sW + st0 * HALF_BYTES, w1 = sW + st1 * HALF_BYTES;
-          const int c = b >> 1;
-          for (int s = 0; s < 2; s++) {
-            const uint32_t A_s = base + P_OFF_A + s * BLK_BYTES, H_s = base + P_OFF_H + s * BLK_BYTES;
-            const uint32_t D_s = tmem + 256 * s, Hd_s = D_s + 128;
-            if (b == 0) {
-              mbar_wait(BAR(QB_AREADY + s), tl & 1);
-              mbar_wait(BAR(QB_ACCFREE + s), (tl & 1) ^ 1);
-              tc_fence_after();
-            }
-            if (b == 8) {                 // D_blk = A . W_blk  (into the drained hidden columns)
-              issue_half(Hd_s, A_s, w0, false);
-              issue_half(Hd_s, A_s + KB_BYTES, w1, true);
-              tc_commit(BAR(QB_OUTDONE + s));
-            } else if ((b & 1) == 0) {    // hidden chunk c = A . W1_c
-              issue_half(Hd_s, A_s, w0, false);
-              issue_half(Hd_s, A_s + KB_BYTES, w1, true);
-              tc_commit(BAR(QB_HIDFULL + s));
-            } else {                      // D_s += relu(hidden chunk c) . W2_c
-              mbar_wait(BAR(QB_HSREADY + s), c & 1);
-              tc_fence_after();
-              issue_half(D_s, H_s, w0, c > 0);
-              issue_half(D_s, H_s + KB_BYTES, w1, true);
-              if (c < 3) tc_commit(BAR(QB_HSFREE + s));
+  } else if (warp == 16) {
+    // ===================================================== MMA issuer (whole warp converged, one lane issues)
+    uint32_t it = 0, tl = 0;
+    for (int pair = blockIdx.x; pair < num_pairs; pair += gridDim.x, tl++) {
+      const uint32_t stage = tl & 1, aph = (tl >> 1) & 1;
+#pragma unroll 1
+      for (int b = 0; b < 9; b++) {
+        const uint32_t st0 = it % NWS, ph0 = (it / NWS) & 1;
+        const uint32_t st1 = (it + 1) % NWS, ph1 = ((it + 1) / NWS) & 1;
+        it += 2;
+        // kind of this block: 0 = up-projection chunk c, 1 = down-projection chunk c, 2 = GNBlock GEMM
+        int kind, c;
+        if (MODE == MODE_EDGE) {
+          if (b == 0) { kind = 0; c = 0; }
+          else if (b == 1) { kind = 2; c = 0; }
+          else { kind = (b & 1) ? 0 : 1; c = (b & 1) ? (b - 1) >> 1 : (b - 2) >> 1; }
+        } else {
+          if (b == 8) { kind = 2; c = 0; }
+          else { kind = b & 1; c = b >> 1; }
+        }
+        mbar_wait(BAR(CB_WFULL + st0), ph0);
+        mbar_wait(BAR(CB_WFULL + st1), ph1);
+        const uint64_t w0 = umma_desc(sW + st0 * HALF_BYTES), w1 = umma_desc(sW + st1 * HALF_BYTES);
+#pragma unroll
+        for (int s = 0; s < 2; s++) {
+          const uint64_t adesc = umma_desc(base + C_OFF_A + (stage * 2 + s) * BLK_BYTES);
+          const uint32_t D_s = tmem + 256 * s, Hd_s = D_s + 128;
+          if (b == 0) {
+            mbar_wait(BAR(CB_AFULL + stage * 2 + s), aph);
+            if (MODE == MODE_NODE) mbar_wait(BAR(CB_ACCFREE + s), (tl & 1) ^ 1);   // Hd still holds the previous h_v
+          }
+          if (MODE == MODE_EDGE && kind == 2) mbar_wait(BAR(CB_ACCFREE + s), (tl & 1) ^ 1);
+          if (kind == 1) mbar_wait(BAR(CB_HSREADY + s), c & 1);
+          tc_fence_after();
+          if (elect_one()) {
+            if (kind == 0) {
+              issue_ss(Hd_s, adesc, w0, w1, false);
+              tc_commit(BAR(CB_HIDFULL + s));
+              if (MODE == MODE_EDGE && c == 3) tc_commit(BAR(CB_AEMPTY + stage * 2 + s));
+            } else if (kind == 1) {
+              issue_ts(D_s, Hd_s, w0, w1, MODE == MODE_EDGE ? true : c > 0);
+              if (MODE == MODE_EDGE && c == 3) tc_commit(BAR(CB_OUTDONE + s));
+            } else {
+              if (MODE == MODE_EDGE) {
+                issue_ss(D_s, adesc, w0, w1, false);
+              } else {
+                issue_ss(Hd_s, adesc, w0, w1, false);
+                tc_commit(BAR(CB_AEMPTY + stage * 2 + s));
+                tc_commit(BAR(CB_OUTDONE + s));
+              }
             }
           }
-          tc_commit(BAR(QB_WEMPTY + st0));
-          tc_commit(BAR(QB_WEMPTY + st1));
+          __syncwarp();
         }
+        if (elect_one()) {
+          tc_commit(BAR(CB_WEMPTY + st0));
+          tc_commit(BAR(CB_WEMPTY + st1));
+        }
+        __syncwarp();
       }
     }
-  } else {
-    // ===================================================== compute groups
-    const int s = warp >> 2;              // sub-tile of this group
-    const int w4 = warp & 3;              // warp within the group == TMEM lane quadrant
-    const int t = tid & 127;              // row of the sub-tile owned in thread-per-row phases
-    const uint32_t lane_base = ((uint32_t)(w4 * 32)) << 16;
-    const uint32_t D_s = tmem + 256 * s, Hd_s = D_s + 128;
-    uint8_t* A_s = sm + P_OFF_A + s * BLK_BYTES;
-    uint8_t* H_s = sm + P_OFF_H + s * BLK_BYTES;
-    float* S_h = reinterpret_cast<float*>(H_s);            // [128][32] fp32 staging (swizzled float4)
-    float* S_f = S_h + 128 * 32;
-    const int l8 = lane & 7, rsub = lane >> 3;
+  } else if (warp >= 8) {
+    // ===================================================== prologue warps, one pair ahead of the MMAs
+    const int pw = warp - 8, s = pw >> 2, q = pw & 3;
+    const float4 b2v = __ldg(reinterpret_cast<const float4*>(a.b2) + lane);
     uint32_t tl = 0;
     for (int pair = blockIdx.x; pair < num_pairs; pair += gridDim.x, tl++) {
-      const int64_t row0 = ((int64_t)pair * 2 + s) * TM;
-      int rows = (int)(a.R - row0);
-      rows = rows < 0 ? 0 : (rows > TM ? TM : rows);
-      // ---------------- prologue: LayerNorm -> bf16 A operand (8 lanes per row)
-#pragma unroll 2
-      for (int i = 0; i < 8; i++) {
-        const int r = w4 * 32 + i * 4 + rsub;
-        float4 v[4];
-        const float4* xr = reinterpret_cast<const float4*>(a.x + (size_t)(row0 + r) * H) + l8;
-#pragma unroll
-        for (int j = 0; j < 4; j++) v[j] = (r < rows) ? __ldg(xr + 8 * j) : make_float4(0.f, 0.f, 0.f, 0.f);
-        float sum = 0.f;
-#pragma unroll
-        for (int j = 0; j < 4; j++) sum += (v[j].x + v[j].y) + (v[j].z + v[j].w);
-        sum += __shfl_xor_sync(0xffffffffu, sum, 1); sum += __shfl_xor_sync(0xffffffffu, sum, 2); sum += __shfl_xor_sync(0xffffffffu, sum, 4);
-        const float mu = sum * (1.0f / H);
-        float q = 0.f;
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-          v[j].x -= mu; v[j].y -= mu; v[j].z -= mu; v[j].w -= mu;
-          q += (v[j].x * v[j].x + v[j].y * v[j].y) + (v[j].z * v[j].z + v[j].w * v[j].w);
-        }
-        q += __shfl_xor_sync(0xffffffffu, q, 1); q += __shfl_xor_sync(0xffffffffu, q, 2); q += __shfl_xor_sync(0xffffffffu, q, 4);
-        const float rs = (r < rows) ? ln_rstd(q * (1.0f / H), a.eps, a.eps_mode) : 0.f;
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-          uint2 pk;
-          pk.x = pack_bf16(v[j].x * rs, v[j].y * rs);
-          pk.y = pack_bf16(v[j].z * rs, v[j].w * rs);
-          *reinterpret_cast<uint2*>(A_s + sw_off(r, 32 * j + 4 * l8)) = pk;
-        }
+      const uint32_t stage = tl & 1, aph = (tl >> 1) & 1;
+      const int64_t row0 = ((int64_t)pair * 2 + s) * TM + 32 * q;   // first row of this warp's 32-row slice
+      const int64_t left = a.R - row0;
+      const int rows = left < 0 ? 0 : (left > 32 ? 32 : (int)left);
+      int my_src = 0, my_dst = 0, my_gid = 0, my_pid = -1;
+      if (lane < rows) {
+        my_gid = a.gid[row0 + lane];
+        if (MODE == MODE_EDGE) { my_src = a.src[row0 + lane]; my_dst = a.dst[row0 + lane]; my_pid = a.part[row0 + lane]; }
       }
+      uint32_t endmask = 0;
+      int pid = 0;
       if (MODE == MODE_EDGE) {
-        // segment structure of this warp's 32 rows: bit i set = row i closes a partial row
-        const int r = w4 * 32 + lane;
-        const int pid = (r < rows) ? a.part[row0 + r] : -1;
-        const int nxt = __shfl_down_sync(0xffffffffu, pid, 1);
-        const bool endb = (r < rows) && (lane == 31 || nxt != pid);
-        const uint32_t m = __ballot_sync(0xffffffffu, endb);
-        if (lane == 0) { sMask[s * 4 + w4] = m; sPid0[s * 4 + w4] = pid; }
+        const int nxt = __shfl_down_sync(0xffffffffu, my_pid, 1);
+        endmask = __ballot_sync(0xffffffffu, lane < rows && (lane == rows - 1 || nxt != my_pid));
+        pid = __shfl_sync(0xffffffffu, my_pid, 0);
+      }
+      mbar_wait(BAR(CB_AEMPTY + stage * 2 + s), aph ^ 1);
+      uint8_t* A = sm + C_OFF_A + (stage * 2 + s) * BLK_BYTES;
+      float4 acc_e = f4zero(), acc_g = f4zero();
+#pragma unroll 1
+      for (int i0 = 0; i0 < 32; i0 += 4) {
+        float4 xv[4], g[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+          const int i = i0 + u;
+          const int gi = __shfl_sync(0xffffffffu, my_gid, i);
+          if (MODE == MODE_EDGE) {
+            const int si = __shfl_sync(0xffffffffu, my_src, i), di = __shfl_sync(0xffffffffu, my_dst, i);
+            if (i < rows) {
+              xv[u] = __ldg(reinterpret_cast<const float4*>(a.x + (size_t)(row0 + i) * H) + lane);
+              const float4 ps = __ldg(reinterpret_cast<const float4*>(a.Psr + (size_t)si * (2 * H)) + lane);
+              const float4 pr = __ldg(reinterpret_cast<const float4*>(a.Psr + (size_t)di * (2 * H) + H) + lane);
+              const float4 pu = __ldg(reinterpret_cast<const float4*>(a.Pu + (size_t)gi * H) + lane);
+              g[u] = make_float4((ps.x + pr.x) + pu.x, (ps.y + pr.y) + pu.y, (ps.z + pr.z) + pu.z, (ps.w + pr.w) + pu.w);
+            } else { xv[u] = f4zero(); g[u] = f4zero(); }
+          } else {
+            if (i < rows) {
+              xv[u] = __ldg(reinterpret_cast<const float4*>(a.x + (size_t)(row0 + i) * H) + lane);
+              const float4 pa = __ldg(reinterpret_cast<const float4*>(a.Pagg + (size_t)(row0 + i) * H) + lane);
+              const float4 pu = __ldg(reinterpret_cast<const float4*>(a.Pu + (size_t)gi * H) + lane);
+              g[u] = f4add(pa, pu);
+            } else { xv[u] = f4zero(); g[u] = f4zero(); }
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+          const int i = i0 + u;
+          const float mu = warp_sum((xv[u].x + xv[u].y) + (xv[u].z + xv[u].w)) * (1.0f / H);
+          const float dx = xv[u].x - mu, dy = xv[u].y - mu, dz = xv[u].z - mu, dw = xv[u].w - mu;
+          const float var = warp_sum((dx * dx + dy * dy) + (dz * dz + dw * dw)) * (1.0f / H);
+          const float rs = (i < rows) ? ln_rstd(var, a.eps, a.eps_mode) : 0.f;
+          const float4 xh = make_float4(dx * rs, dy * rs, dz * rs, dw * rs);
+          uint2 pk;
+          pk.x = pack_bf16(xh.x, xh.y);
+          pk.y = pack_bf16(xh.z, xh.w);
+          *reinterpret_cast<uint2*>(A + sw_off(32 * q + i, 4 * lane)) = pk;
+          if (i < rows) {
+            // y0 = x + (gathered block addends) + b2 ; the epilogue adds the TMEM accumulator onto it
+            float4 y0 = make_float4((xv[u].x + g[u].x) + b2v.x, (xv[u].y + g[u].y) + b2v.y, (xv[u].z + g[u].z) + b2v.z,
+                                    (xv[u].w + g[u].w) + b2v.w);
+            *(reinterpret_cast<float4*>(a.y + (size_t)(row0 + i) * H) + lane) = y0;
+            if (MODE == MODE_NODE) {
+              *(reinterpret_cast<float4*>(a.h_out + (size_t)(row0 + i) * H) + lane) = g[u];
+            } else {
+              acc_e = f4add(acc_e, xh);
+              acc_g = f4add(acc_g, g[u]);
+              if ((endmask >> i) & 1u) {
+                *(reinterpret_cast<float4*>(a.Epart + (size_t)pid * H) + lane) = acc_e;
+                *(reinterpret_cast<float4*>(a.Gpart + (size_t)pid * H) + lane) = acc_g;
+                acc_e = f4zero(); acc_g = f4zero();
+                pid++;
+              }
+            }
+          }
+        }
       }
       fence_async_smem();
-      mbar_arrive(BAR(QB_AREADY + s));
-
-      // ---------------- FFN hidden chunks: TMEM -> +b1 -> relu -> bf16 -> swizzled smem A operand
+      mbar_arrive(BAR(CB_AFULL + stage * 2 + s));
+    }
+  } else {
+    // ===================================================== drain + epilogue groups
+    const int s = warp >> 2;              // sub-tile of this group
+    const int w4 = warp & 3;              // warp within the group == TMEM lane quadrant
+    const uint32_t lane_base = ((uint32_t)(w4 * 32)) << 16;
+    const uint32_t D_s = tmem + 256 * s, Hd_s = D_s + 128;
+    const int q = lane >> 2, cq = 2 * (lane & 3);
+    uint32_t tl = 0;
+    for (int pair = blockIdx.x; pair < num_pairs; pair += gridDim.x, tl++) {
+      const uint32_t stage = tl & 1, aph = (tl >> 1) & 1;
+      const int64_t row0 = ((int64_t)pair * 2 + s) * TM;
+      const int64_t left = a.R - row0;
+      const int rows = left < 0 ? 0 : (left > TM ? TM : (int)left);
+      // acquire the prologue's y0 (and h0) stores of this pair.  Waited here, before the MMAs can release the
+      // A stage, so the barrier cannot run two phases ahead of this wait.
+      mbar_wait(BAR(CB_AFULL + stage * 2 + s), aph);
+      // ---------------- FFN hidden chunks: TMEM fp32 -> +b1 -> relu -> bf16 pairs -> TMEM (in place)
 #pragma unroll 1
       for (int c = 0; c < 4; c++) {
-        mbar_wait(BAR(QB_HIDFULL + s), c & 1);
+        mbar_wait(BAR(CB_HIDFULL + s), c & 1);
         tc_fence_after();
-        if (c >= 1) mbar_wait(BAR(QB_HSFREE + s), (3 * tl + (c - 1)) & 1);
-#pragma unroll 1
+#pragma unroll
         for (int j = 0; j < 4; j++) {
-          float v[32];
-          tc_ld32(Hd_s + 32 * j + lane_base, v);
-          const float* bb = sB1 + c * 128 + j * 32;
+          uint32_t v[32], p[16];
+          TC_LD32(Hd_s + lane_base + 32 * j, v);
+          tc_wait_ld();
+          const float4* bb = reinterpret_cast<const float4*>(sB1 + c * 128 + j * 32);
 #pragma unroll
-          for (int q = 0; q < 4; q++) {
-            uint4 pk;
-            pk.x = pack_bf16_relu(v[q * 8 + 0] + bb[q * 8 + 0], v[q * 8 + 1] + bb[q * 8 + 1]);
-            pk.y = pack_bf16_relu(v[q * 8 + 2] + bb[q * 8 + 2], v[q * 8 + 3] + bb[q * 8 + 3]);
-            pk.z = pack_bf16_relu(v[q * 8 + 4] + bb[q * 8 + 4], v[q * 8 + 5] + bb[q * 8 + 5]);
-            pk.w = pack_bf16_relu(v[q * 8 + 6] + bb[q * 8 + 6], v[q * 8 + 7] + bb[q * 8 + 7]);
-            *reinterpret_cast<uint4*>(H_s + sw_off(t, j * 32 + q * 8)) = pk;
+          for (int t = 0; t < 8; t++) {
+            const float4 b = bb[t];
+            p[2 * t] = pack_bf16_relu(__uint_as_float(v[4 * t]) + b.x, __uint_as_float(v[4 * t + 1]) + b.y);
+            p[2 * t + 1] = pack_bf16_relu(__uint_as_float(v[4 * t + 2]) + b.z, __uint_as_float(v[4 * t + 3]) + b.w);
           }
+          TC_ST16(Hd_s + lane_base + 16 * j, p);   // columns [16j,16j+16) were read in iteration <= j
         }
+        tc_wait_st();
         tc_fence_before();
-        fence_async_smem();
-        mbar_arrive(BAR(QB_HSREADY + s));
+        mbar_arrive(BAR(CB_HSREADY + s));
       }
-
-      // ---------------- final epilogue, 32 columns at a time through the staging tiles
-      mbar_wait(BAR(QB_OUTDONE + s), tl & 1);
-      tc_fence_after();
-#pragma unroll 1
-      for (int qq = 0; qq < 4; qq++) {
-        {  // A: thread per row, TMEM -> staging (D_blk and FFN out + b2)
-          float v[32];
-          tc_ld32(Hd_s + 32 * qq + lane_base, v);
+      // ---------------- final epilogue: y = y0 + D (+ D_blk) in the accumulator-fragment layout.
+      // 8 sub-steps ss = (64-column half ch, 16-row half hh, 8-row half h2); a thread owns 8 float2 per sub-step.
+      float2 yb[2][8], hb[8];
+      uint32_t d[32], e[32];
+#define EPI_ROW(ss) (w4 * 32 + 16 * (((ss) >> 1) & 1) + q + 8 * ((ss) & 1))
+#define EPI_OFF(ss) ((size_t)(row0 + EPI_ROW(ss)) * H + 64 * ((ss) >> 2) + cq)
+      if (MODE == MODE_EDGE) {
+        if (EPI_ROW(0) < rows) {
 #pragma unroll
-          for (int q = 0; q < 8; q++)
-            *reinterpret_cast<float4*>(S_h + t * 32 + ((q ^ (t & 7)) << 2)) = make_float4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
-          tc_ld32(D_s + 32 * qq + lane_base, v);
-          const float* b2 = sB2 + 32 * qq;
-#pragma unroll
-          for (int q = 0; q < 8; q++)
-            *reinterpret_cast<float4*>(S_f + t * 32 + ((q ^ (t & 7)) << 2)) =
-                make_float4(v[q * 4] + b2[q * 4], v[q * 4 + 1] + b2[q * 4 + 1], v[q * 4 + 2] + b2[q * 4 + 2], v[q * 4 + 3] + b2[q * 4 + 3]);
+          for (int n = 0; n < 8; n++) yb[0][n] = __ldcg(reinterpret_cast<const float2*>(a.y + EPI_OFF(0) + 8 * n));
         }
-        __syncwarp();   // every epilogue step touches only this warp's own 32 rows
-        // C: 8 lanes per row (full 128 B lines): gathers + residual, coalesced y store
-#pragma unroll 2
-        for (int i = 0; i < 8; i++) {
-          const int r = w4 * 32 + i * 4 + rsub;
-          if (r < rows) {
-            const size_t grow = (size_t)(row0 + r);
-            const int col = 32 * qq + 4 * l8;
-            const int sidx = r * 32 + ((l8 ^ (r & 7)) << 2);
-            float4 h = *reinterpret_cast<const float4*>(S_h + sidx);
-            const float4 f = *reinterpret_cast<const float4*>(S_f + sidx);
-            const float4 xv = __ldg(reinterpret_cast<const float4*>(a.x + grow * H + col));
-            const float4 pu = __ldg(reinterpret_cast<const float4*>(a.Pu + (size_t)a.gid[grow] * H + col));
-            if (MODE == MODE_EDGE) {
-              const float4 ps = __ldg(reinterpret_cast<const float4*>(a.Psr + (size_t)a.src[grow] * (2 * H) + col));
-              const float4 pr = __ldg(reinterpret_cast<const float4*>(a.Psr + (size_t)a.dst[grow] * (2 * H) + H + col));
-              h.x += (ps.x + pr.x) + pu.x; h.y += (ps.y + pr.y) + pu.y; h.z += (ps.z + pr.z) + pu.z; h.w += (ps.w + pr.w) + pu.w;
-              *reinterpret_cast<float4*>(S_h + sidx) = h;
-            } else {
-              const float4 pa = __ldg(reinterpret_cast<const float4*>(a.Pagg + grow * H + col));
-              h.x += pa.x + pu.x; h.y += pa.y + pu.y; h.z += pa.z + pu.z; h.w += pa.w + pu.w;
-              *reinterpret_cast<float4*>(a.h_out + grow * H + col) = h;
-            }
-            float4 y;
-            y.x = (xv.x + h.x) + f.x; y.y = (xv.y + h.y) + f.y; y.z = (xv.z + h.z) + f.z; y.w = (xv.w + h.w) + f.w;
-            *reinterpret_cast<float4*>(a.y + grow * H + col) = y;
-          }
+      }
+      mbar_wait(BAR(CB_OUTDONE + s), tl & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int ss = 0; ss < 8; ss++) {
+        const int h2 = ss & 1;
+        const bool valid = EPI_ROW(ss) < rows;
+        if (h2 == 0) {
+          const uint32_t toff = lane_base + ((uint32_t)(16 * ((ss >> 1) & 1)) << 16) + 64 * (ss >> 2);
+          TC_LD_FRAG64(D_s + toff, d);
+          if (MODE == MODE_NODE) TC_LD_FRAG64(Hd_s + toff, e);
         }
         if (MODE == MODE_EDGE) {
-          __syncwarp();   // every epilogue step touches only this warp's own 32 rows
-          // E: edge -> receiver segmented sum; thread = (column lane, 32-row block w4), rows in order
-          uint32_t m = sMask[s * 4 + w4];
-          int pid = sPid0[s * 4 + w4];
-          float acc = 0.f;
-          const int cc = lane >> 2, cw = lane & 3;
-#pragma unroll 8
-          for (int i = 0; i < 32; i++) {
-            const int r = w4 * 32 + i;
-            acc += S_h[r * 32 + (((cc ^ (r & 7)) << 2) | cw)];
-            if ((m >> i) & 1u) {
-              a.agg_part[(size_t)pid * H + 32 * qq + lane] = acc;
-              acc = 0.f;
-              pid++;
-            }
+          if (ss < 7 && EPI_ROW(ss + 1) < rows) {
+#pragma unroll
+            for (int n = 0; n < 8; n++) yb[(ss + 1) & 1][n] = __ldcg(reinterpret_cast<const float2*>(a.y + EPI_OFF(ss + 1) + 8 * n));
+          }
+        } else if (valid) {
+#pragma unroll
+          for (int n = 0; n < 8; n++) {
+            yb[0][n] = __ldcg(reinterpret_cast<const float2*>(a.y + EPI_OFF(ss) + 8 * n));
+            hb[n] = __ldcg(reinterpret_cast<const float2*>(a.h_out + EPI_OFF(ss) + 8 * n));
           }
         }
-        __syncwarp();   // every epilogue step touches only this warp's own 32 rows
+        if (h2 == 0) {
+          tc_wait_ld();
+          if (ss == 6) {   // TMEM fully read: release the accumulators to the next pair's MMAs
+            tc_fence_before();
+            mbar_arrive(BAR(CB_ACCFREE + s));
+          }
+        }
+        if (valid) {
+#pragma unroll
+          for (int n = 0; n < 8; n++) {
+            float2 yv = yb[MODE == MODE_EDGE ? (ss & 1) : 0][n];
+            float dx = __uint_as_float(d[4 * n + 2 * h2]), dy = __uint_as_float(d[4 * n + 2 * h2 + 1]);
+            if (MODE == MODE_NODE) {
+              const float bx = __uint_as_float(e[4 * n + 2 * h2]), by = __uint_as_float(e[4 * n + 2 * h2 + 1]);
+              float2 hv = hb[n];
+              hv.x += bx; hv.y += by;
+              *reinterpret_cast<float2*>(a.h_out + EPI_OFF(ss) + 8 * n) = hv;
+              dx += bx; dy += by;
+            }
+            yv.x += dx; yv.y += dy;
+            *reinterpret_cast<float2*>(a.y + EPI_OFF(ss) + 8 * n) = yv;
+          }
+        }
       }
-      tc_fence_before();
-      mbar_arrive(BAR(QB_ACCFREE + s));
+#undef EPI_ROW
+#undef EPI_OFF
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 8) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+  if (warp == 16) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
 }
 
 // ------------------------------------------------------------------ weight packing
@@ -622,7 +727,7 @@ __global__ void k_fold_bias(const float* __restrict__ W, int ldw, int n0, int k0
 struct TcCorePack {
   __nv_bfloat16* w = nullptr;   // [proj 2 | aggproj 1 | edge 9 | node 9] blocks of 32 KB
   float* f = nullptr;           // folded fp32 vectors: cu_e[128] cu_n[128] b1f_e[512] b1f_n[512]
-  const __nv_bfloat16 *w_proj, *w_agg, *w_edge, *w_node;
+  const __nv_bfloat16 *w_proj, *w_agg, *w_edge, *w_node, *w_eblk;
   float *cu_e, *cu_n, *b1f_e, *b1f_n;
 };
 
@@ -654,6 +759,7 @@ int tc_core_pack(gnb_ctx* ctx, const gnb_block_params& blk, const gnb_ffn_params
   __nv_bfloat16* w = p->w;
   const size_t BE = BLK_BYTES / 2;   // elements per block
   p->w_proj = w; p->w_agg = w + 2 * BE; p->w_edge = w + 3 * BE; p->w_node = w + 12 * BE;
+  p->w_eblk = p->w_edge + 1 * BE;    // the edge kernel's W_blk block (We_e with the LN1 scale folded in)
   p->cu_e = p->f; p->cu_n = p->f + 128; p->b1f_e = p->f + 256; p->b1f_n = p->f + 768;
   cudaStream_t st = ctx->stream;
   auto pack = [&](const float* W, int ldw, int n0, int k0, const float* gamma, __nv_bfloat16* dst) {
@@ -664,14 +770,16 @@ int tc_core_pack(gnb_ctx* ctx, const gnb_block_params& blk, const gnb_ffn_params
   pack(blk.We, H, 0, H, g1n, w + 0 * BE);          // P_s
   pack(blk.We, H, 0, 2 * H, g1n, w + 1 * BE);      // P_r
   pack(blk.Wn, H, 0, 0, nullptr, w + 2 * BE);      // W_na (aggregate rows, no LayerNorm)
-  // fused kernels: W1_0 W2_0 W1_1 W2_1 W1_2 W2_2 W1_3 W2_3 W_blk
+  // fused kernels: block order documented at k_core
   for (int kind = 0; kind < 2; kind++) {
     __nv_bfloat16* dst = w + (kind == 0 ? 3 : 12) * BE;
     for (int c = 0; c < 4; c++) {
-      pack(ffn[kind].W1, 4 * H, c * H, 0, ln2[kind].gamma, dst + (2 * c) * BE);   // W1 (4H, H): hidden unit c*128+n
-      pack(ffn[kind].W2, H, 0, c * H, nullptr, dst + (2 * c + 1) * BE);           // W2 (H, 4H): k = hidden index
+      const int i1 = kind == 0 ? (c == 0 ? 0 : 2 * c + 1) : 2 * c;      // W1_c
+      const int i2 = kind == 0 ? 2 * c + 2 : 2 * c + 1;                 // W2_c
+      pack(ffn[kind].W1, 4 * H, c * H, 0, ln2[kind].gamma, dst + i1 * BE);   // W1 (4H, H): hidden unit c*128+n
+      pack(ffn[kind].W2, H, 0, c * H, nullptr, dst + i2 * BE);               // W2 (H, 4H): k = hidden index
     }
-    if (kind == 0) pack(blk.We, H, 0, 0, g1e, dst + 8 * BE);
+    if (kind == 0) pack(blk.We, H, 0, 0, g1e, dst + 1 * BE);
     else pack(blk.Wn, H, 0, H, g1n, dst + 8 * BE);
   }
   // constants folded into the per-graph rows / FFN bias
@@ -693,17 +801,17 @@ int tc_core_pack(gnb_ctx* ctx, const gnb_block_params& blk, const gnb_ffn_params
 }
 
 template <int MODE>
-static int launch_pair(gnb_ctx* ctx, const TcArgs& a, const char* name, double flops, double bytes) {
+static int launch_core(gnb_ctx* ctx, const CoreArgs& a, const char* name, double flops, double bytes) {
   if (a.num_tiles <= 0) return GNB_OK;
   static bool attr_set = false;
   if (!attr_set) {
-    GNB_CUDA(cudaFuncSetAttribute(k_tc_pair<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, P_SMEM));
+    GNB_CUDA(cudaFuncSetAttribute(k_core<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, C_SMEM));
     attr_set = true;
   }
   const int pairs = (a.num_tiles + 1) / 2;
   const int grid = pairs < ctx->sm_count ? pairs : ctx->sm_count;
   Launch L(ctx, name, bytes, flops);
-  k_tc_pair<MODE><<<grid, 320, P_SMEM, ctx->stream>>>(a);
+  k_core<MODE><<<grid, C_THREADS, C_SMEM, ctx->stream>>>(a);
   GNB_CUDA(cudaGetLastError());
   return GNB_OK;
 }
@@ -728,10 +836,14 @@ int tc_core_forward(gnb_ctx* ctx, const gnb_graph* g, const TcCorePack* pk, cons
                     const float* xn, const float* xg, float* ye, float* yn, float* yg) {
   const int64_t E = g->E, N = g->N, B = g->B;
   int rc = GNB_OK;
+  const size_t nparts = (size_t)(g->n_parts > 0 ? g->n_parts : 1);
   float* Pue = arena_ptr<float>(ctx->arena, (size_t)B * H, &rc);
   float* Pun = arena_ptr<float>(ctx->arena, (size_t)B * H, &rc);
   float* Psr = arena_ptr<float>(ctx->arena, (size_t)N * 2 * H, &rc);
-  float* aggp = arena_ptr<float>(ctx->arena, (size_t)(g->n_parts > 0 ? g->n_parts : 1) * H, &rc);
+  float* Epart = arena_ptr<float>(ctx->arena, nparts * H, &rc);
+  float* Gpart = arena_ptr<float>(ctx->arena, nparts * H, &rc);
+  float* Gs = arena_ptr<float>(ctx->arena, (size_t)N * H, &rc);
+  float* agg = arena_ptr<float>(ctx->arena, (size_t)N * H, &rc);
   float* Pagg = arena_ptr<float>(ctx->arena, (size_t)N * H, &rc);
   float* hv = arena_ptr<float>(ctx->arena, (size_t)N * H, &rc);
   float* se = arena_ptr<float>(ctx->arena, (size_t)B * H, &rc);
@@ -757,31 +869,39 @@ int tc_core_forward(gnb_ctx* ctx, const gnb_graph* g, const TcCorePack* pk, cons
     a.eps = ln1[1].eps; a.eps_mode = ln1[1].eps_mode;
     GNB_TRY(launch_proj<SRC_LN>(ctx, a, "tc_node_proj", 2.0 * N * 2 * HH, 4.0 * N * 3 * H));
   }
-  {  // edges: GNBlock edge update + FFN + residual + receiver aggregation
-    TcArgs a{};
+  {  // edges: GNBlock edge update + FFN + residual; partial receiver sums of the inputs
+    CoreArgs a{};
     a.x = xe; a.y = ye; a.R = E; a.num_tiles = ceil_div(E, TM); a.wpack = pk->w_edge;
     a.b1f = pk->b1f_e; a.b2 = ffn[0].b2; a.eps = ln1[0].eps; a.eps_mode = ln1[0].eps_mode;
     a.Psr = Psr; a.Pu = Pue; a.src = g->edge_src; a.dst = g->edge_dst; a.gid = g->edge_graph; a.part = g->edge_part;
-    a.agg_part = aggp;
+    a.Epart = Epart; a.Gpart = Gpart;
     // canonical work of the reference's edge update + edge FFN: 24 H^2 flops and
     // 8H bytes of features + 12 B of index per edge
-    GNB_TRY(launch_pair<MODE_EDGE>(ctx, a, "tc_edge_core", 24.0 * HH * E, (8.0 * H + 12.0) * E));
+    GNB_TRY(launch_core<MODE_EDGE>(ctx, a, "tc_edge_core", 24.0 * HH * E, (8.0 * H + 12.0) * E));
   }
-  {  // W_na . (edge aggregate of each node)
+  // edge -> node aggregate (src/nodefninput.jl:3) by linearity: agg = We_e' (sum ê) + sum (Ps + Pr + Pu)
+  GNB_TRY(launch_segsum(ctx, Gpart, H, g->node_part_ptr, N, Gs));
+  {
     ProjArgs a{};
-    a.x = aggp; a.part_ptr = g->node_part_ptr; a.out = Pagg; a.R = N; a.num_tiles = ceil_div(N, TM); a.nblk = 1;
+    a.x = Epart; a.part_ptr = g->node_part_ptr; a.addend = Gs; a.out = agg; a.R = N; a.num_tiles = ceil_div(N, TM); a.nblk = 1;
+    a.wpack = pk->w_eblk;
+    GNB_TRY(launch_proj<SRC_AGG>(ctx, a, "tc_agg", 2.0 * N * HH, 4.0 * N * 3 * H));
+  }
+  {  // W_na . agg
+    ProjArgs a{};
+    a.x = agg; a.part_ptr = nullptr; a.out = Pagg; a.R = N; a.num_tiles = ceil_div(N, TM); a.nblk = 1;
     a.wpack = pk->w_agg;
     GNB_TRY(launch_proj<SRC_AGG>(ctx, a, "tc_agg_proj", 2.0 * N * HH, 4.0 * N * 2 * H));
   }
   {  // nodes
-    TcArgs a{};
+    CoreArgs a{};
     a.x = xn; a.y = yn; a.R = N; a.num_tiles = ceil_div(N, TM); a.wpack = pk->w_node;
     a.b1f = pk->b1f_n; a.b2 = ffn[1].b2; a.eps = ln1[1].eps; a.eps_mode = ln1[1].eps_mode;
     a.Pu = Pun; a.gid = g->node_graph; a.Pagg = Pagg; a.h_out = hv;
-    GNB_TRY(launch_pair<MODE_NODE>(ctx, a, "tc_node_core", 20.0 * HH * N, (8.0 * H + 8.0) * N));
+    GNB_TRY(launch_core<MODE_NODE>(ctx, a, "tc_node_core", 20.0 * HH * N, (8.0 * H + 8.0) * N));
   }
   // graphs (B rows, fp32 CUDA cores): sums, graph update, graph FFN + residual
-  GNB_TRY(launch_segsum(ctx, aggp, H, g->graph_part_ptr, B, se));
+  GNB_TRY(launch_segsum(ctx, agg, H, g->graph_node_ptr, B, se));
   GNB_TRY(launch_segsum(ctx, hv, H, g->graph_node_ptr, B, sv));
   {
     LinArgs la{};
