@@ -78,6 +78,7 @@ class ProfEntry(C.Structure):
 
 
 SIGNATURES["gnb_ctx_set_profiling"] = (C.c_int, [C.c_void_p, C.c_int])
+SIGNATURES["gnb_debug_tc_timing"] = (C.c_int, [C.POINTER(C.c_ulonglong), C.c_int])
 SIGNATURES["gnb_ctx_profile_read"] = (C.c_int, [C.c_void_p, C.POINTER(ProfEntry), C.c_int, C.POINTER(C.c_int)])
 
 

@@ -196,7 +196,9 @@ enum { SRC_LN = 0, SRC_AGG = 1 };
 struct ProjArgs {
   const float* x;                 // SRC_LN: [R][H];  SRC_AGG: partial rows [n_parts][H]
   const int32_t* part_ptr;        // SRC_AGG: [R+1] or nullptr
-  const float* addend;            // optional [R][H] (nblk == 1)
+  const float* addend;            // optional [*][H], added to output columns [add_col0, add_col0 + H)
+  const int32_t* addend_idx;      // row of `addend` per output row (nullptr: the row itself)
+  int add_col0;
   float* out;                     // [R][nblk*H]
   int64_t R;
   int num_tiles;
@@ -338,7 +340,11 @@ __global__ void __launch_bounds__(192, 1) k_tc_proj(const ProjArgs a) {
           const int r = warp * 32 + 16 * hh + q + 8 * h2;
           if (r < rows) {
             float* o = a.out + (size_t)(row0 + r) * ld + 64 * ch + cq;
-            const float* ad = a.addend ? a.addend + (size_t)(row0 + r) * H + 64 * ch + cq : nullptr;
+            const float* ad = nullptr;
+            if (a.addend && 64 * ch >= a.add_col0) {
+              const int64_t ar = a.addend_idx ? (int64_t)__ldg(a.addend_idx + row0 + r) : row0 + r;
+              ad = a.addend + (size_t)ar * H + (64 * ch - a.add_col0) + cq;
+            }
 #pragma unroll
             for (int n = 0; n < 8; n++) {
               float2 v = make_float2(__uint_as_float(d[4 * n + 2 * h2]), __uint_as_float(d[4 * n + 2 * h2 + 1]));
@@ -374,18 +380,23 @@ struct CoreArgs {
   const float* b2;              // [H]
   float eps;
   int eps_mode;
-  const float* Pu;              // [B][H] per-graph row (graph projection + every folded bias)
-  const int32_t* gid;           // EDGE: edge_graph, NODE: node_graph
+  // two gathered fp32 addend rows per row:  g = add1[idx1 ? idx1[r] : r] + add2[idx2[r]]
+  //   EDGE: add1 = Ps (sender projection), add2 = Pr + Pu[graph] (receiver projection with the per-graph row
+  //         folded in by the node-projection epilogue); both live in Psr [N][2H]
+  //   NODE: add1 = W_na . (edge aggregate) [N][H], add2 = Pu [B][H] indexed by node_graph
+  const float* add1;
+  const int32_t* idx1;
+  int ld1;
+  const float* add2;
+  const int32_t* idx2;
+  int ld2;
   // EDGE
-  const float* Psr;             // [N][2H] sender (cols 0..H) / receiver (cols H..2H) projections
-  const int32_t* src;
-  const int32_t* dst;
   const int32_t* part;          // partial-row id per edge (32-row blocks, receiver runs)
   float* Epart;                 // out [n_parts][H] partial sums of the normalised edge rows
-  float* Gpart;                 // out [n_parts][H] partial sums of the gathered addends Ps+Pr+Pu
+  float* Gpart;                 // out [n_parts][H] partial sums of the gathered addends
   // NODE
-  const float* Pagg;            // [N][H] W_na . (edge aggregate)
   float* h_out;                 // [N][H] block output h_v
+  unsigned long long* dbg;      // diagnostics: clock64 stamps [CTA][warp][32] of one steady-state pair (nullptr: off)
 };
 
 constexpr int HALF_BYTES = KB_BYTES;     // weight ring stage = one 64-wide K half of a block (16 KB)
@@ -397,6 +408,12 @@ constexpr int C_MISC = 512 * 4 + 32 * 8 + 16;        // b1f[512], barriers[32], 
 constexpr int C_SMEM = C_OFF_MISC + C_MISC + 1024;
 constexpr int C_THREADS = 18 * 32;
 enum { CB_WFULL = 0, CB_WEMPTY = 5, CB_AFULL = 10, CB_AEMPTY = 14, CB_HIDFULL = 18, CB_HSREADY = 20, CB_OUTDONE = 22, CB_ACCFREE = 24 };
+
+#define TCDBG(k)                                                                                    \
+  do {                                                                                              \
+    if (a.dbg != nullptr && tl == 4 && lane == 0)                                                   \
+      a.dbg[((size_t)blockIdx.x * 18 + warp) * 32 + (k)] = (unsigned long long)clock64();           \
+  } while (0)
 
 template <int MODE>
 __global__ void __launch_bounds__(C_THREADS, 1) k_core(const CoreArgs a) {
@@ -434,11 +451,12 @@ __global__ void __launch_bounds__(C_THREADS, 1) k_core(const CoreArgs a) {
 
   if (warp == 17) {
     // ===================================================== weight loader
-    uint32_t it = 0;
-    for (int pair = blockIdx.x; pair < num_pairs; pair += gridDim.x) {
+    uint32_t it = 0, tl = 0;
+    for (int pair = blockIdx.x; pair < num_pairs; pair += gridDim.x, tl++) {
       for (int hb = 0; hb < 18; hb++, it++) {
         const uint32_t st = it % NWS, ph = (it / NWS) & 1;
         mbar_wait(BAR(CB_WEMPTY + st), ph ^ 1);
+        TCDBG(hb);
         if (elect_one()) {
           mbar_expect_tx(BAR(CB_WFULL + st), HALF_BYTES);
           bulk_g2s(sW + st * HALF_BYTES, reinterpret_cast<const uint8_t*>(a.wpack) + (size_t)hb * HALF_BYTES, HALF_BYTES,
@@ -467,8 +485,10 @@ __global__ void __launch_bounds__(C_THREADS, 1) k_core(const CoreArgs a) {
           if (b == 8) { kind = 2; c = 0; }
           else { kind = b & 1; c = b >> 1; }
         }
+        TCDBG(b);
         mbar_wait(BAR(CB_WFULL + st0), ph0);
         mbar_wait(BAR(CB_WFULL + st1), ph1);
+        TCDBG(20 + b);
         const uint64_t w0 = umma_desc(sW + st0 * HALF_BYTES), w1 = umma_desc(sW + st1 * HALF_BYTES);
 #pragma unroll
         for (int s = 0; s < 2; s++) {
@@ -506,92 +526,129 @@ __global__ void __launch_bounds__(C_THREADS, 1) k_core(const CoreArgs a) {
           tc_commit(BAR(CB_WEMPTY + st1));
         }
         __syncwarp();
+        TCDBG(9 + b);
       }
     }
   } else if (warp >= 8) {
     // ===================================================== prologue warps, one pair ahead of the MMAs
+    // A warp owns a 32-row slice and walks it in groups of 4 rows (one row = 32 lanes x float4, 512 B coalesced).
+    // Software pipeline: the 12 loads of group k+1 are in flight while group k is normalised; the LayerNorm
+    // reductions of the 4 rows of a group are interleaved level by level (4 independent shuffle chains).
     const int pw = warp - 8, s = pw >> 2, q = pw & 3;
     const float4 b2v = __ldg(reinterpret_cast<const float4*>(a.b2) + lane);
+    const float* base1 = a.add1 + 4 * lane;
+    const float* base2 = a.add2 + 4 * lane;
+    const float* xbase = a.x + 4 * lane;
     uint32_t tl = 0;
     for (int pair = blockIdx.x; pair < num_pairs; pair += gridDim.x, tl++) {
       const uint32_t stage = tl & 1, aph = (tl >> 1) & 1;
       const int64_t row0 = ((int64_t)pair * 2 + s) * TM + 32 * q;   // first row of this warp's 32-row slice
       const int64_t left = a.R - row0;
       const int rows = left < 0 ? 0 : (left > 32 ? 32 : (int)left);
-      int my_src = 0, my_dst = 0, my_gid = 0, my_pid = -1;
+      int my_i1 = 0, my_i2 = 0, my_pid = -1;
       if (lane < rows) {
-        my_gid = a.gid[row0 + lane];
-        if (MODE == MODE_EDGE) { my_src = a.src[row0 + lane]; my_dst = a.dst[row0 + lane]; my_pid = a.part[row0 + lane]; }
+        my_i1 = a.idx1 ? __ldg(a.idx1 + row0 + lane) : (int)(row0 + lane);
+        my_i2 = __ldg(a.idx2 + row0 + lane);
+        if (MODE == MODE_EDGE) my_pid = __ldg(a.part + row0 + lane);
       }
       uint32_t endmask = 0;
-      int pid = 0;
+      int pid_e = 0, pid_g = 0;
       if (MODE == MODE_EDGE) {
         const int nxt = __shfl_down_sync(0xffffffffu, my_pid, 1);
         endmask = __ballot_sync(0xffffffffu, lane < rows && (lane == rows - 1 || nxt != my_pid));
-        pid = __shfl_sync(0xffffffffu, my_pid, 0);
+        pid_e = pid_g = __shfl_sync(0xffffffffu, my_pid, 0);
       }
+      TCDBG(0);
+      float4 xa[4], pa[4], pb[4];
+      // rows past the end re-read the last valid row (always mapped); they are masked out below
+      auto issue = [&](int i0) {
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+          const int i = i0 + u;
+          const int i1 = __shfl_sync(0xffffffffu, my_i1, i), i2 = __shfl_sync(0xffffffffu, my_i2, i);
+          int64_t r = row0 + i;
+          r = r < a.R ? r : a.R - 1;
+          xa[u] = __ldg(reinterpret_cast<const float4*>(xbase + (size_t)r * H));
+          pa[u] = __ldg(reinterpret_cast<const float4*>(base1 + (size_t)i1 * a.ld1));
+          pb[u] = __ldg(reinterpret_cast<const float4*>(base2 + (size_t)i2 * a.ld2));
+        }
+      };
+      issue(0);
+      TCDBG(1);
       mbar_wait(BAR(CB_AEMPTY + stage * 2 + s), aph ^ 1);
+      TCDBG(2);
       uint8_t* A = sm + C_OFF_A + (stage * 2 + s) * BLK_BYTES;
       float4 acc_e = f4zero(), acc_g = f4zero();
 #pragma unroll 1
       for (int i0 = 0; i0 < 32; i0 += 4) {
-        float4 xv[4], g[4];
+        float4 xc[4];
+        // ---- consume the landed group: y0 = x + (gathered block addends) + b2; the epilogue adds the TMEM
+        //      accumulator onto it
 #pragma unroll
         for (int u = 0; u < 4; u++) {
           const int i = i0 + u;
-          const int gi = __shfl_sync(0xffffffffu, my_gid, i);
-          if (MODE == MODE_EDGE) {
-            const int si = __shfl_sync(0xffffffffu, my_src, i), di = __shfl_sync(0xffffffffu, my_dst, i);
-            if (i < rows) {
-              xv[u] = __ldg(reinterpret_cast<const float4*>(a.x + (size_t)(row0 + i) * H) + lane);
-              const float4 ps = __ldg(reinterpret_cast<const float4*>(a.Psr + (size_t)si * (2 * H)) + lane);
-              const float4 pr = __ldg(reinterpret_cast<const float4*>(a.Psr + (size_t)di * (2 * H) + H) + lane);
-              const float4 pu = __ldg(reinterpret_cast<const float4*>(a.Pu + (size_t)gi * H) + lane);
-              g[u] = make_float4((ps.x + pr.x) + pu.x, (ps.y + pr.y) + pu.y, (ps.z + pr.z) + pu.z, (ps.w + pr.w) + pu.w);
-            } else { xv[u] = f4zero(); g[u] = f4zero(); }
-          } else {
-            if (i < rows) {
-              xv[u] = __ldg(reinterpret_cast<const float4*>(a.x + (size_t)(row0 + i) * H) + lane);
-              const float4 pa = __ldg(reinterpret_cast<const float4*>(a.Pagg + (size_t)(row0 + i) * H) + lane);
-              const float4 pu = __ldg(reinterpret_cast<const float4*>(a.Pu + (size_t)gi * H) + lane);
-              g[u] = f4add(pa, pu);
-            } else { xv[u] = f4zero(); g[u] = f4zero(); }
-          }
-        }
-#pragma unroll
-        for (int u = 0; u < 4; u++) {
-          const int i = i0 + u;
-          const float mu = warp_sum((xv[u].x + xv[u].y) + (xv[u].z + xv[u].w)) * (1.0f / H);
-          const float dx = xv[u].x - mu, dy = xv[u].y - mu, dz = xv[u].z - mu, dw = xv[u].w - mu;
-          const float var = warp_sum((dx * dx + dy * dy) + (dz * dz + dw * dw)) * (1.0f / H);
-          const float rs = (i < rows) ? ln_rstd(var, a.eps, a.eps_mode) : 0.f;
-          const float4 xh = make_float4(dx * rs, dy * rs, dz * rs, dw * rs);
-          uint2 pk;
-          pk.x = pack_bf16(xh.x, xh.y);
-          pk.y = pack_bf16(xh.z, xh.w);
-          *reinterpret_cast<uint2*>(A + sw_off(32 * q + i, 4 * lane)) = pk;
+          xc[u] = xa[u];
+          const float4 g = f4add(pa[u], pb[u]);
           if (i < rows) {
-            // y0 = x + (gathered block addends) + b2 ; the epilogue adds the TMEM accumulator onto it
-            float4 y0 = make_float4((xv[u].x + g[u].x) + b2v.x, (xv[u].y + g[u].y) + b2v.y, (xv[u].z + g[u].z) + b2v.z,
-                                    (xv[u].w + g[u].w) + b2v.w);
+            const float4 y0 = make_float4((xc[u].x + g.x) + b2v.x, (xc[u].y + g.y) + b2v.y, (xc[u].z + g.z) + b2v.z,
+                                          (xc[u].w + g.w) + b2v.w);
             *(reinterpret_cast<float4*>(a.y + (size_t)(row0 + i) * H) + lane) = y0;
             if (MODE == MODE_NODE) {
-              *(reinterpret_cast<float4*>(a.h_out + (size_t)(row0 + i) * H) + lane) = g[u];
+              *(reinterpret_cast<float4*>(a.h_out + (size_t)(row0 + i) * H) + lane) = g;
             } else {
-              acc_e = f4add(acc_e, xh);
-              acc_g = f4add(acc_g, g[u]);
+              acc_g = f4add(acc_g, g);
               if ((endmask >> i) & 1u) {
-                *(reinterpret_cast<float4*>(a.Epart + (size_t)pid * H) + lane) = acc_e;
-                *(reinterpret_cast<float4*>(a.Gpart + (size_t)pid * H) + lane) = acc_g;
-                acc_e = f4zero(); acc_g = f4zero();
-                pid++;
+                *(reinterpret_cast<float4*>(a.Gpart + (size_t)pid_g * H) + lane) = acc_g;
+                acc_g = f4zero();
+                pid_g++;
               }
             }
           }
         }
+        if (i0 + 4 < 32) issue(i0 + 4);
+        // ---- LayerNorm of the 4 rows (two-pass, fp32), reductions interleaved across the rows
+        float sm1[4], sq[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) sm1[u] = (xc[u].x + xc[u].y) + (xc[u].z + xc[u].w);
+#pragma unroll
+        for (int o = 16; o; o >>= 1) {
+#pragma unroll
+          for (int u = 0; u < 4; u++) sm1[u] += __shfl_xor_sync(0xffffffffu, sm1[u], o);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+          const float mu = sm1[u] * (1.0f / H);
+          xc[u].x -= mu; xc[u].y -= mu; xc[u].z -= mu; xc[u].w -= mu;
+          sq[u] = (xc[u].x * xc[u].x + xc[u].y * xc[u].y) + (xc[u].z * xc[u].z + xc[u].w * xc[u].w);
+        }
+#pragma unroll
+        for (int o = 16; o; o >>= 1) {
+#pragma unroll
+          for (int u = 0; u < 4; u++) sq[u] += __shfl_xor_sync(0xffffffffu, sq[u], o);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+          const int i = i0 + u;
+          const float rs = (i < rows) ? ln_rstd(sq[u] * (1.0f / H), a.eps, a.eps_mode) : 0.f;
+          const float4 xh = make_float4(xc[u].x * rs, xc[u].y * rs, xc[u].z * rs, xc[u].w * rs);
+          uint2 pk;
+          pk.x = pack_bf16(xh.x, xh.y);
+          pk.y = pack_bf16(xh.z, xh.w);
+          *reinterpret_cast<uint2*>(A + sw_off(32 * q + i, 4 * lane)) = pk;
+          if (MODE == MODE_EDGE) {
+            acc_e = f4add(acc_e, xh);
+            if ((endmask >> i) & 1u) {
+              *(reinterpret_cast<float4*>(a.Epart + (size_t)pid_e * H) + lane) = acc_e;
+              acc_e = f4zero();
+              pid_e++;
+            }
+          }
+        }
+        TCDBG(3 + (i0 >> 2));
       }
       fence_async_smem();
       mbar_arrive(BAR(CB_AFULL + stage * 2 + s));
+      TCDBG(11);
     }
   } else {
     // ===================================================== drain + epilogue groups
@@ -608,11 +665,14 @@ __global__ void __launch_bounds__(C_THREADS, 1) k_core(const CoreArgs a) {
       const int rows = left < 0 ? 0 : (left > TM ? TM : (int)left);
       // acquire the prologue's y0 (and h0) stores of this pair.  Waited here, before the MMAs can release the
       // A stage, so the barrier cannot run two phases ahead of this wait.
+      TCDBG(0);
       mbar_wait(BAR(CB_AFULL + stage * 2 + s), aph);
+      TCDBG(1);
       // ---------------- FFN hidden chunks: TMEM fp32 -> +b1 -> relu -> bf16 pairs -> TMEM (in place)
 #pragma unroll 1
       for (int c = 0; c < 4; c++) {
         mbar_wait(BAR(CB_HIDFULL + s), c & 1);
+        TCDBG(2 + 2 * c);
         tc_fence_after();
 #pragma unroll
         for (int j = 0; j < 4; j++) {
@@ -631,68 +691,99 @@ __global__ void __launch_bounds__(C_THREADS, 1) k_core(const CoreArgs a) {
         tc_wait_st();
         tc_fence_before();
         mbar_arrive(BAR(CB_HSREADY + s));
+        TCDBG(3 + 2 * c);
       }
       // ---------------- final epilogue: y = y0 + D (+ D_blk) in the accumulator-fragment layout.
       // 8 sub-steps ss = (64-column half ch, 16-row half hh, 8-row half h2); a thread owns 8 float2 per sub-step.
-      float2 yb[2][8], hb[8];
-      uint32_t d[32], e[32];
 #define EPI_ROW(ss) (w4 * 32 + 16 * (((ss) >> 1) & 1) + q + 8 * ((ss) & 1))
 #define EPI_OFF(ss) ((size_t)(row0 + EPI_ROW(ss)) * H + 64 * ((ss) >> 2) + cq)
+#define EPI_OFFC(ss) ((size_t)((row0 + EPI_ROW(ss)) < a.R ? (row0 + EPI_ROW(ss)) : a.R - 1) * H + 64 * ((ss) >> 2) + cq)
       if (MODE == MODE_EDGE) {
-        if (EPI_ROW(0) < rows) {
+        // y0 of sub-steps 0..3 is fetched (L2 hits) while the last down-projection is still running, and the
+        // slots are refilled with sub-steps 4..7 as they drain: the accumulator is released ~1 L2 latency after
+        // the MMAs complete instead of 8.
+        float2 yb[4][8];
+        uint32_t d[32];
 #pragma unroll
-          for (int n = 0; n < 8; n++) yb[0][n] = __ldcg(reinterpret_cast<const float2*>(a.y + EPI_OFF(0) + 8 * n));
+        for (int ss = 0; ss < 4; ss++) {
+#pragma unroll
+          for (int n = 0; n < 8; n++) yb[ss][n] = __ldcg(reinterpret_cast<const float2*>(a.y + EPI_OFFC(ss) + 8 * n));
         }
-      }
-      mbar_wait(BAR(CB_OUTDONE + s), tl & 1);
-      tc_fence_after();
+        TCDBG(10);
+        mbar_wait(BAR(CB_OUTDONE + s), tl & 1);
+        TCDBG(11);
+        tc_fence_after();
 #pragma unroll
-      for (int ss = 0; ss < 8; ss++) {
-        const int h2 = ss & 1;
-        const bool valid = EPI_ROW(ss) < rows;
-        if (h2 == 0) {
-          const uint32_t toff = lane_base + ((uint32_t)(16 * ((ss >> 1) & 1)) << 16) + 64 * (ss >> 2);
-          TC_LD_FRAG64(D_s + toff, d);
-          if (MODE == MODE_NODE) TC_LD_FRAG64(Hd_s + toff, e);
-        }
-        if (MODE == MODE_EDGE) {
-          if (ss < 7 && EPI_ROW(ss + 1) < rows) {
-#pragma unroll
-            for (int n = 0; n < 8; n++) yb[(ss + 1) & 1][n] = __ldcg(reinterpret_cast<const float2*>(a.y + EPI_OFF(ss + 1) + 8 * n));
+        for (int ss = 0; ss < 8; ss++) {
+          const int h2 = ss & 1;
+          if (h2 == 0) {
+            const uint32_t toff = lane_base + ((uint32_t)(16 * ((ss >> 1) & 1)) << 16) + 64 * (ss >> 2);
+            TC_LD_FRAG64(D_s + toff, d);
+            tc_wait_ld();
+            if (ss == 6) {   // TMEM fully read: release the accumulators to the next pair's MMAs
+              tc_fence_before();
+              mbar_arrive(BAR(CB_ACCFREE + s));
+            }
           }
-        } else if (valid) {
+          TCDBG(12 + ss);
+          if (EPI_ROW(ss) < rows) {
+#pragma unroll
+            for (int n = 0; n < 8; n++) {
+              float2 yv = yb[ss & 3][n];
+              yv.x += __uint_as_float(d[4 * n + 2 * h2]);
+              yv.y += __uint_as_float(d[4 * n + 2 * h2 + 1]);
+              *reinterpret_cast<float2*>(a.y + EPI_OFF(ss) + 8 * n) = yv;
+            }
+          }
+          if (ss < 4) {
+#pragma unroll
+            for (int n = 0; n < 8; n++) yb[ss][n] = __ldcg(reinterpret_cast<const float2*>(a.y + EPI_OFFC(ss + 4) + 8 * n));
+          }
+        }
+        TCDBG(20);
+      } else {
+        float2 yb[8], hb[8];
+        uint32_t d[32], e[32];
+        mbar_wait(BAR(CB_OUTDONE + s), tl & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int ss = 0; ss < 8; ss++) {
+          const int h2 = ss & 1;
+          const bool valid = EPI_ROW(ss) < rows;
+          if (h2 == 0) {
+            const uint32_t toff = lane_base + ((uint32_t)(16 * ((ss >> 1) & 1)) << 16) + 64 * (ss >> 2);
+            TC_LD_FRAG64(D_s + toff, d);
+            TC_LD_FRAG64(Hd_s + toff, e);
+          }
 #pragma unroll
           for (int n = 0; n < 8; n++) {
-            yb[0][n] = __ldcg(reinterpret_cast<const float2*>(a.y + EPI_OFF(ss) + 8 * n));
-            hb[n] = __ldcg(reinterpret_cast<const float2*>(a.h_out + EPI_OFF(ss) + 8 * n));
+            yb[n] = __ldcg(reinterpret_cast<const float2*>(a.y + EPI_OFFC(ss) + 8 * n));
+            hb[n] = __ldcg(reinterpret_cast<const float2*>(a.h_out + EPI_OFFC(ss) + 8 * n));
           }
-        }
-        if (h2 == 0) {
-          tc_wait_ld();
-          if (ss == 6) {   // TMEM fully read: release the accumulators to the next pair's MMAs
-            tc_fence_before();
-            mbar_arrive(BAR(CB_ACCFREE + s));
+          if (h2 == 0) {
+            tc_wait_ld();
+            if (ss == 6) {
+              tc_fence_before();
+              mbar_arrive(BAR(CB_ACCFREE + s));
+            }
           }
-        }
-        if (valid) {
+          if (valid) {
 #pragma unroll
-          for (int n = 0; n < 8; n++) {
-            float2 yv = yb[MODE == MODE_EDGE ? (ss & 1) : 0][n];
-            float dx = __uint_as_float(d[4 * n + 2 * h2]), dy = __uint_as_float(d[4 * n + 2 * h2 + 1]);
-            if (MODE == MODE_NODE) {
+            for (int n = 0; n < 8; n++) {
               const float bx = __uint_as_float(e[4 * n + 2 * h2]), by = __uint_as_float(e[4 * n + 2 * h2 + 1]);
-              float2 hv = hb[n];
+              float2 hv = hb[n], yv = yb[n];
               hv.x += bx; hv.y += by;
               *reinterpret_cast<float2*>(a.h_out + EPI_OFF(ss) + 8 * n) = hv;
-              dx += bx; dy += by;
+              yv.x += __uint_as_float(d[4 * n + 2 * h2]) + bx;
+              yv.y += __uint_as_float(d[4 * n + 2 * h2 + 1]) + by;
+              *reinterpret_cast<float2*>(a.y + EPI_OFF(ss) + 8 * n) = yv;
             }
-            yv.x += dx; yv.y += dy;
-            *reinterpret_cast<float2*>(a.y + EPI_OFF(ss) + 8 * n) = yv;
           }
         }
       }
 #undef EPI_ROW
 #undef EPI_OFF
+#undef EPI_OFFC
     }
   }
   tc_fence_before();
@@ -723,6 +814,20 @@ __global__ void k_fold_bias(const float* __restrict__ W, int ldw, int n0, int k0
 }
 
 }  // namespace
+
+static unsigned long long* g_tc_dbg = nullptr;
+extern "C" int gnb_debug_tc_timing(unsigned long long* out, int n) {
+  // first call (out == nullptr): allocate + enable;  later calls copy the stamps of the last edge launch out
+  if (!g_tc_dbg) {
+    if (cudaMalloc((void**)&g_tc_dbg, 148 * 18 * 32 * 8) != cudaSuccess) return GNB_ERR_OOM;
+    cudaMemset(g_tc_dbg, 0, 148 * 18 * 32 * 8);
+  }
+  if (out) {
+    if (n > 148 * 18 * 32) n = 148 * 18 * 32;
+    if (cudaMemcpy(out, g_tc_dbg, (size_t)n * 8, cudaMemcpyDeviceToHost) != cudaSuccess) return GNB_ERR_CUDA;
+  }
+  return GNB_OK;
+}
 
 struct TcCorePack {
   __nv_bfloat16* w = nullptr;   // [proj 2 | aggproj 1 | edge 9 | node 9] blocks of 32 KB
@@ -866,6 +971,7 @@ int tc_core_forward(gnb_ctx* ctx, const gnb_graph* g, const TcCorePack* pk, cons
   {  // node projections P_s | P_r
     ProjArgs a{};
     a.x = xn; a.out = Psr; a.R = N; a.num_tiles = ceil_div(N, TM); a.nblk = 2; a.wpack = pk->w_proj;
+    a.addend = Pue; a.addend_idx = g->node_graph; a.add_col0 = H;   // P_r += P_u[graph of the node]
     a.eps = ln1[1].eps; a.eps_mode = ln1[1].eps_mode;
     GNB_TRY(launch_proj<SRC_LN>(ctx, a, "tc_node_proj", 2.0 * N * 2 * HH, 4.0 * N * 3 * H));
   }
@@ -873,8 +979,10 @@ int tc_core_forward(gnb_ctx* ctx, const gnb_graph* g, const TcCorePack* pk, cons
     CoreArgs a{};
     a.x = xe; a.y = ye; a.R = E; a.num_tiles = ceil_div(E, TM); a.wpack = pk->w_edge;
     a.b1f = pk->b1f_e; a.b2 = ffn[0].b2; a.eps = ln1[0].eps; a.eps_mode = ln1[0].eps_mode;
-    a.Psr = Psr; a.Pu = Pue; a.src = g->edge_src; a.dst = g->edge_dst; a.gid = g->edge_graph; a.part = g->edge_part;
+    a.add1 = Psr; a.idx1 = g->edge_src; a.ld1 = 2 * H; a.add2 = Psr + H; a.idx2 = g->edge_dst; a.ld2 = 2 * H;
+    a.part = g->edge_part;
     a.Epart = Epart; a.Gpart = Gpart;
+    a.dbg = g_tc_dbg;
     // canonical work of the reference's edge update + edge FFN: 24 H^2 flops and
     // 8H bytes of features + 12 B of index per edge
     GNB_TRY(launch_core<MODE_EDGE>(ctx, a, "tc_edge_core", 24.0 * HH * E, (8.0 * H + 12.0) * E));
@@ -897,7 +1005,7 @@ int tc_core_forward(gnb_ctx* ctx, const gnb_graph* g, const TcCorePack* pk, cons
     CoreArgs a{};
     a.x = xn; a.y = yn; a.R = N; a.num_tiles = ceil_div(N, TM); a.wpack = pk->w_node;
     a.b1f = pk->b1f_n; a.b2 = ffn[1].b2; a.eps = ln1[1].eps; a.eps_mode = ln1[1].eps_mode;
-    a.Pu = Pun; a.gid = g->node_graph; a.Pagg = Pagg; a.h_out = hv;
+    a.add1 = Pagg; a.idx1 = nullptr; a.ld1 = H; a.add2 = Pun; a.idx2 = g->node_graph; a.ld2 = H; a.h_out = hv;
     GNB_TRY(launch_core<MODE_NODE>(ctx, a, "tc_node_core", 20.0 * HH * N, (8.0 * H + 8.0) * N));
   }
   // graphs (B rows, fp32 CUDA cores): sums, graph update, graph FFN + residual
