@@ -1,0 +1,175 @@
+// Graph-level (B rows) stages of a GNCore with 128-wide features, fp32 CUDA cores.
+//
+// A batch has few graphs (B << N << E), so these stages are latency- not throughput-bound: a CTA owns
+// RT = 8 graphs and all output columns, keeps its rows in shared memory and streams the weights from L2
+// (512 CTAs -> one wave).  Two launches per GNCore replace ten small GEMM / segmented-sum launches:
+//   k_graph_pre :  P_ue = LN1(u) W_eu + c_e          per-graph row of the edge update   (src/edgefninput.jl:6)
+//                  P_un = LN1(u) W_nu + c_n          per-graph row of the node update   (src/nodefninput.jl:5)
+//   k_graph_post:  s_e = sum of the graph's node aggregates (== sum of its edges, src/graphfninput.jl:3)
+//                  s_v = sum of its updated nodes                                      (src/graphfninput.jl:4)
+//                  h_u = W_g [s_e ; s_v ; LN1(u)] + b_g                                 (src/gnblock.jl:67)
+//                  y_u = (u + h_u) + W2 relu(W1 LN2(u) + b1) + b2                       (src/gncore.jl:56-68)
+#include "kernels.cuh"
+#include "graphrows.cuh"
+
+namespace {
+
+constexpr int H = 128;
+constexpr int RT = 8;   // graphs per CTA
+
+__device__ __forceinline__ float ln_rstd(float var, float eps, int mode) {
+  if (mode == GNB_EPS_SQRT_VAR_EPS2) return 1.0f / sqrtf(var + eps * eps);
+  if (mode == GNB_EPS_STD_PLUS_EPS) return 1.0f / (sqrtf(var) + eps);
+  return 1.0f / sqrtf(var + eps);
+}
+
+// LayerNorm of RT rows held in xs[RT][H] (warp w normalises rows w, w+4): out = gamma (x - mu) rstd + beta
+__device__ __forceinline__ void ln_rows(const float (*xs)[H], float (*out)[H], const float* __restrict__ gamma,
+                                        const float* __restrict__ beta, float eps, int mode, int warp, int lane) {
+  const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + lane);
+  const float4 b = __ldg(reinterpret_cast<const float4*>(beta) + lane);
+  for (int r = warp; r < RT; r += 4) {
+    const float4 v = *reinterpret_cast<const float4*>(&xs[r][4 * lane]);
+    float s = (v.x + v.y) + (v.z + v.w);
+#pragma unroll
+    for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const float mu = s * (1.0f / H);
+    const float dx = v.x - mu, dy = v.y - mu, dz = v.z - mu, dw = v.w - mu;
+    float q = (dx * dx + dy * dy) + (dz * dz + dw * dw);
+#pragma unroll
+    for (int o = 16; o; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+    const float rs = ln_rstd(q * (1.0f / H), eps, mode);
+    *reinterpret_cast<float4*>(&out[r][4 * lane]) =
+        make_float4(dx * rs * g.x + b.x, dy * rs * g.y + b.y, dz * rs * g.z + b.z, dw * rs * g.w + b.w);
+  }
+}
+
+// acc[r] += sum_k xs[r][k] * W[k*ldw + n]   for k in [0, K)   (W row-major [k][n], coalesced over the CTA)
+template <int K>
+__device__ __forceinline__ void gemv_rows(const float (*xs)[K], const float* __restrict__ W, int ldw, int n, float* acc) {
+#pragma unroll 2
+  for (int k = 0; k < K; k += 4) {
+    const float w0 = __ldg(W + (size_t)(k + 0) * ldw + n), w1 = __ldg(W + (size_t)(k + 1) * ldw + n);
+    const float w2 = __ldg(W + (size_t)(k + 2) * ldw + n), w3 = __ldg(W + (size_t)(k + 3) * ldw + n);
+#pragma unroll
+    for (int r = 0; r < RT; r++) {
+      const float4 x = *reinterpret_cast<const float4*>(&xs[r][k]);
+      acc[r] = fmaf(x.x, w0, acc[r]);
+      acc[r] = fmaf(x.y, w1, acc[r]);
+      acc[r] = fmaf(x.z, w2, acc[r]);
+      acc[r] = fmaf(x.w, w3, acc[r]);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(128) k_graph_pre(const GraphPreArgs a) {
+  __shared__ __align__(16) float xs[RT][H];
+  __shared__ __align__(16) float xa[RT][H];
+  const int n = threadIdx.x, warp = n >> 5, lane = n & 31;
+  const int64_t g0 = (int64_t)blockIdx.x * RT;
+  for (int r = 0; r < RT; r++) {
+    const int64_t g = g0 + r < a.B ? g0 + r : a.B - 1;
+    xs[r][n] = a.xg[(size_t)g * H + n];
+  }
+  __syncthreads();
+  ln_rows(xs, xa, a.gamma, a.beta, a.eps, a.eps_mode, warp, lane);
+  __syncthreads();
+  float ae[RT], an[RT];
+  const float ce = a.ce[n], cn = a.cn[n];
+#pragma unroll
+  for (int r = 0; r < RT; r++) { ae[r] = ce; an[r] = cn; }
+  gemv_rows<H>(xa, a.Weu, H, n, ae);
+  gemv_rows<H>(xa, a.Wnu, H, n, an);
+#pragma unroll
+  for (int r = 0; r < RT; r++) {
+    if (g0 + r < a.B) {
+      a.Pue[(size_t)(g0 + r) * H + n] = ae[r];
+      a.Pun[(size_t)(g0 + r) * H + n] = an[r];
+    }
+  }
+}
+
+__global__ void __launch_bounds__(128) k_graph_post(const GraphPostArgs a) {
+  __shared__ __align__(16) float xs[RT][H];       // u
+  __shared__ __align__(16) float xa[RT][H];       // LN1(u), later h_u
+  __shared__ __align__(16) float xb[RT][H];       // LN2(u)
+  __shared__ __align__(16) float se[RT][H];
+  __shared__ __align__(16) float sv[RT][H];
+  __shared__ __align__(16) float hid[RT][4 * H];
+  const int n = threadIdx.x, warp = n >> 5, lane = n & 31;
+  const int64_t g0 = (int64_t)blockIdx.x * RT;
+  for (int r = 0; r < RT; r++) {
+    const int64_t g = g0 + r < a.B ? g0 + r : a.B - 1;
+    xs[r][n] = a.xg[(size_t)g * H + n];
+    // ordered sums over the graph's nodes (rows of a graph are contiguous): deterministic, no atomics
+    const int v0 = a.graph_node_ptr[g], v1 = a.graph_node_ptr[g + 1];
+    float s0 = 0.f, s1 = 0.f;
+    int v = v0;
+    for (; v + 3 < v1; v += 4) {
+      const float e0 = a.agg[(size_t)v * H + n], e1 = a.agg[(size_t)(v + 1) * H + n];
+      const float e2 = a.agg[(size_t)(v + 2) * H + n], e3 = a.agg[(size_t)(v + 3) * H + n];
+      const float h0 = a.hv[(size_t)v * H + n], h1 = a.hv[(size_t)(v + 1) * H + n];
+      const float h2 = a.hv[(size_t)(v + 2) * H + n], h3 = a.hv[(size_t)(v + 3) * H + n];
+      s0 += e0; s0 += e1; s0 += e2; s0 += e3;
+      s1 += h0; s1 += h1; s1 += h2; s1 += h3;
+    }
+    for (; v < v1; v++) { s0 += a.agg[(size_t)v * H + n]; s1 += a.hv[(size_t)v * H + n]; }
+    se[r][n] = s0;
+    sv[r][n] = s1;
+  }
+  __syncthreads();
+  ln_rows(xs, xa, a.g1, a.b1ln, a.eps1, a.eps_mode1, warp, lane);
+  ln_rows(xs, xb, a.g2, a.b2ln, a.eps2, a.eps_mode2, warp, lane);
+  __syncthreads();
+  // h_u = W_g [s_e ; s_v ; LN1(u)] + b_g
+  float hu[RT];
+  {
+    const float bg = a.bg[n];
+#pragma unroll
+    for (int r = 0; r < RT; r++) hu[r] = bg;
+    gemv_rows<H>(se, a.Wg, H, n, hu);
+    gemv_rows<H>(sv, a.Wg + (size_t)H * H, H, n, hu);
+    gemv_rows<H>(xa, a.Wg + (size_t)2 * H * H, H, n, hu);
+  }
+  // FFN hidden: relu(W1 LN2(u) + b1), 4H wide: thread n owns hidden units n, n+H, n+2H, n+3H
+#pragma unroll 1
+  for (int c = 0; c < 4; c++) {
+    float hc[RT];
+    const float b1 = a.b1[c * H + n];
+#pragma unroll
+    for (int r = 0; r < RT; r++) hc[r] = b1;
+    gemv_rows<H>(xb, a.W1 + c * H, 4 * H, n, hc);
+#pragma unroll
+    for (int r = 0; r < RT; r++) hid[r][c * H + n] = fmaxf(hc[r], 0.f);
+  }
+  __syncthreads();
+  float f[RT];
+  {
+    const float b2 = a.b2[n];
+#pragma unroll
+    for (int r = 0; r < RT; r++) f[r] = b2;
+    gemv_rows<4 * H>(hid, a.W2, H, n, f);
+  }
+#pragma unroll
+  for (int r = 0; r < RT; r++) {
+    if (g0 + r < a.B) a.yg[(size_t)(g0 + r) * H + n] = (xs[r][n] + hu[r]) + f[r];
+  }
+}
+
+}  // namespace
+
+int launch_graph_pre(gnb_ctx* ctx, const GraphPreArgs& a) {
+  if (a.B <= 0) return GNB_OK;
+  Launch L(ctx, "graph_pre", 4.0 * a.B * 3 * H + 8.0 * H * H, 4.0 * a.B * H * H);
+  k_graph_pre<<<ceil_div(a.B, RT), 128, 0, ctx->stream>>>(a);
+  GNB_CUDA(cudaGetLastError());
+  return GNB_OK;
+}
+
+int launch_graph_post(gnb_ctx* ctx, const GraphPostArgs& a, int64_t N) {
+  if (a.B <= 0) return GNB_OK;
+  Launch L(ctx, "graph_post", 8.0 * N * H + 8.0 * a.B * H + 4.0 * 11 * H * H, 22.0 * a.B * H * H);
+  k_graph_post<<<ceil_div(a.B, RT), 128, 0, ctx->stream>>>(a);
+  GNB_CUDA(cudaGetLastError());
+  return GNB_OK;
+}

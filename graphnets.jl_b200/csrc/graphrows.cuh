@@ -1,0 +1,31 @@
+// Graph-level (B rows) stages of the 128-wide GNCore tensor path (internal interface).
+#pragma once
+#include "common.cuh"
+
+struct GraphPreArgs {
+  const float* xg;       // [B][128] graph features u
+  int64_t B;
+  const float *gamma, *beta;   // LN1 (graph)
+  float eps;
+  int eps_mode;
+  const float* Weu;      // [128][128] rows [3H,4H) of the edge Dense  (k-major)
+  const float* Wnu;      // [128][128] rows [2H,3H) of the node Dense
+  const float *ce, *cn;  // [128] biases with the folded LayerNorm shifts of the tensor path
+  float *Pue, *Pun;      // out [B][128]
+};
+
+struct GraphPostArgs {
+  const float* xg;
+  int64_t B;
+  const int32_t* graph_node_ptr;   // [B+1]
+  const float* agg;      // [N][128] edge -> node aggregates
+  const float* hv;       // [N][128] updated nodes (block output)
+  const float *g1, *b1ln; float eps1; int eps_mode1;   // LN1 (graph)
+  const float *g2, *b2ln; float eps2; int eps_mode2;   // LN2 (graph)
+  const float *Wg, *bg;  // graph Dense (3H -> H), k-major
+  const float *W1, *b1, *W2, *b2;   // graph FFN
+  float* yg;             // out [B][128]
+};
+
+int launch_graph_pre(gnb_ctx* ctx, const GraphPreArgs& a);
+int launch_graph_post(gnb_ctx* ctx, const GraphPostArgs& a, int64_t N);

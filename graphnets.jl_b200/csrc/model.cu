@@ -3,6 +3,7 @@
 // src/gnfeedforward.jl:27-40, src/gngraphnorm.jl:19-26.
 #include "kernels.cuh"
 #include "tc.cuh"
+#include "smallk.cuh"
 
 // ------------------------------------------------------------------ errors / arena / ctx
 static thread_local char g_err[1024] = "";
@@ -160,6 +161,7 @@ struct LayerW {
   gnb_ffn_params ffn[3];
   gnb_ln_params ln1[3], ln2[3];
   TcCorePack* tc = nullptr;  // packed bf16 weights (cores the tensor path supports)
+  float* wnx = nullptr;      // narrow-input blocks: [We ; be] . Wn_agg  ((in_e+2in_n+in_g+1) x out_n), see run_block_wide
 };
 
 struct gnb_model {
@@ -169,6 +171,18 @@ struct gnb_model {
   int in_dims[3] = {0, 0, 0};
   int out_dims[3] = {0, 0, 0};
 };
+
+// out[k][n] = sum_j X[k][j] Wn[j][n],  X = [We ; be]  ((ke+1) x p),  Wn_agg = rows [0,p) of the node Dense (p x q)
+__global__ void k_fold_wnx(const float* __restrict__ We, const float* __restrict__ be, const float* __restrict__ Wn,
+                           int ke, int p, int q, float* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (ke + 1) * q) return;
+  const int k = i / q, n = i % q;
+  const float* x = k < ke ? We + (size_t)k * p : be;
+  float s = 0.f;
+  for (int j = 0; j < p; j++) s = fmaf(x[j], Wn[(size_t)j * q + n], s);
+  out[i] = s;
+}
 
 static int check_block(const gnb_block_params& b, int li) {
   GNB_CHECK(b.in_e >= 0 && b.in_n >= 0 && b.in_g >= 0 && b.out_e >= 0 && b.out_n >= 0 && b.out_g >= 0,
@@ -289,6 +303,22 @@ static int build_model(gnb_ctx* ctx, const gnb_layer* layers, int n_layers, int 
       delete m;
       return GNB_ERR_CUDA;
     }
+    // narrow-input blocks (encoders): the node update of the aggregated edge output is folded onto the
+    // aggregated narrow inputs,  Wn_agg (We Z + deg be) = ([We ; be] Wn_agg) [Z ; deg]
+    for (auto& w : m->layers) {
+      const gnb_block_params& b = w.blk;
+      const int ke = b.in_e + 2 * b.in_n + b.in_g;
+      if (w.kind == GNB_LAYER_BLOCK && b.out_e > 0 && b.out_n > 0 && ke > 0 && ke + 1 + b.in_n + b.in_g <= 32 && b.out_e >= 32) {
+        if (cudaMalloc((void**)&w.wnx, (size_t)(ke + 1) * b.out_n * sizeof(float)) != cudaSuccess) {
+          cudaGetLastError();
+          gnb_model_destroy(m);
+          gnb_set_error("gnb_model_create: cudaMalloc failed");
+          return GNB_ERR_OOM;
+        }
+        k_fold_wnx<<<ceil_div((int64_t)(ke + 1) * b.out_n, 128), 128, 0, ctx->stream>>>(b.We, b.be, b.Wn, ke, b.out_e, b.out_n, w.wnx);
+      }
+    }
+    GNB_CUDA(cudaStreamSynchronize(ctx->stream));
     // tensor-core packs for the cores the tcgen05 path supports
     for (auto& w : m->layers) {
       if (w.kind == GNB_LAYER_CORE && tc_core_supported(w.blk.in_e, w.blk.in_n, w.blk.in_g)) {
@@ -310,8 +340,10 @@ extern "C" int gnb_model_create(gnb_ctx* ctx, const gnb_layer* layers, int n_lay
 extern "C" int gnb_model_destroy(gnb_model* m) {
   if (!m) return GNB_OK;
   cudaSetDevice(m->device);
-  for (auto& w : m->layers)
+  for (auto& w : m->layers) {
     if (w.tc) tc_core_pack_free(w.tc);
+    if (w.wnx) cudaFree(w.wnx);
+  }
   if (m->wbuf) cudaFree(m->wbuf);
   delete m;
   return GNB_OK;
@@ -436,6 +468,159 @@ static int run_block_fp32(gnb_ctx* ctx, const gnb_graph* g, const gnb_block_para
   return GNB_OK;
 }
 
+
+// Shared graph-level tail of the block fast paths: h_u = Wg [sum agg ; sum h_v ; u] + bg   (src/graphfninput.jl:2-6)
+static int run_graph_update_fp32(gnb_ctx* ctx, const gnb_graph* g, const gnb_block_params& b, const float* agg,
+                                 const float* hn, const float* xg, float* hg) {
+  const int c = b.in_g, p = b.out_e, q = b.out_n, r = b.out_g;
+  const int64_t B = g->B;
+  int rc = GNB_OK;
+  float *se = nullptr, *sv = nullptr;
+  if (p > 0) {
+    se = arena_ptr<float>(ctx->arena, (size_t)B * p, &rc);
+    if (rc != GNB_OK) return rc;
+    GNB_TRY(launch_segsum(ctx, agg, p, g->graph_node_ptr, B, se));
+  }
+  if (q > 0) {
+    sv = arena_ptr<float>(ctx->arena, (size_t)B * q, &rc);
+    if (rc != GNB_OK) return rc;
+    GNB_TRY(launch_segsum(ctx, hn, q, g->graph_node_ptr, B, sv));
+  }
+  LinArgs la{};
+  la.R = B; la.Nout = r; la.ldw = r; la.ldo = r; la.out = hg; la.bias = b.bg;
+  if (p > 0) la.src[la.nsrc++] = mk_src(se, p, b.Wg, nullptr);
+  if (q > 0) la.src[la.nsrc++] = mk_src(sv, q, b.Wg + (size_t)p * r, nullptr);
+  if (c > 0) la.src[la.nsrc++] = mk_src(xg, c, b.Wg + (size_t)(p + q) * r, nullptr);
+  return launch_linear_fp32(ctx, la);
+}
+
+// GNBlock with NARROW inputs (encoder): the [e | v_src | v_dst | u] concat is at most 31 wide.
+// Edge update straight from the raw inputs (no node projections, no gathered 128-wide rows); the
+// edge -> node sum is taken over the narrow inputs and transformed afterwards (linearity of Dense).
+static bool block_wide_ok(const LayerW& w) {
+  const gnb_block_params& b = w.blk;
+  const int ke = b.in_e + 2 * b.in_n + b.in_g;
+  return w.kind == GNB_LAYER_BLOCK && b.out_e >= 32 && (b.out_e & 3) == 0 && ke > 0 && ke + 1 <= 32 &&
+         (b.out_n == 0 || (w.wnx != nullptr && (b.out_n & 3) == 0));
+}
+static int run_block_wide(gnb_ctx* ctx, const gnb_graph* g, const LayerW& w, Feat x, FeatOut h) {
+  const gnb_block_params& b = w.blk;
+  const int a = b.in_e, bn_ = b.in_n, c = b.in_g, p = b.out_e, q = b.out_n, r = b.out_g;
+  const int ke = a + 2 * bn_ + c, kz = ke + 1;
+  const int64_t E = g->E, N = g->N;
+  int rc = GNB_OK;
+  {
+    WideArgs wa{};
+    wa.R = E; wa.Nout = p; wa.ldw = p; wa.bias = b.be; wa.out = h.e; wa.ldo = p;
+    if (a > 0) wa.pc[wa.np++] = WidePiece{x.e, nullptr, a, a, b.We};
+    if (bn_ > 0) {
+      wa.pc[wa.np++] = WidePiece{x.n, g->edge_src, bn_, bn_, b.We + (size_t)a * p};
+      wa.pc[wa.np++] = WidePiece{x.n, g->edge_dst, bn_, bn_, b.We + (size_t)(a + bn_) * p};
+    }
+    if (c > 0) wa.pc[wa.np++] = WidePiece{x.g, g->edge_graph, c, c, b.We + (size_t)(a + 2 * bn_) * p};
+    GNB_TRY(launch_wide(ctx, wa));
+  }
+  if (q == 0 && r == 0) return GNB_OK;
+  float* Z = arena_ptr<float>(ctx->arena, (size_t)N * kz, &rc);
+  if (rc != GNB_OK) return rc;
+  {
+    ZsumArgs za{};
+    za.N = N; za.node_in_ptr = g->node_in_ptr; za.edge_src = g->edge_src; za.node_graph = g->node_graph;
+    za.ef = x.e; za.nf = x.n; za.gf = x.g; za.de = a; za.dn = bn_; za.dg = c; za.Z = Z;
+    GNB_TRY(launch_zsum(ctx, za));
+  }
+  float* agg = nullptr;
+  if (r > 0) {   // the graph update needs sum_v agg_v
+    agg = arena_ptr<float>(ctx->arena, (size_t)N * p, &rc);
+    if (rc != GNB_OK) return rc;
+    WideArgs wa{};
+    wa.R = N; wa.Nout = p; wa.ldw = p; wa.out = agg; wa.ldo = p;
+    wa.pc[wa.np++] = WidePiece{Z, nullptr, ke, kz, b.We};
+    wa.pc[wa.np++] = WidePiece{Z + ke, nullptr, 1, kz, b.be};
+    GNB_TRY(launch_wide(ctx, wa));
+  }
+  if (q > 0) {
+    WideArgs wa{};
+    wa.R = N; wa.Nout = q; wa.ldw = q; wa.bias = b.bn; wa.out = h.n; wa.ldo = q;
+    wa.pc[wa.np++] = WidePiece{Z, nullptr, kz, kz, w.wnx};
+    if (bn_ > 0) wa.pc[wa.np++] = WidePiece{x.n, nullptr, bn_, bn_, b.Wn + (size_t)p * q};
+    if (c > 0) wa.pc[wa.np++] = WidePiece{x.g, g->node_graph, c, c, b.Wn + (size_t)(p + bn_) * q};
+    GNB_TRY(launch_wide(ctx, wa));
+  }
+  if (r > 0) GNB_TRY(run_graph_update_fp32(ctx, g, b, agg, h.n, x.g, h.g));
+  return GNB_OK;
+}
+
+// GNBlock with NARROW outputs (decoder): out_e, out_n <= 8; wide inputs streamed once, coalesced.
+static bool block_narrow_ok(const LayerW& w) {
+  const gnb_block_params& b = w.blk;
+  return w.kind == GNB_LAYER_BLOCK && b.out_e > 0 && b.out_e <= 8 && b.out_n <= 8 && b.in_e >= 32 && b.in_e <= 512 &&
+         b.in_n <= 512 && (b.in_e & 3) == 0 && (b.in_n & 3) == 0;
+}
+static int run_block_narrow(gnb_ctx* ctx, const gnb_graph* g, const LayerW& w, Feat x, FeatOut h) {
+  const gnb_block_params& b = w.blk;
+  const int a = b.in_e, bn_ = b.in_n, c = b.in_g, p = b.out_e, q = b.out_n, r = b.out_g;
+  const int64_t E = g->E, N = g->N, B = g->B;
+  int rc = GNB_OK;
+  float *Ps = nullptr, *Pr = nullptr, *Pu = nullptr;
+  if (bn_ > 0) {
+    Ps = arena_ptr<float>(ctx->arena, (size_t)N * p, &rc);
+    Pr = arena_ptr<float>(ctx->arena, (size_t)N * p, &rc);
+    if (rc != GNB_OK) return rc;
+    NarrowArgs na{};
+    na.R = N; na.No = p; na.ldw = p; na.nsrc = 1; na.ldo = p;
+    na.src[0] = NarrowSrc{x.n, bn_, bn_, b.We + (size_t)a * p};
+    na.out = Ps;
+    GNB_TRY(launch_narrow(ctx, na));
+    na.src[0].W = b.We + (size_t)(a + bn_) * p;
+    na.out = Pr;
+    GNB_TRY(launch_narrow(ctx, na));
+  }
+  if (c > 0) {
+    Pu = arena_ptr<float>(ctx->arena, (size_t)B * p, &rc);
+    if (rc != GNB_OK) return rc;
+    LinArgs la{};
+    la.R = B; la.Nout = p; la.ldw = p; la.nsrc = 1; la.ldo = p;
+    la.src[0] = mk_src(x.g, c, b.We + (size_t)(a + 2 * bn_) * p, nullptr);
+    la.bias = b.be; la.out = Pu;
+    GNB_TRY(launch_linear_fp32(ctx, la));
+  }
+  {
+    NarrowArgs na{};
+    na.R = E; na.No = p; na.ldw = p; na.nsrc = 1; na.ldo = p; na.out = h.e;
+    na.src[0] = NarrowSrc{x.e, a, a, b.We};
+    if (Ps) { na.add[na.nadd++] = NarrowAdd{Ps, g->edge_src, p}; na.add[na.nadd++] = NarrowAdd{Pr, g->edge_dst, p}; }
+    if (Pu) na.add[na.nadd++] = NarrowAdd{Pu, g->edge_graph, p};
+    else na.bias = b.be;
+    GNB_TRY(launch_narrow(ctx, na));
+  }
+  if (q == 0 && r == 0) return GNB_OK;
+  float* agg = arena_ptr<float>(ctx->arena, (size_t)N * p, &rc);
+  if (rc != GNB_OK) return rc;
+  GNB_TRY(launch_segsum(ctx, h.e, p, g->node_in_ptr, N, agg));
+  if (q > 0) {
+    float* Pun = nullptr;
+    if (c > 0) {
+      Pun = arena_ptr<float>(ctx->arena, (size_t)B * q, &rc);
+      if (rc != GNB_OK) return rc;
+      LinArgs la{};
+      la.R = B; la.Nout = q; la.ldw = q; la.nsrc = 1; la.ldo = q;
+      la.src[0] = mk_src(x.g, c, b.Wn + (size_t)(p + bn_) * q, nullptr);
+      la.bias = b.bn; la.out = Pun;
+      GNB_TRY(launch_linear_fp32(ctx, la));
+    }
+    NarrowArgs na{};
+    na.R = N; na.No = q; na.ldw = q; na.ldo = q; na.out = h.n;
+    na.src[na.nsrc++] = NarrowSrc{agg, p, p, b.Wn};
+    if (bn_ > 0) na.src[na.nsrc++] = NarrowSrc{x.n, bn_, bn_, b.Wn + (size_t)p * q};
+    if (Pun) na.add[na.nadd++] = NarrowAdd{Pun, g->node_graph, q};
+    else na.bias = b.bn;
+    GNB_TRY(launch_narrow(ctx, na));
+  }
+  if (r > 0) GNB_TRY(run_graph_update_fp32(ctx, g, b, agg, h.n, x.g, h.g));
+  return GNB_OK;
+}
+
 // y = (x + h) + W2 relu(W1 LN2(x) + b1) + b2       (src/gncore.jl:56-68, src/gnfeedforward.jl:27-31)
 int run_ffn_residual_fp32(gnb_ctx* ctx, int64_t R, int d, const gnb_ffn_params& f, const gnb_ln_params& ln2,
                           const float* x, const float* h, float* y) {
@@ -534,7 +719,11 @@ static int forward_device(gnb_ctx* ctx, const gnb_model* m, const gnb_graph* g, 
     if (w.blk.in_g == 0) x.g = nullptr;
     arena_rewind(ctx->arena, mark);
     if (w.kind == GNB_LAYER_BLOCK) {
-      GNB_TRY(run_block_fp32(ctx, g, w.blk, nullptr, x, y));
+      // GNB_PREC_FP32 keeps the reference's operation order (generic path); the other modes may take the
+      // algebraically equivalent streaming paths for narrow-input / narrow-output blocks
+      if (precision != GNB_PREC_FP32 && block_wide_ok(w)) GNB_TRY(run_block_wide(ctx, g, w, x, y));
+      else if (precision != GNB_PREC_FP32 && block_narrow_ok(w)) GNB_TRY(run_block_narrow(ctx, g, w, x, y));
+      else GNB_TRY(run_block_fp32(ctx, g, w.blk, nullptr, x, y));
     } else {
       bool use_tc = (precision != GNB_PREC_FP32) && w.tc != nullptr;
       if (precision == GNB_PREC_BF16 && !w.tc) {

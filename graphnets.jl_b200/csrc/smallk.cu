@@ -1,0 +1,277 @@
+// fp32 CUDA-core kernels for GNBlocks whose input OR output features are narrow (encoder / decoder
+// blocks, src/gnblock.jl:63-69).  These layers are HBM-bound: the wide side is streamed once, coalesced,
+// the narrow side lives in registers / shared memory.
+//
+//   k_wide   : out[r][0..N) = sum_p  in_p[idx_p ? idx_p[r] : r][0..d_p) . W_p  (+ bias)      sum_p d_p <= 32
+//              the [e | v_src | v_dst | u] concat (src/edgefninput.jl:1-8) is assembled per row in shared
+//              memory from the raw narrow inputs and never reaches HBM; one warp computes 8 rows x 128 columns
+//              per step with the weight block resident in shared memory.
+//   k_zsum   : Z[v] = [ sum_{e->v} e_e ; sum_{e->v} v_src(e) ; deg v_v ; deg u_g ; deg ]   (receiver CSR, ordered)
+//              by linearity of Dense:  sum_{e->v} (W_e z_e + b_e) = [W_e ; b_e] Z[v]  - the narrow inputs are
+//              aggregated, then transformed, so the wide h_e is never re-read for the edge->node sum
+//              (src/nodefninput.jl:3).
+//   k_narrow : out[r][0..No) = bias + sum_s x_s[r][0..K_s) . W_s + sum_j add_j[idx_j[r]][0..No)     No <= 8
+//              lane owns 4 consecutive k of a row (512 B coalesced row loads), butterfly reduction per output.
+#include "kernels.cuh"
+#include "smallk.cuh"
+
+namespace {
+
+constexpr int WK_MAX = 32;      // max concatenated input width of k_wide
+constexpr int WIDE_ROWS = 32;   // rows staged per warp step
+constexpr int WIDE_WARPS = 8;
+
+__global__ void __launch_bounds__(WIDE_WARPS * 32) k_wide(const WideArgs a) {
+  extern __shared__ __align__(16) float sm_w[];
+  // layout: Ws[K4][128] (column block of this CTA) | per-warp zin[WIDE_ROWS][K4]
+  const int K4 = a.K4;                       // total input width rounded up to a multiple of 4
+  float* Ws = sm_w;
+  float* zin_all = sm_w + (size_t)K4 * 128;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int col0 = blockIdx.y * 128;
+  // ---- weight block: rows = concatenated k, zero padded
+  for (int i = tid; i < K4 * 128; i += blockDim.x) {
+    const int k = i >> 7, n = i & 127;
+    float w = 0.f;
+    if (col0 + n < a.Nout) {
+      int kk = k;
+      for (int p = 0; p < a.np; p++) {
+        if (kk < a.pc[p].d) { w = a.pc[p].W[(size_t)kk * a.ldw + col0 + n]; break; }
+        kk -= a.pc[p].d;
+      }
+    }
+    Ws[i] = w;
+  }
+  __syncthreads();
+  float* zin = zin_all + (size_t)warp * WIDE_ROWS * K4;
+  const float4 bias = (a.bias && col0 + 4 * lane + 3 < a.Nout) ? *reinterpret_cast<const float4*>(a.bias + col0 + 4 * lane)
+                                                                 : make_float4(0.f, 0.f, 0.f, 0.f);
+  const int64_t nblocks = (a.R + WIDE_ROWS - 1) / WIDE_ROWS;
+  for (int64_t blk = (int64_t)blockIdx.x * WIDE_WARPS + warp; blk < nblocks; blk += (int64_t)gridDim.x * WIDE_WARPS) {
+    const int64_t row0 = blk * WIDE_ROWS;
+    const int rows = (int)((a.R - row0) < WIDE_ROWS ? (a.R - row0) : WIDE_ROWS);
+    // ---- assemble the concat rows of this block in shared memory (zero padded to K4)
+    __syncwarp();
+    int koff = 0;
+    for (int p = 0; p < a.np; p++) {
+      const WidePiece& P = a.pc[p];
+      if (P.idx == nullptr) {
+        // contiguous rows: coalesced over (row, k)
+        const float* src = P.x + (size_t)row0 * P.ldx;
+        if (P.ldx == P.d) {
+          for (int i = lane; i < rows * P.d; i += 32) zin[(i / P.d) * K4 + koff + (i % P.d)] = __ldg(src + i);
+        } else {
+          for (int i = lane; i < rows * P.d; i += 32) zin[(i / P.d) * K4 + koff + (i % P.d)] = __ldg(src + (size_t)(i / P.d) * P.ldx + (i % P.d));
+        }
+      } else {
+        const int64_t my = lane < rows ? (int64_t)__ldg(P.idx + row0 + lane) : 0;
+        for (int i = lane; i < rows * P.d; i += 32) {
+          const int r = i / P.d, k = i % P.d;
+          const int64_t g = __shfl_sync(0xffffffffu, my, r);
+          zin[r * K4 + koff + k] = __ldg(P.x + (size_t)g * P.ldx + k);
+        }
+      }
+      koff += P.d;
+    }
+    if (koff < K4) {
+      for (int i = lane; i < rows * (K4 - koff); i += 32) zin[(i / (K4 - koff)) * K4 + koff + (i % (K4 - koff))] = 0.f;
+    }
+    __syncwarp();
+    // ---- 8 rows x (4 columns per lane) per step
+#pragma unroll 1
+    for (int r0 = 0; r0 < rows; r0 += 8) {
+      float4 acc[8];
+#pragma unroll
+      for (int j = 0; j < 8; j++) acc[j] = bias;
+      for (int k = 0; k < K4; k += 4) {
+        const float4 w0 = *reinterpret_cast<const float4*>(Ws + (k + 0) * 128 + 4 * lane);
+        const float4 w1 = *reinterpret_cast<const float4*>(Ws + (k + 1) * 128 + 4 * lane);
+        const float4 w2 = *reinterpret_cast<const float4*>(Ws + (k + 2) * 128 + 4 * lane);
+        const float4 w3 = *reinterpret_cast<const float4*>(Ws + (k + 3) * 128 + 4 * lane);
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+          const float4 z = *reinterpret_cast<const float4*>(zin + (r0 + j) * K4 + k);   // broadcast
+          acc[j].x = fmaf(z.x, w0.x, acc[j].x); acc[j].y = fmaf(z.x, w0.y, acc[j].y);
+          acc[j].z = fmaf(z.x, w0.z, acc[j].z); acc[j].w = fmaf(z.x, w0.w, acc[j].w);
+          acc[j].x = fmaf(z.y, w1.x, acc[j].x); acc[j].y = fmaf(z.y, w1.y, acc[j].y);
+          acc[j].z = fmaf(z.y, w1.z, acc[j].z); acc[j].w = fmaf(z.y, w1.w, acc[j].w);
+          acc[j].x = fmaf(z.z, w2.x, acc[j].x); acc[j].y = fmaf(z.z, w2.y, acc[j].y);
+          acc[j].z = fmaf(z.z, w2.z, acc[j].z); acc[j].w = fmaf(z.z, w2.w, acc[j].w);
+          acc[j].x = fmaf(z.w, w3.x, acc[j].x); acc[j].y = fmaf(z.w, w3.y, acc[j].y);
+          acc[j].z = fmaf(z.w, w3.z, acc[j].z); acc[j].w = fmaf(z.w, w3.w, acc[j].w);
+        }
+      }
+      const int n = col0 + 4 * lane;
+#pragma unroll
+      for (int j = 0; j < 8; j++) {
+        if (r0 + j < rows) {
+          float* o = a.out + (size_t)(row0 + r0 + j) * a.ldo + n;
+          if (n + 3 < a.Nout) {
+            *reinterpret_cast<float4*>(o) = acc[j];
+          } else {
+            if (n + 0 < a.Nout) o[0] = acc[j].x + (a.bias ? a.bias[n + 0] : 0.f);
+            if (n + 1 < a.Nout) o[1] = acc[j].y + (a.bias ? a.bias[n + 1] : 0.f);
+            if (n + 2 < a.Nout) o[2] = acc[j].z + (a.bias ? a.bias[n + 2] : 0.f);
+          }
+        }
+      }
+    }
+  }
+}
+
+// One warp per node; lane k owns column k of Z (Kz <= 32).
+__global__ void k_zsum(const ZsumArgs a) {
+  const int64_t v = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (v >= a.N) return;
+  const int e0 = a.node_in_ptr[v], e1 = a.node_in_ptr[v + 1];
+  const float deg = (float)(e1 - e0);
+  const int k = lane;
+  const int o_s = a.de, o_v = a.de + a.dn, o_u = a.de + 2 * a.dn, o_d = a.de + 2 * a.dn + a.dg;
+  float s = 0.f;
+  if (k < o_s) {
+    for (int e = e0; e < e1; e++) s += a.ef[(size_t)e * a.de + k];
+  } else if (k < o_v) {
+    for (int e = e0; e < e1; e++) s += a.nf[(size_t)a.edge_src[e] * a.dn + (k - o_s)];
+  } else if (k < o_u) {
+    s = deg * a.nf[(size_t)v * a.dn + (k - o_v)];
+  } else if (k < o_d) {
+    s = deg * a.gf[(size_t)a.node_graph[v] * a.dg + (k - o_u)];
+  } else if (k == o_d) {
+    s = deg;
+  }
+  if (k <= o_d) a.Z[(size_t)v * (o_d + 1) + k] = s;
+}
+
+// lane owns k = 4*lane + 128*c (+0..3); one row per warp step, 4 rows in flight.
+template <int NO>
+__global__ void __launch_bounds__(256) k_narrow(const NarrowArgs a) {
+  __shared__ __align__(16) float Wsm[NARROW_KMAX * NO];   // [k][NO] of all direct sources, concatenated
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  int ktot = 0;
+  for (int s = 0; s < a.nsrc; s++) {
+    const int d = a.src[s].d;
+    for (int i = tid; i < d * NO; i += blockDim.x) {
+      const int k = i / NO, j = i % NO;
+      Wsm[(ktot + k) * NO + j] = j < a.No ? a.src[s].W[(size_t)k * a.ldw + j] : 0.f;
+    }
+    ktot += d;
+  }
+  __syncthreads();
+  const int64_t warps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  for (int64_t r0 = ((int64_t)blockIdx.x * (blockDim.x >> 5) + warp) * 4; r0 < a.R; r0 += warps * 4) {
+    float acc[4][NO];
+#pragma unroll
+    for (int u = 0; u < 4; u++)
+#pragma unroll
+      for (int j = 0; j < NO; j++) acc[u][j] = 0.f;
+    int kbase = 0;
+    for (int s = 0; s < a.nsrc; s++) {
+      const NarrowSrc& S = a.src[s];
+      const bool vec = ((S.ldx & 3) == 0) && ((((uintptr_t)S.x) & 15) == 0);
+      for (int k = 4 * lane; k < S.d; k += 128) {
+        float4 x[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+          const int64_t r = r0 + u < a.R ? r0 + u : a.R - 1;
+          if (vec && k + 3 < S.d) {
+            x[u] = __ldg(reinterpret_cast<const float4*>(S.x + (size_t)r * S.ldx + k));
+          } else {
+            const float* p = S.x + (size_t)r * S.ldx + k;
+            x[u].x = p[0];
+            x[u].y = k + 1 < S.d ? p[1] : 0.f;
+            x[u].z = k + 2 < S.d ? p[2] : 0.f;
+            x[u].w = k + 3 < S.d ? p[3] : 0.f;
+          }
+        }
+        const float* w = Wsm + (size_t)(kbase + k) * NO;
+        const bool t1 = k + 1 < S.d, t2 = k + 2 < S.d, t3 = k + 3 < S.d;
+#pragma unroll
+        for (int j = 0; j < NO; j++) {
+          const float w0 = w[j], w1 = t1 ? w[NO + j] : 0.f, w2 = t2 ? w[2 * NO + j] : 0.f, w3 = t3 ? w[3 * NO + j] : 0.f;
+#pragma unroll
+          for (int u = 0; u < 4; u++)
+            acc[u][j] = fmaf(x[u].w, w3, fmaf(x[u].z, w2, fmaf(x[u].y, w1, fmaf(x[u].x, w0, acc[u][j]))));
+        }
+      }
+      kbase += S.d;
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1)
+#pragma unroll
+      for (int u = 0; u < 4; u++)
+#pragma unroll
+        for (int j = 0; j < NO; j++) acc[u][j] += __shfl_xor_sync(0xffffffffu, acc[u][j], o);
+    // lanes 0 .. 4*No-1 finish one (row, output) each: bias + gathered addends
+    const int u = lane / NO, j = lane % NO;
+    if (u < 4 && j < a.No && r0 + u < a.R) {
+      float v = 0.f;
+#pragma unroll
+      for (int uu = 0; uu < 4; uu++)
+#pragma unroll
+        for (int jj = 0; jj < NO; jj++)
+          if (uu == u && jj == j) v = acc[uu][jj];
+      const int64_t r = r0 + u;
+      if (a.bias) v += a.bias[j];
+      for (int t = 0; t < a.nadd; t++) {
+        const int64_t ar = a.add[t].idx ? (int64_t)a.add[t].idx[r] : r;
+        v += a.add[t].a[(size_t)ar * a.add[t].lda + j];
+      }
+      a.out[(size_t)r * a.ldo + j] = v;
+    }
+  }
+}
+
+}  // namespace
+
+int launch_wide(gnb_ctx* ctx, const WideArgs& a0) {
+  if (a0.R <= 0 || a0.Nout <= 0) return GNB_OK;
+  WideArgs a = a0;
+  int K = 0;
+  for (int p = 0; p < a.np; p++) K += a.pc[p].d;
+  GNB_CHECK(K > 0 && K <= WK_MAX, "launch_wide: concatenated input width %d not in 1..%d", K, WK_MAX);
+  GNB_CHECK((a.ldo & 3) == 0 && ((uintptr_t)a.out & 15) == 0, "launch_wide: output must be 16-byte aligned rows");
+  a.K4 = (K + 3) / 4 * 4;
+  const size_t smem = ((size_t)a.K4 * 128 + (size_t)WIDE_WARPS * WIDE_ROWS * a.K4) * sizeof(float);
+  static bool attr = false;
+  if (!attr) {
+    GNB_CUDA(cudaFuncSetAttribute(k_wide, cudaFuncAttributeMaxDynamicSharedMemorySize, (WK_MAX * 128 + WIDE_WARPS * WIDE_ROWS * WK_MAX) * 4));
+    attr = true;
+  }
+  const int64_t nblocks = (a.R + WIDE_ROWS - 1) / WIDE_ROWS;
+  int64_t gx = (nblocks + WIDE_WARPS - 1) / WIDE_WARPS;
+  const int64_t cap = (int64_t)ctx->sm_count * 4;     // persistent over row blocks: the weight block is loaded once per CTA
+  if (gx > cap) gx = cap;
+  dim3 grid((unsigned)gx, (unsigned)ceil_div(a.Nout, 128));
+  double bytes = 4.0 * a.R * (K + a.Nout) + 4.0 * K * a.Nout;
+  for (int p = 0; p < a.np; p++) if (a.pc[p].idx) bytes += 4.0 * a.R;
+  Launch L(ctx, "wide_fp32", bytes, 2.0 * a.R * K * a.Nout);
+  k_wide<<<grid, WIDE_WARPS * 32, smem, ctx->stream>>>(a);
+  GNB_CUDA(cudaGetLastError());
+  return GNB_OK;
+}
+
+int launch_zsum(gnb_ctx* ctx, const ZsumArgs& a) {
+  if (a.N <= 0) return GNB_OK;
+  GNB_CHECK(a.de + 2 * a.dn + a.dg + 1 <= 32, "launch_zsum: aggregated input width > 32");
+  Launch L(ctx, "zsum_fp32", 0, 0);
+  k_zsum<<<ceil_div(a.N * 32, 256), 256, 0, ctx->stream>>>(a);
+  GNB_CUDA(cudaGetLastError());
+  return GNB_OK;
+}
+
+int launch_narrow(gnb_ctx* ctx, const NarrowArgs& a) {
+  if (a.R <= 0 || a.No <= 0) return GNB_OK;
+  int K = 0;
+  for (int s = 0; s < a.nsrc; s++) K += a.src[s].d;
+  GNB_CHECK(a.No <= 8 && K <= NARROW_KMAX, "launch_narrow: No %d > 8 or K %d > %d", a.No, K, NARROW_KMAX);
+  double bytes = 4.0 * a.R * (K + a.No * (1 + a.nadd));
+  Launch L(ctx, "narrow_fp32", bytes, 2.0 * a.R * K * a.No);
+  int64_t gx = (a.R + 31) / 32;            // 8 warps x 4 rows per CTA step
+  const int64_t cap = (int64_t)ctx->sm_count * 8;
+  if (gx > cap) gx = cap;
+  if (a.No <= 4) k_narrow<4><<<(unsigned)gx, 256, 0, ctx->stream>>>(a);
+  else k_narrow<8><<<(unsigned)gx, 256, 0, ctx->stream>>>(a);
+  GNB_CUDA(cudaGetLastError());
+  return GNB_OK;
+}

@@ -21,6 +21,7 @@
 #include <cuda_bf16.h>
 #include "kernels.cuh"
 #include "tc.cuh"
+#include "graphrows.cuh"
 
 namespace {
 
@@ -196,6 +197,8 @@ enum { SRC_LN = 0, SRC_AGG = 1 };
 struct ProjArgs {
   const float* x;                 // SRC_LN: [R][H];  SRC_AGG: partial rows [n_parts][H]
   const int32_t* part_ptr;        // SRC_AGG: [R+1] or nullptr
+  const float* x2;                // SRC_AGG (optional): second partial-row array summed with the same segments ...
+  float* sum2;                    // ... into sum2 [R][H] (fp32); pass sum2 as `addend` to add it to the output
   const float* addend;            // optional [*][H], added to output columns [add_col0, add_col0 + H)
   const int32_t* addend_idx;      // row of `addend` per output row (nullptr: the row itself)
   int add_col0;
@@ -215,7 +218,7 @@ constexpr int PJ_SMEM = PJ_OFF_MISC + 256 + 1024;
 enum { PB_WFULL = 0, PB_AREADY = 2, PB_ACCFREE = 3, PB_OUTDONE = 4 };
 
 template <int SRC>
-__global__ void __launch_bounds__(192, 1) k_tc_proj(const ProjArgs a) {
+__global__ void __launch_bounds__(192, 2) k_tc_proj(const ProjArgs a) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
@@ -296,31 +299,48 @@ __global__ void __launch_bounds__(192, 1) k_tc_proj(const ProjArgs a) {
           }
         }
       } else {
+        // partial rows of consecutive output rows are consecutive in memory (parts are numbered in edge order,
+        // edges are receiver-sorted): up to 2 partial rows per output row are fetched unconditionally, 4 output
+        // rows (8-16 loads) in flight; longer segments (a receiver spread over > 2 32-edge blocks) loop.
         int p0 = 0, p1 = 0;
         if (lane < wrows) {
           const int64_t r = row0 + warp * 32 + lane;
-          if (a.part_ptr) { p0 = a.part_ptr[r]; p1 = a.part_ptr[r + 1]; }
+          if (a.part_ptr) { p0 = __ldg(a.part_ptr + r); p1 = __ldg(a.part_ptr + r + 1); }
           else { p0 = (int)r; p1 = (int)r + 1; }
         }
+        const float4* X = reinterpret_cast<const float4*>(a.x) + lane;
+        const float4* X2 = reinterpret_cast<const float4*>(a.x2) + lane;
 #pragma unroll 1
         for (int i0 = 0; i0 < 32; i0 += 4) {
-          float4 s[4];
+          float4 s[4], t[4], s2[4], t2[4];
           int q0[4], q1[4];
 #pragma unroll
           for (int u = 0; u < 4; u++) {
             q0[u] = __shfl_sync(0xffffffffu, p0, i0 + u);
             q1[u] = __shfl_sync(0xffffffffu, p1, i0 + u);
-            s[u] = (q0[u] < q1[u]) ? __ldg(reinterpret_cast<const float4*>(a.x + (size_t)q0[u] * H) + lane) : f4zero();
+            s[u] = (q0[u] < q1[u]) ? __ldg(X + (size_t)q0[u] * (H / 4)) : f4zero();
+            t[u] = (q0[u] + 1 < q1[u]) ? __ldg(X + (size_t)(q0[u] + 1) * (H / 4)) : f4zero();
+            if (a.x2) {
+              s2[u] = (q0[u] < q1[u]) ? __ldg(X2 + (size_t)q0[u] * (H / 4)) : f4zero();
+              t2[u] = (q0[u] + 1 < q1[u]) ? __ldg(X2 + (size_t)(q0[u] + 1) * (H / 4)) : f4zero();
+            }
           }
 #pragma unroll
           for (int u = 0; u < 4; u++) {
-            for (int p = q0[u] + 1; p < q1[u]; p++) s[u] = f4add(s[u], __ldg(reinterpret_cast<const float4*>(a.x + (size_t)p * H) + lane));
+            s[u] = f4add(s[u], t[u]);
+            for (int p = q0[u] + 2; p < q1[u]; p++) s[u] = f4add(s[u], __ldg(X + (size_t)p * (H / 4)));
             uint2 pk;
             pk.x = pack_bf16(s[u].x, s[u].y);
             pk.y = pack_bf16(s[u].z, s[u].w);
             *reinterpret_cast<uint2*>(sm + PJ_OFF_A + sw_off(warp * 32 + i0 + u, 4 * lane)) = pk;
+            if (a.x2) {
+              s2[u] = f4add(s2[u], t2[u]);
+              for (int p = q0[u] + 2; p < q1[u]; p++) s2[u] = f4add(s2[u], __ldg(X2 + (size_t)p * (H / 4)));
+              if (i0 + u < wrows) *(reinterpret_cast<float4*>(a.sum2 + (size_t)(row0 + warp * 32 + i0 + u) * H) + lane) = s2[u];
+            }
           }
         }
+        __syncwarp();   // sum2 rows written above are read back (other lanes, same warp) by the epilogue
       }
       fence_async_smem();
       mbar_arrive(BAR(PB_AREADY));
@@ -345,10 +365,12 @@ __global__ void __launch_bounds__(192, 1) k_tc_proj(const ProjArgs a) {
               const int64_t ar = a.addend_idx ? (int64_t)__ldg(a.addend_idx + row0 + r) : row0 + r;
               ad = a.addend + (size_t)ar * H + (64 * ch - a.add_col0) + cq;
             }
+            float2 t[8];
+#pragma unroll
+            for (int n = 0; n < 8; n++) t[n] = ad ? *reinterpret_cast<const float2*>(ad + 8 * n) : make_float2(0.f, 0.f);
 #pragma unroll
             for (int n = 0; n < 8; n++) {
-              float2 v = make_float2(__uint_as_float(d[4 * n + 2 * h2]), __uint_as_float(d[4 * n + 2 * h2 + 1]));
-              if (ad) { const float2 t = *reinterpret_cast<const float2*>(ad + 8 * n); v.x += t.x; v.y += t.y; }
+              float2 v = make_float2(__uint_as_float(d[4 * n + 2 * h2]) + t[n].x, __uint_as_float(d[4 * n + 2 * h2 + 1]) + t[n].y);
               *reinterpret_cast<float2*>(o + 8 * n) = v;
             }
           }
@@ -929,7 +951,7 @@ static int launch_proj(gnb_ctx* ctx, const ProjArgs& a, const char* name, double
     GNB_CUDA(cudaFuncSetAttribute(k_tc_proj<SRC>, cudaFuncAttributeMaxDynamicSharedMemorySize, PJ_SMEM));
     attr_set = true;
   }
-  const int grid = a.num_tiles < ctx->sm_count ? a.num_tiles : ctx->sm_count;
+  const int grid = a.num_tiles < 2 * ctx->sm_count ? a.num_tiles : 2 * ctx->sm_count;
   Launch L(ctx, name, bytes, flops);
   k_tc_proj<SRC><<<grid, 192, PJ_SMEM, ctx->stream>>>(a);
   GNB_CUDA(cudaGetLastError());
@@ -951,21 +973,15 @@ int tc_core_forward(gnb_ctx* ctx, const gnb_graph* g, const TcCorePack* pk, cons
   float* agg = arena_ptr<float>(ctx->arena, (size_t)N * H, &rc);
   float* Pagg = arena_ptr<float>(ctx->arena, (size_t)N * H, &rc);
   float* hv = arena_ptr<float>(ctx->arena, (size_t)N * H, &rc);
-  float* se = arena_ptr<float>(ctx->arena, (size_t)B * H, &rc);
-  float* sv = arena_ptr<float>(ctx->arena, (size_t)B * H, &rc);
-  float* hu = arena_ptr<float>(ctx->arena, (size_t)B * H, &rc);
   if (rc != GNB_OK) return rc;
 
   // per-graph rows (fp32 CUDA cores, B rows): P_ue = W_eu LN1(gf) + be + folded LN shifts, P_un likewise
   {
-    LinArgs la{};
-    la.R = B; la.Nout = H; la.ldw = H; la.nsrc = 1; la.ldo = H;
-    la.src[0] = mk_src(xg, H, blk.We + (size_t)3 * H * H, &ln1[2]);
-    la.bias = pk->cu_e; la.out = Pue;
-    GNB_TRY(launch_linear_fp32(ctx, la));
-    la.src[0] = mk_src(xg, H, blk.Wn + (size_t)2 * H * H, &ln1[2]);
-    la.bias = pk->cu_n; la.out = Pun;
-    GNB_TRY(launch_linear_fp32(ctx, la));
+    GraphPreArgs ga{};
+    ga.xg = xg; ga.B = B; ga.gamma = ln1[2].gamma; ga.beta = ln1[2].beta; ga.eps = ln1[2].eps; ga.eps_mode = ln1[2].eps_mode;
+    ga.Weu = blk.We + (size_t)3 * H * H; ga.Wnu = blk.Wn + (size_t)2 * H * H;
+    ga.ce = pk->cu_e; ga.cn = pk->cu_n; ga.Pue = Pue; ga.Pun = Pun;
+    GNB_TRY(launch_graph_pre(ctx, ga));
   }
   const double HH = (double)H * H;
   {  // node projections P_s | P_r
@@ -988,10 +1004,9 @@ int tc_core_forward(gnb_ctx* ctx, const gnb_graph* g, const TcCorePack* pk, cons
     GNB_TRY(launch_core<MODE_EDGE>(ctx, a, "tc_edge_core", 24.0 * HH * E, (8.0 * H + 12.0) * E));
   }
   // edge -> node aggregate (src/nodefninput.jl:3) by linearity: agg = We_e' (sum ê) + sum (Ps + Pr + Pu)
-  GNB_TRY(launch_segsum(ctx, Gpart, H, g->node_part_ptr, N, Gs));
   {
     ProjArgs a{};
-    a.x = Epart; a.part_ptr = g->node_part_ptr; a.addend = Gs; a.out = agg; a.R = N; a.num_tiles = ceil_div(N, TM); a.nblk = 1;
+    a.x = Epart; a.part_ptr = g->node_part_ptr; a.x2 = Gpart; a.sum2 = Gs; a.addend = Gs; a.out = agg; a.R = N; a.num_tiles = ceil_div(N, TM); a.nblk = 1;
     a.wpack = pk->w_eblk;
     GNB_TRY(launch_proj<SRC_AGG>(ctx, a, "tc_agg", 2.0 * N * HH, 4.0 * N * 3 * H));
   }
@@ -1008,17 +1023,15 @@ int tc_core_forward(gnb_ctx* ctx, const gnb_graph* g, const TcCorePack* pk, cons
     a.add1 = Pagg; a.idx1 = nullptr; a.ld1 = H; a.add2 = Pun; a.idx2 = g->node_graph; a.ld2 = H; a.h_out = hv;
     GNB_TRY(launch_core<MODE_NODE>(ctx, a, "tc_node_core", 20.0 * HH * N, (8.0 * H + 8.0) * N));
   }
-  // graphs (B rows, fp32 CUDA cores): sums, graph update, graph FFN + residual
-  GNB_TRY(launch_segsum(ctx, agg, H, g->graph_node_ptr, B, se));
-  GNB_TRY(launch_segsum(ctx, hv, H, g->graph_node_ptr, B, sv));
+  // graphs (B rows, fp32 CUDA cores): sums over the graph's nodes, graph update, graph FFN + residual
   {
-    LinArgs la{};
-    la.R = B; la.Nout = H; la.ldw = H; la.ldo = H; la.out = hu; la.bias = blk.bg; la.nsrc = 3;
-    la.src[0] = mk_src(se, H, blk.Wg, nullptr);
-    la.src[1] = mk_src(sv, H, blk.Wg + (size_t)H * H, nullptr);
-    la.src[2] = mk_src(xg, H, blk.Wg + (size_t)2 * H * H, &ln1[2]);
-    GNB_TRY(launch_linear_fp32(ctx, la));
+    GraphPostArgs ga{};
+    ga.xg = xg; ga.B = B; ga.graph_node_ptr = g->graph_node_ptr; ga.agg = agg; ga.hv = hv;
+    ga.g1 = ln1[2].gamma; ga.b1ln = ln1[2].beta; ga.eps1 = ln1[2].eps; ga.eps_mode1 = ln1[2].eps_mode;
+    ga.g2 = ln2[2].gamma; ga.b2ln = ln2[2].beta; ga.eps2 = ln2[2].eps; ga.eps_mode2 = ln2[2].eps_mode;
+    ga.Wg = blk.Wg; ga.bg = blk.bg; ga.W1 = ffn[2].W1; ga.b1 = ffn[2].b1; ga.W2 = ffn[2].W2; ga.b2 = ffn[2].b2;
+    ga.yg = yg;
+    GNB_TRY(launch_graph_post(ctx, ga, N));
   }
-  GNB_TRY(run_ffn_residual_fp32(ctx, B, H, ffn[2], ln2[2], xg, hu, yg));
   return GNB_OK;
 }

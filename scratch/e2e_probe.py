@@ -7,9 +7,9 @@ B=4096
 adj, ef, nf = synth("cfg4", B, 1000)
 layers = W.model_params("cfg4"); model = W.to_gn_model(gn, layers)
 x = gn.batch_compact(adj, ef, nf); g=x.graphs; eng=g.engine
-for _ in range(3): y = model(x, precision="fp32")
+for _ in range(3): y = model(x, precision="auto")
 torch.cuda.synchronize()
-t0=time.perf_counter(); y = model(x, precision="fp32"); torch.cuda.synchronize(); print("device fwd wall", time.perf_counter()-t0)
+t0=time.perf_counter(); y = model(x, precision="auto"); torch.cuda.synchronize(); print("device fwd wall", time.perf_counter()-t0)
 mask = torch.from_numpy(np.ascontiguousarray((adj == 1).transpose(0, 2, 1)).astype(np.uint8)).pin_memory()
 h_ef, h_nf = torch.from_numpy(ef).pin_memory(), torch.from_numpy(nf).pin_memory()
 E,N=g.E,g.N
@@ -20,7 +20,7 @@ for i in range(5):
     h = C.c_void_p()
     rc=gn.lib.gnb_graph_lower(eng.ctx, P(mask), 1, 0, nn, 64, B, B, C.byref(h)); assert rc==0
     t1=time.perf_counter()
-    rc=gn.lib.gnb_model_forward_host(eng.ctx, mh, h, P(h_ef), P(h_nf), None, P(h_oe), P(h_on), P(h_og), 0); assert rc==0
+    rc=gn.lib.gnb_model_forward_host(eng.ctx, mh, h, P(h_ef), P(h_nf), None, P(h_oe), P(h_on), P(h_og), 3); assert rc==0
     t2=time.perf_counter()
     gn.lib.gnb_graph_destroy(h)
     t3=time.perf_counter()
