@@ -18,172 +18,14 @@
 // TMEM per sub-tile: D (128 cols, fp32 accumulator) | Hd (128 cols: FFN hidden chunk fp32, rewritten IN PLACE as
 // bf16 by the drain warps and consumed as the TMEM A operand of the down-projection; the 4H hidden activation
 // never touches shared or global memory).
-#include <cuda_bf16.h>
-#include "kernels.cuh"
+#include "tc_ptx.cuh"
 #include "tc.cuh"
 #include "graphrows.cuh"
+#include "tc_edge.cuh"
+
+using namespace tcx;
 
 namespace {
-
-constexpr int H = 128;             // feature width handled by this path
-constexpr int TM = 128;            // rows per tile (UMMA M)
-constexpr int BLK_BYTES = 32768;   // one 128x128 bf16 operand block
-constexpr int KB_BYTES = 16384;    // one 64-wide K half of a block: 128 rows x 128 B
-
-enum { MODE_EDGE = 0, MODE_NODE = 1 };
-
-// ------------------------------------------------------------------ PTX helpers
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-// Bounded spin: a protocol bug traps (launch error) instead of hanging the GPU.
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  uint32_t ok = 0;
-  for (uint32_t spin = 0; !ok; spin++) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok)
-        : "r"(bar), "r"(parity)
-        : "memory");
-    if (spin > (1u << 24)) __trap();
-  }
-}
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
-               "l"(src), "r"(bytes), "r"(bar)
-               : "memory");
-}
-__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-// One lane of a CONVERGED warp.  tcgen05.mma / commit take their operands from uniform registers; issuing
-// them from divergent code (if (lane == 0)) makes ptxas wrap every instruction in an ELECT/branch loop,
-// which costs ~2x the tensor-pipe time of a 128x128x16 UMMA (scratch/hwprobe.cu, T3).
-__device__ __forceinline__ bool elect_one() {
-  uint32_t pred;
-  asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
-  return pred != 0;
-}
-// D[tmem] (+)= A[smem] . B[smem]
-__device__ __forceinline__ void mma_ss(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
-      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
-      : "memory");
-}
-// D[tmem] (+)= A[tmem, bf16 pairs packed per 32-bit column] . B[smem]
-__device__ __forceinline__ void mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
-      "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accum)
-      : "memory");
-}
-// 32 lanes x 32 consecutive fp32 columns: thread i of the warp receives row (lane base + i)
-#define TC_LD32(taddr, r)                                                                                             \
-  asm volatile(                                                                                                       \
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "                                                                       \
-      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,"   \
-      "%29,%30,%31}, [%32];"                                                                                          \
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),   \
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),        \
-        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),       \
-        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])                     \
-      : "r"(taddr)                                                                                                    \
-      : "memory")
-// 16 lanes x 64 fp32 columns in the accumulator-fragment layout (verified by scratch/hwprobe.cu, T1):
-//   r[4n + 2h + c] of lane l = TMEM[lane base + l/4 + 8h][col base + 8n + 2(l%4) + c]
-// four consecutive lanes cover one 32-byte sector of a row: sector-exact global loads / stores from registers.
-#define TC_LD_FRAG64(taddr, r)                                                                                        \
-  asm volatile(                                                                                                       \
-      "tcgen05.ld.sync.aligned.16x256b.x8.b32 "                                                                       \
-      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,"   \
-      "%29,%30,%31}, [%32];"                                                                                          \
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),   \
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),        \
-        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),       \
-        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])                     \
-      : "r"(taddr)                                                                                                    \
-      : "memory")
-// 32 lanes x 16 columns store (thread i writes row lane base + i)
-#define TC_ST16(taddr, r)                                                                                             \
-  asm volatile(                                                                                                       \
-      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%16], {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15};" ::"r"( \
-          r[0]),                                                                                                      \
-      "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]),  \
-      "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(taddr)                                          \
-      : "memory")
-__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-__device__ __forceinline__ void tc_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
-
-// K-major, 128B-swizzled shared-memory matrix descriptor (cute::UMMA::SmemDescriptor layout):
-// start address >> 4 | LBO (unused for swizzled K-major, 1) | SBO = 1024 B between 8-row groups |
-// version 1 (Blackwell) | layout type 2 (SWIZZLE_128B)
-__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
-  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
-}
-// kind::f16 instruction descriptor: D=f32, A=B=bf16, both K-major, N=128, M=128
-constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
-
-// byte offset of element (row r, k) inside a 128-row K-major SW128 operand block (K <= 128)
-__device__ __forceinline__ uint32_t sw_off(int r, int k) {
-  return (uint32_t)((k >> 6) * KB_BYTES + r * 128 + ((((k & 63) >> 3) ^ (r & 7)) << 4) + (k & 7) * 2);
-}
-
-__device__ __forceinline__ float ln_rstd(float var, float eps, int mode) {
-  if (mode == GNB_EPS_SQRT_VAR_EPS2) return rsqrtf(var + eps * eps);
-  if (mode == GNB_EPS_STD_PLUS_EPS) return 1.0f / (sqrtf(var) + eps);
-  return rsqrtf(var + eps);
-}
-__device__ __forceinline__ float warp_sum(float v) {
-#pragma unroll
-  for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  return v;
-}
-// relu fused into the conversion: {lo, hi} = bf16(max(lo,0)), bf16(max(hi,0))
-__device__ __forceinline__ uint32_t pack_bf16_relu(float lo, float hi) {
-  uint32_t d;
-  asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
-  return d;
-}
-__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
-  __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
-  return *reinterpret_cast<uint32_t*>(&t);
-}
-__device__ __forceinline__ float4 f4add(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
-__device__ __forceinline__ float4 f4zero() { return make_float4(0.f, 0.f, 0.f, 0.f); }
-
-// one 128x128x128 block = 8 UMMAs of K=16; A block = two 64-wide K halves 16 KB apart, B = two ring stages.
-// Call from ONE elected lane of a converged warp.
-__device__ __forceinline__ void issue_ss(uint32_t d_tmem, uint64_t adesc, uint64_t w0, uint64_t w1, bool accumulate) {
-#pragma unroll
-  for (int ks = 0; ks < 4; ks++) mma_ss(d_tmem, adesc + 2 * ks, w0 + 2 * ks, IDESC, (accumulate || ks > 0) ? 1u : 0u);
-#pragma unroll
-  for (int ks = 0; ks < 4; ks++) mma_ss(d_tmem, adesc + (KB_BYTES >> 4) + 2 * ks, w1 + 2 * ks, IDESC, 1u);
-}
-// A operand in TMEM: bf16 pairs, 8 columns per K=16 step
-__device__ __forceinline__ void issue_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t w0, uint64_t w1, bool accumulate) {
-#pragma unroll
-  for (int ks = 0; ks < 4; ks++) mma_ts(d_tmem, a_tmem + 8 * ks, w0 + 2 * ks, IDESC, (accumulate || ks > 0) ? 1u : 0u);
-#pragma unroll
-  for (int ks = 0; ks < 4; ks++) mma_ts(d_tmem, a_tmem + 32 + 8 * ks, w1 + 2 * ks, IDESC, 1u);
-}
 
 // =====================================================================================================
 // Projection kernel: out = A . W for 1 or 2 weight blocks (N = 128 or 256), fp32 out.
@@ -992,16 +834,14 @@ int tc_core_forward(gnb_ctx* ctx, const gnb_graph* g, const TcCorePack* pk, cons
     GNB_TRY(launch_proj<SRC_LN>(ctx, a, "tc_node_proj", 2.0 * N * 2 * HH, 4.0 * N * 3 * H));
   }
   {  // edges: GNBlock edge update + FFN + residual; partial receiver sums of the inputs
-    CoreArgs a{};
+    EdgeArgs a{};
     a.x = xe; a.y = ye; a.R = E; a.num_tiles = ceil_div(E, TM); a.wpack = pk->w_edge;
     a.b1f = pk->b1f_e; a.b2 = ffn[0].b2; a.eps = ln1[0].eps; a.eps_mode = ln1[0].eps_mode;
     a.add1 = Psr; a.idx1 = g->edge_src; a.ld1 = 2 * H; a.add2 = Psr + H; a.idx2 = g->edge_dst; a.ld2 = 2 * H;
-    a.part = g->edge_part;
-    a.Epart = Epart; a.Gpart = Gpart;
-    a.dbg = g_tc_dbg;
+    a.part = g->edge_part; a.Epart = Epart; a.Gpart = Gpart; a.dbg = g_tc_dbg;
     // canonical work of the reference's edge update + edge FFN: 24 H^2 flops and
     // 8H bytes of features + 12 B of index per edge
-    GNB_TRY(launch_core<MODE_EDGE>(ctx, a, "tc_edge_core", 24.0 * HH * E, (8.0 * H + 12.0) * E));
+    GNB_TRY(launch_edge5(ctx, a, 24.0 * HH * E, (8.0 * H + 12.0) * E));
   }
   // edge -> node aggregate (src/nodefninput.jl:3) by linearity: agg = We_e' (sum ê) + sum (Ps + Pr + Pu)
   {

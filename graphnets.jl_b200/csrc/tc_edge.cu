@@ -1,0 +1,480 @@
+// Fused GNCore EDGE kernel for 128-wide features (tcgen05 / TMEM / bulk-async weights), generation 5.
+//
+//   y_e = x_e + [ W_ee' ê + P_s[src] + P_r'[dst] ] + [ W2 relu(W1' ê + b1') + b2 ]         ê = LayerNorm-normalised row
+//         (src/gnblock.jl:65 by linearity of Dense, src/gnfeedforward.jl:27-31, src/gncore.jl:56-68)
+//   E_part, G_part = ordered partial sums of ê and of the gathered addends per (32-row block, receiver) run
+//         (the edge -> node aggregation of src/nodefninput.jl:3, "aggregate, then transform")
+//
+// One 128-row tile per pass; persistent CTA, one per SM, 14 warps:
+//   warps 0-3   DRAIN : FFN hidden chunk TMEM fp32 -> +b1 -> relu -> bf16 -> TMEM (in place, the A operand of the
+//                       down-projection); finished accumulator TMEM -> swizzled shared-memory staging tile
+//   warps 4-7   LN    : one tile AHEAD of the MMAs: coalesced row loads (8 rows in flight per warp), LayerNorm with
+//                       transposed butterfly reductions, bf16 A operand into 128B-swizzled K-major shared memory,
+//                       partial sums E_part
+//   warps 8-11  OUT   : one tile BEHIND: staging row + x row + gathered P_s / P_r' rows, all 512 B coalesced,
+//                       -> y (streaming stores), partial sums G_part
+//   warp 12     MMA issuer (one elected lane), warp 13 weight loader (cp.async.bulk, 5 x 16 KB ring)
+// TMEM (512 columns): D[2] accumulators (double buffered across tiles: the epilogue of tile t overlaps the MMAs of
+// tile t+1) | Hd[2] hidden chunks (ping-pong inside a tile: the conversion of chunk c overlaps the MMAs of chunk c+1).
+// MMA order per tile (software-pipelined across tiles so that the tensor pipe never waits for a conversion):
+//   up1 blk down0 up2 down1 up3 down2 [up0 of the next tile] down3
+#include "tc_ptx.cuh"
+#include "tc_edge.cuh"
+
+using namespace tcx;
+
+namespace {
+
+constexpr int HALF_BYTES = KB_BYTES;   // weight ring stage = one 64-wide K half of a block (16 KB)
+constexpr int NWS = 5;
+constexpr int E_OFF_A = 0;                                   // 2 stages x 32 KB
+constexpr int E_OFF_W = 2 * BLK_BYTES;                       // 5 x 16 KB
+constexpr int E_OFF_STG = E_OFF_W + NWS * HALF_BYTES;        // 64 KB: [4 column groups][128 rows][128 B], 16B chunks XOR (row & 7)
+constexpr int E_OFF_MISC = E_OFF_STG + 65536;
+constexpr int E_MISC = 512 * 4 + 128 * 4 + 40 * 8 + 16;      // b1f[512], b2[128], barriers[40], tmem slot
+constexpr int E_SMEM = E_OFF_MISC + E_MISC + 1024;
+constexpr int E_WARPS = 14;
+constexpr int E_THREADS = E_WARPS * 32;
+enum { EB_WFULL = 0, EB_WEMPTY = 5, EB_AFULL = 10, EB_AEMPTY = 12, EB_HIDFULL = 14, EB_HSREADY = 16, EB_OUTDONE = 18,
+       EB_ACCFREE = 20, EB_STGFULL = 22, EB_STGEMPTY = 23 };
+
+// block ids inside the packed edge weights (tc.cu::tc_core_pack): W1_0 W_blk W2_0 W1_1 W2_1 W1_2 W2_2 W1_3 W2_3
+constexpr int PK_W1_0 = 0, PK_BLK = 1, PK_W2_0 = 2, PK_W1_1 = 3, PK_W2_1 = 4, PK_W1_2 = 5, PK_W2_2 = 6, PK_W1_3 = 7, PK_W2_3 = 8;
+// issue order of a tile: [up0 up1 blk] [dn0 dn1] [up2 up3] [dn2 dn3]  (grouped: every SS <-> TS operand-mode switch of the
+// tensor pipe costs ~435 cycles, scratch/hwprobe.cu T5), one nibble per block
+constexpr unsigned long long SEQ_PACKED = (unsigned long long)PK_W1_0 | ((unsigned long long)PK_W1_1 << 4) | ((unsigned long long)PK_BLK << 8) |
+    ((unsigned long long)PK_W2_0 << 12) | ((unsigned long long)PK_W2_1 << 16) | ((unsigned long long)PK_W1_2 << 20) |
+    ((unsigned long long)PK_W1_3 << 24) | ((unsigned long long)PK_W2_2 << 28) | ((unsigned long long)PK_W2_3 << 32);
+
+#ifdef GNB_TC_TIMING
+#define EDBG(k)                                                                                     \
+  do {                                                                                              \
+    if (a.dbg != nullptr && tl == 4 && lane == 0)                                                   \
+      a.dbg[((size_t)blockIdx.x * 18 + warp) * 32 + (k)] = (unsigned long long)clock64();           \
+  } while (0)
+#else
+#define EDBG(k) do { } while (0)
+#endif
+
+// sum over the 32 lanes of 8 per-lane values at once (transposed butterfly: 9 + 8 shuffles instead of 40);
+// every lane returns with all 8 totals
+__device__ __forceinline__ void warp_sum8(float (&v)[8], int lane) {
+  const bool h16 = lane & 16, h8 = lane & 8, h4 = lane & 4;
+  float w[4], z[2];
+#pragma unroll
+  for (int j = 0; j < 4; j++) {
+    const float send = h16 ? v[j] : v[j + 4], keep = h16 ? v[j + 4] : v[j];
+    w[j] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+  }
+#pragma unroll
+  for (int j = 0; j < 2; j++) {
+    const float send = h8 ? w[j] : w[j + 2], keep = h8 ? w[j + 2] : w[j];
+    z[j] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+  }
+  float t;
+  {
+    const float send = h4 ? z[0] : z[1], keep = h4 ? z[1] : z[0];
+    t = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+  }
+  t += __shfl_xor_sync(0xffffffffu, t, 2);
+  t += __shfl_xor_sync(0xffffffffu, t, 1);
+  // lane holds the total of row 4*bit4 + 2*bit3 + bit2
+#pragma unroll
+  for (int j = 0; j < 8; j++) v[j] = __shfl_sync(0xffffffffu, t, ((j & 4) ? 16 : 0) | ((j & 2) ? 8 : 0) | ((j & 1) ? 4 : 0));
+}
+
+// packed fp32x2 (FADD2 / FMUL2 / FFMA2 on sm_100): two lanes of a float4 per instruction
+__device__ __forceinline__ float4 add4(float4 a, float4 b) {
+  const float2 lo = __fadd2_rn(make_float2(a.x, a.y), make_float2(b.x, b.y)), hi = __fadd2_rn(make_float2(a.z, a.w), make_float2(b.z, b.w));
+  return make_float4(lo.x, lo.y, hi.x, hi.y);
+}
+__device__ __forceinline__ float4 adds4(float4 a, float s) {
+  const float2 ss = make_float2(s, s);
+  const float2 lo = __fadd2_rn(make_float2(a.x, a.y), ss), hi = __fadd2_rn(make_float2(a.z, a.w), ss);
+  return make_float4(lo.x, lo.y, hi.x, hi.y);
+}
+__device__ __forceinline__ float4 muls4(float4 a, float s) {
+  const float2 ss = make_float2(s, s);
+  const float2 lo = __fmul2_rn(make_float2(a.x, a.y), ss), hi = __fmul2_rn(make_float2(a.z, a.w), ss);
+  return make_float4(lo.x, lo.y, hi.x, hi.y);
+}
+__device__ __forceinline__ float sumsq4(float4 a) {
+  float2 t = __fmul2_rn(make_float2(a.x, a.y), make_float2(a.x, a.y));
+  t = __ffma2_rn(make_float2(a.z, a.w), make_float2(a.z, a.w), t);
+  return t.x + t.y;
+}
+// 1 / LayerNorm denominator without branches: e_add = eps^2 | 0 | eps and plus = 0 | eps | 0 for the three conventions
+__device__ __forceinline__ float rstd_nb(float var, float e_add, float plus) {
+  const float t = var + e_add;
+  const float r = rsqrtf(fmaxf(t, 1e-38f));
+  return plus > 0.f ? __frcp_rn(fmaf(t, r, plus)) : r;      // sqrt(t) = t * rsqrt(t)
+}
+
+__device__ __forceinline__ float4 ld_stream(const float* p) {   // read-once data: do not keep it in L1
+  float4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+  return v;
+}
+
+__global__ void __launch_bounds__(E_THREADS, 1) k_edge5(const EdgeArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* sm = smem_raw + (base - raw);
+  const uint32_t sW = base + E_OFF_W;
+  float* sB1 = reinterpret_cast<float*>(sm + E_OFF_MISC);
+  float* sB2 = sB1 + 512;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sB2 + 128);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 40);
+  const uint32_t bar0 = smem_u32(bars);
+  auto BAR = [&](int i) { return bar0 + 8u * (uint32_t)i; };
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  if (tid == 0) {
+    for (int i = 0; i < NWS; i++) { mbar_init(BAR(EB_WFULL + i), 1); mbar_init(BAR(EB_WEMPTY + i), 1); }
+    for (int s = 0; s < 2; s++) {
+      mbar_init(BAR(EB_AFULL + s), 128); mbar_init(BAR(EB_AEMPTY + s), 1);
+      mbar_init(BAR(EB_HIDFULL + s), 1); mbar_init(BAR(EB_HSREADY + s), 128);
+      mbar_init(BAR(EB_OUTDONE + s), 1); mbar_init(BAR(EB_ACCFREE + s), 128);
+    }
+    mbar_init(BAR(EB_STGFULL), 128); mbar_init(BAR(EB_STGEMPTY), 128);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 12) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  for (int i = tid; i < 512; i += E_THREADS) sB1[i] = a.b1f[i];
+  if (tid < 128) sB2[tid] = a.b2[tid];
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t HdA = tmem + 256, HdB = tmem + 384;
+  const int grid = gridDim.x;
+
+  if (warp == 13) {
+    // ===================================================== weight loader
+    uint32_t it = 0;
+    auto load_block = [&](int blk) {
+      for (int half = 0; half < 2; half++, it++) {
+        const uint32_t st = it % NWS, ph = (it / NWS) & 1;
+        mbar_wait(BAR(EB_WEMPTY + st), ph ^ 1);
+        if (elect_one()) {
+          const uint32_t nb = (uint32_t)HALF_BYTES;
+          mbar_expect_tx(BAR(EB_WFULL + st), nb);
+          bulk_g2s(sW + st * HALF_BYTES, reinterpret_cast<const uint8_t*>(a.wpack) + (size_t)blk * BLK_BYTES + (size_t)half * HALF_BYTES,
+                   nb, BAR(EB_WFULL + st));
+        }
+        __syncwarp();
+      }
+    };
+    for (int tile = blockIdx.x; tile < a.num_tiles; tile += grid) {
+#pragma unroll 1
+      for (int b = 0; b < 9; b++) load_block((SEQ_PACKED >> (4 * b)) & 15);
+    }
+  } else if (warp == 12) {
+    // ===================================================== MMA issuer (whole warp converged, one lane issues)
+    uint32_t it = 0, tl = 0;
+    uint64_t w0 = 0, w1 = 0;
+    uint32_t st0 = 0, st1 = 0;
+    auto get_w = [&]() {
+      st0 = it % NWS; st1 = (it + 1) % NWS;
+      const uint32_t ph0 = (it / NWS) & 1, ph1 = ((it + 1) / NWS) & 1;
+      it += 2;
+      mbar_wait(BAR(EB_WFULL + st0), ph0);
+      mbar_wait(BAR(EB_WFULL + st1), ph1);
+      w0 = umma_desc(sW + st0 * HALF_BYTES);
+      w1 = umma_desc(sW + st1 * HALF_BYTES);
+    };
+    for (int tile = blockIdx.x; tile < a.num_tiles; tile += grid, tl++) {
+      const uint32_t st = tl & 1, uph = (tl >> 1) & 1;
+      const uint64_t adesc = umma_desc(base + E_OFF_A + st * BLK_BYTES);
+      const uint32_t D = tmem + 128 * st;
+#pragma unroll 1
+      for (int b = 0; b < 9; b++) {
+        EDBG(b);
+        get_w();
+        const bool is_dn = (b == 3) | (b == 4) | (b == 7) | (b == 8);
+        const int hb = ((b == 0) | (b == 3) | (b == 5) | (b == 7)) ? 0 : 1;      // hidden buffer of an up / down block
+        const uint32_t Hd = hb ? HdB : HdA;
+        if (b == 0) mbar_wait(BAR(EB_AFULL + st), uph);                          // A tile of this pass
+        if (b == 2) mbar_wait(BAR(EB_ACCFREE + st), uph ^ 1);                    // accumulator drained (two tiles ago)
+        if (is_dn) mbar_wait(BAR(EB_HSREADY + hb), b >= 7 ? 1u : 0u);            // hidden chunk converted to bf16
+        tc_fence_after();
+        if (elect_one()) {
+          if (is_dn) {
+            issue_ts(D, Hd, w0, w1, true);                                       // D += relu(.)[chunk] W2_c
+          } else if (b == 2) {
+            issue_ss(D, adesc, w0, w1, false);                                   // GNBlock GEMM: first write of D
+          } else {
+            issue_ss(Hd, adesc, w0, w1, false);                                  // FFN up-projection chunk
+            tc_commit(BAR(EB_HIDFULL + hb));
+          }
+          if (b == 6) tc_commit(BAR(EB_AEMPTY + st));                            // last read of the A tile
+          if (b == 8) tc_commit(BAR(EB_OUTDONE + st));                           // accumulator complete
+          tc_commit(BAR(EB_WEMPTY + st0));
+          tc_commit(BAR(EB_WEMPTY + st1));
+        }
+        __syncwarp();
+      }
+      EDBG(9);
+    }
+  } else if (warp < 4) {
+    // ===================================================== DRAIN warps (TMEM lane quadrant = warp)
+    const uint32_t lane_base = ((uint32_t)(warp * 32)) << 16;
+    uint32_t tl = 0;
+    auto convert = [&](uint32_t Hd, int c) {
+      // TMEM fp32 -> +b1 -> relu -> bf16 pairs -> TMEM, in place (columns [16j,16j+16) were read in iteration <= j)
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        uint32_t v[32], p[16];
+        TC_LD32(Hd + lane_base + 32 * j, v);
+        tc_wait_ld();
+        const float4* bb = reinterpret_cast<const float4*>(sB1 + c * 128 + j * 32);
+#pragma unroll
+        for (int t = 0; t < 8; t++) {
+          const float4 b = bb[t];
+          const float2 lo = __fadd2_rn(make_float2(__uint_as_float(v[4 * t]), __uint_as_float(v[4 * t + 1])), make_float2(b.x, b.y));
+          const float2 hi = __fadd2_rn(make_float2(__uint_as_float(v[4 * t + 2]), __uint_as_float(v[4 * t + 3])), make_float2(b.z, b.w));
+          p[2 * t] = pack_bf16_relu(lo.x, lo.y);
+          p[2 * t + 1] = pack_bf16_relu(hi.x, hi.y);
+        }
+        TC_ST16(Hd + lane_base + 16 * j, p);
+      }
+      tc_wait_st();
+      tc_fence_before();
+    };
+    for (int tile = blockIdx.x; tile < a.num_tiles; tile += grid, tl++) {
+      const uint32_t st = tl & 1, uph = (tl >> 1) & 1;
+      EDBG(0);
+#pragma unroll 1
+      for (int c = 0; c < 4; c++) {
+        mbar_wait(BAR(EB_HIDFULL + (c & 1)), (c >> 1) & 1);
+        EDBG(1 + 2 * c);
+        tc_fence_after();
+        convert((c & 1) ? HdB : HdA, c);
+        mbar_arrive(BAR(EB_HSREADY + (c & 1)));
+        EDBG(2 + 2 * c);
+      }
+      // ---------------- finished accumulator -> staging tile (row r = this thread; 4 column groups of 32 fp32)
+      mbar_wait(BAR(EB_OUTDONE + st), uph);
+      EDBG(9);
+      tc_fence_after();
+      mbar_wait(BAR(EB_STGEMPTY), (tl & 1) ^ 1);
+      EDBG(10);
+      const uint32_t D = tmem + 128 * st;
+      const int r = warp * 32 + lane;
+      uint8_t* srow = sm + E_OFF_STG + r * 128;
+#pragma unroll
+      for (int g = 0; g < 4; g++) {
+        uint32_t v[32];
+        TC_LD32(D + lane_base + 32 * g, v);
+        tc_wait_ld();
+        if (g == 3) {   // TMEM fully read: the accumulator goes back to the MMA warp
+          tc_fence_before();
+          mbar_arrive(BAR(EB_ACCFREE + st));
+        }
+#pragma unroll
+        for (int j = 0; j < 8; j++)
+          *reinterpret_cast<uint4*>(srow + g * 16384 + ((j ^ (r & 7)) << 4)) = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+      }
+      mbar_arrive(BAR(EB_STGFULL));
+      EDBG(11);
+    }
+  } else if ((warp & 2) == 0) {
+    // ===================================================== LN warps (4, 5, 8, 9), one tile ahead of the MMAs
+    // 8 lanes per row: lane (rr = lane >> 3, l8 = lane & 7) holds columns 4 l8 + 32 j .. +3 (j = 0..3) of row i0 + rr, so
+    // one load instruction covers 4 rows x 128 contiguous bytes and a row statistic needs 3 shuffle levels instead of 5.
+    const int q = (warp & 1) + ((warp >> 3) << 1);
+    const int rr = lane >> 3, l8 = lane & 7;
+    const float* xbase = a.x + 4 * l8;
+    // swizzled A operand, element (row 32q + i, k = 4 l8 + 32 j): byte (k >> 6) * 16 KB + row * 128 + ((chunk ^ (row & 7)) << 4) + (l8 & 1) * 8
+    const uint32_t a_lane = (uint32_t)((32 * q) * 128 + (l8 & 1) * 8);
+    const uint32_t a_chunk = (uint32_t)(l8 >> 1);            // + 4 (j & 1)
+    // partial-sum pass: lane owns columns 4 lane .. 4 lane + 3 of every row of the slice
+    const uint32_t p_lane = (uint32_t)((lane >> 4) * KB_BYTES + (32 * q) * 128 + (lane & 1) * 8);
+    const uint32_t p_chunk = (uint32_t)((lane & 15) >> 1);
+    const float e_add = a.eps_mode == GNB_EPS_SQRT_VAR_EPS2 ? a.eps * a.eps : (a.eps_mode == GNB_EPS_STD_PLUS_EPS ? 0.f : a.eps);
+    const float e_plus = a.eps_mode == GNB_EPS_STD_PLUS_EPS ? a.eps : 0.f;
+    uint32_t tl = 0;
+    for (int tile = blockIdx.x; tile < a.num_tiles; tile += grid, tl++) {
+      const uint32_t stage = tl & 1, aph = (tl >> 1) & 1;
+      const int64_t row0 = (int64_t)tile * TM + 32 * q;
+      const int64_t left = a.R - row0;
+      const int rows = left < 0 ? 0 : (left > 32 ? 32 : (int)left);
+      int my_pid = -1;
+      if (lane < rows) my_pid = __ldg(a.part + row0 + lane);
+      const int nxt = __shfl_down_sync(0xffffffffu, my_pid, 1);
+      const uint32_t endmask = __ballot_sync(0xffffffffu, lane < rows && (lane == rows - 1 || nxt != my_pid));
+      int pid = __shfl_sync(0xffffffffu, my_pid, 0);
+      EDBG(0);
+      float4 xa[2][4];   // two 4-row steps in flight
+      auto issue = [&](int i0) {
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+          int64_t r = row0 + i0 + 4 * h + rr;
+          r = r < a.R ? r : a.R - 1;      // rows past the end re-read the last row; masked below
+          const float4* p = reinterpret_cast<const float4*>(xbase + (size_t)r * H);
+#pragma unroll
+          for (int j = 0; j < 4; j++) xa[h][j] = __ldg(p + 8 * j);
+        }
+      };
+      issue(0);
+      mbar_wait(BAR(EB_AEMPTY + stage), aph ^ 1);
+      EDBG(1);
+      uint8_t* A = sm + E_OFF_A + stage * BLK_BYTES;
+#pragma unroll 1
+      for (int i0 = 0; i0 < 32; i0 += 8) {
+        float4 xc[2][4];
+        float s[2];
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+#pragma unroll
+          for (int j = 0; j < 4; j++) xc[h][j] = xa[h][j];
+          const float4 t = add4(add4(xc[h][0], xc[h][1]), add4(xc[h][2], xc[h][3]));
+          s[h] = (t.x + t.y) + (t.z + t.w);
+        }
+        if (i0 + 8 < 32) issue(i0 + 8);
+#pragma unroll
+        for (int o = 1; o < 8; o <<= 1) {
+#pragma unroll
+          for (int h = 0; h < 2; h++) s[h] += __shfl_xor_sync(0xffffffffu, s[h], o);
+        }
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+          const float nmu = -s[h] * (1.0f / H);
+          float2 t2 = make_float2(0.f, 0.f);
+#pragma unroll
+          for (int j = 0; j < 4; j++) {
+            xc[h][j] = adds4(xc[h][j], nmu);
+            t2 = __ffma2_rn(make_float2(xc[h][j].x, xc[h][j].y), make_float2(xc[h][j].x, xc[h][j].y), t2);
+            t2 = __ffma2_rn(make_float2(xc[h][j].z, xc[h][j].w), make_float2(xc[h][j].z, xc[h][j].w), t2);
+          }
+          s[h] = t2.x + t2.y;
+        }
+#pragma unroll
+        for (int o = 1; o < 8; o <<= 1) {
+#pragma unroll
+          for (int h = 0; h < 2; h++) s[h] += __shfl_xor_sync(0xffffffffu, s[h], o);
+        }
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+          const int i = i0 + 4 * h + rr;
+          const float rs = (i < rows) ? rstd_nb(s[h] * (1.0f / H), e_add, e_plus) : 0.f;
+          const uint32_t rowoff = a_lane + (uint32_t)i * 128;
+#pragma unroll
+          for (int j = 0; j < 4; j++) {
+            const float4 xh = muls4(xc[h][j], rs);
+            uint2 pk;
+            pk.x = pack_bf16(xh.x, xh.y);
+            pk.y = pack_bf16(xh.z, xh.w);
+            *reinterpret_cast<uint2*>(A + (j >> 1) * KB_BYTES + rowoff + (((a_chunk + 4 * (j & 1)) ^ (uint32_t)(i & 7)) << 4)) = pk;
+          }
+        }
+        EDBG(2 + (i0 >> 3));
+      }
+      // ---- ordered partial sums per (32-row block, receiver) run, taken over the bf16 operand the MMAs consume
+      __syncwarp();
+      {
+        float4 acc = f4zero();
+#pragma unroll 4
+        for (int i = 0; i < 32; i++) {
+          const uint2 v = *reinterpret_cast<const uint2*>(A + p_lane + i * 128 + ((p_chunk ^ (uint32_t)(i & 7)) << 4));
+          acc = add4(acc, make_float4(__uint_as_float(v.x << 16), __uint_as_float(v.x & 0xffff0000u), __uint_as_float(v.y << 16),
+                                      __uint_as_float(v.y & 0xffff0000u)));
+          if ((endmask >> i) & 1u) {
+            *(reinterpret_cast<float4*>(a.Epart + (size_t)pid * H) + lane) = acc;
+            acc = f4zero();
+            pid++;
+          }
+        }
+      }
+      fence_async_smem();
+      mbar_arrive(BAR(EB_AFULL + stage));
+      EDBG(6);
+    }
+  } else {
+    // ===================================================== OUT warps (6, 7, 10, 11), one tile behind the MMAs
+    const int q = (warp & 1) + ((warp >> 3) << 1);
+    const float4 b2v = *reinterpret_cast<const float4*>(sB2 + 4 * lane);
+    const float* xbase = a.x + 4 * lane;
+    const float* base1 = a.add1 + 4 * lane;
+    const float* base2 = a.add2 + 4 * lane;
+    const uint32_t s_lane = (uint32_t)(E_OFF_STG + (lane >> 3) * 16384 + (32 * q) * 128);
+    const uint32_t s_chunk = (uint32_t)(lane & 7);
+    uint32_t tl = 0;
+    for (int tile = blockIdx.x; tile < a.num_tiles; tile += grid, tl++) {
+      const int64_t row0 = (int64_t)tile * TM + 32 * q;
+      const int64_t left = a.R - row0;
+      const int rows = left < 0 ? 0 : (left > 32 ? 32 : (int)left);
+      int my_i1 = 0, my_i2 = 0, my_pid = -1;
+      if (lane < rows) {
+        my_i1 = __ldg(a.idx1 + row0 + lane);
+        my_i2 = __ldg(a.idx2 + row0 + lane);
+        my_pid = __ldg(a.part + row0 + lane);
+      }
+      const int nxt = __shfl_down_sync(0xffffffffu, my_pid, 1);
+      const uint32_t endmask = __ballot_sync(0xffffffffu, lane < rows && (lane == rows - 1 || nxt != my_pid));
+      int pid = __shfl_sync(0xffffffffu, my_pid, 0);
+      EDBG(0);
+      float4 xa[4], pa[4], pb[4];
+      auto issue1 = [&](int u, int i) {
+        const int i1 = __shfl_sync(0xffffffffu, my_i1, i), i2 = __shfl_sync(0xffffffffu, my_i2, i);
+        int64_t r = row0 + i;
+        r = r < a.R ? r : a.R - 1;
+        xa[u] = ld_stream(xbase + (size_t)r * H);                       // second and last read of x: L2 hit
+        pa[u] = __ldg(reinterpret_cast<const float4*>(base1 + (size_t)i1 * a.ld1));
+        pb[u] = __ldg(reinterpret_cast<const float4*>(base2 + (size_t)i2 * a.ld2));
+      };
+#pragma unroll
+      for (int u = 0; u < 4; u++) issue1(u, u);
+      mbar_wait(BAR(EB_STGFULL), tl & 1);
+      EDBG(1);
+      float4 acc = f4zero();
+#pragma unroll 1
+      for (int i0 = 0; i0 < 32; i0 += 4) {
+        float4 d[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+          const int i = i0 + u;
+          d[u] = *reinterpret_cast<const float4*>(sm + s_lane + i * 128 + ((s_chunk ^ (uint32_t)(i & 7)) << 4));
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+          const int i = i0 + u;
+          const float4 g = add4(pa[u], pb[u]);
+          const float4 y = add4(add4(add4(xa[u], g), d[u]), b2v);
+          if (i < rows) __stcs(reinterpret_cast<float4*>(a.y + (size_t)(row0 + i) * H) + lane, y);
+          acc = add4(acc, g);
+          const bool fl = (endmask >> i) & 1u;
+          if (fl) *(reinterpret_cast<float4*>(a.Gpart + (size_t)pid * H) + lane) = acc;
+          acc.x = fl ? 0.f : acc.x; acc.y = fl ? 0.f : acc.y; acc.z = fl ? 0.f : acc.z; acc.w = fl ? 0.f : acc.w;
+          pid += fl ? 1 : 0;
+          if (i0 + 4 < 32) issue1(u, i + 4);   // refill this slot with the same row of the next group
+        }
+      }
+      mbar_arrive(BAR(EB_STGEMPTY));
+      EDBG(2);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 12) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+}
+
+}  // namespace
+
+int launch_edge5(gnb_ctx* ctx, const EdgeArgs& a, double flops, double bytes) {
+  if (a.num_tiles <= 0) return GNB_OK;
+  static bool attr_set = false;
+  if (!attr_set) {
+    GNB_CUDA(cudaFuncSetAttribute(k_edge5, cudaFuncAttributeMaxDynamicSharedMemorySize, E_SMEM));
+    attr_set = true;
+  }
+  const int grid = a.num_tiles < ctx->sm_count ? a.num_tiles : ctx->sm_count;
+  Launch L(ctx, "tc_edge_core", bytes, flops);
+  k_edge5<<<grid, E_THREADS, E_SMEM, ctx->stream>>>(a);
+  GNB_CUDA(cudaGetLastError());
+  return GNB_OK;
+}

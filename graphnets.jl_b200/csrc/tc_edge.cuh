@@ -1,0 +1,25 @@
+// Fused GNCore edge kernel (tcgen05, generation 5); internal interface.
+#pragma once
+#include <cuda_bf16.h>
+#include "common.cuh"
+
+struct EdgeArgs {
+  const float* x;     // [R][128] edge features
+  float* y;           // [R][128] core output
+  int64_t R;
+  int num_tiles;
+  const __nv_bfloat16* wpack;   // 9 packed 32 KB weight blocks (tc.cu::tc_core_pack, edge order)
+  const float* b1f;   // [512] FFN bias with the LN2 shift folded in
+  const float* b2;    // [128]
+  float eps;
+  int eps_mode;
+  // gathered fp32 addend rows: g = add1[idx1[r]] + add2[idx2[r]]   (sender projection, receiver projection + per-graph row)
+  const float* add1; const int32_t* idx1; int ld1;
+  const float* add2; const int32_t* idx2; int ld2;
+  const int32_t* part;   // partial-row id per edge (32-row blocks, receiver runs)
+  float* Epart;          // out [n_parts][128] partial sums of the normalised edge rows
+  float* Gpart;          // out [n_parts][128] partial sums of the gathered addends
+  unsigned long long* dbg;
+};
+
+int launch_edge5(gnb_ctx* ctx, const EdgeArgs& a, double flops, double bytes);

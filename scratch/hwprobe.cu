@@ -259,6 +259,73 @@ __global__ void __launch_bounds__(512, 1) k_probe4(int mode, int iters, long lon
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
 }
 
+
+// ------------------------------------------------------------------------------------------------ T5
+// per 128x128x128 block: 8 UMMAs + NC commits to rotating mbarriers (the fused kernel's issue pattern)
+template <int NC, int ALT>
+__global__ void __launch_bounds__(192, 1) k_probe5(int nblocks, long long* out_cycles) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* sm = smem_raw + (base - raw);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sm + 131072);
+  uint32_t* slot = reinterpret_cast<uint32_t*>(bars + 16);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  for (int i = tid; i < 131072 / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(sm)[i] = 0;
+  if (tid == 0) { for (int i = 0; i < 12; i++) mbar_init(smem_u32(bars + i), 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+  if (warp == 4) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  fence_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *slot;
+  if (warp == 4) {
+    const uint32_t sA = base, sB = base + 32768;
+    constexpr uint32_t idesc = make_idesc(128, 128);
+    const uint64_t dA = umma_desc(sA), dB = umma_desc(sB);
+    long long t0 = clock64();
+    for (int b = 0; b < nblocks; b++) {
+      if (elect_one()) {
+        // ALT bits: 1 = alternate accumulator per block, 2 = TS for every other pair of blocks, 4 = overwrite (accumulate=0) at block start,
+        //           8 = all TS, 16 = N=256 accumulators side by side (single MMA writes 256 columns)
+        const uint32_t D = tmem + (((ALT & 1) && (b & 1)) ? 128u : 0u);
+#pragma unroll
+        for (int ks = 0; ks < 8; ks++) {
+          const uint32_t off = (uint32_t)((ks >> 2) * 16384 + (ks & 3) * 32);
+          const uint32_t acc = ((ALT & 4) && ks == 0) ? 0u : 1u;
+          if ((ALT & 8) || ((ALT & 2) && (b & 2))) mma_ts(D, tmem + 256 + 8 * ks, dB + (off >> 4), idesc, acc);
+          else mma_ss(D, dA + (off >> 4), dB + (off >> 4), idesc, acc);
+        }
+#pragma unroll
+        for (int c = 0; c < NC; c++) tc_commit(smem_u32(bars + 1 + ((b + c) % 8)));
+      }
+      __syncwarp();
+    }
+    if (elect_one()) tc_commit(smem_u32(bars));
+    __syncwarp();
+    mbar_wait(smem_u32(bars), 0);
+    long long t1 = clock64();
+    if (lane == 0) out_cycles[blockIdx.x] = t1 - t0;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+}
+template <int NC, int ALT>
+void run5(const char* name, long long* dC) {
+  CK(cudaFuncSetAttribute(k_probe5<NC, ALT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 133000));
+  int nb = 64, grid = 148;
+  k_probe5<NC, ALT><<<grid, 192, 133000>>>(nb, dC);
+  CK(cudaDeviceSynchronize());
+  std::vector<long long> c(grid);
+  CK(cudaMemcpy(c.data(), dC, grid * 8, cudaMemcpyDeviceToHost));
+  long long mx = 0; for (auto v : c) mx = v > mx ? v : mx;
+  printf("T5: %-40s: %.0f cycles per 128x128x128 block\n", name, (double)mx / nb);
+}
+
 int main() {
   // ---------------- T1 + T2
   {
@@ -307,6 +374,19 @@ int main() {
     run3<false, 128, true>("SS N=128 + smem traffic", dC);
     run3<true, 128, true>("TS N=128 + smem traffic", dC);
     run3<true, 64, true>("TS N=64 + smem traffic", dC);
+  }
+  // ---------------- T5
+  {
+    long long* dC; CK(cudaMalloc(&dC, 148 * 8));
+    run5<1, 0>("SS same D", dC);
+    run5<1, 1>("SS alternate D per block", dC);
+    run5<1, 4>("SS same D, overwrite at block start", dC);
+    run5<1, 5>("SS alternate D + overwrite", dC);
+    run5<1, 8>("TS same D", dC);
+    run5<1, 9>("TS alternate D", dC);
+    run5<1, 2>("SS/TS switching every 2 blocks, same D", dC);
+    run5<1, 3>("SS/TS switching + alternate D", dC);
+    run5<1, 7>("SS/TS switching + alternate D + overwrite", dC);
   }
   // ---------------- T4
   {

@@ -1,4 +1,4 @@
-"""clock64 phase timing of one steady-state tile pair of the fused edge kernel (gnb_debug_tc_timing)."""
+"""clock64 phase timing of one steady-state tile of the fused edge kernel (gnb_debug_tc_timing)."""
 import sys, ctypes as C; sys.path.insert(0, '.')
 import numpy as np, torch
 import graphnets_b200 as gn, workloads as W
@@ -16,15 +16,13 @@ t = np.array(buf[:], dtype=np.int64).reshape(148, 18, 32)
 def show(name, warps, slots, labels):
     print("==", name)
     for cta in (0, 77):
-        base = t[cta, 16, 0]      # MMA warp block 0 start
+        base = t[cta, 12, 0]      # MMA warp, start of the tile
         for w in warps:
             print("  cta %3d warp %2d: " % (cta, w) + " ".join("%s=%d" % (l, t[cta, w, k] - base) for k, l in zip(slots, labels)))
-    d = np.stack([t[:, w, :] for w in warps], 1).astype(float)  # [cta, nw, 32]
+    d = np.stack([t[:, w, :] for w in warps], 1).astype(float)
     dd = np.diff(d[:, :, slots], axis=2).mean(axis=(0, 1))
     print("  mean deltas:", " ".join("%s=%.0f" % (l, v) for l, v in zip(labels[1:], dd)))
-show("MMA warp: block start / after W wait / after issue", [16], list(range(9)) + [], ["b%d" % b for b in range(9)])
-show("MMA warp: after weight wait", [16], [20 + b for b in range(9)], ["w%d" % b for b in range(9)])
-show("MMA warp: issue done", [16], [9 + b for b in range(9)], ["i%d" % b for b in range(9)])
-show("prologue warps", list(range(8, 16)), list(range(12)), ["start", "issued0", "aempty"] + ["g%d" % g for g in range(8)] + ["arrive"])
-show("drain warps", list(range(0, 8)), list(range(21)), ["start", "afull"] + sum([["hf%d" % c, "hs%d" % c] for c in range(4)], []) + ["pref", "outdone"] + ["ss%d" % i for i in range(8)] + ["end"])
-show("loader", [17], list(range(18)), ["h%d" % i for i in range(18)])
+show("MMA warp (start of each block)", [12], list(range(10)), ["up0", "up1", "blk", "dn0", "dn1", "up2", "up3", "dn2", "dn3", "end"])
+show("DRAIN warps", [0, 1, 2, 3], list(range(12)), ["start", "hf0", "hs0", "hf1", "hs1", "hf2", "hs2", "hf3", "hs3", "outdone", "stgempty", "stgfull"])
+show("LN warps", [4, 5, 8, 9], list(range(7)), ["start", "aempty", "g0", "g1", "g2", "g3", "arrive"])
+show("OUT warps", [6, 7, 10, 11], list(range(3)), ["start", "stgfull", "done"])
