@@ -82,6 +82,10 @@ struct gnb_graph {
   int32_t* node_part_ptr = nullptr;   // [N+1]
   int32_t* graph_part_ptr = nullptr;  // [B+1] partial rows of graph b = [graph_part_ptr[b], graph_part_ptr[b+1])
   int64_t n_parts = 0;
+  // same for the node -> graph sums of the tensor path: partial rows per (32-node block, graph) run
+  int32_t* node_gpart = nullptr;       // [N]   partial-row id of each node
+  int32_t* graph_npart_ptr = nullptr;  // [B+1] partial rows of graph b = [graph_npart_ptr[b], graph_npart_ptr[b+1])
+  int64_t n_nparts = 0;
   void* all = nullptr;  // single allocation backing everything above
 };
 

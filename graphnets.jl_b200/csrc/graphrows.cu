@@ -94,7 +94,8 @@ __global__ void __launch_bounds__(128) k_graph_post(const GraphPostArgs a) {
   __shared__ __align__(16) float xa[RT][H];       // LN1(u), later h_u
   __shared__ __align__(16) float xb[RT][H];       // LN2(u)
   __shared__ __align__(16) float se[RT][H];
-  __shared__ __align__(16) float sv[RT][H];
+  __shared__ __align__(16) float sv[RT][H];       // gamma . sum v^, then the node -> graph sum of h_v
+  __shared__ __align__(16) float svg[RT][H];
   __shared__ __align__(16) float hid[RT][4 * H];
   const int n = threadIdx.x, warp = n >> 5, lane = n & 31;
   const int64_t g0 = (int64_t)blockIdx.x * RT;
@@ -103,24 +104,37 @@ __global__ void __launch_bounds__(128) k_graph_post(const GraphPostArgs a) {
     xs[r][n] = a.xg[(size_t)g * H + n];
     // ordered sums over the graph's nodes (rows of a graph are contiguous): deterministic, no atomics
     const int v0 = a.graph_node_ptr[g], v1 = a.graph_node_ptr[g + 1];
-    float s0 = 0.f, s1 = 0.f;
+    float s0 = 0.f;
     int v = v0;
     for (; v + 3 < v1; v += 4) {
       const float e0 = a.agg[(size_t)v * H + n], e1 = a.agg[(size_t)(v + 1) * H + n];
       const float e2 = a.agg[(size_t)(v + 2) * H + n], e3 = a.agg[(size_t)(v + 3) * H + n];
-      const float h0 = a.hv[(size_t)v * H + n], h1 = a.hv[(size_t)(v + 1) * H + n];
-      const float h2 = a.hv[(size_t)(v + 2) * H + n], h3 = a.hv[(size_t)(v + 3) * H + n];
       s0 += e0; s0 += e1; s0 += e2; s0 += e3;
-      s1 += h0; s1 += h1; s1 += h2; s1 += h3;
     }
-    for (; v < v1; v++) { s0 += a.agg[(size_t)v * H + n]; s1 += a.hv[(size_t)v * H + n]; }
+    for (; v < v1; v++) s0 += a.agg[(size_t)v * H + n];
     se[r][n] = s0;
-    sv[r][n] = s1;
+    // partial rows of the node kernel: sum of v^ (scaled by the LN1 node scale, which the packed weights carry) and of the addends
+    const int p0 = a.graph_npart_ptr[g], p1 = a.graph_npart_ptr[g + 1];
+    float sh = 0.f, sg = 0.f;
+    for (int p = p0; p < p1; p++) { sh += a.Vpart[(size_t)p * H + n]; sg += a.Npart[(size_t)p * H + n]; }
+    sv[r][n] = sh * a.g1n[n];
+    svg[r][n] = sg;
   }
   __syncthreads();
   ln_rows(xs, xa, a.g1, a.b1ln, a.eps1, a.eps_mode1, warp, lane);
   ln_rows(xs, xb, a.g2, a.b2ln, a.eps2, a.eps_mode2, warp, lane);
   __syncthreads();
+  // s_v = W_nv (gamma . sum v^) + sum of the addends
+  {
+    float t[RT];
+#pragma unroll
+    for (int r = 0; r < RT; r++) t[r] = svg[r][n];
+    gemv_rows<H>(sv, a.Wnv, H, n, t);
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < RT; r++) sv[r][n] = t[r];
+    __syncthreads();
+  }
   // h_u = W_g [s_e ; s_v ; LN1(u)] + b_g
   float hu[RT];
   {

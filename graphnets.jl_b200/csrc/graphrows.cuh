@@ -19,7 +19,12 @@ struct GraphPostArgs {
   int64_t B;
   const int32_t* graph_node_ptr;   // [B+1]
   const float* agg;      // [N][128] edge -> node aggregates
-  const float* hv;       // [N][128] updated nodes (block output)
+  // node -> graph sum of the block output h_v = W_nv' v^ + addends, by linearity over the partial rows of the node kernel
+  const int32_t* graph_npart_ptr;   // [B+1]
+  const float* Vpart;    // [n_nparts][128] partial sums of the normalised node rows v^
+  const float* Npart;    // [n_nparts][128] partial sums of the node addends
+  const float* Wnv;      // [128][128] rows [H,2H) of the node Dense (k-major), without the LayerNorm scale
+  const float* g1n;      // [128] LN1 (node) scale
   const float *g1, *b1ln; float eps1; int eps_mode1;   // LN1 (graph)
   const float *g2, *b2ln; float eps2; int eps_mode2;   // LN2 (graph)
   const float *Wg, *bg;  // graph Dense (3H -> H), k-major

@@ -317,6 +317,7 @@ extern "C" int gnb_graph_lower(gnb_ctx* ctx, const void* adj, int adj_dtype, int
   size_t o_src = take(E), o_dst = take(E), o_slot = take(E), o_eg = take(E), o_ng = take(N);
   size_t o_gep = take(B + 1), o_gnp = take(B + 1), o_nip = take(N + 1), o_ep = take(E), o_npp = take(N + 1);
   size_t o_gpp = take(B + 1);
+  size_t o_ngp = take(N), o_gnpp = take(B + 1);
   cudaError_t ce = cudaMalloc(&g->all, off ? off : 256);
   if (ce != cudaSuccess) {
     delete g;
@@ -330,6 +331,7 @@ extern "C" int gnb_graph_lower(gnb_ctx* ctx, const void* adj, int adj_dtype, int
   g->graph_node_ptr = (int32_t*)(base + o_gnp); g->node_in_ptr = (int32_t*)(base + o_nip);
   g->edge_part = (int32_t*)(base + o_ep); g->node_part_ptr = (int32_t*)(base + o_npp);
   g->graph_part_ptr = (int32_t*)(base + o_gpp);
+  g->node_gpart = (int32_t*)(base + o_ngp); g->graph_npart_ptr = (int32_t*)(base + o_gnpp);
   int ret = GNB_OK;
   do {
     if (cudaMemcpyAsync(g->graph_node_ptr, gnp.data(), sizeof(int32_t) * (B + 1), cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) { ret = GNB_ERR_CUDA; break; }
@@ -362,6 +364,26 @@ extern "C" int gnb_graph_lower(gnb_ctx* ctx, const void* adj, int adj_dtype, int
     }
     k_graph_part_ptr<<<ceil_div(B + 1, 256), 256, 0, ctx->stream>>>(g->graph_node_ptr, g->node_part_ptr, B, g->graph_part_ptr);
     ctx->launches++;
+    // node -> graph partial-row index (32-node blocks, graph runs): same construction keyed by the node's graph
+    if (N > 0) {
+      int rc2 = GNB_OK;
+      int32_t* flag = arena_ptr<int32_t>(ctx->arena, N, &rc2);
+      int32_t* excl = arena_ptr<int32_t>(ctx->arena, N + 1, &rc2);
+      int32_t* sums2 = arena_ptr<int32_t>(ctx->arena, ceil_div(N, SCAN_ITEMS) + 2, &rc2);
+      if (rc2 != GNB_OK) { ret = rc2; break; }
+      k_part_flags<<<ceil_div(N, 256), 256, 0, ctx->stream>>>(g->node_graph, N, 32, flag);
+      ctx->launches++;
+      if ((ret = exclusive_scan(ctx, flag, N, excl, 1, sums2)) != GNB_OK) break;
+      k_part_finish<<<ceil_div(N, 256), 256, 0, ctx->stream>>>(flag, excl, N, g->node_gpart);
+      k_node_part_ptr<<<ceil_div(B + 1, 256), 256, 0, ctx->stream>>>(g->graph_node_ptr, excl, B, g->graph_npart_ptr);
+      ctx->launches += 2;
+      int32_t np = 0;
+      if (cudaMemcpyAsync(&np, excl + N, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess) { ret = GNB_ERR_CUDA; break; }
+      if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) { ret = GNB_ERR_CUDA; break; }
+      g->n_nparts = np;
+    } else {
+      cudaMemsetAsync(g->graph_npart_ptr, 0, sizeof(int32_t) * (B + 1), ctx->stream);
+    }
     cudaError_t e2 = cudaStreamSynchronize(ctx->stream);
     if (e2 == cudaSuccess) e2 = cudaGetLastError();
     if (e2 != cudaSuccess) { gnb_set_error("gnb_graph_lower: %s", cudaGetErrorString(e2)); ret = GNB_ERR_CUDA; }

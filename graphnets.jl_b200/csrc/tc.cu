@@ -227,434 +227,6 @@ __global__ void __launch_bounds__(192, 2) k_tc_proj(const ProjArgs a) {
   if (warp == 4) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(256u) : "memory");
 }
 
-// =====================================================================================================
-// Fused GNCore kernel for edges (MODE_EDGE) and nodes (MODE_NODE); see the file header.
-// Weight block order per pair, each block used by sub-tile 0 then 1:
-//   EDGE: W1_0  W_blk  W2_0  W1_1  W2_1  W1_2  W2_2  W1_3  W2_3      (W_blk accumulates into D)
-//   NODE: W1_0  W2_0  W1_1  W2_1  W1_2  W2_2  W1_3  W2_3  W_blk      (W_blk -> Hd: the block output h_v is needed
-//                                                                     separately for the node -> graph sum)
-// =====================================================================================================
-struct CoreArgs {
-  const float* x;   // [R][H] rows (input features of this entity kind)
-  float* y;         // [R][H] core output
-  int64_t R;
-  int num_tiles;
-  const __nv_bfloat16* wpack;   // weight blocks in consumption order
-  const float* b1f;             // [4H] FFN bias with the LN2 shift folded in
-  const float* b2;              // [H]
-  float eps;
-  int eps_mode;
-  // two gathered fp32 addend rows per row:  g = add1[idx1 ? idx1[r] : r] + add2[idx2[r]]
-  //   EDGE: add1 = Ps (sender projection), add2 = Pr + Pu[graph] (receiver projection with the per-graph row
-  //         folded in by the node-projection epilogue); both live in Psr [N][2H]
-  //   NODE: add1 = W_na . (edge aggregate) [N][H], add2 = Pu [B][H] indexed by node_graph
-  const float* add1;
-  const int32_t* idx1;
-  int ld1;
-  const float* add2;
-  const int32_t* idx2;
-  int ld2;
-  // EDGE
-  const int32_t* part;          // partial-row id per edge (32-row blocks, receiver runs)
-  float* Epart;                 // out [n_parts][H] partial sums of the normalised edge rows
-  float* Gpart;                 // out [n_parts][H] partial sums of the gathered addends
-  // NODE
-  float* h_out;                 // [N][H] block output h_v
-  unsigned long long* dbg;      // diagnostics: clock64 stamps [CTA][warp][32] of one steady-state pair (nullptr: off)
-};
-
-constexpr int HALF_BYTES = KB_BYTES;     // weight ring stage = one 64-wide K half of a block (16 KB)
-constexpr int NWS = 5;                   // ring stages
-constexpr int C_OFF_A = 0;                           // [stage 2][sub-tile 2] x 32 KB
-constexpr int C_OFF_W = 4 * BLK_BYTES;
-constexpr int C_OFF_MISC = C_OFF_W + NWS * HALF_BYTES;
-constexpr int C_MISC = 512 * 4 + 32 * 8 + 16;        // b1f[512], barriers[32], tmem slot
-constexpr int C_SMEM = C_OFF_MISC + C_MISC + 1024;
-constexpr int C_THREADS = 18 * 32;
-enum { CB_WFULL = 0, CB_WEMPTY = 5, CB_AFULL = 10, CB_AEMPTY = 14, CB_HIDFULL = 18, CB_HSREADY = 20, CB_OUTDONE = 22, CB_ACCFREE = 24 };
-
-#define TCDBG(k)                                                                                    \
-  do {                                                                                              \
-    if (a.dbg != nullptr && tl == 4 && lane == 0)                                                   \
-      a.dbg[((size_t)blockIdx.x * 18 + warp) * 32 + (k)] = (unsigned long long)clock64();           \
-  } while (0)
-
-template <int MODE>
-__global__ void __launch_bounds__(C_THREADS, 1) k_core(const CoreArgs a) {
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t raw = smem_u32(smem_raw);
-  const uint32_t base = (raw + 1023u) & ~1023u;
-  uint8_t* sm = smem_raw + (base - raw);
-  const uint32_t sW = base + C_OFF_W;
-  float* sB1 = reinterpret_cast<float*>(sm + C_OFF_MISC);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sB1 + 512);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 32);
-  const uint32_t bar0 = smem_u32(bars);
-  auto BAR = [&](int i) { return bar0 + 8u * (uint32_t)i; };
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-
-  if (tid == 0) {
-    for (int i = 0; i < NWS; i++) { mbar_init(BAR(CB_WFULL + i), 1); mbar_init(BAR(CB_WEMPTY + i), 1); }
-    for (int i = 0; i < 4; i++) { mbar_init(BAR(CB_AFULL + i), 128); mbar_init(BAR(CB_AEMPTY + i), 1); }
-    for (int s = 0; s < 2; s++) {
-      mbar_init(BAR(CB_HIDFULL + s), 1); mbar_init(BAR(CB_HSREADY + s), 128);
-      mbar_init(BAR(CB_OUTDONE + s), 1); mbar_init(BAR(CB_ACCFREE + s), 128);
-    }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  if (warp == 16) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-  }
-  for (int i = tid; i < 512; i += C_THREADS) sB1[i] = a.b1f[i];
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem = *tmem_slot;
-  const int num_pairs = (a.num_tiles + 1) >> 1;
-
-  if (warp == 17) {
-    // ===================================================== weight loader
-    uint32_t it = 0, tl = 0;
-    for (int pair = blockIdx.x; pair < num_pairs; pair += gridDim.x, tl++) {
-      for (int hb = 0; hb < 18; hb++, it++) {
-        const uint32_t st = it % NWS, ph = (it / NWS) & 1;
-        mbar_wait(BAR(CB_WEMPTY + st), ph ^ 1);
-        TCDBG(hb);
-        if (elect_one()) {
-          mbar_expect_tx(BAR(CB_WFULL + st), HALF_BYTES);
-          bulk_g2s(sW + st * HALF_BYTES, reinterpret_cast<const uint8_t*>(a.wpack) + (size_t)hb * HALF_BYTES, HALF_BYTES,
-                   BAR(CB_WFULL + st));
-        }
-        __syncwarp();
-      }
-    }
-  } else if (warp == 16) {
-    // ===================================================== MMA issuer (whole warp converged, one lane issues)
-    uint32_t it = 0, tl = 0;
-    for (int pair = blockIdx.x; pair < num_pairs; pair += gridDim.x, tl++) {
-      const uint32_t stage = tl & 1, aph = (tl >> 1) & 1;
-#pragma unroll 1
-      for (int b = 0; b < 9; b++) {
-        const uint32_t st0 = it % NWS, ph0 = (it / NWS) & 1;
-        const uint32_t st1 = (it + 1) % NWS, ph1 = ((it + 1) / NWS) & 1;
-        it += 2;
-        // kind of this block: 0 = up-projection chunk c, 1 = down-projection chunk c, 2 = GNBlock GEMM
-        int kind, c;
-        if (MODE == MODE_EDGE) {
-          if (b == 0) { kind = 0; c = 0; }
-          else if (b == 1) { kind = 2; c = 0; }
-          else { kind = (b & 1) ? 0 : 1; c = (b & 1) ? (b - 1) >> 1 : (b - 2) >> 1; }
-        } else {
-          if (b == 8) { kind = 2; c = 0; }
-          else { kind = b & 1; c = b >> 1; }
-        }
-        TCDBG(b);
-        mbar_wait(BAR(CB_WFULL + st0), ph0);
-        mbar_wait(BAR(CB_WFULL + st1), ph1);
-        TCDBG(20 + b);
-        const uint64_t w0 = umma_desc(sW + st0 * HALF_BYTES), w1 = umma_desc(sW + st1 * HALF_BYTES);
-#pragma unroll
-        for (int s = 0; s < 2; s++) {
-          const uint64_t adesc = umma_desc(base + C_OFF_A + (stage * 2 + s) * BLK_BYTES);
-          const uint32_t D_s = tmem + 256 * s, Hd_s = D_s + 128;
-          if (b == 0) {
-            mbar_wait(BAR(CB_AFULL + stage * 2 + s), aph);
-            if (MODE == MODE_NODE) mbar_wait(BAR(CB_ACCFREE + s), (tl & 1) ^ 1);   // Hd still holds the previous h_v
-          }
-          if (MODE == MODE_EDGE && kind == 2) mbar_wait(BAR(CB_ACCFREE + s), (tl & 1) ^ 1);
-          if (kind == 1) mbar_wait(BAR(CB_HSREADY + s), c & 1);
-          tc_fence_after();
-          if (elect_one()) {
-            if (kind == 0) {
-              issue_ss(Hd_s, adesc, w0, w1, false);
-              tc_commit(BAR(CB_HIDFULL + s));
-              if (MODE == MODE_EDGE && c == 3) tc_commit(BAR(CB_AEMPTY + stage * 2 + s));
-            } else if (kind == 1) {
-              issue_ts(D_s, Hd_s, w0, w1, MODE == MODE_EDGE ? true : c > 0);
-              if (MODE == MODE_EDGE && c == 3) tc_commit(BAR(CB_OUTDONE + s));
-            } else {
-              if (MODE == MODE_EDGE) {
-                issue_ss(D_s, adesc, w0, w1, false);
-              } else {
-                issue_ss(Hd_s, adesc, w0, w1, false);
-                tc_commit(BAR(CB_AEMPTY + stage * 2 + s));
-                tc_commit(BAR(CB_OUTDONE + s));
-              }
-            }
-          }
-          __syncwarp();
-        }
-        if (elect_one()) {
-          tc_commit(BAR(CB_WEMPTY + st0));
-          tc_commit(BAR(CB_WEMPTY + st1));
-        }
-        __syncwarp();
-        TCDBG(9 + b);
-      }
-    }
-  } else if (warp >= 8) {
-    // ===================================================== prologue warps, one pair ahead of the MMAs
-    // A warp owns a 32-row slice and walks it in groups of 4 rows (one row = 32 lanes x float4, 512 B coalesced).
-    // Software pipeline: the 12 loads of group k+1 are in flight while group k is normalised; the LayerNorm
-    // reductions of the 4 rows of a group are interleaved level by level (4 independent shuffle chains).
-    const int pw = warp - 8, s = pw >> 2, q = pw & 3;
-    const float4 b2v = __ldg(reinterpret_cast<const float4*>(a.b2) + lane);
-    const float* base1 = a.add1 + 4 * lane;
-    const float* base2 = a.add2 + 4 * lane;
-    const float* xbase = a.x + 4 * lane;
-    uint32_t tl = 0;
-    for (int pair = blockIdx.x; pair < num_pairs; pair += gridDim.x, tl++) {
-      const uint32_t stage = tl & 1, aph = (tl >> 1) & 1;
-      const int64_t row0 = ((int64_t)pair * 2 + s) * TM + 32 * q;   // first row of this warp's 32-row slice
-      const int64_t left = a.R - row0;
-      const int rows = left < 0 ? 0 : (left > 32 ? 32 : (int)left);
-      int my_i1 = 0, my_i2 = 0, my_pid = -1;
-      if (lane < rows) {
-        my_i1 = a.idx1 ? __ldg(a.idx1 + row0 + lane) : (int)(row0 + lane);
-        my_i2 = __ldg(a.idx2 + row0 + lane);
-        if (MODE == MODE_EDGE) my_pid = __ldg(a.part + row0 + lane);
-      }
-      uint32_t endmask = 0;
-      int pid_e = 0, pid_g = 0;
-      if (MODE == MODE_EDGE) {
-        const int nxt = __shfl_down_sync(0xffffffffu, my_pid, 1);
-        endmask = __ballot_sync(0xffffffffu, lane < rows && (lane == rows - 1 || nxt != my_pid));
-        pid_e = pid_g = __shfl_sync(0xffffffffu, my_pid, 0);
-      }
-      TCDBG(0);
-      float4 xa[4], pa[4], pb[4];
-      // rows past the end re-read the last valid row (always mapped); they are masked out below
-      auto issue = [&](int i0) {
-#pragma unroll
-        for (int u = 0; u < 4; u++) {
-          const int i = i0 + u;
-          const int i1 = __shfl_sync(0xffffffffu, my_i1, i), i2 = __shfl_sync(0xffffffffu, my_i2, i);
-          int64_t r = row0 + i;
-          r = r < a.R ? r : a.R - 1;
-          xa[u] = __ldg(reinterpret_cast<const float4*>(xbase + (size_t)r * H));
-          pa[u] = __ldg(reinterpret_cast<const float4*>(base1 + (size_t)i1 * a.ld1));
-          pb[u] = __ldg(reinterpret_cast<const float4*>(base2 + (size_t)i2 * a.ld2));
-        }
-      };
-      issue(0);
-      TCDBG(1);
-      mbar_wait(BAR(CB_AEMPTY + stage * 2 + s), aph ^ 1);
-      TCDBG(2);
-      uint8_t* A = sm + C_OFF_A + (stage * 2 + s) * BLK_BYTES;
-      float4 acc_e = f4zero(), acc_g = f4zero();
-#pragma unroll 1
-      for (int i0 = 0; i0 < 32; i0 += 4) {
-        float4 xc[4];
-        // ---- consume the landed group: y0 = x + (gathered block addends) + b2; the epilogue adds the TMEM
-        //      accumulator onto it
-#pragma unroll
-        for (int u = 0; u < 4; u++) {
-          const int i = i0 + u;
-          xc[u] = xa[u];
-          const float4 g = f4add(pa[u], pb[u]);
-          if (i < rows) {
-            const float4 y0 = make_float4((xc[u].x + g.x) + b2v.x, (xc[u].y + g.y) + b2v.y, (xc[u].z + g.z) + b2v.z,
-                                          (xc[u].w + g.w) + b2v.w);
-            *(reinterpret_cast<float4*>(a.y + (size_t)(row0 + i) * H) + lane) = y0;
-            if (MODE == MODE_NODE) {
-              *(reinterpret_cast<float4*>(a.h_out + (size_t)(row0 + i) * H) + lane) = g;
-            } else {
-              acc_g = f4add(acc_g, g);
-              if ((endmask >> i) & 1u) {
-                *(reinterpret_cast<float4*>(a.Gpart + (size_t)pid_g * H) + lane) = acc_g;
-                acc_g = f4zero();
-                pid_g++;
-              }
-            }
-          }
-        }
-        if (i0 + 4 < 32) issue(i0 + 4);
-        // ---- LayerNorm of the 4 rows (two-pass, fp32), reductions interleaved across the rows
-        float sm1[4], sq[4];
-#pragma unroll
-        for (int u = 0; u < 4; u++) sm1[u] = (xc[u].x + xc[u].y) + (xc[u].z + xc[u].w);
-#pragma unroll
-        for (int o = 16; o; o >>= 1) {
-#pragma unroll
-          for (int u = 0; u < 4; u++) sm1[u] += __shfl_xor_sync(0xffffffffu, sm1[u], o);
-        }
-#pragma unroll
-        for (int u = 0; u < 4; u++) {
-          const float mu = sm1[u] * (1.0f / H);
-          xc[u].x -= mu; xc[u].y -= mu; xc[u].z -= mu; xc[u].w -= mu;
-          sq[u] = (xc[u].x * xc[u].x + xc[u].y * xc[u].y) + (xc[u].z * xc[u].z + xc[u].w * xc[u].w);
-        }
-#pragma unroll
-        for (int o = 16; o; o >>= 1) {
-#pragma unroll
-          for (int u = 0; u < 4; u++) sq[u] += __shfl_xor_sync(0xffffffffu, sq[u], o);
-        }
-#pragma unroll
-        for (int u = 0; u < 4; u++) {
-          const int i = i0 + u;
-          const float rs = (i < rows) ? ln_rstd(sq[u] * (1.0f / H), a.eps, a.eps_mode) : 0.f;
-          const float4 xh = make_float4(xc[u].x * rs, xc[u].y * rs, xc[u].z * rs, xc[u].w * rs);
-          uint2 pk;
-          pk.x = pack_bf16(xh.x, xh.y);
-          pk.y = pack_bf16(xh.z, xh.w);
-          *reinterpret_cast<uint2*>(A + sw_off(32 * q + i, 4 * lane)) = pk;
-          if (MODE == MODE_EDGE) {
-            acc_e = f4add(acc_e, xh);
-            if ((endmask >> i) & 1u) {
-              *(reinterpret_cast<float4*>(a.Epart + (size_t)pid_e * H) + lane) = acc_e;
-              acc_e = f4zero();
-              pid_e++;
-            }
-          }
-        }
-        TCDBG(3 + (i0 >> 2));
-      }
-      fence_async_smem();
-      mbar_arrive(BAR(CB_AFULL + stage * 2 + s));
-      TCDBG(11);
-    }
-  } else {
-    // ===================================================== drain + epilogue groups
-    const int s = warp >> 2;              // sub-tile of this group
-    const int w4 = warp & 3;              // warp within the group == TMEM lane quadrant
-    const uint32_t lane_base = ((uint32_t)(w4 * 32)) << 16;
-    const uint32_t D_s = tmem + 256 * s, Hd_s = D_s + 128;
-    const int q = lane >> 2, cq = 2 * (lane & 3);
-    uint32_t tl = 0;
-    for (int pair = blockIdx.x; pair < num_pairs; pair += gridDim.x, tl++) {
-      const uint32_t stage = tl & 1, aph = (tl >> 1) & 1;
-      const int64_t row0 = ((int64_t)pair * 2 + s) * TM;
-      const int64_t left = a.R - row0;
-      const int rows = left < 0 ? 0 : (left > TM ? TM : (int)left);
-      // acquire the prologue's y0 (and h0) stores of this pair.  Waited here, before the MMAs can release the
-      // A stage, so the barrier cannot run two phases ahead of this wait.
-      TCDBG(0);
-      mbar_wait(BAR(CB_AFULL + stage * 2 + s), aph);
-      TCDBG(1);
-      // ---------------- FFN hidden chunks: TMEM fp32 -> +b1 -> relu -> bf16 pairs -> TMEM (in place)
-#pragma unroll 1
-      for (int c = 0; c < 4; c++) {
-        mbar_wait(BAR(CB_HIDFULL + s), c & 1);
-        TCDBG(2 + 2 * c);
-        tc_fence_after();
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-          uint32_t v[32], p[16];
-          TC_LD32(Hd_s + lane_base + 32 * j, v);
-          tc_wait_ld();
-          const float4* bb = reinterpret_cast<const float4*>(sB1 + c * 128 + j * 32);
-#pragma unroll
-          for (int t = 0; t < 8; t++) {
-            const float4 b = bb[t];
-            p[2 * t] = pack_bf16_relu(__uint_as_float(v[4 * t]) + b.x, __uint_as_float(v[4 * t + 1]) + b.y);
-            p[2 * t + 1] = pack_bf16_relu(__uint_as_float(v[4 * t + 2]) + b.z, __uint_as_float(v[4 * t + 3]) + b.w);
-          }
-          TC_ST16(Hd_s + lane_base + 16 * j, p);   // columns [16j,16j+16) were read in iteration <= j
-        }
-        tc_wait_st();
-        tc_fence_before();
-        mbar_arrive(BAR(CB_HSREADY + s));
-        TCDBG(3 + 2 * c);
-      }
-      // ---------------- final epilogue: y = y0 + D (+ D_blk) in the accumulator-fragment layout.
-      // 8 sub-steps ss = (64-column half ch, 16-row half hh, 8-row half h2); a thread owns 8 float2 per sub-step.
-#define EPI_ROW(ss) (w4 * 32 + 16 * (((ss) >> 1) & 1) + q + 8 * ((ss) & 1))
-#define EPI_OFF(ss) ((size_t)(row0 + EPI_ROW(ss)) * H + 64 * ((ss) >> 2) + cq)
-#define EPI_OFFC(ss) ((size_t)((row0 + EPI_ROW(ss)) < a.R ? (row0 + EPI_ROW(ss)) : a.R - 1) * H + 64 * ((ss) >> 2) + cq)
-      if (MODE == MODE_EDGE) {
-        // y0 of sub-steps 0..3 is fetched (L2 hits) while the last down-projection is still running, and the
-        // slots are refilled with sub-steps 4..7 as they drain: the accumulator is released ~1 L2 latency after
-        // the MMAs complete instead of 8.
-        float2 yb[4][8];
-        uint32_t d[32];
-#pragma unroll
-        for (int ss = 0; ss < 4; ss++) {
-#pragma unroll
-          for (int n = 0; n < 8; n++) yb[ss][n] = __ldcg(reinterpret_cast<const float2*>(a.y + EPI_OFFC(ss) + 8 * n));
-        }
-        TCDBG(10);
-        mbar_wait(BAR(CB_OUTDONE + s), tl & 1);
-        TCDBG(11);
-        tc_fence_after();
-#pragma unroll
-        for (int ss = 0; ss < 8; ss++) {
-          const int h2 = ss & 1;
-          if (h2 == 0) {
-            const uint32_t toff = lane_base + ((uint32_t)(16 * ((ss >> 1) & 1)) << 16) + 64 * (ss >> 2);
-            TC_LD_FRAG64(D_s + toff, d);
-            tc_wait_ld();
-            if (ss == 6) {   // TMEM fully read: release the accumulators to the next pair's MMAs
-              tc_fence_before();
-              mbar_arrive(BAR(CB_ACCFREE + s));
-            }
-          }
-          TCDBG(12 + ss);
-          if (EPI_ROW(ss) < rows) {
-#pragma unroll
-            for (int n = 0; n < 8; n++) {
-              float2 yv = yb[ss & 3][n];
-              yv.x += __uint_as_float(d[4 * n + 2 * h2]);
-              yv.y += __uint_as_float(d[4 * n + 2 * h2 + 1]);
-              *reinterpret_cast<float2*>(a.y + EPI_OFF(ss) + 8 * n) = yv;
-            }
-          }
-          if (ss < 4) {
-#pragma unroll
-            for (int n = 0; n < 8; n++) yb[ss][n] = __ldcg(reinterpret_cast<const float2*>(a.y + EPI_OFFC(ss + 4) + 8 * n));
-          }
-        }
-        TCDBG(20);
-      } else {
-        float2 yb[8], hb[8];
-        uint32_t d[32], e[32];
-        mbar_wait(BAR(CB_OUTDONE + s), tl & 1);
-        tc_fence_after();
-#pragma unroll
-        for (int ss = 0; ss < 8; ss++) {
-          const int h2 = ss & 1;
-          const bool valid = EPI_ROW(ss) < rows;
-          if (h2 == 0) {
-            const uint32_t toff = lane_base + ((uint32_t)(16 * ((ss >> 1) & 1)) << 16) + 64 * (ss >> 2);
-            TC_LD_FRAG64(D_s + toff, d);
-            TC_LD_FRAG64(Hd_s + toff, e);
-          }
-#pragma unroll
-          for (int n = 0; n < 8; n++) {
-            yb[n] = __ldcg(reinterpret_cast<const float2*>(a.y + EPI_OFFC(ss) + 8 * n));
-            hb[n] = __ldcg(reinterpret_cast<const float2*>(a.h_out + EPI_OFFC(ss) + 8 * n));
-          }
-          if (h2 == 0) {
-            tc_wait_ld();
-            if (ss == 6) {
-              tc_fence_before();
-              mbar_arrive(BAR(CB_ACCFREE + s));
-            }
-          }
-          if (valid) {
-#pragma unroll
-            for (int n = 0; n < 8; n++) {
-              const float bx = __uint_as_float(e[4 * n + 2 * h2]), by = __uint_as_float(e[4 * n + 2 * h2 + 1]);
-              float2 hv = hb[n], yv = yb[n];
-              hv.x += bx; hv.y += by;
-              *reinterpret_cast<float2*>(a.h_out + EPI_OFF(ss) + 8 * n) = hv;
-              yv.x += __uint_as_float(d[4 * n + 2 * h2]) + bx;
-              yv.y += __uint_as_float(d[4 * n + 2 * h2 + 1]) + by;
-              *reinterpret_cast<float2*>(a.y + EPI_OFF(ss) + 8 * n) = yv;
-            }
-          }
-        }
-      }
-#undef EPI_ROW
-#undef EPI_OFF
-#undef EPI_OFFC
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 16) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
-}
-
 // ------------------------------------------------------------------ weight packing
 // dst block (bf16, swizzled smem image): B[n][k] = W[(n0+n) + ldw*(k0+k)] * (gamma ? gamma[k] : 1)
 __global__ void k_pack_block(const float* __restrict__ W, int ldw, int n0, int k0, const float* __restrict__ gamma,
@@ -740,16 +312,17 @@ int tc_core_pack(gnb_ctx* ctx, const gnb_block_params& blk, const gnb_ffn_params
   pack(blk.We, H, 0, 2 * H, g1n, w + 1 * BE);      // P_r
   pack(blk.Wn, H, 0, 0, nullptr, w + 2 * BE);      // W_na (aggregate rows, no LayerNorm)
   // fused kernels: block order documented at k_core
+  // both fused kernels (tc_edge.cu) index the blocks as  W1_0 W_blk W2_0 W1_1 W2_1 W1_2 W2_2 W1_3 W2_3
   for (int kind = 0; kind < 2; kind++) {
     __nv_bfloat16* dst = w + (kind == 0 ? 3 : 12) * BE;
     for (int c = 0; c < 4; c++) {
-      const int i1 = kind == 0 ? (c == 0 ? 0 : 2 * c + 1) : 2 * c;      // W1_c
-      const int i2 = kind == 0 ? 2 * c + 2 : 2 * c + 1;                 // W2_c
+      const int i1 = c == 0 ? 0 : 2 * c + 1;      // W1_c
+      const int i2 = 2 * c + 2;                   // W2_c
       pack(ffn[kind].W1, 4 * H, c * H, 0, ln2[kind].gamma, dst + i1 * BE);   // W1 (4H, H): hidden unit c*128+n
       pack(ffn[kind].W2, H, 0, c * H, nullptr, dst + i2 * BE);               // W2 (H, 4H): k = hidden index
     }
     if (kind == 0) pack(blk.We, H, 0, 0, g1e, dst + 1 * BE);
-    else pack(blk.Wn, H, 0, H, g1n, dst + 8 * BE);
+    else pack(blk.Wn, H, 0, H, g1n, dst + 1 * BE);
   }
   // constants folded into the per-graph rows / FFN bias
   k_fold_bias<<<1, 128, 0, st>>>(blk.We, H, 0, 0, H, b1e, blk.be, H, p->cu_e, 0);
@@ -766,22 +339,6 @@ int tc_core_pack(gnb_ctx* ctx, const gnb_block_params& blk, const gnb_ffn_params
     return GNB_ERR_CUDA;
   }
   *out = p;
-  return GNB_OK;
-}
-
-template <int MODE>
-static int launch_core(gnb_ctx* ctx, const CoreArgs& a, const char* name, double flops, double bytes) {
-  if (a.num_tiles <= 0) return GNB_OK;
-  static bool attr_set = false;
-  if (!attr_set) {
-    GNB_CUDA(cudaFuncSetAttribute(k_core<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, C_SMEM));
-    attr_set = true;
-  }
-  const int pairs = (a.num_tiles + 1) / 2;
-  const int grid = pairs < ctx->sm_count ? pairs : ctx->sm_count;
-  Launch L(ctx, name, bytes, flops);
-  k_core<MODE><<<grid, C_THREADS, C_SMEM, ctx->stream>>>(a);
-  GNB_CUDA(cudaGetLastError());
   return GNB_OK;
 }
 
@@ -814,7 +371,9 @@ int tc_core_forward(gnb_ctx* ctx, const gnb_graph* g, const TcCorePack* pk, cons
   float* Gs = arena_ptr<float>(ctx->arena, (size_t)N * H, &rc);
   float* agg = arena_ptr<float>(ctx->arena, (size_t)N * H, &rc);
   float* Pagg = arena_ptr<float>(ctx->arena, (size_t)N * H, &rc);
-  float* hv = arena_ptr<float>(ctx->arena, (size_t)N * H, &rc);
+  const size_t nnparts = (size_t)(g->n_nparts > 0 ? g->n_nparts : 1);
+  float* Vpart = arena_ptr<float>(ctx->arena, nnparts * H, &rc);
+  float* Npart = arena_ptr<float>(ctx->arena, nnparts * H, &rc);
   if (rc != GNB_OK) return rc;
 
   // per-graph rows (fp32 CUDA cores, B rows): P_ue = W_eu LN1(gf) + be + folded LN shifts, P_un likewise
@@ -841,7 +400,7 @@ int tc_core_forward(gnb_ctx* ctx, const gnb_graph* g, const TcCorePack* pk, cons
     a.part = g->edge_part; a.Epart = Epart; a.Gpart = Gpart; a.dbg = g_tc_dbg;
     // canonical work of the reference's edge update + edge FFN: 24 H^2 flops and
     // 8H bytes of features + 12 B of index per edge
-    GNB_TRY(launch_edge5(ctx, a, 24.0 * HH * E, (8.0 * H + 12.0) * E));
+    GNB_TRY(launch_edge5(ctx, a, "tc_edge_core", 24.0 * HH * E, (8.0 * H + 12.0) * E));
   }
   // edge -> node aggregate (src/nodefninput.jl:3) by linearity: agg = We_e' (sum ê) + sum (Ps + Pr + Pu)
   {
@@ -856,17 +415,21 @@ int tc_core_forward(gnb_ctx* ctx, const gnb_graph* g, const TcCorePack* pk, cons
     a.wpack = pk->w_agg;
     GNB_TRY(launch_proj<SRC_AGG>(ctx, a, "tc_agg_proj", 2.0 * N * HH, 4.0 * N * 2 * H));
   }
-  {  // nodes
-    CoreArgs a{};
+  {  // nodes: same fused kernel; the node -> graph sum of the block output h_v = W_nv' v^ + P_agg + P_un[g] is taken by
+     // linearity over the partial sums of v^ (V_part) and of the addends (N_part), so h_v is never materialised
+    EdgeArgs a{};
     a.x = xn; a.y = yn; a.R = N; a.num_tiles = ceil_div(N, TM); a.wpack = pk->w_node;
     a.b1f = pk->b1f_n; a.b2 = ffn[1].b2; a.eps = ln1[1].eps; a.eps_mode = ln1[1].eps_mode;
-    a.add1 = Pagg; a.idx1 = nullptr; a.ld1 = H; a.add2 = Pun; a.idx2 = g->node_graph; a.ld2 = H; a.h_out = hv;
-    GNB_TRY(launch_core<MODE_NODE>(ctx, a, "tc_node_core", 20.0 * HH * N, (8.0 * H + 8.0) * N));
+    a.add1 = Pagg; a.idx1 = nullptr; a.ld1 = H; a.add2 = Pun; a.idx2 = g->node_graph; a.ld2 = H;
+    a.part = g->node_gpart; a.Epart = Vpart; a.Gpart = Npart; a.dbg = nullptr;
+    GNB_TRY(launch_edge5(ctx, a, "tc_node_core", 20.0 * HH * N, (8.0 * H + 8.0) * N));
   }
   // graphs (B rows, fp32 CUDA cores): sums over the graph's nodes, graph update, graph FFN + residual
   {
     GraphPostArgs ga{};
-    ga.xg = xg; ga.B = B; ga.graph_node_ptr = g->graph_node_ptr; ga.agg = agg; ga.hv = hv;
+    ga.xg = xg; ga.B = B; ga.graph_node_ptr = g->graph_node_ptr; ga.agg = agg;
+    ga.graph_npart_ptr = g->graph_npart_ptr; ga.Vpart = Vpart; ga.Npart = Npart;
+    ga.Wnv = blk.Wn + (size_t)H * H; ga.g1n = ln1[1].gamma;
     ga.g1 = ln1[2].gamma; ga.b1ln = ln1[2].beta; ga.eps1 = ln1[2].eps; ga.eps_mode1 = ln1[2].eps_mode;
     ga.g2 = ln2[2].gamma; ga.b2ln = ln2[2].beta; ga.eps2 = ln2[2].eps; ga.eps_mode2 = ln2[2].eps_mode;
     ga.Wg = blk.Wg; ga.bg = blk.bg; ga.W1 = ffn[2].W1; ga.b1 = ffn[2].b1; ga.W2 = ffn[2].W2; ga.b2 = ffn[2].b2;

@@ -410,7 +410,7 @@ __global__ void __launch_bounds__(E_THREADS, 1) k_edge5(const EdgeArgs a) {
       const int rows = left < 0 ? 0 : (left > 32 ? 32 : (int)left);
       int my_i1 = 0, my_i2 = 0, my_pid = -1;
       if (lane < rows) {
-        my_i1 = __ldg(a.idx1 + row0 + lane);
+        my_i1 = a.idx1 ? __ldg(a.idx1 + row0 + lane) : (int)(row0 + lane);
         my_i2 = __ldg(a.idx2 + row0 + lane);
         my_pid = __ldg(a.part + row0 + lane);
       }
@@ -465,7 +465,7 @@ __global__ void __launch_bounds__(E_THREADS, 1) k_edge5(const EdgeArgs a) {
 
 }  // namespace
 
-int launch_edge5(gnb_ctx* ctx, const EdgeArgs& a, double flops, double bytes) {
+int launch_edge5(gnb_ctx* ctx, const EdgeArgs& a, const char* name, double flops, double bytes) {
   if (a.num_tiles <= 0) return GNB_OK;
   static bool attr_set = false;
   if (!attr_set) {
@@ -473,7 +473,7 @@ int launch_edge5(gnb_ctx* ctx, const EdgeArgs& a, double flops, double bytes) {
     attr_set = true;
   }
   const int grid = a.num_tiles < ctx->sm_count ? a.num_tiles : ctx->sm_count;
-  Launch L(ctx, "tc_edge_core", bytes, flops);
+  Launch L(ctx, name, bytes, flops);
   k_edge5<<<grid, E_THREADS, E_SMEM, ctx->stream>>>(a);
   GNB_CUDA(cudaGetLastError());
   return GNB_OK;

@@ -14,7 +14,7 @@ struct EdgeArgs {
   float eps;
   int eps_mode;
   // gathered fp32 addend rows: g = add1[idx1[r]] + add2[idx2[r]]   (sender projection, receiver projection + per-graph row)
-  const float* add1; const int32_t* idx1; int ld1;
+  const float* add1; const int32_t* idx1; int ld1;   // idx1 == nullptr: the row itself
   const float* add2; const int32_t* idx2; int ld2;
   const int32_t* part;   // partial-row id per edge (32-row blocks, receiver runs)
   float* Epart;          // out [n_parts][128] partial sums of the normalised edge rows
@@ -22,4 +22,4 @@ struct EdgeArgs {
   unsigned long long* dbg;
 };
 
-int launch_edge5(gnb_ctx* ctx, const EdgeArgs& a, double flops, double bytes);
+int launch_edge5(gnb_ctx* ctx, const EdgeArgs& a, const char* name, double flops, double bytes);
