@@ -47,7 +47,7 @@ __device__ __forceinline__ void ln_rows(const float (*xs)[H], float (*out)[H], c
 // acc[r] += sum_k xs[r][k] * W[k*ldw + n]   for k in [0, K)   (W row-major [k][n], coalesced over the CTA)
 template <int K>
 __device__ __forceinline__ void gemv_rows(const float (*xs)[K], const float* __restrict__ W, int ldw, int n, float* acc) {
-#pragma unroll 2
+#pragma unroll 4
   for (int k = 0; k < K; k += 4) {
     const float w0 = __ldg(W + (size_t)(k + 0) * ldw + n), w1 = __ldg(W + (size_t)(k + 1) * ldw + n);
     const float w2 = __ldg(W + (size_t)(k + 2) * ldw + n), w3 = __ldg(W + (size_t)(k + 3) * ldw + n);
@@ -106,10 +106,12 @@ __global__ void __launch_bounds__(128) k_graph_post(const GraphPostArgs a) {
     const int v0 = a.graph_node_ptr[g], v1 = a.graph_node_ptr[g + 1];
     float s0 = 0.f;
     int v = v0;
-    for (; v + 3 < v1; v += 4) {
-      const float e0 = a.agg[(size_t)v * H + n], e1 = a.agg[(size_t)(v + 1) * H + n];
-      const float e2 = a.agg[(size_t)(v + 2) * H + n], e3 = a.agg[(size_t)(v + 3) * H + n];
-      s0 += e0; s0 += e1; s0 += e2; s0 += e3;
+    for (; v + 15 < v1; v += 16) {      // 16 independent loads in flight, summed in row order
+      float e[16];
+#pragma unroll
+      for (int j = 0; j < 16; j++) e[j] = a.agg[(size_t)(v + j) * H + n];
+#pragma unroll
+      for (int j = 0; j < 16; j++) s0 += e[j];
     }
     for (; v < v1; v++) s0 += a.agg[(size_t)v * H + n];
     se[r][n] = s0;

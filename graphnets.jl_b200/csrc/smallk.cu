@@ -23,7 +23,7 @@ constexpr int WIDE_WARPS = 8;
 
 __global__ void __launch_bounds__(WIDE_WARPS * 32) k_wide(const WideArgs a) {
   extern __shared__ __align__(16) float sm_w[];
-  // layout: Ws[K4][128] (column block of this CTA) | per-warp zin[WIDE_ROWS][K4]
+  // layout: Ws2[K4/2][128][2] (column block of this CTA, k-pair interleaved for packed FFMA2) | per-warp zin[WIDE_ROWS][K4]
   const int K4 = a.K4;                       // total input width rounded up to a multiple of 4
   float* Ws = sm_w;
   float* zin_all = sm_w + (size_t)K4 * 128;
@@ -40,78 +40,80 @@ __global__ void __launch_bounds__(WIDE_WARPS * 32) k_wide(const WideArgs a) {
         kk -= a.pc[p].d;
       }
     }
-    Ws[i] = w;
+    Ws[((k >> 1) * 128 + n) * 2 + (k & 1)] = w;
   }
   __syncthreads();
   float* zin = zin_all + (size_t)warp * WIDE_ROWS * K4;
-  const float4 bias = (a.bias && col0 + 4 * lane + 3 < a.Nout) ? *reinterpret_cast<const float4*>(a.bias + col0 + 4 * lane)
-                                                                 : make_float4(0.f, 0.f, 0.f, 0.f);
+  const int n = col0 + 4 * lane;
+  float4 bias = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (a.bias) {
+    if (n + 0 < a.Nout) bias.x = a.bias[n + 0];
+    if (n + 1 < a.Nout) bias.y = a.bias[n + 1];
+    if (n + 2 < a.Nout) bias.z = a.bias[n + 2];
+    if (n + 3 < a.Nout) bias.w = a.bias[n + 3];
+  }
   const int64_t nblocks = (a.R + WIDE_ROWS - 1) / WIDE_ROWS;
   for (int64_t blk = (int64_t)blockIdx.x * WIDE_WARPS + warp; blk < nblocks; blk += (int64_t)gridDim.x * WIDE_WARPS) {
     const int64_t row0 = blk * WIDE_ROWS;
     const int rows = (int)((a.R - row0) < WIDE_ROWS ? (a.R - row0) : WIDE_ROWS);
-    // ---- assemble the concat rows of this block in shared memory (zero padded to K4)
+    // ---- assemble the concat rows of this block in shared memory: lane r gathers the pieces of row r
     __syncwarp();
-    int koff = 0;
-    for (int p = 0; p < a.np; p++) {
-      const WidePiece& P = a.pc[p];
-      if (P.idx == nullptr) {
-        // contiguous rows: coalesced over (row, k)
-        const float* src = P.x + (size_t)row0 * P.ldx;
-        if (P.ldx == P.d) {
-          for (int i = lane; i < rows * P.d; i += 32) zin[(i / P.d) * K4 + koff + (i % P.d)] = __ldg(src + i);
+    {
+      float* zr = zin + lane * K4;
+      int koff = 0;
+      for (int p = 0; p < a.np; p++) {
+        const WidePiece& P = a.pc[p];
+        if (lane < rows) {
+          const int64_t g = P.idx ? (int64_t)__ldg(P.idx + row0 + lane) : row0 + lane;
+          const float* src = P.x + (size_t)g * P.ldx;
+          for (int k = 0; k < P.d; k++) zr[koff + k] = __ldg(src + k);
         } else {
-          for (int i = lane; i < rows * P.d; i += 32) zin[(i / P.d) * K4 + koff + (i % P.d)] = __ldg(src + (size_t)(i / P.d) * P.ldx + (i % P.d));
+          for (int k = 0; k < P.d; k++) zr[koff + k] = 0.f;
         }
-      } else {
-        const int64_t my = lane < rows ? (int64_t)__ldg(P.idx + row0 + lane) : 0;
-        for (int i = lane; i < rows * P.d; i += 32) {
-          const int r = i / P.d, k = i % P.d;
-          const int64_t g = __shfl_sync(0xffffffffu, my, r);
-          zin[r * K4 + koff + k] = __ldg(P.x + (size_t)g * P.ldx + k);
-        }
+        koff += P.d;
       }
-      koff += P.d;
-    }
-    if (koff < K4) {
-      for (int i = lane; i < rows * (K4 - koff); i += 32) zin[(i / (K4 - koff)) * K4 + koff + (i % (K4 - koff))] = 0.f;
+      for (int k = koff; k < K4; k++) zr[k] = 0.f;
     }
     __syncwarp();
-    // ---- 8 rows x (4 columns per lane) per step
+    // ---- 8 rows x (4 columns per lane) per step; k pairs on the two halves of packed FFMA2
 #pragma unroll 1
     for (int r0 = 0; r0 < rows; r0 += 8) {
-      float4 acc[8];
+      float2 acc[8][4];
 #pragma unroll
-      for (int j = 0; j < 8; j++) acc[j] = bias;
+      for (int j = 0; j < 8; j++)
+#pragma unroll
+        for (int c = 0; c < 4; c++) acc[j][c] = make_float2(0.f, 0.f);
       for (int k = 0; k < K4; k += 4) {
-        const float4 w0 = *reinterpret_cast<const float4*>(Ws + (k + 0) * 128 + 4 * lane);
-        const float4 w1 = *reinterpret_cast<const float4*>(Ws + (k + 1) * 128 + 4 * lane);
-        const float4 w2 = *reinterpret_cast<const float4*>(Ws + (k + 2) * 128 + 4 * lane);
-        const float4 w3 = *reinterpret_cast<const float4*>(Ws + (k + 3) * 128 + 4 * lane);
+        const float4 wa = *reinterpret_cast<const float4*>(Ws + ((k >> 1) * 128 + 4 * lane) * 2);        // pair k,k+1: cols 0,1
+        const float4 wb = *reinterpret_cast<const float4*>(Ws + ((k >> 1) * 128 + 4 * lane) * 2 + 4);    //             cols 2,3
+        const float4 wc = *reinterpret_cast<const float4*>(Ws + (((k >> 1) + 1) * 128 + 4 * lane) * 2);  // pair k+2,k+3
+        const float4 wd = *reinterpret_cast<const float4*>(Ws + (((k >> 1) + 1) * 128 + 4 * lane) * 2 + 4);
 #pragma unroll
         for (int j = 0; j < 8; j++) {
           const float4 z = *reinterpret_cast<const float4*>(zin + (r0 + j) * K4 + k);   // broadcast
-          acc[j].x = fmaf(z.x, w0.x, acc[j].x); acc[j].y = fmaf(z.x, w0.y, acc[j].y);
-          acc[j].z = fmaf(z.x, w0.z, acc[j].z); acc[j].w = fmaf(z.x, w0.w, acc[j].w);
-          acc[j].x = fmaf(z.y, w1.x, acc[j].x); acc[j].y = fmaf(z.y, w1.y, acc[j].y);
-          acc[j].z = fmaf(z.y, w1.z, acc[j].z); acc[j].w = fmaf(z.y, w1.w, acc[j].w);
-          acc[j].x = fmaf(z.z, w2.x, acc[j].x); acc[j].y = fmaf(z.z, w2.y, acc[j].y);
-          acc[j].z = fmaf(z.z, w2.z, acc[j].z); acc[j].w = fmaf(z.z, w2.w, acc[j].w);
-          acc[j].x = fmaf(z.w, w3.x, acc[j].x); acc[j].y = fmaf(z.w, w3.y, acc[j].y);
-          acc[j].z = fmaf(z.w, w3.z, acc[j].z); acc[j].w = fmaf(z.w, w3.w, acc[j].w);
+          const float2 z01 = make_float2(z.x, z.y), z23 = make_float2(z.z, z.w);
+          acc[j][0] = __ffma2_rn(z01, make_float2(wa.x, wa.y), acc[j][0]);
+          acc[j][1] = __ffma2_rn(z01, make_float2(wa.z, wa.w), acc[j][1]);
+          acc[j][2] = __ffma2_rn(z01, make_float2(wb.x, wb.y), acc[j][2]);
+          acc[j][3] = __ffma2_rn(z01, make_float2(wb.z, wb.w), acc[j][3]);
+          acc[j][0] = __ffma2_rn(z23, make_float2(wc.x, wc.y), acc[j][0]);
+          acc[j][1] = __ffma2_rn(z23, make_float2(wc.z, wc.w), acc[j][1]);
+          acc[j][2] = __ffma2_rn(z23, make_float2(wd.x, wd.y), acc[j][2]);
+          acc[j][3] = __ffma2_rn(z23, make_float2(wd.z, wd.w), acc[j][3]);
         }
       }
-      const int n = col0 + 4 * lane;
 #pragma unroll
       for (int j = 0; j < 8; j++) {
         if (r0 + j < rows) {
           float* o = a.out + (size_t)(row0 + r0 + j) * a.ldo + n;
+          const float4 v = make_float4((acc[j][0].x + acc[j][0].y) + bias.x, (acc[j][1].x + acc[j][1].y) + bias.y,
+                                       (acc[j][2].x + acc[j][2].y) + bias.z, (acc[j][3].x + acc[j][3].y) + bias.w);
           if (n + 3 < a.Nout) {
-            *reinterpret_cast<float4*>(o) = acc[j];
+            *reinterpret_cast<float4*>(o) = v;
           } else {
-            if (n + 0 < a.Nout) o[0] = acc[j].x + (a.bias ? a.bias[n + 0] : 0.f);
-            if (n + 1 < a.Nout) o[1] = acc[j].y + (a.bias ? a.bias[n + 1] : 0.f);
-            if (n + 2 < a.Nout) o[2] = acc[j].z + (a.bias ? a.bias[n + 2] : 0.f);
+            if (n + 0 < a.Nout) o[0] = v.x;
+            if (n + 1 < a.Nout) o[1] = v.y;
+            if (n + 2 < a.Nout) o[2] = v.z;
           }
         }
       }
@@ -222,6 +224,101 @@ __global__ void __launch_bounds__(256) k_narrow(const NarrowArgs a) {
   }
 }
 
+
+// Thread-per-row variant for one WIDE direct source (d % 4 == 0) plus optional small sources (d <= 16):
+// a warp stages 32 rows x 128 columns coalesced into a swizzled shared-memory tile (16 B chunk c of row r at
+// chunk c ^ (r & 7): conflict-free for the row-wise writes and for the column-wise reads), then lane r owns row r
+// and accumulates its NO outputs with the weights broadcast from shared memory - no cross-lane reduction.
+constexpr int N2_WARPS = 4;
+template <int NO>
+__global__ void __launch_bounds__(N2_WARPS * 32) k_narrow2(const NarrowArgs a) {
+  extern __shared__ __align__(16) float sm_n2[];
+  float* Wsm = sm_n2;                                       // [K][NO] of all direct sources, concatenated
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  int ktot = 0;
+  for (int s = 0; s < a.nsrc; s++) {
+    const int d = a.src[s].d;
+    for (int i = tid; i < d * NO; i += blockDim.x) {
+      const int k = i / NO, j = i % NO;
+      Wsm[(ktot + k) * NO + j] = j < a.No ? a.src[s].W[(size_t)k * a.ldw + j] : 0.f;
+    }
+    ktot += d;
+  }
+  __syncthreads();
+  const int kw_pad = (ktot * NO + 3) / 4 * 4;
+  float* tile = sm_n2 + kw_pad + (size_t)warp * 32 * 128;   // [32 rows][128 floats], swizzled
+  const NarrowSrc& S0 = a.src[0];
+  const int64_t nblocks = (a.R + 31) / 32;
+  for (int64_t blk = (int64_t)blockIdx.x * N2_WARPS + warp; blk < nblocks; blk += (int64_t)gridDim.x * N2_WARPS) {
+    const int64_t row0 = blk * 32;
+    float acc[NO];
+#pragma unroll
+    for (int j = 0; j < NO; j++) acc[j] = 0.f;
+    for (int c0 = 0; c0 < S0.d; c0 += 128) {
+      const int cw = S0.d - c0 < 128 ? S0.d - c0 : 128;     // columns of this chunk (multiple of 4)
+      __syncwarp();
+#pragma unroll
+      for (int r8 = 0; r8 < 32; r8 += 8) {
+        float4 v[8];
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+          int64_t r = row0 + r8 + u;
+          r = r < a.R ? r : a.R - 1;
+          v[u] = (4 * lane < cw) ? __ldg(reinterpret_cast<const float4*>(S0.x + (size_t)r * S0.ldx + c0) + lane) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+          const int r = r8 + u;
+          *reinterpret_cast<float4*>(tile + r * 128 + ((lane ^ (r & 7)) << 2)) = v[u];
+        }
+      }
+      __syncwarp();
+      const float* myrow = tile + lane * 128;
+      const float* w = Wsm + (size_t)c0 * NO;
+      for (int c = 0; c < (cw >> 2); c++) {
+        const float4 x = *reinterpret_cast<const float4*>(myrow + ((c ^ (lane & 7)) << 2));
+        const float xs[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+        for (int kk = 0; kk < 4; kk++) {
+          if (NO == 4) {
+            const float4 ww = *reinterpret_cast<const float4*>(w + (4 * c + kk) * 4);
+            acc[0] = fmaf(xs[kk], ww.x, acc[0]); acc[1] = fmaf(xs[kk], ww.y, acc[1]);
+            acc[2] = fmaf(xs[kk], ww.z, acc[2]); acc[3] = fmaf(xs[kk], ww.w, acc[3]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < NO; j++) acc[j] = fmaf(xs[kk], w[(4 * c + kk) * NO + j], acc[j]);
+          }
+        }
+      }
+    }
+    const int64_t r = row0 + lane;
+    if (r < a.R) {
+      int kbase = S0.d;
+      for (int s = 1; s < a.nsrc; s++) {
+        const NarrowSrc& S = a.src[s];
+        for (int k = 0; k < S.d; k++) {
+          const float x = S.x[(size_t)r * S.ldx + k];
+#pragma unroll
+          for (int j = 0; j < NO; j++) acc[j] = fmaf(x, Wsm[(kbase + k) * NO + j], acc[j]);
+        }
+        kbase += S.d;
+      }
+#pragma unroll
+      for (int j = 0; j < NO; j++) {
+        if (j < a.No) {
+          float v = acc[j];
+          if (a.bias) v += a.bias[j];
+          for (int t = 0; t < a.nadd; t++) {
+            const int64_t ar = a.add[t].idx ? (int64_t)a.add[t].idx[r] : r;
+            v += a.add[t].a[(size_t)ar * a.add[t].lda + j];
+          }
+          a.out[(size_t)r * a.ldo + j] = v;
+        }
+      }
+    }
+  }
+}
+
 }  // namespace
 
 int launch_wide(gnb_ctx* ctx, const WideArgs& a0) {
@@ -267,11 +364,31 @@ int launch_narrow(gnb_ctx* ctx, const NarrowArgs& a) {
   GNB_CHECK(a.No <= 8 && K <= NARROW_KMAX, "launch_narrow: No %d > 8 or K %d > %d", a.No, K, NARROW_KMAX);
   double bytes = 4.0 * a.R * (K + a.No * (1 + a.nadd));
   Launch L(ctx, "narrow_fp32", bytes, 2.0 * a.R * K * a.No);
-  int64_t gx = (a.R + 31) / 32;            // 8 warps x 4 rows per CTA step
-  const int64_t cap = (int64_t)ctx->sm_count * 8;
-  if (gx > cap) gx = cap;
-  if (a.No <= 4) k_narrow<4><<<(unsigned)gx, 256, 0, ctx->stream>>>(a);
-  else k_narrow<8><<<(unsigned)gx, 256, 0, ctx->stream>>>(a);
+  // wide first source: thread-per-row through a swizzled staging tile; otherwise the lane-per-k kernel
+  bool small_rest = true;
+  for (int s = 1; s < a.nsrc; s++) small_rest = small_rest && a.src[s].d <= 16;
+  const NarrowSrc& S0 = a.src[0];
+  if (a.nsrc >= 1 && S0.d >= 64 && (S0.d & 3) == 0 && (S0.ldx & 3) == 0 && ((uintptr_t)S0.x & 15) == 0 && small_rest) {
+    const int NOp = a.No <= 4 ? 4 : 8;
+    const size_t smem = ((size_t)(K * NOp + 3) / 4 * 4 + (size_t)N2_WARPS * 32 * 128) * sizeof(float);
+    static bool attr = false;
+    if (!attr) {
+      GNB_CUDA(cudaFuncSetAttribute(k_narrow2<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (NARROW_KMAX * 4 + N2_WARPS * 32 * 128) * 4));
+      GNB_CUDA(cudaFuncSetAttribute(k_narrow2<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (NARROW_KMAX * 8 + N2_WARPS * 32 * 128) * 4));
+      attr = true;
+    }
+    int64_t gx = ((a.R + 31) / 32 + N2_WARPS - 1) / N2_WARPS;
+    const int64_t cap = (int64_t)ctx->sm_count * 3;
+    if (gx > cap) gx = cap;
+    if (NOp == 4) k_narrow2<4><<<(unsigned)gx, N2_WARPS * 32, smem, ctx->stream>>>(a);
+    else k_narrow2<8><<<(unsigned)gx, N2_WARPS * 32, smem, ctx->stream>>>(a);
+  } else {
+    int64_t gx = (a.R + 31) / 32;            // 8 warps x 4 rows per CTA step
+    const int64_t cap = (int64_t)ctx->sm_count * 8;
+    if (gx > cap) gx = cap;
+    if (a.No <= 4) k_narrow<4><<<(unsigned)gx, 256, 0, ctx->stream>>>(a);
+    else k_narrow<8><<<(unsigned)gx, 256, 0, ctx->stream>>>(a);
+  }
   GNB_CUDA(cudaGetLastError());
   return GNB_OK;
 }

@@ -55,18 +55,18 @@ struct ProjArgs {
 
 constexpr int PJ_OFF_A = 0;
 constexpr int PJ_OFF_W = BLK_BYTES;
-constexpr int PJ_OFF_MISC = 3 * BLK_BYTES;
-constexpr int PJ_SMEM = PJ_OFF_MISC + 256 + 1024;
+__host__ __device__ constexpr int pj_off_misc(int nblk) { return (1 + nblk) * BLK_BYTES; }
+__host__ __device__ constexpr int pj_smem(int nblk) { return pj_off_misc(nblk) + 256 + 1024; }
 enum { PB_WFULL = 0, PB_AREADY = 2, PB_ACCFREE = 3, PB_OUTDONE = 4 };
 
-template <int SRC>
-__global__ void __launch_bounds__(192, 2) k_tc_proj(const ProjArgs a) {
+template <int SRC, int NBLK>
+__global__ void __launch_bounds__(192, NBLK == 1 ? 3 : 2) k_tc_proj(const ProjArgs a) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
   uint8_t* sm = smem_raw + (base - raw);
   const uint32_t sA = base + PJ_OFF_A, sW = base + PJ_OFF_W;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sm + PJ_OFF_MISC);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sm + pj_off_misc(NBLK));
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
   const uint32_t bar0 = smem_u32(bars);
   auto BAR = [&](int i) { return bar0 + 8u * (uint32_t)i; };
@@ -77,7 +77,7 @@ __global__ void __launch_bounds__(192, 2) k_tc_proj(const ProjArgs a) {
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 4) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(256u) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)(128 * NBLK)) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   tc_fence_before();
@@ -88,7 +88,7 @@ __global__ void __launch_bounds__(192, 2) k_tc_proj(const ProjArgs a) {
   if (warp == 5) {
     // the (at most 2) weight blocks stay resident in shared memory for the whole kernel
     if (elect_one()) {
-      for (int b = 0; b < a.nblk; b++) {
+      for (int b = 0; b < NBLK; b++) {
         mbar_expect_tx(BAR(PB_WFULL + b), BLK_BYTES);
         bulk_g2s(sW + b * BLK_BYTES, reinterpret_cast<const uint8_t*>(a.wpack) + (size_t)b * BLK_BYTES, BLK_BYTES, BAR(PB_WFULL + b));
       }
@@ -96,14 +96,14 @@ __global__ void __launch_bounds__(192, 2) k_tc_proj(const ProjArgs a) {
     __syncwarp();
   } else if (warp == 4) {
     uint32_t tl = 0;
-    for (int b = 0; b < a.nblk; b++) mbar_wait(BAR(PB_WFULL + b), 0);
+    for (int b = 0; b < NBLK; b++) mbar_wait(BAR(PB_WFULL + b), 0);
     const uint64_t adesc = umma_desc(sA);
     for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, tl++) {
       mbar_wait(BAR(PB_AREADY), tl & 1);
       mbar_wait(BAR(PB_ACCFREE), (tl & 1) ^ 1);
       tc_fence_after();
       if (elect_one()) {
-        for (int b = 0; b < a.nblk; b++) {
+        for (int b = 0; b < NBLK; b++) {
           const uint64_t w = umma_desc(sW + b * BLK_BYTES);
           issue_ss(tmem + 128 * b, adesc, w, w + (KB_BYTES >> 4), false);
         }
@@ -189,10 +189,10 @@ __global__ void __launch_bounds__(192, 2) k_tc_proj(const ProjArgs a) {
       mbar_wait(BAR(PB_OUTDONE), tl & 1);
       tc_fence_after();
       // epilogue in the accumulator-fragment layout: every 4 lanes write one full 32 B sector
-      const int ld = a.nblk * H;
+      const int ld = NBLK * H;
       const int q = lane >> 2, cq = 2 * (lane & 3);
 #pragma unroll 1
-      for (int st = 0; st < 4 * a.nblk; st++) {
+      for (int st = 0; st < 4 * NBLK; st++) {
         const int hh = st & 1, ch = st >> 1;
         uint32_t d[32];
         TC_LD_FRAG64(tmem + lane_base + ((uint32_t)(16 * hh) << 16) + 64 * ch, d);
@@ -224,7 +224,7 @@ __global__ void __launch_bounds__(192, 2) k_tc_proj(const ProjArgs a) {
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(256u) : "memory");
+  if (warp == 4) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((uint32_t)(128 * NBLK)) : "memory");
 }
 
 // ------------------------------------------------------------------ weight packing
@@ -342,17 +342,18 @@ int tc_core_pack(gnb_ctx* ctx, const gnb_block_params& blk, const gnb_ffn_params
   return GNB_OK;
 }
 
-template <int SRC>
+template <int SRC, int NBLK>
 static int launch_proj(gnb_ctx* ctx, const ProjArgs& a, const char* name, double flops, double bytes) {
   if (a.num_tiles <= 0) return GNB_OK;
   static bool attr_set = false;
   if (!attr_set) {
-    GNB_CUDA(cudaFuncSetAttribute(k_tc_proj<SRC>, cudaFuncAttributeMaxDynamicSharedMemorySize, PJ_SMEM));
+    GNB_CUDA(cudaFuncSetAttribute(k_tc_proj<SRC, NBLK>, cudaFuncAttributeMaxDynamicSharedMemorySize, pj_smem(NBLK)));
     attr_set = true;
   }
-  const int grid = a.num_tiles < 2 * ctx->sm_count ? a.num_tiles : 2 * ctx->sm_count;
+  const int per_sm = NBLK == 1 ? 3 : 2;
+  const int grid = a.num_tiles < per_sm * ctx->sm_count ? a.num_tiles : per_sm * ctx->sm_count;
   Launch L(ctx, name, bytes, flops);
-  k_tc_proj<SRC><<<grid, 192, PJ_SMEM, ctx->stream>>>(a);
+  k_tc_proj<SRC, NBLK><<<grid, 192, pj_smem(NBLK), ctx->stream>>>(a);
   GNB_CUDA(cudaGetLastError());
   return GNB_OK;
 }
@@ -390,7 +391,7 @@ int tc_core_forward(gnb_ctx* ctx, const gnb_graph* g, const TcCorePack* pk, cons
     a.x = xn; a.out = Psr; a.R = N; a.num_tiles = ceil_div(N, TM); a.nblk = 2; a.wpack = pk->w_proj;
     a.addend = Pue; a.addend_idx = g->node_graph; a.add_col0 = H;   // P_r += P_u[graph of the node]
     a.eps = ln1[1].eps; a.eps_mode = ln1[1].eps_mode;
-    GNB_TRY(launch_proj<SRC_LN>(ctx, a, "tc_node_proj", 2.0 * N * 2 * HH, 4.0 * N * 3 * H));
+    GNB_TRY((launch_proj<SRC_LN, 2>(ctx, a, "tc_node_proj", 2.0 * N * 2 * HH, 4.0 * N * 3 * H)));
   }
   {  // edges: GNBlock edge update + FFN + residual; partial receiver sums of the inputs
     EdgeArgs a{};
@@ -407,13 +408,13 @@ int tc_core_forward(gnb_ctx* ctx, const gnb_graph* g, const TcCorePack* pk, cons
     ProjArgs a{};
     a.x = Epart; a.part_ptr = g->node_part_ptr; a.x2 = Gpart; a.sum2 = Gs; a.addend = Gs; a.out = agg; a.R = N; a.num_tiles = ceil_div(N, TM); a.nblk = 1;
     a.wpack = pk->w_eblk;
-    GNB_TRY(launch_proj<SRC_AGG>(ctx, a, "tc_agg", 2.0 * N * HH, 4.0 * N * 3 * H));
+    GNB_TRY((launch_proj<SRC_AGG, 1>(ctx, a, "tc_agg", 2.0 * N * HH, 4.0 * N * 3 * H)));
   }
   {  // W_na . agg
     ProjArgs a{};
     a.x = agg; a.part_ptr = nullptr; a.out = Pagg; a.R = N; a.num_tiles = ceil_div(N, TM); a.nblk = 1;
     a.wpack = pk->w_agg;
-    GNB_TRY(launch_proj<SRC_AGG>(ctx, a, "tc_agg_proj", 2.0 * N * HH, 4.0 * N * 2 * H));
+    GNB_TRY((launch_proj<SRC_AGG, 1>(ctx, a, "tc_agg_proj", 2.0 * N * HH, 4.0 * N * 2 * H)));
   }
   {  // nodes: same fused kernel; the node -> graph sum of the block output h_v = W_nv' v^ + P_agg + P_un[g] is taken by
      // linearity over the partial sums of v^ (V_part) and of the addends (N_part), so h_v is never materialised
