@@ -53,31 +53,38 @@ struct ProjArgs {
   int eps_mode;
 };
 
-constexpr int PJ_OFF_A = 0;
-constexpr int PJ_OFF_W = BLK_BYTES;
-__host__ __device__ constexpr int pj_off_misc(int nblk) { return (1 + nblk) * BLK_BYTES; }
+// smem: A[2] (32 KB each) | W[NBLK] (32 KB each, resident) | barriers
+__host__ __device__ constexpr int pj_off_w() { return 2 * BLK_BYTES; }
+__host__ __device__ constexpr int pj_off_misc(int nblk) { return (2 + nblk) * BLK_BYTES; }
 __host__ __device__ constexpr int pj_smem(int nblk) { return pj_off_misc(nblk) + 256 + 1024; }
-enum { PB_WFULL = 0, PB_AREADY = 2, PB_ACCFREE = 3, PB_OUTDONE = 4 };
+enum { PB_WFULL = 0, PB_AFULL = 2, PB_AEMPTY = 4, PB_OUTDONE = 6, PB_ACCFREE = 8 };
+constexpr int PJ_THREADS = 10 * 32;
 
+// Pipelined over tiles: warps 4-7 build the bf16 A operand of tile t+1 (double buffered) while warp 8 issues the MMAs
+// of tile t and warps 0-3 drain the accumulator of tile t-1 (TMEM double buffered); weights stay resident.
 template <int SRC, int NBLK>
-__global__ void __launch_bounds__(192, NBLK == 1 ? 3 : 2) k_tc_proj(const ProjArgs a) {
+__global__ void __launch_bounds__(PJ_THREADS, NBLK == 1 ? 2 : 1) k_tc_proj(const ProjArgs a) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
   uint8_t* sm = smem_raw + (base - raw);
-  const uint32_t sA = base + PJ_OFF_A, sW = base + PJ_OFF_W;
+  const uint32_t sW = base + pj_off_w();
   uint64_t* bars = reinterpret_cast<uint64_t*>(sm + pj_off_misc(NBLK));
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
   const uint32_t bar0 = smem_u32(bars);
   auto BAR = [&](int i) { return bar0 + 8u * (uint32_t)i; };
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  constexpr uint32_t TCOLS = 256u * NBLK;     // 2 accumulator sets
   if (tid == 0) {
     mbar_init(BAR(PB_WFULL), 1); mbar_init(BAR(PB_WFULL + 1), 1);
-    mbar_init(BAR(PB_AREADY), 128); mbar_init(BAR(PB_ACCFREE), 128); mbar_init(BAR(PB_OUTDONE), 1);
+    for (int s = 0; s < 2; s++) {
+      mbar_init(BAR(PB_AFULL + s), 128); mbar_init(BAR(PB_AEMPTY + s), 1);
+      mbar_init(BAR(PB_OUTDONE + s), 1); mbar_init(BAR(PB_ACCFREE + s), 128);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 4) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)(128 * NBLK)) : "memory");
+  if (warp == 8) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TCOLS) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   tc_fence_before();
@@ -85,8 +92,7 @@ __global__ void __launch_bounds__(192, NBLK == 1 ? 3 : 2) k_tc_proj(const ProjAr
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
 
-  if (warp == 5) {
-    // the (at most 2) weight blocks stay resident in shared memory for the whole kernel
+  if (warp == 9) {
     if (elect_one()) {
       for (int b = 0; b < NBLK; b++) {
         mbar_expect_tx(BAR(PB_WFULL + b), BLK_BYTES);
@@ -94,50 +100,97 @@ __global__ void __launch_bounds__(192, NBLK == 1 ? 3 : 2) k_tc_proj(const ProjAr
       }
     }
     __syncwarp();
-  } else if (warp == 4) {
+  } else if (warp == 8) {
     uint32_t tl = 0;
     for (int b = 0; b < NBLK; b++) mbar_wait(BAR(PB_WFULL + b), 0);
-    const uint64_t adesc = umma_desc(sA);
     for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, tl++) {
-      mbar_wait(BAR(PB_AREADY), tl & 1);
-      mbar_wait(BAR(PB_ACCFREE), (tl & 1) ^ 1);
+      const uint32_t st = tl & 1, ph = (tl >> 1) & 1;
+      mbar_wait(BAR(PB_AFULL + st), ph);
+      mbar_wait(BAR(PB_ACCFREE + st), ph ^ 1);
       tc_fence_after();
       if (elect_one()) {
+        const uint64_t adesc = umma_desc(base + st * BLK_BYTES);
         for (int b = 0; b < NBLK; b++) {
           const uint64_t w = umma_desc(sW + b * BLK_BYTES);
-          issue_ss(tmem + 128 * b, adesc, w, w + (KB_BYTES >> 4), false);
+          issue_ss(tmem + (st * NBLK + b) * 128, adesc, w, w + (KB_BYTES >> 4), false);
         }
-        tc_commit(BAR(PB_OUTDONE));
+        tc_commit(BAR(PB_AEMPTY + st));
+        tc_commit(BAR(PB_OUTDONE + st));
       }
       __syncwarp();
     }
-  } else {
-    const uint32_t lane_base = ((uint32_t)(warp * 32)) << 16;
+  } else if (warp >= 4) {
+    // ===================================================== A-operand producers, one tile ahead
+    const int q = warp - 4;
     uint32_t tl = 0;
     for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, tl++) {
-      const int64_t row0 = (int64_t)tile * TM;
-      const int rows = (int)((a.R - row0) < TM ? (a.R - row0) : TM);
-      const int wrows = rows - warp * 32 < 0 ? 0 : (rows - warp * 32 > 32 ? 32 : rows - warp * 32);
-      if (tl > 0) mbar_wait(BAR(PB_OUTDONE), (tl - 1) & 1);   // previous MMAs have finished reading A
-      // 32 lanes per row (512 B, fully coalesced), 4 rows in flight
+      const uint32_t st = tl & 1, ph = (tl >> 1) & 1;
+      const int64_t row0 = (int64_t)tile * TM + 32 * q;
+      const int64_t left = a.R - row0;
+      const int wrows = left < 0 ? 0 : (left > 32 ? 32 : (int)left);
+      uint8_t* A = sm + st * BLK_BYTES;
       if (SRC == SRC_LN) {
+        // 8 lanes per row (tc_edge.cu LN warps): 4 rows x 128 B per load instruction, 3 shuffle levels per statistic
+        const int rr = lane >> 3, l8 = lane & 7;
+        const float* xbase = a.x + 4 * l8;
+        const uint32_t a_lane = (uint32_t)((32 * q) * 128 + (l8 & 1) * 8);
+        const uint32_t a_chunk = (uint32_t)(l8 >> 1);
+        float4 xa[2][4];
+        auto issue = [&](int i0) {
+#pragma unroll
+          for (int h = 0; h < 2; h++) {
+            int64_t r = row0 + i0 + 4 * h + rr;
+            r = r < a.R ? r : a.R - 1;
+            const float4* p = reinterpret_cast<const float4*>(xbase + (size_t)r * H);
+#pragma unroll
+            for (int j = 0; j < 4; j++) xa[h][j] = __ldg(p + 8 * j);
+          }
+        };
+        issue(0);
+        mbar_wait(BAR(PB_AEMPTY + st), ph ^ 1);
 #pragma unroll 1
-        for (int i0 = 0; i0 < 32; i0 += 4) {
-          float4 v[4];
+        for (int i0 = 0; i0 < 32; i0 += 8) {
+          float4 xc[2][4];
+          float s[2];
 #pragma unroll
-          for (int u = 0; u < 4; u++)
-            v[u] = (i0 + u < wrows) ? __ldg(reinterpret_cast<const float4*>(a.x + (size_t)(row0 + warp * 32 + i0 + u) * H) + lane) : f4zero();
+          for (int h = 0; h < 2; h++) {
 #pragma unroll
-          for (int u = 0; u < 4; u++) {
-            const int r = warp * 32 + i0 + u;
-            const float mu = warp_sum((v[u].x + v[u].y) + (v[u].z + v[u].w)) * (1.0f / H);
-            const float dx = v[u].x - mu, dy = v[u].y - mu, dz = v[u].z - mu, dw = v[u].w - mu;
-            const float var = warp_sum((dx * dx + dy * dy) + (dz * dz + dw * dw)) * (1.0f / H);
-            const float rs = (i0 + u < wrows) ? ln_rstd(var, a.eps, a.eps_mode) : 0.f;
-            uint2 pk;
-            pk.x = pack_bf16(dx * rs, dy * rs);
-            pk.y = pack_bf16(dz * rs, dw * rs);
-            *reinterpret_cast<uint2*>(sm + PJ_OFF_A + sw_off(r, 4 * lane)) = pk;
+            for (int j = 0; j < 4; j++) xc[h][j] = xa[h][j];
+            const float4 t = f4add(f4add(xc[h][0], xc[h][1]), f4add(xc[h][2], xc[h][3]));
+            s[h] = (t.x + t.y) + (t.z + t.w);
+          }
+          if (i0 + 8 < 32) issue(i0 + 8);
+#pragma unroll
+          for (int o = 1; o < 8; o <<= 1)
+#pragma unroll
+            for (int h = 0; h < 2; h++) s[h] += __shfl_xor_sync(0xffffffffu, s[h], o);
+#pragma unroll
+          for (int h = 0; h < 2; h++) {
+            const float mu = s[h] * (1.0f / H);
+            float t = 0.f;
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+              xc[h][j].x -= mu; xc[h][j].y -= mu; xc[h][j].z -= mu; xc[h][j].w -= mu;
+              t += (xc[h][j].x * xc[h][j].x + xc[h][j].y * xc[h][j].y) + (xc[h][j].z * xc[h][j].z + xc[h][j].w * xc[h][j].w);
+            }
+            s[h] = t;
+          }
+#pragma unroll
+          for (int o = 1; o < 8; o <<= 1)
+#pragma unroll
+            for (int h = 0; h < 2; h++) s[h] += __shfl_xor_sync(0xffffffffu, s[h], o);
+#pragma unroll
+          for (int h = 0; h < 2; h++) {
+            const int i = i0 + 4 * h + rr;
+            const float rs = (i < wrows) ? ln_rstd(s[h] * (1.0f / H), a.eps, a.eps_mode) : 0.f;
+            const uint32_t rowoff = a_lane + (uint32_t)i * 128;
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+              uint2 pk;
+              pk.x = pack_bf16(xc[h][j].x * rs, xc[h][j].y * rs);
+              pk.y = pack_bf16(xc[h][j].z * rs, xc[h][j].w * rs);
+              *reinterpret_cast<uint2*>(A + (j >> 1) * KB_BYTES + rowoff + (((a_chunk + 4 * (j & 1)) ^ (uint32_t)(i & 7)) << 4)) = pk;
+            }
           }
         }
       } else {
@@ -146,12 +199,34 @@ __global__ void __launch_bounds__(192, NBLK == 1 ? 3 : 2) k_tc_proj(const ProjAr
         // rows (8-16 loads) in flight; longer segments (a receiver spread over > 2 32-edge blocks) loop.
         int p0 = 0, p1 = 0;
         if (lane < wrows) {
-          const int64_t r = row0 + warp * 32 + lane;
+          const int64_t r = row0 + lane;
           if (a.part_ptr) { p0 = __ldg(a.part_ptr + r); p1 = __ldg(a.part_ptr + r + 1); }
           else { p0 = (int)r; p1 = (int)r + 1; }
         }
         const float4* X = reinterpret_cast<const float4*>(a.x) + lane;
         const float4* X2 = reinterpret_cast<const float4*>(a.x2) + lane;
+        mbar_wait(BAR(PB_AEMPTY + st), ph ^ 1);
+        if (a.part_ptr == nullptr) {
+          // plain rows: 8 coalesced row loads in flight
+#pragma unroll 1
+          for (int i0 = 0; i0 < 32; i0 += 8) {
+            float4 v[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+              int64_t r = row0 + i0 + u;
+              r = r < a.R ? r : a.R - 1;
+              v[u] = __ldg(X + (size_t)r * (H / 4));
+            }
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+              const bool ok = i0 + u < wrows;
+              uint2 pk;
+              pk.x = ok ? pack_bf16(v[u].x, v[u].y) : 0u;
+              pk.y = ok ? pack_bf16(v[u].z, v[u].w) : 0u;
+              *reinterpret_cast<uint2*>(A + sw_off(q * 32 + i0 + u, 4 * lane)) = pk;
+            }
+          }
+        } else
 #pragma unroll 1
         for (int i0 = 0; i0 < 32; i0 += 4) {
           float4 s[4], t[4], s2[4], t2[4];
@@ -174,57 +249,80 @@ __global__ void __launch_bounds__(192, NBLK == 1 ? 3 : 2) k_tc_proj(const ProjAr
             uint2 pk;
             pk.x = pack_bf16(s[u].x, s[u].y);
             pk.y = pack_bf16(s[u].z, s[u].w);
-            *reinterpret_cast<uint2*>(sm + PJ_OFF_A + sw_off(warp * 32 + i0 + u, 4 * lane)) = pk;
+            *reinterpret_cast<uint2*>(A + sw_off(q * 32 + i0 + u, 4 * lane)) = pk;
             if (a.x2) {
               s2[u] = f4add(s2[u], t2[u]);
               for (int p = q0[u] + 2; p < q1[u]; p++) s2[u] = f4add(s2[u], __ldg(X2 + (size_t)p * (H / 4)));
-              if (i0 + u < wrows) *(reinterpret_cast<float4*>(a.sum2 + (size_t)(row0 + warp * 32 + i0 + u) * H) + lane) = s2[u];
+              if (i0 + u < wrows) *(reinterpret_cast<float4*>(a.sum2 + (size_t)(row0 + i0 + u) * H) + lane) = s2[u];
             }
           }
         }
-        __syncwarp();   // sum2 rows written above are read back (other lanes, same warp) by the epilogue
       }
       fence_async_smem();
-      mbar_arrive(BAR(PB_AREADY));
-      mbar_wait(BAR(PB_OUTDONE), tl & 1);
+      mbar_arrive(BAR(PB_AFULL + st));   // release: also publishes the sum2 rows to the drain warps
+    }
+  } else {
+    // ===================================================== accumulator drain (TMEM lane quadrant = warp), fragment layout:
+    // every 4 lanes write one full 32 B sector
+    const uint32_t lane_base = ((uint32_t)(warp * 32)) << 16;
+    const int ld = NBLK * H;
+    const int q = lane >> 2, cq = 2 * (lane & 3);
+    uint32_t tl = 0;
+    for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, tl++) {
+      const uint32_t st = tl & 1, ph = (tl >> 1) & 1;
+      const int64_t row0 = (int64_t)tile * TM;
+      const int rows = (int)((a.R - row0) < TM ? (a.R - row0) : TM);
+      // addends may be produced by this tile's A-operand warps (sum2): they are complete once the A tile is
+      mbar_wait(BAR(PB_AFULL + st), ph);
+      int64_t ar[4];
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        int64_t r = row0 + warp * 32 + q + 8 * k;
+        r = r < a.R ? r : a.R - 1;
+        ar[k] = (a.addend && a.addend_idx) ? (int64_t)__ldg(a.addend_idx + r) : r;
+      }
+      float2 t[2][8];
+      auto fetch = [&](int stp, int h2, float2 (&dst)[8]) {
+        const int hh = stp & 1, ch = stp >> 1;
+        const bool has = a.addend != nullptr && 64 * ch >= a.add_col0;
+        const float* ad = a.addend + (size_t)ar[2 * hh + h2] * H + (has ? (64 * ch - a.add_col0) : 0) + cq;
+#pragma unroll
+        for (int n = 0; n < 8; n++) dst[n] = has ? *reinterpret_cast<const float2*>(ad + 8 * n) : make_float2(0.f, 0.f);
+      };
+      fetch(0, 0, t[0]);
+      fetch(0, 1, t[1]);
+      mbar_wait(BAR(PB_OUTDONE + st), ph);
       tc_fence_after();
-      // epilogue in the accumulator-fragment layout: every 4 lanes write one full 32 B sector
-      const int ld = NBLK * H;
-      const int q = lane >> 2, cq = 2 * (lane & 3);
 #pragma unroll 1
-      for (int st = 0; st < 4 * NBLK; st++) {
-        const int hh = st & 1, ch = st >> 1;
+      for (int stp = 0; stp < 4 * NBLK; stp++) {
+        const int hh = stp & 1, ch = stp >> 1;
         uint32_t d[32];
-        TC_LD_FRAG64(tmem + lane_base + ((uint32_t)(16 * hh) << 16) + 64 * ch, d);
+        TC_LD_FRAG64(tmem + (st * NBLK) * 128 + lane_base + ((uint32_t)(16 * hh) << 16) + 64 * ch, d);
         tc_wait_ld();
+        if (stp == 4 * NBLK - 1) {
+          tc_fence_before();
+          mbar_arrive(BAR(PB_ACCFREE + st));
+        }
 #pragma unroll
         for (int h2 = 0; h2 < 2; h2++) {
           const int r = warp * 32 + 16 * hh + q + 8 * h2;
+          float2 v[8];
+#pragma unroll
+          for (int n = 0; n < 8; n++)
+            v[n] = make_float2(__uint_as_float(d[4 * n + 2 * h2]) + t[h2][n].x, __uint_as_float(d[4 * n + 2 * h2 + 1]) + t[h2][n].y);
+          if (stp + 1 < 4 * NBLK) fetch(stp + 1, h2, t[h2]);     // next step's addends fly during this step's stores
           if (r < rows) {
             float* o = a.out + (size_t)(row0 + r) * ld + 64 * ch + cq;
-            const float* ad = nullptr;
-            if (a.addend && 64 * ch >= a.add_col0) {
-              const int64_t ar = a.addend_idx ? (int64_t)__ldg(a.addend_idx + row0 + r) : row0 + r;
-              ad = a.addend + (size_t)ar * H + (64 * ch - a.add_col0) + cq;
-            }
-            float2 t[8];
 #pragma unroll
-            for (int n = 0; n < 8; n++) t[n] = ad ? *reinterpret_cast<const float2*>(ad + 8 * n) : make_float2(0.f, 0.f);
-#pragma unroll
-            for (int n = 0; n < 8; n++) {
-              float2 v = make_float2(__uint_as_float(d[4 * n + 2 * h2]) + t[n].x, __uint_as_float(d[4 * n + 2 * h2 + 1]) + t[n].y);
-              *reinterpret_cast<float2*>(o + 8 * n) = v;
-            }
+            for (int n = 0; n < 8; n++) *reinterpret_cast<float2*>(o + 8 * n) = v[n];
           }
         }
       }
-      tc_fence_before();
-      mbar_arrive(BAR(PB_ACCFREE));
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((uint32_t)(128 * NBLK)) : "memory");
+  if (warp == 8) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TCOLS) : "memory");
 }
 
 // ------------------------------------------------------------------ weight packing
@@ -350,10 +448,10 @@ static int launch_proj(gnb_ctx* ctx, const ProjArgs& a, const char* name, double
     GNB_CUDA(cudaFuncSetAttribute(k_tc_proj<SRC, NBLK>, cudaFuncAttributeMaxDynamicSharedMemorySize, pj_smem(NBLK)));
     attr_set = true;
   }
-  const int per_sm = NBLK == 1 ? 3 : 2;
+  const int per_sm = NBLK == 1 ? 2 : 1;
   const int grid = a.num_tiles < per_sm * ctx->sm_count ? a.num_tiles : per_sm * ctx->sm_count;
   Launch L(ctx, name, bytes, flops);
-  k_tc_proj<SRC, NBLK><<<grid, 192, pj_smem(NBLK), ctx->stream>>>(a);
+  k_tc_proj<SRC, NBLK><<<grid, PJ_THREADS, pj_smem(NBLK), ctx->stream>>>(a);
   GNB_CUDA(cudaGetLastError());
   return GNB_OK;
 }
