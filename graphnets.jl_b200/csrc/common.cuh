@@ -86,7 +86,8 @@ struct gnb_graph {
   int32_t* node_gpart = nullptr;       // [N]   partial-row id of each node
   int32_t* graph_npart_ptr = nullptr;  // [B+1] partial rows of graph b = [graph_npart_ptr[b], graph_npart_ptr[b+1])
   int64_t n_nparts = 0;
-  void* all = nullptr;  // single allocation backing everything above
+  void* all = nullptr;  // single (stream-ordered) allocation backing everything above
+  cudaStream_t stream = nullptr;   // stream the allocation is ordered on
 };
 
 // RAII bracket of one kernel launch: counts it and, when profiling, times it with CUDA events.

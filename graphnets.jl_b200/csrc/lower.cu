@@ -318,7 +318,19 @@ extern "C" int gnb_graph_lower(gnb_ctx* ctx, const void* adj, int adj_dtype, int
   size_t o_gep = take(B + 1), o_gnp = take(B + 1), o_nip = take(N + 1), o_ep = take(E), o_npp = take(N + 1);
   size_t o_gpp = take(B + 1);
   size_t o_ngp = take(N), o_gnpp = take(B + 1);
-  cudaError_t ce = cudaMalloc(&g->all, off ? off : 256);
+  // stream-ordered pool allocation: a lowering per batch (the e2e path) must not pay cudaMalloc / cudaFree device syncs
+  static bool pool_set = false;
+  if (!pool_set) {
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, ctx->device) == cudaSuccess) {
+      uint64_t thr = ~0ull;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    }
+    cudaGetLastError();
+    pool_set = true;
+  }
+  g->stream = ctx->stream;
+  cudaError_t ce = cudaMallocAsync(&g->all, off ? off : 256, ctx->stream);
   if (ce != cudaSuccess) {
     delete g;
     gnb_set_error("gnb_graph_lower: cudaMalloc(%zu) failed: %s", off, cudaGetErrorString(ce));
@@ -390,7 +402,7 @@ extern "C" int gnb_graph_lower(gnb_ctx* ctx, const void* adj, int adj_dtype, int
   } while (0);
 #undef DISPATCH
   if (ret != GNB_OK) {
-    cudaFree(g->all);
+    cudaFreeAsync(g->all, ctx->stream);
     delete g;
     return ret;
   }
@@ -401,7 +413,7 @@ extern "C" int gnb_graph_lower(gnb_ctx* ctx, const void* adj, int adj_dtype, int
 extern "C" int gnb_graph_destroy(gnb_graph* g) {
   if (!g) return GNB_OK;
   cudaSetDevice(g->device);
-  if (g->all) cudaFree(g->all);
+  if (g->all) cudaFreeAsync(g->all, g->stream);
   delete g;
   return GNB_OK;
 }

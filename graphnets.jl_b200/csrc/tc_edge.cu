@@ -6,12 +6,12 @@
 //         (the edge -> node aggregation of src/nodefninput.jl:3, "aggregate, then transform")
 //
 // One 128-row tile per pass; persistent CTA, one per SM, 14 warps:
-//   warps 0-3   DRAIN : FFN hidden chunk TMEM fp32 -> +b1 -> relu -> bf16 -> TMEM (in place, the A operand of the
+//   warps 8-11  DRAIN : FFN hidden chunk TMEM fp32 -> +b1 -> relu -> bf16 -> TMEM (in place, the A operand of the
 //                       down-projection); finished accumulator TMEM -> swizzled shared-memory staging tile
-//   warps 4-7   LN    : one tile AHEAD of the MMAs: coalesced row loads (8 rows in flight per warp), LayerNorm with
+//   warps 0-3   LN    : one tile AHEAD of the MMAs: coalesced row loads (8 rows in flight per warp), LayerNorm with
 //                       transposed butterfly reductions, bf16 A operand into 128B-swizzled K-major shared memory,
 //                       partial sums E_part
-//   warps 8-11  OUT   : one tile BEHIND: staging row + x row + gathered P_s / P_r' rows, all 512 B coalesced,
+//   warps 4-7   OUT   : one tile BEHIND: staging row + x row + gathered P_s / P_r' rows, all 512 B coalesced,
 //                       -> y (streaming stores), partial sums G_part
 //   warp 12     MMA issuer (one elected lane), warp 13 weight loader (cp.async.bulk, 5 x 16 KB ring)
 // TMEM (512 columns): D[2] accumulators (double buffered across tiles: the epilogue of tile t overlaps the MMAs of
@@ -20,6 +20,7 @@
 //   up1 blk down0 up2 down1 up3 down2 [up0 of the next tile] down3
 #include "tc_ptx.cuh"
 #include "tc_edge.cuh"
+#include <stdlib.h>
 
 using namespace tcx;
 
@@ -31,20 +32,33 @@ constexpr int E_OFF_A = 0;                                   // 2 stages x 32 KB
 constexpr int E_OFF_W = 2 * BLK_BYTES;                       // 5 x 16 KB
 constexpr int E_OFF_STG = E_OFF_W + NWS * HALF_BYTES;        // 64 KB: [4 column groups][128 rows][128 B], 16B chunks XOR (row & 7)
 constexpr int E_OFF_MISC = E_OFF_STG + 65536;
-constexpr int E_MISC = 512 * 4 + 128 * 4 + 40 * 8 + 16;      // b1f[512], b2[128], barriers[40], tmem slot
+constexpr int E_MISC = 512 * 4 + 128 * 4 + 40 * 8 + 16;      // (29 barriers used)      // b1f[512], b2[128], barriers[40], tmem slot
 constexpr int E_SMEM = E_OFF_MISC + E_MISC + 1024;
 constexpr int E_WARPS = 14;
 constexpr int E_THREADS = E_WARPS * 32;
 enum { EB_WFULL = 0, EB_WEMPTY = 5, EB_AFULL = 10, EB_AEMPTY = 12, EB_HIDFULL = 14, EB_HSREADY = 16, EB_OUTDONE = 18,
-       EB_ACCFREE = 20, EB_STGFULL = 22, EB_STGEMPTY = 23 };
+       EB_ACCFREE = 20, EB_STGFULL = 22, EB_STGEMPTY = 23, EB_PEERW = 24 };
 
 // block ids inside the packed edge weights (tc.cu::tc_core_pack): W1_0 W_blk W2_0 W1_1 W2_1 W1_2 W2_2 W1_3 W2_3
 constexpr int PK_W1_0 = 0, PK_BLK = 1, PK_W2_0 = 2, PK_W1_1 = 3, PK_W2_1 = 4, PK_W1_2 = 5, PK_W2_2 = 6, PK_W1_3 = 7, PK_W2_3 = 8;
 // issue order of a tile: [up0 up1 blk] [dn0 dn1] [up2 up3] [dn2 dn3]  (grouped: every SS <-> TS operand-mode switch of the
 // tensor pipe costs ~435 cycles, scratch/hwprobe.cu T5), one nibble per block
+#ifdef GNB_EXP_ORDERB
+constexpr unsigned long long SEQ_PACKED = (unsigned long long)PK_W1_0 | ((unsigned long long)PK_W1_1 << 4) | ((unsigned long long)PK_W2_0 << 8) |
+    ((unsigned long long)PK_BLK << 12) | ((unsigned long long)PK_W2_1 << 16) | ((unsigned long long)PK_W1_2 << 20) |
+    ((unsigned long long)PK_W1_3 << 24) | ((unsigned long long)PK_W2_2 << 28) | ((unsigned long long)PK_W2_3 << 32);
+constexpr int B_BLK = 3, B_FIRSTD = 2;
+#define IS_DN(b) (((b) == 2) | ((b) == 4) | ((b) == 7) | ((b) == 8))
+#define HB_OF(b) ((((b) == 0) | ((b) == 2) | ((b) == 5) | ((b) == 7)) ? 0 : 1)
+#else
 constexpr unsigned long long SEQ_PACKED = (unsigned long long)PK_W1_0 | ((unsigned long long)PK_W1_1 << 4) | ((unsigned long long)PK_BLK << 8) |
     ((unsigned long long)PK_W2_0 << 12) | ((unsigned long long)PK_W2_1 << 16) | ((unsigned long long)PK_W1_2 << 20) |
     ((unsigned long long)PK_W1_3 << 24) | ((unsigned long long)PK_W2_2 << 28) | ((unsigned long long)PK_W2_3 << 32);
+constexpr int B_BLK = 2, B_FIRSTD = 2;
+#define IS_DN(b) (((b) == 3) | ((b) == 4) | ((b) == 7) | ((b) == 8))
+#define HB_OF(b) ((((b) == 0) | ((b) == 3) | ((b) == 5) | ((b) == 7)) ? 0 : 1)
+#endif
+
 
 #ifdef GNB_TC_TIMING
 #define EDBG(k)                                                                                     \
@@ -116,6 +130,9 @@ __device__ __forceinline__ float4 ld_stream(const float* p) {   // read-once dat
   return v;
 }
 
+// CL2: the two CTAs of a cluster (an SM pair) run one 256-row MMA stream (cta_group::2): each CTA holds half of every weight
+// block (N split) - half the weight bytes per SM and a ring twice as deep in blocks - and its own 128-row tile otherwise.
+template <bool CL2>
 __global__ void __launch_bounds__(E_THREADS, 1) k_edge5(const EdgeArgs a) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
@@ -129,26 +146,48 @@ __global__ void __launch_bounds__(E_THREADS, 1) k_edge5(const EdgeArgs a) {
   const uint32_t bar0 = smem_u32(bars);
   auto BAR = [&](int i) { return bar0 + 8u * (uint32_t)i; };
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t rank = CL2 ? cluster_ctarank() : 0u;      // == blockIdx.x & 1 (clusters are consecutive block pairs)
+  constexpr uint32_t NARR = CL2 ? 8u : 4u;                  // one arrival per warp (lane 0 after __syncwarp) on the barriers the 4-warp groups feed
 
   if (tid == 0) {
-    for (int i = 0; i < NWS; i++) { mbar_init(BAR(EB_WFULL + i), 1); mbar_init(BAR(EB_WEMPTY + i), 1); }
+    for (int i = 0; i < NWS; i++) { mbar_init(BAR(EB_WFULL + i), 1); mbar_init(BAR(EB_WEMPTY + i), 1); mbar_init(BAR(EB_PEERW + i), 1); }
     for (int s = 0; s < 2; s++) {
-      mbar_init(BAR(EB_AFULL + s), 128); mbar_init(BAR(EB_AEMPTY + s), 1);
-      mbar_init(BAR(EB_HIDFULL + s), 1); mbar_init(BAR(EB_HSREADY + s), 128);
-      mbar_init(BAR(EB_OUTDONE + s), 1); mbar_init(BAR(EB_ACCFREE + s), 128);
+      mbar_init(BAR(EB_AFULL + s), NARR); mbar_init(BAR(EB_AEMPTY + s), 1);
+      mbar_init(BAR(EB_HIDFULL + s), 1); mbar_init(BAR(EB_HSREADY + s), NARR);
+      mbar_init(BAR(EB_OUTDONE + s), 1); mbar_init(BAR(EB_ACCFREE + s), NARR);
     }
-    mbar_init(BAR(EB_STGFULL), 128); mbar_init(BAR(EB_STGEMPTY), 128);
+    mbar_init(BAR(EB_STGFULL), 4); mbar_init(BAR(EB_STGEMPTY), 4);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 12) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (CL2) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   for (int i = tid; i < 512; i += E_THREADS) sB1[i] = a.b1f[i];
   if (tid < 128) sB2[tid] = a.b2[tid];
   tc_fence_before();
   __syncthreads();
+  if (CL2) cluster_sync_all();      // the peer's barriers are initialised before any remote arrive / multicast commit
   tc_fence_after();
+  // leader-side barriers fed by both CTAs: arrive through the cluster address of CTA 0
+  // warp-level arrive: every lane has fenced its own writes; __syncwarp orders them before lane 0's release
+  auto ARRIVE_LEADER = [&](int i) {
+    __syncwarp();
+    if (lane == 0) {
+      if (CL2) mbar_arrive_cluster(map_to_cta(BAR(i), 0));
+      else mbar_arrive(BAR(i));
+    }
+  };
+  auto ARRIVE_LOCAL = [&](int i) {
+    __syncwarp();
+    if (lane == 0) mbar_arrive(BAR(i));
+  };
+#define TILE_OK(t) ((t) - (int)rank < a.num_tiles)   /* both CTAs of a pair run the same number of passes */
   const uint32_t tmem = *tmem_slot;
   const uint32_t HdA = tmem + 256, HdB = tmem + 384;
   const int grid = gridDim.x;
@@ -157,6 +196,20 @@ __global__ void __launch_bounds__(E_THREADS, 1) k_edge5(const EdgeArgs a) {
     // ===================================================== weight loader
     uint32_t it = 0;
     auto load_block = [&](int blk) {
+      if (CL2) {
+        // one ring stage = this CTA's N half of the block: rows [64 rank, 64 rank + 64) of both 64-wide K halves
+        const uint32_t st = it % NWS, ph = (it / NWS) & 1;
+        it++;
+        mbar_wait(BAR(EB_WEMPTY + st), ph ^ 1);
+        if (elect_one()) {
+          mbar_expect_tx(BAR(EB_WFULL + st), HALF_BYTES);
+          const uint8_t* src = reinterpret_cast<const uint8_t*>(a.wpack) + (size_t)blk * BLK_BYTES + (size_t)rank * 8192;
+          bulk_g2s(sW + st * HALF_BYTES, src, 8192, BAR(EB_WFULL + st));
+          bulk_g2s(sW + st * HALF_BYTES + 8192, src + HALF_BYTES, 8192, BAR(EB_WFULL + st));
+        }
+        __syncwarp();
+        return;
+      }
       for (int half = 0; half < 2; half++, it++) {
         const uint32_t st = it % NWS, ph = (it / NWS) & 1;
         mbar_wait(BAR(EB_WEMPTY + st), ph ^ 1);
@@ -169,7 +222,7 @@ __global__ void __launch_bounds__(E_THREADS, 1) k_edge5(const EdgeArgs a) {
         __syncwarp();
       }
     };
-    for (int tile = blockIdx.x; tile < a.num_tiles; tile += grid) {
+    for (int tile = blockIdx.x; TILE_OK(tile); tile += grid) {
 #pragma unroll 1
       for (int b = 0; b < 9; b++) load_block((SEQ_PACKED >> (4 * b)) & 15);
     }
@@ -178,7 +231,28 @@ __global__ void __launch_bounds__(E_THREADS, 1) k_edge5(const EdgeArgs a) {
     uint32_t it = 0, tl = 0;
     uint64_t w0 = 0, w1 = 0;
     uint32_t st0 = 0, st1 = 0;
+    if (CL2 && rank != 0) {
+      // peer CTA: relay "my half of the weight block has landed" to the leader, in ring order
+      for (int tile = blockIdx.x; TILE_OK(tile); tile += grid) {
+#pragma unroll 1
+        for (int b = 0; b < 9; b++, it++) {
+          const uint32_t st = it % NWS, ph = (it / NWS) & 1;
+          mbar_wait(BAR(EB_WFULL + st), ph);
+          if (lane == 0) mbar_arrive_cluster(map_to_cta(BAR(EB_PEERW + st), 0));
+          __syncwarp();
+        }
+      }
+    } else {
     auto get_w = [&]() {
+      if (CL2) {
+        st0 = st1 = it % NWS;
+        const uint32_t ph0 = (it / NWS) & 1;
+        it += 1;
+        mbar_wait(BAR(EB_WFULL + st0), ph0);
+        mbar_wait_cluster(BAR(EB_PEERW + st0), ph0);
+        w0 = umma_desc(sW + st0 * HALF_BYTES);
+        return;
+      }
       st0 = it % NWS; st1 = (it + 1) % NWS;
       const uint32_t ph0 = (it / NWS) & 1, ph1 = ((it + 1) / NWS) & 1;
       it += 2;
@@ -187,7 +261,11 @@ __global__ void __launch_bounds__(E_THREADS, 1) k_edge5(const EdgeArgs a) {
       w0 = umma_desc(sW + st0 * HALF_BYTES);
       w1 = umma_desc(sW + st1 * HALF_BYTES);
     };
-    for (int tile = blockIdx.x; tile < a.num_tiles; tile += grid, tl++) {
+    auto COMMIT = [&](int i) {
+      if (CL2) tc_commit2(BAR(i));
+      else tc_commit(BAR(i));
+    };
+    for (int tile = blockIdx.x; TILE_OK(tile); tile += grid, tl++) {
       const uint32_t st = tl & 1, uph = (tl >> 1) & 1;
       const uint64_t adesc = umma_desc(base + E_OFF_A + st * BLK_BYTES);
       const uint32_t D = tmem + 128 * st;
@@ -195,57 +273,80 @@ __global__ void __launch_bounds__(E_THREADS, 1) k_edge5(const EdgeArgs a) {
       for (int b = 0; b < 9; b++) {
         EDBG(b);
         get_w();
-        const bool is_dn = (b == 3) | (b == 4) | (b == 7) | (b == 8);
-        const int hb = ((b == 0) | (b == 3) | (b == 5) | (b == 7)) ? 0 : 1;      // hidden buffer of an up / down block
+        const bool is_dn = IS_DN(b);
+        const int hb = HB_OF(b);      // hidden buffer of an up / down block
         const uint32_t Hd = hb ? HdB : HdA;
-        if (b == 0) mbar_wait(BAR(EB_AFULL + st), uph);                          // A tile of this pass
-        if (b == 2) mbar_wait(BAR(EB_ACCFREE + st), uph ^ 1);                    // accumulator drained (two tiles ago)
-        if (is_dn) mbar_wait(BAR(EB_HSREADY + hb), b >= 7 ? 1u : 0u);            // hidden chunk converted to bf16
+        if (CL2) {
+          if (b == 0) mbar_wait_cluster(BAR(EB_AFULL + st), uph);
+          if (b == B_FIRSTD) mbar_wait_cluster(BAR(EB_ACCFREE + st), uph ^ 1);
+          if (is_dn) mbar_wait_cluster(BAR(EB_HSREADY + hb), b >= 7 ? 1u : 0u);
+        } else {
+          if (b == 0) mbar_wait(BAR(EB_AFULL + st), uph);                          // A tile of this pass
+          if (b == B_FIRSTD) mbar_wait(BAR(EB_ACCFREE + st), uph ^ 1);                    // accumulator drained (two tiles ago)
+          if (is_dn) mbar_wait(BAR(EB_HSREADY + hb), b >= 7 ? 1u : 0u);            // hidden chunk converted to bf16
+        }
         tc_fence_after();
         if (elect_one()) {
-          if (is_dn) {
-            issue_ts(D, Hd, w0, w1, true);                                       // D += relu(.)[chunk] W2_c
-          } else if (b == 2) {
-            issue_ss(D, adesc, w0, w1, false);                                   // GNBlock GEMM: first write of D
-          } else {
-            issue_ss(Hd, adesc, w0, w1, false);                                  // FFN up-projection chunk
-            tc_commit(BAR(EB_HIDFULL + hb));
+          if (is_dn) {                                                             // D += relu(.)[chunk] W2_c
+            if (CL2) issue_ts2(D, Hd, w0, b != B_FIRSTD);
+            else issue_ts(D, Hd, w0, w1, b != B_FIRSTD);
+          } else if (b == B_BLK) {                                                 // GNBlock GEMM
+            if (CL2) issue_ss2(D, adesc, w0, b != B_FIRSTD);
+            else issue_ss(D, adesc, w0, w1, b != B_FIRSTD);
+          } else {                                                                 // FFN up-projection chunk
+            if (CL2) issue_ss2(Hd, adesc, w0, false);
+            else issue_ss(Hd, adesc, w0, w1, false);
+            COMMIT(EB_HIDFULL + hb);
           }
-          if (b == 6) tc_commit(BAR(EB_AEMPTY + st));                            // last read of the A tile
-          if (b == 8) tc_commit(BAR(EB_OUTDONE + st));                           // accumulator complete
-          tc_commit(BAR(EB_WEMPTY + st0));
-          tc_commit(BAR(EB_WEMPTY + st1));
+          if (b == 6) COMMIT(EB_AEMPTY + st);                                      // last read of the A tile
+          if (b == 8) COMMIT(EB_OUTDONE + st);                                     // accumulator complete
+          COMMIT(EB_WEMPTY + st0);
+          if (!CL2) COMMIT(EB_WEMPTY + st1);
         }
         __syncwarp();
       }
       EDBG(9);
     }
-  } else if (warp < 4) {
+    }
+  } else if (warp >= 8) {
     // ===================================================== DRAIN warps (TMEM lane quadrant = warp)
-    const uint32_t lane_base = ((uint32_t)(warp * 32)) << 16;
+    const int dq = warp - 8;                 // TMEM lane quadrant (== warp % 4)
+    const uint32_t lane_base = ((uint32_t)(dq * 32)) << 16;
     uint32_t tl = 0;
-    auto convert = [&](uint32_t Hd, int c) {
-      // TMEM fp32 -> +b1 -> relu -> bf16 pairs -> TMEM, in place (columns [16j,16j+16) were read in iteration <= j)
+    // TMEM fp32 -> +b1 -> relu -> bf16 pairs -> TMEM, in place.  TMEM loads queue behind the running MMAs (several hundred
+    // cycles each under load), so two 32-column loads are kept in flight; the store of columns [16j,16j+16) only
+    // overwrites columns whose load has completed.
+    auto cvt32 = [&](const uint32_t (&v)[32], const float* bias32, uint32_t dst) {
+      uint32_t p[16];
+      const float4* bb = reinterpret_cast<const float4*>(bias32);
 #pragma unroll
-      for (int j = 0; j < 4; j++) {
-        uint32_t v[32], p[16];
-        TC_LD32(Hd + lane_base + 32 * j, v);
-        tc_wait_ld();
-        const float4* bb = reinterpret_cast<const float4*>(sB1 + c * 128 + j * 32);
-#pragma unroll
-        for (int t = 0; t < 8; t++) {
-          const float4 b = bb[t];
-          const float2 lo = __fadd2_rn(make_float2(__uint_as_float(v[4 * t]), __uint_as_float(v[4 * t + 1])), make_float2(b.x, b.y));
-          const float2 hi = __fadd2_rn(make_float2(__uint_as_float(v[4 * t + 2]), __uint_as_float(v[4 * t + 3])), make_float2(b.z, b.w));
-          p[2 * t] = pack_bf16_relu(lo.x, lo.y);
-          p[2 * t + 1] = pack_bf16_relu(hi.x, hi.y);
-        }
-        TC_ST16(Hd + lane_base + 16 * j, p);
+      for (int t = 0; t < 8; t++) {
+        const float4 b = bb[t];
+        const float2 lo = __fadd2_rn(make_float2(__uint_as_float(v[4 * t]), __uint_as_float(v[4 * t + 1])), make_float2(b.x, b.y));
+        const float2 hi = __fadd2_rn(make_float2(__uint_as_float(v[4 * t + 2]), __uint_as_float(v[4 * t + 3])), make_float2(b.z, b.w));
+        p[2 * t] = pack_bf16_relu(lo.x, lo.y);
+        p[2 * t + 1] = pack_bf16_relu(hi.x, hi.y);
       }
+      TC_ST16(dst, p);
+    };
+    auto convert = [&](uint32_t Hd, int c) {
+      uint32_t va[32], vb[32];
+      const float* bias = sB1 + c * 128;
+      const uint32_t t0 = Hd + lane_base;
+      TC_LD32(t0, va);
+      TC_LD32(t0 + 32, vb);
+      tc_wait_ld();
+      cvt32(va, bias, t0);
+      TC_LD32(t0 + 64, va);
+      cvt32(vb, bias + 32, t0 + 16);
+      TC_LD32(t0 + 96, vb);
+      tc_wait_ld();
+      cvt32(va, bias + 64, t0 + 32);
+      cvt32(vb, bias + 96, t0 + 48);
       tc_wait_st();
       tc_fence_before();
     };
-    for (int tile = blockIdx.x; tile < a.num_tiles; tile += grid, tl++) {
+    for (int tile = blockIdx.x; TILE_OK(tile); tile += grid, tl++) {
       const uint32_t st = tl & 1, uph = (tl >> 1) & 1;
       EDBG(0);
 #pragma unroll 1
@@ -254,7 +355,7 @@ __global__ void __launch_bounds__(E_THREADS, 1) k_edge5(const EdgeArgs a) {
         EDBG(1 + 2 * c);
         tc_fence_after();
         convert((c & 1) ? HdB : HdA, c);
-        mbar_arrive(BAR(EB_HSREADY + (c & 1)));
+        ARRIVE_LEADER(EB_HSREADY + (c & 1));
         EDBG(2 + 2 * c);
       }
       // ---------------- finished accumulator -> staging tile (row r = this thread; 4 column groups of 32 fp32)
@@ -264,29 +365,36 @@ __global__ void __launch_bounds__(E_THREADS, 1) k_edge5(const EdgeArgs a) {
       mbar_wait(BAR(EB_STGEMPTY), (tl & 1) ^ 1);
       EDBG(10);
       const uint32_t D = tmem + 128 * st;
-      const int r = warp * 32 + lane;
+      const int r = dq * 32 + lane;
       uint8_t* srow = sm + E_OFF_STG + r * 128;
+      {
+        uint32_t va[32], vb[32];
+        auto put = [&](const uint32_t (&v)[32], int g) {
 #pragma unroll
-      for (int g = 0; g < 4; g++) {
-        uint32_t v[32];
-        TC_LD32(D + lane_base + 32 * g, v);
+          for (int j = 0; j < 8; j++)
+            *reinterpret_cast<uint4*>(srow + g * 16384 + ((j ^ (r & 7)) << 4)) = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        };
+        TC_LD32(D + lane_base, va);
+        TC_LD32(D + lane_base + 32, vb);
         tc_wait_ld();
-        if (g == 3) {   // TMEM fully read: the accumulator goes back to the MMA warp
-          tc_fence_before();
-          mbar_arrive(BAR(EB_ACCFREE + st));
-        }
-#pragma unroll
-        for (int j = 0; j < 8; j++)
-          *reinterpret_cast<uint4*>(srow + g * 16384 + ((j ^ (r & 7)) << 4)) = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        put(va, 0);
+        TC_LD32(D + lane_base + 64, va);
+        put(vb, 1);
+        TC_LD32(D + lane_base + 96, vb);
+        tc_wait_ld();
+        tc_fence_before();          // TMEM fully read: the accumulator goes back to the MMA warp
+        ARRIVE_LEADER(EB_ACCFREE + st);
+        put(va, 2);
+        put(vb, 3);
       }
-      mbar_arrive(BAR(EB_STGFULL));
+      ARRIVE_LOCAL(EB_STGFULL);
       EDBG(11);
     }
-  } else if ((warp & 2) == 0) {
-    // ===================================================== LN warps (4, 5, 8, 9), one tile ahead of the MMAs
+  } else if (warp < 4) {
+    // ===================================================== LN warps (0-3), one tile ahead of the MMAs
     // 8 lanes per row: lane (rr = lane >> 3, l8 = lane & 7) holds columns 4 l8 + 32 j .. +3 (j = 0..3) of row i0 + rr, so
     // one load instruction covers 4 rows x 128 contiguous bytes and a row statistic needs 3 shuffle levels instead of 5.
-    const int q = (warp & 1) + ((warp >> 3) << 1);
+    const int q = warp & 3;
     const int rr = lane >> 3, l8 = lane & 7;
     const float* xbase = a.x + 4 * l8;
     // swizzled A operand, element (row 32q + i, k = 4 l8 + 32 j): byte (k >> 6) * 16 KB + row * 128 + ((chunk ^ (row & 7)) << 4) + (l8 & 1) * 8
@@ -298,7 +406,7 @@ __global__ void __launch_bounds__(E_THREADS, 1) k_edge5(const EdgeArgs a) {
     const float e_add = a.eps_mode == GNB_EPS_SQRT_VAR_EPS2 ? a.eps * a.eps : (a.eps_mode == GNB_EPS_STD_PLUS_EPS ? 0.f : a.eps);
     const float e_plus = a.eps_mode == GNB_EPS_STD_PLUS_EPS ? a.eps : 0.f;
     uint32_t tl = 0;
-    for (int tile = blockIdx.x; tile < a.num_tiles; tile += grid, tl++) {
+    for (int tile = blockIdx.x; TILE_OK(tile); tile += grid, tl++) {
       const uint32_t stage = tl & 1, aph = (tl >> 1) & 1;
       const int64_t row0 = (int64_t)tile * TM + 32 * q;
       const int64_t left = a.R - row0;
@@ -378,25 +486,33 @@ __global__ void __launch_bounds__(E_THREADS, 1) k_edge5(const EdgeArgs a) {
       __syncwarp();
       {
         float4 acc = f4zero();
-#pragma unroll 4
-        for (int i = 0; i < 32; i++) {
-          const uint2 v = *reinterpret_cast<const uint2*>(A + p_lane + i * 128 + ((p_chunk ^ (uint32_t)(i & 7)) << 4));
-          acc = add4(acc, make_float4(__uint_as_float(v.x << 16), __uint_as_float(v.x & 0xffff0000u), __uint_as_float(v.y << 16),
-                                      __uint_as_float(v.y & 0xffff0000u)));
-          if ((endmask >> i) & 1u) {
-            *(reinterpret_cast<float4*>(a.Epart + (size_t)pid * H) + lane) = acc;
-            acc = f4zero();
-            pid++;
+#pragma unroll 1
+        for (int i0 = 0; i0 < 32; i0 += 16) {
+          uint2 v[16];     // 16 independent shared-memory loads in flight, then the ordered sums
+#pragma unroll
+          for (int u = 0; u < 16; u++) {
+            const int i = i0 + u;
+            v[u] = *reinterpret_cast<const uint2*>(A + p_lane + i * 128 + ((p_chunk ^ (uint32_t)(i & 7)) << 4));
+          }
+#pragma unroll
+          for (int u = 0; u < 16; u++) {
+            const int i = i0 + u;
+            acc = add4(acc, make_float4(__uint_as_float(v[u].x << 16), __uint_as_float(v[u].x & 0xffff0000u),
+                                        __uint_as_float(v[u].y << 16), __uint_as_float(v[u].y & 0xffff0000u)));
+            const bool fl = (endmask >> i) & 1u;
+            if (fl) *(reinterpret_cast<float4*>(a.Epart + (size_t)pid * H) + lane) = acc;
+            acc.x = fl ? 0.f : acc.x; acc.y = fl ? 0.f : acc.y; acc.z = fl ? 0.f : acc.z; acc.w = fl ? 0.f : acc.w;
+            pid += fl ? 1 : 0;
           }
         }
       }
       fence_async_smem();
-      mbar_arrive(BAR(EB_AFULL + stage));
+      ARRIVE_LEADER(EB_AFULL + stage);
       EDBG(6);
     }
   } else {
-    // ===================================================== OUT warps (6, 7, 10, 11), one tile behind the MMAs
-    const int q = (warp & 1) + ((warp >> 3) << 1);
+    // ===================================================== OUT warps (4-7), one tile behind the MMAs
+    const int q = warp & 3;
     const float4 b2v = *reinterpret_cast<const float4*>(sB2 + 4 * lane);
     const float* xbase = a.x + 4 * lane;
     const float* base1 = a.add1 + 4 * lane;
@@ -404,7 +520,7 @@ __global__ void __launch_bounds__(E_THREADS, 1) k_edge5(const EdgeArgs a) {
     const uint32_t s_lane = (uint32_t)(E_OFF_STG + (lane >> 3) * 16384 + (32 * q) * 128);
     const uint32_t s_chunk = (uint32_t)(lane & 7);
     uint32_t tl = 0;
-    for (int tile = blockIdx.x; tile < a.num_tiles; tile += grid, tl++) {
+    for (int tile = blockIdx.x; TILE_OK(tile); tile += grid, tl++) {
       const int64_t row0 = (int64_t)tile * TM + 32 * q;
       const int64_t left = a.R - row0;
       const int rows = left < 0 ? 0 : (left > 32 ? 32 : (int)left);
@@ -454,13 +570,18 @@ __global__ void __launch_bounds__(E_THREADS, 1) k_edge5(const EdgeArgs a) {
           if (i0 + 4 < 32) issue1(u, i + 4);   // refill this slot with the same row of the next group
         }
       }
-      mbar_arrive(BAR(EB_STGEMPTY));
+      ARRIVE_LOCAL(EB_STGEMPTY);
       EDBG(2);
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 12) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+  if (CL2) cluster_sync_all();      // the peer may still be reading this CTA's shared / tensor memory
+  if (warp == 12) {
+    if (CL2) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+  }
+#undef TILE_OK
 }
 
 }  // namespace
@@ -468,13 +589,30 @@ __global__ void __launch_bounds__(E_THREADS, 1) k_edge5(const EdgeArgs a) {
 int launch_edge5(gnb_ctx* ctx, const EdgeArgs& a, const char* name, double flops, double bytes) {
   if (a.num_tiles <= 0) return GNB_OK;
   static bool attr_set = false;
+  static int use_cl2 = 1;
   if (!attr_set) {
-    GNB_CUDA(cudaFuncSetAttribute(k_edge5, cudaFuncAttributeMaxDynamicSharedMemorySize, E_SMEM));
+    GNB_CUDA(cudaFuncSetAttribute(k_edge5<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, E_SMEM));
+    GNB_CUDA(cudaFuncSetAttribute(k_edge5<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, E_SMEM));
+    const char* e = getenv("GNB_EDGE_CTA_PAIR");      // 0: one CTA per tile stream (cta_group::1)
+    if (e) use_cl2 = atoi(e);
     attr_set = true;
   }
-  const int grid = a.num_tiles < ctx->sm_count ? a.num_tiles : ctx->sm_count;
   Launch L(ctx, name, bytes, flops);
-  k_edge5<<<grid, E_THREADS, E_SMEM, ctx->stream>>>(a);
+  if (use_cl2 && ctx->sm_count >= 2) {
+    const int pairs = (a.num_tiles + 1) / 2;
+    const int max_clusters = ctx->sm_count / 2;
+    const int grid = 2 * (pairs < max_clusters ? pairs : max_clusters);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(E_THREADS); cfg.dynamicSmemBytes = E_SMEM; cfg.stream = ctx->stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    GNB_CUDA(cudaLaunchKernelEx(&cfg, k_edge5<true>, a));
+  } else {
+    const int grid = a.num_tiles < ctx->sm_count ? a.num_tiles : ctx->sm_count;
+    k_edge5<false><<<grid, E_THREADS, E_SMEM, ctx->stream>>>(a);
+  }
   GNB_CUDA(cudaGetLastError());
   return GNB_OK;
 }

@@ -166,4 +166,80 @@ static __device__ __forceinline__ void issue_ts(uint32_t d_tmem, uint32_t a_tmem
   for (int ks = 0; ks < 4; ks++) mma_ts(d_tmem, a_tmem + 32 + 8 * ks, w1 + 2 * ks, IDESC, 1u);
 }
 
+
+// ------------------------------------------------------------------ 2-CTA (cta_group::2) helpers
+static __device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+static __device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of the same shared-memory offset in CTA `rank` of the cluster
+static __device__ __forceinline__ uint32_t map_to_cta(uint32_t local_addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(rank));
+  return r;
+}
+static __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  // default .release.cta like CUTLASS' ClusterBarrier::arrive: what is published across the pair is tensor memory (ordered by
+  // tcgen05.fence) and shared memory consumed through the async proxy (ordered by fence.proxy.async); a cluster-scope release
+  // would add a full memory barrier (~1.2k cycles per arrive, measured)
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// wait on a barrier that receives arrivals from the peer CTA (cluster-scope acquire)
+static __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
+  uint32_t ok = 0;
+  for (uint32_t spin = 0; !ok; spin++) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (spin > (1u << 24)) __trap();
+  }
+}
+// arrive::one on the barrier at this offset in both CTAs of the pair once all prior tcgen05 ops of this thread completed
+static __device__ __forceinline__ void tc_commit2(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+               "h"((uint16_t)3)
+               : "memory");
+}
+static __device__ __forceinline__ void mma_ss2(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+      : "memory");
+}
+static __device__ __forceinline__ void mma_ts2(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accum)
+      : "memory");
+}
+// kind::f16 instruction descriptor of the pair MMA: M = 256 (128 rows per CTA), N = 128
+constexpr uint32_t IDESC2 = (1u << 4) | (1u << 7) | (1u << 10) | ((128u >> 3) << 17) | ((256u >> 4) << 24);
+// one 256x128x128 block of the CTA pair: A = each CTA's own 128-row tile (two 64-wide K halves 16 KB apart), B = each CTA's
+// 64-row N half (two K halves 8 KB apart inside a 16 KB ring stage)
+static __device__ __forceinline__ void issue_ss2(uint32_t d_tmem, uint64_t adesc, uint64_t w, bool accumulate) {
+#pragma unroll
+  for (int ks = 0; ks < 4; ks++) mma_ss2(d_tmem, adesc + 2 * ks, w + 2 * ks, IDESC2, (accumulate || ks > 0) ? 1u : 0u);
+#pragma unroll
+  for (int ks = 0; ks < 4; ks++) mma_ss2(d_tmem, adesc + (KB_BYTES >> 4) + 2 * ks, w + (8192 >> 4) + 2 * ks, IDESC2, 1u);
+}
+static __device__ __forceinline__ void issue_ts2(uint32_t d_tmem, uint32_t a_tmem, uint64_t w, bool accumulate) {
+#pragma unroll
+  for (int ks = 0; ks < 4; ks++) mma_ts2(d_tmem, a_tmem + 8 * ks, w + 2 * ks, IDESC2, (accumulate || ks > 0) ? 1u : 0u);
+#pragma unroll
+  for (int ks = 0; ks < 4; ks++) mma_ts2(d_tmem, a_tmem + 32 + 8 * ks, w + (8192 >> 4) + 2 * ks, IDESC2, 1u);
+}
+
 }  // namespace tcx

@@ -23,6 +23,6 @@ def show(name, warps, slots, labels):
     dd = np.diff(d[:, :, slots], axis=2).mean(axis=(0, 1))
     print("  mean deltas:", " ".join("%s=%.0f" % (l, v) for l, v in zip(labels[1:], dd)))
 show("MMA warp (start of each block)", [12], list(range(10)), ["up0", "up1", "blk", "dn0", "dn1", "up2", "up3", "dn2", "dn3", "end"])
-show("DRAIN warps", [0, 1, 2, 3], list(range(12)), ["start", "hf0", "hs0", "hf1", "hs1", "hf2", "hs2", "hf3", "hs3", "outdone", "stgempty", "stgfull"])
-show("LN warps", [4, 5, 8, 9], list(range(7)), ["start", "aempty", "g0", "g1", "g2", "g3", "arrive"])
-show("OUT warps", [6, 7, 10, 11], list(range(3)), ["start", "stgfull", "done"])
+show("DRAIN warps", [8, 9, 10, 11], list(range(12)), ["start", "hf0", "hs0", "hf1", "hs1", "hf2", "hs2", "hf3", "hs3", "outdone", "stgempty", "stgfull"])
+show("LN warps", [0, 1, 2, 3], list(range(7)), ["start", "aempty", "g0", "g1", "g2", "g3", "arrive"])
+show("OUT warps", [4, 5, 6, 7], list(range(3)), ["start", "stgfull", "done"])
