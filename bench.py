@@ -249,7 +249,18 @@ def run_ours(args, rank, world, local_rank):
             peak = peaks["hbm"]
             ach = p["alg_bytes"] / p["launches"] / (per_ms * 1e-3) / 1e9
             roof = {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak}
-        roof.update({"traffic": None, "kernel": name, "launches_per_step": p["launches"] / args.steps,
+        # DRAM bytes (read + write) of one launch of this kernel, from the committed ncu --set full capture
+        # (profiles/r01_ncu_traffic.json; same workload, so it is a property of the kernel, not of this run)
+        traffic, tsrc = None, None
+        tp = os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")
+        if os.path.exists(tp) and args.config == "cfg4" and args.graphs == 4096:
+            tj = json.load(open(tp))
+            if name in tj["kernels"]:
+                traffic, tsrc = tj["kernels"][name]["traffic"], "profiles/r01_ncu_traffic.json"
+        roof.update({"traffic": traffic, "traffic_source": tsrc, "alg_bytes_per_launch": p["alg_bytes"] / p["launches"],
+                     "alg_flops_per_launch": p["alg_flops"] / p["launches"],
+                     "hbm_frac_of_kernel": p["alg_bytes"] / p["launches"] / (per_ms * 1e-3) / 1e9 / peaks["hbm"],
+                     "kernel": name, "launches_per_step": p["launches"] / args.steps,
                      "avg_launch_ms": per_ms, "share_of_step": p["ms"] / (ms * args.steps),
                      "peak_source": "of " + peaks["src"],
                      "kernel_tflops": p["alg_flops"] / p["launches"] / (per_ms * 1e-3) / 1e12})
