@@ -1,8 +1,11 @@
+#pragma unroll 4
+  for (int k = k0; k < k0 + KS; k += 4) {
 // Graph-level (B rows) stages of a GNCore with 128-wide features, fp32 CUDA cores.
 //
 // A batch has few graphs (B << N << E), so these stages are latency- not throughput-bound: a CTA owns
-// RT = 8 graphs and all output columns, keeps its rows in shared memory and streams the weights from L2
-// (512 CTAs -> one wave).  Two launches per GNCore replace ten small GEMM / segmented-sum launches:
+// RT = 8 graphs and all output columns, keeps its rows in shared memory and streams the weights from L2.
+// One launch per GNCore (k_graph_post, which also emits the per-graph rows of the next core; k_graph_pre only
+// runs in front of the first core of a chain) replaces ten small GEMM / segmented-sum launches:
 //   k_graph_pre :  P_ue = LN1(u) W_eu + c_e          per-graph row of the edge update   (src/edgefninput.jl:6)
 //                  P_un = LN1(u) W_nu + c_n          per-graph row of the node update   (src/nodefninput.jl:5)
 //   k_graph_post:  s_e = sum of the graph's node aggregates (== sum of its edges, src/graphfninput.jl:3)
@@ -89,20 +92,67 @@ __global__ void __launch_bounds__(128) k_graph_pre(const GraphPreArgs a) {
   }
 }
 
-__global__ void __launch_bounds__(128) k_graph_post(const GraphPostArgs a) {
-  __shared__ __align__(16) float xs[RT][H];       // u
-  __shared__ __align__(16) float xa[RT][H];       // LN1(u), later h_u
-  __shared__ __align__(16) float xb[RT][H];       // LN2(u)
-  __shared__ __align__(16) float se[RT][H];
-  __shared__ __align__(16) float sv[RT][H];       // gamma . sum v^, then the node -> graph sum of h_v
-  __shared__ __align__(16) float svg[RT][H];
-  __shared__ __align__(16) float hid[RT][4 * H];
-  const int n = threadIdx.x, warp = n >> 5, lane = n & 31;
+// K-slice of gemv_rows: acc[r] += sum_{k in [k0, k0 + KS)} xs[r][k] * W[k*ldw + n]     (xs rows have stride LD floats)
+template <int KS, int LD>
+__device__ __forceinline__ void gemv_slice(const float* xs, int k0, const float* __restrict__ W, int ldw, int n, float* acc) {
+#ifdef GNB_EXP_ROTATE
+  const int rot = (blockIdx.x * 4) % KS;
+#else
+  const int rot = 0;
+#endif
+#pragma unroll 4
+  for (int kk = 0; kk < KS; kk += 4) {
+    const int k = k0 + ((kk + rot) % KS);
+    const float w0 = __ldg(W + (size_t)(k + 0) * ldw + n), w1 = __ldg(W + (size_t)(k + 1) * ldw + n);
+    const float w2 = __ldg(W + (size_t)(k + 2) * ldw + n), w3 = __ldg(W + (size_t)(k + 3) * ldw + n);
+#pragma unroll
+    for (int r = 0; r < RT; r++) {
+      const float4 x = *reinterpret_cast<const float4*>(xs + r * LD + k);
+      acc[r] = fmaf(x.x, w0, acc[r]);
+      acc[r] = fmaf(x.y, w1, acc[r]);
+      acc[r] = fmaf(x.z, w2, acc[r]);
+      acc[r] = fmaf(x.w, w3, acc[r]);
+    }
+  }
+}
+
+// LayerNorm of row r held in xs[r][H] by one warp: out = gamma (x - mu) rstd + beta
+__device__ __forceinline__ void ln_row(const float* xs, float* out, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                       float eps, int mode, int lane) {
+  const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + lane);
+  const float4 b = __ldg(reinterpret_cast<const float4*>(beta) + lane);
+  const float4 v = *reinterpret_cast<const float4*>(xs + 4 * lane);
+  float s = (v.x + v.y) + (v.z + v.w);
+#pragma unroll
+  for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  const float mu = s * (1.0f / H);
+  const float dx = v.x - mu, dy = v.y - mu, dz = v.z - mu, dw = v.w - mu;
+  float q = (dx * dx + dy * dy) + (dz * dz + dw * dw);
+#pragma unroll
+  for (int o = 16; o; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+  const float rs = ln_rstd(q * (1.0f / H), eps, mode);
+  *reinterpret_cast<float4*>(out + 4 * lane) = make_float4(dx * rs * g.x + b.x, dy * rs * g.y + b.y, dz * rs * g.z + b.z, dw * rs * g.w + b.w);
+}
+
+// 512 threads: thread (n = tid & 127, ks = tid >> 7).  The stages are latency-bound chains of L2 weight loads, so every GEMV is
+// split 4 ways along K (partials combined in a fixed order through shared memory: deterministic) and the node sums 4 ways over
+// the graphs of the CTA.
+constexpr int GP_THREADS = 512;
+__global__ void __launch_bounds__(GP_THREADS) k_graph_post(const GraphPostArgs a) {
+  __shared__ __align__(16) float xs[RT][H];        // u
+  __shared__ __align__(16) float cat[RT][3 * H];   // [s_e | s_v | LN1(u)]   (s_v slot first holds gamma . sum v^)
+  __shared__ __align__(16) float xb[RT][H];        // LN2(u); later y_u, LN1'(y_u)
+  __shared__ __align__(16) float svg[RT][H];       // sum of the node addends
+  __shared__ __align__(16) float hid[RT][4 * H];   // FFN hidden; before that the scratch of the K-split reductions
+  float(*red)[RT][H] = reinterpret_cast<float(*)[RT][H]>(&hid[0][0]);      // [4][RT][H] == sizeof(hid)
+  const int tid = threadIdx.x, n = tid & (H - 1), ks = tid >> 7, warp = tid >> 5, lane = tid & 31;
   const int64_t g0 = (int64_t)blockIdx.x * RT;
-  for (int r = 0; r < RT; r++) {
+  // ---- ordered sums over the graph's nodes (rows of a graph are contiguous): deterministic, no atomics; group ks owns
+  // graphs 2 ks, 2 ks + 1 of the CTA
+#pragma unroll 1
+  for (int r = 2 * ks; r < 2 * ks + 2; r++) {
     const int64_t g = g0 + r < a.B ? g0 + r : a.B - 1;
     xs[r][n] = a.xg[(size_t)g * H + n];
-    // ordered sums over the graph's nodes (rows of a graph are contiguous): deterministic, no atomics
     const int v0 = a.graph_node_ptr[g], v1 = a.graph_node_ptr[g + 1];
     float s0 = 0.f;
     int v = v0;
@@ -114,61 +164,102 @@ __global__ void __launch_bounds__(128) k_graph_post(const GraphPostArgs a) {
       for (int j = 0; j < 16; j++) s0 += e[j];
     }
     for (; v < v1; v++) s0 += a.agg[(size_t)v * H + n];
-    se[r][n] = s0;
+    cat[r][n] = s0;
     // partial rows of the node kernel: sum of v^ (scaled by the LN1 node scale, which the packed weights carry) and of the addends
     const int p0 = a.graph_npart_ptr[g], p1 = a.graph_npart_ptr[g + 1];
     float sh = 0.f, sg = 0.f;
     for (int p = p0; p < p1; p++) { sh += a.Vpart[(size_t)p * H + n]; sg += a.Npart[(size_t)p * H + n]; }
-    sv[r][n] = sh * a.g1n[n];
+    cat[r][H + n] = sh * a.g1n[n];
     svg[r][n] = sg;
   }
   __syncthreads();
-  ln_rows(xs, xa, a.g1, a.b1ln, a.eps1, a.eps_mode1, warp, lane);
-  ln_rows(xs, xb, a.g2, a.b2ln, a.eps2, a.eps_mode2, warp, lane);
-  __syncthreads();
-  // s_v = W_nv (gamma . sum v^) + sum of the addends
+  if (warp < RT) ln_row(xs[warp], &cat[warp][2 * H], a.g1, a.b1ln, a.eps1, a.eps_mode1, lane);
+  else ln_row(xs[warp - RT], xb[warp - RT], a.g2, a.b2ln, a.eps2, a.eps_mode2, lane);
+  // ---- s_v = W_nv (gamma . sum v^) + sum of the addends
   {
     float t[RT];
 #pragma unroll
-    for (int r = 0; r < RT; r++) t[r] = svg[r][n];
-    gemv_rows<H>(sv, a.Wnv, H, n, t);
-    __syncthreads();
+    for (int r = 0; r < RT; r++) t[r] = 0.f;
+    gemv_slice<H / 4, 3 * H>(&cat[0][H], ks * (H / 4), a.Wnv, H, n, t);
 #pragma unroll
-    for (int r = 0; r < RT; r++) sv[r][n] = t[r];
+    for (int r = 0; r < RT; r++) red[ks][r][n] = t[r];
+    __syncthreads();      // also publishes the LayerNorm rows
+    if (ks == 0) {
+#pragma unroll
+      for (int r = 0; r < RT; r++) cat[r][H + n] = svg[r][n] + (((red[0][r][n] + red[1][r][n]) + red[2][r][n]) + red[3][r][n]);
+    }
     __syncthreads();
   }
-  // h_u = W_g [s_e ; s_v ; LN1(u)] + b_g
+  // ---- h_u = W_g [s_e ; s_v ; LN1(u)] + b_g          (K = 3H, slice = 96)
   float hu[RT];
   {
+    float t[RT];
+#pragma unroll
+    for (int r = 0; r < RT; r++) t[r] = 0.f;
+    gemv_slice<3 * H / 4, 3 * H>(&cat[0][0], ks * (3 * H / 4), a.Wg, H, n, t);
+#pragma unroll
+    for (int r = 0; r < RT; r++) red[ks][r][n] = t[r];
+    __syncthreads();
     const float bg = a.bg[n];
 #pragma unroll
-    for (int r = 0; r < RT; r++) hu[r] = bg;
-    gemv_rows<H>(se, a.Wg, H, n, hu);
-    gemv_rows<H>(sv, a.Wg + (size_t)H * H, H, n, hu);
-    gemv_rows<H>(xa, a.Wg + (size_t)2 * H * H, H, n, hu);
+    for (int r = 0; r < RT; r++) hu[r] = bg + (((red[0][r][n] + red[1][r][n]) + red[2][r][n]) + red[3][r][n]);
+    __syncthreads();      // red (== hid) is rewritten below
   }
-  // FFN hidden: relu(W1 LN2(u) + b1), 4H wide: thread n owns hidden units n, n+H, n+2H, n+3H
-#pragma unroll 1
-  for (int c = 0; c < 4; c++) {
+  // ---- FFN hidden: relu(W1 LN2(u) + b1), 4H wide: thread (n, ks) owns hidden unit ks H + n
+  {
     float hc[RT];
-    const float b1 = a.b1[c * H + n];
+    const float b1 = a.b1[ks * H + n];
 #pragma unroll
     for (int r = 0; r < RT; r++) hc[r] = b1;
-    gemv_rows<H>(xb, a.W1 + c * H, 4 * H, n, hc);
+    gemv_slice<H, H>(&xb[0][0], 0, a.W1 + ks * H, 4 * H, n, hc);
 #pragma unroll
-    for (int r = 0; r < RT; r++) hid[r][c * H + n] = fmaxf(hc[r], 0.f);
+    for (int r = 0; r < RT; r++) hid[r][ks * H + n] = fmaxf(hc[r], 0.f);
   }
   __syncthreads();
-  float f[RT];
   {
-    const float b2 = a.b2[n];
+    float t[RT];
 #pragma unroll
-    for (int r = 0; r < RT; r++) f[r] = b2;
-    gemv_rows<4 * H>(hid, a.W2, H, n, f);
+    for (int r = 0; r < RT; r++) t[r] = 0.f;
+    gemv_slice<H, 4 * H>(&hid[0][0], ks * H, a.W2, H, n, t);
+    float(*red2)[RT][H] = reinterpret_cast<float(*)[RT][H]>(&cat[0][0]);      // [3][RT][H] == sizeof(cat): slices 1..3
+    if (ks > 0) {
+#pragma unroll
+      for (int r = 0; r < RT; r++) red2[ks - 1][r][n] = t[r];
+    }
+    __syncthreads();
+    if (ks == 0) {
+      const float b2 = a.b2[n];
+#pragma unroll
+      for (int r = 0; r < RT; r++) {
+        const float f = b2 + (((t[r] + red2[0][r][n]) + red2[1][r][n]) + red2[2][r][n]);
+        const float y = (xs[r][n] + hu[r]) + f;
+        if (g0 + r < a.B) a.yg[(size_t)(g0 + r) * H + n] = y;
+        xb[r][n] = y;
+      }
+    }
   }
+  if (a.next_Pue == nullptr) return;      // uniform
+  // ---- per-graph rows of the NEXT core (k_graph_pre fused): P_ue = LN1'(y_u) W_eu' + c_e', P_un likewise
+  __syncthreads();
+  if (warp < RT) ln_row(xb[warp], xs[warp], a.next_gamma, a.next_beta, a.next_eps, a.next_eps_mode, lane);
+  __syncthreads();
+  {
+    float te[RT];
 #pragma unroll
-  for (int r = 0; r < RT; r++) {
-    if (g0 + r < a.B) a.yg[(size_t)(g0 + r) * H + n] = (xs[r][n] + hu[r]) + f[r];
+    for (int r = 0; r < RT; r++) te[r] = 0.f;
+    // groups 0, 1: the two K halves of P_ue; groups 2, 3: of P_un
+    const float* W = ks < 2 ? a.next_Weu : a.next_Wnu;
+    gemv_slice<H / 2, H>(&xs[0][0], (ks & 1) * (H / 2), W, H, n, te);
+#pragma unroll
+    for (int r = 0; r < RT; r++) red[ks][r][n] = te[r];
+    __syncthreads();
+    if ((ks & 1) == 0) {
+      const float c = ks == 0 ? a.next_ce[n] : a.next_cn[n];
+      float* out = ks == 0 ? a.next_Pue : a.next_Pun;
+#pragma unroll
+      for (int r = 0; r < RT; r++)
+        if (g0 + r < a.B) out[(size_t)(g0 + r) * H + n] = c + (red[ks][r][n] + red[ks + 1][r][n]);
+    }
   }
 }
 
@@ -185,7 +276,7 @@ int launch_graph_pre(gnb_ctx* ctx, const GraphPreArgs& a) {
 int launch_graph_post(gnb_ctx* ctx, const GraphPostArgs& a, int64_t N) {
   if (a.B <= 0) return GNB_OK;
   Launch L(ctx, "graph_post", 8.0 * N * H + 8.0 * a.B * H + 4.0 * 11 * H * H, 22.0 * a.B * H * H);
-  k_graph_post<<<ceil_div(a.B, RT), 128, 0, ctx->stream>>>(a);
+  k_graph_post<<<ceil_div(a.B, RT), GP_THREADS, 0, ctx->stream>>>(a);
   GNB_CUDA(cudaGetLastError());
   return GNB_OK;
 }

@@ -30,6 +30,10 @@ struct GraphPostArgs {
   const float *Wg, *bg;  // graph Dense (3H -> H), k-major
   const float *W1, *b1, *W2, *b2;   // graph FFN
   float* yg;             // out [B][128]
+  // optional: the per-graph rows of the NEXT core (k_graph_pre fused into this launch); next_Pue == nullptr: none
+  const float *next_gamma, *next_beta; float next_eps; int next_eps_mode;
+  const float *next_Weu, *next_Wnu, *next_ce, *next_cn;
+  float *next_Pue, *next_Pun;
 };
 
 int launch_graph_pre(gnb_ctx* ctx, const GraphPreArgs& a);

@@ -708,8 +708,21 @@ static int forward_device(gnb_ctx* ctx, const gnb_model* m, const gnb_graph* g, 
     pp[i].n = arena_ptr<float>(ctx->arena, (size_t)g->N * mn, &rc);
     pp[i].g = arena_ptr<float>(ctx->arena, (size_t)g->B * mg, &rc);
   }
+  // per-graph rows of consecutive tensor-path cores are chained (produced by the previous core's tail kernel): two
+  // buffer pairs that survive the per-layer arena rewind
+  TcPreRows pre[2];
+  bool chain = false;
+  for (int i = 0; i + 1 < L; i++)
+    chain |= precision != GNB_PREC_FP32 && m->layers[i].kind == GNB_LAYER_CORE && m->layers[i].tc && m->layers[i + 1].kind == GNB_LAYER_CORE && m->layers[i + 1].tc;
+  if (chain) {
+    for (int i = 0; i < 2; i++) {
+      pre[i].Pue = arena_ptr<float>(ctx->arena, (size_t)g->B * 128, &rc);
+      pre[i].Pun = arena_ptr<float>(ctx->arena, (size_t)g->B * 128, &rc);
+    }
+  }
   if (rc != GNB_OK) return rc;
   Feat x{ef, nf, gf};
+  bool have_pre = false;      // pre[li & 1] holds the rows of layer li
   ArenaMark mark = arena_mark(ctx->arena);
   for (int li = 0; li < L; li++) {
     const LayerW& w = m->layers[li];
@@ -724,6 +737,7 @@ static int forward_device(gnb_ctx* ctx, const gnb_model* m, const gnb_graph* g, 
       if (precision != GNB_PREC_FP32 && block_wide_ok(w)) GNB_TRY(run_block_wide(ctx, g, w, x, y));
       else if (precision != GNB_PREC_FP32 && block_narrow_ok(w)) GNB_TRY(run_block_narrow(ctx, g, w, x, y));
       else GNB_TRY(run_block_fp32(ctx, g, w.blk, nullptr, x, y));
+      have_pre = false;
     } else {
       bool use_tc = (precision != GNB_PREC_FP32) && w.tc != nullptr;
       if (precision == GNB_PREC_BF16 && !w.tc) {
@@ -731,8 +745,18 @@ static int forward_device(gnb_ctx* ctx, const gnb_model* m, const gnb_graph* g, 
                       "(use GNB_PREC_AUTO or GNB_PREC_FP32)", li, w.blk.in_e, w.blk.in_n, w.blk.in_g);
         return GNB_ERR_UNSUPPORTED;
       }
-      if (use_tc) GNB_TRY(tc_core_forward(ctx, g, w.tc, w.blk, w.ffn, w.ln1, w.ln2, x.e, x.n, x.g, y.e, y.n, y.g));
-      else GNB_TRY(run_core_fp32(ctx, g, w, x, y));
+      if (use_tc) {
+        TcNextCore next;
+        if (chain && li + 1 < L && m->layers[li + 1].kind == GNB_LAYER_CORE && m->layers[li + 1].tc) {
+          next.pk = m->layers[li + 1].tc; next.blk = &m->layers[li + 1].blk; next.ln1 = m->layers[li + 1].ln1;
+        }
+        GNB_TRY(tc_core_forward(ctx, g, w.tc, w.blk, w.ffn, w.ln1, w.ln2, x.e, x.n, x.g, y.e, y.n, y.g,
+                                have_pre ? pre[li & 1] : TcPreRows(), next, next.pk ? pre[(li + 1) & 1] : TcPreRows()));
+        have_pre = next.pk != nullptr;
+      } else {
+        GNB_TRY(run_core_fp32(ctx, g, w, x, y));
+        have_pre = false;
+      }
     }
     x = Feat{y.e, y.n, y.g};
   }

@@ -458,12 +458,13 @@ static int launch_proj(gnb_ctx* ctx, const ProjArgs& a, const char* name, double
 
 int tc_core_forward(gnb_ctx* ctx, const gnb_graph* g, const TcCorePack* pk, const gnb_block_params& blk,
                     const gnb_ffn_params* ffn, const gnb_ln_params* ln1, const gnb_ln_params* ln2, const float* xe,
-                    const float* xn, const float* xg, float* ye, float* yn, float* yg) {
+                    const float* xn, const float* xg, float* ye, float* yn, float* yg, TcPreRows pre_in, TcNextCore next,
+                    TcPreRows pre_out) {
   const int64_t E = g->E, N = g->N, B = g->B;
   int rc = GNB_OK;
   const size_t nparts = (size_t)(g->n_parts > 0 ? g->n_parts : 1);
-  float* Pue = arena_ptr<float>(ctx->arena, (size_t)B * H, &rc);
-  float* Pun = arena_ptr<float>(ctx->arena, (size_t)B * H, &rc);
+  float* Pue = pre_in.Pue ? pre_in.Pue : arena_ptr<float>(ctx->arena, (size_t)B * H, &rc);
+  float* Pun = pre_in.Pue ? pre_in.Pun : arena_ptr<float>(ctx->arena, (size_t)B * H, &rc);
   float* Psr = arena_ptr<float>(ctx->arena, (size_t)N * 2 * H, &rc);
   float* Epart = arena_ptr<float>(ctx->arena, nparts * H, &rc);
   float* Gpart = arena_ptr<float>(ctx->arena, nparts * H, &rc);
@@ -476,7 +477,7 @@ int tc_core_forward(gnb_ctx* ctx, const gnb_graph* g, const TcCorePack* pk, cons
   if (rc != GNB_OK) return rc;
 
   // per-graph rows (fp32 CUDA cores, B rows): P_ue = W_eu LN1(gf) + be + folded LN shifts, P_un likewise
-  {
+  if (!pre_in.Pue) {
     GraphPreArgs ga{};
     ga.xg = xg; ga.B = B; ga.gamma = ln1[2].gamma; ga.beta = ln1[2].beta; ga.eps = ln1[2].eps; ga.eps_mode = ln1[2].eps_mode;
     ga.Weu = blk.We + (size_t)3 * H * H; ga.Wnu = blk.Wn + (size_t)2 * H * H;
@@ -533,6 +534,12 @@ int tc_core_forward(gnb_ctx* ctx, const gnb_graph* g, const TcCorePack* pk, cons
     ga.g2 = ln2[2].gamma; ga.b2ln = ln2[2].beta; ga.eps2 = ln2[2].eps; ga.eps_mode2 = ln2[2].eps_mode;
     ga.Wg = blk.Wg; ga.bg = blk.bg; ga.W1 = ffn[2].W1; ga.b1 = ffn[2].b1; ga.W2 = ffn[2].W2; ga.b2 = ffn[2].b2;
     ga.yg = yg;
+    if (next.pk && pre_out.Pue) {      // the per-graph rows of the next core, from y_u, in the same launch
+      ga.next_gamma = next.ln1[2].gamma; ga.next_beta = next.ln1[2].beta; ga.next_eps = next.ln1[2].eps; ga.next_eps_mode = next.ln1[2].eps_mode;
+      ga.next_Weu = next.blk->We + (size_t)3 * H * H; ga.next_Wnu = next.blk->Wn + (size_t)2 * H * H;
+      ga.next_ce = next.pk->cu_e; ga.next_cn = next.pk->cu_n;
+      ga.next_Pue = pre_out.Pue; ga.next_Pun = pre_out.Pun;
+    }
     GNB_TRY(launch_graph_post(ctx, ga, N));
   }
   return GNB_OK;
