@@ -1,5 +1,3 @@
-#pragma unroll 4
-  for (int k = k0; k < k0 + KS; k += 4) {
 // Graph-level (B rows) stages of a GNCore with 128-wide features, fp32 CUDA cores.
 //
 // A batch has few graphs (B << N << E), so these stages are latency- not throughput-bound: a CTA owns
@@ -95,14 +93,8 @@ __global__ void __launch_bounds__(128) k_graph_pre(const GraphPreArgs a) {
 // K-slice of gemv_rows: acc[r] += sum_{k in [k0, k0 + KS)} xs[r][k] * W[k*ldw + n]     (xs rows have stride LD floats)
 template <int KS, int LD>
 __device__ __forceinline__ void gemv_slice(const float* xs, int k0, const float* __restrict__ W, int ldw, int n, float* acc) {
-#ifdef GNB_EXP_ROTATE
-  const int rot = (blockIdx.x * 4) % KS;
-#else
-  const int rot = 0;
-#endif
 #pragma unroll 4
-  for (int kk = 0; kk < KS; kk += 4) {
-    const int k = k0 + ((kk + rot) % KS);
+  for (int k = k0; k < k0 + KS; k += 4) {
     const float w0 = __ldg(W + (size_t)(k + 0) * ldw + n), w1 = __ldg(W + (size_t)(k + 1) * ldw + n);
     const float w2 = __ldg(W + (size_t)(k + 2) * ldw + n), w3 = __ldg(W + (size_t)(k + 3) * ldw + n);
 #pragma unroll
