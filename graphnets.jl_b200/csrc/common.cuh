@@ -61,6 +61,11 @@ struct gnb_ctx {
   int64_t launches = 0;
   // host-variant staging (device side), grown on demand
   Arena staging;
+  // generic bf16 tensor-core linear layers (tc_gemm.cu): enabled per forward by the precision mode; packed weights are
+  // cached per (model id, weight block)
+  bool use_tc_lin = false;
+  uint64_t cur_model_id = 0;
+  void* lin_cache = nullptr;
 };
 
 struct gnb_graph {

@@ -41,6 +41,10 @@ struct LinArgs {
 // out = act( sum_s LN_s(x_s) W_s + bias + sum_j add_j[idx_j] )     fp32 CUDA cores
 int launch_linear_fp32(gnb_ctx* ctx, const LinArgs& a);
 
+// dispatch: bf16 tcgen05 kernel (tc_gemm.cu) when the forward runs in a tensor-core precision mode and the layer is wide
+// enough, else the fp32 kernel
+int launch_linear(gnb_ctx* ctx, const LinArgs& a);
+
 // out[s][:] = sum_{r in [ptr[s], ptr[s+1])} x[r][:]  in ascending r (deterministic)
 int launch_segsum(gnb_ctx* ctx, const float* x, int D, const int32_t* ptr, int64_t S, float* out);
 

@@ -4,6 +4,8 @@
 #include "kernels.cuh"
 #include "tc.cuh"
 #include "smallk.cuh"
+#include "tc_gemm.cuh"
+#include <atomic>
 
 // ------------------------------------------------------------------ errors / arena / ctx
 static thread_local char g_err[1024] = "";
@@ -80,6 +82,7 @@ extern "C" int gnb_ctx_destroy(gnb_ctx* c) {
   cudaSetDevice(c->device);
   c->arena.release();
   c->staging.release();
+  tc_lin_cache_free(c->lin_cache);
   for (auto& r : c->prof_recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
   for (auto e : c->ev_pool) cudaEventDestroy(e);
   delete c;
@@ -164,8 +167,11 @@ struct LayerW {
   float* wnx = nullptr;      // narrow-input blocks: [We ; be] . Wn_agg  ((in_e+2in_n+in_g+1) x out_n), see run_block_wide
 };
 
+static std::atomic<uint64_t> g_model_ids{1};
+
 struct gnb_model {
   int device = 0;
+  uint64_t id = g_model_ids.fetch_add(1);      // key of the per-context packed-weight cache (tc_gemm.cu)
   std::vector<LayerW> layers;
   float* wbuf = nullptr;  // owned device copy of every weight (nullptr: weights by reference)
   int in_dims[3] = {0, 0, 0};
@@ -362,6 +368,11 @@ extern "C" int gnb_model_out_dims(const gnb_model* m, int32_t* e, int32_t* n, in
 struct Feat { const float* e; const float* n; const float* g; };
 struct FeatOut { float* e; float* n; float* g; };
 
+int launch_linear(gnb_ctx* ctx, const LinArgs& a) {
+  if (ctx->use_tc_lin && tc_lin_supported(a)) return launch_linear_tc(ctx, a);
+  return launch_linear_fp32(ctx, a);
+}
+
 LinSrc mk_src(const float* x, int d, const float* W, const gnb_ln_params* ln) {
   LinSrc s;
   s.x = x; s.d = d; s.ldx = d; s.W = W;
@@ -393,10 +404,10 @@ static int run_block_fp32(gnb_ctx* ctx, const gnb_graph* g, const gnb_block_para
       la.R = N; la.Nout = p; la.ldw = p; la.nsrc = 1; la.ldo = p;
       la.src[0] = mk_src(x.n, bn_, b.We + (size_t)a * p, lnn);
       la.out = Ps;
-      GNB_TRY(launch_linear_fp32(ctx, la));
+      GNB_TRY(launch_linear(ctx, la));
       la.src[0] = mk_src(x.n, bn_, b.We + (size_t)(a + bn_) * p, lnn);
       la.out = Pr;
-      GNB_TRY(launch_linear_fp32(ctx, la));
+      GNB_TRY(launch_linear(ctx, la));
     }
     if (c > 0) {
       Pu = arena_ptr<float>(ctx->arena, (size_t)B * p, &rc);
@@ -406,7 +417,7 @@ static int run_block_fp32(gnb_ctx* ctx, const gnb_graph* g, const gnb_block_para
       la.src[0] = mk_src(x.g, c, b.We + (size_t)(a + 2 * bn_) * p, lng);
       la.bias = b.be;
       la.out = Pu;
-      GNB_TRY(launch_linear_fp32(ctx, la));
+      GNB_TRY(launch_linear(ctx, la));
     }
     LinArgs la{};
     la.R = E; la.Nout = p; la.ldw = p; la.ldo = p; la.out = h.e;
@@ -417,7 +428,7 @@ static int run_block_fp32(gnb_ctx* ctx, const gnb_graph* g, const gnb_block_para
     }
     if (Pu) la.add[la.nadd++] = LinAdd{Pu, g->edge_graph, p};
     else la.bias = b.be;
-    GNB_TRY(launch_linear_fp32(ctx, la));
+    GNB_TRY(launch_linear(ctx, la));
     // edge -> node aggregation over the receiver CSR (src/nodefninput.jl:3)
     if (q > 0 || r > 0) {
       agg = arena_ptr<float>(ctx->arena, (size_t)N * p, &rc);
@@ -435,7 +446,7 @@ static int run_block_fp32(gnb_ctx* ctx, const gnb_graph* g, const gnb_block_para
       la.src[0] = mk_src(x.g, c, b.Wn + (size_t)(p + bn_) * q, lng);
       la.bias = b.bn;
       la.out = Pu;
-      GNB_TRY(launch_linear_fp32(ctx, la));
+      GNB_TRY(launch_linear(ctx, la));
     }
     LinArgs la{};
     la.R = N; la.Nout = q; la.ldw = q; la.ldo = q; la.out = h.n;
@@ -443,7 +454,7 @@ static int run_block_fp32(gnb_ctx* ctx, const gnb_graph* g, const gnb_block_para
     if (bn_ > 0) la.src[la.nsrc++] = mk_src(x.n, bn_, b.Wn + (size_t)p * q, lnn);
     if (Pu) la.add[la.nadd++] = LinAdd{Pu, g->node_graph, q};
     else la.bias = b.bn;
-    GNB_TRY(launch_linear_fp32(ctx, la));
+    GNB_TRY(launch_linear(ctx, la));
   }
   if (r > 0) {
     float *se = nullptr, *sv = nullptr;
@@ -463,7 +474,7 @@ static int run_block_fp32(gnb_ctx* ctx, const gnb_graph* g, const gnb_block_para
     if (p > 0) la.src[la.nsrc++] = mk_src(se, p, b.Wg, nullptr);
     if (q > 0) la.src[la.nsrc++] = mk_src(sv, q, b.Wg + (size_t)p * r, nullptr);
     if (c > 0) la.src[la.nsrc++] = mk_src(x.g, c, b.Wg + (size_t)(p + q) * r, lng);
-    GNB_TRY(launch_linear_fp32(ctx, la));
+    GNB_TRY(launch_linear(ctx, la));
   }
   return GNB_OK;
 }
@@ -638,7 +649,7 @@ int run_ffn_residual_fp32(gnb_ctx* ctx, int64_t R, int d, const gnb_ffn_params& 
     l1.R = rows; l1.Nout = 4 * d; l1.ldw = 4 * d; l1.nsrc = 1; l1.ldo = 4 * d;
     l1.src[0] = mk_src(x + (size_t)r0 * d, d, f.W1, &ln2);
     l1.bias = f.b1; l1.relu = 1; l1.out = hid;
-    GNB_TRY(launch_linear_fp32(ctx, l1));
+    GNB_TRY(launch_linear(ctx, l1));
     LinArgs l2{};
     l2.R = rows; l2.Nout = d; l2.ldw = d; l2.nsrc = 1; l2.ldo = d;
     l2.src[0] = mk_src(hid, 4 * d, f.W2, nullptr);
@@ -646,7 +657,7 @@ int run_ffn_residual_fp32(gnb_ctx* ctx, int64_t R, int d, const gnb_ffn_params& 
     l2.add[l2.nadd++] = LinAdd{x + (size_t)r0 * d, nullptr, d};
     l2.add[l2.nadd++] = LinAdd{h + (size_t)r0 * d, nullptr, d};
     l2.out = y + (size_t)r0 * d;
-    GNB_TRY(launch_linear_fp32(ctx, l2));
+    GNB_TRY(launch_linear(ctx, l2));
   }
   return GNB_OK;
 }
@@ -691,6 +702,8 @@ static int forward_device(gnb_ctx* ctx, const gnb_model* m, const gnb_graph* g, 
   GNB_CHECK(m->out_dims[2] == 0 || out_gf, "gnb_model_forward: out_gf is NULL");
   GNB_CUDA(cudaSetDevice(ctx->device));
   if (reset_arena) ctx->arena.reset();
+  ctx->use_tc_lin = precision != GNB_PREC_FP32 && m->wbuf != nullptr;      // needs model-owned weights (cache key = model id)
+  ctx->cur_model_id = m->id;
   const int L = (int)m->layers.size();
   // ping-pong activation buffers sized for the widest intermediate layer output
   size_t me = 0, mn = 0, mg = 0;
@@ -740,7 +753,8 @@ static int forward_device(gnb_ctx* ctx, const gnb_model* m, const gnb_graph* g, 
       have_pre = false;
     } else {
       bool use_tc = (precision != GNB_PREC_FP32) && w.tc != nullptr;
-      if (precision == GNB_PREC_BF16 && !w.tc) {
+      const bool wide_ok = (w.blk.in_e % 128 == 0) && (w.blk.in_n % 128 == 0) && (w.blk.in_g % 128 == 0) && m->wbuf != nullptr;
+      if (precision == GNB_PREC_BF16 && !w.tc && !wide_ok) {      // wide_ok: the generic tcgen05 linear layers (tc_gemm.cu) apply
         gnb_set_error("layer %d: GNCore dims (%d,%d,%d) are not supported by the tcgen05 bf16 path "
                       "(use GNB_PREC_AUTO or GNB_PREC_FP32)", li, w.blk.in_e, w.blk.in_n, w.blk.in_g);
         return GNB_ERR_UNSUPPORTED;

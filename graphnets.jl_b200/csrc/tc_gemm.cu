@@ -1,0 +1,396 @@
+// Generic bf16 tcgen05 linear layer for WIDE GNCore layers (hidden width 256, 384, ...: every width that is a multiple of 64
+// on the K side and of 128 on the N side), same contract as the fp32 kernel it replaces (fp32.cu::k_linear):
+//
+//   out = act( sum_s LN_s(x_s) W_s + bias + sum_j add_j[idx_j] )
+//
+// i.e. every Dense of src/gnblock.jl:65-67 and src/gnfeedforward.jl:27-31 after the linearity split of the concat
+// (src/edgefninput.jl:1-8): direct row sources are concatenated along K, gathered node / graph projections are added in the
+// epilogue.  The 128-wide cores have their own fully fused kernel (tc_edge.cu); this one trades fusion for generality: one
+// launch per Dense, activations make an HBM round trip between launches.
+//
+// Work item = (128-row tile, group of NG <= 2 output blocks of 128 columns); a persistent CTA walks the row tiles and, inside
+// a tile, the column groups (the LayerNorm statistics of the tile are computed once and kept in shared memory).  10 warps:
+//   warps 4-7  A producers : fp32 rows -> LayerNorm (two-pass statistics, affine applied here) -> bf16 -> 128B-swizzled K-major
+//                            64-wide slabs (16 KB) through a 4-stage ring
+//   warp 9     W loader    : cp.async.bulk of pre-packed bf16 slabs (NG x 16 KB per K step) through a 3-stage ring
+//   warp 8     MMA issuer  : per K step 4 UMMAs (K = 16) per output block into TMEM (2 accumulator sets x 256 columns)
+//   warps 0-3  drain       : accumulator fragments -> + bias + gathered addends -> relu -> sector-exact fp32 stores
+#include "tc_ptx.cuh"
+#include "tc_gemm.cuh"
+#include <map>
+#include <tuple>
+
+using namespace tcx;
+
+namespace {
+
+constexpr int SLAB = KB_BYTES;            // 128 rows x 64 k bf16
+constexpr int NA = 4, NW = 3;             // ring depths
+constexpr int G_OFF_A = 0;
+constexpr int G_OFF_W = NA * SLAB;                    // stages of 2 slabs
+constexpr int G_OFF_STAT = G_OFF_W + NW * 2 * SLAB;   // float2 stats[3][128]
+constexpr int G_OFF_BAR = G_OFF_STAT + 3 * 128 * 8;
+constexpr int G_SMEM = G_OFF_BAR + 32 * 8 + 16 + 1024;
+constexpr int G_THREADS = 10 * 32;
+enum { GB_WFULL = 0, GB_WEMPTY = 3, GB_AFULL = 6, GB_AEMPTY = 10, GB_ACCFULL = 14, GB_ACCFREE = 16 };
+
+struct GemmArgs {
+  int64_t R;
+  int Nout, ldo;
+  int nsrc;
+  const float* x[3]; int ldx[3]; int d[3];
+  const float* gamma[3]; const float* beta[3]; float eps[3]; int eps_mode[3];
+  int KS;                         // total K / 64
+  const __nv_bfloat16* wpack;     // [n group][K step][block in group][8192 elements]
+  const float* bias;
+  int nadd;
+  const float* add[4]; const int32_t* add_idx[4]; int lda[4];
+  int relu;
+  float* out;
+  int num_tiles, ngroups, NG;     // NG output blocks per group (1 or 2)
+};
+
+__global__ void __launch_bounds__(G_THREADS, 1) k_tc_lin(const GemmArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* sm = smem_raw + (base - raw);
+  float2* stats = reinterpret_cast<float2*>(sm + G_OFF_STAT);      // (mean, rstd) per source and row of the tile
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sm + G_OFF_BAR);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 32);
+  const uint32_t bar0 = smem_u32(bars);
+  auto BAR = [&](int i) { return bar0 + 8u * (uint32_t)i; };
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) {
+    for (int i = 0; i < NW; i++) { mbar_init(BAR(GB_WFULL + i), 1); mbar_init(BAR(GB_WEMPTY + i), 1); }
+    for (int i = 0; i < NA; i++) { mbar_init(BAR(GB_AFULL + i), 4); mbar_init(BAR(GB_AEMPTY + i), 1); }
+    for (int i = 0; i < 2; i++) { mbar_init(BAR(GB_ACCFULL + i), 1); mbar_init(BAR(GB_ACCFREE + i), 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 8) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const int KS = a.KS, NG = a.NG;
+
+  if (warp == 9) {
+    // ===================================================== weight loader
+    uint32_t it = 0;
+    for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
+      for (int ng = 0; ng < a.ngroups; ng++) {
+        const uint8_t* src = reinterpret_cast<const uint8_t*>(a.wpack) + (size_t)ng * KS * NG * SLAB;
+#pragma unroll 1
+        for (int ks = 0; ks < KS; ks++, it++) {
+          const uint32_t st = it % NW, ph = (it / NW) & 1;
+          mbar_wait(BAR(GB_WEMPTY + st), ph ^ 1);
+          if (elect_one()) {
+            const uint32_t nb = (uint32_t)(NG * SLAB);
+            mbar_expect_tx(BAR(GB_WFULL + st), nb);
+            bulk_g2s(base + G_OFF_W + st * 2 * SLAB, src + (size_t)ks * NG * SLAB, nb, BAR(GB_WFULL + st));
+          }
+          __syncwarp();
+        }
+      }
+    }
+  } else if (warp == 8) {
+    // ===================================================== MMA issuer
+    uint32_t ita = 0, itw = 0, item = 0;
+    for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
+      for (int ng = 0; ng < a.ngroups; ng++, item++) {
+        const uint32_t buf = item & 1, aph = (item >> 1) & 1;
+        mbar_wait(BAR(GB_ACCFREE + buf), aph ^ 1);
+        tc_fence_after();
+#pragma unroll 1
+        for (int ks = 0; ks < KS; ks++, ita++, itw++) {
+          const uint32_t as = ita % NA, pa = (ita / NA) & 1, ws = itw % NW, pw = (itw / NW) & 1;
+          mbar_wait(BAR(GB_AFULL + as), pa);
+          mbar_wait(BAR(GB_WFULL + ws), pw);
+          tc_fence_after();
+          if (elect_one()) {
+            const uint64_t ad = umma_desc(base + G_OFF_A + as * SLAB);
+            for (int nb = 0; nb < NG; nb++) {
+              const uint64_t wd = umma_desc(base + G_OFF_W + ws * 2 * SLAB + nb * SLAB);
+              const uint32_t D = tmem + buf * 256 + nb * 128;
+#pragma unroll
+              for (int k4 = 0; k4 < 4; k4++) mma_ss(D, ad + 2 * k4, wd + 2 * k4, IDESC, (ks > 0 || k4 > 0) ? 1u : 0u);
+            }
+            tc_commit(BAR(GB_AEMPTY + as));
+            tc_commit(BAR(GB_WEMPTY + ws));
+            if (ks == KS - 1) tc_commit(BAR(GB_ACCFULL + buf));
+          }
+          __syncwarp();
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================================================== A producers: warp q owns rows 32 q .. 32 q + 31 of the tile
+    const int q = warp - 4;
+    const int hr = lane >> 4, c16 = lane & 15;      // two rows per load instruction, 16 lanes x 16 B per row slab
+    uint32_t it = 0;
+    for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
+      const int64_t row0 = (int64_t)tile * TM + 32 * q;
+      // ---- LayerNorm statistics of this warp's rows, two-pass in fp32 (src/gngraphnorm.jl:19-26), kept for all column groups
+      for (int s = 0; s < a.nsrc; s++) {
+        if (a.gamma[s] == nullptr) continue;
+        const int d = a.d[s], nv = d >> 7;      // float4 per lane (d multiple of 128) + tail
+#pragma unroll 1
+        for (int r = 0; r < 32; r++) {
+          int64_t row = row0 + r;
+          row = row < a.R ? row : a.R - 1;
+          const float* xr = a.x[s] + (size_t)row * a.ldx[s];
+          float sum = 0.f;
+          for (int k = 4 * lane; k < d; k += 128) {
+            const float4 v = __ldg(reinterpret_cast<const float4*>(xr + k));
+            sum += (v.x + v.y) + (v.z + v.w);
+          }
+          sum = warp_sum(sum);
+          const float mu = sum / (float)d;
+          float sq = 0.f;
+          for (int k = 4 * lane; k < d; k += 128) {
+            const float4 v = __ldg(reinterpret_cast<const float4*>(xr + k));
+            const float dx = v.x - mu, dy = v.y - mu, dz = v.z - mu, dw = v.w - mu;
+            sq += (dx * dx + dy * dy) + (dz * dz + dw * dw);
+          }
+          sq = warp_sum(sq);
+          if (lane == 0) stats[s * 128 + 32 * q + r] = make_float2(mu, ln_rstd(sq / (float)d, a.eps[s], a.eps_mode[s]));
+          (void)nv;
+        }
+      }
+      __syncwarp();
+      for (int ng = 0; ng < a.ngroups; ng++) {
+        int s = 0, koff = 0;
+#pragma unroll 1
+        for (int ks = 0; ks < KS; ks++, it++) {
+          while (koff >= a.d[s]) { koff -= a.d[s]; s++; }
+          const uint32_t st = it % NA, ph = (it / NA) & 1;
+          const bool ln = a.gamma[s] != nullptr;
+          float4 g4 = make_float4(1.f, 1.f, 1.f, 1.f), b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (ln) {
+            g4 = __ldg(reinterpret_cast<const float4*>(a.gamma[s] + koff + 4 * c16));
+            b4 = __ldg(reinterpret_cast<const float4*>(a.beta[s] + koff + 4 * c16));
+          }
+          const float* xs = a.x[s] + koff + 4 * c16;
+          const int ldx = a.ldx[s];
+          uint8_t* A = sm + G_OFF_A + st * SLAB;
+          mbar_wait(BAR(GB_AEMPTY + st), ph ^ 1);
+#pragma unroll 1
+          for (int i0 = 0; i0 < 32; i0 += 16) {
+            float4 v[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+              int64_t row = row0 + i0 + 2 * u + hr;
+              row = row < a.R ? row : a.R - 1;
+              v[u] = __ldg(reinterpret_cast<const float4*>(xs + (size_t)row * ldx));
+            }
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+              const int r = 32 * q + i0 + 2 * u + hr;
+              float4 t = v[u];
+              if (ln) {
+                const float2 ms = stats[s * 128 + r];
+                t.x = (t.x - ms.x) * ms.y * g4.x + b4.x;
+                t.y = (t.y - ms.x) * ms.y * g4.y + b4.y;
+                t.z = (t.z - ms.x) * ms.y * g4.z + b4.z;
+                t.w = (t.w - ms.x) * ms.y * g4.w + b4.w;
+              }
+              if (row0 + i0 + 2 * u + hr >= a.R) t = f4zero();
+              uint2 pk;
+              pk.x = pack_bf16(t.x, t.y);
+              pk.y = pack_bf16(t.z, t.w);
+              *reinterpret_cast<uint2*>(A + sw_off(r, 4 * c16)) = pk;
+            }
+          }
+          fence_async_smem();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(BAR(GB_AFULL + st));
+          koff += 64;
+        }
+      }
+    }
+  } else {
+    // ===================================================== drain (TMEM lane quadrant = warp), accumulator-fragment layout:
+    // every 4 lanes own one 32 B sector of a row
+    const uint32_t lane_base = ((uint32_t)(warp * 32)) << 16;
+    const int qr = lane >> 2, cq = 2 * (lane & 3);
+    uint32_t item = 0;
+    for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
+      const int64_t row0 = (int64_t)tile * TM + 32 * warp;
+      // the 4 rows of this lane: 16 hh + 8 h2 + qr
+      int64_t arow[4][4];
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        int64_t r = row0 + 16 * (k >> 1) + 8 * (k & 1) + qr;
+        r = r < a.R ? r : a.R - 1;
+#pragma unroll
+        for (int j = 0; j < 4; j++) arow[j][k] = (j < a.nadd && a.add_idx[j]) ? (int64_t)__ldg(a.add_idx[j] + r) : r;
+      }
+      for (int ng = 0; ng < a.ngroups; ng++, item++) {
+        const uint32_t buf = item & 1, ph = (item >> 1) & 1;
+        mbar_wait(BAR(GB_ACCFULL + buf), ph);
+        tc_fence_after();
+        const int nsteps = 4 * NG;      // (hh, 64-column chunk) steps
+#pragma unroll 1
+        for (int stp = 0; stp < nsteps; stp++) {
+          const int hh = stp & 1, ch = stp >> 1;
+          const int col = ng * NG * 128 + 64 * ch + cq;      // + 8 n
+          uint32_t dreg[32];
+          TC_LD_FRAG64(tmem + buf * 256 + lane_base + ((uint32_t)(16 * hh) << 16) + 64 * ch, dreg);
+          tc_wait_ld();
+          if (stp == nsteps - 1) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(BAR(GB_ACCFREE + buf));
+          }
+#pragma unroll
+          for (int h2 = 0; h2 < 2; h2++) {
+            const int k = 2 * hh + h2;
+            const int64_t row = row0 + 16 * hh + 8 * h2 + qr;
+            float2 v[8];
+#pragma unroll
+            for (int n = 0; n < 8; n++) {
+              v[n] = make_float2(__uint_as_float(dreg[4 * n + 2 * h2]), __uint_as_float(dreg[4 * n + 2 * h2 + 1]));
+              if (a.bias) {
+                const float2 b = __ldg(reinterpret_cast<const float2*>(a.bias + col + 8 * n));
+                v[n].x += b.x; v[n].y += b.y;
+              }
+            }
+            for (int j = 0; j < a.nadd; j++) {
+              const float* ap = a.add[j] + (size_t)arow[j][k] * a.lda[j] + col;
+#pragma unroll
+              for (int n = 0; n < 8; n++) {
+                const float2 t = __ldg(reinterpret_cast<const float2*>(ap + 8 * n));
+                v[n].x += t.x; v[n].y += t.y;
+              }
+            }
+            if (a.relu) {
+#pragma unroll
+              for (int n = 0; n < 8; n++) { v[n].x = fmaxf(v[n].x, 0.f); v[n].y = fmaxf(v[n].y, 0.f); }
+            }
+            if (row < a.R) {
+              float* o = a.out + (size_t)row * a.ldo + col;
+#pragma unroll
+              for (int n = 0; n < 8; n++) *reinterpret_cast<float2*>(o + 8 * n) = v[n];
+            }
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 8) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+}
+
+// packed[((ng * KS + ks) * NG + nb) * 8192 + swizzled(n, k)] = bf16(W[(ks*64 + k) * ldw + (ng*NG + nb)*128 + n]),
+// W given per source as k-major row blocks (LinSrc::W)
+struct PackSrc { const float* W[3]; int d[3]; int nsrc; };
+__global__ void k_pack_lin(PackSrc ps, int ldw, int KS, int NG, int ngroups, __nv_bfloat16* __restrict__ dst) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;      // over ngroups * KS * NG * 8192
+  const int64_t total = (int64_t)ngroups * KS * NG * 8192;
+  if (idx >= total) return;
+  const int e = (int)(idx & 8191);
+  int64_t slab = idx >> 13;
+  const int nb = (int)(slab % NG); slab /= NG;
+  const int ks = (int)(slab % KS);
+  const int ng = (int)(slab / KS);
+  const int k = e >> 7, n = e & 127;      // element (n, k) of the slab, k in [0, 64)
+  int kk = ks * 64 + k, s = 0;
+  while (kk >= ps.d[s]) { kk -= ps.d[s]; s++; }
+  const float w = ps.W[s][(size_t)kk * ldw + (size_t)(ng * NG + nb) * 128 + n];
+  dst[(idx >> 13) * 8192 + (sw_off(n, k) >> 1)] = __float2bfloat16_rn(w);
+}
+
+struct PackKey {
+  uint64_t model;
+  const float* W[3];
+  int d[3];
+  int Nout, ldw;
+  bool operator<(const PackKey& o) const {
+    return std::tie(model, W[0], W[1], W[2], d[0], d[1], d[2], Nout, ldw) <
+           std::tie(o.model, o.W[0], o.W[1], o.W[2], o.d[0], o.d[1], o.d[2], o.Nout, o.ldw);
+  }
+};
+struct PackCache { std::map<PackKey, __nv_bfloat16*> m; };
+
+}  // namespace
+
+void tc_lin_cache_free(void* cache) {
+  if (!cache) return;
+  PackCache* c = static_cast<PackCache*>(cache);
+  for (auto& kv : c->m) cudaFree(kv.second);
+  delete c;
+}
+
+bool tc_lin_supported(const LinArgs& a) {
+  if (a.R < 256 || a.Nout < 128 || (a.Nout & 127) || a.nsrc < 1) return false;
+  int K = 0;
+  for (int s = 0; s < a.nsrc; s++) {
+    if (a.src[s].d <= 0 || (a.src[s].d & 63) || (a.src[s].ldx & 3)) return false;
+    if (a.src[s].gamma && (a.src[s].d & 127)) return false;
+    K += a.src[s].d;
+  }
+  if (K < 128 || (a.ldo & 1)) return false;
+  for (int j = 0; j < a.nadd; j++)
+    if (a.add[j].lda & 1) return false;
+  return true;
+}
+
+int launch_linear_tc(gnb_ctx* ctx, const LinArgs& a) {
+  if (a.R <= 0) return GNB_OK;
+  static bool attr_set = false;
+  if (!attr_set) {
+    GNB_CUDA(cudaFuncSetAttribute(k_tc_lin, cudaFuncAttributeMaxDynamicSharedMemorySize, G_SMEM));
+    attr_set = true;
+  }
+  GemmArgs g{};
+  g.R = a.R; g.Nout = a.Nout; g.ldo = a.ldo; g.nsrc = a.nsrc;
+  int K = 0;
+  PackKey key{};
+  key.model = ctx->cur_model_id; key.Nout = a.Nout; key.ldw = a.ldw;
+  PackSrc ps{};
+  ps.nsrc = a.nsrc;
+  for (int s = 0; s < 3; s++) { ps.d[s] = 1 << 30; }
+  for (int s = 0; s < a.nsrc; s++) {
+    g.x[s] = a.src[s].x; g.ldx[s] = a.src[s].ldx; g.d[s] = a.src[s].d;
+    g.gamma[s] = a.src[s].gamma; g.beta[s] = a.src[s].beta; g.eps[s] = a.src[s].eps; g.eps_mode[s] = a.src[s].eps_mode;
+    key.W[s] = a.src[s].W; key.d[s] = a.src[s].d;
+    ps.W[s] = a.src[s].W; ps.d[s] = a.src[s].d;
+    K += a.src[s].d;
+  }
+  for (int s = a.nsrc; s < 3; s++) g.d[s] = 1 << 30;
+  g.KS = K / 64;
+  const int nblk = a.Nout / 128;
+  g.NG = (nblk % 2 == 0) ? 2 : 1;
+  g.ngroups = nblk / g.NG;
+  g.num_tiles = (int)ceil_div(a.R, TM);
+  g.bias = a.bias; g.nadd = a.nadd; g.relu = a.relu; g.out = a.out;
+  for (int j = 0; j < a.nadd; j++) { g.add[j] = a.add[j].a; g.add_idx[j] = a.add[j].idx; g.lda[j] = a.add[j].lda; }
+  // packed bf16 weights: built on first use, cached per (model, weight block)
+  if (!ctx->lin_cache) ctx->lin_cache = new PackCache();
+  PackCache* cache = static_cast<PackCache*>(ctx->lin_cache);
+  auto itc = cache->m.find(key);
+  if (itc == cache->m.end()) {
+    __nv_bfloat16* dst = nullptr;
+    const size_t elems = (size_t)K * a.Nout;
+    if (cudaMalloc((void**)&dst, elems * sizeof(__nv_bfloat16)) != cudaSuccess) {
+      cudaGetLastError();
+      gnb_set_error("launch_linear_tc: cudaMalloc(%zu) for packed weights failed", elems * 2);
+      return GNB_ERR_OOM;
+    }
+    k_pack_lin<<<(unsigned)ceil_div((int64_t)elems, 256), 256, 0, ctx->stream>>>(ps, a.ldw, g.KS, g.NG, g.ngroups, dst);
+    GNB_CUDA(cudaGetLastError());
+    ctx->launches++;
+    itc = cache->m.emplace(key, dst).first;
+  }
+  g.wpack = itc->second;
+  double bytes = 4.0 * ((double)a.R * (K + (double)a.Nout * (1 + a.nadd))) + 2.0 * K * a.Nout;
+  Launch L(ctx, "tc_linear", bytes, 2.0 * a.R * K * a.Nout);
+  const int grid = g.num_tiles < ctx->sm_count ? g.num_tiles : ctx->sm_count;
+  k_tc_lin<<<grid, G_THREADS, G_SMEM, ctx->stream>>>(g);
+  GNB_CUDA(cudaGetLastError());
+  return GNB_OK;
+}

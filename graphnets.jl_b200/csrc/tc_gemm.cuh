@@ -1,0 +1,9 @@
+// Generic bf16 tcgen05 linear layer for wide GNCore layers (internal interface, see tc_gemm.cu).
+#pragma once
+#include "kernels.cuh"
+
+// true when launch_linear_tc can run this layer (row sources multiples of 64 wide, output a multiple of 128, enough rows)
+bool tc_lin_supported(const LinArgs& a);
+// same contract as launch_linear_fp32, bf16 operands / fp32 accumulation on the tensor cores
+int launch_linear_tc(gnb_ctx* ctx, const LinArgs& a);
+void tc_lin_cache_free(void* cache);
