@@ -9,15 +9,18 @@
 // launch per Dense, activations make an HBM round trip between launches.
 //
 // Work item = (128-row tile, group of NG <= 2 output blocks of 128 columns); a persistent CTA walks the row tiles and, inside
-// a tile, the column groups (the LayerNorm statistics of the tile are computed once and kept in shared memory).  10 warps:
-//   warps 4-7  A producers : fp32 rows -> LayerNorm (two-pass statistics, affine applied here) -> bf16 -> 128B-swizzled K-major
-//                            64-wide slabs (16 KB) through a 4-stage ring
-//   warp 9     W loader    : cp.async.bulk of pre-packed bf16 slabs (NG x 16 KB per K step) through a 3-stage ring
-//   warp 8     MMA issuer  : per K step 4 UMMAs (K = 16) per output block into TMEM (2 accumulator sets x 256 columns)
+// a tile, the column groups (the LayerNorm statistics of the tile are computed once and kept in shared memory).  14 warps:
+//   warps 4-11 A producers : fp32 rows -> LayerNorm (two-pass statistics, affine applied here) -> bf16 -> 128B-swizzled K-major
+//                            64-wide slabs (16 KB) through a 6-stage ring; K <= 256: the slabs of a row tile are produced
+//                            once and reused by all column groups
+//   warp 13    W loader    : cp.async.bulk of pre-packed bf16 slabs (NG x 16 KB per K step) through a 3-stage ring
+//   warp 12    MMA issuer  : per K step 4 UMMAs (K = 16) per output block into TMEM (2 accumulator sets x 256 columns)
 //   warps 0-3  drain       : accumulator fragments -> + bias + gathered addends -> relu -> sector-exact fp32 stores
 #include "tc_ptx.cuh"
 #include "tc_gemm.cuh"
 #include <map>
+#include <string>
+#include <stdlib.h>
 #include <tuple>
 
 using namespace tcx;
@@ -25,14 +28,15 @@ using namespace tcx;
 namespace {
 
 constexpr int SLAB = KB_BYTES;            // 128 rows x 64 k bf16
-constexpr int NA = 4, NW = 3;             // ring depths
+constexpr int NA = 6, NW = 3;             // ring depths (A: 6 x 16 KB, W: 3 x 32 KB)
 constexpr int G_OFF_A = 0;
 constexpr int G_OFF_W = NA * SLAB;                    // stages of 2 slabs
 constexpr int G_OFF_STAT = G_OFF_W + NW * 2 * SLAB;   // float2 stats[3][128]
 constexpr int G_OFF_BAR = G_OFF_STAT + 3 * 128 * 8;
 constexpr int G_SMEM = G_OFF_BAR + 32 * 8 + 16 + 1024;
-constexpr int G_THREADS = 10 * 32;
-enum { GB_WFULL = 0, GB_WEMPTY = 3, GB_AFULL = 6, GB_AEMPTY = 10, GB_ACCFULL = 14, GB_ACCFREE = 16 };
+constexpr int G_THREADS = 14 * 32;
+constexpr int W_MMA = 12, W_LOAD = 13;      // warps 0-3 drain, 4-11 A producers
+enum { GB_WFULL = 0, GB_WEMPTY = 3, GB_AFULL = 6, GB_AEMPTY = 12, GB_ACCFULL = 18, GB_ACCFREE = 20 };
 
 struct GemmArgs {
   int64_t R;
@@ -48,6 +52,7 @@ struct GemmArgs {
   int relu;
   float* out;
   int num_tiles, ngroups, NG;     // NG output blocks per group (1 or 2)
+  int resident;                   // the A slabs of a row tile are produced once and reused by every column group (KS <= NA - 2)
 };
 
 __global__ void __launch_bounds__(G_THREADS, 1) k_tc_lin(const GemmArgs a) {
@@ -63,11 +68,11 @@ __global__ void __launch_bounds__(G_THREADS, 1) k_tc_lin(const GemmArgs a) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid == 0) {
     for (int i = 0; i < NW; i++) { mbar_init(BAR(GB_WFULL + i), 1); mbar_init(BAR(GB_WEMPTY + i), 1); }
-    for (int i = 0; i < NA; i++) { mbar_init(BAR(GB_AFULL + i), 4); mbar_init(BAR(GB_AEMPTY + i), 1); }
+    for (int i = 0; i < NA; i++) { mbar_init(BAR(GB_AFULL + i), 8); mbar_init(BAR(GB_AEMPTY + i), 1); }
     for (int i = 0; i < 2; i++) { mbar_init(BAR(GB_ACCFULL + i), 1); mbar_init(BAR(GB_ACCFREE + i), 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 8) {
+  if (warp == W_MMA) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -77,7 +82,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) k_tc_lin(const GemmArgs a) {
   const uint32_t tmem = *tmem_slot;
   const int KS = a.KS, NG = a.NG;
 
-  if (warp == 9) {
+  if (warp == W_LOAD) {
     // ===================================================== weight loader
     uint32_t it = 0;
     for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
@@ -96,18 +101,20 @@ __global__ void __launch_bounds__(G_THREADS, 1) k_tc_lin(const GemmArgs a) {
         }
       }
     }
-  } else if (warp == 8) {
+  } else if (warp == W_MMA) {
     // ===================================================== MMA issuer
-    uint32_t ita = 0, itw = 0, item = 0;
-    for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
+    uint32_t ita = 0, itw = 0, item = 0, tl = 0;
+    for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, tl++) {
       for (int ng = 0; ng < a.ngroups; ng++, item++) {
         const uint32_t buf = item & 1, aph = (item >> 1) & 1;
         mbar_wait(BAR(GB_ACCFREE + buf), aph ^ 1);
         tc_fence_after();
+        if (a.resident) ita = tl * KS;      // every column group walks the same slabs of the tile
+        const bool first = !a.resident || ng == 0, last = !a.resident || ng == a.ngroups - 1;
 #pragma unroll 1
         for (int ks = 0; ks < KS; ks++, ita++, itw++) {
           const uint32_t as = ita % NA, pa = (ita / NA) & 1, ws = itw % NW, pw = (itw / NW) & 1;
-          mbar_wait(BAR(GB_AFULL + as), pa);
+          if (first) mbar_wait(BAR(GB_AFULL + as), pa);
           mbar_wait(BAR(GB_WFULL + ws), pw);
           tc_fence_after();
           if (elect_one()) {
@@ -118,7 +125,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) k_tc_lin(const GemmArgs a) {
 #pragma unroll
               for (int k4 = 0; k4 < 4; k4++) mma_ss(D, ad + 2 * k4, wd + 2 * k4, IDESC, (ks > 0 || k4 > 0) ? 1u : 0u);
             }
-            tc_commit(BAR(GB_AEMPTY + as));
+            if (last) tc_commit(BAR(GB_AEMPTY + as));
             tc_commit(BAR(GB_WEMPTY + ws));
             if (ks == KS - 1) tc_commit(BAR(GB_ACCFULL + buf));
           }
@@ -127,42 +134,82 @@ __global__ void __launch_bounds__(G_THREADS, 1) k_tc_lin(const GemmArgs a) {
       }
     }
   } else if (warp >= 4) {
-    // ===================================================== A producers: warp q owns rows 32 q .. 32 q + 31 of the tile
-    const int q = warp - 4;
+    // ===================================================== A producers: warp pw owns rows 16 pw .. 16 pw + 15 of the tile
+    const int pw = warp - 4;
     const int hr = lane >> 4, c16 = lane & 15;      // two rows per load instruction, 16 lanes x 16 B per row slab
     uint32_t it = 0;
     for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
-      const int64_t row0 = (int64_t)tile * TM + 32 * q;
+      const int64_t row0 = (int64_t)tile * TM + 16 * pw;
       // ---- LayerNorm statistics of this warp's rows, two-pass in fp32 (src/gngraphnorm.jl:19-26), kept for all column groups
+      // (16 lanes per row, the row stays in registers for both passes; 2 row pairs = 4 rows of loads in flight)
       for (int s = 0; s < a.nsrc; s++) {
         if (a.gamma[s] == nullptr) continue;
-        const int d = a.d[s], nv = d >> 7;      // float4 per lane (d multiple of 128) + tail
+        const int d = a.d[s], nv = d >> 6;      // float4 per lane and row (d <= 512: nv <= 8)
+        const float* xs = a.x[s] + 4 * c16;
+        const float inv_d = 1.0f / (float)d;
 #pragma unroll 1
-        for (int r = 0; r < 32; r++) {
-          int64_t row = row0 + r;
-          row = row < a.R ? row : a.R - 1;
-          const float* xr = a.x[s] + (size_t)row * a.ldx[s];
-          float sum = 0.f;
-          for (int k = 4 * lane; k < d; k += 128) {
-            const float4 v = __ldg(reinterpret_cast<const float4*>(xr + k));
-            sum += (v.x + v.y) + (v.z + v.w);
+        for (int r0 = 0; r0 < 16; r0 += 4) {
+          float4 v[2][8];
+#pragma unroll
+          for (int p = 0; p < 2; p++) {
+            int64_t row = row0 + r0 + 2 * p + hr;
+            row = row < a.R ? row : a.R - 1;
+            const float* xr = xs + (size_t)row * a.ldx[s];
+#pragma unroll
+            for (int j = 0; j < 8; j++) v[p][j] = j < nv ? __ldg(reinterpret_cast<const float4*>(xr + 64 * j)) : f4zero();
           }
-          sum = warp_sum(sum);
-          const float mu = sum / (float)d;
-          float sq = 0.f;
-          for (int k = 4 * lane; k < d; k += 128) {
-            const float4 v = __ldg(reinterpret_cast<const float4*>(xr + k));
-            const float dx = v.x - mu, dy = v.y - mu, dz = v.z - mu, dw = v.w - mu;
-            sq += (dx * dx + dy * dy) + (dz * dz + dw * dw);
+          float sum[2], sq[2];
+#pragma unroll
+          for (int p = 0; p < 2; p++) {
+            float t = 0.f;
+#pragma unroll
+            for (int j = 0; j < 8; j++) t += (v[p][j].x + v[p][j].y) + (v[p][j].z + v[p][j].w);
+            sum[p] = t;
           }
-          sq = warp_sum(sq);
-          if (lane == 0) stats[s * 128 + 32 * q + r] = make_float2(mu, ln_rstd(sq / (float)d, a.eps[s], a.eps_mode[s]));
-          (void)nv;
+#pragma unroll
+          for (int o = 1; o < 16; o <<= 1)
+#pragma unroll
+            for (int p = 0; p < 2; p++) sum[p] += __shfl_xor_sync(0xffffffffu, sum[p], o);
+#pragma unroll
+          for (int p = 0; p < 2; p++) {
+            const float mu = sum[p] * inv_d;
+            float t = 0.f;
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+              if (j < nv) {
+                const float dx = v[p][j].x - mu, dy = v[p][j].y - mu, dz = v[p][j].z - mu, dw = v[p][j].w - mu;
+                t += (dx * dx + dy * dy) + (dz * dz + dw * dw);
+              }
+            }
+            sq[p] = t;
+            sum[p] = mu;
+          }
+#pragma unroll
+          for (int o = 1; o < 16; o <<= 1)
+#pragma unroll
+            for (int p = 0; p < 2; p++) sq[p] += __shfl_xor_sync(0xffffffffu, sq[p], o);
+          if (c16 == 0) {
+#pragma unroll
+            for (int p = 0; p < 2; p++)
+              stats[s * 128 + 16 * pw + r0 + 2 * p + hr] = make_float2(sum[p], ln_rstd(sq[p] * inv_d, a.eps[s], a.eps_mode[s]));
+          }
         }
       }
       __syncwarp();
-      for (int ng = 0; ng < a.ngroups; ng++) {
+      const int npass = a.resident ? 1 : a.ngroups;
+      for (int ng = 0; ng < npass; ng++) {
         int s = 0, koff = 0;
+        float4 vn[8];      // the loads of the next slab fly while the current one is converted
+        auto issue = [&](int ss, int kk) {
+          const float* xs = a.x[ss] + kk + 4 * c16;
+#pragma unroll
+          for (int u = 0; u < 8; u++) {
+            int64_t row = row0 + 2 * u + hr;
+            row = row < a.R ? row : a.R - 1;
+            vn[u] = __ldg(reinterpret_cast<const float4*>(xs + (size_t)row * a.ldx[ss]));
+          }
+        };
+        issue(0, 0);
 #pragma unroll 1
         for (int ks = 0; ks < KS; ks++, it++) {
           while (koff >= a.d[s]) { koff -= a.d[s]; s++; }
@@ -173,36 +220,32 @@ __global__ void __launch_bounds__(G_THREADS, 1) k_tc_lin(const GemmArgs a) {
             g4 = __ldg(reinterpret_cast<const float4*>(a.gamma[s] + koff + 4 * c16));
             b4 = __ldg(reinterpret_cast<const float4*>(a.beta[s] + koff + 4 * c16));
           }
-          const float* xs = a.x[s] + koff + 4 * c16;
-          const int ldx = a.ldx[s];
+          float4 v[8];
+#pragma unroll
+          for (int u = 0; u < 8; u++) v[u] = vn[u];
+          if (ks + 1 < KS) {
+            int s2 = s, k2 = koff + 64;
+            while (k2 >= a.d[s2]) { k2 -= a.d[s2]; s2++; }
+            issue(s2, k2);
+          }
           uint8_t* A = sm + G_OFF_A + st * SLAB;
           mbar_wait(BAR(GB_AEMPTY + st), ph ^ 1);
-#pragma unroll 1
-          for (int i0 = 0; i0 < 32; i0 += 16) {
-            float4 v[8];
 #pragma unroll
-            for (int u = 0; u < 8; u++) {
-              int64_t row = row0 + i0 + 2 * u + hr;
-              row = row < a.R ? row : a.R - 1;
-              v[u] = __ldg(reinterpret_cast<const float4*>(xs + (size_t)row * ldx));
+          for (int u = 0; u < 8; u++) {
+            const int r = 16 * pw + 2 * u + hr;
+            float4 t = v[u];
+            if (ln) {
+              const float2 ms = stats[s * 128 + r];
+              t.x = (t.x - ms.x) * ms.y * g4.x + b4.x;
+              t.y = (t.y - ms.x) * ms.y * g4.y + b4.y;
+              t.z = (t.z - ms.x) * ms.y * g4.z + b4.z;
+              t.w = (t.w - ms.x) * ms.y * g4.w + b4.w;
             }
-#pragma unroll
-            for (int u = 0; u < 8; u++) {
-              const int r = 32 * q + i0 + 2 * u + hr;
-              float4 t = v[u];
-              if (ln) {
-                const float2 ms = stats[s * 128 + r];
-                t.x = (t.x - ms.x) * ms.y * g4.x + b4.x;
-                t.y = (t.y - ms.x) * ms.y * g4.y + b4.y;
-                t.z = (t.z - ms.x) * ms.y * g4.z + b4.z;
-                t.w = (t.w - ms.x) * ms.y * g4.w + b4.w;
-              }
-              if (row0 + i0 + 2 * u + hr >= a.R) t = f4zero();
-              uint2 pk;
-              pk.x = pack_bf16(t.x, t.y);
-              pk.y = pack_bf16(t.z, t.w);
-              *reinterpret_cast<uint2*>(A + sw_off(r, 4 * c16)) = pk;
-            }
+            if (row0 + 2 * u + hr >= a.R) t = f4zero();
+            uint2 pk;
+            pk.x = pack_bf16(t.x, t.y);
+            pk.y = pack_bf16(t.z, t.w);
+            *reinterpret_cast<uint2*>(A + sw_off(r, 4 * c16)) = pk;
           }
           fence_async_smem();
           __syncwarp();
@@ -232,48 +275,52 @@ __global__ void __launch_bounds__(G_THREADS, 1) k_tc_lin(const GemmArgs a) {
         const uint32_t buf = item & 1, ph = (item >> 1) & 1;
         mbar_wait(BAR(GB_ACCFULL + buf), ph);
         tc_fence_after();
-        const int nsteps = 4 * NG;      // (hh, 64-column chunk) steps
+        const int nch = 2 * NG;      // 64-column chunks
 #pragma unroll 1
-        for (int stp = 0; stp < nsteps; stp++) {
-          const int hh = stp & 1, ch = stp >> 1;
+        for (int ch = 0; ch < nch; ch++) {
           const int col = ng * NG * 128 + 64 * ch + cq;      // + 8 n
-          uint32_t dreg[32];
-          TC_LD_FRAG64(tmem + buf * 256 + lane_base + ((uint32_t)(16 * hh) << 16) + 64 * ch, dreg);
-          tc_wait_ld();
-          if (stp == nsteps - 1) {
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(BAR(GB_ACCFREE + buf));
-          }
 #pragma unroll
-          for (int h2 = 0; h2 < 2; h2++) {
-            const int k = 2 * hh + h2;
-            const int64_t row = row0 + 16 * hh + 8 * h2 + qr;
-            float2 v[8];
-#pragma unroll
-            for (int n = 0; n < 8; n++) {
-              v[n] = make_float2(__uint_as_float(dreg[4 * n + 2 * h2]), __uint_as_float(dreg[4 * n + 2 * h2 + 1]));
-              if (a.bias) {
-                const float2 b = __ldg(reinterpret_cast<const float2*>(a.bias + col + 8 * n));
-                v[n].x += b.x; v[n].y += b.y;
-              }
+          for (int hh = 0; hh < 2; hh++) {
+            uint32_t dreg[32];
+            TC_LD_FRAG64(tmem + buf * 256 + lane_base + ((uint32_t)(16 * hh) << 16) + 64 * ch, dreg);
+            tc_wait_ld();
+            if (ch == nch - 1 && hh == 1) {
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(BAR(GB_ACCFREE + buf));
             }
-            for (int j = 0; j < a.nadd; j++) {
-              const float* ap = a.add[j] + (size_t)arow[j][k] * a.lda[j] + col;
+#pragma unroll
+            for (int h2 = 0; h2 < 2; h2++) {
+              const int k = 2 * hh + h2;
+              const int64_t row = row0 + 16 * hh + 8 * h2 + qr;
+              float2 v[8];
 #pragma unroll
               for (int n = 0; n < 8; n++) {
-                const float2 t = __ldg(reinterpret_cast<const float2*>(ap + 8 * n));
-                v[n].x += t.x; v[n].y += t.y;
+                v[n] = make_float2(__uint_as_float(dreg[4 * n + 2 * h2]), __uint_as_float(dreg[4 * n + 2 * h2 + 1]));
+                if (a.bias) {
+                  const float2 b = __ldg(reinterpret_cast<const float2*>(a.bias + col + 8 * n));
+                  v[n].x += b.x; v[n].y += b.y;
+                }
               }
-            }
-            if (a.relu) {
 #pragma unroll
-              for (int n = 0; n < 8; n++) { v[n].x = fmaxf(v[n].x, 0.f); v[n].y = fmaxf(v[n].y, 0.f); }
-            }
-            if (row < a.R) {
-              float* o = a.out + (size_t)row * a.ldo + col;
+              for (int j = 0; j < 4; j++) {
+                if (j >= a.nadd) break;
+                const float* ap = a.add[j] + (size_t)arow[j][k] * a.lda[j] + col;
 #pragma unroll
-              for (int n = 0; n < 8; n++) *reinterpret_cast<float2*>(o + 8 * n) = v[n];
+                for (int n = 0; n < 8; n++) {
+                  const float2 t = __ldg(reinterpret_cast<const float2*>(ap + 8 * n));
+                  v[n].x += t.x; v[n].y += t.y;
+                }
+              }
+              if (a.relu) {
+#pragma unroll
+                for (int n = 0; n < 8; n++) { v[n].x = fmaxf(v[n].x, 0.f); v[n].y = fmaxf(v[n].y, 0.f); }
+              }
+              if (row < a.R) {
+                float* o = a.out + (size_t)row * a.ldo + col;
+#pragma unroll
+                for (int n = 0; n < 8; n++) *reinterpret_cast<float2*>(o + 8 * n) = v[n];
+              }
             }
           }
         }
@@ -282,7 +329,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) k_tc_lin(const GemmArgs a) {
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 8) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+  if (warp == W_MMA) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
 }
 
 // packed[((ng * KS + ks) * NG + nb) * 8192 + swizzled(n, k)] = bf16(W[(ks*64 + k) * ldw + (ng*NG + nb)*128 + n]),
@@ -330,7 +377,7 @@ bool tc_lin_supported(const LinArgs& a) {
   int K = 0;
   for (int s = 0; s < a.nsrc; s++) {
     if (a.src[s].d <= 0 || (a.src[s].d & 63) || (a.src[s].ldx & 3)) return false;
-    if (a.src[s].gamma && (a.src[s].d & 127)) return false;
+    if (a.src[s].gamma && ((a.src[s].d & 127) || a.src[s].d > 512)) return false;
     K += a.src[s].d;
   }
   if (K < 128 || (a.ldo & 1)) return false;
@@ -367,6 +414,7 @@ int launch_linear_tc(gnb_ctx* ctx, const LinArgs& a) {
   g.NG = (nblk % 2 == 0) ? 2 : 1;
   g.ngroups = nblk / g.NG;
   g.num_tiles = (int)ceil_div(a.R, TM);
+  g.resident = (g.KS <= NA - 2 && g.ngroups > 1) ? 1 : 0;
   g.bias = a.bias; g.nadd = a.nadd; g.relu = a.relu; g.out = a.out;
   for (int j = 0; j < a.nadd; j++) { g.add[j] = a.add[j].a; g.add_idx[j] = a.add[j].idx; g.lda[j] = a.add[j].lda; }
   // packed bf16 weights: built on first use, cached per (model, weight block)
@@ -388,7 +436,11 @@ int launch_linear_tc(gnb_ctx* ctx, const LinArgs& a) {
   }
   g.wpack = itc->second;
   double bytes = 4.0 * ((double)a.R * (K + (double)a.Nout * (1 + a.nadd))) + 2.0 * K * a.Nout;
-  Launch L(ctx, "tc_linear", bytes, 2.0 * a.R * K * a.Nout);
+  // profile tag per layer shape (interned: Launch keeps the pointer)
+  static std::map<std::pair<int, int>, std::string> names;
+  auto nit = names.find({K, a.Nout});
+  if (nit == names.end()) nit = names.emplace(std::make_pair(K, a.Nout), "tc_linear_k" + std::to_string(K) + "_n" + std::to_string(a.Nout)).first;
+  Launch L(ctx, ctx->profiling && getenv("GNB_PROFILE_SHAPES") ? nit->second.c_str() : "tc_linear", bytes, 2.0 * a.R * K * a.Nout);
   const int grid = g.num_tiles < ctx->sm_count ? g.num_tiles : ctx->sm_count;
   k_tc_lin<<<grid, G_THREADS, G_SMEM, ctx->stream>>>(g);
   GNB_CUDA(cudaGetLastError());
