@@ -15,6 +15,7 @@ struct LinSrc {
   const float* beta;
   float eps;
   int eps_mode;
+  int x_bf16;          // tensor-core path only: x is a bf16 [R][ldx] matrix (the hidden activation of an FFN), no LayerNorm
 };
 
 // Row-gathered addend of the epilogue: out[r][:] += a[idx ? idx[r] : r][:]
@@ -36,6 +37,7 @@ struct LinArgs {
   int relu;
   float* out;     // [R][ldo]
   int ldo;
+  int out_bf16;   // tensor-core path only: out is a bf16 [R][ldo] matrix
 };
 
 // out = act( sum_s LN_s(x_s) W_s + bias + sum_j add_j[idx_j] )     fp32 CUDA cores

@@ -374,7 +374,7 @@ int launch_linear(gnb_ctx* ctx, const LinArgs& a) {
 }
 
 LinSrc mk_src(const float* x, int d, const float* W, const gnb_ln_params* ln) {
-  LinSrc s;
+  LinSrc s{};
   s.x = x; s.d = d; s.ldx = d; s.W = W;
   s.gamma = ln ? ln->gamma : nullptr;
   s.beta = ln ? ln->beta : nullptr;
@@ -636,20 +636,32 @@ static int run_block_narrow(gnb_ctx* ctx, const gnb_graph* g, const LayerW& w, F
 int run_ffn_residual_fp32(gnb_ctx* ctx, int64_t R, int d, const gnb_ffn_params& f, const gnb_ln_params& ln2,
                           const float* x, const float* h, float* y) {
   if (R <= 0) return GNB_OK;
+  // tensor-core precision modes: both Dense layers on the generic tcgen05 kernel with the hidden activation kept in bf16
+  // (exactly what the down-projection's MMA consumes anyway: halves the HBM round trip of the 4d-wide hidden rows)
+  bool bf16_hidden = false;
+  if (ctx->use_tc_lin) {
+    LinArgs t1{}, t2{};
+    t1.R = R; t1.Nout = 4 * d; t1.nsrc = 1; t1.ldo = 4 * d; t1.src[0] = mk_src(x, d, f.W1, &ln2);
+    t2.R = R; t2.Nout = d; t2.nsrc = 1; t2.ldo = d; t2.src[0] = mk_src(x, 4 * d, f.W2, nullptr); t2.src[0].x_bf16 = 1;
+    t2.nadd = 2; t2.add[0] = LinAdd{x, nullptr, d}; t2.add[1] = LinAdd{h, nullptr, d};
+    bf16_hidden = tc_lin_supported(t1) && tc_lin_supported(t2);
+  }
   const size_t cap_bytes = (size_t)1 << 30;  // hidden scratch per chunk
-  int64_t chunk = (int64_t)(cap_bytes / ((size_t)4 * d * sizeof(float)));
+  const size_t esz = bf16_hidden ? 2 : 4;
+  int64_t chunk = (int64_t)(cap_bytes / ((size_t)4 * d * esz));
   if (chunk < 1024) chunk = 1024;
   if (chunk > R) chunk = R;
   int rc = GNB_OK;
-  float* hid = arena_ptr<float>(ctx->arena, (size_t)chunk * 4 * d, &rc);
+  float* hid = reinterpret_cast<float*>(arena_ptr<char>(ctx->arena, (size_t)chunk * 4 * d * esz, &rc));
   if (rc != GNB_OK) return rc;
   for (int64_t r0 = 0; r0 < R; r0 += chunk) {
     int64_t rows = R - r0 < chunk ? R - r0 : chunk;
+    // a short last chunk falls back to fp32 hidden rows only if the tensor-core kernel refuses it (R < 256): the buffer is
+    // large enough either way when chunk == R, otherwise rows == chunk except for the tail
     LinArgs l1{};
     l1.R = rows; l1.Nout = 4 * d; l1.ldw = 4 * d; l1.nsrc = 1; l1.ldo = 4 * d;
     l1.src[0] = mk_src(x + (size_t)r0 * d, d, f.W1, &ln2);
     l1.bias = f.b1; l1.relu = 1; l1.out = hid;
-    GNB_TRY(launch_linear(ctx, l1));
     LinArgs l2{};
     l2.R = rows; l2.Nout = d; l2.ldw = d; l2.nsrc = 1; l2.ldo = d;
     l2.src[0] = mk_src(hid, 4 * d, f.W2, nullptr);
@@ -657,6 +669,17 @@ int run_ffn_residual_fp32(gnb_ctx* ctx, int64_t R, int d, const gnb_ffn_params& 
     l2.add[l2.nadd++] = LinAdd{x + (size_t)r0 * d, nullptr, d};
     l2.add[l2.nadd++] = LinAdd{h + (size_t)r0 * d, nullptr, d};
     l2.out = y + (size_t)r0 * d;
+    bool bf = bf16_hidden;
+    if (bf) {
+      l1.out_bf16 = 1; l2.src[0].x_bf16 = 1;
+      bf = tc_lin_supported(l1) && tc_lin_supported(l2);
+      if (!bf) { l1.out_bf16 = 0; l2.src[0].x_bf16 = 0; }      // tail chunk too short for the tensor-core kernel
+    }
+    if (!bf && bf16_hidden && (size_t)rows * 4 * d * 4 > (size_t)chunk * 4 * d * esz) {
+      gnb_set_error("run_ffn_residual: hidden scratch too small for an fp32 tail chunk");
+      return GNB_ERR_INVALID;
+    }
+    GNB_TRY(launch_linear(ctx, l1));
     GNB_TRY(launch_linear(ctx, l2));
   }
   return GNB_OK;

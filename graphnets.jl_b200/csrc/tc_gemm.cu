@@ -9,13 +9,13 @@
 // launch per Dense, activations make an HBM round trip between launches.
 //
 // Work item = (128-row tile, group of NG <= 2 output blocks of 128 columns); a persistent CTA walks the row tiles and, inside
-// a tile, the column groups (the LayerNorm statistics of the tile are computed once and kept in shared memory).  14 warps:
+// a tile, the column groups (the LayerNorm statistics of the tile are computed once and kept in shared memory).  18 warps:
 //   warps 4-11 A producers : fp32 rows -> LayerNorm (two-pass statistics, affine applied here) -> bf16 -> 128B-swizzled K-major
 //                            64-wide slabs (16 KB) through a 6-stage ring; K <= 256: the slabs of a row tile are produced
 //                            once and reused by all column groups
-//   warp 13    W loader    : cp.async.bulk of pre-packed bf16 slabs (NG x 16 KB per K step) through a 3-stage ring
-//   warp 12    MMA issuer  : per K step 4 UMMAs (K = 16) per output block into TMEM (2 accumulator sets x 256 columns)
-//   warps 0-3  drain       : accumulator fragments -> + bias + gathered addends -> relu -> sector-exact fp32 stores
+//   warp 17    W loader    : cp.async.bulk of pre-packed bf16 slabs (NG x 16 KB per K step) through a 3-stage ring
+//   warp 16    MMA issuer  : per K step 4 UMMAs (K = 16) per output block into TMEM (2 accumulator sets x 256 columns)
+//   warps 0-3, 12-15 drain : accumulator fragments -> + bias + gathered addends -> relu -> sector-exact fp32 stores
 #include "tc_ptx.cuh"
 #include "tc_gemm.cuh"
 #include <map>
@@ -34,22 +34,22 @@ constexpr int G_OFF_W = NA * SLAB;                    // stages of 2 slabs
 constexpr int G_OFF_STAT = G_OFF_W + NW * 2 * SLAB;   // float2 stats[3][128]
 constexpr int G_OFF_BAR = G_OFF_STAT + 3 * 128 * 8;
 constexpr int G_SMEM = G_OFF_BAR + 32 * 8 + 16 + 1024;
-constexpr int G_THREADS = 14 * 32;
-constexpr int W_MMA = 12, W_LOAD = 13;      // warps 0-3 drain, 4-11 A producers
+constexpr int G_THREADS = 18 * 32;
+constexpr int W_MMA = 16, W_LOAD = 17;      // warps 0-3 and 12-15 drain (TMEM lane quadrant = warp % 4), 4-11 A producers
 enum { GB_WFULL = 0, GB_WEMPTY = 3, GB_AFULL = 6, GB_AEMPTY = 12, GB_ACCFULL = 18, GB_ACCFREE = 20 };
 
 struct GemmArgs {
   int64_t R;
   int Nout, ldo;
   int nsrc;
-  const float* x[3]; int ldx[3]; int d[3];
+  const float* x[3]; int ldx[3]; int d[3]; int xbf[3];      // xbf: the source is bf16 (ldx in elements)
   const float* gamma[3]; const float* beta[3]; float eps[3]; int eps_mode[3];
   int KS;                         // total K / 64
   const __nv_bfloat16* wpack;     // [n group][K step][block in group][8192 elements]
   const float* bias;
   int nadd;
   const float* add[4]; const int32_t* add_idx[4]; int lda[4];
-  int relu;
+  int relu, out_bf16;
   float* out;
   int num_tiles, ngroups, NG;     // NG output blocks per group (1 or 2)
   int resident;                   // the A slabs of a row tile are produced once and reused by every column group (KS <= NA - 2)
@@ -69,7 +69,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) k_tc_lin(const GemmArgs a) {
   if (tid == 0) {
     for (int i = 0; i < NW; i++) { mbar_init(BAR(GB_WFULL + i), 1); mbar_init(BAR(GB_WEMPTY + i), 1); }
     for (int i = 0; i < NA; i++) { mbar_init(BAR(GB_AFULL + i), 8); mbar_init(BAR(GB_AEMPTY + i), 1); }
-    for (int i = 0; i < 2; i++) { mbar_init(BAR(GB_ACCFULL + i), 1); mbar_init(BAR(GB_ACCFREE + i), 4); }
+    for (int i = 0; i < 2; i++) { mbar_init(BAR(GB_ACCFULL + i), 1); mbar_init(BAR(GB_ACCFREE + i), 8); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == W_MMA) {
@@ -81,6 +81,9 @@ __global__ void __launch_bounds__(G_THREADS, 1) k_tc_lin(const GemmArgs a) {
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
   const int KS = a.KS, NG = a.NG;
+  // every CTA walks the K slabs starting at a different offset: the CTAs run in lock step, and without the rotation all of
+  // them stream the same weight slab from the same L2 slice at the same time
+  const int rot = (int)((blockIdx.x * 5u) % (uint32_t)KS);
 
   if (warp == W_LOAD) {
     // ===================================================== weight loader
@@ -95,7 +98,8 @@ __global__ void __launch_bounds__(G_THREADS, 1) k_tc_lin(const GemmArgs a) {
           if (elect_one()) {
             const uint32_t nb = (uint32_t)(NG * SLAB);
             mbar_expect_tx(BAR(GB_WFULL + st), nb);
-            bulk_g2s(base + G_OFF_W + st * 2 * SLAB, src + (size_t)ks * NG * SLAB, nb, BAR(GB_WFULL + st));
+            const int kr = ks + rot < KS ? ks + rot : ks + rot - KS;
+            bulk_g2s(base + G_OFF_W + st * 2 * SLAB, src + (size_t)kr * NG * SLAB, nb, BAR(GB_WFULL + st));
           }
           __syncwarp();
         }
@@ -133,7 +137,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) k_tc_lin(const GemmArgs a) {
         }
       }
     }
-  } else if (warp >= 4) {
+  } else if (warp >= 4 && warp < 12) {
     // ===================================================== A producers: warp pw owns rows 16 pw .. 16 pw + 15 of the tile
     const int pw = warp - 4;
     const int hr = lane >> 4, c16 = lane & 15;      // two rows per load instruction, 16 lanes x 16 B per row slab
@@ -198,23 +202,40 @@ __global__ void __launch_bounds__(G_THREADS, 1) k_tc_lin(const GemmArgs a) {
       __syncwarp();
       const int npass = a.resident ? 1 : a.ngroups;
       for (int ng = 0; ng < npass; ng++) {
-        int s = 0, koff = 0;
         float4 vn[8];      // the loads of the next slab fly while the current one is converted
+        // K slab ks of this CTA's (rotated) order -> (source, offset inside the source)
+        auto locate = [&](int ks, int& ss, int& kk) {
+          const int kr = ks + rot < KS ? ks + rot : ks + rot - KS;
+          ss = 0; kk = kr * 64;
+          while (kk >= a.d[ss]) { kk -= a.d[ss]; ss++; }
+        };
         auto issue = [&](int ss, int kk) {
-          const float* xs = a.x[ss] + kk + 4 * c16;
+          if (a.xbf[ss]) {
+            const __nv_bfloat16* xs = reinterpret_cast<const __nv_bfloat16*>(a.x[ss]) + kk + 8 * (lane & 7);
 #pragma unroll
-          for (int u = 0; u < 8; u++) {
-            int64_t row = row0 + 2 * u + hr;
-            row = row < a.R ? row : a.R - 1;
-            vn[u] = __ldg(reinterpret_cast<const float4*>(xs + (size_t)row * a.ldx[ss]));
+            for (int u = 0; u < 4; u++) {
+              int64_t row = row0 + 4 * u + (lane >> 3);
+              row = row < a.R ? row : a.R - 1;
+              vn[u] = __ldg(reinterpret_cast<const float4*>(xs + (size_t)row * a.ldx[ss]));
+            }
+          } else {
+            const float* xs = a.x[ss] + kk + 4 * c16;
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+              int64_t row = row0 + 2 * u + hr;
+              row = row < a.R ? row : a.R - 1;
+              vn[u] = __ldg(reinterpret_cast<const float4*>(xs + (size_t)row * a.ldx[ss]));
+            }
           }
         };
-        issue(0, 0);
+        int s, koff;
+        locate(0, s, koff);
+        issue(s, koff);
 #pragma unroll 1
         for (int ks = 0; ks < KS; ks++, it++) {
-          while (koff >= a.d[s]) { koff -= a.d[s]; s++; }
+          locate(ks, s, koff);
           const uint32_t st = it % NA, ph = (it / NA) & 1;
-          const bool ln = a.gamma[s] != nullptr;
+          const bool ln = a.gamma[s] != nullptr, bf = a.xbf[s] != 0;
           float4 g4 = make_float4(1.f, 1.f, 1.f, 1.f), b4 = make_float4(0.f, 0.f, 0.f, 0.f);
           if (ln) {
             g4 = __ldg(reinterpret_cast<const float4*>(a.gamma[s] + koff + 4 * c16));
@@ -224,67 +245,81 @@ __global__ void __launch_bounds__(G_THREADS, 1) k_tc_lin(const GemmArgs a) {
 #pragma unroll
           for (int u = 0; u < 8; u++) v[u] = vn[u];
           if (ks + 1 < KS) {
-            int s2 = s, k2 = koff + 64;
-            while (k2 >= a.d[s2]) { k2 -= a.d[s2]; s2++; }
+            int s2, k2;
+            locate(ks + 1, s2, k2);
             issue(s2, k2);
           }
           uint8_t* A = sm + G_OFF_A + st * SLAB;
           mbar_wait(BAR(GB_AEMPTY + st), ph ^ 1);
+          if (bf) {
 #pragma unroll
-          for (int u = 0; u < 8; u++) {
-            const int r = 16 * pw + 2 * u + hr;
-            float4 t = v[u];
-            if (ln) {
-              const float2 ms = stats[s * 128 + r];
-              t.x = (t.x - ms.x) * ms.y * g4.x + b4.x;
-              t.y = (t.y - ms.x) * ms.y * g4.y + b4.y;
-              t.z = (t.z - ms.x) * ms.y * g4.z + b4.z;
-              t.w = (t.w - ms.x) * ms.y * g4.w + b4.w;
+            for (int u = 0; u < 4; u++) {
+              const int r = 16 * pw + 4 * u + (lane >> 3);
+              float4 t = v[u];
+              if (row0 + 4 * u + (lane >> 3) >= a.R) t = f4zero();
+              *reinterpret_cast<float4*>(A + r * 128 + (((lane & 7) ^ (r & 7)) << 4)) = t;
             }
-            if (row0 + 2 * u + hr >= a.R) t = f4zero();
-            uint2 pk;
-            pk.x = pack_bf16(t.x, t.y);
-            pk.y = pack_bf16(t.z, t.w);
-            *reinterpret_cast<uint2*>(A + sw_off(r, 4 * c16)) = pk;
+          } else {
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+              const int r = 16 * pw + 2 * u + hr;
+              float4 t = v[u];
+              if (ln) {
+                const float2 ms = stats[s * 128 + r];
+                t.x = (t.x - ms.x) * ms.y * g4.x + b4.x;
+                t.y = (t.y - ms.x) * ms.y * g4.y + b4.y;
+                t.z = (t.z - ms.x) * ms.y * g4.z + b4.z;
+                t.w = (t.w - ms.x) * ms.y * g4.w + b4.w;
+              }
+              if (row0 + 2 * u + hr >= a.R) t = f4zero();
+              uint2 pk;
+              pk.x = pack_bf16(t.x, t.y);
+              pk.y = pack_bf16(t.z, t.w);
+              *reinterpret_cast<uint2*>(A + sw_off(r, 4 * c16)) = pk;
+            }
           }
           fence_async_smem();
           __syncwarp();
           if (lane == 0) mbar_arrive(BAR(GB_AFULL + st));
-          koff += 64;
         }
       }
     }
-  } else {
-    // ===================================================== drain (TMEM lane quadrant = warp), accumulator-fragment layout:
-    // every 4 lanes own one 32 B sector of a row
-    const uint32_t lane_base = ((uint32_t)(warp * 32)) << 16;
+  } else if (warp < 4 || (warp >= 12 && warp < 16)) {
+    // ===================================================== drain (TMEM lane quadrant = warp % 4; the two warps of a quadrant
+    // split the 64-column chunks of the column group), accumulator-fragment layout: every 4 lanes own one 32 B sector of a row
+    const int dq = warp & 3, dh = warp >= 12 ? 1 : 0;
+    const uint32_t lane_base = ((uint32_t)(dq * 32)) << 16;
     const int qr = lane >> 2, cq = 2 * (lane & 3);
     uint32_t item = 0;
     for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
-      const int64_t row0 = (int64_t)tile * TM + 32 * warp;
+      const int64_t row0 = (int64_t)tile * TM + 32 * dq;
       // the 4 rows of this lane: 16 hh + 8 h2 + qr
-      int64_t arow[4][4];
+      int32_t arow[4][4];      // gathered addend rows (row counts fit 31 bits: checked by the lowering)
 #pragma unroll
       for (int k = 0; k < 4; k++) {
         int64_t r = row0 + 16 * (k >> 1) + 8 * (k & 1) + qr;
         r = r < a.R ? r : a.R - 1;
 #pragma unroll
-        for (int j = 0; j < 4; j++) arow[j][k] = (j < a.nadd && a.add_idx[j]) ? (int64_t)__ldg(a.add_idx[j] + r) : r;
+        for (int j = 0; j < 4; j++) arow[j][k] = (j < a.nadd && a.add_idx[j]) ? __ldg(a.add_idx[j] + r) : (int32_t)r;
       }
       for (int ng = 0; ng < a.ngroups; ng++, item++) {
         const uint32_t buf = item & 1, ph = (item >> 1) & 1;
         mbar_wait(BAR(GB_ACCFULL + buf), ph);
         tc_fence_after();
-        const int nch = 2 * NG;      // 64-column chunks
+        const int nch = NG;      // 64-column chunks of this warp: [dh * NG, dh * NG + NG)
 #pragma unroll 1
-        for (int ch = 0; ch < nch; ch++) {
+        for (int c = 0; c < nch; c++) {
+          const int ch = dh * NG + c;
           const int col = ng * NG * 128 + 64 * ch + cq;      // + 8 n
+          float2 bias[8];
+#pragma unroll
+          for (int n = 0; n < 8; n++) bias[n] = a.bias ? __ldg(reinterpret_cast<const float2*>(a.bias + col + 8 * n)) : make_float2(0.f, 0.f);
 #pragma unroll
           for (int hh = 0; hh < 2; hh++) {
             uint32_t dreg[32];
             TC_LD_FRAG64(tmem + buf * 256 + lane_base + ((uint32_t)(16 * hh) << 16) + 64 * ch, dreg);
             tc_wait_ld();
-            if (ch == nch - 1 && hh == 1) {
+            if (c == nch - 1 && hh == 1) {
               tc_fence_before();
               __syncwarp();
               if (lane == 0) mbar_arrive(BAR(GB_ACCFREE + buf));
@@ -295,17 +330,12 @@ __global__ void __launch_bounds__(G_THREADS, 1) k_tc_lin(const GemmArgs a) {
               const int64_t row = row0 + 16 * hh + 8 * h2 + qr;
               float2 v[8];
 #pragma unroll
-              for (int n = 0; n < 8; n++) {
-                v[n] = make_float2(__uint_as_float(dreg[4 * n + 2 * h2]), __uint_as_float(dreg[4 * n + 2 * h2 + 1]));
-                if (a.bias) {
-                  const float2 b = __ldg(reinterpret_cast<const float2*>(a.bias + col + 8 * n));
-                  v[n].x += b.x; v[n].y += b.y;
-                }
-              }
+              for (int n = 0; n < 8; n++)
+                v[n] = make_float2(__uint_as_float(dreg[4 * n + 2 * h2]) + bias[n].x, __uint_as_float(dreg[4 * n + 2 * h2 + 1]) + bias[n].y);
 #pragma unroll
               for (int j = 0; j < 4; j++) {
                 if (j >= a.nadd) break;
-                const float* ap = a.add[j] + (size_t)arow[j][k] * a.lda[j] + col;
+                const float* ap = a.add[j] + (size_t)(uint32_t)arow[j][k] * a.lda[j] + col;
 #pragma unroll
                 for (int n = 0; n < 8; n++) {
                   const float2 t = __ldg(reinterpret_cast<const float2*>(ap + 8 * n));
@@ -317,9 +347,15 @@ __global__ void __launch_bounds__(G_THREADS, 1) k_tc_lin(const GemmArgs a) {
                 for (int n = 0; n < 8; n++) { v[n].x = fmaxf(v[n].x, 0.f); v[n].y = fmaxf(v[n].y, 0.f); }
               }
               if (row < a.R) {
-                float* o = a.out + (size_t)row * a.ldo + col;
+                if (a.out_bf16) {
+                  __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(a.out) + (size_t)row * a.ldo + col;
 #pragma unroll
-                for (int n = 0; n < 8; n++) *reinterpret_cast<float2*>(o + 8 * n) = v[n];
+                  for (int n = 0; n < 8; n++) *reinterpret_cast<uint32_t*>(o + 8 * n) = pack_bf16(v[n].x, v[n].y);
+                } else {
+                  float* o = a.out + (size_t)row * a.ldo + col;
+#pragma unroll
+                  for (int n = 0; n < 8; n++) *reinterpret_cast<float2*>(o + 8 * n) = v[n];
+                }
               }
             }
           }
@@ -373,10 +409,11 @@ void tc_lin_cache_free(void* cache) {
 }
 
 bool tc_lin_supported(const LinArgs& a) {
-  if (a.R < 256 || a.Nout < 128 || (a.Nout & 127) || a.nsrc < 1) return false;
+  if (a.R < 256 || a.R > 0x7fffffffLL || a.Nout < 128 || (a.Nout & 127) || a.nsrc < 1) return false;
   int K = 0;
   for (int s = 0; s < a.nsrc; s++) {
-    if (a.src[s].d <= 0 || (a.src[s].d & 63) || (a.src[s].ldx & 3)) return false;
+    if (a.src[s].d <= 0 || (a.src[s].d & 63) || (a.src[s].ldx & (a.src[s].x_bf16 ? 7 : 3))) return false;
+    if (a.src[s].x_bf16 && a.src[s].gamma) return false;
     if (a.src[s].gamma && ((a.src[s].d & 127) || a.src[s].d > 512)) return false;
     K += a.src[s].d;
   }
@@ -402,7 +439,7 @@ int launch_linear_tc(gnb_ctx* ctx, const LinArgs& a) {
   ps.nsrc = a.nsrc;
   for (int s = 0; s < 3; s++) { ps.d[s] = 1 << 30; }
   for (int s = 0; s < a.nsrc; s++) {
-    g.x[s] = a.src[s].x; g.ldx[s] = a.src[s].ldx; g.d[s] = a.src[s].d;
+    g.x[s] = a.src[s].x; g.ldx[s] = a.src[s].ldx; g.d[s] = a.src[s].d; g.xbf[s] = a.src[s].x_bf16;
     g.gamma[s] = a.src[s].gamma; g.beta[s] = a.src[s].beta; g.eps[s] = a.src[s].eps; g.eps_mode[s] = a.src[s].eps_mode;
     key.W[s] = a.src[s].W; key.d[s] = a.src[s].d;
     ps.W[s] = a.src[s].W; ps.d[s] = a.src[s].d;
@@ -415,7 +452,7 @@ int launch_linear_tc(gnb_ctx* ctx, const LinArgs& a) {
   g.ngroups = nblk / g.NG;
   g.num_tiles = (int)ceil_div(a.R, TM);
   g.resident = (g.KS <= NA - 2 && g.ngroups > 1) ? 1 : 0;
-  g.bias = a.bias; g.nadd = a.nadd; g.relu = a.relu; g.out = a.out;
+  g.bias = a.bias; g.nadd = a.nadd; g.relu = a.relu; g.out = a.out; g.out_bf16 = a.out_bf16;
   for (int j = 0; j < a.nadd; j++) { g.add[j] = a.add[j].a; g.add_idx[j] = a.add[j].idx; g.lda[j] = a.add[j].lda; }
   // packed bf16 weights: built on first use, cached per (model, weight block)
   if (!ctx->lin_cache) ctx->lin_cache = new PackCache();
@@ -435,7 +472,8 @@ int launch_linear_tc(gnb_ctx* ctx, const LinArgs& a) {
     itc = cache->m.emplace(key, dst).first;
   }
   g.wpack = itc->second;
-  double bytes = 4.0 * ((double)a.R * (K + (double)a.Nout * (1 + a.nadd))) + 2.0 * K * a.Nout;
+  double bytes = 2.0 * K * a.Nout + 4.0 * (double)a.R * a.Nout * a.nadd + (a.out_bf16 ? 2.0 : 4.0) * a.R * a.Nout;
+  for (int s = 0; s < a.nsrc; s++) bytes += (a.src[s].x_bf16 ? 2.0 : 4.0) * a.R * a.src[s].d;
   // profile tag per layer shape (interned: Launch keeps the pointer)
   static std::map<std::pair<int, int>, std::string> names;
   auto nit = names.find({K, a.Nout});
