@@ -63,10 +63,32 @@ struct gnb_ctx {
   Arena staging;
   // generic bf16 tensor-core linear layers (tc_gemm.cu): enabled per forward by the precision mode; packed weights are
   // cached per (model id, weight block)
+  // one-time per-device setup (cudaFuncSetAttribute, memory-pool attributes) is tracked per context, not per process:
+  // a process may own one context per GPU
+  uint64_t once_mask = 0;
+  cudaEvent_t done_ev = nullptr;      // end of this context's last forward (cross-context serialisation, model.cu)
+  // host-buffer forward (gnb_model_forward_host): PCIe copies overlapped with compute on a second stream.  The edge input is
+  // uploaded in row chunks and the first consumer (the encoder's edge kernel) starts on a chunk as soon as it has landed; the
+  // edge output is downloaded as soon as the decoder's edge kernel has written it, under the node / graph kernels.
+  struct HostPipe {
+    cudaStream_t copy = nullptr;
+    cudaEvent_t ev_chunk[8] = {}, ev_ready = nullptr, ev_in = nullptr;
+    const float* d_ef = nullptr; int64_t ef_rows = 0; int nchunks = 0; bool ef_pending = false;      // upload in flight
+    const float* d_out_ef = nullptr; float* h_out_ef = nullptr; size_t out_bytes = 0; bool out_pending = false, out_early = false;
+  } pipe;
   bool use_tc_lin = false;
   uint64_t cur_model_id = 0;
   void* lin_cache = nullptr;
 };
+
+enum { ONCE_EDGE5 = 0, ONCE_PROJ_LN2, ONCE_PROJ_AGG1, ONCE_PROJ_OTHER, ONCE_TC_LIN, ONCE_WIDE, ONCE_NARROW2, ONCE_POOL };
+// true exactly once per (context, key)
+static inline bool ctx_first(gnb_ctx* c, int key) {
+  const uint64_t b = 1ull << key;
+  if (c->once_mask & b) return false;
+  c->once_mask |= b;
+  return true;
+}
 
 struct gnb_graph {
   int device = 0;

@@ -319,15 +319,13 @@ extern "C" int gnb_graph_lower(gnb_ctx* ctx, const void* adj, int adj_dtype, int
   size_t o_gpp = take(B + 1);
   size_t o_ngp = take(N), o_gnpp = take(B + 1);
   // stream-ordered pool allocation: a lowering per batch (the e2e path) must not pay cudaMalloc / cudaFree device syncs
-  static bool pool_set = false;
-  if (!pool_set) {
+  if (ctx_first(ctx, ONCE_POOL)) {
     cudaMemPool_t pool;
     if (cudaDeviceGetDefaultMemPool(&pool, ctx->device) == cudaSuccess) {
       uint64_t thr = ~0ull;
       cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
     }
     cudaGetLastError();
-    pool_set = true;
   }
   g->stream = ctx->stream;
   cudaError_t ce = cudaMallocAsync(&g->all, off ? off : 256, ctx->stream);

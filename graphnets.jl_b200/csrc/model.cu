@@ -6,6 +6,7 @@
 #include "smallk.cuh"
 #include "tc_gemm.cuh"
 #include <atomic>
+#include <mutex>
 
 // ------------------------------------------------------------------ errors / arena / ctx
 static thread_local char g_err[1024] = "";
@@ -61,6 +62,14 @@ void Arena::release() {
   chunks.clear();
 }
 
+// Forwards of DIFFERENT contexts on the same device are serialised on the device (stream-ordered, the host does not block):
+// every persistent tcgen05 kernel is sized to own all SMs / tensor memory, and two of them from different streams running
+// interleaved dead-lock (observed at 4096 graphs: bounded spins trap after ~70 s).  Copies, the lowering and the host-side
+// work of one context still overlap the forward of the other - which is what a double-buffered input pipeline needs.
+static std::mutex g_chain_mu;
+static cudaEvent_t g_chain_ev[64] = {};
+static gnb_ctx* g_chain_ctx[64] = {};
+
 extern "C" gnb_ctx* gnb_ctx_create(int device, int* err) {
   int n = 0;
   cudaError_t e = cudaGetDeviceCount(&n);
@@ -82,7 +91,18 @@ extern "C" int gnb_ctx_destroy(gnb_ctx* c) {
   cudaSetDevice(c->device);
   c->arena.release();
   c->staging.release();
+  {
+    std::lock_guard<std::mutex> lk(g_chain_mu);
+    if (c->device < 64 && g_chain_ctx[c->device] == c) { g_chain_ctx[c->device] = nullptr; g_chain_ev[c->device] = nullptr; }
+  }
+  if (c->done_ev) cudaEventDestroy(c->done_ev);
   tc_lin_cache_free(c->lin_cache);
+  if (c->pipe.copy) {
+    cudaStreamDestroy(c->pipe.copy);
+    for (auto e : c->pipe.ev_chunk) if (e) cudaEventDestroy(e);
+    if (c->pipe.ev_ready) cudaEventDestroy(c->pipe.ev_ready);
+    if (c->pipe.ev_in) cudaEventDestroy(c->pipe.ev_in);
+  }
   for (auto& r : c->prof_recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
   for (auto e : c->ev_pool) cudaEventDestroy(e);
   delete c;
@@ -168,6 +188,8 @@ struct LayerW {
 };
 
 static std::atomic<uint64_t> g_model_ids{1};
+
+
 
 struct gnb_model {
   int device = 0;
@@ -529,7 +551,26 @@ static int run_block_wide(gnb_ctx* ctx, const gnb_graph* g, const LayerW& w, Fea
       wa.pc[wa.np++] = WidePiece{x.n, g->edge_dst, bn_, bn_, b.We + (size_t)(a + bn_) * p};
     }
     if (c > 0) wa.pc[wa.np++] = WidePiece{x.g, g->edge_graph, c, c, b.We + (size_t)(a + 2 * bn_) * p};
-    GNB_TRY(launch_wide(ctx, wa));
+    if (ctx->pipe.ef_pending && x.e == ctx->pipe.d_ef && a > 0) {
+      // the edge rows are still being uploaded (gnb_model_forward_host): one launch per chunk, each behind its copy
+      const int nch = ctx->pipe.nchunks;
+      const int64_t per = (E + nch - 1) / nch;
+      for (int ci = 0; ci < nch; ci++) {
+        const int64_t r0 = ci * per, r1 = r0 + per < E ? r0 + per : E;
+        if (r0 >= r1) break;
+        GNB_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->pipe.ev_chunk[ci], 0));
+        WideArgs wc = wa;
+        wc.R = r1 - r0; wc.out = h.e + (size_t)r0 * p;
+        for (int i = 0; i < wc.np; i++) {
+          if (wc.pc[i].idx) wc.pc[i].idx += r0;
+          else wc.pc[i].x += (size_t)r0 * wc.pc[i].ldx;
+        }
+        GNB_TRY(launch_wide(ctx, wc));
+      }
+      ctx->pipe.ef_pending = false;
+    } else {
+      GNB_TRY(launch_wide(ctx, wa));
+    }
   }
   if (q == 0 && r == 0) return GNB_OK;
   float* Z = arena_ptr<float>(ctx->arena, (size_t)N * kz, &rc);
@@ -604,6 +645,14 @@ static int run_block_narrow(gnb_ctx* ctx, const gnb_graph* g, const LayerW& w, F
     if (Pu) na.add[na.nadd++] = NarrowAdd{Pu, g->edge_graph, p};
     else na.bias = b.be;
     GNB_TRY(launch_narrow(ctx, na));
+    if (ctx->pipe.out_pending && h.e == ctx->pipe.d_out_ef) {
+      // the edge output is final: download it now, under the node / graph kernels of this block (gnb_model_forward_host)
+      GNB_CUDA(cudaEventRecord(ctx->pipe.ev_ready, ctx->stream));
+      GNB_CUDA(cudaStreamWaitEvent(ctx->pipe.copy, ctx->pipe.ev_ready, 0));
+      GNB_CUDA(cudaMemcpyAsync(ctx->pipe.h_out_ef, h.e, ctx->pipe.out_bytes, cudaMemcpyDeviceToHost, ctx->pipe.copy));
+      ctx->pipe.out_pending = false;
+      ctx->pipe.out_early = true;
+    }
   }
   if (q == 0 && r == 0) return GNB_OK;
   float* agg = arena_ptr<float>(ctx->arena, (size_t)N * p, &rc);
@@ -711,7 +760,7 @@ static void arena_rewind(Arena& a, const ArenaMark& m) {
   for (size_t i = 0; i < a.chunks.size(); i++) a.chunks[i].used = i < m.nchunks ? m.used[i] : 0;
 }
 
-static int forward_device(gnb_ctx* ctx, const gnb_model* m, const gnb_graph* g, const float* ef, const float* nf,
+static int forward_device_impl(gnb_ctx* ctx, const gnb_model* m, const gnb_graph* g, const float* ef, const float* nf,
                    const float* gf, float* out_ef, float* out_nf, float* out_gf, int precision, bool reset_arena) {
   GNB_CHECK(ctx && m && g, "gnb_model_forward: null argument");
   GNB_CHECK(ctx->device == m->device && ctx->device == g->device, "gnb_model_forward: ctx/model/graph on different devices");
@@ -758,6 +807,11 @@ static int forward_device(gnb_ctx* ctx, const gnb_model* m, const gnb_graph* g, 
   }
   if (rc != GNB_OK) return rc;
   Feat x{ef, nf, gf};
+  if (ctx->pipe.ef_pending && !(precision != GNB_PREC_FP32 && block_wide_ok(m->layers[0]) && m->layers[0].blk.in_e > 0)) {
+    // chunked upload in flight but the first layer reads all edge rows at once: wait for the last chunk
+    for (int ci = 0; ci < ctx->pipe.nchunks; ci++) GNB_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->pipe.ev_chunk[ci], 0));
+    ctx->pipe.ef_pending = false;
+  }
   bool have_pre = false;      // pre[li & 1] holds the rows of layer li
   ArenaMark mark = arena_mark(ctx->arena);
   for (int li = 0; li < L; li++) {
@@ -802,6 +856,20 @@ static int forward_device(gnb_ctx* ctx, const gnb_model* m, const gnb_graph* g, 
 
 
 
+static int forward_device(gnb_ctx* ctx, const gnb_model* m, const gnb_graph* g, const float* ef, const float* nf,
+                          const float* gf, float* out_ef, float* out_nf, float* out_gf, int precision, bool reset_arena) {
+  if (!ctx || ctx->device < 0 || ctx->device >= 64)
+    return forward_device_impl(ctx, m, g, ef, nf, gf, out_ef, out_nf, out_gf, precision, reset_arena);
+  std::lock_guard<std::mutex> lk(g_chain_mu);      // held while the kernels are enqueued (host time only)
+  const int d = ctx->device;
+  cudaSetDevice(d);
+  if (g_chain_ctx[d] && g_chain_ctx[d] != ctx && g_chain_ev[d]) cudaStreamWaitEvent(ctx->stream, g_chain_ev[d], 0);
+  const int rc = forward_device_impl(ctx, m, g, ef, nf, gf, out_ef, out_nf, out_gf, precision, reset_arena);
+  if (!ctx->done_ev) cudaEventCreateWithFlags(&ctx->done_ev, cudaEventDisableTiming);
+  if (ctx->done_ev && cudaEventRecord(ctx->done_ev, ctx->stream) == cudaSuccess) { g_chain_ev[d] = ctx->done_ev; g_chain_ctx[d] = ctx; }
+  return rc;
+}
+
 extern "C" int gnb_model_forward(gnb_ctx* ctx, const gnb_model* m, const gnb_graph* g, const float* ef,
                                  const float* nf, const float* gf, float* out_ef, float* out_nf, float* out_gf,
                                  int precision) {
@@ -824,14 +892,52 @@ extern "C" int gnb_model_forward_host(gnb_ctx* ctx, const gnb_model* m, const gn
   float* d_on = on ? arena_ptr<float>(ctx->staging, on, &rc) : nullptr;
   float* d_og = og ? arena_ptr<float>(ctx->staging, og, &rc) : nullptr;
   if (rc != GNB_OK) return rc;
-  if (d_ie) GNB_CUDA(cudaMemcpyAsync(d_ie, ef, ie * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+  auto& P = ctx->pipe;
+  if (!P.copy) {
+    GNB_CUDA(cudaStreamCreateWithFlags(&P.copy, cudaStreamNonBlocking));
+    for (auto& e : P.ev_chunk) GNB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    GNB_CUDA(cudaEventCreateWithFlags(&P.ev_ready, cudaEventDisableTiming));
+    GNB_CUDA(cudaEventCreateWithFlags(&P.ev_in, cudaEventDisableTiming));
+  }
+  // the copy stream starts behind whatever the compute stream has queued on these buffers (previous forward)
+  GNB_CUDA(cudaEventRecord(P.ev_in, ctx->stream));
+  GNB_CUDA(cudaStreamWaitEvent(P.copy, P.ev_in, 0));
   if (d_in) GNB_CUDA(cudaMemcpyAsync(d_in, nf, in * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
   if (d_ig) GNB_CUDA(cudaMemcpyAsync(d_ig, gf, ig * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
-  GNB_TRY(forward_device(ctx, m, g, d_ie, d_in, d_ig, d_oe, d_on, d_og, precision, true));
-  if (d_oe && out_ef) GNB_CUDA(cudaMemcpyAsync(out_ef, d_oe, oe * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+  P.ef_pending = false; P.out_pending = false; P.out_early = false;
+  if (d_ie) {
+    const int64_t E = g->E;
+    const int de = m->in_dims[0];
+    if (ie * sizeof(float) >= ((size_t)8 << 20)) {      // worth pipelining: 4 row chunks on the copy stream
+      P.nchunks = 4;
+      const int64_t per = (E + P.nchunks - 1) / P.nchunks;
+      for (int ci = 0; ci < P.nchunks; ci++) {
+        const int64_t r0 = ci * per, r1 = r0 + per < E ? r0 + per : E;
+        if (r0 < r1)
+          GNB_CUDA(cudaMemcpyAsync(d_ie + (size_t)r0 * de, ef + (size_t)r0 * de, (size_t)(r1 - r0) * de * sizeof(float),
+                                   cudaMemcpyHostToDevice, P.copy));
+        GNB_CUDA(cudaEventRecord(P.ev_chunk[ci], P.copy));
+      }
+      P.d_ef = d_ie; P.ef_rows = E; P.ef_pending = true;
+    } else {
+      GNB_CUDA(cudaMemcpyAsync(d_ie, ef, ie * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    }
+  }
+  if (d_oe && out_ef && oe * sizeof(float) >= ((size_t)4 << 20)) {
+    P.d_out_ef = d_oe; P.h_out_ef = out_ef; P.out_bytes = oe * sizeof(float); P.out_pending = true;
+  }
+  int frc = forward_device(ctx, m, g, d_ie, d_in, d_ig, d_oe, d_on, d_og, precision, true);
+  const bool early = P.out_early;
+  P.ef_pending = false; P.out_pending = false; P.out_early = false;
+  if (frc != GNB_OK) {
+    cudaStreamSynchronize(P.copy);
+    return frc;
+  }
+  if (d_oe && out_ef && !early) GNB_CUDA(cudaMemcpyAsync(out_ef, d_oe, oe * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
   if (d_on && out_nf) GNB_CUDA(cudaMemcpyAsync(out_nf, d_on, on * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
   if (d_og && out_gf) GNB_CUDA(cudaMemcpyAsync(out_gf, d_og, og * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
   GNB_CUDA(cudaStreamSynchronize(ctx->stream));
+  GNB_CUDA(cudaStreamSynchronize(P.copy));
   return GNB_OK;
 }
 

@@ -330,10 +330,8 @@ int launch_wide(gnb_ctx* ctx, const WideArgs& a0) {
   GNB_CHECK((a.ldo & 3) == 0 && ((uintptr_t)a.out & 15) == 0, "launch_wide: output must be 16-byte aligned rows");
   a.K4 = (K + 3) / 4 * 4;
   const size_t smem = ((size_t)a.K4 * 128 + (size_t)WIDE_WARPS * WIDE_ROWS * a.K4) * sizeof(float);
-  static bool attr = false;
-  if (!attr) {
+  if (ctx_first(ctx, ONCE_WIDE)) {
     GNB_CUDA(cudaFuncSetAttribute(k_wide, cudaFuncAttributeMaxDynamicSharedMemorySize, (WK_MAX * 128 + WIDE_WARPS * WIDE_ROWS * WK_MAX) * 4));
-    attr = true;
   }
   const int64_t nblocks = (a.R + WIDE_ROWS - 1) / WIDE_ROWS;
   int64_t gx = (nblocks + WIDE_WARPS - 1) / WIDE_WARPS;
@@ -371,11 +369,9 @@ int launch_narrow(gnb_ctx* ctx, const NarrowArgs& a) {
   if (a.nsrc >= 1 && S0.d >= 64 && (S0.d & 3) == 0 && (S0.ldx & 3) == 0 && ((uintptr_t)S0.x & 15) == 0 && small_rest) {
     const int NOp = a.No <= 4 ? 4 : 8;
     const size_t smem = ((size_t)(K * NOp + 3) / 4 * 4 + (size_t)N2_WARPS * 32 * 128) * sizeof(float);
-    static bool attr = false;
-    if (!attr) {
+    if (ctx_first(ctx, ONCE_NARROW2)) {
       GNB_CUDA(cudaFuncSetAttribute(k_narrow2<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (NARROW_KMAX * 4 + N2_WARPS * 32 * 128) * 4));
       GNB_CUDA(cudaFuncSetAttribute(k_narrow2<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (NARROW_KMAX * 8 + N2_WARPS * 32 * 128) * 4));
-      attr = true;
     }
     int64_t gx = ((a.R + 31) / 32 + N2_WARPS - 1) / N2_WARPS;
     const int64_t cap = (int64_t)ctx->sm_count * 3;

@@ -443,11 +443,8 @@ int tc_core_pack(gnb_ctx* ctx, const gnb_block_params& blk, const gnb_ffn_params
 template <int SRC, int NBLK>
 static int launch_proj(gnb_ctx* ctx, const ProjArgs& a, const char* name, double flops, double bytes) {
   if (a.num_tiles <= 0) return GNB_OK;
-  static bool attr_set = false;
-  if (!attr_set) {
+  if (ctx_first(ctx, (SRC == SRC_LN && NBLK == 2) ? ONCE_PROJ_LN2 : ((SRC == SRC_AGG && NBLK == 1) ? ONCE_PROJ_AGG1 : ONCE_PROJ_OTHER)))
     GNB_CUDA(cudaFuncSetAttribute(k_tc_proj<SRC, NBLK>, cudaFuncAttributeMaxDynamicSharedMemorySize, pj_smem(NBLK)));
-    attr_set = true;
-  }
   const int per_sm = NBLK == 1 ? 2 : 1;
   const int grid = a.num_tiles < per_sm * ctx->sm_count ? a.num_tiles : per_sm * ctx->sm_count;
   Launch L(ctx, name, bytes, flops);

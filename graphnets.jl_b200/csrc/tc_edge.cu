@@ -588,14 +588,13 @@ __global__ void __launch_bounds__(E_THREADS, 1) k_edge5(const EdgeArgs a) {
 
 int launch_edge5(gnb_ctx* ctx, const EdgeArgs& a, const char* name, double flops, double bytes) {
   if (a.num_tiles <= 0) return GNB_OK;
-  static bool attr_set = false;
-  static int use_cl2 = 1;
-  if (!attr_set) {
+  static const int use_cl2 = [] {      // GNB_EDGE_CTA_PAIR=0: one CTA per tile stream (cta_group::1)
+    const char* e = getenv("GNB_EDGE_CTA_PAIR");
+    return e ? atoi(e) : 1;
+  }();
+  if (ctx_first(ctx, ONCE_EDGE5)) {
     GNB_CUDA(cudaFuncSetAttribute(k_edge5<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, E_SMEM));
     GNB_CUDA(cudaFuncSetAttribute(k_edge5<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, E_SMEM));
-    const char* e = getenv("GNB_EDGE_CTA_PAIR");      // 0: one CTA per tile stream (cta_group::1)
-    if (e) use_cl2 = atoi(e);
-    attr_set = true;
   }
   Launch L(ctx, name, bytes, flops);
   if (use_cl2 && ctx->sm_count >= 2) {

@@ -425,11 +425,7 @@ bool tc_lin_supported(const LinArgs& a) {
 
 int launch_linear_tc(gnb_ctx* ctx, const LinArgs& a) {
   if (a.R <= 0) return GNB_OK;
-  static bool attr_set = false;
-  if (!attr_set) {
-    GNB_CUDA(cudaFuncSetAttribute(k_tc_lin, cudaFuncAttributeMaxDynamicSharedMemorySize, G_SMEM));
-    attr_set = true;
-  }
+  if (ctx_first(ctx, ONCE_TC_LIN)) GNB_CUDA(cudaFuncSetAttribute(k_tc_lin, cudaFuncAttributeMaxDynamicSharedMemorySize, G_SMEM));
   GemmArgs g{};
   g.R = a.R; g.Nout = a.Nout; g.ldo = a.ldo; g.nsrc = a.nsrc;
   int K = 0;
