@@ -391,13 +391,393 @@ struct PackKey {
   uint64_t model;
   const float* W[3];
   int d[3];
-  int Nout, ldw;
+  int Nout, ldw, ng;
   bool operator<(const PackKey& o) const {
-    return std::tie(model, W[0], W[1], W[2], d[0], d[1], d[2], Nout, ldw) <
-           std::tie(o.model, o.W[0], o.W[1], o.W[2], o.d[0], o.d[1], o.d[2], o.Nout, o.ldw);
+    return std::tie(model, W[0], W[1], W[2], d[0], d[1], d[2], Nout, ldw, ng) <
+           std::tie(o.model, o.W[0], o.W[1], o.W[2], o.d[0], o.d[1], o.d[2], o.Nout, o.ldw, o.ng);
   }
 };
 struct PackCache { std::map<PackKey, __nv_bfloat16*> m; };
+
+// =====================================================================================================
+// Fused GNFeedForward + residuals for hidden width 256 (src/gnfeedforward.jl:27-31, src/gncore.jl:56-59):
+//   y = x + h + W2 relu(W1 LN2(x) + b1) + b2
+// One 128-row tile per pass, persistent CTA, the 4H = 1024 wide hidden activation never leaves the SM (the generic path above
+// writes / reads it through HBM: 4 KB per row).  Per tile 8 hidden chunks of 128 units, software pipelined:
+//   up(c)  : Hd[c & 1] (TMEM, 128 fp32 columns) = A . W1[:, chunk c]          4 K slabs x 4 UMMAs (SS)
+//   conv(c): Hd -> + b1 -> relu -> bf16, in place (DRAIN warps)               the A operand of the down projection (TS)
+//   down(c): D (TMEM, 256 fp32 columns) += relu(.)[chunk c] . W2[chunk c, :]   2 output blocks x 8 UMMAs (TS)
+// issued as up0 up1 down0 up2 down1 ... so that conv(c) runs under up(c+1).  TMEM: D 256 + Hd 2 x 128 = 512 columns.
+// 14 warps: 0-3 DRAIN (conversion), 4-7 A producers (LayerNorm -> bf16 slabs, next tile), 8-11 EPI (D + b2 + x + h -> y,
+// fragment layout), 12 MMA issuer (two slabs = 8 UMMAs per iteration), 13 weight loader (16 KB slabs, 5-stage ring: W1 slabs of chunk c, then W2 slabs of chunk c-1).
+// =====================================================================================================
+constexpr int F_H = 256, F_KS = F_H / 64, F_CH = 4 * F_H / 128;      // 4 K slabs, 8 hidden chunks
+constexpr int F_NW = 5;                                   // weight ring: 5 x 16 KB, consumed two slabs at a time
+constexpr int F_OFF_A = 0;                                // 2 stages x 4 slabs
+constexpr int F_OFF_W = 2 * F_KS * SLAB;
+constexpr int F_OFF_STAT = F_OFF_W + F_NW * SLAB;         // float2 stats[128]
+constexpr int F_OFF_B1 = F_OFF_STAT + 128 * 8;            // float b1[1024]
+constexpr int F_OFF_BAR = F_OFF_B1 + 4 * F_H * 4;
+constexpr int F_SMEM = F_OFF_BAR + 32 * 8 + 16 + 1024;
+constexpr int F_THREADS = 14 * 32;
+enum { FB_WFULL = 0, FB_WEMPTY = 5, FB_AFULL = 10, FB_AEMPTY = 12, FB_HIDFULL = 14, FB_HSREADY = 16, FB_ACCFULL = 18, FB_ACCFREE = 19 };
+
+struct FfnArgs {
+  const float* x;       // [R][256]
+  const float* h;       // [R][256] block output (second residual addend)
+  float* y;             // [R][256]
+  int64_t R;
+  int num_tiles;
+  const float *gamma, *beta; float eps; int eps_mode;      // LN2
+  const __nv_bfloat16* w1;      // [8 chunks][4 K slabs][8192]
+  const __nv_bfloat16* w2;      // [2 output blocks][16 K slabs][8192]
+  const float *b1, *b2;
+};
+
+__global__ void __launch_bounds__(F_THREADS, 1) k_tc_ffn256(const FfnArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* sm = smem_raw + (base - raw);
+  float2* stats = reinterpret_cast<float2*>(sm + F_OFF_STAT);
+  float* sB1 = reinterpret_cast<float*>(sm + F_OFF_B1);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sm + F_OFF_BAR);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 32);
+  const uint32_t bar0 = smem_u32(bars);
+  auto BAR = [&](int i) { return bar0 + 8u * (uint32_t)i; };
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) {
+    for (int i = 0; i < F_NW; i++) { mbar_init(BAR(FB_WFULL + i), 1); mbar_init(BAR(FB_WEMPTY + i), 1); }
+    for (int i = 0; i < 2; i++) {
+      mbar_init(BAR(FB_AFULL + i), 4); mbar_init(BAR(FB_AEMPTY + i), 1);
+      mbar_init(BAR(FB_HIDFULL + i), 1); mbar_init(BAR(FB_HSREADY + i), 4);
+    }
+    mbar_init(BAR(FB_ACCFULL), 1); mbar_init(BAR(FB_ACCFREE), 4);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 12) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  for (int i = tid; i < 4 * F_H; i += F_THREADS) sB1[i] = a.b1[i];
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t Dt = tmem, Hd0 = tmem + 256;      // D: columns [0, 256); Hd[b]: [256 + 128 b, +128)
+  // the hidden chunks are independent terms of the down projection: every CTA starts at a different one, so that the
+  // lock-stepped CTAs do not stream the same weight slab from the same L2 slice at the same time
+  const int crot = (int)(blockIdx.x & (F_CH - 1));
+  static_assert((F_CH & (F_CH - 1)) == 0, "chunk rotation uses a mask");
+
+  if (warp == 13) {
+    // ===================================================== weight loader: slabs in the order the MMA warp consumes them
+    uint32_t it = 0;
+    auto load = [&](const __nv_bfloat16* src) {
+      const uint32_t st = it % F_NW, ph = (it / F_NW) & 1;
+      it++;
+      mbar_wait(BAR(FB_WEMPTY + st), ph ^ 1);
+      if (elect_one()) {
+        mbar_expect_tx(BAR(FB_WFULL + st), SLAB);
+        bulk_g2s(base + F_OFF_W + st * SLAB, src, SLAB, BAR(FB_WFULL + st));
+      }
+      __syncwarp();
+    };
+    for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
+#pragma unroll 1
+      for (int c = 0; c <= F_CH; c++) {
+        if (c < F_CH)
+          for (int ks = 0; ks < F_KS; ks++) load(a.w1 + (size_t)(((c + crot) & (F_CH - 1)) * F_KS + ks) * 8192);
+        if (c >= 1)
+          for (int nb = 0; nb < 2; nb++)
+            for (int kh = 0; kh < 2; kh++) load(a.w2 + (size_t)(nb * (4 * F_H / 64) + 2 * ((c - 1 + crot) & (F_CH - 1)) + kh) * 8192);
+      }
+    }
+  } else if (warp == 12) {
+    // ===================================================== MMA issuer: two weight slabs (8 UMMAs) per iteration - the issue
+    // overhead of a barrier wait + fence + election per 4 UMMAs is more than the 256 cycles those UMMAs take
+    uint32_t it = 0, tl = 0, nhid[2] = {0, 0};
+    uint64_t wd0 = 0, wd1 = 0;
+    uint32_t ws0 = 0, ws1 = 0;
+    auto get_w2 = [&]() {
+      ws0 = it % F_NW; ws1 = (it + 1) % F_NW;
+      const uint32_t p0 = (it / F_NW) & 1, p1 = ((it + 1) / F_NW) & 1;
+      it += 2;
+      mbar_wait(BAR(FB_WFULL + ws0), p0);
+      mbar_wait(BAR(FB_WFULL + ws1), p1);
+      wd0 = umma_desc(base + F_OFF_W + ws0 * SLAB);
+      wd1 = umma_desc(base + F_OFF_W + ws1 * SLAB);
+    };
+    for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, tl++) {
+      const uint32_t st = tl & 1;
+      mbar_wait(BAR(FB_AFULL + st), (tl >> 1) & 1);
+#pragma unroll 1
+      for (int c = 0; c <= F_CH; c++) {
+        if (c < F_CH) {      // up projection of chunk c: K slabs (0,1) then (2,3)
+          const uint32_t Hd = Hd0 + 128 * (c & 1);
+#pragma unroll 1
+          for (int kp = 0; kp < F_KS / 2; kp++) {
+            get_w2();
+            tc_fence_after();
+            if (elect_one()) {
+              const uint64_t ad = umma_desc(base + F_OFF_A + (st * F_KS + 2 * kp) * SLAB);
+#pragma unroll
+              for (int k4 = 0; k4 < 4; k4++) mma_ss(Hd, ad + 2 * k4, wd0 + 2 * k4, IDESC, (kp > 0 || k4 > 0) ? 1u : 0u);
+#pragma unroll
+              for (int k4 = 0; k4 < 4; k4++) mma_ss(Hd, ad + (SLAB >> 4) + 2 * k4, wd1 + 2 * k4, IDESC, 1u);
+              tc_commit(BAR(FB_WEMPTY + ws0));
+              tc_commit(BAR(FB_WEMPTY + ws1));
+              if (kp == F_KS / 2 - 1) {
+                tc_commit(BAR(FB_HIDFULL + (c & 1)));
+                if (c == F_CH - 1) tc_commit(BAR(FB_AEMPTY + st));
+              }
+            }
+            __syncwarp();
+          }
+        }
+        if (c >= 1) {        // down projection of chunk c - 1: one output block (both K halves) per iteration
+          const int cc = c - 1, hb = cc & 1;
+          const uint32_t Hd = Hd0 + 128 * hb;
+          mbar_wait(BAR(FB_HSREADY + hb), nhid[hb] & 1);      // conversion of this chunk done
+          nhid[hb]++;
+          if (cc == 0) mbar_wait(BAR(FB_ACCFREE), (tl & 1) ^ 1);      // D drained by the epilogue of the previous tile
+#pragma unroll 1
+          for (int nb = 0; nb < 2; nb++) {
+            get_w2();
+            tc_fence_after();
+            if (elect_one()) {
+#pragma unroll
+              for (int k4 = 0; k4 < 4; k4++) mma_ts(Dt + 128 * nb, Hd + 8 * k4, wd0 + 2 * k4, IDESC, (cc > 0 || k4 > 0) ? 1u : 0u);
+#pragma unroll
+              for (int k4 = 0; k4 < 4; k4++) mma_ts(Dt + 128 * nb, Hd + 32 + 8 * k4, wd1 + 2 * k4, IDESC, 1u);
+              tc_commit(BAR(FB_WEMPTY + ws0));
+              tc_commit(BAR(FB_WEMPTY + ws1));
+              if (cc == F_CH - 1 && nb == 1) tc_commit(BAR(FB_ACCFULL));
+            }
+            __syncwarp();
+          }
+        }
+      }
+    }
+  } else if (warp < 4) {
+    // ===================================================== DRAIN: hidden chunk fp32 -> + b1 -> relu -> bf16, in place in TMEM
+    const uint32_t lane_base = ((uint32_t)(warp * 32)) << 16;
+    auto cvt32 = [&](const uint32_t (&v)[32], const float* bias32, uint32_t dst) {
+      uint32_t p[16];
+      const float4* bb = reinterpret_cast<const float4*>(bias32);
+#pragma unroll
+      for (int t = 0; t < 8; t++) {
+        const float4 b = bb[t];
+        p[2 * t] = pack_bf16_relu(__uint_as_float(v[4 * t]) + b.x, __uint_as_float(v[4 * t + 1]) + b.y);
+        p[2 * t + 1] = pack_bf16_relu(__uint_as_float(v[4 * t + 2]) + b.z, __uint_as_float(v[4 * t + 3]) + b.w);
+      }
+      TC_ST16(dst, p);
+    };
+    uint32_t nh[2] = {0, 0};
+    for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
+#pragma unroll 1
+      for (int c = 0; c < F_CH; c++) {
+        const int hb = c & 1;
+        mbar_wait(BAR(FB_HIDFULL + hb), nh[hb] & 1);
+        nh[hb]++;
+        tc_fence_after();
+        uint32_t va[32], vb[32];
+        const float* bias = sB1 + ((c + crot) & (F_CH - 1)) * 128;
+        const uint32_t t0 = Hd0 + 128 * hb + lane_base;
+        TC_LD32(t0, va);
+        TC_LD32(t0 + 32, vb);
+        tc_wait_ld();
+        cvt32(va, bias, t0);
+        TC_LD32(t0 + 64, va);
+        cvt32(vb, bias + 32, t0 + 16);
+        TC_LD32(t0 + 96, vb);
+        tc_wait_ld();
+        cvt32(va, bias + 64, t0 + 32);
+        cvt32(vb, bias + 96, t0 + 48);
+        tc_wait_st();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(BAR(FB_HSREADY + hb));
+      }
+    }
+  } else if (warp < 8) {
+    // ===================================================== A producers (next tile): LayerNorm -> bf16 slabs, warp q rows 32 q .. + 31
+    const int q = warp - 4;
+    const int hr = lane >> 4, c16 = lane & 15;
+    uint32_t tl = 0;
+    for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, tl++) {
+      const int64_t row0 = (int64_t)tile * TM + 32 * q;
+      // two-pass statistics, 16 lanes per row, the row in registers (4 float4 per lane), 2 row pairs in flight
+      const float* xs = a.x + 4 * c16;
+#pragma unroll 1
+      for (int r0 = 0; r0 < 32; r0 += 4) {
+        float4 v[2][4];
+#pragma unroll
+        for (int p = 0; p < 2; p++) {
+          int64_t row = row0 + r0 + 2 * p + hr;
+          row = row < a.R ? row : a.R - 1;
+#pragma unroll
+          for (int j = 0; j < 4; j++) v[p][j] = __ldg(reinterpret_cast<const float4*>(xs + (size_t)row * F_H + 64 * j));
+        }
+        float sum[2], sq[2];
+#pragma unroll
+        for (int p = 0; p < 2; p++) {
+          float t = 0.f;
+#pragma unroll
+          for (int j = 0; j < 4; j++) t += (v[p][j].x + v[p][j].y) + (v[p][j].z + v[p][j].w);
+          sum[p] = t;
+        }
+#pragma unroll
+        for (int o = 1; o < 16; o <<= 1)
+#pragma unroll
+          for (int p = 0; p < 2; p++) sum[p] += __shfl_xor_sync(0xffffffffu, sum[p], o);
+#pragma unroll
+        for (int p = 0; p < 2; p++) {
+          const float mu = sum[p] * (1.0f / F_H);
+          float t = 0.f;
+#pragma unroll
+          for (int j = 0; j < 4; j++) {
+            const float dx = v[p][j].x - mu, dy = v[p][j].y - mu, dz = v[p][j].z - mu, dw = v[p][j].w - mu;
+            t += (dx * dx + dy * dy) + (dz * dz + dw * dw);
+          }
+          sq[p] = t;
+          sum[p] = mu;
+        }
+#pragma unroll
+        for (int o = 1; o < 16; o <<= 1)
+#pragma unroll
+          for (int p = 0; p < 2; p++) sq[p] += __shfl_xor_sync(0xffffffffu, sq[p], o);
+        if (c16 == 0) {
+#pragma unroll
+          for (int p = 0; p < 2; p++) stats[32 * q + r0 + 2 * p + hr] = make_float2(sum[p], ln_rstd(sq[p] * (1.0f / F_H), a.eps, a.eps_mode));
+        }
+      }
+      __syncwarp();
+      const uint32_t st = tl & 1;
+      mbar_wait(BAR(FB_AEMPTY + st), ((tl >> 1) & 1) ^ 1);
+#pragma unroll 1
+      for (int ks = 0; ks < F_KS; ks++) {
+        const float4 g4 = __ldg(reinterpret_cast<const float4*>(a.gamma + 64 * ks + 4 * c16));
+        const float4 b4 = __ldg(reinterpret_cast<const float4*>(a.beta + 64 * ks + 4 * c16));
+        uint8_t* A = sm + F_OFF_A + (st * F_KS + ks) * SLAB;
+#pragma unroll 1
+        for (int i0 = 0; i0 < 32; i0 += 16) {
+          float4 v[8];
+#pragma unroll
+          for (int u = 0; u < 8; u++) {
+            int64_t row = row0 + i0 + 2 * u + hr;
+            row = row < a.R ? row : a.R - 1;
+            v[u] = __ldg(reinterpret_cast<const float4*>(xs + (size_t)row * F_H + 64 * ks));
+          }
+#pragma unroll
+          for (int u = 0; u < 8; u++) {
+            const int r = 32 * q + i0 + 2 * u + hr;
+            const float2 ms = stats[r];
+            float4 t = v[u];
+            t.x = (t.x - ms.x) * ms.y * g4.x + b4.x;
+            t.y = (t.y - ms.x) * ms.y * g4.y + b4.y;
+            t.z = (t.z - ms.x) * ms.y * g4.z + b4.z;
+            t.w = (t.w - ms.x) * ms.y * g4.w + b4.w;
+            if (row0 + i0 + 2 * u + hr >= a.R) t = f4zero();
+            uint2 pk;
+            pk.x = pack_bf16(t.x, t.y);
+            pk.y = pack_bf16(t.z, t.w);
+            *reinterpret_cast<uint2*>(A + sw_off(r, 4 * c16)) = pk;
+          }
+        }
+      }
+      fence_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(BAR(FB_AFULL + st));
+    }
+  } else if (warp < 12) {
+    // ===================================================== EPI (TMEM lane quadrant = warp % 4): y = D + b2 + x + h
+    // 16 half-steps per tile (4 column chunks x 2 row halves x 2 row sub-blocks), each 8 float2 per lane; the x / h rows of the
+    // NEXT half-step are in flight while the current one is combined and stored (they do not depend on the accumulator, so the
+    // first ones are requested before the accumulator is even complete): the window in which D is busy stays short
+    const int dq = warp & 3;
+    const uint32_t lane_base = ((uint32_t)(dq * 32)) << 16;
+    const int qr = lane >> 2, cq = 2 * (lane & 3);
+    uint32_t tl = 0;
+    for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, tl++) {
+      const int64_t row0 = (int64_t)tile * TM + 32 * dq;
+      float2 nx[8], nh[8];
+      auto issue = [&](int hs) {      // half-step hs = 4 ch + 2 hh + h2
+        const int ch = hs >> 2, hh = (hs >> 1) & 1, h2 = hs & 1;
+        int64_t row = row0 + 16 * hh + 8 * h2 + qr;
+        row = row < a.R ? row : a.R - 1;
+        const float* xp = a.x + (size_t)row * F_H + 64 * ch + cq;
+        const float* hp = a.h + (size_t)row * F_H + 64 * ch + cq;
+#pragma unroll
+        for (int n = 0; n < 8; n++) {
+          nx[n] = __ldg(reinterpret_cast<const float2*>(xp + 8 * n));
+          nh[n] = __ldg(reinterpret_cast<const float2*>(hp + 8 * n));
+        }
+      };
+      issue(0);
+      mbar_wait(BAR(FB_ACCFULL), tl & 1);
+      tc_fence_after();
+#pragma unroll 1
+      for (int st2 = 0; st2 < 8; st2++) {      // (ch, hh)
+        const int ch = st2 >> 1, hh = st2 & 1;
+        uint32_t dreg[32];
+        TC_LD_FRAG64(Dt + lane_base + ((uint32_t)(16 * hh) << 16) + 64 * ch, dreg);
+        tc_wait_ld();
+        if (st2 == 7) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(BAR(FB_ACCFREE));
+        }
+#pragma unroll
+        for (int h2 = 0; h2 < 2; h2++) {
+          const int hs = 2 * st2 + h2;
+          float2 v[8];
+#pragma unroll
+          for (int n = 0; n < 8; n++) v[n] = make_float2(nx[n].x + nh[n].x, nx[n].y + nh[n].y);
+          if (hs + 1 < 16) issue(hs + 1);
+          const int64_t row = row0 + 16 * hh + 8 * h2 + qr;
+          const int col = 64 * ch + cq;
+#pragma unroll
+          for (int n = 0; n < 8; n++) {
+            const float2 b = __ldg(reinterpret_cast<const float2*>(a.b2 + col + 8 * n));
+            v[n].x = (v[n].x + __uint_as_float(dreg[4 * n + 2 * h2])) + b.x;
+            v[n].y = (v[n].y + __uint_as_float(dreg[4 * n + 2 * h2 + 1])) + b.y;
+          }
+          if (row < a.R) {
+            float* o = a.y + (size_t)row * F_H + col;
+#pragma unroll
+            for (int n = 0; n < 8; n++) *reinterpret_cast<float2*>(o + 8 * n) = v[n];
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 12) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+}
+
+// packed bf16 weight slabs of one Dense, built on first use and cached per (model, weight block, group size)
+static int get_pack(gnb_ctx* ctx, const PackKey& key, const PackSrc& ps, int ldw, int K, int Nout, int NG, const __nv_bfloat16** out) {
+  if (!ctx->lin_cache) ctx->lin_cache = new PackCache();
+  PackCache* cache = static_cast<PackCache*>(ctx->lin_cache);
+  auto itc = cache->m.find(key);
+  if (itc == cache->m.end()) {
+    __nv_bfloat16* dst = nullptr;
+    const size_t elems = (size_t)K * Nout;
+    if (cudaMalloc((void**)&dst, elems * sizeof(__nv_bfloat16)) != cudaSuccess) {
+      cudaGetLastError();
+      gnb_set_error("tc_gemm: cudaMalloc(%zu) for packed weights failed", elems * 2);
+      return GNB_ERR_OOM;
+    }
+    k_pack_lin<<<(unsigned)ceil_div((int64_t)elems, 256), 256, 0, ctx->stream>>>(ps, ldw, K / 64, NG, Nout / 128 / NG, dst);
+    GNB_CUDA(cudaGetLastError());
+    ctx->launches++;
+    itc = cache->m.emplace(key, dst).first;
+  }
+  *out = itc->second;
+  return GNB_OK;
+}
 
 }  // namespace
 
@@ -430,7 +810,7 @@ int launch_linear_tc(gnb_ctx* ctx, const LinArgs& a) {
   g.R = a.R; g.Nout = a.Nout; g.ldo = a.ldo; g.nsrc = a.nsrc;
   int K = 0;
   PackKey key{};
-  key.model = ctx->cur_model_id; key.Nout = a.Nout; key.ldw = a.ldw;
+  key.model = ctx->cur_model_id; key.Nout = a.Nout; key.ldw = a.ldw; key.ng = (a.Nout / 128) % 2 == 0 ? 2 : 1;
   PackSrc ps{};
   ps.nsrc = a.nsrc;
   for (int s = 0; s < 3; s++) { ps.d[s] = 1 << 30; }
@@ -450,24 +830,7 @@ int launch_linear_tc(gnb_ctx* ctx, const LinArgs& a) {
   g.resident = (g.KS <= NA - 2 && g.ngroups > 1) ? 1 : 0;
   g.bias = a.bias; g.nadd = a.nadd; g.relu = a.relu; g.out = a.out; g.out_bf16 = a.out_bf16;
   for (int j = 0; j < a.nadd; j++) { g.add[j] = a.add[j].a; g.add_idx[j] = a.add[j].idx; g.lda[j] = a.add[j].lda; }
-  // packed bf16 weights: built on first use, cached per (model, weight block)
-  if (!ctx->lin_cache) ctx->lin_cache = new PackCache();
-  PackCache* cache = static_cast<PackCache*>(ctx->lin_cache);
-  auto itc = cache->m.find(key);
-  if (itc == cache->m.end()) {
-    __nv_bfloat16* dst = nullptr;
-    const size_t elems = (size_t)K * a.Nout;
-    if (cudaMalloc((void**)&dst, elems * sizeof(__nv_bfloat16)) != cudaSuccess) {
-      cudaGetLastError();
-      gnb_set_error("launch_linear_tc: cudaMalloc(%zu) for packed weights failed", elems * 2);
-      return GNB_ERR_OOM;
-    }
-    k_pack_lin<<<(unsigned)ceil_div((int64_t)elems, 256), 256, 0, ctx->stream>>>(ps, a.ldw, g.KS, g.NG, g.ngroups, dst);
-    GNB_CUDA(cudaGetLastError());
-    ctx->launches++;
-    itc = cache->m.emplace(key, dst).first;
-  }
-  g.wpack = itc->second;
+  GNB_TRY(get_pack(ctx, key, ps, a.ldw, K, a.Nout, g.NG, &g.wpack));
   double bytes = 2.0 * K * a.Nout + 4.0 * (double)a.R * a.Nout * a.nadd + (a.out_bf16 ? 2.0 : 4.0) * a.R * a.Nout;
   for (int s = 0; s < a.nsrc; s++) bytes += (a.src[s].x_bf16 ? 2.0 : 4.0) * a.R * a.src[s].d;
   // profile tag per layer shape (interned: Launch keeps the pointer)
@@ -477,6 +840,34 @@ int launch_linear_tc(gnb_ctx* ctx, const LinArgs& a) {
   Launch L(ctx, ctx->profiling && getenv("GNB_PROFILE_SHAPES") ? nit->second.c_str() : "tc_linear", bytes, 2.0 * a.R * K * a.Nout);
   const int grid = g.num_tiles < ctx->sm_count ? g.num_tiles : ctx->sm_count;
   k_tc_lin<<<grid, G_THREADS, G_SMEM, ctx->stream>>>(g);
+  GNB_CUDA(cudaGetLastError());
+  return GNB_OK;
+}
+
+bool tc_ffn256_supported(int64_t R, int d) { return d == F_H && R >= 256 && R <= 0x7fffffffLL; }
+
+int launch_ffn256_tc(gnb_ctx* ctx, int64_t R, const gnb_ffn_params& f, const gnb_ln_params& ln2, const float* x, const float* h, float* y) {
+  if (R <= 0) return GNB_OK;
+  if (ctx_first(ctx, ONCE_TC_FFN)) GNB_CUDA(cudaFuncSetAttribute(k_tc_ffn256, cudaFuncAttributeMaxDynamicSharedMemorySize, F_SMEM));
+  FfnArgs a{};
+  a.x = x; a.h = h; a.y = y; a.R = R; a.num_tiles = (int)ceil_div(R, TM);
+  a.gamma = ln2.gamma; a.beta = ln2.beta; a.eps = ln2.eps; a.eps_mode = ln2.eps_mode;
+  a.b1 = f.b1; a.b2 = f.b2;
+  PackKey k1{}, k2{};
+  PackSrc p1{}, p2{};
+  for (int s = 0; s < 3; s++) { p1.d[s] = p2.d[s] = 1 << 30; }
+  k1.model = k2.model = ctx->cur_model_id;
+  k1.W[0] = f.W1; k1.d[0] = F_H; k1.Nout = 4 * F_H; k1.ldw = 4 * F_H; k1.ng = 1;
+  k2.W[0] = f.W2; k2.d[0] = 4 * F_H; k2.Nout = F_H; k2.ldw = F_H; k2.ng = 1;
+  p1.nsrc = p2.nsrc = 1;
+  p1.W[0] = f.W1; p1.d[0] = F_H;
+  p2.W[0] = f.W2; p2.d[0] = 4 * F_H;
+  GNB_TRY(get_pack(ctx, k1, p1, 4 * F_H, F_H, 4 * F_H, 1, &a.w1));
+  GNB_TRY(get_pack(ctx, k2, p2, F_H, 4 * F_H, F_H, 1, &a.w2));
+  // canonical work of the reference FFN: 16 d^2 flop per row, x / h read and y written once
+  Launch L(ctx, "tc_ffn256", 4.0 * 3 * F_H * R, 16.0 * F_H * F_H * R);
+  const int grid = a.num_tiles < ctx->sm_count ? a.num_tiles : ctx->sm_count;
+  k_tc_ffn256<<<grid, F_THREADS, F_SMEM, ctx->stream>>>(a);
   GNB_CUDA(cudaGetLastError());
   return GNB_OK;
 }
