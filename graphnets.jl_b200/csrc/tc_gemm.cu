@@ -692,33 +692,21 @@ __global__ void __launch_bounds__(F_THREADS, 1) k_tc_ffn256(const FfnArgs a) {
     }
   } else if (warp < 12) {
     // ===================================================== EPI (TMEM lane quadrant = warp % 4): y = D + b2 + x + h
-    // 16 half-steps per tile (4 column chunks x 2 row halves x 2 row sub-blocks), each 8 float2 per lane; the x / h rows of the
-    // NEXT half-step are in flight while the current one is combined and stored (they do not depend on the accumulator, so the
-    // first ones are requested before the accumulator is even complete): the window in which D is busy stays short
+    // The accumulator is single buffered (TMEM: D 256 + 2 x 128 hidden columns), so the window in which it is busy is serial
+    // with the next tile's down projections.  Phase 1 keeps it short: TMEM -> registers -> y (raw accumulator, fragment-layout
+    // sector-exact stores, no loads), then D is released.  Phase 2 runs beside the next tile's MMAs: the same warp re-reads its
+    // 32 rows from L2 as coalesced 1 KB rows and adds x, h and b2 (4 rows in flight).
     const int dq = warp & 3;
     const uint32_t lane_base = ((uint32_t)(dq * 32)) << 16;
     const int qr = lane >> 2, cq = 2 * (lane & 3);
+    const float4 b2a = __ldg(reinterpret_cast<const float4*>(a.b2) + lane), b2b = __ldg(reinterpret_cast<const float4*>(a.b2) + 32 + lane);
     uint32_t tl = 0;
     for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, tl++) {
       const int64_t row0 = (int64_t)tile * TM + 32 * dq;
-      float2 nx[8], nh[8];
-      auto issue = [&](int hs) {      // half-step hs = 4 ch + 2 hh + h2
-        const int ch = hs >> 2, hh = (hs >> 1) & 1, h2 = hs & 1;
-        int64_t row = row0 + 16 * hh + 8 * h2 + qr;
-        row = row < a.R ? row : a.R - 1;
-        const float* xp = a.x + (size_t)row * F_H + 64 * ch + cq;
-        const float* hp = a.h + (size_t)row * F_H + 64 * ch + cq;
-#pragma unroll
-        for (int n = 0; n < 8; n++) {
-          nx[n] = __ldg(reinterpret_cast<const float2*>(xp + 8 * n));
-          nh[n] = __ldg(reinterpret_cast<const float2*>(hp + 8 * n));
-        }
-      };
-      issue(0);
       mbar_wait(BAR(FB_ACCFULL), tl & 1);
       tc_fence_after();
 #pragma unroll 1
-      for (int st2 = 0; st2 < 8; st2++) {      // (ch, hh)
+      for (int st2 = 0; st2 < 8; st2++) {      // (64-column chunk, row half)
         const int ch = st2 >> 1, hh = st2 & 1;
         uint32_t dreg[32];
         TC_LD_FRAG64(Dt + lane_base + ((uint32_t)(16 * hh) << 16) + 64 * ch, dreg);
@@ -730,23 +718,38 @@ __global__ void __launch_bounds__(F_THREADS, 1) k_tc_ffn256(const FfnArgs a) {
         }
 #pragma unroll
         for (int h2 = 0; h2 < 2; h2++) {
-          const int hs = 2 * st2 + h2;
-          float2 v[8];
-#pragma unroll
-          for (int n = 0; n < 8; n++) v[n] = make_float2(nx[n].x + nh[n].x, nx[n].y + nh[n].y);
-          if (hs + 1 < 16) issue(hs + 1);
           const int64_t row = row0 + 16 * hh + 8 * h2 + qr;
-          const int col = 64 * ch + cq;
-#pragma unroll
-          for (int n = 0; n < 8; n++) {
-            const float2 b = __ldg(reinterpret_cast<const float2*>(a.b2 + col + 8 * n));
-            v[n].x = (v[n].x + __uint_as_float(dreg[4 * n + 2 * h2])) + b.x;
-            v[n].y = (v[n].y + __uint_as_float(dreg[4 * n + 2 * h2 + 1])) + b.y;
-          }
           if (row < a.R) {
-            float* o = a.y + (size_t)row * F_H + col;
+            float* o = a.y + (size_t)row * F_H + 64 * ch + cq;
 #pragma unroll
-            for (int n = 0; n < 8; n++) *reinterpret_cast<float2*>(o + 8 * n) = v[n];
+            for (int n = 0; n < 8; n++) *reinterpret_cast<float2*>(o + 8 * n) = make_float2(__uint_as_float(dreg[4 * n + 2 * h2]), __uint_as_float(dreg[4 * n + 2 * h2 + 1]));
+          }
+        }
+      }
+      __syncwarp();      // the rows below were written by other lanes of this warp
+      const int64_t left = a.R - row0;
+      const int rows = left < 0 ? 0 : (left > 32 ? 32 : (int)left);
+#pragma unroll 1
+      for (int i0 = 0; i0 < rows; i0 += 4) {
+        float4 ya[4], yb[4], xa[4], xb4[4], ha[4], hb4[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+          const int64_t r = row0 + (i0 + u < rows ? i0 + u : rows - 1);
+          const size_t o = (size_t)r * F_H + 4 * lane;
+          ya[u] = __ldcg(reinterpret_cast<const float4*>(a.y + o)); yb[u] = __ldcg(reinterpret_cast<const float4*>(a.y + o + 128));
+          xa[u] = __ldg(reinterpret_cast<const float4*>(a.x + o)); xb4[u] = __ldg(reinterpret_cast<const float4*>(a.x + o + 128));
+          ha[u] = __ldg(reinterpret_cast<const float4*>(a.h + o)); hb4[u] = __ldg(reinterpret_cast<const float4*>(a.h + o + 128));
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+          if (i0 + u < rows) {
+            const size_t o = (size_t)(row0 + i0 + u) * F_H + 4 * lane;
+            const float4 ra = make_float4(((xa[u].x + ha[u].x) + ya[u].x) + b2a.x, ((xa[u].y + ha[u].y) + ya[u].y) + b2a.y,
+                                          ((xa[u].z + ha[u].z) + ya[u].z) + b2a.z, ((xa[u].w + ha[u].w) + ya[u].w) + b2a.w);
+            const float4 rb = make_float4(((xb4[u].x + hb4[u].x) + yb[u].x) + b2b.x, ((xb4[u].y + hb4[u].y) + yb[u].y) + b2b.y,
+                                          ((xb4[u].z + hb4[u].z) + yb[u].z) + b2b.z, ((xb4[u].w + hb4[u].w) + yb[u].w) + b2b.w);
+            *reinterpret_cast<float4*>(a.y + o) = ra;
+            *reinterpret_cast<float4*>(a.y + o + 128) = rb;
           }
         }
       }
