@@ -45,6 +45,16 @@ def test_cfg5_shape_tensor_path(gn, B):
     assert "tc_linear" not in prof32
 
 
+def test_cfg5_many_small_graphs(gn):
+    """300 graphs of 4 nodes / 5 edges: the graph rows (B >= 256) also take the tensor-core kernels (fused FFN, tc_linear)."""
+    w = W.make_workload("cfg5", B=300, n_nodes=4, n_edges=5)
+    layers = W.model_params("cfg5")
+    got, prof = _run(gn, layers, w, "auto")
+    _, ref = run_oracle(layers, w)
+    assert_parity(got, ref, BF16_TOL, "cfg5 small graphs")
+    assert prof["tc_ffn256"]["launches"] == 3 * 4, prof["tc_ffn256"]      # edge, node and graph FFN of each of the 4 cores
+
+
 def test_cfg3_shape_tensor_path(gn):
     """hidden 384 (3 output blocks: odd block count), node-only inputs, fully connected graphs of 8-24 nodes."""
     w = W.make_workload("cfg3", B=20, n_nodes=(8, 24))
