@@ -81,7 +81,7 @@ struct gnb_ctx {
   void* lin_cache = nullptr;
 };
 
-enum { ONCE_EDGE5 = 0, ONCE_PROJ_LN2, ONCE_PROJ_AGG1, ONCE_PROJ_OTHER, ONCE_TC_LIN, ONCE_TC_FFN, ONCE_WIDE, ONCE_NARROW2, ONCE_POOL };
+enum { ONCE_EDGE5 = 0, ONCE_PROJ_LN2, ONCE_PROJ_AGG1, ONCE_PROJ_OTHER, ONCE_TC_LIN, ONCE_TC_FFN, ONCE_TC_FFN384, ONCE_WIDE, ONCE_NARROW2, ONCE_POOL };
 // true exactly once per (context, key)
 static inline bool ctx_first(gnb_ctx* c, int key) {
   const uint64_t b = 1ull << key;

@@ -685,7 +685,7 @@ static int run_block_narrow(gnb_ctx* ctx, const gnb_graph* g, const LayerW& w, F
 int run_ffn_residual_fp32(gnb_ctx* ctx, int64_t R, int d, const gnb_ffn_params& f, const gnb_ln_params& ln2,
                           const float* x, const float* h, float* y) {
   if (R <= 0) return GNB_OK;
-  if (ctx->use_tc_lin && tc_ffn256_supported(R, d)) return launch_ffn256_tc(ctx, R, f, ln2, x, h, y);      // fused, hidden on chip
+  if (ctx->use_tc_lin && tc_ffn256_supported(R, d)) return launch_ffn256_tc(ctx, R, f, ln2, x, h, y, d);      // fused, hidden on chip
   // tensor-core precision modes: both Dense layers on the generic tcgen05 kernel with the hidden activation kept in bf16
   // (exactly what the down-projection's MMA consumes anyway: halves the HBM round trip of the 4d-wide hidden rows)
   bool bf16_hidden = false;

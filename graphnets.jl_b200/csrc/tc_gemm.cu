@@ -400,7 +400,7 @@ struct PackKey {
 struct PackCache { std::map<PackKey, __nv_bfloat16*> m; };
 
 // =====================================================================================================
-// Fused GNFeedForward + residuals for hidden width 256 (src/gnfeedforward.jl:27-31, src/gncore.jl:56-59):
+// Fused GNFeedForward + residuals for hidden width FH = 256 or 384 (src/gnfeedforward.jl:27-31, src/gncore.jl:56-59):
 //   y = x + h + W2 relu(W1 LN2(x) + b1) + b2
 // One 128-row tile per pass, persistent CTA, the 4H = 1024 wide hidden activation never leaves the SM (the generic path above
 // writes / reads it through HBM: 4 KB per row).  Per tile 8 hidden chunks of 128 units, software pipelined:
@@ -408,19 +408,26 @@ struct PackCache { std::map<PackKey, __nv_bfloat16*> m; };
 //   conv(c): Hd -> + b1 -> relu -> bf16, in place (DRAIN warps)               the A operand of the down projection (TS)
 //   down(c): D (TMEM, 256 fp32 columns) += relu(.)[chunk c] . W2[chunk c, :]   2 output blocks x 8 UMMAs (TS)
 // issued as up0 up1 down0 up2 down1 ... so that conv(c) runs under up(c+1).  TMEM: D 256 + Hd 2 x 128 = 512 columns.
+// FH = 384: D takes 384 columns, so there is ONE hidden buffer (up(c) conv(c) down(c) in sequence) and one A stage (96 KB).
 // 14 warps: 0-3 DRAIN (conversion), 4-7 A producers (LayerNorm -> bf16 slabs, next tile), 8-11 EPI (D + b2 + x + h -> y,
 // fragment layout), 12 MMA issuer (two slabs = 8 UMMAs per iteration), 13 weight loader (16 KB slabs, 5-stage ring: W1 slabs of chunk c, then W2 slabs of chunk c-1).
 // =====================================================================================================
-constexpr int F_H = 256, F_KS = F_H / 64, F_CH = 4 * F_H / 128;      // 4 K slabs, 8 hidden chunks
 constexpr int F_NW = 5;                                   // weight ring: 5 x 16 KB, consumed two slabs at a time
-constexpr int F_OFF_A = 0;                                // 2 stages x 4 slabs
-constexpr int F_OFF_W = 2 * F_KS * SLAB;
-constexpr int F_OFF_STAT = F_OFF_W + F_NW * SLAB;         // float2 stats[128]
-constexpr int F_OFF_B1 = F_OFF_STAT + 128 * 8;            // float b1[1024]
-constexpr int F_OFF_BAR = F_OFF_B1 + 4 * F_H * 4;
-constexpr int F_SMEM = F_OFF_BAR + 32 * 8 + 16 + 1024;
 constexpr int F_THREADS = 14 * 32;
 enum { FB_WFULL = 0, FB_WEMPTY = 5, FB_AFULL = 10, FB_AEMPTY = 12, FB_HIDFULL = 14, FB_HSREADY = 16, FB_ACCFULL = 18, FB_ACCFREE = 19 };
+template <int FH> struct FfnCfg {
+  static constexpr int KS = FH / 64;               // K slabs of the up projection
+  static constexpr int CH = 4 * FH / 128;          // hidden chunks
+  static constexpr int NB = FH / 128;              // output blocks of the down projection
+  static constexpr int NHD = FH <= 256 ? 2 : 1;    // hidden buffers in TMEM (D = FH columns, 512 in total)
+  static constexpr int NAS = FH <= 256 ? 2 : 1;    // A tile stages in shared memory
+  static constexpr int OFF_A = 0;
+  static constexpr int OFF_W = NAS * KS * SLAB;
+  static constexpr int OFF_STAT = OFF_W + F_NW * SLAB;      // float2 stats[128]
+  static constexpr int OFF_B1 = OFF_STAT + 128 * 8;         // float b1[4 FH]
+  static constexpr int OFF_BAR = OFF_B1 + 4 * FH * 4;
+  static constexpr int SMEM = OFF_BAR + 32 * 8 + 16 + 1024;
+};
 
 struct FfnArgs {
   const float* x;       // [R][256]
@@ -434,7 +441,11 @@ struct FfnArgs {
   const float *b1, *b2;
 };
 
-__global__ void __launch_bounds__(F_THREADS, 1) k_tc_ffn256(const FfnArgs a) {
+template <int FH>
+__global__ void __launch_bounds__(F_THREADS, 1) k_tc_ffn(const FfnArgs a) {
+  using Cfg = FfnCfg<FH>;
+  constexpr int F_H = FH, F_KS = Cfg::KS, F_CH = Cfg::CH, F_NB = Cfg::NB, NHD = Cfg::NHD, NAS = Cfg::NAS;
+  constexpr int F_OFF_A = Cfg::OFF_A, F_OFF_W = Cfg::OFF_W, F_OFF_STAT = Cfg::OFF_STAT, F_OFF_B1 = Cfg::OFF_B1, F_OFF_BAR = Cfg::OFF_BAR;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
@@ -464,11 +475,11 @@ __global__ void __launch_bounds__(F_THREADS, 1) k_tc_ffn256(const FfnArgs a) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
-  const uint32_t Dt = tmem, Hd0 = tmem + 256;      // D: columns [0, 256); Hd[b]: [256 + 128 b, +128)
+  const uint32_t Dt = tmem, Hd0 = tmem + F_H;      // D: columns [0, FH); Hd[b]: [FH + 128 b, +128)
   // the hidden chunks are independent terms of the down projection: every CTA starts at a different one, so that the
   // lock-stepped CTAs do not stream the same weight slab from the same L2 slice at the same time
-  const int crot = (int)(blockIdx.x & (F_CH - 1));
-  static_assert((F_CH & (F_CH - 1)) == 0, "chunk rotation uses a mask");
+  const int crot = (int)(blockIdx.x % F_CH);
+  auto rotc = [&](int c) { const int t = c + crot; return t < F_CH ? t : t - F_CH; };
 
   if (warp == 13) {
     // ===================================================== weight loader: slabs in the order the MMA warp consumes them
@@ -485,12 +496,13 @@ __global__ void __launch_bounds__(F_THREADS, 1) k_tc_ffn256(const FfnArgs a) {
     };
     for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
 #pragma unroll 1
-      for (int c = 0; c <= F_CH; c++) {
+      for (int c = 0; c < F_CH + NHD - 1; c++) {
         if (c < F_CH)
-          for (int ks = 0; ks < F_KS; ks++) load(a.w1 + (size_t)(((c + crot) & (F_CH - 1)) * F_KS + ks) * 8192);
-        if (c >= 1)
-          for (int nb = 0; nb < 2; nb++)
-            for (int kh = 0; kh < 2; kh++) load(a.w2 + (size_t)(nb * (4 * F_H / 64) + 2 * ((c - 1 + crot) & (F_CH - 1)) + kh) * 8192);
+          for (int ks = 0; ks < F_KS; ks++) load(a.w1 + (size_t)(rotc(c) * F_KS + ks) * 8192);
+        const int cc = c - (NHD - 1);
+        if (cc >= 0)
+          for (int nb = 0; nb < F_NB; nb++)
+            for (int kh = 0; kh < 2; kh++) load(a.w2 + (size_t)(nb * (4 * F_H / 64) + 2 * rotc(cc) + kh) * 8192);
       }
     }
   } else if (warp == 12) {
@@ -509,12 +521,12 @@ __global__ void __launch_bounds__(F_THREADS, 1) k_tc_ffn256(const FfnArgs a) {
       wd1 = umma_desc(base + F_OFF_W + ws1 * SLAB);
     };
     for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, tl++) {
-      const uint32_t st = tl & 1;
-      mbar_wait(BAR(FB_AFULL + st), (tl >> 1) & 1);
+      const uint32_t st = tl % NAS;
+      mbar_wait(BAR(FB_AFULL + st), (tl / NAS) & 1);
 #pragma unroll 1
-      for (int c = 0; c <= F_CH; c++) {
-        if (c < F_CH) {      // up projection of chunk c: K slabs (0,1) then (2,3)
-          const uint32_t Hd = Hd0 + 128 * (c & 1);
+      for (int c = 0; c < F_CH + NHD - 1; c++) {
+        if (c < F_CH) {      // up projection of chunk c: K slabs two at a time
+          const uint32_t Hd = Hd0 + 128 * (c % NHD);
 #pragma unroll 1
           for (int kp = 0; kp < F_KS / 2; kp++) {
             get_w2();
@@ -528,21 +540,21 @@ __global__ void __launch_bounds__(F_THREADS, 1) k_tc_ffn256(const FfnArgs a) {
               tc_commit(BAR(FB_WEMPTY + ws0));
               tc_commit(BAR(FB_WEMPTY + ws1));
               if (kp == F_KS / 2 - 1) {
-                tc_commit(BAR(FB_HIDFULL + (c & 1)));
+                tc_commit(BAR(FB_HIDFULL + (c % NHD)));
                 if (c == F_CH - 1) tc_commit(BAR(FB_AEMPTY + st));
               }
             }
             __syncwarp();
           }
         }
-        if (c >= 1) {        // down projection of chunk c - 1: one output block (both K halves) per iteration
-          const int cc = c - 1, hb = cc & 1;
+        if (c >= NHD - 1) {  // down projection of chunk c - (NHD - 1): one output block (both K halves) per iteration
+          const int cc = c - (NHD - 1), hb = cc % NHD;
           const uint32_t Hd = Hd0 + 128 * hb;
           mbar_wait(BAR(FB_HSREADY + hb), nhid[hb] & 1);      // conversion of this chunk done
           nhid[hb]++;
           if (cc == 0) mbar_wait(BAR(FB_ACCFREE), (tl & 1) ^ 1);      // D drained by the epilogue of the previous tile
 #pragma unroll 1
-          for (int nb = 0; nb < 2; nb++) {
+          for (int nb = 0; nb < F_NB; nb++) {
             get_w2();
             tc_fence_after();
             if (elect_one()) {
@@ -552,7 +564,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) k_tc_ffn256(const FfnArgs a) {
               for (int k4 = 0; k4 < 4; k4++) mma_ts(Dt + 128 * nb, Hd + 32 + 8 * k4, wd1 + 2 * k4, IDESC, 1u);
               tc_commit(BAR(FB_WEMPTY + ws0));
               tc_commit(BAR(FB_WEMPTY + ws1));
-              if (cc == F_CH - 1 && nb == 1) tc_commit(BAR(FB_ACCFULL));
+              if (cc == F_CH - 1 && nb == F_NB - 1) tc_commit(BAR(FB_ACCFULL));
             }
             __syncwarp();
           }
@@ -577,12 +589,12 @@ __global__ void __launch_bounds__(F_THREADS, 1) k_tc_ffn256(const FfnArgs a) {
     for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
 #pragma unroll 1
       for (int c = 0; c < F_CH; c++) {
-        const int hb = c & 1;
+        const int hb = c % NHD;
         mbar_wait(BAR(FB_HIDFULL + hb), nh[hb] & 1);
         nh[hb]++;
         tc_fence_after();
         uint32_t va[32], vb[32];
-        const float* bias = sB1 + ((c + crot) & (F_CH - 1)) * 128;
+        const float* bias = sB1 + rotc(c) * 128;
         const uint32_t t0 = Hd0 + 128 * hb + lane_base;
         TC_LD32(t0, va);
         TC_LD32(t0 + 32, vb);
@@ -611,20 +623,20 @@ __global__ void __launch_bounds__(F_THREADS, 1) k_tc_ffn256(const FfnArgs a) {
       const float* xs = a.x + 4 * c16;
 #pragma unroll 1
       for (int r0 = 0; r0 < 32; r0 += 4) {
-        float4 v[2][4];
+        float4 v[2][F_KS];
 #pragma unroll
         for (int p = 0; p < 2; p++) {
           int64_t row = row0 + r0 + 2 * p + hr;
           row = row < a.R ? row : a.R - 1;
 #pragma unroll
-          for (int j = 0; j < 4; j++) v[p][j] = __ldg(reinterpret_cast<const float4*>(xs + (size_t)row * F_H + 64 * j));
+          for (int j = 0; j < F_KS; j++) v[p][j] = __ldg(reinterpret_cast<const float4*>(xs + (size_t)row * F_H + 64 * j));
         }
         float sum[2], sq[2];
 #pragma unroll
         for (int p = 0; p < 2; p++) {
           float t = 0.f;
 #pragma unroll
-          for (int j = 0; j < 4; j++) t += (v[p][j].x + v[p][j].y) + (v[p][j].z + v[p][j].w);
+          for (int j = 0; j < F_KS; j++) t += (v[p][j].x + v[p][j].y) + (v[p][j].z + v[p][j].w);
           sum[p] = t;
         }
 #pragma unroll
@@ -636,7 +648,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) k_tc_ffn256(const FfnArgs a) {
           const float mu = sum[p] * (1.0f / F_H);
           float t = 0.f;
 #pragma unroll
-          for (int j = 0; j < 4; j++) {
+          for (int j = 0; j < F_KS; j++) {
             const float dx = v[p][j].x - mu, dy = v[p][j].y - mu, dz = v[p][j].z - mu, dw = v[p][j].w - mu;
             t += (dx * dx + dy * dy) + (dz * dz + dw * dw);
           }
@@ -653,8 +665,8 @@ __global__ void __launch_bounds__(F_THREADS, 1) k_tc_ffn256(const FfnArgs a) {
         }
       }
       __syncwarp();
-      const uint32_t st = tl & 1;
-      mbar_wait(BAR(FB_AEMPTY + st), ((tl >> 1) & 1) ^ 1);
+      const uint32_t st = tl % NAS;
+      mbar_wait(BAR(FB_AEMPTY + st), ((tl / NAS) & 1) ^ 1);
 #pragma unroll 1
       for (int ks = 0; ks < F_KS; ks++) {
         const float4 g4 = __ldg(reinterpret_cast<const float4*>(a.gamma + 64 * ks + 4 * c16));
@@ -699,19 +711,21 @@ __global__ void __launch_bounds__(F_THREADS, 1) k_tc_ffn256(const FfnArgs a) {
     const int dq = warp & 3;
     const uint32_t lane_base = ((uint32_t)(dq * 32)) << 16;
     const int qr = lane >> 2, cq = 2 * (lane & 3);
-    const float4 b2a = __ldg(reinterpret_cast<const float4*>(a.b2) + lane), b2b = __ldg(reinterpret_cast<const float4*>(a.b2) + 32 + lane);
+    float4 b2v[F_NB];
+#pragma unroll
+    for (int s2 = 0; s2 < F_NB; s2++) b2v[s2] = __ldg(reinterpret_cast<const float4*>(a.b2) + 32 * s2 + lane);
     uint32_t tl = 0;
     for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, tl++) {
       const int64_t row0 = (int64_t)tile * TM + 32 * dq;
       mbar_wait(BAR(FB_ACCFULL), tl & 1);
       tc_fence_after();
 #pragma unroll 1
-      for (int st2 = 0; st2 < 8; st2++) {      // (64-column chunk, row half)
+      for (int st2 = 0; st2 < 2 * (F_H / 64); st2++) {      // (64-column chunk, row half)
         const int ch = st2 >> 1, hh = st2 & 1;
         uint32_t dreg[32];
         TC_LD_FRAG64(Dt + lane_base + ((uint32_t)(16 * hh) << 16) + 64 * ch, dreg);
         tc_wait_ld();
-        if (st2 == 7) {
+        if (st2 == 2 * (F_H / 64) - 1) {
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(BAR(FB_ACCFREE));
@@ -730,26 +744,29 @@ __global__ void __launch_bounds__(F_THREADS, 1) k_tc_ffn256(const FfnArgs a) {
       const int64_t left = a.R - row0;
       const int rows = left < 0 ? 0 : (left > 32 ? 32 : (int)left);
 #pragma unroll 1
-      for (int i0 = 0; i0 < rows; i0 += 4) {
-        float4 ya[4], yb[4], xa[4], xb4[4], ha[4], hb4[4];
+      for (int i0 = 0; i0 < rows; i0 += 2) {
+        float4 yy[2][F_NB], xx[2][F_NB], hh2[2][F_NB];      // 2 rows x F_NB 512-byte segments in flight
 #pragma unroll
-        for (int u = 0; u < 4; u++) {
+        for (int u = 0; u < 2; u++) {
           const int64_t r = row0 + (i0 + u < rows ? i0 + u : rows - 1);
           const size_t o = (size_t)r * F_H + 4 * lane;
-          ya[u] = __ldcg(reinterpret_cast<const float4*>(a.y + o)); yb[u] = __ldcg(reinterpret_cast<const float4*>(a.y + o + 128));
-          xa[u] = __ldg(reinterpret_cast<const float4*>(a.x + o)); xb4[u] = __ldg(reinterpret_cast<const float4*>(a.x + o + 128));
-          ha[u] = __ldg(reinterpret_cast<const float4*>(a.h + o)); hb4[u] = __ldg(reinterpret_cast<const float4*>(a.h + o + 128));
+#pragma unroll
+          for (int s2 = 0; s2 < F_NB; s2++) {
+            yy[u][s2] = __ldcg(reinterpret_cast<const float4*>(a.y + o + 128 * s2));
+            xx[u][s2] = __ldg(reinterpret_cast<const float4*>(a.x + o + 128 * s2));
+            hh2[u][s2] = __ldg(reinterpret_cast<const float4*>(a.h + o + 128 * s2));
+          }
         }
 #pragma unroll
-        for (int u = 0; u < 4; u++) {
+        for (int u = 0; u < 2; u++) {
           if (i0 + u < rows) {
             const size_t o = (size_t)(row0 + i0 + u) * F_H + 4 * lane;
-            const float4 ra = make_float4(((xa[u].x + ha[u].x) + ya[u].x) + b2a.x, ((xa[u].y + ha[u].y) + ya[u].y) + b2a.y,
-                                          ((xa[u].z + ha[u].z) + ya[u].z) + b2a.z, ((xa[u].w + ha[u].w) + ya[u].w) + b2a.w);
-            const float4 rb = make_float4(((xb4[u].x + hb4[u].x) + yb[u].x) + b2b.x, ((xb4[u].y + hb4[u].y) + yb[u].y) + b2b.y,
-                                          ((xb4[u].z + hb4[u].z) + yb[u].z) + b2b.z, ((xb4[u].w + hb4[u].w) + yb[u].w) + b2b.w);
-            *reinterpret_cast<float4*>(a.y + o) = ra;
-            *reinterpret_cast<float4*>(a.y + o + 128) = rb;
+#pragma unroll
+            for (int s2 = 0; s2 < F_NB; s2++) {
+              const float4 X = xx[u][s2], Hh = hh2[u][s2], Y = yy[u][s2], Bv = b2v[s2];
+              *reinterpret_cast<float4*>(a.y + o + 128 * s2) = make_float4(((X.x + Hh.x) + Y.x) + Bv.x, ((X.y + Hh.y) + Y.y) + Bv.y,
+                                                                         ((X.z + Hh.z) + Y.z) + Bv.z, ((X.w + Hh.w) + Y.w) + Bv.w);
+            }
           }
         }
       }
@@ -847,11 +864,11 @@ int launch_linear_tc(gnb_ctx* ctx, const LinArgs& a) {
   return GNB_OK;
 }
 
-bool tc_ffn256_supported(int64_t R, int d) { return d == F_H && R >= 256 && R <= 0x7fffffffLL; }
+bool tc_ffn256_supported(int64_t R, int d) { return (d == 256 || d == 384) && R >= 256 && R <= 0x7fffffffLL; }
 
-int launch_ffn256_tc(gnb_ctx* ctx, int64_t R, const gnb_ffn_params& f, const gnb_ln_params& ln2, const float* x, const float* h, float* y) {
-  if (R <= 0) return GNB_OK;
-  if (ctx_first(ctx, ONCE_TC_FFN)) GNB_CUDA(cudaFuncSetAttribute(k_tc_ffn256, cudaFuncAttributeMaxDynamicSharedMemorySize, F_SMEM));
+template <int FH>
+static int launch_ffn_t(gnb_ctx* ctx, int once_key, int64_t R, const gnb_ffn_params& f, const gnb_ln_params& ln2, const float* x, const float* h, float* y) {
+  if (ctx_first(ctx, once_key)) GNB_CUDA(cudaFuncSetAttribute(k_tc_ffn<FH>, cudaFuncAttributeMaxDynamicSharedMemorySize, FfnCfg<FH>::SMEM));
   FfnArgs a{};
   a.x = x; a.h = h; a.y = y; a.R = R; a.num_tiles = (int)ceil_div(R, TM);
   a.gamma = ln2.gamma; a.beta = ln2.beta; a.eps = ln2.eps; a.eps_mode = ln2.eps_mode;
@@ -860,17 +877,23 @@ int launch_ffn256_tc(gnb_ctx* ctx, int64_t R, const gnb_ffn_params& f, const gnb
   PackSrc p1{}, p2{};
   for (int s = 0; s < 3; s++) { p1.d[s] = p2.d[s] = 1 << 30; }
   k1.model = k2.model = ctx->cur_model_id;
-  k1.W[0] = f.W1; k1.d[0] = F_H; k1.Nout = 4 * F_H; k1.ldw = 4 * F_H; k1.ng = 1;
-  k2.W[0] = f.W2; k2.d[0] = 4 * F_H; k2.Nout = F_H; k2.ldw = F_H; k2.ng = 1;
+  k1.W[0] = f.W1; k1.d[0] = FH; k1.Nout = 4 * FH; k1.ldw = 4 * FH; k1.ng = 1;
+  k2.W[0] = f.W2; k2.d[0] = 4 * FH; k2.Nout = FH; k2.ldw = FH; k2.ng = 1;
   p1.nsrc = p2.nsrc = 1;
-  p1.W[0] = f.W1; p1.d[0] = F_H;
-  p2.W[0] = f.W2; p2.d[0] = 4 * F_H;
-  GNB_TRY(get_pack(ctx, k1, p1, 4 * F_H, F_H, 4 * F_H, 1, &a.w1));
-  GNB_TRY(get_pack(ctx, k2, p2, F_H, 4 * F_H, F_H, 1, &a.w2));
+  p1.W[0] = f.W1; p1.d[0] = FH;
+  p2.W[0] = f.W2; p2.d[0] = 4 * FH;
+  GNB_TRY(get_pack(ctx, k1, p1, 4 * FH, FH, 4 * FH, 1, &a.w1));
+  GNB_TRY(get_pack(ctx, k2, p2, FH, 4 * FH, FH, 1, &a.w2));
   // canonical work of the reference FFN: 16 d^2 flop per row, x / h read and y written once
-  Launch L(ctx, "tc_ffn256", 4.0 * 3 * F_H * R, 16.0 * F_H * F_H * R);
+  Launch L(ctx, FH == 256 ? "tc_ffn256" : "tc_ffn384", 4.0 * 3 * FH * R, 16.0 * FH * FH * R);
   const int grid = a.num_tiles < ctx->sm_count ? a.num_tiles : ctx->sm_count;
-  k_tc_ffn256<<<grid, F_THREADS, F_SMEM, ctx->stream>>>(a);
+  k_tc_ffn<FH><<<grid, F_THREADS, FfnCfg<FH>::SMEM, ctx->stream>>>(a);
   GNB_CUDA(cudaGetLastError());
   return GNB_OK;
+}
+
+int launch_ffn256_tc(gnb_ctx* ctx, int64_t R, const gnb_ffn_params& f, const gnb_ln_params& ln2, const float* x, const float* h, float* y, int d) {
+  if (R <= 0) return GNB_OK;
+  if (d == 256) return launch_ffn_t<256>(ctx, ONCE_TC_FFN, R, f, ln2, x, h, y);
+  return launch_ffn_t<384>(ctx, ONCE_TC_FFN384, R, f, ln2, x, h, y);
 }

@@ -8,6 +8,6 @@ bool tc_lin_supported(const LinArgs& a);
 int launch_linear_tc(gnb_ctx* ctx, const LinArgs& a);
 void tc_lin_cache_free(void* cache);
 
-// fused GNFeedForward + residuals, y = x + h + W2 relu(W1 LN2(x) + b1) + b2, for hidden width 256 (hidden activation on chip)
+// fused GNFeedForward + residuals, y = x + h + W2 relu(W1 LN2(x) + b1) + b2, for hidden width 256 or 384 (hidden activation on chip)
 bool tc_ffn256_supported(int64_t R, int d);
-int launch_ffn256_tc(gnb_ctx* ctx, int64_t R, const gnb_ffn_params& f, const gnb_ln_params& ln2, const float* x, const float* h, float* y);
+int launch_ffn256_tc(gnb_ctx* ctx, int64_t R, const gnb_ffn_params& f, const gnb_ln_params& ln2, const float* x, const float* h, float* y, int d);
