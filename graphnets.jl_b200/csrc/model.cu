@@ -429,8 +429,9 @@ static int run_block_fp32(gnb_ctx* ctx, const gnb_graph* g, const gnb_block_para
       GNB_TRY(launch_linear(ctx, la));
       la.src[0] = mk_src(x.n, bn_, b.We + (size_t)(a + bn_) * p, lnn);
       la.out = Pr;
-      GNB_TRY(launch_linear(ctx, la));
+      if (!(ctx->use_tc_lin && c > 0)) GNB_TRY(launch_linear(ctx, la));      // else: launched below, with the per-graph row folded in
     }
+    bool pu_folded = false;
     if (c > 0) {
       Pu = arena_ptr<float>(ctx->arena, (size_t)B * p, &rc);
       if (rc != GNB_OK) return rc;
@@ -440,6 +441,17 @@ static int run_block_fp32(gnb_ctx* ctx, const gnb_graph* g, const gnb_block_para
       la.bias = b.be;
       la.out = Pu;
       GNB_TRY(launch_linear(ctx, la));
+      if (ctx->use_tc_lin && bn_ > 0) {
+        // tensor-core precision modes: P_r'[v] = P_r[v] + P_u[graph(v)] once per node (N rows), so that the per-edge launch
+        // gathers two rows instead of three (its epilogue is what bounds it)
+        LinArgs lr{};
+        lr.R = N; lr.Nout = p; lr.ldw = p; lr.nsrc = 1; lr.ldo = p;
+        lr.src[0] = mk_src(x.n, bn_, b.We + (size_t)(a + bn_) * p, lnn);
+        lr.add[lr.nadd++] = LinAdd{Pu, g->node_graph, p};
+        lr.out = Pr;
+        GNB_TRY(launch_linear(ctx, lr));
+        pu_folded = true;
+      }
     }
     LinArgs la{};
     la.R = E; la.Nout = p; la.ldw = p; la.ldo = p; la.out = h.e;
@@ -448,8 +460,8 @@ static int run_block_fp32(gnb_ctx* ctx, const gnb_graph* g, const gnb_block_para
       la.add[la.nadd++] = LinAdd{Ps, g->edge_src, p};
       la.add[la.nadd++] = LinAdd{Pr, g->edge_dst, p};
     }
-    if (Pu) la.add[la.nadd++] = LinAdd{Pu, g->edge_graph, p};
-    else la.bias = b.be;
+    if (Pu && !pu_folded) la.add[la.nadd++] = LinAdd{Pu, g->edge_graph, p};
+    else if (!Pu) la.bias = b.be;
     GNB_TRY(launch_linear(ctx, la));
     // edge -> node aggregation over the receiver CSR (src/nodefninput.jl:3)
     if (q > 0 || r > 0) {
