@@ -232,7 +232,7 @@ def run_ours(args, rank, world, local_rank):
     for hb, f in ((h_oe, y.ef), (h_on, y.nf), (h_og, y.gf)):
         assert torch.equal(hb, f.compact.cpu()), "host-ABI result differs from the device-resident result"
 
-    # Software-pipelined variant (the one reported): two host threads, each with its own context + stream + pinned output
+    # Software-pipelined variant (opt-in, --e2e-streams 2): two host threads, each with its own context + stream + pinned output
     # buffers, alternate batches through the same synchronous public calls, so the PCIe copies and the lowering of one batch
     # overlap the forward of the other.  Every step still uploads its own inputs and downloads its own results.
     e2e_s, e2e_mode = e2e_single_s, "single stream"
@@ -352,7 +352,9 @@ def main():
     ap.add_argument("--graphs", type=int, default=4096, help="graphs per GPU")
     ap.add_argument("--ref-graphs", type=int, default=32, help="graphs per step of the CPU reference sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--e2e-streams", type=int, default=2, help="1: strictly sequential e2e steps; 2: two pipelined host threads")
+    # 2 = two pipelined host threads / contexts (measured 8.2 ms per cfg4 step at 1, 2 and 4 GPUs, but one 8-GPU run trapped inside
+    # a forward - not understood yet), so the default stays the strictly sequential single-stream measurement
+    ap.add_argument("--e2e-streams", type=int, default=1, help="1: strictly sequential e2e steps; 2: two pipelined host threads")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     rank = int(os.environ.get("RANK", "0"))
