@@ -1,4 +1,9 @@
-"""-m gpu: double-buffered host-buffer forward with two contexts (runs last: file name sorts after the other GPU tests)."""
+"""-m gpu: double-buffered host-buffer forward with two contexts (runs last: file name sorts after the other GPU tests).
+
+Opt-in (GNB_TEST_TWO_CONTEXTS=1): the mode is experimental - it ran clean at 1, 2 and 4 GPUs, but one 8-GPU bench run
+trapped inside a forward and the cause is not understood yet."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -14,6 +19,7 @@ def gn():
     return g
 
 
+@pytest.mark.skipif(os.environ.get("GNB_TEST_TWO_CONTEXTS") != "1", reason="experimental two-context pipelining: opt-in")
 def test_two_contexts_pipelined_host_forward(gn):
     """Double-buffered input pipeline: two host threads, each with its own context and stream, alternate batches through the
     synchronous host-buffer calls (bench.py `e2e`).  The library serialises the forwards of different contexts on the device
