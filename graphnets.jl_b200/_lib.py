@@ -6,9 +6,11 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libgnb200.so")
+# GNB_LIB_VARIANT selects a test-only build of the library (build.py VARIANTS); the product path never sets it
+_VARIANT = os.environ.get("GNB_LIB_VARIANT", "")
+LIB_PATH = os.path.join(HERE, "libgnb200_%s.so" % _VARIANT if _VARIANT else "libgnb200.so")
 
-GNB_OK, GNB_ERR_INVALID, GNB_ERR_CUDA, GNB_ERR_OOM, GNB_ERR_UNSUPPORTED = 0, -1, -2, -3, -4
+GNB_OK, GNB_ERR_INVALID, GNB_ERR_CUDA, GNB_ERR_OOM, GNB_ERR_UNSUPPORTED, GNB_ERR_TIMEOUT = 0, -1, -2, -3, -4, -5
 PREC_FP32, PREC_BF16, PREC_AUTO = 0, 2, 3
 ADJ_F32, ADJ_U8, ADJ_I32 = 0, 1, 2
 LAYER_BLOCK, LAYER_CORE = 0, 1
@@ -86,6 +88,10 @@ class GnbError(RuntimeError):
     pass
 
 
+class GnbTimeout(GnbError):
+    """GNB_ERR_TIMEOUT: a kernel watchdog fired; the context is still usable, that forward's results are not."""
+
+
 def _load():
     if not os.path.exists(LIB_PATH):
         raise ImportError(
@@ -112,4 +118,6 @@ def check(rc):
         raise AssertionError(msg)
     if rc == GNB_ERR_OOM:
         raise MemoryError(msg)
+    if rc == GNB_ERR_TIMEOUT:
+        raise GnbTimeout("gnb200 error %d: %s" % (rc, msg))
     raise GnbError("gnb200 error %d: %s" % (rc, msg))

@@ -32,31 +32,52 @@ def _digest():
     return h.hexdigest()
 
 
+# Test-only variants of the library: {name: (sources recompiled, extra flags)}; every other object is shared with the
+# product build.  `oldproj` keeps round 1's k_tc_proj barrier protocol so that tests/test_gpu_watchdog.py can reproduce
+# its dead-lock (GNB_LIB_VARIANT=oldproj selects it in _lib.py); the product never loads a variant.
+VARIANTS = {"oldproj": (["tc.cu"], ["-DGNB_OLD_PROJ_PROTOCOL"])}
+
+
+def variant_path(name):
+    return os.path.join(HERE, "libgnb200_%s.so" % name)
+
+
 def build(force=False, verbose=False):
     os.makedirs(BUILD, exist_ok=True)
     stamp = os.path.join(BUILD, "stamp")
     dig = _digest()
-    if not force and os.path.exists(OUT) and os.path.exists(stamp) and open(stamp).read() == dig:
+    outs = [OUT] + [variant_path(v) for v in VARIANTS]
+    if not force and all(os.path.exists(o) for o in outs) and os.path.exists(stamp) and open(stamp).read() == dig:
         return OUT
 
-    def cc(src):
-        obj = os.path.join(BUILD, src.replace(".cu", ".o"))
-        cmd = [NVCC] + FLAGS + ["-c", os.path.join(CSRC, src), "-o", obj]
+    def cc(job):
+        src, tag, extra = job
+        obj = os.path.join(BUILD, src.replace(".cu", tag + ".o"))
+        cmd = [NVCC] + FLAGS + extra + ["-c", os.path.join(CSRC, src), "-o", obj]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError("nvcc failed for %s:\n%s\n%s" % (src, r.stdout, r.stderr))
-        if verbose:
+        if verbose and not tag:
             sys.stderr.write(r.stderr)
         return obj
 
-    with ThreadPoolExecutor(max_workers=len(SOURCES)) as ex:
-        objs = list(ex.map(cc, SOURCES))
-    # cudart is linked statically (nvcc default) and the driver API is resolved at run time via
-    # cudaGetDriverEntryPoint, so the .so loads on a box without libcuda (symbol checks on CPU).
-    cmd = [NVCC, "-shared", "-o", OUT] + objs
-    r = subprocess.run(cmd, capture_output=True, text=True)
-    if r.returncode != 0:
-        raise RuntimeError("link failed:\n%s\n%s" % (r.stdout, r.stderr))
+    jobs = [(s, "", []) for s in SOURCES]
+    for v, (srcs, extra) in VARIANTS.items():
+        jobs += [(s, "_" + v, extra) for s in srcs]
+    with ThreadPoolExecutor(max_workers=len(jobs)) as ex:
+        objs = dict(zip([(j[0], j[1]) for j in jobs], ex.map(cc, jobs)))
+
+    def link(out, tag, srcs):
+        # cudart is linked statically (nvcc default) and the driver API is resolved at run time via
+        # cudaGetDriverEntryPoint, so the .so loads on a box without libcuda (symbol checks on CPU).
+        cmd = [NVCC, "-shared", "-o", out] + [objs[(s, tag if s in srcs else "")] for s in SOURCES]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError("link failed:\n%s\n%s" % (r.stdout, r.stderr))
+
+    link(OUT, "", [])
+    for v, (srcs, _) in VARIANTS.items():
+        link(variant_path(v), "_" + v, srcs)
     with open(stamp, "w") as f:
         f.write(dig)
     return OUT

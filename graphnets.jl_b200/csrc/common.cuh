@@ -46,6 +46,12 @@ struct Arena {
   void release();
 };
 
+// Kernel watchdog arguments of the tcgen05 kernels (tc_ptx.cuh): device-global abort flag + wait limit.
+struct WatchArgs {
+  int* flag;                        // gnb_ctx::d_abort
+  unsigned long long limit_ns;      // GNB_WATCHDOG_MS (default 10 s)
+};
+
 struct ProfRec { int tag; cudaEvent_t a, b; double bytes, flops; };
 struct ProfTag { const char* name; int64_t launches; double ms, bytes, flops; };
 
@@ -79,7 +85,17 @@ struct gnb_ctx {
   bool use_tc_lin = false;
   uint64_t cur_model_id = 0;
   void* lin_cache = nullptr;
+  // kernel watchdog: raised by a tcgen05 kernel whose mbarrier wait timed out; mirrored to pinned host memory behind every forward
+  int* d_abort = nullptr;
+  int* h_abort = nullptr;
+  unsigned long long wd_limit_ns = 10000000000ull;
+  // test hook (GNB_DEBUG_PROJ_DRAIN_DELAY_NS): stalls the accumulator-drain warps of k_tc_proj per tile, to exercise the
+  // barrier protocol with one role far behind the others
+  unsigned int dbg_proj_drain_delay_ns = 0;
 };
+static inline WatchArgs ctx_watch(const gnb_ctx* c) { return WatchArgs{c->d_abort, c->wd_limit_ns}; }
+// Returns GNB_ERR_TIMEOUT (and clears the flag) if a kernel watchdog fired; call after the stream has been synchronised.
+int ctx_check_watchdog(gnb_ctx* c);
 
 enum { ONCE_EDGE5 = 0, ONCE_PROJ_LN2, ONCE_PROJ_AGG1, ONCE_PROJ_OTHER, ONCE_TC_LIN, ONCE_TC_FFN, ONCE_TC_FFN384, ONCE_WIDE, ONCE_NARROW2, ONCE_POOL };
 // true exactly once per (context, key)

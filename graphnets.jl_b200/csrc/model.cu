@@ -6,6 +6,7 @@
 #include "smallk.cuh"
 #include "tc_gemm.cuh"
 #include <atomic>
+#include <stdlib.h>
 #include <mutex>
 
 // ------------------------------------------------------------------ errors / arena / ctx
@@ -62,10 +63,13 @@ void Arena::release() {
   chunks.clear();
 }
 
-// Forwards of DIFFERENT contexts on the same device are serialised on the device (stream-ordered, the host does not block):
-// every persistent tcgen05 kernel is sized to own all SMs / tensor memory, and two of them from different streams running
-// interleaved dead-lock (observed at 4096 graphs: bounded spins trap after ~70 s).  Copies, the lowering and the host-side
-// work of one context still overlap the forward of the other - which is what a double-buffered input pipeline needs.
+// Forwards of DIFFERENT contexts on the same device are ordered on the device (stream-ordered event chain, the host does not
+// block): every persistent tcgen05 kernel is sized to own all SMs, so two forwards interleaved kernel by kernel only take
+// turns at the SMs and evict each other's L2 working set.  This is a THROUGHPUT choice, not a correctness requirement: the
+// round-1 dead-lock of interleaved forwards was a barrier-protocol bug of k_tc_proj (fixed, see tc.cu) and
+// tests/test_zz_gpu_two_contexts.py runs the interleaved mode (GNB_CHAIN_FORWARDS=0) against the oracle-checked result.
+// Copies, the lowering and the host-side work of one context still overlap the forward of the other - which is what a
+// double-buffered input pipeline needs.
 static std::mutex g_chain_mu;
 static cudaEvent_t g_chain_ev[64] = {};
 static gnb_ctx* g_chain_ctx[64] = {};
@@ -83,6 +87,20 @@ extern "C" gnb_ctx* gnb_ctx_create(int device, int* err) {
   gnb_ctx* c = new gnb_ctx();
   c->device = device;
   cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device);
+  if (cudaMalloc((void**)&c->d_abort, 256) != cudaSuccess || cudaMemset(c->d_abort, 0, 256) != cudaSuccess ||
+      cudaHostAlloc((void**)&c->h_abort, sizeof(int), cudaHostAllocDefault) != cudaSuccess) {
+    gnb_set_error("gnb_ctx_create: watchdog flag allocation failed: %s", cudaGetErrorString(cudaGetLastError()));
+    if (c->d_abort) cudaFree(c->d_abort);
+    delete c;
+    if (err) *err = GNB_ERR_CUDA;
+    return nullptr;
+  }
+  *c->h_abort = 0;
+  if (const char* e = getenv("GNB_WATCHDOG_MS")) {
+    const long long ms = atoll(e);
+    if (ms > 0) c->wd_limit_ns = (unsigned long long)ms * 1000000ull;
+  }
+  if (const char* e = getenv("GNB_DEBUG_PROJ_DRAIN_DELAY_NS")) c->dbg_proj_drain_delay_ns = (unsigned int)atoi(e);
   if (err) *err = GNB_OK;
   return c;
 }
@@ -96,6 +114,8 @@ extern "C" int gnb_ctx_destroy(gnb_ctx* c) {
     if (c->device < 64 && g_chain_ctx[c->device] == c) { g_chain_ctx[c->device] = nullptr; g_chain_ev[c->device] = nullptr; }
   }
   if (c->done_ev) cudaEventDestroy(c->done_ev);
+  if (c->d_abort) cudaFree(c->d_abort);
+  if (c->h_abort) cudaFreeHost(c->h_abort);
   tc_lin_cache_free(c->lin_cache);
   if (c->pipe.copy) {
     cudaStreamDestroy(c->pipe.copy);
@@ -113,11 +133,22 @@ extern "C" int gnb_ctx_set_stream(gnb_ctx* c, void* s) {
   c->stream = (cudaStream_t)s;
   return GNB_OK;
 }
+// Kernel watchdog (tc_ptx.cuh): the flag is mirrored to pinned host memory behind every forward; a raised flag turns the
+// next synchronising call of this context into GNB_ERR_TIMEOUT and is then cleared (the context stays usable).
+int ctx_check_watchdog(gnb_ctx* c) {
+  if (!c->h_abort || *c->h_abort == 0) return GNB_OK;
+  *c->h_abort = 0;
+  cudaMemsetAsync(c->d_abort, 0, sizeof(int), c->stream);
+  cudaStreamSynchronize(c->stream);
+  gnb_set_error("kernel watchdog: a barrier wait inside a tcgen05 kernel exceeded %llu ms (protocol dead-lock); the kernel "
+                "was drained, the results of that forward are invalid", c->wd_limit_ns / 1000000ull);
+  return GNB_ERR_TIMEOUT;
+}
 extern "C" int gnb_sync(gnb_ctx* c) {
   GNB_CHECK(c, "gnb_sync: null ctx");
   GNB_CUDA(cudaSetDevice(c->device));
   GNB_CUDA(cudaStreamSynchronize(c->stream));
-  return GNB_OK;
+  return ctx_check_watchdog(c);
 }
 extern "C" int64_t gnb_ctx_launch_count(const gnb_ctx* c) { return c ? c->launches : 0; }
 
@@ -871,13 +902,18 @@ static int forward_device_impl(gnb_ctx* ctx, const gnb_model* m, const gnb_graph
 
 static int forward_device(gnb_ctx* ctx, const gnb_model* m, const gnb_graph* g, const float* ef, const float* nf,
                           const float* gf, float* out_ef, float* out_nf, float* out_gf, int precision, bool reset_arena) {
-  if (!ctx || ctx->device < 0 || ctx->device >= 64)
-    return forward_device_impl(ctx, m, g, ef, nf, gf, out_ef, out_nf, out_gf, precision, reset_arena);
+  const char* chain_env = getenv("GNB_CHAIN_FORWARDS");
+  if (!ctx || ctx->device < 0 || ctx->device >= 64 || (chain_env && atoi(chain_env) == 0)) {
+    const int rc0 = forward_device_impl(ctx, m, g, ef, nf, gf, out_ef, out_nf, out_gf, precision, reset_arena);
+    if (ctx && ctx->h_abort) cudaMemcpyAsync(ctx->h_abort, ctx->d_abort, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream);
+    return rc0;
+  }
   std::lock_guard<std::mutex> lk(g_chain_mu);      // held while the kernels are enqueued (host time only)
   const int d = ctx->device;
   cudaSetDevice(d);
   if (g_chain_ctx[d] && g_chain_ctx[d] != ctx && g_chain_ev[d]) cudaStreamWaitEvent(ctx->stream, g_chain_ev[d], 0);
   const int rc = forward_device_impl(ctx, m, g, ef, nf, gf, out_ef, out_nf, out_gf, precision, reset_arena);
+  cudaMemcpyAsync(ctx->h_abort, ctx->d_abort, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream);
   if (!ctx->done_ev) cudaEventCreateWithFlags(&ctx->done_ev, cudaEventDisableTiming);
   if (ctx->done_ev && cudaEventRecord(ctx->done_ev, ctx->stream) == cudaSuccess) { g_chain_ev[d] = ctx->done_ev; g_chain_ctx[d] = ctx; }
   return rc;
@@ -951,7 +987,7 @@ extern "C" int gnb_model_forward_host(gnb_ctx* ctx, const gnb_model* m, const gn
   if (d_og && out_gf) GNB_CUDA(cudaMemcpyAsync(out_gf, d_og, og * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
   GNB_CUDA(cudaStreamSynchronize(ctx->stream));
   GNB_CUDA(cudaStreamSynchronize(P.copy));
-  return GNB_OK;
+  return ctx_check_watchdog(ctx);
 }
 
 static int forward_by_reference(gnb_ctx* ctx, const gnb_graph* g, const gnb_layer* layers, int n, const float* ef,

@@ -51,13 +51,26 @@ struct ProjArgs {
   const __nv_bfloat16* wpack;
   float eps;
   int eps_mode;
+  WatchArgs wd;                   // kernel watchdog (tc_ptx.cuh)
+  unsigned int dbg_drain_delay_ns;   // test hook: stall the drain warps per tile (gnb_ctx::dbg_proj_drain_delay_ns)
 };
 
 // smem: A[2] (32 KB each) | W[NBLK] (32 KB each, resident) | barriers
 __host__ __device__ constexpr int pj_off_w() { return 2 * BLK_BYTES; }
 __host__ __device__ constexpr int pj_off_misc(int nblk) { return (2 + nblk) * BLK_BYTES; }
 __host__ __device__ constexpr int pj_smem(int nblk) { return pj_off_misc(nblk) + 256 + 1024; }
-enum { PB_WFULL = 0, PB_AFULL = 2, PB_AEMPTY = 4, PB_OUTDONE = 6, PB_ACCFREE = 8 };
+// Barrier protocol (every waiter sits inside the back-pressure loop of the barrier it waits on, so a 1-bit phase parity can
+// never alias - no producer can complete phase n + 1 of a barrier before every waiter has observed phase n):
+//   AFULL[st]   producers (128 arrivals) -> MMA warp          next phase needs AEMPTY[st] <- MMA warp after it saw AFULL
+//   AEMPTY[st]  MMA commit -> producers                       next phase needs AFULL[st]  <- producers after they saw AEMPTY
+//   ASEEN[st]   MMA warp (after it saw AFULL) -> drain warps  next phase needs ACCFREE[st] <- drain warps after they saw ASEEN
+//   OUTDONE[st] MMA commit -> drain warps                     next phase needs ACCFREE[st] <- drain warps after they saw OUTDONE
+//   ACCFREE[st] drain warps (128 arrivals) -> MMA warp        next phase needs OUTDONE[st] <- MMA warp after it saw ACCFREE
+// Round 1 let the drain warps wait on AFULL directly (they need the producers' sum2 rows): they are NOT in AFULL's loop -
+// the producers only need the MMA warp to refill a stage - so a drain warp delayed by more than one tile found AFULL two
+// phases ahead, read the aliased parity as "not yet complete" and waited forever (the dead-lock of the two-context mode,
+// reproduced with GNB_DEBUG_PROJ_DRAIN_DELAY_NS under -DGNB_OLD_PROJ_PROTOCOL, tests/test_gpu_watchdog.py).
+enum { PB_WFULL = 0, PB_AFULL = 2, PB_AEMPTY = 4, PB_OUTDONE = 6, PB_ACCFREE = 8, PB_ASEEN = 10 };
 constexpr int PJ_THREADS = 10 * 32;
 
 // Pipelined over tiles: warps 4-7 build the bf16 A operand of tile t+1 (double buffered) while warp 8 issues the MMAs
@@ -74,12 +87,15 @@ __global__ void __launch_bounds__(PJ_THREADS, NBLK == 1 ? 2 : 1) k_tc_proj(const
   const uint32_t bar0 = smem_u32(bars);
   auto BAR = [&](int i) { return bar0 + 8u * (uint32_t)i; };
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  Watch wd{a.wd.flag, a.wd.limit_ns, false};
+#define mbar_wait(b, p) mbar_wait_w((b), (p), wd)
   constexpr uint32_t TCOLS = 256u * NBLK;     // 2 accumulator sets
   if (tid == 0) {
     mbar_init(BAR(PB_WFULL), 1); mbar_init(BAR(PB_WFULL + 1), 1);
     for (int s = 0; s < 2; s++) {
       mbar_init(BAR(PB_AFULL + s), 128); mbar_init(BAR(PB_AEMPTY + s), 1);
       mbar_init(BAR(PB_OUTDONE + s), 1); mbar_init(BAR(PB_ACCFREE + s), 128);
+      mbar_init(BAR(PB_ASEEN + s), 1);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -103,11 +119,13 @@ __global__ void __launch_bounds__(PJ_THREADS, NBLK == 1 ? 2 : 1) k_tc_proj(const
   } else if (warp == 8) {
     uint32_t tl = 0;
     for (int b = 0; b < NBLK; b++) mbar_wait(BAR(PB_WFULL + b), 0);
-    for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, tl++) {
+    for (int tile = blockIdx.x; tile < a.num_tiles && !wd.dead; tile += gridDim.x, tl++) {
       const uint32_t st = tl & 1, ph = (tl >> 1) & 1;
       mbar_wait(BAR(PB_AFULL + st), ph);
       mbar_wait(BAR(PB_ACCFREE + st), ph ^ 1);
       tc_fence_after();
+      if (lane == 0) mbar_arrive(BAR(PB_ASEEN + st));      // release: forwards the producers' sum2 rows to the drain warps
+      __syncwarp();
       if (elect_one()) {
         const uint64_t adesc = umma_desc(base + st * BLK_BYTES);
         for (int b = 0; b < NBLK; b++) {
@@ -123,7 +141,7 @@ __global__ void __launch_bounds__(PJ_THREADS, NBLK == 1 ? 2 : 1) k_tc_proj(const
     // ===================================================== A-operand producers, one tile ahead
     const int q = warp - 4;
     uint32_t tl = 0;
-    for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, tl++) {
+    for (int tile = blockIdx.x; tile < a.num_tiles && !wd.dead; tile += gridDim.x, tl++) {
       const uint32_t st = tl & 1, ph = (tl >> 1) & 1;
       const int64_t row0 = (int64_t)tile * TM + 32 * q;
       const int64_t left = a.R - row0;
@@ -268,12 +286,17 @@ __global__ void __launch_bounds__(PJ_THREADS, NBLK == 1 ? 2 : 1) k_tc_proj(const
     const int ld = NBLK * H;
     const int q = lane >> 2, cq = 2 * (lane & 3);
     uint32_t tl = 0;
-    for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, tl++) {
+    for (int tile = blockIdx.x; tile < a.num_tiles && !wd.dead; tile += gridDim.x, tl++) {
       const uint32_t st = tl & 1, ph = (tl >> 1) & 1;
       const int64_t row0 = (int64_t)tile * TM;
       const int rows = (int)((a.R - row0) < TM ? (a.R - row0) : TM);
+      if (a.dbg_drain_delay_ns) __nanosleep(a.dbg_drain_delay_ns);      // test hook
       // addends may be produced by this tile's A-operand warps (sum2): they are complete once the A tile is
-      mbar_wait(BAR(PB_AFULL + st), ph);
+#ifdef GNB_OLD_PROJ_PROTOCOL
+      mbar_wait(BAR(PB_AFULL + st), ph);      // round-1 protocol, kept only to reproduce its dead-lock
+#else
+      mbar_wait(BAR(PB_ASEEN + st), ph);
+#endif
       int64_t ar[4];
 #pragma unroll
       for (int k = 0; k < 4; k++) {
@@ -323,6 +346,7 @@ __global__ void __launch_bounds__(PJ_THREADS, NBLK == 1 ? 2 : 1) k_tc_proj(const
   tc_fence_before();
   __syncthreads();
   if (warp == 8) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TCOLS) : "memory");
+#undef mbar_wait
 }
 
 // ------------------------------------------------------------------ weight packing
@@ -448,7 +472,10 @@ static int launch_proj(gnb_ctx* ctx, const ProjArgs& a, const char* name, double
   const int per_sm = NBLK == 1 ? 2 : 1;
   const int grid = a.num_tiles < per_sm * ctx->sm_count ? a.num_tiles : per_sm * ctx->sm_count;
   Launch L(ctx, name, bytes, flops);
-  k_tc_proj<SRC, NBLK><<<grid, PJ_THREADS, pj_smem(NBLK), ctx->stream>>>(a);
+  ProjArgs aw = a;
+  aw.wd = ctx_watch(ctx);
+  aw.dbg_drain_delay_ns = ctx->dbg_proj_drain_delay_ns;
+  k_tc_proj<SRC, NBLK><<<grid, PJ_THREADS, pj_smem(NBLK), ctx->stream>>>(aw);
   GNB_CUDA(cudaGetLastError());
   return GNB_OK;
 }
@@ -494,7 +521,7 @@ int tc_core_forward(gnb_ctx* ctx, const gnb_graph* g, const TcCorePack* pk, cons
     a.x = xe; a.y = ye; a.R = E; a.num_tiles = ceil_div(E, TM); a.wpack = pk->w_edge;
     a.b1f = pk->b1f_e; a.b2 = ffn[0].b2; a.eps = ln1[0].eps; a.eps_mode = ln1[0].eps_mode;
     a.add1 = Psr; a.idx1 = g->edge_src; a.ld1 = 2 * H; a.add2 = Psr + H; a.idx2 = g->edge_dst; a.ld2 = 2 * H;
-    a.part = g->edge_part; a.Epart = Epart; a.Gpart = Gpart; a.dbg = g_tc_dbg;
+    a.part = g->edge_part; a.Epart = Epart; a.Gpart = Gpart; a.dbg = g_tc_dbg; a.wd = ctx_watch(ctx);
     // canonical work of the reference's edge update + edge FFN: 24 H^2 flops and
     // 8H bytes of features + 12 B of index per edge
     GNB_TRY(launch_edge5(ctx, a, "tc_edge_core", 24.0 * HH * E, (8.0 * H + 12.0) * E));
@@ -518,7 +545,7 @@ int tc_core_forward(gnb_ctx* ctx, const gnb_graph* g, const TcCorePack* pk, cons
     a.x = xn; a.y = yn; a.R = N; a.num_tiles = ceil_div(N, TM); a.wpack = pk->w_node;
     a.b1f = pk->b1f_n; a.b2 = ffn[1].b2; a.eps = ln1[1].eps; a.eps_mode = ln1[1].eps_mode;
     a.add1 = Pagg; a.idx1 = nullptr; a.ld1 = H; a.add2 = Pun; a.idx2 = g->node_graph; a.ld2 = H;
-    a.part = g->node_gpart; a.Epart = Vpart; a.Gpart = Npart; a.dbg = nullptr;
+    a.part = g->node_gpart; a.Epart = Vpart; a.Gpart = Npart; a.dbg = nullptr; a.wd = ctx_watch(ctx);
     GNB_TRY(launch_edge5(ctx, a, "tc_node_core", 20.0 * HH * N, (8.0 * H + 8.0) * N));
   }
   // graphs (B rows, fp32 CUDA cores): sums over the graph's nodes, graph update, graph FFN + residual

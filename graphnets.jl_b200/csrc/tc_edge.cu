@@ -187,7 +187,10 @@ __global__ void __launch_bounds__(E_THREADS, 1) k_edge5(const EdgeArgs a) {
     __syncwarp();
     if (lane == 0) mbar_arrive(BAR(i));
   };
-#define TILE_OK(t) ((t) - (int)rank < a.num_tiles)   /* both CTAs of a pair run the same number of passes */
+  Watch wd{a.wd.flag, a.wd.limit_ns, false};
+#define mbar_wait(b, p) mbar_wait_w((b), (p), wd)
+#define mbar_wait_cluster(b, p) mbar_wait_w((b), (p), wd)      /* barriers that receive arrivals from the peer CTA */
+#define TILE_OK(t) ((t) - (int)rank < a.num_tiles && !wd.dead)   /* both CTAs of a pair run the same number of passes */
   const uint32_t tmem = *tmem_slot;
   const uint32_t HdA = tmem + 256, HdB = tmem + 384;
   const int grid = gridDim.x;
@@ -582,16 +585,17 @@ __global__ void __launch_bounds__(E_THREADS, 1) k_edge5(const EdgeArgs a) {
     else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
   }
 #undef TILE_OK
+#undef mbar_wait
+#undef mbar_wait_cluster
 }
 
 }  // namespace
 
 int launch_edge5(gnb_ctx* ctx, const EdgeArgs& a, const char* name, double flops, double bytes) {
   if (a.num_tiles <= 0) return GNB_OK;
-  static const int use_cl2 = [] {      // GNB_EDGE_CTA_PAIR=0: one CTA per tile stream (cta_group::1)
-    const char* e = getenv("GNB_EDGE_CTA_PAIR");
-    return e ? atoi(e) : 1;
-  }();
+  // GNB_EDGE_CTA_PAIR=0: one CTA per tile stream (cta_group::1).  Read per launch so that a test can run both instantiations.
+  const char* pair_env = getenv("GNB_EDGE_CTA_PAIR");
+  const int use_cl2 = pair_env ? atoi(pair_env) : 1;
   if (ctx_first(ctx, ONCE_EDGE5)) {
     GNB_CUDA(cudaFuncSetAttribute(k_edge5<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, E_SMEM));
     GNB_CUDA(cudaFuncSetAttribute(k_edge5<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, E_SMEM));

@@ -20,6 +20,7 @@ struct EdgeArgs {
   float* Epart;          // out [n_parts][128] partial sums of the normalised edge rows
   float* Gpart;          // out [n_parts][128] partial sums of the gathered addends
   unsigned long long* dbg;
+  WatchArgs wd;          // kernel watchdog (tc_ptx.cuh)
 };
 
 int launch_edge5(gnb_ctx* ctx, const EdgeArgs& a, const char* name, double flops, double bytes);

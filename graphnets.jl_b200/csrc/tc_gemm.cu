@@ -27,6 +27,8 @@ using namespace tcx;
 
 namespace {
 
+#define mbar_wait(b, p) mbar_wait_w((b), (p), wd)      /* `wd`: the kernel's Watch (tc_ptx.cuh) */
+
 constexpr int SLAB = KB_BYTES;            // 128 rows x 64 k bf16
 constexpr int NA = 6, NW = 3;             // ring depths (A: 6 x 16 KB, W: 3 x 32 KB)
 constexpr int G_OFF_A = 0;
@@ -53,6 +55,7 @@ struct GemmArgs {
   float* out;
   int num_tiles, ngroups, NG;     // NG output blocks per group (1 or 2)
   int resident;                   // the A slabs of a row tile are produced once and reused by every column group (KS <= NA - 2)
+  WatchArgs wd;                   // kernel watchdog (tc_ptx.cuh)
 };
 
 __global__ void __launch_bounds__(G_THREADS, 1) k_tc_lin(const GemmArgs a) {
@@ -66,6 +69,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) k_tc_lin(const GemmArgs a) {
   const uint32_t bar0 = smem_u32(bars);
   auto BAR = [&](int i) { return bar0 + 8u * (uint32_t)i; };
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  Watch wd{a.wd.flag, a.wd.limit_ns, false};
   if (tid == 0) {
     for (int i = 0; i < NW; i++) { mbar_init(BAR(GB_WFULL + i), 1); mbar_init(BAR(GB_WEMPTY + i), 1); }
     for (int i = 0; i < NA; i++) { mbar_init(BAR(GB_AFULL + i), 8); mbar_init(BAR(GB_AEMPTY + i), 1); }
@@ -88,7 +92,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) k_tc_lin(const GemmArgs a) {
   if (warp == W_LOAD) {
     // ===================================================== weight loader
     uint32_t it = 0;
-    for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
+    for (int tile = blockIdx.x; tile < a.num_tiles && !wd.dead; tile += gridDim.x) {
       for (int ng = 0; ng < a.ngroups; ng++) {
         const uint8_t* src = reinterpret_cast<const uint8_t*>(a.wpack) + (size_t)ng * KS * NG * SLAB;
 #pragma unroll 1
@@ -108,7 +112,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) k_tc_lin(const GemmArgs a) {
   } else if (warp == W_MMA) {
     // ===================================================== MMA issuer
     uint32_t ita = 0, itw = 0, item = 0, tl = 0;
-    for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, tl++) {
+    for (int tile = blockIdx.x; tile < a.num_tiles && !wd.dead; tile += gridDim.x, tl++) {
       for (int ng = 0; ng < a.ngroups; ng++, item++) {
         const uint32_t buf = item & 1, aph = (item >> 1) & 1;
         mbar_wait(BAR(GB_ACCFREE + buf), aph ^ 1);
@@ -142,7 +146,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) k_tc_lin(const GemmArgs a) {
     const int pw = warp - 4;
     const int hr = lane >> 4, c16 = lane & 15;      // two rows per load instruction, 16 lanes x 16 B per row slab
     uint32_t it = 0;
-    for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
+    for (int tile = blockIdx.x; tile < a.num_tiles && !wd.dead; tile += gridDim.x) {
       const int64_t row0 = (int64_t)tile * TM + 16 * pw;
       // ---- LayerNorm statistics of this warp's rows, two-pass in fp32 (src/gngraphnorm.jl:19-26), kept for all column groups
       // (16 lanes per row, the row stays in registers for both passes; 2 row pairs = 4 rows of loads in flight)
@@ -291,7 +295,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) k_tc_lin(const GemmArgs a) {
     const uint32_t lane_base = ((uint32_t)(dq * 32)) << 16;
     const int qr = lane >> 2, cq = 2 * (lane & 3);
     uint32_t item = 0;
-    for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
+    for (int tile = blockIdx.x; tile < a.num_tiles && !wd.dead; tile += gridDim.x) {
       const int64_t row0 = (int64_t)tile * TM + 32 * dq;
       // the 4 rows of this lane: 16 hh + 8 h2 + qr
       int32_t arow[4][4];      // gathered addend rows (row counts fit 31 bits: checked by the lowering)
@@ -439,6 +443,7 @@ struct FfnArgs {
   const __nv_bfloat16* w1;      // [8 chunks][4 K slabs][8192]
   const __nv_bfloat16* w2;      // [2 output blocks][16 K slabs][8192]
   const float *b1, *b2;
+  WatchArgs wd;                 // kernel watchdog (tc_ptx.cuh)
 };
 
 template <int FH>
@@ -457,6 +462,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) k_tc_ffn(const FfnArgs a) {
   const uint32_t bar0 = smem_u32(bars);
   auto BAR = [&](int i) { return bar0 + 8u * (uint32_t)i; };
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  Watch wd{a.wd.flag, a.wd.limit_ns, false};
   if (tid == 0) {
     for (int i = 0; i < F_NW; i++) { mbar_init(BAR(FB_WFULL + i), 1); mbar_init(BAR(FB_WEMPTY + i), 1); }
     for (int i = 0; i < 2; i++) {
@@ -494,7 +500,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) k_tc_ffn(const FfnArgs a) {
       }
       __syncwarp();
     };
-    for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
+    for (int tile = blockIdx.x; tile < a.num_tiles && !wd.dead; tile += gridDim.x) {
 #pragma unroll 1
       for (int c = 0; c < F_CH + NHD - 1; c++) {
         if (c < F_CH)
@@ -520,7 +526,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) k_tc_ffn(const FfnArgs a) {
       wd0 = umma_desc(base + F_OFF_W + ws0 * SLAB);
       wd1 = umma_desc(base + F_OFF_W + ws1 * SLAB);
     };
-    for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, tl++) {
+    for (int tile = blockIdx.x; tile < a.num_tiles && !wd.dead; tile += gridDim.x, tl++) {
       const uint32_t st = tl % NAS;
       mbar_wait(BAR(FB_AFULL + st), (tl / NAS) & 1);
 #pragma unroll 1
@@ -586,7 +592,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) k_tc_ffn(const FfnArgs a) {
       TC_ST16(dst, p);
     };
     uint32_t nh[2] = {0, 0};
-    for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
+    for (int tile = blockIdx.x; tile < a.num_tiles && !wd.dead; tile += gridDim.x) {
 #pragma unroll 1
       for (int c = 0; c < F_CH; c++) {
         const int hb = c % NHD;
@@ -617,7 +623,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) k_tc_ffn(const FfnArgs a) {
     const int q = warp - 4;
     const int hr = lane >> 4, c16 = lane & 15;
     uint32_t tl = 0;
-    for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, tl++) {
+    for (int tile = blockIdx.x; tile < a.num_tiles && !wd.dead; tile += gridDim.x, tl++) {
       const int64_t row0 = (int64_t)tile * TM + 32 * q;
       // two-pass statistics, 16 lanes per row, the row in registers (4 float4 per lane), 2 row pairs in flight
       const float* xs = a.x + 4 * c16;
@@ -715,7 +721,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) k_tc_ffn(const FfnArgs a) {
 #pragma unroll
     for (int s2 = 0; s2 < F_NB; s2++) b2v[s2] = __ldg(reinterpret_cast<const float4*>(a.b2) + 32 * s2 + lane);
     uint32_t tl = 0;
-    for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, tl++) {
+    for (int tile = blockIdx.x; tile < a.num_tiles && !wd.dead; tile += gridDim.x, tl++) {
       const int64_t row0 = (int64_t)tile * TM + 32 * dq;
       mbar_wait(BAR(FB_ACCFULL), tl & 1);
       tc_fence_after();
@@ -859,6 +865,7 @@ int launch_linear_tc(gnb_ctx* ctx, const LinArgs& a) {
   if (nit == names.end()) nit = names.emplace(std::make_pair(K, a.Nout), "tc_linear_k" + std::to_string(K) + "_n" + std::to_string(a.Nout)).first;
   Launch L(ctx, ctx->profiling && getenv("GNB_PROFILE_SHAPES") ? nit->second.c_str() : "tc_linear", bytes, 2.0 * a.R * K * a.Nout);
   const int grid = g.num_tiles < ctx->sm_count ? g.num_tiles : ctx->sm_count;
+  g.wd = ctx_watch(ctx);
   k_tc_lin<<<grid, G_THREADS, G_SMEM, ctx->stream>>>(g);
   GNB_CUDA(cudaGetLastError());
   return GNB_OK;
@@ -873,6 +880,7 @@ static int launch_ffn_t(gnb_ctx* ctx, int once_key, int64_t R, const gnb_ffn_par
   a.x = x; a.h = h; a.y = y; a.R = R; a.num_tiles = (int)ceil_div(R, TM);
   a.gamma = ln2.gamma; a.beta = ln2.beta; a.eps = ln2.eps; a.eps_mode = ln2.eps_mode;
   a.b1 = f.b1; a.b2 = f.b2;
+  a.wd = ctx_watch(ctx);
   PackKey k1{}, k2{};
   PackSrc p1{}, p2{};
   for (int s = 0; s < 3; s++) { p1.d[s] = p2.d[s] = 1 << 30; }

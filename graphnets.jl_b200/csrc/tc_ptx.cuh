@@ -25,19 +25,56 @@ static __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 static __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
-// Bounded spin: a protocol bug traps (launch error) instead of hanging the GPU.
-static __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  uint32_t ok = 0;
-  for (uint32_t spin = 0; !ok; spin++) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok)
-        : "r"(bar), "r"(parity)
-        : "memory");
-    if (spin > (1u << 24)) __trap();
+// Kernel watchdog.  Every mbarrier wait is a bounded wait: if a wait does not complete within `limit_ns` (a protocol
+// dead-lock), the waiting warp raises the device-global flag, marks itself dead and stops waiting; every other warp of
+// every CTA sees the flag at its next slow-path check and does the same, so the kernel drains and EXITS instead of
+// hanging or trapping (a trap leaves a sticky error that kills the CUDA context).  The host reads the flag at its
+// next synchronisation point and returns GNB_ERR_TIMEOUT; the results of that forward are invalid.
+// All waits are executed by whole, converged warps; the votes keep the outcome warp-uniform.
+// (WatchArgs, the kernel-argument half, lives in common.cuh)
+struct Watch {
+  int* flag;
+  unsigned long long limit_ns;
+  bool dead;
+};
+static __device__ __forceinline__ uint32_t mbar_test(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok;
+}
+static __device__ __forceinline__ unsigned long long gtimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+// slow path (out of line: keeps the fast path at one try_wait + one vote); returns true when the watchdog fired
+static __device__ __noinline__ bool mbar_wait_slow(uint32_t bar, uint32_t parity, int* flag, unsigned long long limit_ns) {
+  const unsigned long long t0 = gtimer_ns();
+  for (uint32_t spin = 1;; spin++) {
+    if (__all_sync(0xffffffffu, mbar_test(bar, parity))) return false;
+    if ((spin & 63u) == 0u) {
+      int dead = 0;
+      if ((threadIdx.x & 31) == 0) {
+        dead = *reinterpret_cast<volatile int*>(flag);
+        if (!dead && gtimer_ns() - t0 > limit_ns) {
+          atomicExch(flag, 1);
+          dead = 1;
+        }
+      }
+      if (__shfl_sync(0xffffffffu, dead, 0)) return true;
+    }
   }
+}
+static __device__ __forceinline__ void mbar_wait_w(uint32_t bar, uint32_t parity, Watch& w) {
+  if (w.dead) return;
+  if (__all_sync(0xffffffffu, mbar_test(bar, parity))) return;
+  w.dead = mbar_wait_slow(bar, parity, w.flag, w.limit_ns);
 }
 static __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
@@ -188,20 +225,6 @@ static __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr
   // tcgen05.fence) and shared memory consumed through the async proxy (ordered by fence.proxy.async); a cluster-scope release
   // would add a full memory barrier (~1.2k cycles per arrive, measured)
   asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
-}
-// wait on a barrier that receives arrivals from the peer CTA (cluster-scope acquire)
-static __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
-  uint32_t ok = 0;
-  for (uint32_t spin = 0; !ok; spin++) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok)
-        : "r"(bar), "r"(parity)
-        : "memory");
-    if (spin > (1u << 24)) __trap();
-  }
 }
 // arrive::one on the barrier at this offset in both CTAs of the pair once all prior tcgen05 ops of this thread completed
 static __device__ __forceinline__ void tc_commit2(uint32_t bar) {

@@ -29,6 +29,8 @@ extern "C" {
 #define GNB_ERR_CUDA        -2
 #define GNB_ERR_OOM         -3
 #define GNB_ERR_UNSUPPORTED -4
+#define GNB_ERR_TIMEOUT     -5   /* a kernel's watchdog fired (barrier wait > GNB_WATCHDOG_MS, default 10 s): the kernel
+                                    drained and exited, the CUDA context stays usable, the results of that forward are invalid */
 
 #define GNB_PREC_FP32 0   /* CUDA-core fp32 path, parity 1e-5 relative                       */
 #define GNB_PREC_BF16 2   /* tcgen05 bf16 tensor-core path (fp32 accumulate), parity 1e-2   */

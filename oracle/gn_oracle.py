@@ -433,3 +433,23 @@ def rel_err(y, ref):
     if ref.size == 0:
         return 0.0
     return float(np.max(np.abs(y - ref)) / max(np.max(np.abs(ref)), 1e-30))
+
+
+def elementwise_err(y, ref):
+    """SURVEY 8c second metric: worst element-wise |y - ref| / (|ref| + 1e-3 max|ref|) - relative error per element with
+    a floor that keeps near-zero reference entries from dividing by nothing."""
+    ref = np.asarray(ref, np.float64)
+    y = np.asarray(y, np.float64)
+    if ref.size == 0:
+        return 0.0
+    floor = 1e-3 * max(np.max(np.abs(ref)), 1e-30)
+    return float(np.max(np.abs(y - ref) / (np.abs(ref) + floor)))
+
+
+def rms_err(y, ref):
+    """||y - ref||_2 / ||ref||_2: the average relative error (insensitive to a single unlucky element)."""
+    ref = np.asarray(ref, np.float64)
+    y = np.asarray(y, np.float64)
+    if ref.size == 0:
+        return 0.0
+    return float(np.sqrt(np.sum((y - ref) ** 2)) / max(np.sqrt(np.sum(ref ** 2)), 1e-30))

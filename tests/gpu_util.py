@@ -5,8 +5,20 @@ import numpy as np
 from oracle import gn_oracle as O
 import workloads as W
 
+import json
+import os
+
 FP32_TOL = 1e-5     # north_star: fp32 path features within 1e-5 relative (SURVEY 8c definition)
 BF16_TOL = 1e-2     # tensor-core path
+# Second metric of SURVEY 8c, asserted beside the max-norm one: worst element-wise |y - ref| / (|ref| + 1e-3 max|ref|).
+# A max-norm error eps allows at most eps / 1e-3 here (all of it landing on a zero of the reference); the bounds below are
+# far tighter than that implication - an element-wise blow-up on small outputs hidden by the max norm would trip them.
+FP32_EW_TOL = 1e-3
+BF16_EW_TOL = 5.0
+# ... and the RMS relative error ||y - ref|| / ||ref||, which no single element can hide in
+FP32_RMS_TOL = 5e-6
+BF16_RMS_TOL = 5e-3
+_LOG = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out", "parity_errors.jsonl")
 
 
 def run_product(gn, layers, w, precision="fp32", eps_mode=0):
@@ -30,5 +42,11 @@ def assert_parity(got, ref, tol, what=""):
             continue
         assert a.shape == b.shape, "%s %s: shape %s vs %s" % (what, name, a.shape, b.shape)
         assert np.isfinite(a).all(), "%s %s: non-finite output" % (what, name)
-        err = O.rel_err(a, b)
+        err, ew, rms = O.rel_err(a, b), O.elementwise_err(a, b), O.rms_err(a, b)
+        if os.path.isdir(os.path.dirname(_LOG)):
+            with open(_LOG, "a") as f:
+                f.write(json.dumps(dict(case=what, tensor=name, shape=list(a.shape), tol=tol, max_norm=err, elementwise=ew, rms=rms)) + "\n")
         assert err <= tol, "%s %s: rel err %.3e > %.1e" % (what, name, err, tol)
+        ew_tol, rms_tol = (FP32_EW_TOL, FP32_RMS_TOL) if tol <= FP32_TOL else (BF16_EW_TOL, BF16_RMS_TOL)
+        assert ew <= ew_tol, "%s %s: element-wise err %.3e > %.1e (max-norm %.3e)" % (what, name, ew, ew_tol, err)
+        assert rms <= rms_tol, "%s %s: rms err %.3e > %.1e" % (what, name, rms, rms_tol)

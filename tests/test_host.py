@@ -99,3 +99,13 @@ def test_shard_ranges(gn):
         assert max(tot) - min(tot) <= 2 * m.max()
     assert gn.shard_ranges([], 2) == [(0, 0), (0, 0)]
     assert gn.shard_ranges([0, 0, 0, 0], 2) == [(0, 2), (2, 4)]
+
+
+def test_default_precision_is_fp32(gn):
+    """The reference computes in Float32: the drop-in answers at fp32 parity unless the caller opts in to the tensor path."""
+    assert gn.get_precision() == "fp32"
+    gn.set_precision("auto")
+    assert gn.get_precision() == "auto"
+    gn.set_precision("fp32")
+    with pytest.raises(AssertionError):
+        gn.set_precision("fp16")
