@@ -87,8 +87,8 @@ __global__ void __launch_bounds__(PJ_THREADS, NBLK == 1 ? 2 : 1) k_tc_proj(const
   const uint32_t bar0 = smem_u32(bars);
   auto BAR = [&](int i) { return bar0 + 8u * (uint32_t)i; };
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  Watch wd{a.wd.flag, a.wd.limit_ns, false};
-#define mbar_wait(b, p) mbar_wait_w((b), (p), wd)
+  bool wd_dead = false;      // kernel watchdog (tc_ptx.cuh)
+#define mbar_wait(b, p) mbar_wait_w((b), (p), wd_dead, a.wd)
   constexpr uint32_t TCOLS = 256u * NBLK;     // 2 accumulator sets
   if (tid == 0) {
     mbar_init(BAR(PB_WFULL), 1); mbar_init(BAR(PB_WFULL + 1), 1);
@@ -119,7 +119,7 @@ __global__ void __launch_bounds__(PJ_THREADS, NBLK == 1 ? 2 : 1) k_tc_proj(const
   } else if (warp == 8) {
     uint32_t tl = 0;
     for (int b = 0; b < NBLK; b++) mbar_wait(BAR(PB_WFULL + b), 0);
-    for (int tile = blockIdx.x; tile < a.num_tiles && !wd.dead; tile += gridDim.x, tl++) {
+    for (int tile = blockIdx.x; tile < a.num_tiles && !wd_dead; tile += gridDim.x, tl++) {
       const uint32_t st = tl & 1, ph = (tl >> 1) & 1;
       mbar_wait(BAR(PB_AFULL + st), ph);
       mbar_wait(BAR(PB_ACCFREE + st), ph ^ 1);
@@ -141,7 +141,7 @@ __global__ void __launch_bounds__(PJ_THREADS, NBLK == 1 ? 2 : 1) k_tc_proj(const
     // ===================================================== A-operand producers, one tile ahead
     const int q = warp - 4;
     uint32_t tl = 0;
-    for (int tile = blockIdx.x; tile < a.num_tiles && !wd.dead; tile += gridDim.x, tl++) {
+    for (int tile = blockIdx.x; tile < a.num_tiles && !wd_dead; tile += gridDim.x, tl++) {
       const uint32_t st = tl & 1, ph = (tl >> 1) & 1;
       const int64_t row0 = (int64_t)tile * TM + 32 * q;
       const int64_t left = a.R - row0;
@@ -286,7 +286,7 @@ __global__ void __launch_bounds__(PJ_THREADS, NBLK == 1 ? 2 : 1) k_tc_proj(const
     const int ld = NBLK * H;
     const int q = lane >> 2, cq = 2 * (lane & 3);
     uint32_t tl = 0;
-    for (int tile = blockIdx.x; tile < a.num_tiles && !wd.dead; tile += gridDim.x, tl++) {
+    for (int tile = blockIdx.x; tile < a.num_tiles && !wd_dead; tile += gridDim.x, tl++) {
       const uint32_t st = tl & 1, ph = (tl >> 1) & 1;
       const int64_t row0 = (int64_t)tile * TM;
       const int rows = (int)((a.R - row0) < TM ? (a.R - row0) : TM);

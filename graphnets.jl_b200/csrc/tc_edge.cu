@@ -187,10 +187,10 @@ __global__ void __launch_bounds__(E_THREADS, 1) k_edge5(const EdgeArgs a) {
     __syncwarp();
     if (lane == 0) mbar_arrive(BAR(i));
   };
-  Watch wd{a.wd.flag, a.wd.limit_ns, false};
-#define mbar_wait(b, p) mbar_wait_w((b), (p), wd)
-#define mbar_wait_cluster(b, p) mbar_wait_w((b), (p), wd)      /* barriers that receive arrivals from the peer CTA */
-#define TILE_OK(t) ((t) - (int)rank < a.num_tiles && !wd.dead)   /* both CTAs of a pair run the same number of passes */
+  bool wd_dead = false;      // kernel watchdog (tc_ptx.cuh)
+#define mbar_wait(b, p) mbar_wait_w((b), (p), wd_dead, a.wd)
+#define mbar_wait_cluster(b, p) mbar_wait_w((b), (p), wd_dead, a.wd)      /* barriers that receive arrivals from the peer CTA */
+#define TILE_OK(t) ((t) - (int)rank < a.num_tiles && !wd_dead)   /* both CTAs of a pair run the same number of passes */
   const uint32_t tmem = *tmem_slot;
   const uint32_t HdA = tmem + 256, HdB = tmem + 384;
   const int grid = gridDim.x;

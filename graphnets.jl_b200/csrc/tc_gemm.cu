@@ -27,7 +27,7 @@ using namespace tcx;
 
 namespace {
 
-#define mbar_wait(b, p) mbar_wait_w((b), (p), wd)      /* `wd`: the kernel's Watch (tc_ptx.cuh) */
+#define mbar_wait(b, p) mbar_wait_w((b), (p), wd_dead, a.wd)      /* `wd`: the kernel's Watch (tc_ptx.cuh) */
 
 constexpr int SLAB = KB_BYTES;            // 128 rows x 64 k bf16
 constexpr int NA = 6, NW = 3;             // ring depths (A: 6 x 16 KB, W: 3 x 32 KB)
@@ -69,7 +69,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) k_tc_lin(const GemmArgs a) {
   const uint32_t bar0 = smem_u32(bars);
   auto BAR = [&](int i) { return bar0 + 8u * (uint32_t)i; };
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  Watch wd{a.wd.flag, a.wd.limit_ns, false};
+  bool wd_dead = false;      // kernel watchdog (tc_ptx.cuh)
   if (tid == 0) {
     for (int i = 0; i < NW; i++) { mbar_init(BAR(GB_WFULL + i), 1); mbar_init(BAR(GB_WEMPTY + i), 1); }
     for (int i = 0; i < NA; i++) { mbar_init(BAR(GB_AFULL + i), 8); mbar_init(BAR(GB_AEMPTY + i), 1); }
@@ -92,7 +92,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) k_tc_lin(const GemmArgs a) {
   if (warp == W_LOAD) {
     // ===================================================== weight loader
     uint32_t it = 0;
-    for (int tile = blockIdx.x; tile < a.num_tiles && !wd.dead; tile += gridDim.x) {
+    for (int tile = blockIdx.x; tile < a.num_tiles && !wd_dead; tile += gridDim.x) {
       for (int ng = 0; ng < a.ngroups; ng++) {
         const uint8_t* src = reinterpret_cast<const uint8_t*>(a.wpack) + (size_t)ng * KS * NG * SLAB;
 #pragma unroll 1
@@ -112,7 +112,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) k_tc_lin(const GemmArgs a) {
   } else if (warp == W_MMA) {
     // ===================================================== MMA issuer
     uint32_t ita = 0, itw = 0, item = 0, tl = 0;
-    for (int tile = blockIdx.x; tile < a.num_tiles && !wd.dead; tile += gridDim.x, tl++) {
+    for (int tile = blockIdx.x; tile < a.num_tiles && !wd_dead; tile += gridDim.x, tl++) {
       for (int ng = 0; ng < a.ngroups; ng++, item++) {
         const uint32_t buf = item & 1, aph = (item >> 1) & 1;
         mbar_wait(BAR(GB_ACCFREE + buf), aph ^ 1);
@@ -146,7 +146,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) k_tc_lin(const GemmArgs a) {
     const int pw = warp - 4;
     const int hr = lane >> 4, c16 = lane & 15;      // two rows per load instruction, 16 lanes x 16 B per row slab
     uint32_t it = 0;
-    for (int tile = blockIdx.x; tile < a.num_tiles && !wd.dead; tile += gridDim.x) {
+    for (int tile = blockIdx.x; tile < a.num_tiles && !wd_dead; tile += gridDim.x) {
       const int64_t row0 = (int64_t)tile * TM + 16 * pw;
       // ---- LayerNorm statistics of this warp's rows, two-pass in fp32 (src/gngraphnorm.jl:19-26), kept for all column groups
       // (16 lanes per row, the row stays in registers for both passes; 2 row pairs = 4 rows of loads in flight)
@@ -295,7 +295,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) k_tc_lin(const GemmArgs a) {
     const uint32_t lane_base = ((uint32_t)(dq * 32)) << 16;
     const int qr = lane >> 2, cq = 2 * (lane & 3);
     uint32_t item = 0;
-    for (int tile = blockIdx.x; tile < a.num_tiles && !wd.dead; tile += gridDim.x) {
+    for (int tile = blockIdx.x; tile < a.num_tiles && !wd_dead; tile += gridDim.x) {
       const int64_t row0 = (int64_t)tile * TM + 32 * dq;
       // the 4 rows of this lane: 16 hh + 8 h2 + qr
       int32_t arow[4][4];      // gathered addend rows (row counts fit 31 bits: checked by the lowering)
@@ -462,7 +462,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) k_tc_ffn(const FfnArgs a) {
   const uint32_t bar0 = smem_u32(bars);
   auto BAR = [&](int i) { return bar0 + 8u * (uint32_t)i; };
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  Watch wd{a.wd.flag, a.wd.limit_ns, false};
+  bool wd_dead = false;      // kernel watchdog (tc_ptx.cuh)
   if (tid == 0) {
     for (int i = 0; i < F_NW; i++) { mbar_init(BAR(FB_WFULL + i), 1); mbar_init(BAR(FB_WEMPTY + i), 1); }
     for (int i = 0; i < 2; i++) {
@@ -500,7 +500,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) k_tc_ffn(const FfnArgs a) {
       }
       __syncwarp();
     };
-    for (int tile = blockIdx.x; tile < a.num_tiles && !wd.dead; tile += gridDim.x) {
+    for (int tile = blockIdx.x; tile < a.num_tiles && !wd_dead; tile += gridDim.x) {
 #pragma unroll 1
       for (int c = 0; c < F_CH + NHD - 1; c++) {
         if (c < F_CH)
@@ -526,7 +526,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) k_tc_ffn(const FfnArgs a) {
       wd0 = umma_desc(base + F_OFF_W + ws0 * SLAB);
       wd1 = umma_desc(base + F_OFF_W + ws1 * SLAB);
     };
-    for (int tile = blockIdx.x; tile < a.num_tiles && !wd.dead; tile += gridDim.x, tl++) {
+    for (int tile = blockIdx.x; tile < a.num_tiles && !wd_dead; tile += gridDim.x, tl++) {
       const uint32_t st = tl % NAS;
       mbar_wait(BAR(FB_AFULL + st), (tl / NAS) & 1);
 #pragma unroll 1
@@ -592,7 +592,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) k_tc_ffn(const FfnArgs a) {
       TC_ST16(dst, p);
     };
     uint32_t nh[2] = {0, 0};
-    for (int tile = blockIdx.x; tile < a.num_tiles && !wd.dead; tile += gridDim.x) {
+    for (int tile = blockIdx.x; tile < a.num_tiles && !wd_dead; tile += gridDim.x) {
 #pragma unroll 1
       for (int c = 0; c < F_CH; c++) {
         const int hb = c % NHD;
@@ -623,7 +623,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) k_tc_ffn(const FfnArgs a) {
     const int q = warp - 4;
     const int hr = lane >> 4, c16 = lane & 15;
     uint32_t tl = 0;
-    for (int tile = blockIdx.x; tile < a.num_tiles && !wd.dead; tile += gridDim.x, tl++) {
+    for (int tile = blockIdx.x; tile < a.num_tiles && !wd_dead; tile += gridDim.x, tl++) {
       const int64_t row0 = (int64_t)tile * TM + 32 * q;
       // two-pass statistics, 16 lanes per row, the row in registers (4 float4 per lane), 2 row pairs in flight
       const float* xs = a.x + 4 * c16;
@@ -721,7 +721,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) k_tc_ffn(const FfnArgs a) {
 #pragma unroll
     for (int s2 = 0; s2 < F_NB; s2++) b2v[s2] = __ldg(reinterpret_cast<const float4*>(a.b2) + 32 * s2 + lane);
     uint32_t tl = 0;
-    for (int tile = blockIdx.x; tile < a.num_tiles && !wd.dead; tile += gridDim.x, tl++) {
+    for (int tile = blockIdx.x; tile < a.num_tiles && !wd_dead; tile += gridDim.x, tl++) {
       const int64_t row0 = (int64_t)tile * TM + 32 * dq;
       mbar_wait(BAR(FB_ACCFULL), tl & 1);
       tc_fence_after();

@@ -32,11 +32,8 @@ static __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t byt
 // next synchronisation point and returns GNB_ERR_TIMEOUT; the results of that forward are invalid.
 // All waits are executed by whole, converged warps; the votes keep the outcome warp-uniform.
 // (WatchArgs, the kernel-argument half, lives in common.cuh)
-struct Watch {
-  int* flag;
-  unsigned long long limit_ns;
-  bool dead;
-};
+// Per-thread state is one predicate (`dead`); the flag pointer and the limit stay in the kernel-parameter constant bank and
+// are only read on the slow path, so the watchdog costs the hot loops no registers.
 static __device__ __forceinline__ uint32_t mbar_test(uint32_t bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
@@ -53,8 +50,8 @@ static __device__ __forceinline__ unsigned long long gtimer_ns() {
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
   return t;
 }
-// slow path (out of line: keeps the fast path at one try_wait + one vote); returns true when the watchdog fired
-static __device__ __noinline__ bool mbar_wait_slow(uint32_t bar, uint32_t parity, int* flag, unsigned long long limit_ns) {
+// slow path; returns true when the watchdog fired
+static __device__ __forceinline__ bool mbar_wait_slow(uint32_t bar, uint32_t parity, int* flag, unsigned long long limit_ns) {
   const unsigned long long t0 = gtimer_ns();
   for (uint32_t spin = 1;; spin++) {
     if (__all_sync(0xffffffffu, mbar_test(bar, parity))) return false;
@@ -71,10 +68,10 @@ static __device__ __noinline__ bool mbar_wait_slow(uint32_t bar, uint32_t parity
     }
   }
 }
-static __device__ __forceinline__ void mbar_wait_w(uint32_t bar, uint32_t parity, Watch& w) {
-  if (w.dead) return;
+static __device__ __forceinline__ void mbar_wait_w(uint32_t bar, uint32_t parity, bool& dead, const WatchArgs& wa) {
+  if (dead) return;
   if (__all_sync(0xffffffffu, mbar_test(bar, parity))) return;
-  w.dead = mbar_wait_slow(bar, parity, w.flag, w.limit_ns);
+  dead = mbar_wait_slow(bar, parity, wa.flag, wa.limit_ns);
 }
 static __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),

@@ -252,9 +252,26 @@ def layernorm(x, gamma, beta, eps=1e-5, eps_mode=EPS_SQRT_VAR_EPS2):
     return (xc / den) * gamma.astype(dt) + beta.astype(dt)
 
 
+def round_bf16(a):
+    """Round-to-nearest-even to bfloat16 precision (8 significand bits), returned in float64."""
+    a = np.ascontiguousarray(a, np.float32)
+    u = a.view(np.uint32).astype(np.uint64)
+    r = (((u + 0x7FFF + ((u >> 16) & 1)) >> 16) << 16).astype(np.uint32)
+    return r.view(np.float32).astype(np.float64)
+
+
+# When set (only by `forward_sparse(..., bf16_operands=True)`), every Dense rounds BOTH matmul operands to bfloat16 and
+# accumulates in float64: the arithmetic model of a bf16 tensor-core GEMM with exact accumulation.  Used by the -m gpu tests
+# of the wide tensor path to tell kernel error from the error bf16 operands carry by construction.
+_BF16_OPERANDS = False
+
+
 def dense(x, W, b, relu=False):
     """Flux Dense: sigma.(W*x .+ b), applied to the trailing (feature) dim of x."""
-    y = x @ W.astype(x.dtype).T + b.astype(x.dtype)
+    if _BF16_OPERANDS:
+        y = round_bf16(x) @ round_bf16(W).T + np.asarray(b, np.float64)
+    else:
+        y = x @ W.astype(x.dtype).T + b.astype(x.dtype)
     return np.maximum(y, 0) if relu else y
 
 
@@ -339,17 +356,23 @@ def gncore(c, block_fn, ef, nf, gf, eps_mode=EPS_SQRT_VAR_EPS2):
     return tuple((xs[i] + blk[i]) + ff[i] for i in range(3))
 
 
-def forward_sparse(layers, g, ef, nf, gf, eps_mode=EPS_SQRT_VAR_EPS2, dt=np.float64):
+def forward_sparse(layers, g, ef, nf, gf, eps_mode=EPS_SQRT_VAR_EPS2, dt=np.float64, bf16_operands=False):
     """Sequential model: list of ("block", params) / ("core", params) (GNCoreList is a left
-    fold, src/gncorelist.jl:43-45)."""
+    fold, src/gncorelist.jl:43-45).  bf16_operands: the Dense layers of the GNCore layers round their matmul operands to
+    bfloat16 (see _BF16_OPERANDS) - NOT the reference semantics, only an error model for the tensor-path tests."""
+    global _BF16_OPERANDS
     cast = lambda a: None if a is None else np.asarray(a, dt)
     ef, nf, gf = cast(ef), cast(nf), cast(gf)
     for kind, p in layers:
         if kind == "block":
             ef, nf, gf = gnblock_sparse(p, g, ef, nf, gf, dt)
         else:
-            ef, nf, gf = gncore(p, lambda bp, a, b, c: gnblock_sparse(bp, g, a, b, c, dt),
-                                ef, nf, gf, eps_mode)
+            _BF16_OPERANDS = bool(bf16_operands)
+            try:
+                ef, nf, gf = gncore(p, lambda bp, a, b, c: gnblock_sparse(bp, g, a, b, c, dt),
+                                    ef, nf, gf, eps_mode)
+            finally:
+                _BF16_OPERANDS = False
     return ef, nf, gf
 
 

@@ -8,6 +8,9 @@ import torch
 import workloads as W
 from tests.gpu_util import BF16_TOL, FP32_TOL, assert_parity, run_oracle
 
+# the wide cores carry more bf16 operand error than the 128-wide ones (tests/gpu_util.py::assert_wide_parity): RMS bound = max-norm bound
+WIDE_RMS_TOL = 1.5e-2
+
 pytestmark = pytest.mark.gpu
 
 
@@ -38,7 +41,7 @@ def test_cfg5_shape_tensor_path(gn, B):
     layers = W.model_params("cfg5")
     got, prof = _run(gn, layers, w, "auto")
     _, ref = run_oracle(layers, w)
-    assert_parity(got, ref, BF16_TOL, "cfg5 auto")
+    assert_parity(got, ref, BF16_TOL, "cfg5 auto", rms_tol=WIDE_RMS_TOL)
     assert "tc_linear" in prof and prof["tc_linear"]["launches"] > 0, "the tcgen05 linear kernel did not run: %s" % list(prof)
     got32, prof32 = _run(gn, layers, w, "fp32")
     assert_parity(got32, ref, FP32_TOL, "cfg5 fp32")
@@ -51,7 +54,7 @@ def test_cfg5_many_small_graphs(gn):
     layers = W.model_params("cfg5")
     got, prof = _run(gn, layers, w, "auto")
     _, ref = run_oracle(layers, w)
-    assert_parity(got, ref, BF16_TOL, "cfg5 small graphs")
+    assert_parity(got, ref, BF16_TOL, "cfg5 small graphs", rms_tol=WIDE_RMS_TOL)
     assert prof["tc_ffn256"]["launches"] == 3 * 4, prof["tc_ffn256"]      # edge, node and graph FFN of each of the 4 cores
 
 
@@ -61,7 +64,7 @@ def test_cfg3_shape_tensor_path(gn):
     layers = W.model_params("cfg3")
     got, prof = _run(gn, layers, w, "auto")
     _, ref = run_oracle(layers, w)
-    assert_parity(got, ref, BF16_TOL, "cfg3 auto")
+    assert_parity(got, ref, BF16_TOL, "cfg3 auto", rms_tol=WIDE_RMS_TOL)
     assert "tc_linear" in prof
 
 
@@ -70,7 +73,7 @@ def test_bf16_mode_accepts_wide_cores(gn):
     layers = W.model_params("cfg5")
     got, prof = _run(gn, layers, w, "bf16")
     _, ref = run_oracle(layers, w)
-    assert_parity(got, ref, BF16_TOL, "cfg5 bf16")
+    assert_parity(got, ref, BF16_TOL, "cfg5 bf16", rms_tol=WIDE_RMS_TOL)
 
 
 def test_repeated_forward_is_deterministic(gn):
