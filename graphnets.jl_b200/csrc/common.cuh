@@ -106,6 +106,10 @@ static inline bool ctx_first(gnb_ctx* c, int key) {
   return true;
 }
 
+// Cut of the partial-row index of the tensor path (edge_part / node_gpart): a partial row never spans a 16-row boundary,
+// so that each of the eight 16-row epilogue warps of the fused kernel (tc_edge.cu) owns whole partial rows.
+constexpr int GNB_PART_ROWS = 16;
+
 struct gnb_graph {
   int device = 0;
   int32_t B = 0, PN = 0;
@@ -119,13 +123,13 @@ struct gnb_graph {
   int32_t* graph_edge_ptr = nullptr;  // [B+1]
   int32_t* graph_node_ptr = nullptr;  // [B+1]
   int32_t* node_in_ptr = nullptr;     // [N+1] CSR over receivers (edges are receiver-sorted)
-  // tensor-core path: 128-edge tiles; per tile, per distinct receiver one partial row.
+  // tensor-core path: per (GNB_PART_ROWS-edge block, receiver) run one partial row.
   // node v sums partial rows [node_part_ptr[v], node_part_ptr[v+1])  (deterministic, no atomics)
   int32_t* edge_part = nullptr;       // [E]   partial-row id of each edge
   int32_t* node_part_ptr = nullptr;   // [N+1]
   int32_t* graph_part_ptr = nullptr;  // [B+1] partial rows of graph b = [graph_part_ptr[b], graph_part_ptr[b+1])
   int64_t n_parts = 0;
-  // same for the node -> graph sums of the tensor path: partial rows per (32-node block, graph) run
+  // same for the node -> graph sums of the tensor path: partial rows per (GNB_PART_ROWS-node block, graph) run
   int32_t* node_gpart = nullptr;       // [N]   partial-row id of each node
   int32_t* graph_npart_ptr = nullptr;  // [B+1] partial rows of graph b = [graph_npart_ptr[b], graph_npart_ptr[b+1])
   int64_t n_nparts = 0;

@@ -351,7 +351,7 @@ extern "C" int gnb_graph_lower(gnb_ctx* ctx, const void* adj, int adj_dtype, int
     k_fill_const<<<1, 32, 0, ctx->stream>>>(g->graph_edge_ptr + B, 1, (int32_t)E);
     k_fill_const<<<1, 32, 0, ctx->stream>>>(g->node_in_ptr + N, 1, (int32_t)E);
     ctx->launches += 2;
-    // tensor-path partial-row index (tile = 128 edges)
+    // tensor-path partial-row index (cut every GNB_PART_ROWS edges)
     if (E > 0) {
       int rc2 = GNB_OK;
       int32_t* flag = arena_ptr<int32_t>(ctx->arena, E, &rc2);
@@ -359,7 +359,7 @@ extern "C" int gnb_graph_lower(gnb_ctx* ctx, const void* adj, int adj_dtype, int
       int32_t* sums2 = arena_ptr<int32_t>(ctx->arena, ceil_div(E, SCAN_ITEMS) + 2, &rc2);
       if (rc2 != GNB_OK) { ret = rc2; break; }
       int eb = ceil_div(E, 256);
-      k_part_flags<<<eb, 256, 0, ctx->stream>>>(g->edge_dst, E, 32, flag);
+      k_part_flags<<<eb, 256, 0, ctx->stream>>>(g->edge_dst, E, GNB_PART_ROWS, flag);
       ctx->launches++;
       if ((ret = exclusive_scan(ctx, flag, E, excl, 1, sums2)) != GNB_OK) break;
       k_part_finish<<<eb, 256, 0, ctx->stream>>>(flag, excl, E, g->edge_part);
@@ -374,14 +374,14 @@ extern "C" int gnb_graph_lower(gnb_ctx* ctx, const void* adj, int adj_dtype, int
     }
     k_graph_part_ptr<<<ceil_div(B + 1, 256), 256, 0, ctx->stream>>>(g->graph_node_ptr, g->node_part_ptr, B, g->graph_part_ptr);
     ctx->launches++;
-    // node -> graph partial-row index (32-node blocks, graph runs): same construction keyed by the node's graph
+    // node -> graph partial-row index (GNB_PART_ROWS-node blocks, graph runs): same construction keyed by the node's graph
     if (N > 0) {
       int rc2 = GNB_OK;
       int32_t* flag = arena_ptr<int32_t>(ctx->arena, N, &rc2);
       int32_t* excl = arena_ptr<int32_t>(ctx->arena, N + 1, &rc2);
       int32_t* sums2 = arena_ptr<int32_t>(ctx->arena, ceil_div(N, SCAN_ITEMS) + 2, &rc2);
       if (rc2 != GNB_OK) { ret = rc2; break; }
-      k_part_flags<<<ceil_div(N, 256), 256, 0, ctx->stream>>>(g->node_graph, N, 32, flag);
+      k_part_flags<<<ceil_div(N, 256), 256, 0, ctx->stream>>>(g->node_graph, N, GNB_PART_ROWS, flag);
       ctx->launches++;
       if ((ret = exclusive_scan(ctx, flag, N, excl, 1, sums2)) != GNB_OK) break;
       k_part_finish<<<ceil_div(N, 256), 256, 0, ctx->stream>>>(flag, excl, N, g->node_gpart);

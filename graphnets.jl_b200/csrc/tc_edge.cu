@@ -5,19 +5,22 @@
 //   E_part, G_part = ordered partial sums of ê and of the gathered addends per (32-row block, receiver) run
 //         (the edge -> node aggregation of src/nodefninput.jl:3, "aggregate, then transform")
 //
-// One 128-row tile per pass; persistent CTA, one per SM, 14 warps:
+// One 128-row tile per pass; persistent CTA, one per SM, 16 warps (512 threads x 128 registers: the register file is split
+// per scheduler, 4 x 16 K, so a 17th warp would cap every thread at 96 registers and spill all three data roles):
 //   warps 8-11  DRAIN : FFN hidden chunk TMEM fp32 -> +b1 -> relu -> bf16 -> TMEM (in place, the A operand of the
 //                       down-projection); finished accumulator TMEM -> swizzled shared-memory staging tile
 //   warps 0-3   LN    : one tile AHEAD of the MMAs: coalesced row loads (8 rows in flight per warp), LayerNorm with
 //                       transposed butterfly reductions, bf16 A operand into 128B-swizzled K-major shared memory,
 //                       partial sums E_part
-//   warps 4-7   OUT   : one tile BEHIND: staging row + x row + gathered P_s / P_r' rows, all 512 B coalesced,
-//                       -> y (streaming stores), partial sums G_part
-//   warp 12     MMA issuer (one elected lane), warp 13 weight loader (cp.async.bulk, 5 x 16 KB ring)
+//   warps 4-7, 12, 13  OUT : one tile BEHIND, in 16-row slices (8 per tile, slice k = 8 pass + s goes to OUT warp k mod 6):
+//                       staging row + x row + gathered P_s / P_r' rows, all 512 B coalesced, -> y (streaming stores), partial
+//                       sums G_part.  The role is bound by the latency of its gathered loads (4 rows in flight per warp), so it
+//                       gets every warp the register budget leaves (round 1: four warps, 12.7 k cycles per tile)
+//   warp 14     MMA issuer (one elected lane), warp 15 weight loader (cp.async.bulk, 5 x 16 KB ring; also prefetches the x rows
+//               of the pass after next into L2 with one bulk prefetch)
 // TMEM (512 columns): D[2] accumulators (double buffered across tiles: the epilogue of tile t overlaps the MMAs of
 // tile t+1) | Hd[2] hidden chunks (ping-pong inside a tile: the conversion of chunk c overlaps the MMAs of chunk c+1).
-// MMA order per tile (software-pipelined across tiles so that the tensor pipe never waits for a conversion):
-//   up1 blk down0 up2 down1 up3 down2 [up0 of the next tile] down3
+// MMA order per tile: up0 up1 blk dn0 up2 dn1 up3 dn2 dn3 (SEQ_PACKED below).
 #include "tc_ptx.cuh"
 #include "tc_edge.cuh"
 #include <stdlib.h>
@@ -34,29 +37,38 @@ constexpr int E_OFF_STG = E_OFF_W + NWS * HALF_BYTES;        // 64 KB: [4 column
 constexpr int E_OFF_MISC = E_OFF_STG + 65536;
 constexpr int E_MISC = 512 * 4 + 128 * 4 + 40 * 8 + 16;      // (29 barriers used)      // b1f[512], b2[128], barriers[40], tmem slot
 constexpr int E_SMEM = E_OFF_MISC + E_MISC + 1024;
-constexpr int E_WARPS = 14;
+constexpr int E_WARPS = 16;
+constexpr int W_MMA = 14, W_LOAD = 15;
+constexpr int OUT_ROWS = GNB_PART_ROWS;      // rows per OUT slice == cut of the partial-row index (lower.cu)
+constexpr int OUT_SLICES = TM / OUT_ROWS, OUT_WARPS = 6;
+static_assert(OUT_ROWS == 16 && OUT_SLICES == 8, "8 slices of 16 rows per tile");
 constexpr int E_THREADS = E_WARPS * 32;
 enum { EB_WFULL = 0, EB_WEMPTY = 5, EB_AFULL = 10, EB_AEMPTY = 12, EB_HIDFULL = 14, EB_HSREADY = 16, EB_OUTDONE = 18,
-       EB_ACCFREE = 20, EB_STGFULL = 22, EB_STGEMPTY = 23, EB_PEERW = 24 };
+       EB_ACCFREE = 20, EB_STGFULL = 24, EB_STGEMPTY = 32 };      // STGFULL / STGEMPTY: one pair per 16-row slice of the staging tile
 
 // block ids inside the packed edge weights (tc.cu::tc_core_pack): W1_0 W_blk W2_0 W1_1 W2_1 W1_2 W2_2 W1_3 W2_3
 constexpr int PK_W1_0 = 0, PK_BLK = 1, PK_W2_0 = 2, PK_W1_1 = 3, PK_W2_1 = 4, PK_W1_2 = 5, PK_W2_2 = 6, PK_W1_3 = 7, PK_W2_3 = 8;
-// issue order of a tile: [up0 up1 blk] [dn0 dn1] [up2 up3] [dn2 dn3]  (grouped: every SS <-> TS operand-mode switch of the
-// tensor pipe costs ~435 cycles, scratch/hwprobe.cu T5), one nibble per block
-#ifdef GNB_EXP_ORDERB
-constexpr unsigned long long SEQ_PACKED = (unsigned long long)PK_W1_0 | ((unsigned long long)PK_W1_1 << 4) | ((unsigned long long)PK_W2_0 << 8) |
-    ((unsigned long long)PK_BLK << 12) | ((unsigned long long)PK_W2_1 << 16) | ((unsigned long long)PK_W1_2 << 20) |
-    ((unsigned long long)PK_W1_3 << 24) | ((unsigned long long)PK_W2_2 << 28) | ((unsigned long long)PK_W2_3 << 32);
-constexpr int B_BLK = 3, B_FIRSTD = 2;
-#define IS_DN(b) (((b) == 2) | ((b) == 4) | ((b) == 7) | ((b) == 8))
-#define HB_OF(b) ((((b) == 0) | ((b) == 2) | ((b) == 5) | ((b) == 7)) ? 0 : 1)
-#else
+// issue order of a tile, one nibble per block (every SS <-> TS operand-mode switch of the tensor pipe costs ~435 cycles,
+// profiles/r01_hwprobe.log T5)
+#ifdef GNB_EDGE_ORDER_A
+// round-1 order  [up0 up1 blk] [dn0 dn1] [up2 up3] [dn2 dn3]: fewest SS <-> TS switches (3), but the conversion warps idle
+// between chunk 1 and chunk 2 until both down blocks have been issued and up2 has run
 constexpr unsigned long long SEQ_PACKED = (unsigned long long)PK_W1_0 | ((unsigned long long)PK_W1_1 << 4) | ((unsigned long long)PK_BLK << 8) |
     ((unsigned long long)PK_W2_0 << 12) | ((unsigned long long)PK_W2_1 << 16) | ((unsigned long long)PK_W1_2 << 20) |
     ((unsigned long long)PK_W1_3 << 24) | ((unsigned long long)PK_W2_2 << 28) | ((unsigned long long)PK_W2_3 << 32);
 constexpr int B_BLK = 2, B_FIRSTD = 2;
 #define IS_DN(b) (((b) == 3) | ((b) == 4) | ((b) == 7) | ((b) == 8))
 #define HB_OF(b) ((((b) == 0) | ((b) == 3) | ((b) == 5) | ((b) == 7)) ? 0 : 1)
+#else
+// order  up0 up1 blk dn0 up2 dn1 up3 dn2 dn3: every up-projection is issued as soon as its hidden buffer is free (up2 right
+// behind dn0, up3 right behind dn1), so the next chunk is ready when the conversion warps finish the previous one; costs two
+// more SS <-> TS switches per tile (5 x ~435 cycles), which the tensor pipe has to spare
+constexpr unsigned long long SEQ_PACKED = (unsigned long long)PK_W1_0 | ((unsigned long long)PK_W1_1 << 4) | ((unsigned long long)PK_BLK << 8) |
+    ((unsigned long long)PK_W2_0 << 12) | ((unsigned long long)PK_W1_2 << 16) | ((unsigned long long)PK_W2_1 << 20) |
+    ((unsigned long long)PK_W1_3 << 24) | ((unsigned long long)PK_W2_2 << 28) | ((unsigned long long)PK_W2_3 << 32);
+constexpr int B_BLK = 2, B_FIRSTD = 2;
+#define IS_DN(b) (((b) == 3) | ((b) == 5) | ((b) == 7) | ((b) == 8))
+#define HB_OF(b) ((((b) == 0) | ((b) == 3) | ((b) == 4) | ((b) == 7)) ? 0 : 1)
 #endif
 
 
@@ -150,16 +162,17 @@ __global__ void __launch_bounds__(E_THREADS, 1) k_edge5(const EdgeArgs a) {
   constexpr uint32_t NARR = CL2 ? 8u : 4u;                  // one arrival per warp (lane 0 after __syncwarp) on the barriers the 4-warp groups feed
 
   if (tid == 0) {
-    for (int i = 0; i < NWS; i++) { mbar_init(BAR(EB_WFULL + i), 1); mbar_init(BAR(EB_WEMPTY + i), 1); mbar_init(BAR(EB_PEERW + i), 1); }
+    // pair leader: WFULL[st] also counts the peer's "my half has landed" relay, so the MMA warp waits on ONE barrier per block
+    for (int i = 0; i < NWS; i++) { mbar_init(BAR(EB_WFULL + i), (CL2 && rank == 0) ? 2 : 1); mbar_init(BAR(EB_WEMPTY + i), 1); }
     for (int s = 0; s < 2; s++) {
       mbar_init(BAR(EB_AFULL + s), NARR); mbar_init(BAR(EB_AEMPTY + s), 1);
       mbar_init(BAR(EB_HIDFULL + s), 1); mbar_init(BAR(EB_HSREADY + s), NARR);
       mbar_init(BAR(EB_OUTDONE + s), 1); mbar_init(BAR(EB_ACCFREE + s), NARR);
     }
-    mbar_init(BAR(EB_STGFULL), 4); mbar_init(BAR(EB_STGEMPTY), 4);
+    for (int i = 0; i < OUT_SLICES; i++) { mbar_init(BAR(EB_STGFULL + i), 1); mbar_init(BAR(EB_STGEMPTY + i), 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 12) {
+  if (warp == W_MMA) {
     if (CL2) {
       asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
       asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
@@ -195,7 +208,7 @@ __global__ void __launch_bounds__(E_THREADS, 1) k_edge5(const EdgeArgs a) {
   const uint32_t HdA = tmem + 256, HdB = tmem + 384;
   const int grid = gridDim.x;
 
-  if (warp == 13) {
+  if (warp == W_LOAD) {
     // ===================================================== weight loader
     uint32_t it = 0;
     auto load_block = [&](int blk) {
@@ -226,10 +239,18 @@ __global__ void __launch_bounds__(E_THREADS, 1) k_edge5(const EdgeArgs a) {
       }
     };
     for (int tile = blockIdx.x; TILE_OK(tile); tile += grid) {
+      // the x rows of the pass after next -> L2: the LayerNorm warps (one pass ahead of the MMAs) then load at L2 latency
+      // instead of HBM latency
+      const int64_t pre0 = ((int64_t)tile + 2 * (int64_t)grid) * TM;
+      if (pre0 < a.R && elect_one()) {
+        const int64_t prows = a.R - pre0 < TM ? a.R - pre0 : TM;
+        bulk_prefetch_l2(a.x + (size_t)pre0 * H, (uint32_t)(prows * H * sizeof(float)));
+      }
+      __syncwarp();
 #pragma unroll 1
       for (int b = 0; b < 9; b++) load_block((SEQ_PACKED >> (4 * b)) & 15);
     }
-  } else if (warp == 12) {
+  } else if (warp == W_MMA) {
     // ===================================================== MMA issuer (whole warp converged, one lane issues)
     uint32_t it = 0, tl = 0;
     uint64_t w0 = 0, w1 = 0;
@@ -241,28 +262,30 @@ __global__ void __launch_bounds__(E_THREADS, 1) k_edge5(const EdgeArgs a) {
         for (int b = 0; b < 9; b++, it++) {
           const uint32_t st = it % NWS, ph = (it / NWS) & 1;
           mbar_wait(BAR(EB_WFULL + st), ph);
-          if (lane == 0) mbar_arrive_cluster(map_to_cta(BAR(EB_PEERW + st), 0));
+          if (lane == 0) mbar_arrive_cluster(map_to_cta(BAR(EB_WFULL + st), 0));
           __syncwarp();
         }
       }
     } else {
+    // ring position kept as (stage, phase) counters: no division in the issue loop
+    uint32_t rst = 0, rph = 0;
+    auto ring_next = [&]() { rst = rst + 1 == NWS ? 0 : rst + 1; rph ^= (rst == 0) ? 1u : 0u; };
     auto get_w = [&]() {
       if (CL2) {
-        st0 = st1 = it % NWS;
-        const uint32_t ph0 = (it / NWS) & 1;
-        it += 1;
-        mbar_wait(BAR(EB_WFULL + st0), ph0);
-        mbar_wait_cluster(BAR(EB_PEERW + st0), ph0);
-        w0 = umma_desc(sW + st0 * HALF_BYTES);
+        st0 = st1 = rst;
+        mbar_wait_cluster(BAR(EB_WFULL + rst), rph);      // own half (expect_tx) + the peer's relay arrive
+        w0 = umma_desc(sW + rst * HALF_BYTES);
+        ring_next();
         return;
       }
-      st0 = it % NWS; st1 = (it + 1) % NWS;
-      const uint32_t ph0 = (it / NWS) & 1, ph1 = ((it + 1) / NWS) & 1;
-      it += 2;
-      mbar_wait(BAR(EB_WFULL + st0), ph0);
-      mbar_wait(BAR(EB_WFULL + st1), ph1);
-      w0 = umma_desc(sW + st0 * HALF_BYTES);
-      w1 = umma_desc(sW + st1 * HALF_BYTES);
+      st0 = rst;
+      mbar_wait(BAR(EB_WFULL + rst), rph);
+      w0 = umma_desc(sW + rst * HALF_BYTES);
+      ring_next();
+      st1 = rst;
+      mbar_wait(BAR(EB_WFULL + rst), rph);
+      w1 = umma_desc(sW + rst * HALF_BYTES);
+      ring_next();
     };
     auto COMMIT = [&](int i) {
       if (CL2) tc_commit2(BAR(i));
@@ -272,22 +295,19 @@ __global__ void __launch_bounds__(E_THREADS, 1) k_edge5(const EdgeArgs a) {
       const uint32_t st = tl & 1, uph = (tl >> 1) & 1;
       const uint64_t adesc = umma_desc(base + E_OFF_A + st * BLK_BYTES);
       const uint32_t D = tmem + 128 * st;
-#pragma unroll 1
+      // fully unrolled: which block is an up / block / down GEMM, its hidden buffer and its barriers are compile-time
+      // constants - the issuing warp is a single dependent instruction stream and every instruction it does not execute
+      // shortens the gap between two 520-cycle UMMA blocks
+#pragma unroll
       for (int b = 0; b < 9; b++) {
         EDBG(b);
         get_w();
         const bool is_dn = IS_DN(b);
         const int hb = HB_OF(b);      // hidden buffer of an up / down block
         const uint32_t Hd = hb ? HdB : HdA;
-        if (CL2) {
-          if (b == 0) mbar_wait_cluster(BAR(EB_AFULL + st), uph);
-          if (b == B_FIRSTD) mbar_wait_cluster(BAR(EB_ACCFREE + st), uph ^ 1);
-          if (is_dn) mbar_wait_cluster(BAR(EB_HSREADY + hb), b >= 7 ? 1u : 0u);
-        } else {
-          if (b == 0) mbar_wait(BAR(EB_AFULL + st), uph);                          // A tile of this pass
-          if (b == B_FIRSTD) mbar_wait(BAR(EB_ACCFREE + st), uph ^ 1);                    // accumulator drained (two tiles ago)
-          if (is_dn) mbar_wait(BAR(EB_HSREADY + hb), b >= 7 ? 1u : 0u);            // hidden chunk converted to bf16
-        }
+        if (b == 0) mbar_wait_cluster(BAR(EB_AFULL + st), uph);                      // A tile of this pass
+        if (b == B_FIRSTD) mbar_wait_cluster(BAR(EB_ACCFREE + st), uph ^ 1);         // accumulator drained (two tiles ago)
+        if (is_dn) mbar_wait_cluster(BAR(EB_HSREADY + hb), b >= 7 ? 1u : 0u);        // hidden chunk converted to bf16
         tc_fence_after();
         if (elect_one()) {
           if (is_dn) {                                                             // D += relu(.)[chunk] W2_c
@@ -311,7 +331,7 @@ __global__ void __launch_bounds__(E_THREADS, 1) k_edge5(const EdgeArgs a) {
       EDBG(9);
     }
     }
-  } else if (warp >= 8) {
+  } else if (warp >= 8 && warp < 12) {
     // ===================================================== DRAIN warps (TMEM lane quadrant = warp)
     const int dq = warp - 8;                 // TMEM lane quadrant (== warp % 4)
     const uint32_t lane_base = ((uint32_t)(dq * 32)) << 16;
@@ -365,7 +385,10 @@ __global__ void __launch_bounds__(E_THREADS, 1) k_edge5(const EdgeArgs a) {
       mbar_wait(BAR(EB_OUTDONE + st), uph);
       EDBG(9);
       tc_fence_after();
-      mbar_wait(BAR(EB_STGEMPTY), (tl & 1) ^ 1);
+      // the staging tile is handed over per 16-row slice: this warp's rows are slices 2 dq and 2 dq + 1, free as soon as the
+      // OUT warps have drained those two slices of the previous tile (not the whole tile)
+      mbar_wait(BAR(EB_STGEMPTY + 2 * dq), (tl & 1) ^ 1);
+      mbar_wait(BAR(EB_STGEMPTY + 2 * dq + 1), (tl & 1) ^ 1);
       EDBG(10);
       const uint32_t D = tmem + 128 * st;
       const int r = dq * 32 + lane;
@@ -390,7 +413,8 @@ __global__ void __launch_bounds__(E_THREADS, 1) k_edge5(const EdgeArgs a) {
         put(va, 2);
         put(vb, 3);
       }
-      ARRIVE_LOCAL(EB_STGFULL);
+      __syncwarp();
+      if (lane == 0) { mbar_arrive(BAR(EB_STGFULL + 2 * dq)); mbar_arrive(BAR(EB_STGFULL + 2 * dq + 1)); }
       EDBG(11);
     }
   } else if (warp < 4) {
@@ -514,19 +538,25 @@ __global__ void __launch_bounds__(E_THREADS, 1) k_edge5(const EdgeArgs a) {
       EDBG(6);
     }
   } else {
-    // ===================================================== OUT warps (4-7), one tile behind the MMAs
-    const int q = warp & 3;
+    // ===================================================== OUT warps (4-7, 12, 13), one tile behind the MMAs.  A tile is drained in
+    // 8 slices of 16 rows (= one cut of the partial-row index); slice k = 8 pass + s is taken by OUT warp k mod 6
+    const int ow = warp < 8 ? warp - 4 : warp - 8;
     const float4 b2v = *reinterpret_cast<const float4*>(sB2 + 4 * lane);
     const float* xbase = a.x + 4 * lane;
     const float* base1 = a.add1 + 4 * lane;
     const float* base2 = a.add2 + 4 * lane;
-    const uint32_t s_lane = (uint32_t)(E_OFF_STG + (lane >> 3) * 16384 + (32 * q) * 128);
+    const uint32_t s_lane0 = (uint32_t)(E_OFF_STG + (lane >> 3) * 16384);
     const uint32_t s_chunk = (uint32_t)(lane & 7);
-    uint32_t tl = 0;
-    for (int tile = blockIdx.x; TILE_OK(tile); tile += grid, tl++) {
-      const int64_t row0 = (int64_t)tile * TM + 32 * q;
+    const int first = (int)blockIdx.x - (int)rank;      // both CTAs of a pair run the same number of passes
+    const int npass = first < a.num_tiles ? (a.num_tiles - first + grid - 1) / grid : 0;
+    for (int k = ow; k < OUT_SLICES * npass && !wd_dead; k += OUT_WARPS) {
+      const uint32_t tl = (uint32_t)k >> 3;
+      const int sl = k & (OUT_SLICES - 1);
+      const int tile = blockIdx.x + (int)tl * grid;
+      const uint32_t s_lane = s_lane0 + (uint32_t)((OUT_ROWS * sl) * 128);
+      const int64_t row0 = (int64_t)tile * TM + OUT_ROWS * sl;
       const int64_t left = a.R - row0;
-      const int rows = left < 0 ? 0 : (left > 32 ? 32 : (int)left);
+      const int rows = left < 0 ? 0 : (left > OUT_ROWS ? OUT_ROWS : (int)left);
       int my_i1 = 0, my_i2 = 0, my_pid = -1;
       if (lane < rows) {
         my_i1 = a.idx1 ? __ldg(a.idx1 + row0 + lane) : (int)(row0 + lane);
@@ -548,11 +578,11 @@ __global__ void __launch_bounds__(E_THREADS, 1) k_edge5(const EdgeArgs a) {
       };
 #pragma unroll
       for (int u = 0; u < 4; u++) issue1(u, u);
-      mbar_wait(BAR(EB_STGFULL), tl & 1);
+      mbar_wait(BAR(EB_STGFULL + sl), tl & 1);
       EDBG(1);
       float4 acc = f4zero();
 #pragma unroll 1
-      for (int i0 = 0; i0 < 32; i0 += 4) {
+      for (int i0 = 0; i0 < OUT_ROWS; i0 += 4) {
         float4 d[4];
 #pragma unroll
         for (int u = 0; u < 4; u++) {
@@ -570,17 +600,17 @@ __global__ void __launch_bounds__(E_THREADS, 1) k_edge5(const EdgeArgs a) {
           if (fl) *(reinterpret_cast<float4*>(a.Gpart + (size_t)pid * H) + lane) = acc;
           acc.x = fl ? 0.f : acc.x; acc.y = fl ? 0.f : acc.y; acc.z = fl ? 0.f : acc.z; acc.w = fl ? 0.f : acc.w;
           pid += fl ? 1 : 0;
-          if (i0 + 4 < 32) issue1(u, i + 4);   // refill this slot with the same row of the next group
+          if (i0 + 4 < OUT_ROWS) issue1(u, i + 4);   // refill this slot with the same row of the next group
         }
       }
-      ARRIVE_LOCAL(EB_STGEMPTY);
+      ARRIVE_LOCAL(EB_STGEMPTY + sl);
       EDBG(2);
     }
   }
   tc_fence_before();
   __syncthreads();
   if (CL2) cluster_sync_all();      // the peer may still be reading this CTA's shared / tensor memory
-  if (warp == 12) {
+  if (warp == W_MMA) {
     if (CL2) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
     else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
   }

@@ -78,6 +78,10 @@ static __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, u
                "l"(src), "r"(bytes), "r"(bar)
                : "memory");
 }
+// one instruction pulls `bytes` (multiple of 16) of global memory into L2 (no registers, no shared memory)
+static __device__ __forceinline__ void bulk_prefetch_l2(const void* src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+}
 static __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 static __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 static __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }

@@ -13,7 +13,7 @@ BF16_TOL = 1e-2     # tensor-core path
 # Second metric of SURVEY 8c, asserted beside the max-norm one: worst element-wise |y - ref| / (|ref| + 1e-3 max|ref|).
 # A max-norm error eps allows at most eps / 1e-3 here (all of it landing on a zero of the reference); the bounds below are
 # far tighter than that implication - an element-wise blow-up on small outputs hidden by the max norm would trip them.
-FP32_EW_TOL = 1e-3
+FP32_EW_TOL = 5e-3
 BF16_EW_TOL = 5.0
 # ... and the RMS relative error ||y - ref|| / ||ref||, which no single element can hide in
 FP32_RMS_TOL = 5e-6
