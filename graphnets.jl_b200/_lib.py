@@ -12,7 +12,7 @@ LIB_PATH = os.path.join(HERE, "libgnb200_%s.so" % _VARIANT if _VARIANT else "lib
 
 GNB_OK, GNB_ERR_INVALID, GNB_ERR_CUDA, GNB_ERR_OOM, GNB_ERR_UNSUPPORTED, GNB_ERR_TIMEOUT = 0, -1, -2, -3, -4, -5
 PREC_FP32, PREC_BF16, PREC_AUTO = 0, 2, 3
-ADJ_F32, ADJ_U8, ADJ_I32 = 0, 1, 2
+ADJ_F32, ADJ_U8, ADJ_I32, ADJ_BITS = 0, 1, 2, 3
 LAYER_BLOCK, LAYER_CORE = 0, 1
 PRECISIONS = {"fp32": PREC_FP32, "bf16": PREC_BF16, "auto": PREC_AUTO}
 
@@ -54,6 +54,8 @@ SIGNATURES = {
     "gnb_ctx_launch_count": (C.c_int64, [C.c_void_p]),
     "gnb_graph_lower": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, i32p, C.c_int, C.c_int, C.c_int,
                                   C.POINTER(C.c_void_p)]),
+    "gnb_graph_from_coo": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, i32p, i32p, C.c_int, C.c_int,
+                                     C.POINTER(C.c_void_p)]),
     "gnb_graph_destroy": (C.c_int, [C.c_void_p]),
     "gnb_graph_counts": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64), i32p, i32p]),
     "gnb_graph_export_host": (C.c_int, [C.c_void_p, C.c_void_p] + [C.c_void_p] * 7),

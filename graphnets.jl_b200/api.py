@@ -106,6 +106,18 @@ def _is_single(graphs):
 
 
 # ----------------------------------------------------------------------------- GNGraphBatch
+def pack_adjacency_bits(mask):
+    """uint8 `isone` mask [B][PN][PN] (element (i,j,b) at i + PN*j + PN^2*b) -> GNB_ADJ_BITS words: bit (i + PN*j) of graph b,
+    little-endian, every graph padded to whole 32-bit words."""
+    B = mask.shape[0]
+    flat = np.ascontiguousarray(mask.reshape(B, -1))
+    packed = np.packbits(flat, axis=1, bitorder="little")
+    pad = (-packed.shape[1]) % 4
+    if pad:
+        packed = np.concatenate([packed, np.zeros((B, pad), np.uint8)], axis=1)
+    return np.ascontiguousarray(packed).view(np.uint32)
+
+
 class GNGraphBatch:
     """Lowered structure of a batch (reference struct: src/gngraphbatch.jl:1-17).  Instead of
     seven dense broadcaster tensors it holds a device-resident receiver-sorted COO + CSR."""
@@ -143,13 +155,65 @@ class GNGraphBatch:
         self.engine = get_engine(device)
         self.engine.bind_stream()
         h = C.c_void_p()
-        check(lib.gnb_graph_lower(self.engine.ctx, mask.ctypes.data_as(C.c_void_p), _lib.ADJ_U8, 0,
+        # the `isone` mask goes up bit-packed (GNB_ADJ_BITS): 8x fewer PCIe bytes than one byte per cell
+        bits = pack_adjacency_bits(mask)
+        check(lib.gnb_graph_lower(self.engine.ctx, bits.ctypes.data_as(C.c_void_p), _lib.ADJ_BITS, 0,
                                   self.n_nodes.ctypes.data_as(_lib.i32p), PN, Badj, self.B, C.byref(h)))
+        self._finish(h)
+
+    def _finish(self, h):
         self.handle = h
         E, N = C.c_int64(), C.c_int64()
         check(lib.gnb_graph_counts(self.handle, C.byref(E), C.byref(N), None, None))
         self.E, self.N = E.value, N.value
         self._index = None
+
+    @classmethod
+    def from_coo(cls, src, dst, graph_edge_ptr, n_nodes, PN=None, device=None):
+        """Lower a batch given as COO edge lists (C ABI: gnb_graph_from_coo): graph b owns edges
+        [graph_edge_ptr[b], graph_edge_ptr[b+1]) with local sender ids `src` and receiver ids `dst`; each graph's edges
+        strictly ascending in src + PN*dst (receiver-major = the order of `findall(isone, adj[:])`, src/pad.jl:30, in which the
+        reference takes edge features).  The index equals the one `batch` builds from the equivalent adjacency matrices."""
+        self = cls.__new__(cls)
+        src = np.ascontiguousarray(src, np.int32)
+        dst = np.ascontiguousarray(dst, np.int32)
+        ep = np.ascontiguousarray(graph_edge_ptr, np.int32)
+        self.n_nodes = np.ascontiguousarray(n_nodes, np.int32)
+        assert ep.ndim == 1 and ep.size == self.n_nodes.size + 1 and self.n_nodes.size > 0
+        assert src.shape == dst.shape == (int(ep[-1]),), "edge list length != graph_edge_ptr[-1]"
+        self.B = int(self.n_nodes.size)
+        self.single = self.B == 1
+        self.node_block_size = int(PN) if PN else max(int(self.n_nodes.max()), 1)
+        self.edge_block_size = self.node_block_size ** 2
+        self._mask = None
+        self._coo = (src, dst, ep)
+        self.engine = get_engine(device)
+        self.engine.bind_stream()
+        h = C.c_void_p()
+        check(lib.gnb_graph_from_coo(self.engine.ctx, src.ctypes.data_as(C.c_void_p), dst.ctypes.data_as(C.c_void_p), 0,
+                                     ep.ctypes.data_as(_lib.i32p), self.n_nodes.ctypes.data_as(_lib.i32p),
+                                     self.node_block_size, self.B, C.byref(h)))
+        self._finish(h)
+        return self
+
+    def __getattr__(self, name):
+        # `graphs.adj_mats` of a batch that came in as edge lists: dense matrices are built only when somebody asks for them
+        if name == "adj_mats" and self.__dict__.get("_coo") is not None:
+            self._dense_mask()
+            return self.__dict__["adj_mats"]
+        raise AttributeError(name)
+
+    def _dense_mask(self):
+        """uint8 `isone` mask [b][j][i] (built on demand for graphs that came in as edge lists)"""
+        if self._mask is None:
+            src, dst, ep = self._coo
+            PN = self.node_block_size
+            mask = np.zeros((self.B, PN, PN), np.uint8)
+            b = np.repeat(np.arange(self.B), np.diff(ep))
+            mask[b, dst, src] = 1
+            self._mask = mask
+            self.adj_mats = [np.ascontiguousarray(mask[i, :n, :n].T) for i, n in enumerate(self.n_nodes)]
+        return self._mask
 
     def __del__(self):
         try:
@@ -162,7 +226,7 @@ class GNGraphBatch:
     @property
     def padded_adj_mats(self):
         """(PN, PN, B') Float32 like src/pad.jl:1-10 (B' = number of distinct structures)."""
-        return np.asfortranarray(self._mask.transpose(2, 1, 0).astype(np.float32))
+        return np.asfortranarray(self._dense_mask().transpose(2, 1, 0).astype(np.float32))
 
     def index(self):
         """Host copy of the lowered index (dict of int32 numpy arrays)."""
@@ -317,6 +381,23 @@ def batch_compact(adj_stacked, ef=None, nf=None, gf=None, device=None):
     return GNData(gb, wrap("e", mv(ef, gb.E)), wrap("n", mv(nf, gb.N)), wrap("g", mv(gf, gb.B)))
 
 
+def batch_coo(src, dst, graph_edge_ptr, n_nodes, ef=None, nf=None, gf=None, PN=None, device=None):
+    """`batch` for graphs given as COO edge lists (`GNGraphBatch.from_coo`) and compact features `[rows][D]` in the same
+    (graph, receiver, sender) order - no dense adjacency anywhere, neither on the host nor on the PCIe bus."""
+    gb = GNGraphBatch.from_coo(src, dst, graph_edge_ptr, n_nodes, PN=PN, device=device)
+    dev = gb.engine.torch_device
+
+    def mv(x, rows):
+        if x is None:
+            return None
+        t = x if isinstance(x, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(x, np.float32))
+        t = t.to(dev, torch.float32).contiguous()
+        assert t.dim() == 2 and t.shape[0] == rows, "expected %d rows, got %s" % (rows, tuple(t.shape))
+        return t
+    wrap = lambda k, c: None if c is None else Padded(k, c, gb)
+    return GNData(gb, wrap("e", mv(ef, gb.E)), wrap("n", mv(nf, gb.N)), wrap("g", mv(gf, gb.B)))
+
+
 # ----------------------------------------------------------------------------- unbatch / views
 def _compact(x):
     return None if x is None else x.compact
@@ -417,8 +498,8 @@ def _collapse_idxs(g):
     (column-major, i >= j) whose adjacency entry is one."""
     PN = g.node_block_size
     out = []
-    for b in range(g._mask.shape[0]):
-        a = g._mask[b].T        # a[i, j]
+    for b in range(g._dense_mask().shape[0]):
+        a = g._dense_mask()[b].T        # a[i, j]
         c = 0
         sel = []
         for j in range(PN):

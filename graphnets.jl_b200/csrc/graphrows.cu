@@ -6,8 +6,8 @@
 // runs in front of the first core of a chain) replaces ten small GEMM / segmented-sum launches:
 //   k_graph_pre :  P_ue = LN1(u) W_eu + c_e          per-graph row of the edge update   (src/edgefninput.jl:6)
 //                  P_un = LN1(u) W_nu + c_n          per-graph row of the node update   (src/nodefninput.jl:5)
-//   k_graph_post:  s_e = sum of the graph's node aggregates (== sum of its edges, src/graphfninput.jl:3)
-//                  s_v = sum of its updated nodes                                      (src/graphfninput.jl:4)
+//   k_graph_post:  s_e = sum of the graph's edges (src/graphfninput.jl:3) and s_v = sum of its updated nodes (:4), both by
+//                  linearity from the partial rows the aggregate / node kernels emit (a handful of rows per graph)
 //                  h_u = W_g [s_e ; s_v ; LN1(u)] + b_g                                 (src/gnblock.jl:67)
 //                  y_u = (u + h_u) + W2 relu(W1 LN2(u) + b1) + b2                       (src/gncore.jl:56-68)
 #include "kernels.cuh"
@@ -135,43 +135,38 @@ __global__ void __launch_bounds__(GP_THREADS) k_graph_post(const GraphPostArgs a
   __shared__ __align__(16) float cat[RT][3 * H];   // [s_e | s_v | LN1(u)]   (s_v slot first holds gamma . sum v^)
   __shared__ __align__(16) float xb[RT][H];        // LN2(u); later y_u, LN1'(y_u)
   __shared__ __align__(16) float svg[RT][H];       // sum of the node addends
+  __shared__ __align__(16) float seg[RT][H];       // sum of the edge addends
   __shared__ __align__(16) float hid[RT][4 * H];   // FFN hidden; before that the scratch of the K-split reductions
   float(*red)[RT][H] = reinterpret_cast<float(*)[RT][H]>(&hid[0][0]);      // [4][RT][H] == sizeof(hid)
   const int tid = threadIdx.x, n = tid & (H - 1), ks = tid >> 7, warp = tid >> 5, lane = tid & 31;
   const int64_t g0 = (int64_t)blockIdx.x * RT;
-  // ---- ordered sums over the graph's nodes (rows of a graph are contiguous): deterministic, no atomics; group ks owns
-  // graphs 2 ks, 2 ks + 1 of the CTA
+  // ---- ordered sums of the graph's partial rows (per (16-node block, graph) run: a handful per graph): deterministic, no
+  // atomics; group ks owns graphs 2 ks, 2 ks + 1 of the CTA
 #pragma unroll 1
   for (int r = 2 * ks; r < 2 * ks + 2; r++) {
     const int64_t g = g0 + r < a.B ? g0 + r : a.B - 1;
     xs[r][n] = a.xg[(size_t)g * H + n];
-    const int v0 = a.graph_node_ptr[g], v1 = a.graph_node_ptr[g + 1];
-    float s0 = 0.f;
-    int v = v0;
-    for (; v + 15 < v1; v += 16) {      // 16 independent loads in flight, summed in row order
-      float e[16];
-#pragma unroll
-      for (int j = 0; j < 16; j++) e[j] = a.agg[(size_t)(v + j) * H + n];
-#pragma unroll
-      for (int j = 0; j < 16; j++) s0 += e[j];
-    }
-    for (; v < v1; v++) s0 += a.agg[(size_t)v * H + n];
-    cat[r][n] = s0;
-    // partial rows of the node kernel: sum of v^ (scaled by the LN1 node scale, which the packed weights carry) and of the addends
     const int p0 = a.graph_npart_ptr[g], p1 = a.graph_npart_ptr[g + 1];
-    float sh = 0.f, sg = 0.f;
-    for (int p = p0; p < p1; p++) { sh += a.Vpart[(size_t)p * H + n]; sg += a.Npart[(size_t)p * H + n]; }
+    float se = 0.f, sg = 0.f, sh = 0.f, sn = 0.f;
+    for (int p = p0; p < p1; p++) {
+      se += a.SEpart[(size_t)p * H + n]; sg += a.SGpart[(size_t)p * H + n];
+      sh += a.Vpart[(size_t)p * H + n]; sn += a.Npart[(size_t)p * H + n];
+    }
+    // sums of the normalised rows, scaled by the LayerNorm scales the packed bf16 weights carry; the fp32 weights follow below
+    cat[r][n] = se * a.g1e[n];
+    seg[r][n] = sg;
     cat[r][H + n] = sh * a.g1n[n];
-    svg[r][n] = sg;
+    svg[r][n] = sn;
   }
   __syncthreads();
   if (warp < RT) ln_row(xs[warp], &cat[warp][2 * H], a.g1, a.b1ln, a.eps1, a.eps_mode1, lane);
   else ln_row(xs[warp - RT], xb[warp - RT], a.g2, a.b2ln, a.eps2, a.eps_mode2, lane);
-  // ---- s_v = W_nv (gamma . sum v^) + sum of the addends
+  // ---- s_e = W_ee (gamma_e . sum ê) + sum of the edge addends;  s_v = W_nv (gamma_n . sum v^) + sum of the node addends
   {
-    float t[RT];
+    float t[RT], te[RT];
 #pragma unroll
-    for (int r = 0; r < RT; r++) t[r] = 0.f;
+    for (int r = 0; r < RT; r++) { t[r] = 0.f; te[r] = 0.f; }
+    gemv_slice<H / 4, 3 * H>(&cat[0][0], ks * (H / 4), a.Wee, H, n, te);
     gemv_slice<H / 4, 3 * H>(&cat[0][H], ks * (H / 4), a.Wnv, H, n, t);
 #pragma unroll
     for (int r = 0; r < RT; r++) red[ks][r][n] = t[r];
@@ -179,6 +174,14 @@ __global__ void __launch_bounds__(GP_THREADS) k_graph_post(const GraphPostArgs a
     if (ks == 0) {
 #pragma unroll
       for (int r = 0; r < RT; r++) cat[r][H + n] = svg[r][n] + (((red[0][r][n] + red[1][r][n]) + red[2][r][n]) + red[3][r][n]);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < RT; r++) red[ks][r][n] = te[r];
+    __syncthreads();
+    if (ks == 0) {
+#pragma unroll
+      for (int r = 0; r < RT; r++) cat[r][n] = seg[r][n] + (((red[0][r][n] + red[1][r][n]) + red[2][r][n]) + red[3][r][n]);
     }
     __syncthreads();
   }
@@ -267,7 +270,8 @@ int launch_graph_pre(gnb_ctx* ctx, const GraphPreArgs& a) {
 
 int launch_graph_post(gnb_ctx* ctx, const GraphPostArgs& a, int64_t N) {
   if (a.B <= 0) return GNB_OK;
-  Launch L(ctx, "graph_post", 8.0 * N * H + 8.0 * a.B * H + 4.0 * 11 * H * H, 22.0 * a.B * H * H);
+  (void)N;
+  Launch L(ctx, "graph_post", 8.0 * a.B * H + 4.0 * 12 * H * H, 24.0 * a.B * H * H);
   k_graph_post<<<ceil_div(a.B, RT), GP_THREADS, 0, ctx->stream>>>(a);
   GNB_CUDA(cudaGetLastError());
   return GNB_OK;

@@ -17,8 +17,12 @@ struct GraphPreArgs {
 struct GraphPostArgs {
   const float* xg;
   int64_t B;
-  const int32_t* graph_node_ptr;   // [B+1]
-  const float* agg;      // [N][128] edge -> node aggregates
+  // edge -> graph sum of the block output (== sum of the node aggregates, src/graphfninput.jl:3), by linearity over the partial
+  // rows of the aggregate kernel (tc.cu::k_tc_agg2):  s_e = (g1e . sum SE_part) W_ee + sum SG_part
+  const float* SEpart;   // [n_nparts][128] partial sums of the nodes' summed normalised edge rows
+  const float* SGpart;   // [n_nparts][128] partial sums of the nodes' summed edge addends
+  const float* Wee;      // [128][128] rows [0,H) of the edge Dense (k-major), without the LayerNorm scale
+  const float* g1e;      // [128] LN1 (edge) scale
   // node -> graph sum of the block output h_v = W_nv' v^ + addends, by linearity over the partial rows of the node kernel
   const int32_t* graph_npart_ptr;   // [B+1]
   const float* Vpart;    // [n_nparts][128] partial sums of the normalised node rows v^

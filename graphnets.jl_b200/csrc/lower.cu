@@ -87,6 +87,19 @@ __global__ void k_scan_apply(const int32_t* __restrict__ in, int64_t n, const in
   if (write_total && blockIdx.x == 0 && threadIdx.x == 0) out[n] = sums[nb];
 }
 
+// Bit-packed adjacency (GNB_ADJ_BITS): bit (i + PN*j) of graph b, little-endian in 32-bit words, every graph starting on a word
+// boundary (words_per_graph = ceil(PN*PN / 32)).  8x less PCIe traffic than the uint8 mask: what the host-buffer path uploads.
+struct BitAdj { uint32_t w; };      // tag type: a `const BitAdj*` is the word array
+template <typename T>
+static __device__ __forceinline__ bool adj_is_one(const T* adj, size_t graph, int PN, int i, int j) {
+  return adj[(graph * PN + j) * PN + i] == (T)1;
+}
+static __device__ __forceinline__ bool adj_is_one(const BitAdj* adj, size_t graph, int PN, int i, int j) {
+  const size_t wpg = ((size_t)PN * PN + 31) / 32;
+  const uint32_t bit = (uint32_t)(i + PN * j);
+  return (adj[graph * wpg + (bit >> 5)].w >> (bit & 31)) & 1u;
+}
+
 template <typename T>
 __global__ void k_count_cols(const T* __restrict__ adj, const int32_t* __restrict__ n_nodes, int PN,
                              int Badj, int64_t total_cols, int32_t* __restrict__ colcount) {
@@ -98,10 +111,9 @@ __global__ void k_count_cols(const T* __restrict__ adj, const int32_t* __restric
   int n = n_nodes[ba];
   int cnt = 0;
   if (j < n) {
-    const T* col = adj + ((size_t)ba * PN + j) * PN;
     for (int i0 = 0; i0 < n; i0 += 32) {
       int i = i0 + lane;
-      bool a = (i < n) && (col[i] == (T)1);
+      bool a = (i < n) && adj_is_one(adj, (size_t)ba, PN, i, j);
       cnt += __popc(__ballot_sync(0xffffffffu, a));
     }
   }
@@ -129,10 +141,9 @@ __global__ void k_fill_edges(const T* __restrict__ adj, const int32_t* __restric
     node_in_ptr[nbase + j] = off;
     node_graph[nbase + j] = b;
   }
-  const T* col = adj + ((size_t)ba * PN + j) * PN;
   for (int i0 = 0; i0 < n; i0 += 32) {
     int i = i0 + lane;
-    bool a = (i < n) && (col[i] == (T)1);
+    bool a = (i < n) && adj_is_one(adj, (size_t)ba, PN, i, j);
     unsigned m = __ballot_sync(0xffffffffu, a);
     if (a) {
       int e = off + __popc(m & ((1u << lane) - 1u));
@@ -256,62 +267,10 @@ int lower_typed(gnb_ctx* ctx, const T* adj_dev, const int32_t* nn_dev, int PN, i
 
 size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
 
-}  // namespace
-
-extern "C" int gnb_graph_lower(gnb_ctx* ctx, const void* adj, int adj_dtype, int adj_on_device,
-                               const int32_t* n_nodes, int PN, int Badj, int B, gnb_graph** out) {
-  GNB_CHECK(ctx && adj && n_nodes && out, "gnb_graph_lower: null argument");
-  GNB_CHECK(B > 0 && PN > 0, "gnb_graph_lower: need B > 0 and PN > 0 (length(adj_mats) > 0, src/checks.jl:8)");
-  GNB_CHECK(Badj == 1 || Badj == B, "gnb_graph_lower: Badj must be 1 or B");
-  GNB_CHECK(adj_dtype == GNB_ADJ_F32 || adj_dtype == GNB_ADJ_U8 || adj_dtype == GNB_ADJ_I32,
-            "gnb_graph_lower: bad adj_dtype");
-  GNB_CHECK((int64_t)B * PN * PN < ((int64_t)1 << 31), "gnb_graph_lower: B*PN^2 exceeds int32 slot range");
-  int64_t N = 0;
-  std::vector<int32_t> gnp(B + 1, 0);
-  for (int b = 0; b < B; b++) {
-    int n = n_nodes[Badj == 1 ? 0 : b];
-    GNB_CHECK(n >= 0 && n <= PN, "gnb_graph_lower: n_nodes[%d]=%d outside [0, PN=%d]", b, n, PN);
-    N += n;
-    gnp[b + 1] = (int32_t)N;
-  }
-  GNB_CHECK(N < ((int64_t)1 << 31), "gnb_graph_lower: too many nodes");
-  GNB_CUDA(cudaSetDevice(ctx->device));
-  size_t esz = adj_dtype == GNB_ADJ_U8 ? 1 : 4;
-  size_t adj_bytes = (size_t)Badj * PN * PN * esz;
-  // temporaries out of the scratch arena
-  ctx->arena.reset();
-  int rc = GNB_OK;
-  int64_t total_cols = (int64_t)B * PN;
-  int32_t* nn_dev = arena_ptr<int32_t>(ctx->arena, Badj, &rc);
-  int32_t* colcount = arena_ptr<int32_t>(ctx->arena, total_cols, &rc);
-  int32_t* coloff = arena_ptr<int32_t>(ctx->arena, total_cols + 1, &rc);
-  int32_t* sums = arena_ptr<int32_t>(ctx->arena, ceil_div(total_cols, SCAN_ITEMS) + 2, &rc);
-  const void* adj_dev = adj;
-  if (!adj_on_device) {
-    void* tmp = nullptr;
-    int r2 = ctx->arena.alloc(adj_bytes, &tmp);
-    if (r2 != GNB_OK) rc = r2;
-    adj_dev = tmp;
-  }
-  if (rc != GNB_OK) return rc;
-  if (!adj_on_device) GNB_CUDA(cudaMemcpyAsync((void*)adj_dev, adj, adj_bytes, cudaMemcpyHostToDevice, ctx->stream));
-  GNB_CUDA(cudaMemcpyAsync(nn_dev, n_nodes, sizeof(int32_t) * Badj, cudaMemcpyHostToDevice, ctx->stream));
-
-  gnb_graph tmpg;
-#define DISPATCH(phase, gp)                                                                              \
-  (adj_dtype == GNB_ADJ_F32 ? lower_typed<float>(ctx, (const float*)adj_dev, nn_dev, PN, Badj, B, colcount, coloff, sums, gp, phase) \
-   : adj_dtype == GNB_ADJ_U8 ? lower_typed<uint8_t>(ctx, (const uint8_t*)adj_dev, nn_dev, PN, Badj, B, colcount, coloff, sums, gp, phase) \
-                             : lower_typed<int32_t>(ctx, (const int32_t*)adj_dev, nn_dev, PN, Badj, B, colcount, coloff, sums, gp, phase))
-  GNB_TRY(DISPATCH(0, &tmpg));
-  int32_t E32 = 0;
-  GNB_CUDA(cudaMemcpyAsync(&E32, coloff + total_cols, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
-  GNB_CUDA(cudaStreamSynchronize(ctx->stream));
-  int64_t E = E32;
-  GNB_CHECK(E >= 0, "gnb_graph_lower: edge count overflow");
-
-  gnb_graph* g = new gnb_graph();
-  g->device = ctx->device;
-  g->B = B; g->PN = PN; g->E = E; g->N = N;
+// one stream-ordered allocation backing every index array of the graph (B, E, N set by the caller)
+int graph_alloc(gnb_ctx* ctx, gnb_graph* g) {
+  const int64_t E = g->E, N = g->N;
+  const int B = g->B;
   size_t off = 0;
   auto take = [&](size_t n) { size_t o = off; off += align_up(n * sizeof(int32_t)); return o; };
   size_t o_src = take(E), o_dst = take(E), o_slot = take(E), o_eg = take(E), o_ng = take(N);
@@ -330,8 +289,8 @@ extern "C" int gnb_graph_lower(gnb_ctx* ctx, const void* adj, int adj_dtype, int
   g->stream = ctx->stream;
   cudaError_t ce = cudaMallocAsync(&g->all, off ? off : 256, ctx->stream);
   if (ce != cudaSuccess) {
+    gnb_set_error("graph lowering: cudaMalloc(%zu) failed: %s", off, cudaGetErrorString(ce));
     delete g;
-    gnb_set_error("gnb_graph_lower: cudaMalloc(%zu) failed: %s", off, cudaGetErrorString(ce));
     return GNB_ERR_OOM;
   }
   char* base = (char*)g->all;
@@ -342,11 +301,16 @@ extern "C" int gnb_graph_lower(gnb_ctx* ctx, const void* adj, int adj_dtype, int
   g->edge_part = (int32_t*)(base + o_ep); g->node_part_ptr = (int32_t*)(base + o_npp);
   g->graph_part_ptr = (int32_t*)(base + o_gpp);
   g->node_gpart = (int32_t*)(base + o_ngp); g->graph_npart_ptr = (int32_t*)(base + o_gnpp);
+  return GNB_OK;
+}
+
+// sentinels + the partial-row indexes of the tensor path; expects edge_dst, node_in_ptr[0..N), node_graph, graph_node_ptr and
+// graph_edge_ptr[0..B) on the device.  Synchronises the stream.
+int graph_finish(gnb_ctx* ctx, gnb_graph* g) {
+  const int64_t E = g->E, N = g->N;
+  const int B = g->B;
   int ret = GNB_OK;
   do {
-    if (cudaMemcpyAsync(g->graph_node_ptr, gnp.data(), sizeof(int32_t) * (B + 1), cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) { ret = GNB_ERR_CUDA; break; }
-    // nodes beyond the last column with edges / isolated columns all get a pointer: fill by kernel
-    if ((ret = DISPATCH(1, g)) != GNB_OK) break;
     // sentinels: graph_edge_ptr[B] = E, node_in_ptr[N] = E
     k_fill_const<<<1, 32, 0, ctx->stream>>>(g->graph_edge_ptr + B, 1, (int32_t)E);
     k_fill_const<<<1, 32, 0, ctx->stream>>>(g->node_in_ptr + N, 1, (int32_t)E);
@@ -396,9 +360,189 @@ extern "C" int gnb_graph_lower(gnb_ctx* ctx, const void* adj, int adj_dtype, int
     }
     cudaError_t e2 = cudaStreamSynchronize(ctx->stream);
     if (e2 == cudaSuccess) e2 = cudaGetLastError();
-    if (e2 != cudaSuccess) { gnb_set_error("gnb_graph_lower: %s", cudaGetErrorString(e2)); ret = GNB_ERR_CUDA; }
+    if (e2 != cudaSuccess) { gnb_set_error("graph lowering: %s", cudaGetErrorString(e2)); ret = GNB_ERR_CUDA; }
+  } while (0);
+  return ret;
+}
+
+}  // namespace
+
+extern "C" int gnb_graph_lower(gnb_ctx* ctx, const void* adj, int adj_dtype, int adj_on_device,
+                               const int32_t* n_nodes, int PN, int Badj, int B, gnb_graph** out) {
+  GNB_CHECK(ctx && adj && n_nodes && out, "gnb_graph_lower: null argument");
+  GNB_CHECK(B > 0 && PN > 0, "gnb_graph_lower: need B > 0 and PN > 0 (length(adj_mats) > 0, src/checks.jl:8)");
+  GNB_CHECK(Badj == 1 || Badj == B, "gnb_graph_lower: Badj must be 1 or B");
+  GNB_CHECK(adj_dtype == GNB_ADJ_F32 || adj_dtype == GNB_ADJ_U8 || adj_dtype == GNB_ADJ_I32 || adj_dtype == GNB_ADJ_BITS,
+            "gnb_graph_lower: bad adj_dtype");
+  GNB_CHECK((int64_t)B * PN * PN < ((int64_t)1 << 31), "gnb_graph_lower: B*PN^2 exceeds int32 slot range");
+  int64_t N = 0;
+  std::vector<int32_t> gnp(B + 1, 0);
+  for (int b = 0; b < B; b++) {
+    int n = n_nodes[Badj == 1 ? 0 : b];
+    GNB_CHECK(n >= 0 && n <= PN, "gnb_graph_lower: n_nodes[%d]=%d outside [0, PN=%d]", b, n, PN);
+    N += n;
+    gnp[b + 1] = (int32_t)N;
+  }
+  GNB_CHECK(N < ((int64_t)1 << 31), "gnb_graph_lower: too many nodes");
+  GNB_CUDA(cudaSetDevice(ctx->device));
+  size_t esz = adj_dtype == GNB_ADJ_U8 ? 1 : 4;
+  size_t adj_bytes = adj_dtype == GNB_ADJ_BITS ? (size_t)Badj * (((size_t)PN * PN + 31) / 32) * 4 : (size_t)Badj * PN * PN * esz;
+  // temporaries out of the scratch arena
+  ctx->arena.reset();
+  int rc = GNB_OK;
+  int64_t total_cols = (int64_t)B * PN;
+  int32_t* nn_dev = arena_ptr<int32_t>(ctx->arena, Badj, &rc);
+  int32_t* colcount = arena_ptr<int32_t>(ctx->arena, total_cols, &rc);
+  int32_t* coloff = arena_ptr<int32_t>(ctx->arena, total_cols + 1, &rc);
+  int32_t* sums = arena_ptr<int32_t>(ctx->arena, ceil_div(total_cols, SCAN_ITEMS) + 2, &rc);
+  const void* adj_dev = adj;
+  if (!adj_on_device) {
+    void* tmp = nullptr;
+    int r2 = ctx->arena.alloc(adj_bytes, &tmp);
+    if (r2 != GNB_OK) rc = r2;
+    adj_dev = tmp;
+  }
+  if (rc != GNB_OK) return rc;
+  if (!adj_on_device) GNB_CUDA(cudaMemcpyAsync((void*)adj_dev, adj, adj_bytes, cudaMemcpyHostToDevice, ctx->stream));
+  GNB_CUDA(cudaMemcpyAsync(nn_dev, n_nodes, sizeof(int32_t) * Badj, cudaMemcpyHostToDevice, ctx->stream));
+
+  gnb_graph tmpg;
+#define DISPATCH(phase, gp)                                                                              \
+  (adj_dtype == GNB_ADJ_F32 ? lower_typed<float>(ctx, (const float*)adj_dev, nn_dev, PN, Badj, B, colcount, coloff, sums, gp, phase) \
+   : adj_dtype == GNB_ADJ_U8 ? lower_typed<uint8_t>(ctx, (const uint8_t*)adj_dev, nn_dev, PN, Badj, B, colcount, coloff, sums, gp, phase) \
+   : adj_dtype == GNB_ADJ_BITS ? lower_typed<BitAdj>(ctx, (const BitAdj*)adj_dev, nn_dev, PN, Badj, B, colcount, coloff, sums, gp, phase) \
+                             : lower_typed<int32_t>(ctx, (const int32_t*)adj_dev, nn_dev, PN, Badj, B, colcount, coloff, sums, gp, phase))
+  GNB_TRY(DISPATCH(0, &tmpg));
+  int32_t E32 = 0;
+  GNB_CUDA(cudaMemcpyAsync(&E32, coloff + total_cols, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+  GNB_CUDA(cudaStreamSynchronize(ctx->stream));
+  int64_t E = E32;
+  GNB_CHECK(E >= 0, "gnb_graph_lower: edge count overflow");
+
+  gnb_graph* g = new gnb_graph();
+  g->device = ctx->device;
+  g->B = B; g->PN = PN; g->E = E; g->N = N;
+  GNB_TRY(graph_alloc(ctx, g));
+  int ret = GNB_OK;
+  do {
+    if (cudaMemcpyAsync(g->graph_node_ptr, gnp.data(), sizeof(int32_t) * (B + 1), cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) { ret = GNB_ERR_CUDA; break; }
+    // nodes beyond the last column with edges / isolated columns all get a pointer: fill by kernel
+    if ((ret = DISPATCH(1, g)) != GNB_OK) break;
+    ret = graph_finish(ctx, g);
   } while (0);
 #undef DISPATCH
+  if (ret != GNB_OK) {
+    cudaFreeAsync(g->all, ctx->stream);
+    delete g;
+    return ret;
+  }
+  *out = g;
+  return GNB_OK;
+}
+
+// ---- lowering from COO edge lists (src/batch.jl:53-64 + src/pad.jl:26-46 without the dense detour) ---------------------
+namespace {
+// first index in [0, n) with a[idx] > v  (a ascending)
+__device__ __forceinline__ int upper_bound_i32(const int32_t* __restrict__ a, int n, int v) {
+  int lo = 0, hi = n;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (a[mid] <= v) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+__global__ void k_coo_fill(const int32_t* __restrict__ src, const int32_t* __restrict__ dst, const int32_t* __restrict__ gep,
+                           const int32_t* __restrict__ gnp, int B, int PN, int64_t E, int32_t* __restrict__ edge_src,
+                           int32_t* __restrict__ edge_dst, int32_t* __restrict__ edge_slot, int32_t* __restrict__ edge_graph,
+                           int* __restrict__ err) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= E) return;
+  const int b = upper_bound_i32(gep, B + 1, (int)e) - 1;      // gep[b] <= e < gep[b+1]
+  const int n = gnp[b + 1] - gnp[b];
+  const int i = src[e], j = dst[e];
+  bool ok = i >= 0 && i < n && j >= 0 && j < n;
+  if (ok && e > gep[b]) {
+    // ascending padded slot i + PN*j inside a graph == the reference's findall(isone, adj[:]) order; strict: no duplicates
+    const int64_t prev = (int64_t)src[e - 1] + (int64_t)PN * dst[e - 1];
+    ok = (int64_t)i + (int64_t)PN * j > prev;
+  }
+  if (!ok) { atomicOr(err, 1); return; }      // error reporting only: not on the data path
+  edge_src[e] = gnp[b] + i;
+  edge_dst[e] = gnp[b] + j;
+  edge_slot[e] = i + PN * j;
+  edge_graph[e] = b;
+}
+// node_in_ptr[v] = first edge whose receiver is >= v (receivers ascend globally); node_graph[v]
+__global__ void k_coo_nodes(const int32_t* __restrict__ edge_dst, int64_t E, const int32_t* __restrict__ gnp, int B, int64_t N,
+                            int32_t* __restrict__ node_in_ptr, int32_t* __restrict__ node_graph) {
+  const int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (v > N) return;
+  node_in_ptr[v] = v == 0 ? 0 : upper_bound_i32(edge_dst, (int)E, (int)v - 1);
+  if (v < N) node_graph[v] = upper_bound_i32(gnp, B + 1, (int)v) - 1;
+}
+}  // namespace
+
+extern "C" int gnb_graph_from_coo(gnb_ctx* ctx, const int32_t* src, const int32_t* dst, int coo_on_device,
+                                  const int32_t* graph_edge_ptr, const int32_t* n_nodes, int PN, int B, gnb_graph** out) {
+  GNB_CHECK(ctx && graph_edge_ptr && n_nodes && out, "gnb_graph_from_coo: null argument");
+  GNB_CHECK(B > 0, "gnb_graph_from_coo: need B > 0 (length(adj_mats) > 0, src/checks.jl:8)");
+  GNB_CHECK(graph_edge_ptr[0] == 0, "gnb_graph_from_coo: graph_edge_ptr[0] must be 0");
+  int64_t N = 0;
+  int maxn = 0;
+  std::vector<int32_t> gnp(B + 1, 0);
+  for (int b = 0; b < B; b++) {
+    GNB_CHECK(n_nodes[b] >= 0, "gnb_graph_from_coo: n_nodes[%d] < 0", b);
+    GNB_CHECK(graph_edge_ptr[b + 1] >= graph_edge_ptr[b], "gnb_graph_from_coo: graph_edge_ptr must ascend");
+    maxn = n_nodes[b] > maxn ? n_nodes[b] : maxn;
+    N += n_nodes[b];
+    gnp[b + 1] = (int32_t)N;
+  }
+  if (PN <= 0) PN = maxn > 0 ? maxn : 1;      // padadjmats: common size = largest graph (src/pad.jl:3)
+  GNB_CHECK(PN >= maxn, "gnb_graph_from_coo: PN=%d smaller than the largest graph (%d nodes)", PN, maxn);
+  GNB_CHECK(N < ((int64_t)1 << 31) && (int64_t)B * PN * PN < ((int64_t)1 << 31), "gnb_graph_from_coo: index range exceeds int32");
+  const int64_t E = graph_edge_ptr[B];
+  GNB_CHECK(E == 0 || (src && dst), "gnb_graph_from_coo: null edge list");
+  GNB_CUDA(cudaSetDevice(ctx->device));
+  ctx->arena.reset();
+  int rc = GNB_OK;
+  const int32_t *d_src = src, *d_dst = dst;
+  if (!coo_on_device && E > 0) {
+    int32_t* t0 = arena_ptr<int32_t>(ctx->arena, E, &rc);
+    int32_t* t1 = arena_ptr<int32_t>(ctx->arena, E, &rc);
+    if (rc != GNB_OK) return rc;
+    GNB_CUDA(cudaMemcpyAsync(t0, src, sizeof(int32_t) * E, cudaMemcpyHostToDevice, ctx->stream));
+    GNB_CUDA(cudaMemcpyAsync(t1, dst, sizeof(int32_t) * E, cudaMemcpyHostToDevice, ctx->stream));
+    d_src = t0; d_dst = t1;
+  }
+  int* d_err = arena_ptr<int>(ctx->arena, 1, &rc);
+  if (rc != GNB_OK) return rc;
+  gnb_graph* g = new gnb_graph();
+  g->device = ctx->device;
+  g->B = B; g->PN = PN; g->E = E; g->N = N;
+  GNB_TRY(graph_alloc(ctx, g));
+  int ret = GNB_OK;
+  int h_err = 0;
+  do {
+    if (cudaMemsetAsync(d_err, 0, sizeof(int), ctx->stream) != cudaSuccess ||
+        cudaMemcpyAsync(g->graph_node_ptr, gnp.data(), sizeof(int32_t) * (B + 1), cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess ||
+        cudaMemcpyAsync(g->graph_edge_ptr, graph_edge_ptr, sizeof(int32_t) * (B + 1), cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) { ret = GNB_ERR_CUDA; break; }
+    if (E > 0) {
+      k_coo_fill<<<ceil_div(E, 256), 256, 0, ctx->stream>>>(d_src, d_dst, g->graph_edge_ptr, g->graph_node_ptr, B, PN, E, g->edge_src,
+                                                            g->edge_dst, g->edge_slot, g->edge_graph, d_err);
+      ctx->launches++;
+    }
+    if (cudaMemcpyAsync(&h_err, d_err, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess ||
+        cudaStreamSynchronize(ctx->stream) != cudaSuccess) { ret = GNB_ERR_CUDA; break; }
+    if (h_err) {
+      gnb_set_error("gnb_graph_from_coo: every graph's edges must have 0 <= src, dst < n_nodes and be strictly ascending in the "
+                    "padded slot src + PN*dst (receiver-major, the order of findall(isone, adj[:]), src/pad.jl:30)");
+      ret = GNB_ERR_INVALID;
+      break;
+    }
+    k_coo_nodes<<<ceil_div(N + 1, 256), 256, 0, ctx->stream>>>(g->edge_dst, E, g->graph_node_ptr, B, N, g->node_in_ptr, g->node_graph);
+    ctx->launches++;
+    ret = graph_finish(ctx, g);
+  } while (0);
   if (ret != GNB_OK) {
     cudaFreeAsync(g->all, ctx->stream);
     delete g;

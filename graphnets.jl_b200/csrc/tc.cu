@@ -28,19 +28,14 @@ using namespace tcx;
 namespace {
 
 // =====================================================================================================
-// Projection kernel: out = A . W for 1 or 2 weight blocks (N = 128 or 256), fp32 out.
-//   SRC_LN : A = LayerNorm-normalised rows of x (affine folded into W)   -> P_s | P_r of the nodes
-//   SRC_AGG: A = ordered sum of the partial rows [part_ptr[r], part_ptr[r+1]) of x (part_ptr == nullptr: row r
-//            itself); `addend` (optional, [R][H]) is added to the single-block output
-// 6 warps: 0-3 prologue/epilogue, 4 MMA issuer, 5 weight loader.  One 128-row tile per iteration.
+// Projection kernel: out = A . W for NBLK weight blocks (N = 128 NBLK), fp32 out; A = LayerNorm-normalised rows of x (affine
+// folded into W) -> P_s | P_r of the nodes.  `addend` (optional) is added to one 128-column block of the output.
+// 10 warps: 0-3 drain, 4-7 A-operand producers, 8 MMA issuer, 9 weight loader.  One 128-row tile per iteration.
 // =====================================================================================================
-enum { SRC_LN = 0, SRC_AGG = 1 };
+enum { SRC_LN = 0 };
 
 struct ProjArgs {
-  const float* x;                 // SRC_LN: [R][H];  SRC_AGG: partial rows [n_parts][H]
-  const int32_t* part_ptr;        // SRC_AGG: [R+1] or nullptr
-  const float* x2;                // SRC_AGG (optional): second partial-row array summed with the same segments ...
-  float* sum2;                    // ... into sum2 [R][H] (fp32); pass sum2 as `addend` to add it to the output
+  const float* x;                 // [R][H]
   const float* addend;            // optional [*][H], added to output columns [add_col0, add_col0 + H)
   const int32_t* addend_idx;      // row of `addend` per output row (nullptr: the row itself)
   int add_col0;
@@ -66,7 +61,7 @@ __host__ __device__ constexpr int pj_smem(int nblk) { return pj_off_misc(nblk) +
 //   ASEEN[st]   MMA warp (after it saw AFULL) -> drain warps  next phase needs ACCFREE[st] <- drain warps after they saw ASEEN
 //   OUTDONE[st] MMA commit -> drain warps                     next phase needs ACCFREE[st] <- drain warps after they saw OUTDONE
 //   ACCFREE[st] drain warps (128 arrivals) -> MMA warp        next phase needs OUTDONE[st] <- MMA warp after it saw ACCFREE
-// Round 1 let the drain warps wait on AFULL directly (they need the producers' sum2 rows): they are NOT in AFULL's loop -
+// Round 1 let the drain warps wait on AFULL directly (their addends could come from the producers): they are NOT in AFULL's loop -
 // the producers only need the MMA warp to refill a stage - so a drain warp delayed by more than one tile found AFULL two
 // phases ahead, read the aliased parity as "not yet complete" and waited forever (the dead-lock of the two-context mode,
 // reproduced with GNB_DEBUG_PROJ_DRAIN_DELAY_NS under -DGNB_OLD_PROJ_PROTOCOL, tests/test_gpu_watchdog.py).
@@ -124,7 +119,7 @@ __global__ void __launch_bounds__(PJ_THREADS, NBLK == 1 ? 2 : 1) k_tc_proj(const
       mbar_wait(BAR(PB_AFULL + st), ph);
       mbar_wait(BAR(PB_ACCFREE + st), ph ^ 1);
       tc_fence_after();
-      if (lane == 0) mbar_arrive(BAR(PB_ASEEN + st));      // release: forwards the producers' sum2 rows to the drain warps
+      if (lane == 0) mbar_arrive(BAR(PB_ASEEN + st));      // release: forwards whatever the producers published to the drain warps
       __syncwarp();
       if (elect_one()) {
         const uint64_t adesc = umma_desc(base + st * BLK_BYTES);
@@ -147,7 +142,7 @@ __global__ void __launch_bounds__(PJ_THREADS, NBLK == 1 ? 2 : 1) k_tc_proj(const
       const int64_t left = a.R - row0;
       const int wrows = left < 0 ? 0 : (left > 32 ? 32 : (int)left);
       uint8_t* A = sm + st * BLK_BYTES;
-      if (SRC == SRC_LN) {
+      {
         // 8 lanes per row (tc_edge.cu LN warps): 4 rows x 128 B per load instruction, 3 shuffle levels per statistic
         const int rr = lane >> 3, l8 = lane & 7;
         const float* xbase = a.x + 4 * l8;
@@ -211,73 +206,9 @@ __global__ void __launch_bounds__(PJ_THREADS, NBLK == 1 ? 2 : 1) k_tc_proj(const
             }
           }
         }
-      } else {
-        // partial rows of consecutive output rows are consecutive in memory (parts are numbered in edge order,
-        // edges are receiver-sorted): up to 2 partial rows per output row are fetched unconditionally, 4 output
-        // rows (8-16 loads) in flight; longer segments (a receiver spread over > 2 32-edge blocks) loop.
-        int p0 = 0, p1 = 0;
-        if (lane < wrows) {
-          const int64_t r = row0 + lane;
-          if (a.part_ptr) { p0 = __ldg(a.part_ptr + r); p1 = __ldg(a.part_ptr + r + 1); }
-          else { p0 = (int)r; p1 = (int)r + 1; }
-        }
-        const float4* X = reinterpret_cast<const float4*>(a.x) + lane;
-        const float4* X2 = reinterpret_cast<const float4*>(a.x2) + lane;
-        mbar_wait(BAR(PB_AEMPTY + st), ph ^ 1);
-        if (a.part_ptr == nullptr) {
-          // plain rows: 8 coalesced row loads in flight
-#pragma unroll 1
-          for (int i0 = 0; i0 < 32; i0 += 8) {
-            float4 v[8];
-#pragma unroll
-            for (int u = 0; u < 8; u++) {
-              int64_t r = row0 + i0 + u;
-              r = r < a.R ? r : a.R - 1;
-              v[u] = __ldg(X + (size_t)r * (H / 4));
-            }
-#pragma unroll
-            for (int u = 0; u < 8; u++) {
-              const bool ok = i0 + u < wrows;
-              uint2 pk;
-              pk.x = ok ? pack_bf16(v[u].x, v[u].y) : 0u;
-              pk.y = ok ? pack_bf16(v[u].z, v[u].w) : 0u;
-              *reinterpret_cast<uint2*>(A + sw_off(q * 32 + i0 + u, 4 * lane)) = pk;
-            }
-          }
-        } else
-#pragma unroll 1
-        for (int i0 = 0; i0 < 32; i0 += 4) {
-          float4 s[4], t[4], s2[4], t2[4];
-          int q0[4], q1[4];
-#pragma unroll
-          for (int u = 0; u < 4; u++) {
-            q0[u] = __shfl_sync(0xffffffffu, p0, i0 + u);
-            q1[u] = __shfl_sync(0xffffffffu, p1, i0 + u);
-            s[u] = (q0[u] < q1[u]) ? __ldg(X + (size_t)q0[u] * (H / 4)) : f4zero();
-            t[u] = (q0[u] + 1 < q1[u]) ? __ldg(X + (size_t)(q0[u] + 1) * (H / 4)) : f4zero();
-            if (a.x2) {
-              s2[u] = (q0[u] < q1[u]) ? __ldg(X2 + (size_t)q0[u] * (H / 4)) : f4zero();
-              t2[u] = (q0[u] + 1 < q1[u]) ? __ldg(X2 + (size_t)(q0[u] + 1) * (H / 4)) : f4zero();
-            }
-          }
-#pragma unroll
-          for (int u = 0; u < 4; u++) {
-            s[u] = f4add(s[u], t[u]);
-            for (int p = q0[u] + 2; p < q1[u]; p++) s[u] = f4add(s[u], __ldg(X + (size_t)p * (H / 4)));
-            uint2 pk;
-            pk.x = pack_bf16(s[u].x, s[u].y);
-            pk.y = pack_bf16(s[u].z, s[u].w);
-            *reinterpret_cast<uint2*>(A + sw_off(q * 32 + i0 + u, 4 * lane)) = pk;
-            if (a.x2) {
-              s2[u] = f4add(s2[u], t2[u]);
-              for (int p = q0[u] + 2; p < q1[u]; p++) s2[u] = f4add(s2[u], __ldg(X2 + (size_t)p * (H / 4)));
-              if (i0 + u < wrows) *(reinterpret_cast<float4*>(a.sum2 + (size_t)(row0 + i0 + u) * H) + lane) = s2[u];
-            }
-          }
-        }
       }
       fence_async_smem();
-      mbar_arrive(BAR(PB_AFULL + st));   // release: also publishes the sum2 rows to the drain warps
+      mbar_arrive(BAR(PB_AFULL + st));
     }
   } else {
     // ===================================================== accumulator drain (TMEM lane quadrant = warp), fragment layout:
@@ -291,7 +222,7 @@ __global__ void __launch_bounds__(PJ_THREADS, NBLK == 1 ? 2 : 1) k_tc_proj(const
       const int64_t row0 = (int64_t)tile * TM;
       const int rows = (int)((a.R - row0) < TM ? (a.R - row0) : TM);
       if (a.dbg_drain_delay_ns) __nanosleep(a.dbg_drain_delay_ns);      // test hook
-      // addends may be produced by this tile's A-operand warps (sum2): they are complete once the A tile is
+      // the drain warps may prefetch their addends once the A tile is complete
 #ifdef GNB_OLD_PROJ_PROTOCOL
       mbar_wait(BAR(PB_AFULL + st), ph);      // round-1 protocol, kept only to reproduce its dead-lock
 #else
@@ -349,6 +280,214 @@ __global__ void __launch_bounds__(PJ_THREADS, NBLK == 1 ? 2 : 1) k_tc_proj(const
 #undef mbar_wait
 }
 
+// =====================================================================================================
+// Node aggregate + its projection in one pass (replaces round 1's tc_agg + tc_agg_proj launches):
+//   P_agg[v] = W_na agg_v,   agg_v = W_ee' (sum_{e->v} ê_e) + sum_{e->v} (P_s[src] + P_r'[dst])          (src/nodefninput.jl:3)
+//            = (sum ê) F + (sum G) W_na            F = W_ee' W_na folded (fp32) when the model is packed
+// A = [ bf16(sum of the node's E_part rows) | bf16(sum of its G_part rows) ]  (K = 256), one 128 x 128 accumulator.
+// agg itself is never materialised: the graph update only needs sum_v agg_v, which by linearity is
+// (sum_v sum ê) W_ee' + sum_v sum G - so the producers also emit the ordered sums of both operands per (16-node block,
+// graph) run (SE_part, SG_part; index node_gpart) and k_graph_post finishes them in fp32.
+// 14 warps: 0-3 drain, 4-11 producers (16 rows each = one cut of node_gpart), 12 MMA issuer, 13 weight loader.
+// Barriers as k_tc_proj (no ASEEN: the drain warps read nothing the producers write).
+// =====================================================================================================
+struct Agg2Args {
+  const float* Epart;             // [n_parts][H]
+  const float* Gpart;             // [n_parts][H]
+  const int32_t* part_ptr;        // [R+1] node -> its partial rows [part_ptr[v], part_ptr[v+1])
+  const int32_t* gpart;           // [R]   node -> (16-node block, graph) run id (gnb_graph::node_gpart)
+  float* SEpart;                  // out [n_nparts][H]
+  float* SGpart;                  // out [n_nparts][H]
+  float* out;                     // out [R][H]  P_agg
+  int64_t R;
+  int num_tiles;
+  const __nv_bfloat16* wpack;     // 2 blocks: F, W_na
+  WatchArgs wd;
+};
+constexpr int AG_THREADS = 14 * 32;
+constexpr int AG_STAGE = 2 * BLK_BYTES;                      // A0 | A1
+constexpr int AG_OFF_W = 2 * AG_STAGE;
+constexpr int AG_OFF_MISC = AG_OFF_W + 2 * BLK_BYTES;
+constexpr int AG_SMEM = AG_OFF_MISC + 256 + 1024;
+enum { AB_WFULL = 0, AB_AFULL = 1, AB_AEMPTY = 3, AB_OUTDONE = 5, AB_ACCFREE = 7 };
+
+__global__ void __launch_bounds__(AG_THREADS, 1) k_tc_agg2(const Agg2Args a) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* sm = smem_raw + (base - raw);
+  const uint32_t sW = base + AG_OFF_W;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sm + AG_OFF_MISC);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+  const uint32_t bar0 = smem_u32(bars);
+  auto BAR = [&](int i) { return bar0 + 8u * (uint32_t)i; };
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  bool wd_dead = false;      // kernel watchdog (tc_ptx.cuh)
+#define mbar_wait(b, p) mbar_wait_w((b), (p), wd_dead, a.wd)
+  if (tid == 0) {
+    mbar_init(BAR(AB_WFULL), 1);
+    for (int s = 0; s < 2; s++) {
+      mbar_init(BAR(AB_AFULL + s), 8); mbar_init(BAR(AB_AEMPTY + s), 1);
+      mbar_init(BAR(AB_OUTDONE + s), 1); mbar_init(BAR(AB_ACCFREE + s), 4);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 12) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(256u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 13) {
+    if (elect_one()) {
+      mbar_expect_tx(BAR(AB_WFULL), 2 * BLK_BYTES);
+      bulk_g2s(sW, a.wpack, BLK_BYTES, BAR(AB_WFULL));
+      bulk_g2s(sW + BLK_BYTES, reinterpret_cast<const uint8_t*>(a.wpack) + BLK_BYTES, BLK_BYTES, BAR(AB_WFULL));
+    }
+    __syncwarp();
+  } else if (warp == 12) {
+    uint32_t tl = 0;
+    mbar_wait(BAR(AB_WFULL), 0);
+    const uint64_t w0 = umma_desc(sW), w1 = umma_desc(sW + BLK_BYTES);
+    for (int tile = blockIdx.x; tile < a.num_tiles && !wd_dead; tile += gridDim.x, tl++) {
+      const uint32_t st = tl & 1, ph = (tl >> 1) & 1;
+      mbar_wait(BAR(AB_AFULL + st), ph);
+      mbar_wait(BAR(AB_ACCFREE + st), ph ^ 1);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint64_t a0 = umma_desc(base + st * AG_STAGE), a1 = umma_desc(base + st * AG_STAGE + BLK_BYTES);
+        issue_ss(tmem + st * 128, a0, w0, w0 + (KB_BYTES >> 4), false);
+        issue_ss(tmem + st * 128, a1, w1, w1 + (KB_BYTES >> 4), true);
+        tc_commit(BAR(AB_AEMPTY + st));
+        tc_commit(BAR(AB_OUTDONE + st));
+      }
+      __syncwarp();
+    }
+  } else if (warp >= 4) {
+    // ===================================================== producers: warp pw owns rows 16 pw .. 16 pw + 15 of the tile
+    const int pw = warp - 4;
+    const float4* XE = reinterpret_cast<const float4*>(a.Epart) + lane;
+    const float4* XG = reinterpret_cast<const float4*>(a.Gpart) + lane;
+    uint32_t tl = 0;
+    for (int tile = blockIdx.x; tile < a.num_tiles && !wd_dead; tile += gridDim.x, tl++) {
+      const uint32_t st = tl & 1, ph = (tl >> 1) & 1;
+      const int64_t row0 = (int64_t)tile * TM + 16 * pw;
+      const int64_t left = a.R - row0;
+      const int rows = left < 0 ? 0 : (left > 16 ? 16 : (int)left);
+      int p0 = 0, p1 = 0, my_gp = -1;
+      if (lane < rows) {
+        p0 = __ldg(a.part_ptr + row0 + lane);
+        p1 = __ldg(a.part_ptr + row0 + lane + 1);
+        my_gp = __ldg(a.gpart + row0 + lane);
+      }
+      const int nxt = __shfl_down_sync(0xffffffffu, my_gp, 1);
+      const uint32_t endmask = __ballot_sync(0xffffffffu, lane < rows && (lane == rows - 1 || nxt != my_gp));
+      int gp = __shfl_sync(0xffffffffu, my_gp, 0);
+      uint8_t* A0 = sm + st * AG_STAGE;
+      uint8_t* A1 = A0 + BLK_BYTES;
+      float4 accE = f4zero(), accG = f4zero();
+      mbar_wait(BAR(AB_AEMPTY + st), ph ^ 1);
+#pragma unroll 1
+      for (int i0 = 0; i0 < 16; i0 += 4) {
+        // partial rows of consecutive nodes are consecutive in memory (parts are numbered in edge order, edges are
+        // receiver-sorted): up to 2 partial rows per node are fetched unconditionally, 4 nodes (16 loads) in flight
+        float4 s[4], t[4], s2[4], t2[4];
+        int q0[4], q1[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+          q0[u] = __shfl_sync(0xffffffffu, p0, i0 + u);
+          q1[u] = __shfl_sync(0xffffffffu, p1, i0 + u);
+          const bool h0 = q0[u] < q1[u], h1 = q0[u] + 1 < q1[u];
+          s[u] = h0 ? __ldg(XE + (size_t)q0[u] * (H / 4)) : f4zero();
+          t[u] = h1 ? __ldg(XE + (size_t)(q0[u] + 1) * (H / 4)) : f4zero();
+          s2[u] = h0 ? __ldg(XG + (size_t)q0[u] * (H / 4)) : f4zero();
+          t2[u] = h1 ? __ldg(XG + (size_t)(q0[u] + 1) * (H / 4)) : f4zero();
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+          const int i = i0 + u;
+          s[u] = f4add(s[u], t[u]);
+          s2[u] = f4add(s2[u], t2[u]);
+          for (int p = q0[u] + 2; p < q1[u]; p++) {
+            s[u] = f4add(s[u], __ldg(XE + (size_t)p * (H / 4)));
+            s2[u] = f4add(s2[u], __ldg(XG + (size_t)p * (H / 4)));
+          }
+          uint2 pk;
+          pk.x = pack_bf16(s[u].x, s[u].y); pk.y = pack_bf16(s[u].z, s[u].w);
+          *reinterpret_cast<uint2*>(A0 + sw_off(16 * pw + i, 4 * lane)) = pk;      // rows past the end are zero (no parts)
+          pk.x = pack_bf16(s2[u].x, s2[u].y); pk.y = pack_bf16(s2[u].z, s2[u].w);
+          *reinterpret_cast<uint2*>(A1 + sw_off(16 * pw + i, 4 * lane)) = pk;
+          // ordered sums per (16-node block, graph) run, in fp32
+          accE = f4add(accE, s[u]);
+          accG = f4add(accG, s2[u]);
+          const bool fl = (endmask >> i) & 1u;      // warp-uniform
+          if (fl) {
+            *(reinterpret_cast<float4*>(a.SEpart + (size_t)gp * H) + lane) = accE;
+            *(reinterpret_cast<float4*>(a.SGpart + (size_t)gp * H) + lane) = accG;
+            accE = f4zero(); accG = f4zero();
+            gp++;
+          }
+        }
+      }
+      fence_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(BAR(AB_AFULL + st));
+    }
+  } else {
+    // ===================================================== accumulator drain (TMEM lane quadrant = warp), fragment layout:
+    // every 4 lanes write one full 32 B sector
+    const uint32_t lane_base = ((uint32_t)(warp * 32)) << 16;
+    const int q = lane >> 2, cq = 2 * (lane & 3);
+    uint32_t tl = 0;
+    for (int tile = blockIdx.x; tile < a.num_tiles && !wd_dead; tile += gridDim.x, tl++) {
+      const uint32_t st = tl & 1, ph = (tl >> 1) & 1;
+      const int64_t row0 = (int64_t)tile * TM;
+      const int rows = (int)((a.R - row0) < TM ? (a.R - row0) : TM);
+      mbar_wait(BAR(AB_OUTDONE + st), ph);
+      tc_fence_after();
+#pragma unroll 1
+      for (int stp = 0; stp < 4; stp++) {
+        const int hh = stp & 1, ch = stp >> 1;
+        uint32_t d[32];
+        TC_LD_FRAG64(tmem + st * 128 + lane_base + ((uint32_t)(16 * hh) << 16) + 64 * ch, d);
+        tc_wait_ld();
+        if (stp == 3) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(BAR(AB_ACCFREE + st));
+        }
+#pragma unroll
+        for (int h2 = 0; h2 < 2; h2++) {
+          const int r = warp * 32 + 16 * hh + q + 8 * h2;
+          if (r < rows) {
+            float* o = a.out + (size_t)(row0 + r) * H + 64 * ch + cq;
+#pragma unroll
+            for (int n = 0; n < 8; n++)
+              *reinterpret_cast<float2*>(o + 8 * n) = make_float2(__uint_as_float(d[4 * n + 2 * h2]), __uint_as_float(d[4 * n + 2 * h2 + 1]));
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 12) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(256u) : "memory");
+#undef mbar_wait
+}
+
+// F[k][n] = gamma[k] * sum_j A[k][j] * B[j][n]     (A = rows [0,H) of the edge Dense, B = rows [0,H) of the node Dense; all
+// k-major H x H fp32): the fold of W_ee' W_na
+__global__ void k_fold_matmul(const float* __restrict__ A, const float* __restrict__ B, const float* __restrict__ gamma,
+                              float* __restrict__ F) {
+  const int k = blockIdx.x, n = threadIdx.x;      // H x H
+  float s = 0.f;
+  for (int j = 0; j < H; j++) s = fmaf(A[(size_t)k * H + j], B[(size_t)j * H + n], s);
+  F[(size_t)k * H + n] = s * gamma[k];
+}
+
 // ------------------------------------------------------------------ weight packing
 // dst block (bf16, swizzled smem image): B[n][k] = W[(n0+n) + ldw*(k0+k)] * (gamma ? gamma[k] : 1)
 __global__ void k_pack_block(const float* __restrict__ W, int ldw, int n0, int k0, const float* __restrict__ gamma,
@@ -388,9 +527,9 @@ extern "C" int gnb_debug_tc_timing(unsigned long long* out, int n) {
 }
 
 struct TcCorePack {
-  __nv_bfloat16* w = nullptr;   // [proj 2 | aggproj 1 | edge 9 | node 9] blocks of 32 KB
+  __nv_bfloat16* w = nullptr;   // [proj 2 | agg2: F, W_na | edge 9 | node 9] blocks of 32 KB
   float* f = nullptr;           // folded fp32 vectors: cu_e[128] cu_n[128] b1f_e[512] b1f_n[512]
-  const __nv_bfloat16 *w_proj, *w_agg, *w_edge, *w_node, *w_eblk;
+  const __nv_bfloat16 *w_proj, *w_agg, *w_edge, *w_node;
   float *cu_e, *cu_n, *b1f_e, *b1f_n;
 };
 
@@ -411,7 +550,7 @@ int tc_core_pack(gnb_ctx* ctx, const gnb_block_params& blk, const gnb_ffn_params
   for (int i = 0; i < 2; i++)
     if (ln1[i].eps != ln2[i].eps || ln1[i].eps_mode != ln2[i].eps_mode) return GNB_OK;
   TcCorePack* p = new TcCorePack();
-  const size_t nblk = 2 + 1 + 9 + 9;
+  const size_t nblk = 2 + 2 + 9 + 9;
   if (cudaMalloc((void**)&p->w, nblk * BLK_BYTES) != cudaSuccess ||
       cudaMalloc((void**)&p->f, (128 + 128 + 512 + 512) * sizeof(float)) != cudaSuccess) {
     cudaGetLastError();
@@ -421,8 +560,7 @@ int tc_core_pack(gnb_ctx* ctx, const gnb_block_params& blk, const gnb_ffn_params
   }
   __nv_bfloat16* w = p->w;
   const size_t BE = BLK_BYTES / 2;   // elements per block
-  p->w_proj = w; p->w_agg = w + 2 * BE; p->w_edge = w + 3 * BE; p->w_node = w + 12 * BE;
-  p->w_eblk = p->w_edge + 1 * BE;    // the edge kernel's W_blk block (We_e with the LN1 scale folded in)
+  p->w_proj = w; p->w_agg = w + 2 * BE; p->w_edge = w + 4 * BE; p->w_node = w + 13 * BE;
   p->cu_e = p->f; p->cu_n = p->f + 128; p->b1f_e = p->f + 256; p->b1f_n = p->f + 768;
   cudaStream_t st = ctx->stream;
   auto pack = [&](const float* W, int ldw, int n0, int k0, const float* gamma, __nv_bfloat16* dst) {
@@ -432,11 +570,21 @@ int tc_core_pack(gnb_ctx* ctx, const gnb_block_params& blk, const gnb_ffn_params
   const float *g1e = ln1[0].gamma, *g1n = ln1[1].gamma, *b1e = ln1[0].beta, *b1n = ln1[1].beta;
   pack(blk.We, H, 0, H, g1n, w + 0 * BE);          // P_s
   pack(blk.We, H, 0, 2 * H, g1n, w + 1 * BE);      // P_r
-  pack(blk.Wn, H, 0, 0, nullptr, w + 2 * BE);      // W_na (aggregate rows, no LayerNorm)
+  // agg2 blocks: F = W_ee' W_na (folded in fp32, then rounded once) and W_na (aggregate rows, no LayerNorm)
+  float* Ftmp = nullptr;
+  if (cudaMalloc((void**)&Ftmp, (size_t)H * H * sizeof(float)) != cudaSuccess) {
+    cudaGetLastError();
+    tc_core_pack_free(p);
+    gnb_set_error("tc_core_pack: cudaMalloc failed");
+    return GNB_ERR_OOM;
+  }
+  k_fold_matmul<<<H, H, 0, st>>>(blk.We, blk.Wn, g1e, Ftmp);
+  pack(Ftmp, H, 0, 0, nullptr, w + 2 * BE);
+  pack(blk.Wn, H, 0, 0, nullptr, w + 3 * BE);
   // fused kernels: block order documented at k_core
   // both fused kernels (tc_edge.cu) index the blocks as  W1_0 W_blk W2_0 W1_1 W2_1 W1_2 W2_2 W1_3 W2_3
   for (int kind = 0; kind < 2; kind++) {
-    __nv_bfloat16* dst = w + (kind == 0 ? 3 : 12) * BE;
+    __nv_bfloat16* dst = w + (kind == 0 ? 4 : 13) * BE;
     for (int c = 0; c < 4; c++) {
       const int i1 = c == 0 ? 0 : 2 * c + 1;      // W1_c
       const int i2 = 2 * c + 2;                   // W2_c
@@ -455,6 +603,7 @@ int tc_core_pack(gnb_ctx* ctx, const gnb_block_params& blk, const gnb_ffn_params
   k_fold_bias<<<4, 128, 0, st>>>(ffn[1].W1, 4 * H, 0, 0, H, ln2[1].beta, ffn[1].b1, 4 * H, p->b1f_n, 0);
   cudaError_t e = cudaStreamSynchronize(st);
   if (e == cudaSuccess) e = cudaGetLastError();
+  cudaFree(Ftmp);
   if (e != cudaSuccess) {
     gnb_set_error("tc_core_pack: %s", cudaGetErrorString(e));
     tc_core_pack_free(p);
@@ -467,7 +616,7 @@ int tc_core_pack(gnb_ctx* ctx, const gnb_block_params& blk, const gnb_ffn_params
 template <int SRC, int NBLK>
 static int launch_proj(gnb_ctx* ctx, const ProjArgs& a, const char* name, double flops, double bytes) {
   if (a.num_tiles <= 0) return GNB_OK;
-  if (ctx_first(ctx, (SRC == SRC_LN && NBLK == 2) ? ONCE_PROJ_LN2 : ((SRC == SRC_AGG && NBLK == 1) ? ONCE_PROJ_AGG1 : ONCE_PROJ_OTHER)))
+  if (ctx_first(ctx, NBLK == 2 ? ONCE_PROJ_LN2 : ONCE_PROJ_OTHER))
     GNB_CUDA(cudaFuncSetAttribute(k_tc_proj<SRC, NBLK>, cudaFuncAttributeMaxDynamicSharedMemorySize, pj_smem(NBLK)));
   const int per_sm = NBLK == 1 ? 2 : 1;
   const int grid = a.num_tiles < per_sm * ctx->sm_count ? a.num_tiles : per_sm * ctx->sm_count;
@@ -492,10 +641,10 @@ int tc_core_forward(gnb_ctx* ctx, const gnb_graph* g, const TcCorePack* pk, cons
   float* Psr = arena_ptr<float>(ctx->arena, (size_t)N * 2 * H, &rc);
   float* Epart = arena_ptr<float>(ctx->arena, nparts * H, &rc);
   float* Gpart = arena_ptr<float>(ctx->arena, nparts * H, &rc);
-  float* Gs = arena_ptr<float>(ctx->arena, (size_t)N * H, &rc);
-  float* agg = arena_ptr<float>(ctx->arena, (size_t)N * H, &rc);
   float* Pagg = arena_ptr<float>(ctx->arena, (size_t)N * H, &rc);
   const size_t nnparts = (size_t)(g->n_nparts > 0 ? g->n_nparts : 1);
+  float* SEpart = arena_ptr<float>(ctx->arena, nnparts * H, &rc);
+  float* SGpart = arena_ptr<float>(ctx->arena, nnparts * H, &rc);
   float* Vpart = arena_ptr<float>(ctx->arena, nnparts * H, &rc);
   float* Npart = arena_ptr<float>(ctx->arena, nnparts * H, &rc);
   if (rc != GNB_OK) return rc;
@@ -526,18 +675,21 @@ int tc_core_forward(gnb_ctx* ctx, const gnb_graph* g, const TcCorePack* pk, cons
     // 8H bytes of features + 12 B of index per edge
     GNB_TRY(launch_edge5(ctx, a, "tc_edge_core", 24.0 * HH * E, (8.0 * H + 12.0) * E));
   }
-  // edge -> node aggregate (src/nodefninput.jl:3) by linearity: agg = We_e' (sum ê) + sum (Ps + Pr + Pu)
+  // edge -> node aggregate (src/nodefninput.jl:3) and its node-update projection in one pass, by linearity:
+  // P_agg = W_na [ W_ee' (sum ê) + sum (Ps + Pr + Pu) ] = (sum ê) F + (sum G) W_na;  the per-graph sums of both operands go to
+  // k_graph_post (agg itself is never materialised)
   {
-    ProjArgs a{};
-    a.x = Epart; a.part_ptr = g->node_part_ptr; a.x2 = Gpart; a.sum2 = Gs; a.addend = Gs; a.out = agg; a.R = N; a.num_tiles = ceil_div(N, TM); a.nblk = 1;
-    a.wpack = pk->w_eblk;
-    GNB_TRY((launch_proj<SRC_AGG, 1>(ctx, a, "tc_agg", 2.0 * N * HH, 4.0 * N * 3 * H)));
-  }
-  {  // W_na . agg
-    ProjArgs a{};
-    a.x = agg; a.part_ptr = nullptr; a.out = Pagg; a.R = N; a.num_tiles = ceil_div(N, TM); a.nblk = 1;
-    a.wpack = pk->w_agg;
-    GNB_TRY((launch_proj<SRC_AGG, 1>(ctx, a, "tc_agg_proj", 2.0 * N * HH, 4.0 * N * 2 * H)));
+    Agg2Args a{};
+    a.Epart = Epart; a.Gpart = Gpart; a.part_ptr = g->node_part_ptr; a.gpart = g->node_gpart;
+    a.SEpart = SEpart; a.SGpart = SGpart; a.out = Pagg; a.R = N; a.num_tiles = ceil_div(N, TM); a.wpack = pk->w_agg;
+    a.wd = ctx_watch(ctx);
+    if (a.num_tiles > 0) {
+      if (ctx_first(ctx, ONCE_AGG2)) GNB_CUDA(cudaFuncSetAttribute(k_tc_agg2, cudaFuncAttributeMaxDynamicSharedMemorySize, AG_SMEM));
+      const int grid = a.num_tiles < ctx->sm_count ? a.num_tiles : ctx->sm_count;
+      Launch L(ctx, "tc_agg", 4.0 * (2.0 * nparts + N) * H, 2.0 * N * 2 * HH);
+      k_tc_agg2<<<grid, AG_THREADS, AG_SMEM, ctx->stream>>>(a);
+      GNB_CUDA(cudaGetLastError());
+    }
   }
   {  // nodes: same fused kernel; the node -> graph sum of the block output h_v = W_nv' v^ + P_agg + P_un[g] is taken by
      // linearity over the partial sums of v^ (V_part) and of the addends (N_part), so h_v is never materialised
@@ -551,8 +703,9 @@ int tc_core_forward(gnb_ctx* ctx, const gnb_graph* g, const TcCorePack* pk, cons
   // graphs (B rows, fp32 CUDA cores): sums over the graph's nodes, graph update, graph FFN + residual
   {
     GraphPostArgs ga{};
-    ga.xg = xg; ga.B = B; ga.graph_node_ptr = g->graph_node_ptr; ga.agg = agg;
-    ga.graph_npart_ptr = g->graph_npart_ptr; ga.Vpart = Vpart; ga.Npart = Npart;
+    ga.xg = xg; ga.B = B;
+    ga.graph_npart_ptr = g->graph_npart_ptr; ga.Vpart = Vpart; ga.Npart = Npart; ga.SEpart = SEpart; ga.SGpart = SGpart;
+    ga.Wee = blk.We; ga.g1e = ln1[0].gamma;
     ga.Wnv = blk.Wn + (size_t)H * H; ga.g1n = ln1[1].gamma;
     ga.g1 = ln1[2].gamma; ga.b1ln = ln1[2].beta; ga.eps1 = ln1[2].eps; ga.eps_mode1 = ln1[2].eps_mode;
     ga.g2 = ln2[2].gamma; ga.b2ln = ln2[2].beta; ga.eps2 = ln2[2].eps; ga.eps_mode2 = ln2[2].eps_mode;

@@ -207,6 +207,8 @@ __global__ void __launch_bounds__(E_THREADS, 1) k_edge5(const EdgeArgs a) {
   const uint32_t tmem = *tmem_slot;
   const uint32_t HdA = tmem + 256, HdB = tmem + 384;
   const int grid = gridDim.x;
+  const int first_tile = (int)blockIdx.x - (int)rank;      // both CTAs of a pair run the same number of passes
+  const int npass = first_tile < a.num_tiles ? (a.num_tiles - first_tile + grid - 1) / grid : 0;
 
   if (warp == W_LOAD) {
     // ===================================================== weight loader
@@ -369,18 +371,24 @@ __global__ void __launch_bounds__(E_THREADS, 1) k_edge5(const EdgeArgs a) {
       tc_wait_st();
       tc_fence_before();
     };
-    for (int tile = blockIdx.x; TILE_OK(tile); tile += grid, tl++) {
+    auto conv = [&](int c) {      // chunk c of whichever pass the MMA warp is feeding: the barrier phases repeat per pass
+      mbar_wait(BAR(EB_HIDFULL + (c & 1)), (c >> 1) & 1);
+      EDBG(1 + 2 * c);
+      tc_fence_after();
+      convert((c & 1) ? HdB : HdA, c);
+      ARRIVE_LEADER(EB_HSREADY + (c & 1));
+      EDBG(2 + 2 * c);
+    };
+    // Software-pipelined over passes:  C2 C3 (pass t) | C0 C1 (pass t+1) | stage (pass t).  The staging copy has to wait for
+    // the OUT warps to drain this warp's two slices of the previous tile; with the first two chunks of the next pass converted
+    // before that wait, the MMA warp keeps four blocks of work (dn0 up2 dn1 up3) while this warp is blocked.  (Converting all
+    // four chunks first and staging last - round 1 - let the slowest quadrant gate every pass: 15 k cycles per tile.)
+    if (npass > 0 && !wd_dead) { tl = 0; EDBG(0); conv(0); conv(1); }
+    for (tl = 0; (int)tl < npass && !wd_dead; tl++) {
       const uint32_t st = tl & 1, uph = (tl >> 1) & 1;
-      EDBG(0);
-#pragma unroll 1
-      for (int c = 0; c < 4; c++) {
-        mbar_wait(BAR(EB_HIDFULL + (c & 1)), (c >> 1) & 1);
-        EDBG(1 + 2 * c);
-        tc_fence_after();
-        convert((c & 1) ? HdB : HdA, c);
-        ARRIVE_LEADER(EB_HSREADY + (c & 1));
-        EDBG(2 + 2 * c);
-      }
+      conv(2);
+      conv(3);
+      if ((int)tl + 1 < npass) { conv(0); conv(1); }
       // ---------------- finished accumulator -> staging tile (row r = this thread; 4 column groups of 32 fp32)
       mbar_wait(BAR(EB_OUTDONE + st), uph);
       EDBG(9);
@@ -539,7 +547,14 @@ __global__ void __launch_bounds__(E_THREADS, 1) k_edge5(const EdgeArgs a) {
     }
   } else {
     // ===================================================== OUT warps (4-7, 12, 13), one tile behind the MMAs.  A tile is drained in
-    // 8 slices of 16 rows (= one cut of the partial-row index); slice k = 8 pass + s is taken by OUT warp k mod 6
+    // 8 slices of 16 rows (= one cut of the partial-row index); slice k = 8 pass + s is taken by OUT warp k mod 6.
+    // The role is bound by the latency of its three global loads per row (x for the residual, gathered P_s[src], P_r'[dst]), so
+    // the rows of SIX rows are kept in flight in a rolling window that runs across slice boundaries: the indices of the next
+    // slice are fetched while the current one is processed, and its first rows are issued from the tail of the current slice.
+#ifndef GNB_OUT_DEPTH
+#define GNB_OUT_DEPTH 6
+#endif
+    constexpr int DEPTH = GNB_OUT_DEPTH;
     const int ow = warp < 8 ? warp - 4 : warp - 8;
     const float4 b2v = *reinterpret_cast<const float4*>(sB2 + 4 * lane);
     const float* xbase = a.x + 4 * lane;
@@ -547,64 +562,68 @@ __global__ void __launch_bounds__(E_THREADS, 1) k_edge5(const EdgeArgs a) {
     const float* base2 = a.add2 + 4 * lane;
     const uint32_t s_lane0 = (uint32_t)(E_OFF_STG + (lane >> 3) * 16384);
     const uint32_t s_chunk = (uint32_t)(lane & 7);
-    const int first = (int)blockIdx.x - (int)rank;      // both CTAs of a pair run the same number of passes
-    const int npass = first < a.num_tiles ? (a.num_tiles - first + grid - 1) / grid : 0;
-    for (int k = ow; k < OUT_SLICES * npass && !wd_dead; k += OUT_WARPS) {
+    const int total = OUT_SLICES * npass;
+    // per-lane row attributes of a slice (lane i < 16 holds row i): gather indices and partial-row id
+    auto slice_row0 = [&](int k) { return ((int64_t)blockIdx.x + (int64_t)(k >> 3) * grid) * TM + OUT_ROWS * (k & (OUT_SLICES - 1)); };
+    auto load_attr = [&](int64_t row0, int& i1, int& i2, int& pid) {
+      i1 = 0; i2 = 0; pid = -1;
+      if (lane < OUT_ROWS && row0 + lane < a.R) {
+        i1 = a.idx1 ? __ldg(a.idx1 + row0 + lane) : (int)(row0 + lane);
+        i2 = __ldg(a.idx2 + row0 + lane);
+        pid = __ldg(a.part + row0 + lane);
+      }
+    };
+    float4 xa[DEPTH], pa[DEPTH], pb[DEPTH];
+    auto issue1 = [&](int u, int64_t row0, int src_i1, int src_i2, int i) {
+      const int i1 = __shfl_sync(0xffffffffu, src_i1, i), i2 = __shfl_sync(0xffffffffu, src_i2, i);
+      int64_t r = row0 + i;
+      r = r < a.R ? r : a.R - 1;
+      xa[u] = ld_stream(xbase + (size_t)r * H);                       // second and last read of x: L2 hit
+      pa[u] = __ldg(reinterpret_cast<const float4*>(base1 + (size_t)i1 * a.ld1));
+      pb[u] = __ldg(reinterpret_cast<const float4*>(base2 + (size_t)i2 * a.ld2));
+    };
+    int c_i1 = 0, c_i2 = 0, c_pid = -1, n_i1 = 0, n_i2 = 0, n_pid = -1;
+    if (ow < total) {
+      load_attr(slice_row0(ow), c_i1, c_i2, c_pid);
+#pragma unroll
+      for (int u = 0; u < DEPTH; u++) issue1(u, slice_row0(ow), c_i1, c_i2, u);
+    }
+    for (int k = ow; k < total && !wd_dead; k += OUT_WARPS) {
       const uint32_t tl = (uint32_t)k >> 3;
       const int sl = k & (OUT_SLICES - 1);
-      const int tile = blockIdx.x + (int)tl * grid;
       const uint32_t s_lane = s_lane0 + (uint32_t)((OUT_ROWS * sl) * 128);
-      const int64_t row0 = (int64_t)tile * TM + OUT_ROWS * sl;
+      const int64_t row0 = slice_row0(k);
       const int64_t left = a.R - row0;
       const int rows = left < 0 ? 0 : (left > OUT_ROWS ? OUT_ROWS : (int)left);
-      int my_i1 = 0, my_i2 = 0, my_pid = -1;
-      if (lane < rows) {
-        my_i1 = a.idx1 ? __ldg(a.idx1 + row0 + lane) : (int)(row0 + lane);
-        my_i2 = __ldg(a.idx2 + row0 + lane);
-        my_pid = __ldg(a.part + row0 + lane);
-      }
-      const int nxt = __shfl_down_sync(0xffffffffu, my_pid, 1);
-      const uint32_t endmask = __ballot_sync(0xffffffffu, lane < rows && (lane == rows - 1 || nxt != my_pid));
-      int pid = __shfl_sync(0xffffffffu, my_pid, 0);
+      const bool has_next = k + OUT_WARPS < total;      // warp-uniform
+      const int64_t nrow0 = slice_row0(has_next ? k + OUT_WARPS : k);
+      if (has_next) load_attr(nrow0, n_i1, n_i2, n_pid);
+      const int nxt = __shfl_down_sync(0xffffffffu, c_pid, 1);
+      const uint32_t endmask = __ballot_sync(0xffffffffu, lane < rows && (lane == rows - 1 || nxt != c_pid));
+      int pid = __shfl_sync(0xffffffffu, c_pid, 0);
       EDBG(0);
-      float4 xa[4], pa[4], pb[4];
-      auto issue1 = [&](int u, int i) {
-        const int i1 = __shfl_sync(0xffffffffu, my_i1, i), i2 = __shfl_sync(0xffffffffu, my_i2, i);
-        int64_t r = row0 + i;
-        r = r < a.R ? r : a.R - 1;
-        xa[u] = ld_stream(xbase + (size_t)r * H);                       // second and last read of x: L2 hit
-        pa[u] = __ldg(reinterpret_cast<const float4*>(base1 + (size_t)i1 * a.ld1));
-        pb[u] = __ldg(reinterpret_cast<const float4*>(base2 + (size_t)i2 * a.ld2));
-      };
-#pragma unroll
-      for (int u = 0; u < 4; u++) issue1(u, u);
       mbar_wait(BAR(EB_STGFULL + sl), tl & 1);
       EDBG(1);
       float4 acc = f4zero();
-#pragma unroll 1
-      for (int i0 = 0; i0 < OUT_ROWS; i0 += 4) {
-        float4 d[4];
 #pragma unroll
-        for (int u = 0; u < 4; u++) {
-          const int i = i0 + u;
-          d[u] = *reinterpret_cast<const float4*>(sm + s_lane + i * 128 + ((s_chunk ^ (uint32_t)(i & 7)) << 4));
-        }
-#pragma unroll
-        for (int u = 0; u < 4; u++) {
-          const int i = i0 + u;
-          const float4 g = add4(pa[u], pb[u]);
-          const float4 y = add4(add4(add4(xa[u], g), d[u]), b2v);
-          if (i < rows) __stcs(reinterpret_cast<float4*>(a.y + (size_t)(row0 + i) * H) + lane, y);
-          acc = add4(acc, g);
-          const bool fl = (endmask >> i) & 1u;
-          if (fl) *(reinterpret_cast<float4*>(a.Gpart + (size_t)pid * H) + lane) = acc;
-          acc.x = fl ? 0.f : acc.x; acc.y = fl ? 0.f : acc.y; acc.z = fl ? 0.f : acc.z; acc.w = fl ? 0.f : acc.w;
-          pid += fl ? 1 : 0;
-          if (i0 + 4 < OUT_ROWS) issue1(u, i + 4);   // refill this slot with the same row of the next group
-        }
+      for (int i = 0; i < OUT_ROWS; i++) {
+        const int u = i % DEPTH;
+        const float4 d = *reinterpret_cast<const float4*>(sm + s_lane + i * 128 + ((s_chunk ^ (uint32_t)(i & 7)) << 4));
+        const float4 g = add4(pa[u], pb[u]);
+        const float4 y = add4(add4(add4(xa[u], g), d), b2v);
+        if (i < rows) __stcs(reinterpret_cast<float4*>(a.y + (size_t)(row0 + i) * H) + lane, y);
+        acc = add4(acc, g);
+        const bool fl = (endmask >> i) & 1u;
+        if (fl) *(reinterpret_cast<float4*>(a.Gpart + (size_t)pid * H) + lane) = acc;
+        acc.x = fl ? 0.f : acc.x; acc.y = fl ? 0.f : acc.y; acc.z = fl ? 0.f : acc.z; acc.w = fl ? 0.f : acc.w;
+        pid += fl ? 1 : 0;
+        // refill this slot: row i + DEPTH of this slice, or - past its end - the matching row of this warp's next slice
+        if (i + DEPTH < OUT_ROWS) issue1(u, row0, c_i1, c_i2, i + DEPTH);
+        else if (has_next) issue1(u, nrow0, n_i1, n_i2, i + DEPTH - OUT_ROWS);
       }
       ARRIVE_LOCAL(EB_STGEMPTY + sl);
       EDBG(2);
+      c_i1 = n_i1; c_i2 = n_i2; c_pid = n_pid;
     }
   }
   tc_fence_before();

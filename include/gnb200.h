@@ -39,6 +39,8 @@ extern "C" {
 #define GNB_ADJ_F32 0
 #define GNB_ADJ_U8  1
 #define GNB_ADJ_I32 2
+#define GNB_ADJ_BITS 3   /* bit-packed `isone` mask: bit (i + PN*j) of graph b in little-endian uint32 words, every graph starting
+                            on a word boundary (ceil(PN*PN/32) words per graph) - 8x fewer bytes than the uint8 mask */
 
 /* LayerNorm denominator (Flux `normalise`, third-party) */
 #define GNB_EPS_SQRT_VAR_EPS2 0  /* sqrt(var + eps^2)  - default (Flux 0.14)  */
@@ -105,6 +107,15 @@ int         gnb_debug_tc_timing(unsigned long long* out, int n);
  *   Badj     1 (single-adjacency mode, structure shared by all B graphs, src/batch.jl:66) or B. */
 int gnb_graph_lower(gnb_ctx*, const void* adj, int adj_dtype, int adj_on_device,
                     const int32_t* n_nodes, int PN, int Badj, int B, gnb_graph** out);
+/* The same lowering from COO edge lists, without the dense detour (batch on edge lists: src/batch.jl:53-64 + the `findall`
+ * of src/pad.jl:26-46).  Graph b owns edges [graph_edge_ptr[b], graph_edge_ptr[b+1]) with LOCAL node ids sender src[e] (row i)
+ * and receiver dst[e] (column j) in [0, n_nodes[b]).  Each graph's edges must be strictly ascending in the padded slot
+ * src + PN*dst (receiver-major) - the order in which the reference lists the active entries of an adjacency matrix and in
+ * which edge features are given; anything else is GNB_ERR_INVALID.  src / dst: int32, HOST or device (coo_on_device);
+ * graph_edge_ptr [B+1] and n_nodes [B]: HOST.  PN <= 0: the largest n_nodes (padadjmats, src/pad.jl:3).
+ * The resulting index is bit-identical to gnb_graph_lower on the equivalent adjacency matrices. */
+int gnb_graph_from_coo(gnb_ctx*, const int32_t* src, const int32_t* dst, int coo_on_device,
+                       const int32_t* graph_edge_ptr, const int32_t* n_nodes, int PN, int B, gnb_graph** out);
 int gnb_graph_destroy(gnb_graph*);
 int gnb_graph_counts(const gnb_graph*, int64_t* E, int64_t* N, int32_t* B, int32_t* PN);
 /* Copy the index to HOST buffers (any may be NULL).  edge_src/edge_dst are global compact node

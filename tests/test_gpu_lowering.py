@@ -120,3 +120,91 @@ def test_lower_rejects_bad_arguments(gn):
     assert rc == -1 and b"n_nodes" in gn.lib.gnb_last_error()
     rc = gn.lib.gnb_graph_lower(eng.ctx, buf.ctypes.data_as(C.c_void_p), 1, 0, nn, 4, 2, 3, C.byref(h))
     assert rc == -1
+
+
+def _random_batch(rng, B, nmax):
+    adjs = []
+    for _ in range(B):
+        n = int(rng.integers(1, nmax + 1))
+        adjs.append((rng.random((n, n)) < rng.uniform(0.0, 0.9)).astype(np.uint8))
+    adjs[0] = np.zeros((3, 3), np.uint8)      # an empty graph in front
+    return adjs
+
+
+def _coo_of(adjs, PN):
+    src, dst, ep = [], [], [0]
+    for a in adjs:
+        j, i = np.nonzero(a.T == 1)          # receiver-major: ascending i + PN*j
+        src.append(i)
+        dst.append(j)
+        ep.append(ep[-1] + i.size)
+    return np.concatenate(src).astype(np.int32), np.concatenate(dst).astype(np.int32), np.array(ep, np.int32)
+
+
+def test_coo_lowering_equals_dense_lowering(gn):
+    """the index from COO edge lists == the index from the dense adjacency (== the oracle), bit for bit, and a
+    forward on it gives the same features."""
+    rng = np.random.default_rng(41)
+    adjs = _random_batch(rng, 37, 19)
+    PN = max(a.shape[0] for a in adjs)
+    src, dst, ep = _coo_of(adjs, PN)
+    nn = np.array([a.shape[0] for a in adjs], np.int32)
+    gd = gn.GNGraphBatch(adjs)
+    gc = gn.GNGraphBatch.from_coo(src, dst, ep, nn)
+    ref = O.lower(adjs)
+    assert (gc.E, gc.N, gc.B, gc.node_block_size) == (gd.E, gd.N, gd.B, gd.node_block_size) == (ref["E"], ref["N"], ref["B"], PN)
+    for k in ("edge_src", "edge_dst", "edge_slot", "edge_graph", "graph_edge_ptr", "graph_node_ptr", "node_in_ptr"):
+        assert np.array_equal(gc.index()[k], gd.index()[k]), k
+        assert np.array_equal(gc.index()[k], ref[k].astype(np.int32)), k
+    # the reference-facing fields are still there (built on demand)
+    assert all(np.array_equal(a, b) for a, b in zip(gc.adj_mats, adjs))
+    ef = rng.random((gd.E, 4), dtype=np.float32)
+    nf = rng.random((gd.N, 3), dtype=np.float32)
+    blk = gn.GNBlock((4, 3, 0), (5, 6, 7), rng=np.random.default_rng(3))
+    xd = gn.GNData(gd, gn.Padded("e", torch.from_numpy(ef).cuda(), gd), gn.Padded("n", torch.from_numpy(nf).cuda(), gd), None)
+    xc = gn.batch_coo(src, dst, ep, nn, ef=ef, nf=nf)
+    yd, yc = blk(xd), blk(xc)
+    for f in ("ef", "nf", "gf"):
+        assert torch.equal(getattr(yd, f).compact, getattr(yc, f).compact), f
+
+
+def test_coo_lowering_rejects_bad_edge_lists(gn):
+    nn = np.array([3, 2], np.int32)
+    ep = np.array([0, 2, 3], np.int32)
+    ok = (np.array([0, 2, 1], np.int32), np.array([0, 1, 1], np.int32))
+    gn.GNGraphBatch.from_coo(ok[0], ok[1], ep, nn)
+    for src, dst in [(np.array([2, 0, 1], np.int32), np.array([1, 0, 1], np.int32)),      # not receiver-major
+                     (np.array([0, 0, 1], np.int32), np.array([0, 0, 1], np.int32)),      # duplicate edge
+                     (np.array([0, 3, 1], np.int32), np.array([0, 1, 1], np.int32)),      # sender out of range
+                     (np.array([0, 2, 1], np.int32), np.array([0, 1, 2], np.int32))]:     # receiver out of range (graph of 2 nodes)
+        with pytest.raises(AssertionError):
+            gn.GNGraphBatch.from_coo(src, dst, ep, nn)
+
+
+def test_bit_packed_adjacency_equals_byte_mask(gn):
+    """GNB_ADJ_BITS (what `batch` uploads) against the uint8 / float32 / int32 entry points of gnb_graph_lower, PN not a multiple
+    of 32 bits per graph."""
+    import ctypes as C
+    rng = np.random.default_rng(43)
+    B, PN = 21, 7
+    adj = (rng.random((B, PN, PN)) < 0.4).astype(np.uint8)
+    nn = np.full(B, PN, np.int32)
+    eng = gn.get_engine()
+    lib, L = gn.lib, gn.pkg._lib
+    mask = np.ascontiguousarray(adj.transpose(0, 2, 1))
+    outs = []
+    for dtype, arr in ((L.ADJ_U8, mask), (L.ADJ_F32, mask.astype(np.float32)), (L.ADJ_I32, mask.astype(np.int32)),
+                       (L.ADJ_BITS, gn.pack_adjacency_bits(mask))):
+        h = C.c_void_p()
+        eng.bind_stream()
+        L.check(lib.gnb_graph_lower(eng.ctx, arr.ctypes.data_as(C.c_void_p), dtype, 0, nn.ctypes.data_as(L.i32p), PN, B, B, C.byref(h)))
+        E = C.c_int64()
+        L.check(lib.gnb_graph_counts(h, C.byref(E), None, None, None))
+        src, dst, slot = (np.empty(E.value, np.int32) for _ in range(3))
+        p = lambda a: a.ctypes.data_as(C.c_void_p)
+        L.check(lib.gnb_graph_export_host(eng.ctx, h, p(src), p(dst), p(slot), None, None, None, None))
+        lib.gnb_graph_destroy(h)
+        outs.append((E.value, src, dst, slot))
+    assert outs[0][0] == int(adj.sum())
+    for o in outs[1:]:
+        assert o[0] == outs[0][0] and all(np.array_equal(a, b) for a, b in zip(o[1:], outs[0][1:]))

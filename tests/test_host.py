@@ -109,3 +109,38 @@ def test_default_precision_is_fp32(gn):
     gn.set_precision("fp32")
     with pytest.raises(AssertionError):
         gn.set_precision("fp16")
+
+
+# names the reference exports for this path (src/GraphNets.jl:12-50) and north_star lists
+REFERENCE_EXPORTS = ["GNGraphBatch", "batch", "unbatch", "GNBlock", "zerodim2nothing", "GNCore", "GNCoreList", "efview", "nfview",
+                     "gfview", "flatunpaddednf", "flatunpaddedef", "collapsef", "unpaddedcollapsedef", "flatunpaddedcollapsedef"]
+
+
+def test_julia_shim_binds_only_declared_symbols_and_defines_the_reference_exports(gn):
+    """julia/GraphNetsB200.jl cannot run here (no Julia toolchain): check statically that every symbol it ccalls is declared in
+    include/gnb200.h and exported by the library, that it exports every name the reference exports for this path, and that every
+    exported name is defined in the file."""
+    src = open(os.path.join(ROOT, "julia", "GraphNetsB200.jl")).read()
+    code = "\n".join(l.split("#")[0] if not l.lstrip().startswith("#") else "" for l in src.splitlines())
+    called = set(re.findall(r"ccall\(\(:(gnb_[a-z0-9_]+),\s*LIB\)", code))
+    declared = set(_header_symbols())
+    assert called and called <= declared, "undeclared symbols in the Julia shim: %s" % sorted(called - declared)
+    lib = ctypes.CDLL(gn.LIB_PATH)
+    for n in called:
+        assert hasattr(lib, n), n
+    # the model path (the benchmarked one) and the edge-list entry are reachable from Julia
+    for n in ("gnb_model_create", "gnb_model_forward", "gnb_corelist_forward", "gnb_core_forward", "gnb_block_forward",
+              "gnb_graph_lower", "gnb_graph_from_coo", "gnb_pad_edges", "gnb_pad_nodes", "gnb_collapse_edges", "gnb_graph_export_host"):
+        assert n in called, "%s is not bound by the Julia shim" % n
+    m = re.search(r"^export\s+(.*?)^end", code, flags=re.S | re.M)
+    assert m, "no export list"
+    exported = set(re.findall(r"[A-Za-z_][A-Za-z0-9_!]*", m.group(1)))
+    missing = [n for n in REFERENCE_EXPORTS if n not in exported]
+    assert not missing, "reference exports missing from the Julia shim: %s" % missing
+    for n in exported:
+        pat = r"(^|\s)(function\s+%s\b|(mutable\s+)?struct\s+%s\b|%s\([^)]*\)(\s+where\s+\{[^}]*\})?\s*=|const\s+%s\b)" % ((re.escape(n),) * 4)
+        assert re.search(pat, code, flags=re.M), "%s is exported but not defined" % n
+    # reference field names of the layer structs (src/gnblock.jl:39-45, src/gncore.jl:38-44, src/gncorelist.jl:29-31)
+    for pat in (r"struct GNBlock\s+edgefn; nodefn; graphfn; dropout", r"struct GNCore\s+block; ffwd; gn1; gn2",
+                r"struct GNCoreList\s+list", r"struct GNFeedForward\s+eff; nff; gff", r"struct GNGraphNorm\s+edgeln; nodeln; graphln"):
+        assert re.search(pat, code), pat
