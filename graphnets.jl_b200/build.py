@@ -38,7 +38,7 @@ def _digest():
 VARIANTS = {"oldproj": (["tc.cu"], ["-DGNB_OLD_PROJ_PROTOCOL"]),
             "timing": (["tc_edge.cu"], ["-DGNB_TC_TIMING"]),
             "ordera": (["tc_edge.cu"], ["-DGNB_EDGE_ORDER_A"]),      # A/B: round-1 MMA issue order
-            "depth4": (["tc_edge.cu"], ["-DGNB_OUT_DEPTH=4"])}       # A/B: rows in flight per OUT warp      # clock64 phase stamps of the fused kernel (tools/edge_timing.py)
+            "depth8": (["tc_edge.cu"], ["-DGNB_OUT_DEPTH=8"])}       # A/B: rows in flight per OUT warp      # clock64 phase stamps of the fused kernel (tools/edge_timing.py)
 
 
 def variant_path(name):

@@ -549,12 +549,13 @@ __global__ void __launch_bounds__(E_THREADS, 1) k_edge5(const EdgeArgs a) {
     // ===================================================== OUT warps (4-7, 12, 13), one tile behind the MMAs.  A tile is drained in
     // 8 slices of 16 rows (= one cut of the partial-row index); slice k = 8 pass + s is taken by OUT warp k mod 6.
     // The role is bound by the latency of its three global loads per row (x for the residual, gathered P_s[src], P_r'[dst]), so
-    // the rows of SIX rows are kept in flight in a rolling window that runs across slice boundaries: the indices of the next
+    // the loads of DEPTH rows are kept in flight in a rolling window that runs across slice boundaries: the indices of the next
     // slice are fetched while the current one is processed, and its first rows are issued from the tail of the current slice.
 #ifndef GNB_OUT_DEPTH
-#define GNB_OUT_DEPTH 6
+#define GNB_OUT_DEPTH 4
 #endif
     constexpr int DEPTH = GNB_OUT_DEPTH;
+    static_assert(OUT_ROWS % DEPTH == 0, "the rolling window keeps its slot numbering across slices only if DEPTH divides the slice");
     const int ow = warp < 8 ? warp - 4 : warp - 8;
     const float4 b2v = *reinterpret_cast<const float4*>(sB2 + 4 * lane);
     const float* xbase = a.x + 4 * lane;

@@ -90,7 +90,7 @@ static __device__ __forceinline__ void tc_commit(uint32_t bar) {
 }
 // One lane of a CONVERGED warp.  tcgen05.mma / commit take their operands from uniform registers; issuing
 // them from divergent code (if (lane == 0)) makes ptxas wrap every instruction in an ELECT/branch loop,
-// which costs ~2x the tensor-pipe time of a 128x128x16 UMMA (scratch/hwprobe.cu, T3).
+// which costs ~2x the tensor-pipe time of a 128x128x16 UMMA (tools/micro/hwprobe.cu, T3).
 static __device__ __forceinline__ bool elect_one() {
   uint32_t pred;
   asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
@@ -126,7 +126,7 @@ static __device__ __forceinline__ void mma_ts(uint32_t d_tmem, uint32_t a_tmem, 
         "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])                     \
       : "r"(taddr)                                                                                                    \
       : "memory")
-// 16 lanes x 64 fp32 columns in the accumulator-fragment layout (verified by scratch/hwprobe.cu, T1):
+// 16 lanes x 64 fp32 columns in the accumulator-fragment layout (verified by tools/micro/hwprobe.cu, T1):
 //   r[4n + 2h + c] of lane l = TMEM[lane base + l/4 + 8h][col base + 8n + 2(l%4) + c]
 // four consecutive lanes cover one 32-byte sector of a row: sector-exact global loads / stores from registers.
 #define TC_LD_FRAG64(taddr, r)                                                                                        \

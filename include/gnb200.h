@@ -95,7 +95,7 @@ int         gnb_ctx_set_profiling(gnb_ctx*, int on);
 int         gnb_ctx_profile_read(gnb_ctx*, gnb_prof_entry* out, int cap, int* n);
 /* Diagnostics of the fused tcgen05 edge kernel: the first call (out == NULL) switches on clock64 stamping
  * of one steady-state tile pair per CTA; later calls copy the stamps [CTA 148][warp 18][slot 32] of the
- * most recent edge launch to `out` (n = capacity in 64-bit words).  Used by scratch/tc_timing.py only. */
+ * most recent edge launch to `out` (n = capacity in 64-bit words).  Used by tools/edge_timing.py (test-only library variant "timing") only. */
 int         gnb_debug_tc_timing(unsigned long long* out, int n);
 
 /* ---------------------------------------------------------------- lowering ---------- */

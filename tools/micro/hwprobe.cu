@@ -3,7 +3,7 @@
 //   T2  tcgen05.mma with the A operand in TMEM (bf16 packed, written in place over fp32 columns)
 //   T3  tensor-pipe time per 128x128x128 block: SS vs TS, N=128 vs N=256, with shared-memory contention
 //   T4  tcgen05.ld throughput (32x32b.x32 and 16x256b.x8) with 4 / 8 warps
-// build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o scratch/hwprobe scratch/hwprobe.cu
+// build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o /tmp/hwprobe tools/micro/hwprobe.cu
 #include <cstdio>
 #include <cstdlib>
 #include <cstdint>
