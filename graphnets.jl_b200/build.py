@@ -36,9 +36,7 @@ def _digest():
 # product build.  `oldproj` keeps round 1's k_tc_proj barrier protocol so that tests/test_gpu_watchdog.py can reproduce
 # its dead-lock (GNB_LIB_VARIANT=oldproj selects it in _lib.py); the product never loads a variant.
 VARIANTS = {"oldproj": (["tc.cu"], ["-DGNB_OLD_PROJ_PROTOCOL"]),
-            "timing": (["tc_edge.cu"], ["-DGNB_TC_TIMING"]),
-            "ordera": (["tc_edge.cu"], ["-DGNB_EDGE_ORDER_A"]),      # A/B: round-1 MMA issue order
-            "depth8": (["tc_edge.cu"], ["-DGNB_OUT_DEPTH=8"])}       # A/B: rows in flight per OUT warp      # clock64 phase stamps of the fused kernel (tools/edge_timing.py)
+            "timing": (["tc_edge.cu"], ["-DGNB_TC_TIMING"])}      # clock64 phase stamps of the fused kernel (tools/edge_timing.py)
 
 
 def variant_path(name):

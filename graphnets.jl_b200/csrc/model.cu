@@ -216,6 +216,7 @@ struct LayerW {
   gnb_ln_params ln1[3], ln2[3];
   TcCorePack* tc = nullptr;  // packed bf16 weights (cores the tensor path supports)
   float* wnx = nullptr;      // narrow-input blocks: [We ; be] . Wn_agg  ((in_e+2in_n+in_g+1) x out_n), see run_block_wide
+  float* decW4 = nullptr;    // narrow-output blocks behind a tensor-path core: rows [0, in_e) of the edge Dense padded to 4 outputs
 };
 
 static std::atomic<uint64_t> g_model_ids{1};
@@ -241,6 +242,14 @@ __global__ void k_fold_wnx(const float* __restrict__ We, const float* __restrict
   float s = 0.f;
   for (int j = 0; j < p; j++) s = fmaf(x[j], Wn[(size_t)j * q + n], s);
   out[i] = s;
+}
+
+// out[k][j] = j < p ? We[k][j] : 0     (k < K; We k-major with leading dimension p)
+__global__ void k_pad_w4(const float* __restrict__ We, int K, int p, float* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= K * 4) return;
+  const int k = i >> 2, j = i & 3;
+  out[i] = j < p ? We[(size_t)k * p + j] : 0.f;
 }
 
 static int check_block(const gnb_block_params& b, int li) {
@@ -388,6 +397,21 @@ static int build_model(gnb_ctx* ctx, const gnb_layer* layers, int n_layers, int 
         }
       }
     }
+    // a narrow-output block right behind a tensor-path core can be fused into that core's edge kernel (dec_fusable below)
+    for (size_t li = 1; li < m->layers.size(); li++) {
+      LayerW& w = m->layers[li];
+      const LayerW& prev = m->layers[li - 1];
+      if (w.kind == GNB_LAYER_BLOCK && prev.kind == GNB_LAYER_CORE && prev.tc && w.blk.in_e == 128 && w.blk.out_e > 0 && w.blk.out_e <= 4) {
+        if (cudaMalloc((void**)&w.decW4, 128 * 4 * sizeof(float)) != cudaSuccess) {
+          cudaGetLastError();
+          gnb_model_destroy(m);
+          gnb_set_error("gnb_model_create: cudaMalloc failed");
+          return GNB_ERR_OOM;
+        }
+        k_pad_w4<<<2, 256, 0, ctx->stream>>>(w.blk.We, 128, w.blk.out_e, w.decW4);
+      }
+    }
+    GNB_CUDA(cudaStreamSynchronize(ctx->stream));
   }
   *out = m;
   return GNB_OK;
@@ -402,6 +426,7 @@ extern "C" int gnb_model_destroy(gnb_model* m) {
   for (auto& w : m->layers) {
     if (w.tc) tc_core_pack_free(w.tc);
     if (w.wnx) cudaFree(w.wnx);
+    if (w.decW4) cudaFree(w.decW4);
   }
   if (m->wbuf) cudaFree(m->wbuf);
   delete m;
@@ -652,7 +677,29 @@ static bool block_narrow_ok(const LayerW& w) {
   return w.kind == GNB_LAYER_BLOCK && b.out_e > 0 && b.out_e <= 8 && b.out_n <= 8 && b.in_e >= 32 && b.in_e <= 512 &&
          b.in_n <= 512 && (b.in_e & 3) == 0 && (b.in_n & 3) == 0;
 }
-static int run_block_narrow(gnb_ctx* ctx, const gnb_graph* g, const LayerW& w, Feat x, FeatOut h) {
+// Edge update of a narrow decoder whose edge-feature term was already computed by the previous core's edge kernel
+// (partial[e][0..4) = y_e . We[0:128, :]):  h_e = partial + Ps[src] + Pr[dst] + (Pu[graph] | be)      (src/gnblock.jl:65)
+__global__ void k_dec_finish(const float* __restrict__ partial, const float* __restrict__ Ps, const float* __restrict__ Pr,
+                             const float* __restrict__ Pu, const float* __restrict__ be, const int32_t* __restrict__ src,
+                             const int32_t* __restrict__ dst, const int32_t* __restrict__ eg, int64_t E, int p, float* __restrict__ out) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= E) return;
+  const float4 v4 = __ldg(reinterpret_cast<const float4*>(partial) + e);
+  float v[4] = {v4.x, v4.y, v4.z, v4.w};
+  const int s_ = Ps ? src[e] : 0, d_ = Pr ? dst[e] : 0, g_ = Pu ? eg[e] : 0;
+  for (int j = 0; j < p; j++) {
+    float t = v[j];
+    if (Ps) t += __ldg(Ps + (size_t)s_ * p + j) + __ldg(Pr + (size_t)d_ * p + j);
+    t += Pu ? __ldg(Pu + (size_t)g_ * p + j) : be[j];
+    out[(size_t)e * p + j] = t;
+  }
+}
+
+static bool dec_fusable(const LayerW& core, const LayerW& dec) {
+  return core.kind == GNB_LAYER_CORE && core.tc != nullptr && dec.decW4 != nullptr && block_narrow_ok(dec);
+}
+
+static int run_block_narrow(gnb_ctx* ctx, const gnb_graph* g, const LayerW& w, Feat x, FeatOut h, const float* edge_partial = nullptr) {
   const gnb_block_params& b = w.blk;
   const int a = b.in_e, bn_ = b.in_n, c = b.in_g, p = b.out_e, q = b.out_n, r = b.out_g;
   const int64_t E = g->E, N = g->N, B = g->B;
@@ -681,13 +728,21 @@ static int run_block_narrow(gnb_ctx* ctx, const gnb_graph* g, const LayerW& w, F
     GNB_TRY(launch_linear_fp32(ctx, la));
   }
   {
-    NarrowArgs na{};
-    na.R = E; na.No = p; na.ldw = p; na.nsrc = 1; na.ldo = p; na.out = h.e;
-    na.src[0] = NarrowSrc{x.e, a, a, b.We};
-    if (Ps) { na.add[na.nadd++] = NarrowAdd{Ps, g->edge_src, p}; na.add[na.nadd++] = NarrowAdd{Pr, g->edge_dst, p}; }
-    if (Pu) na.add[na.nadd++] = NarrowAdd{Pu, g->edge_graph, p};
-    else na.bias = b.be;
-    GNB_TRY(launch_narrow(ctx, na));
+    if (edge_partial) {      // the edge-feature term came out of the previous core's edge kernel
+      if (E > 0) {
+        Launch L(ctx, "dec_finish", 4.0 * E * (4 + p + 3), 0);
+        k_dec_finish<<<ceil_div(E, 256), 256, 0, ctx->stream>>>(edge_partial, Ps, Pr, Pu, b.be, g->edge_src, g->edge_dst, g->edge_graph, E, p, h.e);
+        GNB_CUDA(cudaGetLastError());
+      }
+    } else {
+      NarrowArgs na{};
+      na.R = E; na.No = p; na.ldw = p; na.nsrc = 1; na.ldo = p; na.out = h.e;
+      na.src[0] = NarrowSrc{x.e, a, a, b.We};
+      if (Ps) { na.add[na.nadd++] = NarrowAdd{Ps, g->edge_src, p}; na.add[na.nadd++] = NarrowAdd{Pr, g->edge_dst, p}; }
+      if (Pu) na.add[na.nadd++] = NarrowAdd{Pu, g->edge_graph, p};
+      else na.bias = b.be;
+      GNB_TRY(launch_narrow(ctx, na));
+    }
     if (ctx->pipe.out_pending && h.e == ctx->pipe.d_out_ef) {
       // the edge output is final: download it now, under the node / graph kernels of this block (gnb_model_forward_host)
       GNB_CUDA(cudaEventRecord(ctx->pipe.ev_ready, ctx->stream));
@@ -849,7 +904,16 @@ static int forward_device_impl(gnb_ctx* ctx, const gnb_model* m, const gnb_graph
       pre[i].Pun = arena_ptr<float>(ctx->arena, (size_t)g->B * 128, &rc);
     }
   }
+  // fused narrow decoder: the edge kernel of a tensor-path core hands y_e . W_dec to the narrow block behind it
+  const char* fuse_env = getenv("GNB_FUSE_DECODER");
+  const bool fuse_dec = precision != GNB_PREC_FP32 && !(fuse_env && atoi(fuse_env) == 0);
+  float* dec_partial = nullptr;
+  if (fuse_dec) {
+    for (int i = 0; i + 1 < L && !dec_partial; i++)
+      if (dec_fusable(m->layers[i], m->layers[i + 1])) dec_partial = arena_ptr<float>(ctx->arena, (size_t)g->E * 4, &rc);
+  }
   if (rc != GNB_OK) return rc;
+  bool have_partial = false;      // dec_partial holds the edge term of layer li
   Feat x{ef, nf, gf};
   if (ctx->pipe.ef_pending && !(precision != GNB_PREC_FP32 && block_wide_ok(m->layers[0]) && m->layers[0].blk.in_e > 0)) {
     // chunked upload in flight but the first layer reads all edge rows at once: wait for the last chunk
@@ -869,9 +933,10 @@ static int forward_device_impl(gnb_ctx* ctx, const gnb_model* m, const gnb_graph
       // GNB_PREC_FP32 keeps the reference's operation order (generic path); the other modes may take the
       // algebraically equivalent streaming paths for narrow-input / narrow-output blocks
       if (precision != GNB_PREC_FP32 && block_wide_ok(w)) GNB_TRY(run_block_wide(ctx, g, w, x, y));
-      else if (precision != GNB_PREC_FP32 && block_narrow_ok(w)) GNB_TRY(run_block_narrow(ctx, g, w, x, y));
+      else if (precision != GNB_PREC_FP32 && block_narrow_ok(w)) GNB_TRY(run_block_narrow(ctx, g, w, x, y, have_partial ? dec_partial : nullptr));
       else GNB_TRY(run_block_fp32(ctx, g, w.blk, nullptr, x, y));
       have_pre = false;
+      have_partial = false;
     } else {
       bool use_tc = (precision != GNB_PREC_FP32) && w.tc != nullptr;
       const bool wide_ok = (w.blk.in_e % 128 == 0) && (w.blk.in_n % 128 == 0) && (w.blk.in_g % 128 == 0) && m->wbuf != nullptr;
@@ -885,12 +950,16 @@ static int forward_device_impl(gnb_ctx* ctx, const gnb_model* m, const gnb_graph
         if (chain && li + 1 < L && m->layers[li + 1].kind == GNB_LAYER_CORE && m->layers[li + 1].tc) {
           next.pk = m->layers[li + 1].tc; next.blk = &m->layers[li + 1].blk; next.ln1 = m->layers[li + 1].ln1;
         }
+        TcDecFuse dec;
+        if (dec_partial && li + 1 < L && dec_fusable(w, m->layers[li + 1])) { dec.W4 = m->layers[li + 1].decW4; dec.partial = dec_partial; }
         GNB_TRY(tc_core_forward(ctx, g, w.tc, w.blk, w.ffn, w.ln1, w.ln2, x.e, x.n, x.g, y.e, y.n, y.g,
-                                have_pre ? pre[li & 1] : TcPreRows(), next, next.pk ? pre[(li + 1) & 1] : TcPreRows()));
+                                have_pre ? pre[li & 1] : TcPreRows(), next, next.pk ? pre[(li + 1) & 1] : TcPreRows(), dec));
         have_pre = next.pk != nullptr;
+        have_partial = dec.W4 != nullptr;
       } else {
         GNB_TRY(run_core_fp32(ctx, g, w, x, y));
         have_pre = false;
+        have_partial = false;
       }
     }
     x = Feat{y.e, y.n, y.g};

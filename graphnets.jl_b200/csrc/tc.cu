@@ -632,7 +632,7 @@ static int launch_proj(gnb_ctx* ctx, const ProjArgs& a, const char* name, double
 int tc_core_forward(gnb_ctx* ctx, const gnb_graph* g, const TcCorePack* pk, const gnb_block_params& blk,
                     const gnb_ffn_params* ffn, const gnb_ln_params* ln1, const gnb_ln_params* ln2, const float* xe,
                     const float* xn, const float* xg, float* ye, float* yn, float* yg, TcPreRows pre_in, TcNextCore next,
-                    TcPreRows pre_out) {
+                    TcPreRows pre_out, TcDecFuse dec) {
   const int64_t E = g->E, N = g->N, B = g->B;
   int rc = GNB_OK;
   const size_t nparts = (size_t)(g->n_parts > 0 ? g->n_parts : 1);
@@ -671,6 +671,7 @@ int tc_core_forward(gnb_ctx* ctx, const gnb_graph* g, const TcCorePack* pk, cons
     a.b1f = pk->b1f_e; a.b2 = ffn[0].b2; a.eps = ln1[0].eps; a.eps_mode = ln1[0].eps_mode;
     a.add1 = Psr; a.idx1 = g->edge_src; a.ld1 = 2 * H; a.add2 = Psr + H; a.idx2 = g->edge_dst; a.ld2 = 2 * H;
     a.part = g->edge_part; a.Epart = Epart; a.Gpart = Gpart; a.dbg = g_tc_dbg; a.wd = ctx_watch(ctx);
+    a.decW = dec.W4; a.dec_out = dec.partial;      // fused narrow decoder: y_e is not stored (ye may be nullptr)
     // canonical work of the reference's edge update + edge FFN: 24 H^2 flops and
     // 8H bytes of features + 12 B of index per edge
     GNB_TRY(launch_edge5(ctx, a, "tc_edge_core", 24.0 * HH * E, (8.0 * H + 12.0) * E));

@@ -17,8 +17,11 @@ struct TcNextCore {      // what the tail kernel needs to know about the next co
   const gnb_block_params* blk = nullptr;
   const gnb_ln_params* ln1 = nullptr;
 };
+// Fused narrow decoder (model.cu): the edge kernel of the LAST core stores y_e . W4 instead of y_e (tc_edge.cuh, EdgeArgs::decW)
+struct TcDecFuse { const float* W4 = nullptr; float* partial = nullptr; };
 // pre_in.Pue != nullptr: the rows of this core were already produced by the previous core's tail kernel
 int tc_core_forward(gnb_ctx* ctx, const gnb_graph* g, const TcCorePack* pk, const gnb_block_params& blk,
                     const gnb_ffn_params* ffn, const gnb_ln_params* ln1, const gnb_ln_params* ln2,
                     const float* xe, const float* xn, const float* xg, float* ye, float* yn, float* yg,
-                    TcPreRows pre_in = TcPreRows(), TcNextCore next = TcNextCore(), TcPreRows pre_out = TcPreRows());
+                    TcPreRows pre_in = TcPreRows(), TcNextCore next = TcNextCore(), TcPreRows pre_out = TcPreRows(),
+                    TcDecFuse dec = TcDecFuse());

@@ -37,10 +37,15 @@ constexpr int E_OFF_STG = E_OFF_W + NWS * HALF_BYTES;        // 64 KB: [4 column
 constexpr int E_OFF_MISC = E_OFF_STG + 65536;
 constexpr int E_MISC = 512 * 4 + 128 * 4 + 40 * 8 + 16;      // (29 barriers used)      // b1f[512], b2[128], barriers[40], tmem slot
 constexpr int E_SMEM = E_OFF_MISC + E_MISC + 1024;
-constexpr int E_WARPS = 16;
-constexpr int W_MMA = 14, W_LOAD = 15;
+#ifndef GNB_OUT_WARPS
+#define GNB_OUT_WARPS 6
+#endif
+constexpr int OUT_WARPS = GNB_OUT_WARPS;      // 6: 16 warps x 128 registers;  8: 18 warps x 96 registers (one slice per OUT warp)
+static_assert(OUT_WARPS == 6 || OUT_WARPS == 8, "OUT warps: 4-7 + 12,13 or 4-7 + 12-15");
+constexpr int E_WARPS = 10 + OUT_WARPS;
+constexpr int W_MMA = 8 + OUT_WARPS, W_LOAD = 9 + OUT_WARPS;
 constexpr int OUT_ROWS = GNB_PART_ROWS;      // rows per OUT slice == cut of the partial-row index (lower.cu)
-constexpr int OUT_SLICES = TM / OUT_ROWS, OUT_WARPS = 6;
+constexpr int OUT_SLICES = TM / OUT_ROWS;
 static_assert(OUT_ROWS == 16 && OUT_SLICES == 8, "8 slices of 16 rows per tile");
 constexpr int E_THREADS = E_WARPS * 32;
 enum { EB_WFULL = 0, EB_WEMPTY = 5, EB_AFULL = 10, EB_AEMPTY = 12, EB_HIDFULL = 14, EB_HSREADY = 16, EB_OUTDONE = 18,
@@ -82,33 +87,6 @@ constexpr int B_BLK = 2, B_FIRSTD = 2;
 #define EDBG(k) do { } while (0)
 #endif
 
-// sum over the 32 lanes of 8 per-lane values at once (transposed butterfly: 9 + 8 shuffles instead of 40);
-// every lane returns with all 8 totals
-__device__ __forceinline__ void warp_sum8(float (&v)[8], int lane) {
-  const bool h16 = lane & 16, h8 = lane & 8, h4 = lane & 4;
-  float w[4], z[2];
-#pragma unroll
-  for (int j = 0; j < 4; j++) {
-    const float send = h16 ? v[j] : v[j + 4], keep = h16 ? v[j + 4] : v[j];
-    w[j] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
-  }
-#pragma unroll
-  for (int j = 0; j < 2; j++) {
-    const float send = h8 ? w[j] : w[j + 2], keep = h8 ? w[j + 2] : w[j];
-    z[j] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
-  }
-  float t;
-  {
-    const float send = h4 ? z[0] : z[1], keep = h4 ? z[1] : z[0];
-    t = keep + __shfl_xor_sync(0xffffffffu, send, 4);
-  }
-  t += __shfl_xor_sync(0xffffffffu, t, 2);
-  t += __shfl_xor_sync(0xffffffffu, t, 1);
-  // lane holds the total of row 4*bit4 + 2*bit3 + bit2
-#pragma unroll
-  for (int j = 0; j < 8; j++) v[j] = __shfl_sync(0xffffffffu, t, ((j & 4) ? 16 : 0) | ((j & 2) ? 8 : 0) | ((j & 1) ? 4 : 0));
-}
-
 // packed fp32x2 (FADD2 / FMUL2 / FFMA2 on sm_100): two lanes of a float4 per instruction
 __device__ __forceinline__ float4 add4(float4 a, float4 b) {
   const float2 lo = __fadd2_rn(make_float2(a.x, a.y), make_float2(b.x, b.y)), hi = __fadd2_rn(make_float2(a.z, a.w), make_float2(b.z, b.w));
@@ -123,11 +101,6 @@ __device__ __forceinline__ float4 muls4(float4 a, float s) {
   const float2 ss = make_float2(s, s);
   const float2 lo = __fmul2_rn(make_float2(a.x, a.y), ss), hi = __fmul2_rn(make_float2(a.z, a.w), ss);
   return make_float4(lo.x, lo.y, hi.x, hi.y);
-}
-__device__ __forceinline__ float sumsq4(float4 a) {
-  float2 t = __fmul2_rn(make_float2(a.x, a.y), make_float2(a.x, a.y));
-  t = __ffma2_rn(make_float2(a.z, a.w), make_float2(a.z, a.w), t);
-  return t.x + t.y;
 }
 // 1 / LayerNorm denominator without branches: e_add = eps^2 | 0 | eps and plus = 0 | eps | 0 for the three conventions
 __device__ __forceinline__ float rstd_nb(float var, float e_add, float plus) {
@@ -144,7 +117,34 @@ __device__ __forceinline__ float4 ld_stream(const float* p) {   // read-once dat
 
 // CL2: the two CTAs of a cluster (an SM pair) run one 256-row MMA stream (cta_group::2): each CTA holds half of every weight
 // block (N split) - half the weight bytes per SM and a ring twice as deep in blocks - and its own 128-row tile otherwise.
-template <bool CL2>
+// sum over the 32 lanes of 16 per-lane values at once (transposed butterfly: 8 + 4 + 2 + 1 + 1 shuffles instead of 80); lane l
+// returns the total of value 8 b4 + 4 b3 + 2 b2 + b1 (b_i = bit i of l; both lanes of a pair hold the same total)
+__device__ __forceinline__ float warp_sum16(const float (&v)[16], int lane) {
+  const bool h16 = lane & 16, h8 = lane & 8, h4 = lane & 4, h2 = lane & 2;
+  float w[8], z[4], y2[2];
+#pragma unroll
+  for (int j = 0; j < 8; j++) {
+    const float send = h16 ? v[j] : v[j + 8], keep = h16 ? v[j + 8] : v[j];
+    w[j] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+  }
+#pragma unroll
+  for (int j = 0; j < 4; j++) {
+    const float send = h8 ? w[j] : w[j + 4], keep = h8 ? w[j + 4] : w[j];
+    z[j] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+  }
+#pragma unroll
+  for (int j = 0; j < 2; j++) {
+    const float send = h4 ? z[j] : z[j + 2], keep = h4 ? z[j + 2] : z[j];
+    y2[j] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+  }
+  const float send = h2 ? y2[0] : y2[1], keep = h2 ? y2[1] : y2[0];
+  float t = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+  t += __shfl_xor_sync(0xffffffffu, t, 1);
+  return t;
+}
+
+// DEC: fused narrow decoder - the OUT warps do not store y but y . decW (EdgeArgs::decW)
+template <bool CL2, bool DEC>
 __global__ void __launch_bounds__(E_THREADS, 1) k_edge5(const EdgeArgs a) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
@@ -383,12 +383,19 @@ __global__ void __launch_bounds__(E_THREADS, 1) k_edge5(const EdgeArgs a) {
     // the OUT warps to drain this warp's two slices of the previous tile; with the first two chunks of the next pass converted
     // before that wait, the MMA warp keeps four blocks of work (dn0 up2 dn1 up3) while this warp is blocked.  (Converting all
     // four chunks first and staging last - round 1 - let the slowest quadrant gate every pass: 15 k cycles per tile.)
+#ifndef GNB_DRAIN_PIPELINED      /* default: all four chunks of a pass, then its staging copy (measured faster: 0.86 vs 0.89 ms) */
+    for (tl = 0; (int)tl < npass && !wd_dead; tl++) {
+      const uint32_t st = tl & 1, uph = (tl >> 1) & 1;
+      EDBG(0);
+      conv(0); conv(1); conv(2); conv(3);
+#else
     if (npass > 0 && !wd_dead) { tl = 0; EDBG(0); conv(0); conv(1); }
     for (tl = 0; (int)tl < npass && !wd_dead; tl++) {
       const uint32_t st = tl & 1, uph = (tl >> 1) & 1;
       conv(2);
       conv(3);
       if ((int)tl + 1 < npass) { conv(0); conv(1); }
+#endif
       // ---------------- finished accumulator -> staging tile (row r = this thread; 4 column groups of 32 fp32)
       mbar_wait(BAR(EB_OUTDONE + st), uph);
       EDBG(9);
@@ -574,6 +581,95 @@ __global__ void __launch_bounds__(E_THREADS, 1) k_edge5(const EdgeArgs a) {
         pid = __ldg(a.part + row0 + lane);
       }
     };
+#ifndef GNB_OUT_ROLLING      /* default: 4-row groups in a compact loop (a fully unrolled 16-row window - below - costs more in instruction-cache misses than it saves: 0.96 vs 0.86 ms per launch) */
+    // Four rows of loads are in flight per warp.  The window runs ACROSS slices: the gather indices of this warp's next slice are
+    // fetched at the start of the current one and its first group is issued from the last group of the current one, so a slice
+    // starts with its loads already in flight (without this every slice paid two full load latencies before its first row).
+    float4 wdec[4];      // DEC: rows 4 lane .. 4 lane + 3 of decW (4 outputs each)
+    if (DEC) {
+#pragma unroll
+      for (int c = 0; c < 4; c++) wdec[c] = __ldg(reinterpret_cast<const float4*>(a.decW) + 4 * lane + c);
+    }
+    float4 xa[4], pa[4], pb[4];
+    auto issue1 = [&](int u, int64_t rb, int src_i1, int src_i2, int i) {
+      const int i1 = __shfl_sync(0xffffffffu, src_i1, i), i2 = __shfl_sync(0xffffffffu, src_i2, i);
+      int64_t r = rb + i;
+      r = r < a.R ? r : a.R - 1;
+      xa[u] = ld_stream(xbase + (size_t)r * H);                       // second and last read of x: L2 hit
+      pa[u] = __ldg(reinterpret_cast<const float4*>(base1 + (size_t)i1 * a.ld1));
+      pb[u] = __ldg(reinterpret_cast<const float4*>(base2 + (size_t)i2 * a.ld2));
+    };
+    int c_i1 = 0, c_i2 = 0, c_pid = -1, n_i1 = 0, n_i2 = 0, n_pid = -1;
+    if (ow < total) {
+      load_attr(slice_row0(ow), c_i1, c_i2, c_pid);
+#pragma unroll
+      for (int u = 0; u < 4; u++) issue1(u, slice_row0(ow), c_i1, c_i2, u);
+    }
+    for (int k = ow; k < total && !wd_dead; k += OUT_WARPS) {
+      const uint32_t tl = (uint32_t)k >> 3;
+      const int sl = k & (OUT_SLICES - 1);
+      const uint32_t s_lane = s_lane0 + (uint32_t)((OUT_ROWS * sl) * 128);
+      const int64_t row0 = slice_row0(k);
+      const int64_t left = a.R - row0;
+      const int rows = left < 0 ? 0 : (left > OUT_ROWS ? OUT_ROWS : (int)left);
+      const bool has_next = k + OUT_WARPS < total;      // warp-uniform
+      const int64_t nrow0 = slice_row0(has_next ? k + OUT_WARPS : k);
+      if (has_next) load_attr(nrow0, n_i1, n_i2, n_pid);
+      const int nxt = __shfl_down_sync(0xffffffffu, c_pid, 1);
+      const uint32_t endmask = __ballot_sync(0xffffffffu, lane < rows && (lane == rows - 1 || nxt != c_pid));
+      int pid = __shfl_sync(0xffffffffu, c_pid, 0);
+      EDBG(0);
+      mbar_wait(BAR(EB_STGFULL + sl), tl & 1);
+      EDBG(1);
+      float4 acc = f4zero();
+#pragma unroll 1
+      for (int i0 = 0; i0 < OUT_ROWS; i0 += 4) {
+        float4 d[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+          const int i = i0 + u;
+          d[u] = *reinterpret_cast<const float4*>(sm + s_lane + i * 128 + ((s_chunk ^ (uint32_t)(i & 7)) << 4));
+        }
+        // where the refills of this group come from: the next group of this slice or the first group of the next slice
+        const bool cur = i0 + 4 < OUT_ROWS;
+        const int64_t rb = cur ? row0 : nrow0;
+        const int s1 = cur ? c_i1 : n_i1, s2 = cur ? c_i2 : n_i2;
+        const int ib = cur ? i0 + 4 : 0;
+        const bool refill = cur || has_next;      // warp-uniform
+        float od[16];      // DEC: this lane's share of the 4 decoder outputs of the 4 rows of the group
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+          const int i = i0 + u;
+          const float4 g = add4(pa[u], pb[u]);
+          const float4 y = add4(add4(add4(xa[u], g), d[u]), b2v);
+          if (DEC) {
+            od[4 * u + 0] = fmaf(y.w, wdec[3].x, fmaf(y.z, wdec[2].x, fmaf(y.y, wdec[1].x, y.x * wdec[0].x)));
+            od[4 * u + 1] = fmaf(y.w, wdec[3].y, fmaf(y.z, wdec[2].y, fmaf(y.y, wdec[1].y, y.x * wdec[0].y)));
+            od[4 * u + 2] = fmaf(y.w, wdec[3].z, fmaf(y.z, wdec[2].z, fmaf(y.y, wdec[1].z, y.x * wdec[0].z)));
+            od[4 * u + 3] = fmaf(y.w, wdec[3].w, fmaf(y.z, wdec[2].w, fmaf(y.y, wdec[1].w, y.x * wdec[0].w)));
+          } else if (i < rows) {
+            __stcs(reinterpret_cast<float4*>(a.y + (size_t)(row0 + i) * H) + lane, y);
+          }
+          acc = add4(acc, g);
+          const bool fl = (endmask >> i) & 1u;
+          if (fl) *(reinterpret_cast<float4*>(a.Gpart + (size_t)pid * H) + lane) = acc;
+          acc.x = fl ? 0.f : acc.x; acc.y = fl ? 0.f : acc.y; acc.z = fl ? 0.f : acc.z; acc.w = fl ? 0.f : acc.w;
+          pid += fl ? 1 : 0;
+          if (refill) issue1(u, rb, s1, s2, ib + u);
+        }
+        if (DEC) {
+          // 16 totals (4 rows x 4 outputs) land on the even lanes: value 8 b4 + 4 b3 + 2 b2 + b1 = 4 u + j, i.e. 16 consecutive floats
+          const float t = warp_sum16(od, lane);
+          const int vi = lane >> 1;
+          if ((lane & 1) == 0 && i0 + (vi >> 2) < rows) a.dec_out[(size_t)(row0 + i0) * 4 + vi] = t;
+        }
+      }
+      ARRIVE_LOCAL(EB_STGEMPTY + sl);
+      EDBG(2);
+      c_i1 = n_i1; c_i2 = n_i2; c_pid = n_pid;
+    }
+#else
+    static_assert(!DEC, "the rolling-window variant does not implement the fused decoder");
     float4 xa[DEPTH], pa[DEPTH], pb[DEPTH];
     auto issue1 = [&](int u, int64_t row0, int src_i1, int src_i2, int i) {
       const int i1 = __shfl_sync(0xffffffffu, src_i1, i), i2 = __shfl_sync(0xffffffffu, src_i2, i);
@@ -626,6 +722,7 @@ __global__ void __launch_bounds__(E_THREADS, 1) k_edge5(const EdgeArgs a) {
       EDBG(2);
       c_i1 = n_i1; c_i2 = n_i2; c_pid = n_pid;
     }
+  #endif
   }
   tc_fence_before();
   __syncthreads();
@@ -647,9 +744,12 @@ int launch_edge5(gnb_ctx* ctx, const EdgeArgs& a, const char* name, double flops
   const char* pair_env = getenv("GNB_EDGE_CTA_PAIR");
   const int use_cl2 = pair_env ? atoi(pair_env) : 1;
   if (ctx_first(ctx, ONCE_EDGE5)) {
-    GNB_CUDA(cudaFuncSetAttribute(k_edge5<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, E_SMEM));
-    GNB_CUDA(cudaFuncSetAttribute(k_edge5<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, E_SMEM));
+    GNB_CUDA(cudaFuncSetAttribute(k_edge5<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, E_SMEM));
+    GNB_CUDA(cudaFuncSetAttribute(k_edge5<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, E_SMEM));
+    GNB_CUDA(cudaFuncSetAttribute(k_edge5<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, E_SMEM));
+    GNB_CUDA(cudaFuncSetAttribute(k_edge5<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, E_SMEM));
   }
+  const bool dec = a.decW != nullptr;
   Launch L(ctx, name, bytes, flops);
   if (use_cl2 && ctx->sm_count >= 2) {
     const int pairs = (a.num_tiles + 1) / 2;
@@ -661,10 +761,12 @@ int launch_edge5(gnb_ctx* ctx, const EdgeArgs& a, const char* name, double flops
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
-    GNB_CUDA(cudaLaunchKernelEx(&cfg, k_edge5<true>, a));
+    if (dec) GNB_CUDA(cudaLaunchKernelEx(&cfg, k_edge5<true, true>, a));
+    else GNB_CUDA(cudaLaunchKernelEx(&cfg, k_edge5<true, false>, a));
   } else {
     const int grid = a.num_tiles < ctx->sm_count ? a.num_tiles : ctx->sm_count;
-    k_edge5<false><<<grid, E_THREADS, E_SMEM, ctx->stream>>>(a);
+    if (dec) k_edge5<false, true><<<grid, E_THREADS, E_SMEM, ctx->stream>>>(a);
+    else k_edge5<false, false><<<grid, E_THREADS, E_SMEM, ctx->stream>>>(a);
   }
   GNB_CUDA(cudaGetLastError());
   return GNB_OK;

@@ -21,6 +21,11 @@ struct EdgeArgs {
   float* Gpart;          // out [n_parts][128] partial sums of the gathered addends
   unsigned long long* dbg;
   WatchArgs wd;          // kernel watchdog (tc_ptx.cuh)
+  // Fused narrow decoder (last core of a model followed by a GNBlock with out_e <= 4, src/gnblock.jl:65): instead of storing y
+  // the kernel stores dec_out[r][0..4) = y[r] . decW  (the edge-feature rows of the decoder's edge Dense, fp32, padded to 4
+  // outputs) - y itself is consumed by nothing else, so 2 x R x 512 B of HBM traffic and one full streaming pass disappear.
+  const float* decW;     // [128][4] k-major, nullptr: store y as usual
+  float* dec_out;        // [R][4]
 };
 
 int launch_edge5(gnb_ctx* ctx, const EdgeArgs& a, const char* name, double flops, double bytes);

@@ -141,3 +141,25 @@ def test_cfg3_shape_steady_state(gn):
     assert "tc_ffn384" in prof, list(prof)
     worst = assert_wide_parity(got, layers, w, "cfg3 B=180")
     assert worst <= BF16_TOL, worst
+
+
+def test_fused_narrow_decoder_equals_unfused(gn):
+    """The last core's edge kernel hands y_e . W_dec to the narrow decoder instead of storing y_e (csrc/tc_edge.cuh, decW):
+    same result as the unfused path (GNB_FUSE_DECODER=0) up to fp32 summation order, both within tolerance of the oracle;
+    ragged tiles and variable-size graphs included."""
+    rng = np.random.default_rng(31)
+    adjs = _variable_graphs(rng, 150)
+    layers, w = _stack128(rng, adjs)
+    res = {}
+    for mode in ("1", "0"):
+        os.environ["GNB_FUSE_DECODER"] = mode
+        try:
+            _, got, prof = _run(gn, layers, w, "auto")
+        finally:
+            os.environ.pop("GNB_FUSE_DECODER", None)
+        res[mode] = (got, prof)
+    assert "dec_finish" in res["1"][1] and "dec_finish" not in res["0"][1], (list(res["1"][1]), list(res["0"][1]))
+    for a, b in zip(res["1"][0], res["0"][0]):
+        assert np.abs(a - b).max() <= 1e-5 * np.abs(b).max(), "fused and unfused decoder differ by more than fp32 rounding"
+    _, ref = run_oracle(layers, w)
+    assert_parity(res["1"][0], ref, BF16_TOL, "fused decoder, variable graphs")

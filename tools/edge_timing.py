@@ -29,7 +29,8 @@ n = 148 * 18 * 32
 buf = (C.c_ulonglong * n)()
 assert gn.lib.gnb_debug_tc_timing(buf, n) == 0
 t = np.array(buf[:], dtype=np.int64).reshape(148, 18, 32)
-MMA, DRAIN, LN, OUT = 14, [8, 9, 10, 11], [0, 1, 2, 3], [4, 5, 6, 7, 12, 13]
+NOUT = 8 if os.environ.get("GNB_LIB_VARIANT", "").endswith("18") else 6
+MMA, DRAIN, LN, OUT = 8 + NOUT, [8, 9, 10, 11], [0, 1, 2, 3], [4, 5, 6, 7] + list(range(12, 8 + NOUT))
 
 
 def show(name, warps, slots, labels):
