@@ -6,13 +6,13 @@ so import it through the repo-root shim:  `import graphnets_b200 as gn`.
 from ._lib import lib, LIB_PATH, GnbError
 from .engine import get_engine
 from .api import (GNData, GNGraphBatch, Padded, batch, batch_compact, batch_coo, pack_adjacency_bits, unbatch, checks, efview, nfview, gfview,
-                  flatunpaddednf, flatunpaddedef, collapsef, unpaddedcollapsedef, flatunpaddedcollapsedef)
+                  flatunpaddednf, flatunpaddedef, logitcrossentropy, collapsef, unpaddedcollapsedef, flatunpaddedcollapsedef)
 from .layers import (GNBlock, GNCore, GNCoreList, GNSequential, GNFeedForward, GNGraphNorm, Dense, Chain,
                      LayerNorm, Dropout, set_precision, get_precision)
 from .shard import shard_ranges, shard_batch
 
 __all__ = [
     "GNGraphBatch", "batch", "batch_compact", "batch_coo", "pack_adjacency_bits", "unbatch", "GNBlock", "GNCore", "GNCoreList", "GNSequential", "efview", "nfview",
-    "gfview", "flatunpaddednf", "flatunpaddedef", "collapsef", "unpaddedcollapsedef", "flatunpaddedcollapsedef",
+    "gfview", "flatunpaddednf", "flatunpaddedef", "logitcrossentropy", "collapsef", "unpaddedcollapsedef", "flatunpaddedcollapsedef",
     "GNData", "Padded", "set_precision", "get_precision", "get_engine", "shard_ranges", "shard_batch",
 ]

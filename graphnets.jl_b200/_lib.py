@@ -76,6 +76,9 @@ SIGNATURES = {
 }
 
 
+SIGNATURES["gnb_logit_cross_entropy"] = (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_void_p, C.c_void_p])
+
+
 class ProfEntry(C.Structure):
     _fields_ = [("name", C.c_char * 48), ("launches", C.c_int64), ("ms", C.c_double),
                 ("alg_bytes", C.c_double), ("alg_flops", C.c_double)]

@@ -479,6 +479,22 @@ def flatunpaddedef(t):
     return _fields(t).ef.compact.t()
 
 
+# ----------------------------------------------------------------------------- loss over the compact views
+def logitcrossentropy(yhat, y):
+    """Flux.logitcrossentropy(flatunpaddednf(yhat_batch), flatunpaddednf(target_batch)) as in the reference's training example
+    (examples/sort/sort.jl:76-78).  `yhat`, `y`: `Padded` features (or compact `[rows][D]` device tensors) of the same shape;
+    returns a 0-dim device tensor: mean over the real rows of -sum_d y * logsoftmax(yhat)."""
+    a = yhat.compact if isinstance(yhat, Padded) else yhat
+    b = y.compact if isinstance(y, Padded) else y
+    assert tuple(a.shape) == tuple(b.shape) and a.dim() == 2, "logits / targets must be compact [rows][D] of equal shape"
+    a, b = a.contiguous(), b.to(a.device, torch.float32).contiguous()
+    eng = yhat.graphs.engine if isinstance(yhat, Padded) else get_engine(a.device)
+    eng.bind_stream()
+    out = torch.empty((), dtype=torch.float32, device=a.device)
+    check(lib.gnb_logit_cross_entropy(eng.ctx, _ptr(a), _ptr(b), int(a.shape[1]), int(a.shape[0]), _ptr(out), None))
+    return out
+
+
 # ----------------------------------------------------------------------------- edge collapsing
 def collapsef(t):
     """collapsef (src/gngraphbatch.jl:83-85): (DE, PN(PN+1)/2, B), mean of slots (i,j) and (j,i)."""

@@ -162,6 +162,15 @@ int gnb_corelist_forward(gnb_ctx*, const gnb_graph*, const gnb_core_params* core
                          const float* ef, const float* nf, const float* gf,
                          float* out_ef, float* out_nf, float* out_gf, int precision);
 
+/* ---------------------------------------------------------------- loss ---------------- */
+/* Flux.logitcrossentropy over the compact views, as the reference's training example computes it
+ * (examples/sort/sort.jl:76-78: logitcrossentropy(flatunpaddednf(y), flatunpaddednf(targets)), likewise for the edges;
+ * src/views.jl:80-98):  *loss = mean over the R rows of  -sum_d targets[r][d] * logsoftmax(logits[r])[d].
+ * logits / targets: compact (D, R) device matrices (feature dim contiguous); loss: DEVICE float; per_row: optional device
+ * [R] (NULL: not written).  Deterministic (fixed-order sums). */
+int gnb_logit_cross_entropy(gnb_ctx*, const float* logits, const float* targets, int D, int64_t R,
+                            float* loss, float* per_row);
+
 #ifdef __cplusplus
 }
 #endif

