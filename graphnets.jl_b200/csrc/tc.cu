@@ -50,9 +50,13 @@ struct ProjArgs {
   unsigned int dbg_drain_delay_ns;   // test hook: stall the drain warps per tile (gnb_ctx::dbg_proj_drain_delay_ns)
 };
 
-// smem: A[2] (32 KB each) | W[NBLK] (32 KB each, resident) | barriers
+// smem: A[2] (32 KB each) | W[2 NBLK] (32 KB each, resident: NBLK bf16 "hi" blocks, then their NBLK "lo" blocks) | barriers
+// Weights are split  W = hi + lo  (hi = bf16(W), lo = bf16(W - hi)) and every output block is D = A.hi + A.lo: the rounding
+// error of a bf16 WEIGHT is the same for every row, so it does not average out in the sums over hundreds of edges / nodes that
+// feed the graph update - it was the dominant (coherent) error of the graph features (tools/dec_sensitivity.py).  The rounding
+// of the ACTIVATIONS is independent per row and stays; node-level kernels are cheap (N rows), so the second MMA is free.
 __host__ __device__ constexpr int pj_off_w() { return 2 * BLK_BYTES; }
-__host__ __device__ constexpr int pj_off_misc(int nblk) { return (2 + nblk) * BLK_BYTES; }
+__host__ __device__ constexpr int pj_off_misc(int nblk) { return (2 + 2 * nblk) * BLK_BYTES; }
 __host__ __device__ constexpr int pj_smem(int nblk) { return pj_off_misc(nblk) + 256 + 1024; }
 // Barrier protocol (every waiter sits inside the back-pressure loop of the barrier it waits on, so a 1-bit phase parity can
 // never alias - no producer can complete phase n + 1 of a barrier before every waiter has observed phase n):
@@ -105,9 +109,10 @@ __global__ void __launch_bounds__(PJ_THREADS, NBLK == 1 ? 2 : 1) k_tc_proj(const
 
   if (warp == 9) {
     if (elect_one()) {
-      for (int b = 0; b < NBLK; b++) {
-        mbar_expect_tx(BAR(PB_WFULL + b), BLK_BYTES);
+      for (int b = 0; b < NBLK; b++) {      // barrier b: hi and lo block of output block b
+        mbar_expect_tx(BAR(PB_WFULL + b), 2 * BLK_BYTES);
         bulk_g2s(sW + b * BLK_BYTES, reinterpret_cast<const uint8_t*>(a.wpack) + (size_t)b * BLK_BYTES, BLK_BYTES, BAR(PB_WFULL + b));
+        bulk_g2s(sW + (NBLK + b) * BLK_BYTES, reinterpret_cast<const uint8_t*>(a.wpack) + (size_t)(NBLK + b) * BLK_BYTES, BLK_BYTES, BAR(PB_WFULL + b));
       }
     }
     __syncwarp();
@@ -124,8 +129,9 @@ __global__ void __launch_bounds__(PJ_THREADS, NBLK == 1 ? 2 : 1) k_tc_proj(const
       if (elect_one()) {
         const uint64_t adesc = umma_desc(base + st * BLK_BYTES);
         for (int b = 0; b < NBLK; b++) {
-          const uint64_t w = umma_desc(sW + b * BLK_BYTES);
+          const uint64_t w = umma_desc(sW + b * BLK_BYTES), wl = umma_desc(sW + (NBLK + b) * BLK_BYTES);
           issue_ss(tmem + (st * NBLK + b) * 128, adesc, w, w + (KB_BYTES >> 4), false);
+          issue_ss(tmem + (st * NBLK + b) * 128, adesc, wl, wl + (KB_BYTES >> 4), true);
         }
         tc_commit(BAR(PB_AEMPTY + st));
         tc_commit(BAR(PB_OUTDONE + st));
@@ -284,7 +290,8 @@ __global__ void __launch_bounds__(PJ_THREADS, NBLK == 1 ? 2 : 1) k_tc_proj(const
 // Node aggregate + its projection in one pass (replaces round 1's tc_agg + tc_agg_proj launches):
 //   P_agg[v] = W_na agg_v,   agg_v = W_ee' (sum_{e->v} ê_e) + sum_{e->v} (P_s[src] + P_r'[dst])          (src/nodefninput.jl:3)
 //            = (sum ê) F + (sum G) W_na            F = W_ee' W_na folded (fp32) when the model is packed
-// A = [ bf16(sum of the node's E_part rows) | bf16(sum of its G_part rows) ]  (K = 256), one 128 x 128 accumulator.
+// A = [ bf16(sum of the node's E_part rows) | bf16(sum of its G_part rows) ]  (K = 256), one 128 x 128 accumulator; the weights
+// are split hi + lo like k_tc_proj's (4 resident blocks), so there is room for ONE A stage only.
 // agg itself is never materialised: the graph update only needs sum_v agg_v, which by linearity is
 // (sum_v sum ê) W_ee' + sum_v sum G - so the producers also emit the ordered sums of both operands per (16-node block,
 // graph) run (SE_part, SG_part; index node_gpart) and k_graph_post finishes them in fp32.
@@ -301,13 +308,14 @@ struct Agg2Args {
   float* out;                     // out [R][H]  P_agg
   int64_t R;
   int num_tiles;
-  const __nv_bfloat16* wpack;     // 2 blocks: F, W_na
+  const __nv_bfloat16* wpack;     // 4 blocks: F hi, W_na hi, F lo, W_na lo (hi / lo weight split, see k_tc_proj)
   WatchArgs wd;
 };
 constexpr int AG_THREADS = 14 * 32;
 constexpr int AG_STAGE = 2 * BLK_BYTES;                      // A0 | A1
-constexpr int AG_OFF_W = 2 * AG_STAGE;
-constexpr int AG_OFF_MISC = AG_OFF_W + 2 * BLK_BYTES;
+constexpr int AG_NSTAGE = 1;                                 // one A stage: the hi / lo weight split (k_tc_proj) needs 4 resident blocks
+constexpr int AG_OFF_W = AG_NSTAGE * AG_STAGE;
+constexpr int AG_OFF_MISC = AG_OFF_W + 4 * BLK_BYTES;
 constexpr int AG_SMEM = AG_OFF_MISC + 256 + 1024;
 enum { AB_WFULL = 0, AB_AFULL = 1, AB_AEMPTY = 3, AB_OUTDONE = 5, AB_ACCFREE = 7 };
 
@@ -326,10 +334,8 @@ __global__ void __launch_bounds__(AG_THREADS, 1) k_tc_agg2(const Agg2Args a) {
 #define mbar_wait(b, p) mbar_wait_w((b), (p), wd_dead, a.wd)
   if (tid == 0) {
     mbar_init(BAR(AB_WFULL), 1);
-    for (int s = 0; s < 2; s++) {
-      mbar_init(BAR(AB_AFULL + s), 8); mbar_init(BAR(AB_AEMPTY + s), 1);
-      mbar_init(BAR(AB_OUTDONE + s), 1); mbar_init(BAR(AB_ACCFREE + s), 4);
-    }
+    mbar_init(BAR(AB_AFULL), 8); mbar_init(BAR(AB_AEMPTY), 1);
+    for (int s = 0; s < 2; s++) { mbar_init(BAR(AB_OUTDONE + s), 1); mbar_init(BAR(AB_ACCFREE + s), 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 12) {
@@ -343,25 +349,27 @@ __global__ void __launch_bounds__(AG_THREADS, 1) k_tc_agg2(const Agg2Args a) {
 
   if (warp == 13) {
     if (elect_one()) {
-      mbar_expect_tx(BAR(AB_WFULL), 2 * BLK_BYTES);
-      bulk_g2s(sW, a.wpack, BLK_BYTES, BAR(AB_WFULL));
-      bulk_g2s(sW + BLK_BYTES, reinterpret_cast<const uint8_t*>(a.wpack) + BLK_BYTES, BLK_BYTES, BAR(AB_WFULL));
+      mbar_expect_tx(BAR(AB_WFULL), 4 * BLK_BYTES);      // F hi, W_na hi, F lo, W_na lo
+      for (int b = 0; b < 4; b++)
+        bulk_g2s(sW + b * BLK_BYTES, reinterpret_cast<const uint8_t*>(a.wpack) + (size_t)b * BLK_BYTES, BLK_BYTES, BAR(AB_WFULL));
     }
     __syncwarp();
   } else if (warp == 12) {
     uint32_t tl = 0;
     mbar_wait(BAR(AB_WFULL), 0);
-    const uint64_t w0 = umma_desc(sW), w1 = umma_desc(sW + BLK_BYTES);
+    const uint64_t w0 = umma_desc(sW), w1 = umma_desc(sW + BLK_BYTES), w0l = umma_desc(sW + 2 * BLK_BYTES), w1l = umma_desc(sW + 3 * BLK_BYTES);
+    const uint64_t a0 = umma_desc(base), a1 = umma_desc(base + BLK_BYTES);      // the single A stage
     for (int tile = blockIdx.x; tile < a.num_tiles && !wd_dead; tile += gridDim.x, tl++) {
-      const uint32_t st = tl & 1, ph = (tl >> 1) & 1;
-      mbar_wait(BAR(AB_AFULL + st), ph);
+      const uint32_t st = tl & 1, ph = (tl >> 1) & 1;      // accumulator (TMEM) double buffer
+      mbar_wait(BAR(AB_AFULL), tl & 1);
       mbar_wait(BAR(AB_ACCFREE + st), ph ^ 1);
       tc_fence_after();
       if (elect_one()) {
-        const uint64_t a0 = umma_desc(base + st * AG_STAGE), a1 = umma_desc(base + st * AG_STAGE + BLK_BYTES);
         issue_ss(tmem + st * 128, a0, w0, w0 + (KB_BYTES >> 4), false);
+        issue_ss(tmem + st * 128, a0, w0l, w0l + (KB_BYTES >> 4), true);
         issue_ss(tmem + st * 128, a1, w1, w1 + (KB_BYTES >> 4), true);
-        tc_commit(BAR(AB_AEMPTY + st));
+        issue_ss(tmem + st * 128, a1, w1l, w1l + (KB_BYTES >> 4), true);
+        tc_commit(BAR(AB_AEMPTY));
         tc_commit(BAR(AB_OUTDONE + st));
       }
       __syncwarp();
@@ -373,7 +381,6 @@ __global__ void __launch_bounds__(AG_THREADS, 1) k_tc_agg2(const Agg2Args a) {
     const float4* XG = reinterpret_cast<const float4*>(a.Gpart) + lane;
     uint32_t tl = 0;
     for (int tile = blockIdx.x; tile < a.num_tiles && !wd_dead; tile += gridDim.x, tl++) {
-      const uint32_t st = tl & 1, ph = (tl >> 1) & 1;
       const int64_t row0 = (int64_t)tile * TM + 16 * pw;
       const int64_t left = a.R - row0;
       const int rows = left < 0 ? 0 : (left > 16 ? 16 : (int)left);
@@ -386,10 +393,10 @@ __global__ void __launch_bounds__(AG_THREADS, 1) k_tc_agg2(const Agg2Args a) {
       const int nxt = __shfl_down_sync(0xffffffffu, my_gp, 1);
       const uint32_t endmask = __ballot_sync(0xffffffffu, lane < rows && (lane == rows - 1 || nxt != my_gp));
       int gp = __shfl_sync(0xffffffffu, my_gp, 0);
-      uint8_t* A0 = sm + st * AG_STAGE;
+      uint8_t* A0 = sm;
       uint8_t* A1 = A0 + BLK_BYTES;
       float4 accE = f4zero(), accG = f4zero();
-      mbar_wait(BAR(AB_AEMPTY + st), ph ^ 1);
+      mbar_wait(BAR(AB_AEMPTY), (tl & 1) ^ 1);      // the MMAs of the previous tile have read the (single) A stage
 #pragma unroll 1
       for (int i0 = 0; i0 < 16; i0 += 4) {
         // partial rows of consecutive nodes are consecutive in memory (parts are numbered in edge order, edges are
@@ -434,7 +441,7 @@ __global__ void __launch_bounds__(AG_THREADS, 1) k_tc_agg2(const Agg2Args a) {
       }
       fence_async_smem();
       __syncwarp();
-      if (lane == 0) mbar_arrive(BAR(AB_AFULL + st));
+      if (lane == 0) mbar_arrive(BAR(AB_AFULL));
     }
   } else {
     // ===================================================== accumulator drain (TMEM lane quadrant = warp), fragment layout:
@@ -489,16 +496,18 @@ __global__ void k_fold_matmul(const float* __restrict__ A, const float* __restri
 }
 
 // ------------------------------------------------------------------ weight packing
-// dst block (bf16, swizzled smem image): B[n][k] = W[(n0+n) + ldw*(k0+k)] * (gamma ? gamma[k] : 1)
+// dst block (bf16, swizzled smem image): B[n][k] = W[(n0+n) + ldw*(k0+k)] * (gamma ? gamma[k] : 1);  lo: the residual
+// bf16(w - bf16(w)) of the hi / lo weight split
 __global__ void k_pack_block(const float* __restrict__ W, int ldw, int n0, int k0, const float* __restrict__ gamma,
-                             __nv_bfloat16* __restrict__ dst) {
+                             __nv_bfloat16* __restrict__ dst, int lo) {
   int idx = blockIdx.x * blockDim.x + threadIdx.x;   // 128 x 128
   if (idx >= 128 * 128) return;
   int k = idx >> 7, n = idx & 127;
   float w = W[(size_t)(n0 + n) + (size_t)ldw * (k0 + k)];
   if (gamma) w *= gamma[k];
   uint32_t off = sw_off(n, k);
-  dst[off >> 1] = __float2bfloat16_rn(w);
+  const __nv_bfloat16 hi = __float2bfloat16_rn(w);
+  dst[off >> 1] = lo ? __float2bfloat16_rn(w - __bfloat162float(hi)) : hi;
 }
 // out[n] = (b ? b[n] : 0) + sum_k W[(n0+n) + ldw*(k0+k)] * beta[k]     (LayerNorm shift folded into a bias)
 __global__ void k_fold_bias(const float* __restrict__ W, int ldw, int n0, int k0, int K, const float* __restrict__ beta,
@@ -527,7 +536,7 @@ extern "C" int gnb_debug_tc_timing(unsigned long long* out, int n) {
 }
 
 struct TcCorePack {
-  __nv_bfloat16* w = nullptr;   // [proj 2 | agg2: F, W_na | edge 9 | node 9] blocks of 32 KB
+  __nv_bfloat16* w = nullptr;   // [proj: Ps Pr hi, Ps Pr lo | agg2: F W_na hi, F W_na lo | edge 9 | node 9] blocks of 32 KB
   float* f = nullptr;           // folded fp32 vectors: cu_e[128] cu_n[128] b1f_e[512] b1f_n[512]
   const __nv_bfloat16 *w_proj, *w_agg, *w_edge, *w_node;
   float *cu_e, *cu_n, *b1f_e, *b1f_n;
@@ -550,7 +559,7 @@ int tc_core_pack(gnb_ctx* ctx, const gnb_block_params& blk, const gnb_ffn_params
   for (int i = 0; i < 2; i++)
     if (ln1[i].eps != ln2[i].eps || ln1[i].eps_mode != ln2[i].eps_mode) return GNB_OK;
   TcCorePack* p = new TcCorePack();
-  const size_t nblk = 2 + 2 + 9 + 9;
+  const size_t nblk = 4 + 4 + 9 + 9;
   if (cudaMalloc((void**)&p->w, nblk * BLK_BYTES) != cudaSuccess ||
       cudaMalloc((void**)&p->f, (128 + 128 + 512 + 512) * sizeof(float)) != cudaSuccess) {
     cudaGetLastError();
@@ -560,16 +569,18 @@ int tc_core_pack(gnb_ctx* ctx, const gnb_block_params& blk, const gnb_ffn_params
   }
   __nv_bfloat16* w = p->w;
   const size_t BE = BLK_BYTES / 2;   // elements per block
-  p->w_proj = w; p->w_agg = w + 2 * BE; p->w_edge = w + 4 * BE; p->w_node = w + 13 * BE;
+  p->w_proj = w; p->w_agg = w + 4 * BE; p->w_edge = w + 8 * BE; p->w_node = w + 17 * BE;
   p->cu_e = p->f; p->cu_n = p->f + 128; p->b1f_e = p->f + 256; p->b1f_n = p->f + 768;
   cudaStream_t st = ctx->stream;
-  auto pack = [&](const float* W, int ldw, int n0, int k0, const float* gamma, __nv_bfloat16* dst) {
-    k_pack_block<<<64, 256, 0, st>>>(W, ldw, n0, k0, gamma, dst);
+  auto pack = [&](const float* W, int ldw, int n0, int k0, const float* gamma, __nv_bfloat16* dst, int lo = 0) {
+    k_pack_block<<<64, 256, 0, st>>>(W, ldw, n0, k0, gamma, dst, lo);
   };
   // We: (128, 4*128) input rows [e | v_src | v_dst | u]; Wn: (128, 3*128) input rows [agg | v | u]
   const float *g1e = ln1[0].gamma, *g1n = ln1[1].gamma, *b1e = ln1[0].beta, *b1n = ln1[1].beta;
-  pack(blk.We, H, 0, H, g1n, w + 0 * BE);          // P_s
-  pack(blk.We, H, 0, 2 * H, g1n, w + 1 * BE);      // P_r
+  for (int lo = 0; lo < 2; lo++) {
+    pack(blk.We, H, 0, H, g1n, w + (2 * lo + 0) * BE, lo);          // P_s
+    pack(blk.We, H, 0, 2 * H, g1n, w + (2 * lo + 1) * BE, lo);      // P_r
+  }
   // agg2 blocks: F = W_ee' W_na (folded in fp32, then rounded once) and W_na (aggregate rows, no LayerNorm)
   float* Ftmp = nullptr;
   if (cudaMalloc((void**)&Ftmp, (size_t)H * H * sizeof(float)) != cudaSuccess) {
@@ -579,12 +590,14 @@ int tc_core_pack(gnb_ctx* ctx, const gnb_block_params& blk, const gnb_ffn_params
     return GNB_ERR_OOM;
   }
   k_fold_matmul<<<H, H, 0, st>>>(blk.We, blk.Wn, g1e, Ftmp);
-  pack(Ftmp, H, 0, 0, nullptr, w + 2 * BE);
-  pack(blk.Wn, H, 0, 0, nullptr, w + 3 * BE);
+  for (int lo = 0; lo < 2; lo++) {
+    pack(Ftmp, H, 0, 0, nullptr, w + (4 + 2 * lo) * BE, lo);
+    pack(blk.Wn, H, 0, 0, nullptr, w + (5 + 2 * lo) * BE, lo);
+  }
   // fused kernels: block order documented at k_core
   // both fused kernels (tc_edge.cu) index the blocks as  W1_0 W_blk W2_0 W1_1 W2_1 W1_2 W2_2 W1_3 W2_3
   for (int kind = 0; kind < 2; kind++) {
-    __nv_bfloat16* dst = w + (kind == 0 ? 4 : 13) * BE;
+    __nv_bfloat16* dst = w + (kind == 0 ? 8 : 17) * BE;
     for (int c = 0; c < 4; c++) {
       const int i1 = c == 0 ? 0 : 2 * c + 1;      // W1_c
       const int i2 = 2 * c + 2;                   // W2_c
