@@ -39,7 +39,8 @@ struct ProjArgs {
   const float* addend;            // optional [*][H], added to output columns [add_col0, add_col0 + H)
   const int32_t* addend_idx;      // row of `addend` per output row (nullptr: the row itself)
   int add_col0;
-  float* out;                     // [R][nblk*H]
+  float* out;                     // [R][nblk*H] fp32, or (out_bf16) the same matrix in bf16
+  int out_bf16;
   int64_t R;
   int num_tiles;
   int nblk;                       // weight blocks (1 or 2)
@@ -272,9 +273,15 @@ __global__ void __launch_bounds__(PJ_THREADS, NBLK == 1 ? 2 : 1) k_tc_proj(const
             v[n] = make_float2(__uint_as_float(d[4 * n + 2 * h2]) + t[h2][n].x, __uint_as_float(d[4 * n + 2 * h2 + 1]) + t[h2][n].y);
           if (stp + 1 < 4 * NBLK) fetch(stp + 1, h2, t[h2]);     // next step's addends fly during this step's stores
           if (r < rows) {
-            float* o = a.out + (size_t)(row0 + r) * ld + 64 * ch + cq;
+            if (a.out_bf16) {      // rows consumed as gathered addends by the fused edge kernel: half the bytes to write and to gather
+              __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(a.out) + (size_t)(row0 + r) * ld + 64 * ch + cq;
 #pragma unroll
-            for (int n = 0; n < 8; n++) *reinterpret_cast<float2*>(o + 8 * n) = v[n];
+              for (int n = 0; n < 8; n++) *reinterpret_cast<uint32_t*>(o + 8 * n) = pack_bf16(v[n].x, v[n].y);
+            } else {
+              float* o = a.out + (size_t)(row0 + r) * ld + 64 * ch + cq;
+#pragma unroll
+              for (int n = 0; n < 8; n++) *reinterpret_cast<float2*>(o + 8 * n) = v[n];
+            }
           }
         }
       }
@@ -651,7 +658,13 @@ int tc_core_forward(gnb_ctx* ctx, const gnb_graph* g, const TcCorePack* pk, cons
   const size_t nparts = (size_t)(g->n_parts > 0 ? g->n_parts : 1);
   float* Pue = pre_in.Pue ? pre_in.Pue : arena_ptr<float>(ctx->arena, (size_t)B * H, &rc);
   float* Pun = pre_in.Pue ? pre_in.Pun : arena_ptr<float>(ctx->arena, (size_t)B * H, &rc);
-  float* Psr = arena_ptr<float>(ctx->arena, (size_t)N * 2 * H, &rc);
+  // P_s | P_r' of the nodes in bf16: the fused edge kernel gathers two of these rows per EDGE, so their size sets its L2 -> SM
+  // traffic and how many rows of loads fit in its registers; the rounding is independent per node and element (it averages out in
+  // every sum, unlike the rounding of a weight - see the hi / lo split of the packed weights)
+  // (GNB_PSR_FP32=1 keeps them in fp32: A/B toggle)
+  static const bool psr_bf16 = getenv("GNB_PSR_FP32") == nullptr || atoi(getenv("GNB_PSR_FP32")) == 0;
+  const size_t psr_es = psr_bf16 ? 2 : 4;
+  uint8_t* Psr = arena_ptr<uint8_t>(ctx->arena, (size_t)N * 2 * H * psr_es, &rc);
   float* Epart = arena_ptr<float>(ctx->arena, nparts * H, &rc);
   float* Gpart = arena_ptr<float>(ctx->arena, nparts * H, &rc);
   float* Pagg = arena_ptr<float>(ctx->arena, (size_t)N * H, &rc);
@@ -673,16 +686,16 @@ int tc_core_forward(gnb_ctx* ctx, const gnb_graph* g, const TcCorePack* pk, cons
   const double HH = (double)H * H;
   {  // node projections P_s | P_r
     ProjArgs a{};
-    a.x = xn; a.out = Psr; a.R = N; a.num_tiles = ceil_div(N, TM); a.nblk = 2; a.wpack = pk->w_proj;
+    a.x = xn; a.out = reinterpret_cast<float*>(Psr); a.out_bf16 = psr_bf16; a.R = N; a.num_tiles = ceil_div(N, TM); a.nblk = 2; a.wpack = pk->w_proj;
     a.addend = Pue; a.addend_idx = g->node_graph; a.add_col0 = H;   // P_r += P_u[graph of the node]
     a.eps = ln1[1].eps; a.eps_mode = ln1[1].eps_mode;
-    GNB_TRY((launch_proj<SRC_LN, 2>(ctx, a, "tc_node_proj", 2.0 * N * 2 * HH, 4.0 * N * 3 * H)));
+    GNB_TRY((launch_proj<SRC_LN, 2>(ctx, a, "tc_node_proj", 2.0 * N * 2 * HH, 4.0 * N * H + (double)psr_es * N * 2 * H)));
   }
   {  // edges: GNBlock edge update + FFN + residual; partial receiver sums of the inputs
     EdgeArgs a{};
     a.x = xe; a.y = ye; a.R = E; a.num_tiles = ceil_div(E, TM); a.wpack = pk->w_edge;
     a.b1f = pk->b1f_e; a.b2 = ffn[0].b2; a.eps = ln1[0].eps; a.eps_mode = ln1[0].eps_mode;
-    a.add1 = Psr; a.idx1 = g->edge_src; a.ld1 = 2 * H; a.add2 = Psr + H; a.idx2 = g->edge_dst; a.ld2 = 2 * H;
+    a.add1 = Psr; a.idx1 = g->edge_src; a.ld1 = 2 * H; a.add2 = Psr + H * psr_es; a.idx2 = g->edge_dst; a.ld2 = 2 * H; a.add_bf16 = psr_bf16;
     a.part = g->edge_part; a.Epart = Epart; a.Gpart = Gpart; a.dbg = g_tc_dbg; a.wd = ctx_watch(ctx);
     a.decW = dec.W4; a.dec_out = dec.partial;      // fused narrow decoder: y_e is not stored (ye may be nullptr)
     // canonical work of the reference's edge update + edge FFN: 24 H^2 flops and
@@ -710,7 +723,7 @@ int tc_core_forward(gnb_ctx* ctx, const gnb_graph* g, const TcCorePack* pk, cons
     EdgeArgs a{};
     a.x = xn; a.y = yn; a.R = N; a.num_tiles = ceil_div(N, TM); a.wpack = pk->w_node;
     a.b1f = pk->b1f_n; a.b2 = ffn[1].b2; a.eps = ln1[1].eps; a.eps_mode = ln1[1].eps_mode;
-    a.add1 = Pagg; a.idx1 = nullptr; a.ld1 = H; a.add2 = Pun; a.idx2 = g->node_graph; a.ld2 = H;
+    a.add1 = Pagg; a.idx1 = nullptr; a.ld1 = H; a.add2 = Pun; a.idx2 = g->node_graph; a.ld2 = H; a.add_bf16 = 0;
     a.part = g->node_gpart; a.Epart = Vpart; a.Gpart = Npart; a.dbg = nullptr; a.wd = ctx_watch(ctx);
     GNB_TRY(launch_edge5(ctx, a, "tc_node_core", 20.0 * HH * N, (8.0 * H + 8.0) * N));
   }

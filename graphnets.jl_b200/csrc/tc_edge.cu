@@ -24,6 +24,7 @@
 #include "tc_ptx.cuh"
 #include "tc_edge.cuh"
 #include <stdlib.h>
+#include <type_traits>
 
 using namespace tcx;
 
@@ -102,6 +103,10 @@ __device__ __forceinline__ float4 muls4(float4 a, float s) {
   const float2 lo = __fmul2_rn(make_float2(a.x, a.y), ss), hi = __fmul2_rn(make_float2(a.z, a.w), ss);
   return make_float4(lo.x, lo.y, hi.x, hi.y);
 }
+// four bf16 (two packed words) -> fp32
+__device__ __forceinline__ float4 bf4(uint2 v) {
+  return make_float4(__uint_as_float(v.x << 16), __uint_as_float(v.x & 0xffff0000u), __uint_as_float(v.y << 16), __uint_as_float(v.y & 0xffff0000u));
+}
 // 1 / LayerNorm denominator without branches: e_add = eps^2 | 0 | eps and plus = 0 | eps | 0 for the three conventions
 __device__ __forceinline__ float rstd_nb(float var, float e_add, float plus) {
   const float t = var + e_add;
@@ -144,7 +149,8 @@ __device__ __forceinline__ float warp_sum16(const float (&v)[16], int lane) {
 }
 
 // DEC: fused narrow decoder - the OUT warps do not store y but y . decW (EdgeArgs::decW)
-template <bool CL2, bool DEC>
+// PBF: the gathered addend rows are bf16 (EdgeArgs::add_bf16: the edges' P_s | P_r'), else fp32 (the nodes' P_agg, P_un)
+template <bool CL2, bool DEC, bool PBF>
 __global__ void __launch_bounds__(E_THREADS, 1) k_edge5(const EdgeArgs a) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
@@ -566,8 +572,10 @@ __global__ void __launch_bounds__(E_THREADS, 1) k_edge5(const EdgeArgs a) {
     const int ow = warp < 8 ? warp - 4 : warp - 8;
     const float4 b2v = *reinterpret_cast<const float4*>(sB2 + 4 * lane);
     const float* xbase = a.x + 4 * lane;
-    const float* base1 = a.add1 + 4 * lane;
-    const float* base2 = a.add2 + 4 * lane;
+    // this lane's 4 columns of a gathered row: 16 B of an fp32 row, 8 B of a bf16 row
+    const uint8_t* base1 = reinterpret_cast<const uint8_t*>(a.add1) + (PBF ? 8 : 16) * lane;
+    const uint8_t* base2 = reinterpret_cast<const uint8_t*>(a.add2) + (PBF ? 8 : 16) * lane;
+    const size_t ldb1 = (size_t)a.ld1 * (PBF ? 2 : 4), ldb2 = (size_t)a.ld2 * (PBF ? 2 : 4);
     const uint32_t s_lane0 = (uint32_t)(E_OFF_STG + (lane >> 3) * 16384);
     const uint32_t s_chunk = (uint32_t)(lane & 7);
     const int total = OUT_SLICES * npass;
@@ -581,7 +589,8 @@ __global__ void __launch_bounds__(E_THREADS, 1) k_edge5(const EdgeArgs a) {
         pid = __ldg(a.part + row0 + lane);
       }
     };
-#ifndef GNB_OUT_ROLLING      /* default: 4-row groups in a compact loop (a fully unrolled 16-row window - below - costs more in instruction-cache misses than it saves: 0.96 vs 0.86 ms per launch) */
+    // (a fully unrolled 16-row rolling window was measured slower than this compact 4-row-group loop: 0.96 vs 0.86 ms per launch,
+    // instruction-cache misses)
     // Four rows of loads are in flight per warp.  The window runs ACROSS slices: the gather indices of this warp's next slice are
     // fetched at the start of the current one and its first group is issued from the last group of the current one, so a slice
     // starts with its loads already in flight (without this every slice paid two full load latencies before its first row).
@@ -590,14 +599,24 @@ __global__ void __launch_bounds__(E_THREADS, 1) k_edge5(const EdgeArgs a) {
 #pragma unroll
       for (int c = 0; c < 4; c++) wdec[c] = __ldg(reinterpret_cast<const float4*>(a.decW) + 4 * lane + c);
     }
-    float4 xa[4], pa[4], pb[4];
+    float4 xa[4];
+    typename std::conditional<PBF, uint2, float4>::type pa[4], pb[4];
     auto issue1 = [&](int u, int64_t rb, int src_i1, int src_i2, int i) {
       const int i1 = __shfl_sync(0xffffffffu, src_i1, i), i2 = __shfl_sync(0xffffffffu, src_i2, i);
       int64_t r = rb + i;
       r = r < a.R ? r : a.R - 1;
       xa[u] = ld_stream(xbase + (size_t)r * H);                       // second and last read of x: L2 hit
-      pa[u] = __ldg(reinterpret_cast<const float4*>(base1 + (size_t)i1 * a.ld1));
-      pb[u] = __ldg(reinterpret_cast<const float4*>(base2 + (size_t)i2 * a.ld2));
+      if constexpr (PBF) {
+        pa[u] = __ldg(reinterpret_cast<const uint2*>(base1 + (size_t)i1 * ldb1));
+        pb[u] = __ldg(reinterpret_cast<const uint2*>(base2 + (size_t)i2 * ldb2));
+      } else {
+        pa[u] = __ldg(reinterpret_cast<const float4*>(base1 + (size_t)i1 * ldb1));
+        pb[u] = __ldg(reinterpret_cast<const float4*>(base2 + (size_t)i2 * ldb2));
+      }
+    };
+    auto gathered = [&](int u) {      // g = add1[idx1] + add2[idx2] of window slot u, fp32
+      if constexpr (PBF) return add4(bf4(pa[u]), bf4(pb[u]));
+      else return add4(pa[u], pb[u]);
     };
     int c_i1 = 0, c_i2 = 0, c_pid = -1, n_i1 = 0, n_i2 = 0, n_pid = -1;
     if (ow < total) {
@@ -640,7 +659,7 @@ __global__ void __launch_bounds__(E_THREADS, 1) k_edge5(const EdgeArgs a) {
 #pragma unroll
         for (int u = 0; u < 4; u++) {
           const int i = i0 + u;
-          const float4 g = add4(pa[u], pb[u]);
+          const float4 g = gathered(u);
           const float4 y = add4(add4(add4(xa[u], g), d[u]), b2v);
           if (DEC) {
             od[4 * u + 0] = fmaf(y.w, wdec[3].x, fmaf(y.z, wdec[2].x, fmaf(y.y, wdec[1].x, y.x * wdec[0].x)));
@@ -668,61 +687,6 @@ __global__ void __launch_bounds__(E_THREADS, 1) k_edge5(const EdgeArgs a) {
       EDBG(2);
       c_i1 = n_i1; c_i2 = n_i2; c_pid = n_pid;
     }
-#else
-    static_assert(!DEC, "the rolling-window variant does not implement the fused decoder");
-    float4 xa[DEPTH], pa[DEPTH], pb[DEPTH];
-    auto issue1 = [&](int u, int64_t row0, int src_i1, int src_i2, int i) {
-      const int i1 = __shfl_sync(0xffffffffu, src_i1, i), i2 = __shfl_sync(0xffffffffu, src_i2, i);
-      int64_t r = row0 + i;
-      r = r < a.R ? r : a.R - 1;
-      xa[u] = ld_stream(xbase + (size_t)r * H);                       // second and last read of x: L2 hit
-      pa[u] = __ldg(reinterpret_cast<const float4*>(base1 + (size_t)i1 * a.ld1));
-      pb[u] = __ldg(reinterpret_cast<const float4*>(base2 + (size_t)i2 * a.ld2));
-    };
-    int c_i1 = 0, c_i2 = 0, c_pid = -1, n_i1 = 0, n_i2 = 0, n_pid = -1;
-    if (ow < total) {
-      load_attr(slice_row0(ow), c_i1, c_i2, c_pid);
-#pragma unroll
-      for (int u = 0; u < DEPTH; u++) issue1(u, slice_row0(ow), c_i1, c_i2, u);
-    }
-    for (int k = ow; k < total && !wd_dead; k += OUT_WARPS) {
-      const uint32_t tl = (uint32_t)k >> 3;
-      const int sl = k & (OUT_SLICES - 1);
-      const uint32_t s_lane = s_lane0 + (uint32_t)((OUT_ROWS * sl) * 128);
-      const int64_t row0 = slice_row0(k);
-      const int64_t left = a.R - row0;
-      const int rows = left < 0 ? 0 : (left > OUT_ROWS ? OUT_ROWS : (int)left);
-      const bool has_next = k + OUT_WARPS < total;      // warp-uniform
-      const int64_t nrow0 = slice_row0(has_next ? k + OUT_WARPS : k);
-      if (has_next) load_attr(nrow0, n_i1, n_i2, n_pid);
-      const int nxt = __shfl_down_sync(0xffffffffu, c_pid, 1);
-      const uint32_t endmask = __ballot_sync(0xffffffffu, lane < rows && (lane == rows - 1 || nxt != c_pid));
-      int pid = __shfl_sync(0xffffffffu, c_pid, 0);
-      EDBG(0);
-      mbar_wait(BAR(EB_STGFULL + sl), tl & 1);
-      EDBG(1);
-      float4 acc = f4zero();
-#pragma unroll
-      for (int i = 0; i < OUT_ROWS; i++) {
-        const int u = i % DEPTH;
-        const float4 d = *reinterpret_cast<const float4*>(sm + s_lane + i * 128 + ((s_chunk ^ (uint32_t)(i & 7)) << 4));
-        const float4 g = add4(pa[u], pb[u]);
-        const float4 y = add4(add4(add4(xa[u], g), d), b2v);
-        if (i < rows) __stcs(reinterpret_cast<float4*>(a.y + (size_t)(row0 + i) * H) + lane, y);
-        acc = add4(acc, g);
-        const bool fl = (endmask >> i) & 1u;
-        if (fl) *(reinterpret_cast<float4*>(a.Gpart + (size_t)pid * H) + lane) = acc;
-        acc.x = fl ? 0.f : acc.x; acc.y = fl ? 0.f : acc.y; acc.z = fl ? 0.f : acc.z; acc.w = fl ? 0.f : acc.w;
-        pid += fl ? 1 : 0;
-        // refill this slot: row i + DEPTH of this slice, or - past its end - the matching row of this warp's next slice
-        if (i + DEPTH < OUT_ROWS) issue1(u, row0, c_i1, c_i2, i + DEPTH);
-        else if (has_next) issue1(u, nrow0, n_i1, n_i2, i + DEPTH - OUT_ROWS);
-      }
-      ARRIVE_LOCAL(EB_STGEMPTY + sl);
-      EDBG(2);
-      c_i1 = n_i1; c_i2 = n_i2; c_pid = n_pid;
-    }
-  #endif
   }
   tc_fence_before();
   __syncthreads();
@@ -738,35 +702,55 @@ __global__ void __launch_bounds__(E_THREADS, 1) k_edge5(const EdgeArgs a) {
 
 }  // namespace
 
+namespace {
+template <bool CL2, bool DEC, bool PBF>
+int launch_edge5_t(gnb_ctx* ctx, const EdgeArgs& a, int grid) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(E_THREADS); cfg.dynamicSmemBytes = E_SMEM; cfg.stream = ctx->stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = CL2 ? 2 : 1; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  GNB_CUDA(cudaLaunchKernelEx(&cfg, k_edge5<CL2, DEC, PBF>, a));
+  return GNB_OK;
+}
+template <bool CL2, bool DEC, bool PBF>
+int edge5_smem_attr() {
+  GNB_CUDA(cudaFuncSetAttribute(k_edge5<CL2, DEC, PBF>, cudaFuncAttributeMaxDynamicSharedMemorySize, E_SMEM));
+  return GNB_OK;
+}
+}  // namespace
+
 int launch_edge5(gnb_ctx* ctx, const EdgeArgs& a, const char* name, double flops, double bytes) {
   if (a.num_tiles <= 0) return GNB_OK;
   // GNB_EDGE_CTA_PAIR=0: one CTA per tile stream (cta_group::1).  Read per launch so that a test can run both instantiations.
   const char* pair_env = getenv("GNB_EDGE_CTA_PAIR");
-  const int use_cl2 = pair_env ? atoi(pair_env) : 1;
-  if (ctx_first(ctx, ONCE_EDGE5)) {
-    GNB_CUDA(cudaFuncSetAttribute(k_edge5<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, E_SMEM));
-    GNB_CUDA(cudaFuncSetAttribute(k_edge5<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, E_SMEM));
-    GNB_CUDA(cudaFuncSetAttribute(k_edge5<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, E_SMEM));
-    GNB_CUDA(cudaFuncSetAttribute(k_edge5<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, E_SMEM));
-  }
-  const bool dec = a.decW != nullptr;
-  Launch L(ctx, name, bytes, flops);
-  if (use_cl2 && ctx->sm_count >= 2) {
-    const int pairs = (a.num_tiles + 1) / 2;
-    const int max_clusters = ctx->sm_count / 2;
-    const int grid = 2 * (pairs < max_clusters ? pairs : max_clusters);
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(E_THREADS); cfg.dynamicSmemBytes = E_SMEM; cfg.stream = ctx->stream;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeClusterDimension;
-    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-    cfg.attrs = at; cfg.numAttrs = 1;
-    if (dec) GNB_CUDA(cudaLaunchKernelEx(&cfg, k_edge5<true, true>, a));
-    else GNB_CUDA(cudaLaunchKernelEx(&cfg, k_edge5<true, false>, a));
+  const bool cl2 = (pair_env ? atoi(pair_env) : 1) && ctx->sm_count >= 2;
+  const bool dec = a.decW != nullptr, pbf = a.add_bf16 != 0;
+  int grid;
+  if (cl2) {
+    const int pairs = (a.num_tiles + 1) / 2, max_clusters = ctx->sm_count / 2;
+    grid = 2 * (pairs < max_clusters ? pairs : max_clusters);
   } else {
-    const int grid = a.num_tiles < ctx->sm_count ? a.num_tiles : ctx->sm_count;
-    if (dec) k_edge5<false, true><<<grid, E_THREADS, E_SMEM, ctx->stream>>>(a);
-    else k_edge5<false, false><<<grid, E_THREADS, E_SMEM, ctx->stream>>>(a);
+    grid = a.num_tiles < ctx->sm_count ? a.num_tiles : ctx->sm_count;
+  }
+  if (ctx_first(ctx, ONCE_EDGE5)) {
+    GNB_TRY((edge5_smem_attr<false, false, false>())); GNB_TRY((edge5_smem_attr<false, false, true>()));
+    GNB_TRY((edge5_smem_attr<false, true, false>())); GNB_TRY((edge5_smem_attr<false, true, true>()));
+    GNB_TRY((edge5_smem_attr<true, false, false>())); GNB_TRY((edge5_smem_attr<true, false, true>()));
+    GNB_TRY((edge5_smem_attr<true, true, false>())); GNB_TRY((edge5_smem_attr<true, true, true>()));
+  }
+  Launch L(ctx, name, bytes, flops);
+  const int sel = (cl2 ? 4 : 0) | (dec ? 2 : 0) | (pbf ? 1 : 0);
+  switch (sel) {
+    case 0: GNB_TRY((launch_edge5_t<false, false, false>(ctx, a, grid))); break;
+    case 1: GNB_TRY((launch_edge5_t<false, false, true>(ctx, a, grid))); break;
+    case 2: GNB_TRY((launch_edge5_t<false, true, false>(ctx, a, grid))); break;
+    case 3: GNB_TRY((launch_edge5_t<false, true, true>(ctx, a, grid))); break;
+    case 4: GNB_TRY((launch_edge5_t<true, false, false>(ctx, a, grid))); break;
+    case 5: GNB_TRY((launch_edge5_t<true, false, true>(ctx, a, grid))); break;
+    case 6: GNB_TRY((launch_edge5_t<true, true, false>(ctx, a, grid))); break;
+    default: GNB_TRY((launch_edge5_t<true, true, true>(ctx, a, grid))); break;
   }
   GNB_CUDA(cudaGetLastError());
   return GNB_OK;

@@ -13,9 +13,11 @@ struct EdgeArgs {
   const float* b2;    // [128]
   float eps;
   int eps_mode;
-  // gathered fp32 addend rows: g = add1[idx1[r]] + add2[idx2[r]]   (sender projection, receiver projection + per-graph row)
-  const float* add1; const int32_t* idx1; int ld1;   // idx1 == nullptr: the row itself
-  const float* add2; const int32_t* idx2; int ld2;
+  // gathered addend rows: g = add1[idx1[r]] + add2[idx2[r]]   (sender projection, receiver projection + per-graph row);
+  // add_bf16: both are bf16 matrices (the edges' P_s | P_r'), else fp32 (the nodes' P_agg, P_un); ld in elements
+  const void* add1; const int32_t* idx1; int ld1;   // idx1 == nullptr: the row itself
+  const void* add2; const int32_t* idx2; int ld2;
+  int add_bf16;
   const int32_t* part;   // partial-row id per edge (32-row blocks, receiver runs)
   float* Epart;          // out [n_parts][128] partial sums of the normalised edge rows
   float* Gpart;          // out [n_parts][128] partial sums of the gathered addends
