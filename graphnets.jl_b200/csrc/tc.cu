@@ -526,6 +526,21 @@ __global__ void k_fold_bias(const float* __restrict__ W, int ldw, int n0, int k0
   out[n] = s;
 }
 
+// Bias slabs of the fused kernel (tc_edge.cu): the FFN biases are added by the tensor core as one extra K = 16 step
+// ones[128][16] . slab[n][16]^T with slab[n][0] = bf16(b[n]), slab[n][1] = bf16(b[n] - slab[n][0]) (hi / lo split: exact to 2^-17),
+// zeros elsewhere.  Five slabs of 128 rows: the four hidden chunks of b1' (LN2 shift folded in) and b2.  Layout: K-major,
+// NO swizzle, 8 x 16 B core matrices: element (n, k) at byte (n >> 3) * 256 + (k >> 3) * 128 + (n & 7) * 16 + (k & 7) * 2.
+__global__ void k_pack_bias(const float* __restrict__ b1f /*[512]*/, const float* __restrict__ b2 /*[128]*/, __nv_bfloat16* __restrict__ dst) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;      // 640 rows
+  if (i >= 640) return;
+  const float b = i < 512 ? b1f[i] : b2[i - 512];
+  const int slab = i >> 7, n = i & 127;
+  __nv_bfloat16* o = dst + (size_t)slab * 2048 + (n >> 3) * 128 + (n & 7) * 8;
+  const __nv_bfloat16 hi = __float2bfloat16_rn(b);
+  o[0] = hi;
+  o[1] = __float2bfloat16_rn(b - __bfloat162float(hi));
+}
+
 }  // namespace
 
 static unsigned long long* g_tc_dbg = nullptr;
@@ -547,6 +562,8 @@ struct TcCorePack {
   float* f = nullptr;           // folded fp32 vectors: cu_e[128] cu_n[128] b1f_e[512] b1f_n[512]
   const __nv_bfloat16 *w_proj, *w_agg, *w_edge, *w_node;
   float *cu_e, *cu_n, *b1f_e, *b1f_n;
+  __nv_bfloat16* bias = nullptr;      // bias slabs of the fused kernel (k_pack_bias): [edge 5 x 4 KB | node 5 x 4 KB]
+  const __nv_bfloat16 *bias_e, *bias_n;
 };
 
 bool tc_core_supported(int de, int dn, int dg) { return de == H && dn == H && dg == H; }
@@ -555,6 +572,7 @@ void tc_core_pack_free(TcCorePack* p) {
   if (!p) return;
   if (p->w) cudaFree(p->w);
   if (p->f) cudaFree(p->f);
+  if (p->bias) cudaFree(p->bias);
   delete p;
 }
 
@@ -568,7 +586,8 @@ int tc_core_pack(gnb_ctx* ctx, const gnb_block_params& blk, const gnb_ffn_params
   TcCorePack* p = new TcCorePack();
   const size_t nblk = 4 + 4 + 9 + 9;
   if (cudaMalloc((void**)&p->w, nblk * BLK_BYTES) != cudaSuccess ||
-      cudaMalloc((void**)&p->f, (128 + 128 + 512 + 512) * sizeof(float)) != cudaSuccess) {
+      cudaMalloc((void**)&p->f, (128 + 128 + 512 + 512) * sizeof(float)) != cudaSuccess ||
+      cudaMalloc((void**)&p->bias, 2 * TC_BIAS_PACK_BYTES) != cudaSuccess) {
     cudaGetLastError();
     tc_core_pack_free(p);
     gnb_set_error("tc_core_pack: cudaMalloc failed");
@@ -621,6 +640,10 @@ int tc_core_pack(gnb_ctx* ctx, const gnb_block_params& blk, const gnb_ffn_params
   k_fold_bias<<<1, 128, 0, st>>>(blk.Wn, H, 0, H, H, b1n, blk.bn, H, p->cu_n, 0);
   k_fold_bias<<<4, 128, 0, st>>>(ffn[0].W1, 4 * H, 0, 0, H, ln2[0].beta, ffn[0].b1, 4 * H, p->b1f_e, 0);
   k_fold_bias<<<4, 128, 0, st>>>(ffn[1].W1, 4 * H, 0, 0, H, ln2[1].beta, ffn[1].b1, 4 * H, p->b1f_n, 0);
+  p->bias_e = p->bias; p->bias_n = p->bias + TC_BIAS_PACK_BYTES / 2;
+  cudaMemsetAsync(p->bias, 0, 2 * TC_BIAS_PACK_BYTES, st);
+  k_pack_bias<<<5, 128, 0, st>>>(p->b1f_e, ffn[0].b2, p->bias);
+  k_pack_bias<<<5, 128, 0, st>>>(p->b1f_n, ffn[1].b2, p->bias + TC_BIAS_PACK_BYTES / 2);
   cudaError_t e = cudaStreamSynchronize(st);
   if (e == cudaSuccess) e = cudaGetLastError();
   cudaFree(Ftmp);
@@ -694,7 +717,7 @@ int tc_core_forward(gnb_ctx* ctx, const gnb_graph* g, const TcCorePack* pk, cons
   {  // edges: GNBlock edge update + FFN + residual; partial receiver sums of the inputs
     EdgeArgs a{};
     a.x = xe; a.y = ye; a.R = E; a.num_tiles = ceil_div(E, TM); a.wpack = pk->w_edge;
-    a.b1f = pk->b1f_e; a.b2 = ffn[0].b2; a.eps = ln1[0].eps; a.eps_mode = ln1[0].eps_mode;
+    a.bias_pack = pk->bias_e; a.eps = ln1[0].eps; a.eps_mode = ln1[0].eps_mode;
     a.add1 = Psr; a.idx1 = g->edge_src; a.ld1 = 2 * H; a.add2 = Psr + H * psr_es; a.idx2 = g->edge_dst; a.ld2 = 2 * H; a.add_bf16 = psr_bf16;
     a.part = g->edge_part; a.Epart = Epart; a.Gpart = Gpart; a.dbg = g_tc_dbg; a.wd = ctx_watch(ctx);
     a.decW = dec.W4; a.dec_out = dec.partial;      // fused narrow decoder: y_e is not stored (ye may be nullptr)
@@ -722,7 +745,7 @@ int tc_core_forward(gnb_ctx* ctx, const gnb_graph* g, const TcCorePack* pk, cons
      // linearity over the partial sums of v^ (V_part) and of the addends (N_part), so h_v is never materialised
     EdgeArgs a{};
     a.x = xn; a.y = yn; a.R = N; a.num_tiles = ceil_div(N, TM); a.wpack = pk->w_node;
-    a.b1f = pk->b1f_n; a.b2 = ffn[1].b2; a.eps = ln1[1].eps; a.eps_mode = ln1[1].eps_mode;
+    a.bias_pack = pk->bias_n; a.eps = ln1[1].eps; a.eps_mode = ln1[1].eps_mode;
     a.add1 = Pagg; a.idx1 = nullptr; a.ld1 = H; a.add2 = Pun; a.idx2 = g->node_graph; a.ld2 = H; a.add_bf16 = 0;
     a.part = g->node_gpart; a.Epart = Vpart; a.Gpart = Npart; a.dbg = nullptr; a.wd = ctx_watch(ctx);
     GNB_TRY(launch_edge5(ctx, a, "tc_node_core", 20.0 * HH * N, (8.0 * H + 8.0) * N));

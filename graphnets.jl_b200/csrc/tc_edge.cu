@@ -31,13 +31,26 @@ using namespace tcx;
 namespace {
 
 constexpr int HALF_BYTES = KB_BYTES;   // weight ring stage = one 64-wide K half of a block (16 KB)
-constexpr int NWS = 5;
+// shared memory (CL2: per CTA of the pair).  The FFN biases are added by the tensor core: one extra K = 16 UMMA per up block /
+// per GNBlock block,  ONES[128][16] (column 0 = 1) . BIAS slab (row n = [hi(b_n), lo(b_n), 0 ...]), so that the conversion warps
+// (the serial link of the MMA chain) only have to relu + pack, and the OUT warps do not add b2.
 constexpr int E_OFF_A = 0;                                   // 2 stages x 32 KB
-constexpr int E_OFF_W = 2 * BLK_BYTES;                       // 5 x 16 KB
-constexpr int E_OFF_STG = E_OFF_W + NWS * HALF_BYTES;        // 64 KB: [4 column groups][128 rows][128 B], 16B chunks XOR (row & 7)
-constexpr int E_OFF_MISC = E_OFF_STG + 65536;
-constexpr int E_MISC = 512 * 4 + 128 * 4 + 40 * 8 + 16;      // (29 barriers used)      // b1f[512], b2[128], barriers[40], tmem slot
-constexpr int E_SMEM = E_OFF_MISC + E_MISC + 1024;
+constexpr int E_OFF_STG = 2 * BLK_BYTES;                     // 64 KB: [4 column groups][128 rows][128 B], 16B chunks XOR (row & 7)
+constexpr int E_OFF_ONES = E_OFF_STG + 65536;                // 4 KB: A operand of the bias step (K-major, no swizzle, 8 x 16 B core matrices)
+constexpr int E_OFF_BIAS = E_OFF_ONES + 4096;                // 5 bias slabs: this CTA's N rows (CL2: 64 of 128 -> 2 KB per slab)
+__host__ __device__ constexpr int e_bias_bytes(bool cl2) { return 5 * (cl2 ? 2048 : 4096); }
+__host__ __device__ constexpr int e_nws(bool cl2) { return cl2 ? 5 : 4; }       // weight ring stages of 16 KB (CL2: one block per stage; else two stages per block)
+__host__ __device__ constexpr int e_off_w(bool cl2) { return E_OFF_BIAS + e_bias_bytes(cl2); }
+__host__ __device__ constexpr int e_off_misc(bool cl2) { return e_off_w(cl2) + e_nws(cl2) * HALF_BYTES; }
+constexpr int E_MISC = 40 * 8 + 16;      // barriers[40] (29 used), tmem slot
+__host__ __device__ constexpr int e_smem(bool cl2) { return e_off_misc(cl2) + E_MISC + 1024; }
+static_assert(e_off_w(true) % 1024 == 0 && e_off_w(false) % 1024 == 0, "swizzled weight stages need 1024 B alignment");
+static_assert(e_smem(true) <= 232448 && e_smem(false) <= 232448, "shared memory budget (227 KB per CTA)");
+// K-major operand WITHOUT swizzle: core matrices of 8 rows x 16 B; LBO = 128 B between the two core matrices of a K = 16 step,
+// SBO = 256 B between 8-row groups (cute::UMMA::SmemDescriptor, LayoutType::INTERLEAVE)
+__device__ __forceinline__ uint64_t umma_desc_nosw(uint32_t saddr) {
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (8ull << 16) | (16ull << 32) | (1ull << 46);
+}
 #ifndef GNB_OUT_WARPS
 #define GNB_OUT_WARPS 6
 #endif
@@ -56,16 +69,6 @@ enum { EB_WFULL = 0, EB_WEMPTY = 5, EB_AFULL = 10, EB_AEMPTY = 12, EB_HIDFULL = 
 constexpr int PK_W1_0 = 0, PK_BLK = 1, PK_W2_0 = 2, PK_W1_1 = 3, PK_W2_1 = 4, PK_W1_2 = 5, PK_W2_2 = 6, PK_W1_3 = 7, PK_W2_3 = 8;
 // issue order of a tile, one nibble per block (every SS <-> TS operand-mode switch of the tensor pipe costs ~435 cycles,
 // profiles/r01_hwprobe.log T5)
-#ifdef GNB_EDGE_ORDER_A
-// round-1 order  [up0 up1 blk] [dn0 dn1] [up2 up3] [dn2 dn3]: fewest SS <-> TS switches (3), but the conversion warps idle
-// between chunk 1 and chunk 2 until both down blocks have been issued and up2 has run
-constexpr unsigned long long SEQ_PACKED = (unsigned long long)PK_W1_0 | ((unsigned long long)PK_W1_1 << 4) | ((unsigned long long)PK_BLK << 8) |
-    ((unsigned long long)PK_W2_0 << 12) | ((unsigned long long)PK_W2_1 << 16) | ((unsigned long long)PK_W1_2 << 20) |
-    ((unsigned long long)PK_W1_3 << 24) | ((unsigned long long)PK_W2_2 << 28) | ((unsigned long long)PK_W2_3 << 32);
-constexpr int B_BLK = 2, B_FIRSTD = 2;
-#define IS_DN(b) (((b) == 3) | ((b) == 4) | ((b) == 7) | ((b) == 8))
-#define HB_OF(b) ((((b) == 0) | ((b) == 3) | ((b) == 5) | ((b) == 7)) ? 0 : 1)
-#else
 // order  up0 up1 blk dn0 up2 dn1 up3 dn2 dn3: every up-projection is issued as soon as its hidden buffer is free (up2 right
 // behind dn0, up3 right behind dn1), so the next chunk is ready when the conversion warps finish the previous one; costs two
 // more SS <-> TS switches per tile (5 x ~435 cycles), which the tensor pipe has to spare
@@ -75,7 +78,7 @@ constexpr unsigned long long SEQ_PACKED = (unsigned long long)PK_W1_0 | ((unsign
 constexpr int B_BLK = 2, B_FIRSTD = 2;
 #define IS_DN(b) (((b) == 3) | ((b) == 5) | ((b) == 7) | ((b) == 8))
 #define HB_OF(b) ((((b) == 0) | ((b) == 3) | ((b) == 4) | ((b) == 7)) ? 0 : 1)
-#endif
+#define UPCHUNK_OF(b) ((b) == 0 ? 0 : ((b) == 1 ? 1 : ((b) == 4 ? 2 : 3)))      /* hidden chunk of an up block */
 
 
 #ifdef GNB_TC_TIMING
@@ -156,10 +159,9 @@ __global__ void __launch_bounds__(E_THREADS, 1) k_edge5(const EdgeArgs a) {
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
   uint8_t* sm = smem_raw + (base - raw);
-  const uint32_t sW = base + E_OFF_W;
-  float* sB1 = reinterpret_cast<float*>(sm + E_OFF_MISC);
-  float* sB2 = sB1 + 512;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sB2 + 128);
+  constexpr int NWS = e_nws(CL2);
+  const uint32_t sW = base + e_off_w(CL2);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sm + e_off_misc(CL2));
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 40);
   const uint32_t bar0 = smem_u32(bars);
   auto BAR = [&](int i) { return bar0 + 8u * (uint32_t)i; };
@@ -187,8 +189,19 @@ __global__ void __launch_bounds__(E_THREADS, 1) k_edge5(const EdgeArgs a) {
       asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
   }
-  for (int i = tid; i < 512; i += E_THREADS) sB1[i] = a.b1f[i];
-  if (tid < 128) sB2[tid] = a.b2[tid];
+  {
+    // ONES: element (row r, k = 0) = 1.0, everything else 0;  BIAS: this CTA's rows of the five packed slabs
+    uint4* ones = reinterpret_cast<uint4*>(sm + E_OFF_ONES);      // 256 x 16 B: chunk (r >> 3) * 16 + (k >> 3) * 8 + (r & 7)
+    for (int i = tid; i < 256; i += E_THREADS) ones[i] = make_uint4(((i >> 3) & 1) ? 0u : 0x3F80u, 0u, 0u, 0u);
+    constexpr int SLAB = CL2 ? 2048 : 4096;
+    const uint4* src = reinterpret_cast<const uint4*>(a.bias_pack);
+    uint4* dstb = reinterpret_cast<uint4*>(sm + E_OFF_BIAS);
+    for (int i = tid; i < 5 * SLAB / 16; i += E_THREADS) {
+      const int slab = i / (SLAB / 16), j = i % (SLAB / 16);
+      dstb[i] = __ldg(src + slab * (TC_BIAS_SLAB_BYTES / 16) + (CL2 ? (int)rank * (SLAB / 16) : 0) + j);
+    }
+    fence_async_smem();      // generic-proxy writes -> visible to the UMMAs (async proxy)
+  }
   tc_fence_before();
   __syncthreads();
   if (CL2) cluster_sync_all();      // the peer's barriers are initialised before any remote arrive / multicast commit
@@ -299,6 +312,8 @@ __global__ void __launch_bounds__(E_THREADS, 1) k_edge5(const EdgeArgs a) {
       if (CL2) tc_commit2(BAR(i));
       else tc_commit(BAR(i));
     };
+    constexpr uint32_t SLAB = CL2 ? 2048 : 4096;
+    const uint64_t ones_desc = umma_desc_nosw(base + E_OFF_ONES), bias_desc = umma_desc_nosw(base + E_OFF_BIAS);
     for (int tile = blockIdx.x; TILE_OK(tile); tile += grid, tl++) {
       const uint32_t st = tl & 1, uph = (tl >> 1) & 1;
       const uint64_t adesc = umma_desc(base + E_OFF_A + st * BLK_BYTES);
@@ -321,12 +336,13 @@ __global__ void __launch_bounds__(E_THREADS, 1) k_edge5(const EdgeArgs a) {
           if (is_dn) {                                                             // D += relu(.)[chunk] W2_c
             if (CL2) issue_ts2(D, Hd, w0, b != B_FIRSTD);
             else issue_ts(D, Hd, w0, w1, b != B_FIRSTD);
-          } else if (b == B_BLK) {                                                 // GNBlock GEMM
-            if (CL2) issue_ss2(D, adesc, w0, b != B_FIRSTD);
-            else issue_ss(D, adesc, w0, w1, b != B_FIRSTD);
-          } else {                                                                 // FFN up-projection chunk
-            if (CL2) issue_ss2(Hd, adesc, w0, false);
-            else issue_ss(Hd, adesc, w0, w1, false);
+          } else if (b == B_BLK) {                                                 // GNBlock GEMM (+ b2)
+            if (CL2) { issue_ss2(D, adesc, w0, b != B_FIRSTD); mma_ss2(D, ones_desc, bias_desc + 4 * (SLAB >> 4), IDESC2, 1u); }
+            else { issue_ss(D, adesc, w0, w1, b != B_FIRSTD); mma_ss(D, ones_desc, bias_desc + 4 * (SLAB >> 4), IDESC, 1u); }
+          } else {                                                                 // FFN up-projection chunk (+ b1')
+            const int c = UPCHUNK_OF(b);
+            if (CL2) { issue_ss2(Hd, adesc, w0, false); mma_ss2(Hd, ones_desc, bias_desc + c * (SLAB >> 4), IDESC2, 1u); }
+            else { issue_ss(Hd, adesc, w0, w1, false); mma_ss(Hd, ones_desc, bias_desc + c * (SLAB >> 4), IDESC, 1u); }
             COMMIT(EB_HIDFULL + hb);
           }
           if (b == 6) COMMIT(EB_AEMPTY + st);                                      // last read of the A tile
@@ -347,33 +363,26 @@ __global__ void __launch_bounds__(E_THREADS, 1) k_edge5(const EdgeArgs a) {
     // TMEM fp32 -> +b1 -> relu -> bf16 pairs -> TMEM, in place.  TMEM loads queue behind the running MMAs (several hundred
     // cycles each under load), so two 32-column loads are kept in flight; the store of columns [16j,16j+16) only
     // overwrites columns whose load has completed.
-    auto cvt32 = [&](const uint32_t (&v)[32], const float* bias32, uint32_t dst) {
+    // (the bias is already in the accumulator: the MMA warp adds it with a K = 16 step)
+    auto cvt32 = [&](const uint32_t (&v)[32], uint32_t dst) {
       uint32_t p[16];
-      const float4* bb = reinterpret_cast<const float4*>(bias32);
 #pragma unroll
-      for (int t = 0; t < 8; t++) {
-        const float4 b = bb[t];
-        const float2 lo = __fadd2_rn(make_float2(__uint_as_float(v[4 * t]), __uint_as_float(v[4 * t + 1])), make_float2(b.x, b.y));
-        const float2 hi = __fadd2_rn(make_float2(__uint_as_float(v[4 * t + 2]), __uint_as_float(v[4 * t + 3])), make_float2(b.z, b.w));
-        p[2 * t] = pack_bf16_relu(lo.x, lo.y);
-        p[2 * t + 1] = pack_bf16_relu(hi.x, hi.y);
-      }
+      for (int t = 0; t < 16; t++) p[t] = pack_bf16_relu(__uint_as_float(v[2 * t]), __uint_as_float(v[2 * t + 1]));
       TC_ST16(dst, p);
     };
-    auto convert = [&](uint32_t Hd, int c) {
+    auto convert = [&](uint32_t Hd) {
       uint32_t va[32], vb[32];
-      const float* bias = sB1 + c * 128;
       const uint32_t t0 = Hd + lane_base;
       TC_LD32(t0, va);
       TC_LD32(t0 + 32, vb);
       tc_wait_ld();
-      cvt32(va, bias, t0);
+      cvt32(va, t0);
       TC_LD32(t0 + 64, va);
-      cvt32(vb, bias + 32, t0 + 16);
+      cvt32(vb, t0 + 16);
       TC_LD32(t0 + 96, vb);
       tc_wait_ld();
-      cvt32(va, bias + 64, t0 + 32);
-      cvt32(vb, bias + 96, t0 + 48);
+      cvt32(va, t0 + 32);
+      cvt32(vb, t0 + 48);
       tc_wait_st();
       tc_fence_before();
     };
@@ -381,7 +390,7 @@ __global__ void __launch_bounds__(E_THREADS, 1) k_edge5(const EdgeArgs a) {
       mbar_wait(BAR(EB_HIDFULL + (c & 1)), (c >> 1) & 1);
       EDBG(1 + 2 * c);
       tc_fence_after();
-      convert((c & 1) ? HdB : HdA, c);
+      convert((c & 1) ? HdB : HdA);
       ARRIVE_LEADER(EB_HSREADY + (c & 1));
       EDBG(2 + 2 * c);
     };
@@ -570,7 +579,6 @@ __global__ void __launch_bounds__(E_THREADS, 1) k_edge5(const EdgeArgs a) {
     constexpr int DEPTH = GNB_OUT_DEPTH;
     static_assert(OUT_ROWS % DEPTH == 0, "the rolling window keeps its slot numbering across slices only if DEPTH divides the slice");
     const int ow = warp < 8 ? warp - 4 : warp - 8;
-    const float4 b2v = *reinterpret_cast<const float4*>(sB2 + 4 * lane);
     const float* xbase = a.x + 4 * lane;
     // this lane's 4 columns of a gathered row: 16 B of an fp32 row, 8 B of a bf16 row
     const uint8_t* base1 = reinterpret_cast<const uint8_t*>(a.add1) + (PBF ? 8 : 16) * lane;
@@ -660,7 +668,7 @@ __global__ void __launch_bounds__(E_THREADS, 1) k_edge5(const EdgeArgs a) {
         for (int u = 0; u < 4; u++) {
           const int i = i0 + u;
           const float4 g = gathered(u);
-          const float4 y = add4(add4(add4(xa[u], g), d[u]), b2v);
+          const float4 y = add4(add4(xa[u], g), d[u]);      // (b2 is in the accumulator)
           if (DEC) {
             od[4 * u + 0] = fmaf(y.w, wdec[3].x, fmaf(y.z, wdec[2].x, fmaf(y.y, wdec[1].x, y.x * wdec[0].x)));
             od[4 * u + 1] = fmaf(y.w, wdec[3].y, fmaf(y.z, wdec[2].y, fmaf(y.y, wdec[1].y, y.x * wdec[0].y)));
@@ -706,7 +714,7 @@ namespace {
 template <bool CL2, bool DEC, bool PBF>
 int launch_edge5_t(gnb_ctx* ctx, const EdgeArgs& a, int grid) {
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(E_THREADS); cfg.dynamicSmemBytes = E_SMEM; cfg.stream = ctx->stream;
+  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(E_THREADS); cfg.dynamicSmemBytes = e_smem(CL2); cfg.stream = ctx->stream;
   cudaLaunchAttribute at[1];
   at[0].id = cudaLaunchAttributeClusterDimension;
   at[0].val.clusterDim.x = CL2 ? 2 : 1; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
@@ -716,7 +724,7 @@ int launch_edge5_t(gnb_ctx* ctx, const EdgeArgs& a, int grid) {
 }
 template <bool CL2, bool DEC, bool PBF>
 int edge5_smem_attr() {
-  GNB_CUDA(cudaFuncSetAttribute(k_edge5<CL2, DEC, PBF>, cudaFuncAttributeMaxDynamicSharedMemorySize, E_SMEM));
+  GNB_CUDA(cudaFuncSetAttribute(k_edge5<CL2, DEC, PBF>, cudaFuncAttributeMaxDynamicSharedMemorySize, e_smem(CL2)));
   return GNB_OK;
 }
 }  // namespace

@@ -3,14 +3,16 @@
 #include <cuda_bf16.h>
 #include "common.cuh"
 
+constexpr int TC_BIAS_SLAB_BYTES = 4096;                  // 128 rows x 16 bf16 (one K = 16 step), no swizzle
+constexpr int TC_BIAS_PACK_BYTES = 5 * TC_BIAS_SLAB_BYTES;
+
 struct EdgeArgs {
   const float* x;     // [R][128] edge features
   float* y;           // [R][128] core output
   int64_t R;
   int num_tiles;
   const __nv_bfloat16* wpack;   // 9 packed 32 KB weight blocks (tc.cu::tc_core_pack, edge order)
-  const float* b1f;   // [512] FFN bias with the LN2 shift folded in
-  const float* b2;    // [128]
+  const __nv_bfloat16* bias_pack;   // 5 bias slabs of 4 KB (tc.cu::k_pack_bias): b1' chunks 0-3 (LN2 shift folded in), b2
   float eps;
   int eps_mode;
   // gathered addend rows: g = add1[idx1[r]] + add2[idx2[r]]   (sender projection, receiver projection + per-graph row);
