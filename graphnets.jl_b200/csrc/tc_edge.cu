@@ -18,9 +18,12 @@
 //                       gets every warp the register budget leaves (round 1: four warps, 12.7 k cycles per tile)
 //   warp 14     MMA issuer (one elected lane), warp 15 weight loader (cp.async.bulk, 5 x 16 KB ring; also prefetches the x rows
 //               of the pass after next into L2 with one bulk prefetch)
-// TMEM (512 columns): D[2] accumulators (double buffered across tiles: the epilogue of tile t overlaps the MMAs of
-// tile t+1) | Hd[2] hidden chunks (ping-pong inside a tile: the conversion of chunk c overlaps the MMAs of chunk c+1).
-// MMA order per tile: up0 up1 blk dn0 up2 dn1 up3 dn2 dn3 (SEQ_PACKED below).
+// TMEM (512 columns): D accumulator (128) | Hd[3] hidden chunk buffers (3 x 128), used round-robin by the stream of hidden
+// chunks (4 per tile), so that up to three up-projections are in flight ahead of the conversion warps: the MMA warp never
+// waits for a single conversion round trip (round 1 / early round 2: D[2] + Hd[2], where the tensor pipe idled half of
+// every tile behind the serial chain  up(c) -> convert -> down(c) -> up(c+2)).  The accumulator is single buffered: it is
+// drained (TMEM -> staging tile) while the first three up-projections of the next tile run.
+// MMA order per tile: up0 up1 up2 blk dn0 up3 dn1 dn2 dn3 (SEQ_PACKED below).
 #include "tc_ptx.cuh"
 #include "tc_edge.cuh"
 #include <stdlib.h>
@@ -62,23 +65,21 @@ constexpr int OUT_ROWS = GNB_PART_ROWS;      // rows per OUT slice == cut of the
 constexpr int OUT_SLICES = TM / OUT_ROWS;
 static_assert(OUT_ROWS == 16 && OUT_SLICES == 8, "8 slices of 16 rows per tile");
 constexpr int E_THREADS = E_WARPS * 32;
-enum { EB_WFULL = 0, EB_WEMPTY = 5, EB_AFULL = 10, EB_AEMPTY = 12, EB_HIDFULL = 14, EB_HSREADY = 16, EB_OUTDONE = 18,
-       EB_ACCFREE = 20, EB_STGFULL = 24, EB_STGEMPTY = 32 };      // STGFULL / STGEMPTY: one pair per 16-row slice of the staging tile
+enum { EB_WFULL = 0, EB_WEMPTY = 5, EB_AFULL = 10, EB_AEMPTY = 12, EB_HIDFULL = 14, EB_HSREADY = 17, EB_OUTDONE = 20,
+       EB_ACCFREE = 21, EB_STGFULL = 24, EB_STGEMPTY = 32 };      // STGFULL / STGEMPTY: one pair per 16-row slice of the staging tile
 
 // block ids inside the packed edge weights (tc.cu::tc_core_pack): W1_0 W_blk W2_0 W1_1 W2_1 W1_2 W2_2 W1_3 W2_3
 constexpr int PK_W1_0 = 0, PK_BLK = 1, PK_W2_0 = 2, PK_W1_1 = 3, PK_W2_1 = 4, PK_W1_2 = 5, PK_W2_2 = 6, PK_W1_3 = 7, PK_W2_3 = 8;
-// issue order of a tile, one nibble per block (every SS <-> TS operand-mode switch of the tensor pipe costs ~435 cycles,
-// profiles/r01_hwprobe.log T5)
-// order  up0 up1 blk dn0 up2 dn1 up3 dn2 dn3: every up-projection is issued as soon as its hidden buffer is free (up2 right
-// behind dn0, up3 right behind dn1), so the next chunk is ready when the conversion warps finish the previous one; costs two
-// more SS <-> TS switches per tile (5 x ~435 cycles), which the tensor pipe has to spare
-constexpr unsigned long long SEQ_PACKED = (unsigned long long)PK_W1_0 | ((unsigned long long)PK_W1_1 << 4) | ((unsigned long long)PK_BLK << 8) |
-    ((unsigned long long)PK_W2_0 << 12) | ((unsigned long long)PK_W1_2 << 16) | ((unsigned long long)PK_W2_1 << 20) |
-    ((unsigned long long)PK_W1_3 << 24) | ((unsigned long long)PK_W2_2 << 28) | ((unsigned long long)PK_W2_3 << 32);
-constexpr int B_BLK = 2, B_FIRSTD = 2;
-#define IS_DN(b) (((b) == 3) | ((b) == 5) | ((b) == 7) | ((b) == 8))
-#define HB_OF(b) ((((b) == 0) | ((b) == 3) | ((b) == 4) | ((b) == 7)) ? 0 : 1)
-#define UPCHUNK_OF(b) ((b) == 0 ? 0 : ((b) == 1 ? 1 : ((b) == 4 ? 2 : 3)))      /* hidden chunk of an up block */
+// issue order of a tile, one nibble per block:  up0 up1 up2 blk dn0 up3 dn1 dn2 dn3.  Three up-projections fill the three hidden
+// buffers while the conversion warps work; up3 re-uses the buffer of chunk 0 right behind dn0.  Four SS <-> TS operand-mode
+// switches of the tensor pipe per tile (~435 cycles each, profiles/r01_hwprobe.log T5).
+constexpr unsigned long long SEQ_PACKED = (unsigned long long)PK_W1_0 | ((unsigned long long)PK_W1_1 << 4) | ((unsigned long long)PK_W1_2 << 8) |
+    ((unsigned long long)PK_BLK << 12) | ((unsigned long long)PK_W2_0 << 16) | ((unsigned long long)PK_W1_3 << 20) |
+    ((unsigned long long)PK_W2_1 << 24) | ((unsigned long long)PK_W2_2 << 28) | ((unsigned long long)PK_W2_3 << 32);
+constexpr int B_BLK = 3, B_LASTA = 5;      // the GNBlock block is the first write of the accumulator; up3 is the last read of the A tile
+#define IS_DN(b) (((b) == 4) | ((b) >= 6))
+#define IS_UP(b) (((b) <= 2) | ((b) == 5))
+#define CHUNK_OF(b) ((b) <= 2 ? (b) : ((b) == 4 ? 0 : ((b) == 5 ? 3 : (b) - 5)))      /* hidden chunk (0-3) of an up / down block */
 
 
 #ifdef GNB_TC_TIMING
@@ -172,11 +173,9 @@ __global__ void __launch_bounds__(E_THREADS, 1) k_edge5(const EdgeArgs a) {
   if (tid == 0) {
     // pair leader: WFULL[st] also counts the peer's "my half has landed" relay, so the MMA warp waits on ONE barrier per block
     for (int i = 0; i < NWS; i++) { mbar_init(BAR(EB_WFULL + i), (CL2 && rank == 0) ? 2 : 1); mbar_init(BAR(EB_WEMPTY + i), 1); }
-    for (int s = 0; s < 2; s++) {
-      mbar_init(BAR(EB_AFULL + s), NARR); mbar_init(BAR(EB_AEMPTY + s), 1);
-      mbar_init(BAR(EB_HIDFULL + s), 1); mbar_init(BAR(EB_HSREADY + s), NARR);
-      mbar_init(BAR(EB_OUTDONE + s), 1); mbar_init(BAR(EB_ACCFREE + s), NARR);
-    }
+    for (int s = 0; s < 2; s++) { mbar_init(BAR(EB_AFULL + s), NARR); mbar_init(BAR(EB_AEMPTY + s), 1); }
+    for (int s = 0; s < 3; s++) { mbar_init(BAR(EB_HIDFULL + s), 1); mbar_init(BAR(EB_HSREADY + s), NARR); }
+    mbar_init(BAR(EB_OUTDONE), 1); mbar_init(BAR(EB_ACCFREE), NARR);
     for (int i = 0; i < OUT_SLICES; i++) { mbar_init(BAR(EB_STGFULL + i), 1); mbar_init(BAR(EB_STGEMPTY + i), 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -224,7 +223,7 @@ __global__ void __launch_bounds__(E_THREADS, 1) k_edge5(const EdgeArgs a) {
 #define mbar_wait_cluster(b, p) mbar_wait_w((b), (p), wd_dead, a.wd)      /* barriers that receive arrivals from the peer CTA */
 #define TILE_OK(t) ((t) - (int)rank < a.num_tiles && !wd_dead)   /* both CTAs of a pair run the same number of passes */
   const uint32_t tmem = *tmem_slot;
-  const uint32_t HdA = tmem + 256, HdB = tmem + 384;
+  const uint32_t Hd0 = tmem + 128;      // hidden buffer i at Hd0 + 128 i; the accumulator at tmem
   const int grid = gridDim.x;
   const int first_tile = (int)blockIdx.x - (int)rank;      // both CTAs of a pair run the same number of passes
   const int npass = first_tile < a.num_tiles ? (a.num_tiles - first_tile + grid - 1) / grid : 0;
@@ -314,43 +313,47 @@ __global__ void __launch_bounds__(E_THREADS, 1) k_edge5(const EdgeArgs a) {
     };
     constexpr uint32_t SLAB = CL2 ? 2048 : 4096;
     const uint64_t ones_desc = umma_desc_nosw(base + E_OFF_ONES), bias_desc = umma_desc_nosw(base + E_OFF_BIAS);
+    // position of the next up / down block in the stream of hidden chunks: buffer (chunk mod 3) and use count parity
+    uint32_t ub = 0, uq = 0, db = 0, dq = 0;
     for (int tile = blockIdx.x; TILE_OK(tile); tile += grid, tl++) {
       const uint32_t st = tl & 1, uph = (tl >> 1) & 1;
       const uint64_t adesc = umma_desc(base + E_OFF_A + st * BLK_BYTES);
-      const uint32_t D = tmem + 128 * st;
-      // fully unrolled: which block is an up / block / down GEMM, its hidden buffer and its barriers are compile-time
-      // constants - the issuing warp is a single dependent instruction stream and every instruction it does not execute
-      // shortens the gap between two 520-cycle UMMA blocks
+      const uint32_t D = tmem;
+      // fully unrolled: which block is an up / block / down GEMM and its bias slab are compile-time constants - the issuing
+      // warp is a single dependent instruction stream and every instruction it does not execute shortens the gap between two
+      // 520-cycle UMMA blocks
 #pragma unroll
       for (int b = 0; b < 9; b++) {
         EDBG(b);
         get_w();
-        const bool is_dn = IS_DN(b);
-        const int hb = HB_OF(b);      // hidden buffer of an up / down block
-        const uint32_t Hd = hb ? HdB : HdA;
+        const bool is_dn = IS_DN(b), is_up = IS_UP(b);
         if (b == 0) mbar_wait_cluster(BAR(EB_AFULL + st), uph);                      // A tile of this pass
-        if (b == B_FIRSTD) mbar_wait_cluster(BAR(EB_ACCFREE + st), uph ^ 1);         // accumulator drained (two tiles ago)
-        if (is_dn) mbar_wait_cluster(BAR(EB_HSREADY + hb), b >= 7 ? 1u : 0u);        // hidden chunk converted to bf16
+        if (b == B_BLK) mbar_wait_cluster(BAR(EB_ACCFREE), (tl & 1) ^ 1);            // accumulator of the previous tile drained
+        if (is_dn) mbar_wait_cluster(BAR(EB_HSREADY + db), dq & 1);                  // hidden chunk converted to bf16
         tc_fence_after();
         if (elect_one()) {
           if (is_dn) {                                                             // D += relu(.)[chunk] W2_c
-            if (CL2) issue_ts2(D, Hd, w0, b != B_FIRSTD);
-            else issue_ts(D, Hd, w0, w1, b != B_FIRSTD);
-          } else if (b == B_BLK) {                                                 // GNBlock GEMM (+ b2)
-            if (CL2) { issue_ss2(D, adesc, w0, b != B_FIRSTD); mma_ss2(D, ones_desc, bias_desc + 4 * (SLAB >> 4), IDESC2, 1u); }
-            else { issue_ss(D, adesc, w0, w1, b != B_FIRSTD); mma_ss(D, ones_desc, bias_desc + 4 * (SLAB >> 4), IDESC, 1u); }
+            const uint32_t Hd = Hd0 + 128 * db;
+            if (CL2) issue_ts2(D, Hd, w0, true);
+            else issue_ts(D, Hd, w0, w1, true);
+          } else if (b == B_BLK) {                                                 // GNBlock GEMM (+ b2): first write of D
+            if (CL2) { issue_ss2(D, adesc, w0, false); mma_ss2(D, ones_desc, bias_desc + 4 * (SLAB >> 4), IDESC2, 1u); }
+            else { issue_ss(D, adesc, w0, w1, false); mma_ss(D, ones_desc, bias_desc + 4 * (SLAB >> 4), IDESC, 1u); }
           } else {                                                                 // FFN up-projection chunk (+ b1')
-            const int c = UPCHUNK_OF(b);
+            const int c = CHUNK_OF(b);
+            const uint32_t Hd = Hd0 + 128 * ub;
             if (CL2) { issue_ss2(Hd, adesc, w0, false); mma_ss2(Hd, ones_desc, bias_desc + c * (SLAB >> 4), IDESC2, 1u); }
             else { issue_ss(Hd, adesc, w0, w1, false); mma_ss(Hd, ones_desc, bias_desc + c * (SLAB >> 4), IDESC, 1u); }
-            COMMIT(EB_HIDFULL + hb);
+            COMMIT(EB_HIDFULL + ub);
           }
-          if (b == 6) COMMIT(EB_AEMPTY + st);                                      // last read of the A tile
-          if (b == 8) COMMIT(EB_OUTDONE + st);                                     // accumulator complete
+          if (b == B_LASTA) COMMIT(EB_AEMPTY + st);                                // last read of the A tile
+          if (b == 8) COMMIT(EB_OUTDONE);                                          // accumulator complete
           COMMIT(EB_WEMPTY + st0);
           if (!CL2) COMMIT(EB_WEMPTY + st1);
         }
         __syncwarp();
+        if (is_up) { ub = ub == 2 ? 0 : ub + 1; uq += ub == 0 ? 1u : 0u; }
+        if (is_dn) { db = db == 2 ? 0 : db + 1; dq += db == 0 ? 1u : 0u; }
       }
       EDBG(9);
     }
@@ -360,10 +363,9 @@ __global__ void __launch_bounds__(E_THREADS, 1) k_edge5(const EdgeArgs a) {
     const int dq = warp - 8;                 // TMEM lane quadrant (== warp % 4)
     const uint32_t lane_base = ((uint32_t)(dq * 32)) << 16;
     uint32_t tl = 0;
-    // TMEM fp32 -> +b1 -> relu -> bf16 pairs -> TMEM, in place.  TMEM loads queue behind the running MMAs (several hundred
-    // cycles each under load), so two 32-column loads are kept in flight; the store of columns [16j,16j+16) only
-    // overwrites columns whose load has completed.
-    // (the bias is already in the accumulator: the MMA warp adds it with a K = 16 step)
+    // TMEM fp32 -> relu -> bf16 pairs -> TMEM, in place (the bias is already in the accumulator: the MMA warp adds it with a
+    // K = 16 step).  Two 32-column loads are kept in flight; the store of columns [16j,16j+16) only overwrites columns whose
+    // load has completed.  (tcgen05.ld + wait is ~22 cycles even under a full UMMA queue: tools/micro/tmem_lat.cu)
     auto cvt32 = [&](const uint32_t (&v)[32], uint32_t dst) {
       uint32_t p[16];
 #pragma unroll
@@ -386,33 +388,21 @@ __global__ void __launch_bounds__(E_THREADS, 1) k_edge5(const EdgeArgs a) {
       tc_wait_st();
       tc_fence_before();
     };
-    auto conv = [&](int c) {      // chunk c of whichever pass the MMA warp is feeding: the barrier phases repeat per pass
-      mbar_wait(BAR(EB_HIDFULL + (c & 1)), (c >> 1) & 1);
+    uint32_t cb = 0, cq = 0;      // position in the stream of hidden chunks: buffer, use count
+    auto conv = [&](int c) {
+      mbar_wait(BAR(EB_HIDFULL + cb), cq & 1);
       EDBG(1 + 2 * c);
       tc_fence_after();
-      convert((c & 1) ? HdB : HdA);
-      ARRIVE_LEADER(EB_HSREADY + (c & 1));
+      convert(Hd0 + 128 * cb);
+      ARRIVE_LEADER(EB_HSREADY + cb);
       EDBG(2 + 2 * c);
+      cb = cb == 2 ? 0 : cb + 1; cq += cb == 0 ? 1u : 0u;
     };
-    // Software-pipelined over passes:  C2 C3 (pass t) | C0 C1 (pass t+1) | stage (pass t).  The staging copy has to wait for
-    // the OUT warps to drain this warp's two slices of the previous tile; with the first two chunks of the next pass converted
-    // before that wait, the MMA warp keeps four blocks of work (dn0 up2 dn1 up3) while this warp is blocked.  (Converting all
-    // four chunks first and staging last - round 1 - let the slowest quadrant gate every pass: 15 k cycles per tile.)
-#ifndef GNB_DRAIN_PIPELINED      /* default: all four chunks of a pass, then its staging copy (measured faster: 0.86 vs 0.89 ms) */
     for (tl = 0; (int)tl < npass && !wd_dead; tl++) {
-      const uint32_t st = tl & 1, uph = (tl >> 1) & 1;
       EDBG(0);
       conv(0); conv(1); conv(2); conv(3);
-#else
-    if (npass > 0 && !wd_dead) { tl = 0; EDBG(0); conv(0); conv(1); }
-    for (tl = 0; (int)tl < npass && !wd_dead; tl++) {
-      const uint32_t st = tl & 1, uph = (tl >> 1) & 1;
-      conv(2);
-      conv(3);
-      if ((int)tl + 1 < npass) { conv(0); conv(1); }
-#endif
       // ---------------- finished accumulator -> staging tile (row r = this thread; 4 column groups of 32 fp32)
-      mbar_wait(BAR(EB_OUTDONE + st), uph);
+      mbar_wait(BAR(EB_OUTDONE), tl & 1);
       EDBG(9);
       tc_fence_after();
       // the staging tile is handed over per 16-row slice: this warp's rows are slices 2 dq and 2 dq + 1, free as soon as the
@@ -420,7 +410,7 @@ __global__ void __launch_bounds__(E_THREADS, 1) k_edge5(const EdgeArgs a) {
       mbar_wait(BAR(EB_STGEMPTY + 2 * dq), (tl & 1) ^ 1);
       mbar_wait(BAR(EB_STGEMPTY + 2 * dq + 1), (tl & 1) ^ 1);
       EDBG(10);
-      const uint32_t D = tmem + 128 * st;
+      const uint32_t D = tmem;
       const int r = dq * 32 + lane;
       uint8_t* srow = sm + E_OFF_STG + r * 128;
       {
@@ -439,7 +429,7 @@ __global__ void __launch_bounds__(E_THREADS, 1) k_edge5(const EdgeArgs a) {
         TC_LD32(D + lane_base + 96, vb);
         tc_wait_ld();
         tc_fence_before();          // TMEM fully read: the accumulator goes back to the MMA warp
-        ARRIVE_LEADER(EB_ACCFREE + st);
+        ARRIVE_LEADER(EB_ACCFREE);
         put(va, 2);
         put(vb, 3);
       }
