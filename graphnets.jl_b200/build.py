@@ -37,6 +37,10 @@ def _digest():
 # its dead-lock (GNB_LIB_VARIANT=oldproj selects it in _lib.py); the product never loads a variant.
 VARIANTS = {"oldproj": (["tc.cu"], ["-DGNB_OLD_PROJ_PROTOCOL"]),
             "timing": (["tc_edge.cu"], ["-DGNB_TC_TIMING"])}      # clock64 phase stamps of the fused kernel (tools/edge_timing.py)
+# development only: GNB_AB_FLAGS="-DX=1" python build.py builds libgnb200_ab.so with those flags on the tensor-path sources, for
+# same-box A/B runs (tools/ab_edge.sh ab)
+if os.environ.get("GNB_AB_FLAGS"):
+    VARIANTS["ab"] = (["tc_edge.cu", "tc.cu", "tc_gemm.cu"], os.environ["GNB_AB_FLAGS"].split())
 
 
 def variant_path(name):

@@ -6,6 +6,7 @@
 #include <stdarg.h>
 #include <string.h>
 #include <vector>
+#include <atomic>
 #include <string>
 #include "../../include/gnb200.h"
 
@@ -40,6 +41,7 @@ void gnb_set_error(const char* fmt, ...);
 struct Arena {
   struct Chunk { char* base; size_t cap; size_t used; };
   std::vector<Chunk> chunks;
+  uint64_t gen = 0;      // bumped whenever the set of chunks changes (pointers handed out before are then stale)
   size_t min_chunk = (size_t)64 << 20;
   int alloc(size_t bytes, void** out);
   void reset();
@@ -55,9 +57,27 @@ struct WatchArgs {
 struct ProfRec { int tag; cudaEvent_t a, b; double bytes, flops; };
 struct ProfTag { const char* name; int64_t launches; double ms, bytes, flops; };
 
+// A whole forward captured as a CUDA graph (model.cu::gnb_model_forward): keyed by everything the enqueued work depends on.
+struct FwdGraph {
+  uint64_t model_id, graph_uid, arena_gen;
+  const void* ptr[6];
+  int precision, env_sig;
+  int seen;                  // eager calls with this key so far (the graph is captured on the second one)
+  cudaGraphExec_t exec;      // nullptr: not captured (yet), or capture not possible
+  bool no_graph;
+  int64_t launches;          // kernels in the graph (gnb_ctx::launches accounting)
+  uint64_t last_use;
+};
+
 struct gnb_ctx {
   int device = 0;
   bool profiling = false;
+  std::vector<FwdGraph> fwd_graphs;
+  uint64_t fwd_tick = 0;
+  // the legacy default stream cannot be captured: forwards bound to it are captured / replayed on this side stream, forked from
+  // and joined back into the caller's stream with events (same ordering as an eager forward)
+  cudaStream_t gstream = nullptr;
+  cudaEvent_t g_fork = nullptr, g_join = nullptr;
   std::vector<ProfRec> prof_recs;
   std::vector<ProfTag> prof_tags;
   std::vector<cudaEvent_t> ev_pool;
@@ -110,8 +130,10 @@ static inline bool ctx_first(gnb_ctx* c, int key) {
 // so that each of the eight 16-row epilogue warps of the fused kernel (tc_edge.cu) owns whole partial rows.
 constexpr int GNB_PART_ROWS = 16;
 
+inline std::atomic<uint64_t> g_graph_uids{1};
 struct gnb_graph {
   int device = 0;
+  uint64_t uid = g_graph_uids.fetch_add(1);      // never reused (a destroyed graph's address may be)
   int32_t B = 0, PN = 0;
   int64_t E = 0, N = 0;
   // device arrays

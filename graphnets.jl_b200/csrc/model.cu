@@ -41,6 +41,7 @@ int Arena::alloc(size_t bytes, void** out) {
     return GNB_ERR_OOM;
   }
   chunks.push_back({(char*)p, cap, bytes});
+  gen++;
   *out = p;
   return GNB_OK;
 }
@@ -53,6 +54,7 @@ void Arena::reset() {
     void* p = nullptr;
     for (auto& c : chunks) cudaFree(c.base);
     chunks.clear();
+    gen++;
     if (cudaMalloc(&p, total) == cudaSuccess) chunks.push_back({(char*)p, total, 0});
     else cudaGetLastError();
   }
@@ -60,6 +62,7 @@ void Arena::reset() {
 }
 void Arena::release() {
   for (auto& c : chunks) cudaFree(c.base);
+  gen++;
   chunks.clear();
 }
 
@@ -116,6 +119,10 @@ extern "C" int gnb_ctx_destroy(gnb_ctx* c) {
   if (c->done_ev) cudaEventDestroy(c->done_ev);
   if (c->d_abort) cudaFree(c->d_abort);
   if (c->h_abort) cudaFreeHost(c->h_abort);
+  for (auto& fg : c->fwd_graphs) if (fg.exec) cudaGraphExecDestroy(fg.exec);
+  if (c->gstream) cudaStreamDestroy(c->gstream);
+  if (c->g_fork) cudaEventDestroy(c->g_fork);
+  if (c->g_join) cudaEventDestroy(c->g_join);
   tc_lin_cache_free(c->lin_cache);
   if (c->pipe.copy) {
     cudaStreamDestroy(c->pipe.copy);
@@ -988,10 +995,116 @@ static int forward_device(gnb_ctx* ctx, const gnb_model* m, const gnb_graph* g, 
   return rc;
 }
 
+// ------------------------------------------------------------------ forward as a CUDA graph
+// A device-resident forward is 30-50 dependent launches of 5-900 us kernels: the launch gaps are 4 % of config 4's step and
+// most of config 2's.  The second forward with the same (model, graph, buffers, precision, workspace) is captured into a CUDA
+// graph and replayed from then on (steady-state serving / evaluation loops call with the same buffers).  Nothing in a forward
+// depends on host state other than the key: scratch comes from the bump arena (same sequence -> same pointers while the arena
+// generation is unchanged).  GNB_CUDA_GRAPH=0 disables; profiling (per-launch events) and callers that are themselves
+// capturing the stream always run eagerly.
+static int graphs_enabled() {
+  static const int on = [] { const char* e = getenv("GNB_CUDA_GRAPH"); return e ? atoi(e) : 1; }();
+  return on;
+}
+static int env_signature() {      // environment toggles that are read per launch (tests flip them between calls)
+  const char* p = getenv("GNB_EDGE_CTA_PAIR");
+  return p ? 1 + atoi(p) : 0;
+}
+static int forward_graphed(gnb_ctx* ctx, const gnb_model* m, const gnb_graph* g, const float* ef, const float* nf,
+                           const float* gf, float* out_ef, float* out_nf, float* out_gf, int precision) {
+  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+  if (!ctx || !m || !g || !graphs_enabled() || ctx->profiling ||
+      cudaStreamIsCapturing(ctx->stream, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone)
+    return forward_device(ctx, m, g, ef, nf, gf, out_ef, out_nf, out_gf, precision, true);
+  const void* ptr[6] = {ef, nf, gf, out_ef, out_nf, out_gf};
+  const int sig = env_signature();
+  const bool legacy = ctx->stream == nullptr || ctx->stream == cudaStreamLegacy;
+  FwdGraph* fg = nullptr;
+  for (auto& e : ctx->fwd_graphs)
+    if (e.model_id == m->id && e.graph_uid == g->uid && e.arena_gen == ctx->arena.gen && e.precision == precision &&
+        e.env_sig == sig && memcmp(e.ptr, ptr, sizeof(ptr)) == 0) { fg = &e; break; }
+  if (!fg) {
+    // first sight: run eagerly (sizes the arena, packs weights, sets function attributes); remember the key
+    const int rc = forward_device(ctx, m, g, ef, nf, gf, out_ef, out_nf, out_gf, precision, true);
+    if (rc != GNB_OK) return rc;
+    ctx->arena.reset();      // coalesce the workspace now (waits for the forward if it has to re-allocate): its addresses are final
+    if (ctx->fwd_graphs.size() >= 8) {      // evict the least recently used entry
+      size_t lru = 0;
+      for (size_t i = 1; i < ctx->fwd_graphs.size(); i++) if (ctx->fwd_graphs[i].last_use < ctx->fwd_graphs[lru].last_use) lru = i;
+      if (ctx->fwd_graphs[lru].exec) cudaGraphExecDestroy(ctx->fwd_graphs[lru].exec);
+      ctx->fwd_graphs.erase(ctx->fwd_graphs.begin() + lru);
+    }
+    FwdGraph e{};
+    e.model_id = m->id; e.graph_uid = g->uid; e.arena_gen = ctx->arena.gen; e.precision = precision; e.env_sig = sig;
+    memcpy(e.ptr, ptr, sizeof(ptr));
+    e.seen = 1; e.last_use = ++ctx->fwd_tick;
+    ctx->fwd_graphs.push_back(e);
+    return GNB_OK;
+  }
+  fg->last_use = ++ctx->fwd_tick;
+  if (!fg->exec && !fg->no_graph) {
+    // capture this forward (the capture itself executes nothing), then fall through to the replay
+    cudaSetDevice(ctx->device);
+    const int64_t l0 = ctx->launches;
+    const uint64_t gen0 = ctx->arena.gen;
+    cudaGraph_t graph = nullptr;
+    cudaStream_t user = ctx->stream;
+    bool ok = true;
+    if (legacy) {
+      if (!ctx->gstream) ok = cudaStreamCreateWithFlags(&ctx->gstream, cudaStreamNonBlocking) == cudaSuccess &&
+                              cudaEventCreateWithFlags(&ctx->g_fork, cudaEventDisableTiming) == cudaSuccess &&
+                              cudaEventCreateWithFlags(&ctx->g_join, cudaEventDisableTiming) == cudaSuccess;
+      if (ok) ctx->stream = ctx->gstream;
+    }
+    ok = ok && cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeRelaxed) == cudaSuccess;
+    int rc = GNB_OK;
+    if (ok) {
+      rc = forward_device_impl(ctx, m, g, ef, nf, gf, out_ef, out_nf, out_gf, precision, true);
+      ok = cudaStreamEndCapture(ctx->stream, &graph) == cudaSuccess && rc == GNB_OK && graph != nullptr && gen0 == ctx->arena.gen;
+    }
+    ctx->stream = user;
+    if (ok) ok = cudaGraphInstantiate(&fg->exec, graph, 0) == cudaSuccess;
+    if (graph) cudaGraphDestroy(graph);
+    fg->launches = ctx->launches - l0;
+    ctx->launches = l0;
+    if (!ok) {
+      cudaGetLastError();
+      fg->exec = nullptr;
+      fg->no_graph = true;
+      if (gen0 != ctx->arena.gen) fg->arena_gen = ~0ull;      // the workspace moved under the capture: this key is dead
+    }
+  }
+  if (!fg->exec) return forward_device(ctx, m, g, ef, nf, gf, out_ef, out_nf, out_gf, precision, true);
+  // replay, with the same cross-context ordering and watchdog mirror as an eager forward (forward_device)
+  const char* chain_env = getenv("GNB_CHAIN_FORWARDS");
+  const bool chain = ctx->device >= 0 && ctx->device < 64 && !(chain_env && atoi(chain_env) == 0);
+  std::unique_lock<std::mutex> lk(g_chain_mu, std::defer_lock);
+  if (chain) lk.lock();
+  const int d = ctx->device;
+  cudaSetDevice(d);
+  if (chain && g_chain_ctx[d] && g_chain_ctx[d] != ctx && g_chain_ev[d]) cudaStreamWaitEvent(ctx->stream, g_chain_ev[d], 0);
+  if (legacy) {
+    GNB_CUDA(cudaEventRecord(ctx->g_fork, ctx->stream));
+    GNB_CUDA(cudaStreamWaitEvent(ctx->gstream, ctx->g_fork, 0));
+    GNB_CUDA(cudaGraphLaunch(fg->exec, ctx->gstream));
+    GNB_CUDA(cudaEventRecord(ctx->g_join, ctx->gstream));
+    GNB_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->g_join, 0));
+  } else {
+    GNB_CUDA(cudaGraphLaunch(fg->exec, ctx->stream));
+  }
+  ctx->launches += fg->launches;
+  cudaMemcpyAsync(ctx->h_abort, ctx->d_abort, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream);
+  if (chain) {
+    if (!ctx->done_ev) cudaEventCreateWithFlags(&ctx->done_ev, cudaEventDisableTiming);
+    if (ctx->done_ev && cudaEventRecord(ctx->done_ev, ctx->stream) == cudaSuccess) { g_chain_ev[d] = ctx->done_ev; g_chain_ctx[d] = ctx; }
+  }
+  return GNB_OK;
+}
+
 extern "C" int gnb_model_forward(gnb_ctx* ctx, const gnb_model* m, const gnb_graph* g, const float* ef,
                                  const float* nf, const float* gf, float* out_ef, float* out_nf, float* out_gf,
                                  int precision) {
-  return forward_device(ctx, m, g, ef, nf, gf, out_ef, out_nf, out_gf, precision, true);
+  return forward_graphed(ctx, m, g, ef, nf, gf, out_ef, out_nf, out_gf, precision);
 }
 
 extern "C" int gnb_model_forward_host(gnb_ctx* ctx, const gnb_model* m, const gnb_graph* g, const float* ef,

@@ -319,10 +319,11 @@ __global__ void __launch_bounds__(E_THREADS, 1) k_edge5(const EdgeArgs a) {
       const uint32_t st = tl & 1, uph = (tl >> 1) & 1;
       const uint64_t adesc = umma_desc(base + E_OFF_A + st * BLK_BYTES);
       const uint32_t D = tmem;
-      // fully unrolled: which block is an up / block / down GEMM and its bias slab are compile-time constants - the issuing
-      // warp is a single dependent instruction stream and every instruction it does not execute shortens the gap between two
-      // 520-cycle UMMA blocks
-#pragma unroll
+      // A compact loop, NOT unrolled: the nine blocks unrolled are ~29 KB of straight-line code that every pass streams through
+      // the SM's instruction cache, which the four other roles' loops need (ncu: instruction-cache hit rate 70 %, "no
+      // instruction" the second largest stall reason of the kernel).  All branches are warp-uniform.
+      int upc = 0;      // hidden chunk of the next up block (its bias slab)
+#pragma unroll 1
       for (int b = 0; b < 9; b++) {
         EDBG(b);
         get_w();
@@ -340,7 +341,7 @@ __global__ void __launch_bounds__(E_THREADS, 1) k_edge5(const EdgeArgs a) {
             if (CL2) { issue_ss2(D, adesc, w0, false); mma_ss2(D, ones_desc, bias_desc + 4 * (SLAB >> 4), IDESC2, 1u); }
             else { issue_ss(D, adesc, w0, w1, false); mma_ss(D, ones_desc, bias_desc + 4 * (SLAB >> 4), IDESC, 1u); }
           } else {                                                                 // FFN up-projection chunk (+ b1')
-            const int c = CHUNK_OF(b);
+            const int c = upc;
             const uint32_t Hd = Hd0 + 128 * ub;
             if (CL2) { issue_ss2(Hd, adesc, w0, false); mma_ss2(Hd, ones_desc, bias_desc + c * (SLAB >> 4), IDESC2, 1u); }
             else { issue_ss(Hd, adesc, w0, w1, false); mma_ss(Hd, ones_desc, bias_desc + c * (SLAB >> 4), IDESC, 1u); }
@@ -352,7 +353,7 @@ __global__ void __launch_bounds__(E_THREADS, 1) k_edge5(const EdgeArgs a) {
           if (!CL2) COMMIT(EB_WEMPTY + st1);
         }
         __syncwarp();
-        if (is_up) { ub = ub == 2 ? 0 : ub + 1; uq += ub == 0 ? 1u : 0u; }
+        if (is_up) { ub = ub == 2 ? 0 : ub + 1; uq += ub == 0 ? 1u : 0u; upc++; }
         if (is_dn) { db = db == 2 ? 0 : db + 1; dq += db == 0 ? 1u : 0u; }
       }
       EDBG(9);
@@ -400,7 +401,8 @@ __global__ void __launch_bounds__(E_THREADS, 1) k_edge5(const EdgeArgs a) {
     };
     for (tl = 0; (int)tl < npass && !wd_dead; tl++) {
       EDBG(0);
-      conv(0); conv(1); conv(2); conv(3);
+#pragma unroll 1
+      for (int c = 0; c < 4; c++) conv(c);      // one copy of the conversion code (instruction cache)
       // ---------------- finished accumulator -> staging tile (row r = this thread; 4 column groups of 32 fp32)
       mbar_wait(BAR(EB_OUTDONE), tl & 1);
       EDBG(9);

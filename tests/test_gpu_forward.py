@@ -193,6 +193,56 @@ def test_forward_host_pipelined_copies(gn, precision):
         assert np.array_equal(og, y.gf.compact.cpu().numpy()), rep
 
 
+@pytest.mark.parametrize("precision,side_stream", [("auto", False), ("auto", True), ("fp32", False)])
+def test_forward_replayed_as_cuda_graph(gn, precision, side_stream):
+    """gnb_model_forward captures the second forward with the same (model, graph, buffers) into a CUDA graph and replays it
+    from then on (model.cu::forward_graphed): replays must equal the eager result bit for bit - with the context bound to
+    torch's legacy default stream (captured on the library's side stream) and to a side stream - see new inputs written into
+    the same buffers, and a call with different buffers in between must not disturb the cached graph."""
+    import ctypes as C
+    w = W.make_workload("cfg4", B=64, seed=11)
+    layers = W.model_params("cfg4")
+    model = W.to_gn_model(gn, layers)
+    x = gn.batch(W.as_batch_input(w))
+    eng = x.graphs.engine
+    stream = torch.cuda.Stream() if side_stream else torch.cuda.current_stream()
+    with torch.cuda.stream(stream):
+        y0 = model(x, precision=precision)      # eager (new output buffers each call -> new keys)
+        ref = [t.compact.clone() for t in (y0.ef, y0.nf, y0.gf)]
+        h = model._model(eng)
+        eng.bind_stream()
+        outs = [torch.full_like(r, float("nan")) for r in ref]
+        ptr = lambda t: C.c_void_p(t.data_ptr())
+        prec = gn.pkg._lib.PRECISIONS[precision]
+        call = lambda ef_t, o: gn.lib.gnb_model_forward(eng.ctx, h, x.graphs.handle, ptr(ef_t), ptr(x.nf.compact), None,
+                                                        ptr(o[0]), ptr(o[1]), ptr(o[2]), prec)
+        l0 = eng.launches
+        for rep in range(5):      # 1: eager, 2: capture + replay, 3..: replay
+            for o in outs: o.fill_(float("nan"))
+            assert call(x.ef.compact, outs) == 0, gn.lib.gnb_last_error()
+            eng.sync()
+            for o, r in zip(outs, ref): assert torch.equal(o, r), (rep, precision)
+            if rep == 2:      # another key in between
+                other = [torch.empty_like(r) for r in ref]
+                assert call(x.ef.compact, other) == 0
+                eng.sync()
+                for o, r in zip(other, ref): assert torch.equal(o, r)
+        assert eng.launches > l0      # replays are accounted like eager launches
+        # new data in the same input buffer: the graph reads the buffer, not a snapshot
+        ef2 = x.ef.compact.clone()
+        x.ef.compact.mul_(0.5)
+        assert call(x.ef.compact, outs) == 0
+        eng.sync()
+        y_half = [o.clone() for o in outs]
+        x.ef.compact.copy_(ef2)
+        eager = [torch.empty_like(r) for r in ref]      # fresh buffers -> eager
+        x_half = ef2 * 0.5
+        assert call(x_half, eager) == 0
+        eng.sync()
+        for a_, b_ in zip(y_half, eager): assert torch.equal(a_, b_)
+    torch.cuda.synchronize()
+
+
 def test_single_layer_abi_entry_points(gn):
     """gnb_block_forward / gnb_core_forward / gnb_corelist_forward on caller-owned device weights."""
     import ctypes as C

@@ -44,7 +44,7 @@ def show(name, warps, slots, labels):
     print("  mean deltas:", " ".join("%s=%.0f" % (l, v) for l, v in zip(labels[1:], dd)))
 
 
-show("MMA warp (start of each block)", [MMA], list(range(10)), ["up0", "up1", "blk", "dn0", "dn1", "up2", "up3", "dn2", "dn3", "end"])
+show("MMA warp (start of each block)", [MMA], list(range(10)), ["up0", "up1", "up2", "blk", "dn0", "up3", "dn1", "dn2", "dn3", "end"])
 show("DRAIN warps", DRAIN, list(range(12)), ["start", "hf0", "hs0", "hf1", "hs1", "hf2", "hs2", "hf3", "hs3", "outdone", "stgempty", "stgfull"])
 show("LN warps", LN, list(range(7)), ["start", "aempty", "g0", "g1", "g2", "g3", "arrive"])
 show("OUT warps (last slice of the stamped pass per warp)", OUT, list(range(3)), ["start", "stgfull", "done"])
