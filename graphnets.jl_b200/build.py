@@ -39,8 +39,11 @@ VARIANTS = {"oldproj": (["tc.cu"], ["-DGNB_OLD_PROJ_PROTOCOL"]),
             "timing": (["tc_edge.cu"], ["-DGNB_TC_TIMING"])}      # clock64 phase stamps of the fused kernel (tools/edge_timing.py)
 # development only: GNB_AB_FLAGS="-DX=1" python build.py builds libgnb200_ab.so with those flags on the tensor-path sources, for
 # same-box A/B runs (tools/ab_edge.sh ab)
+# several at once: GNB_AB_FLAGS="ab1:-DX=1;ab2:-DY=1 -DZ" builds libgnb200_ab1.so, libgnb200_ab2.so
 if os.environ.get("GNB_AB_FLAGS"):
-    VARIANTS["ab"] = (["tc_edge.cu", "tc.cu", "tc_gemm.cu"], os.environ["GNB_AB_FLAGS"].split())
+    for i, spec in enumerate(os.environ["GNB_AB_FLAGS"].split(";")):
+        name, _, flags = spec.partition(":") if ":" in spec else ("ab" if i == 0 else "ab%d" % i, "", spec)
+        VARIANTS[name.strip()] = (["tc_edge.cu", "tc.cu", "tc_gemm.cu"], flags.split())
 
 
 def variant_path(name):

@@ -415,6 +415,11 @@ __global__ void __launch_bounds__(E_THREADS, 1) k_edge5(const EdgeArgs a) {
       const uint32_t D = tmem;
       const int r = dq * 32 + lane;
       uint8_t* srow = sm + E_OFF_STG + r * 128;
+#ifdef GNB_ABL_DRAIN_NOSTG
+      tc_fence_before();
+      ARRIVE_LEADER(EB_ACCFREE);
+      if (a.R < 0)
+#endif
       {
         uint32_t va[32], vb[32];
         auto put = [&](const uint32_t (&v)[32], int g) {
@@ -477,10 +482,15 @@ __global__ void __launch_bounds__(E_THREADS, 1) k_edge5(const EdgeArgs a) {
           for (int j = 0; j < 4; j++) xa[h][j] = __ldg(p + 8 * j);
         }
       };
+#ifndef GNB_ABL_LN_NONE
       issue(0);
+#endif
       mbar_wait(BAR(EB_AEMPTY + stage), aph ^ 1);
       EDBG(1);
       uint8_t* A = sm + E_OFF_A + stage * BLK_BYTES;
+#ifdef GNB_ABL_LN_NONE
+      if (a.R < 0)
+#endif
 #pragma unroll 1
       for (int i0 = 0; i0 < 32; i0 += 8) {
         float4 xc[2][4];
@@ -533,6 +543,9 @@ __global__ void __launch_bounds__(E_THREADS, 1) k_edge5(const EdgeArgs a) {
       }
       // ---- ordered partial sums per (32-row block, receiver) run, taken over the bf16 operand the MMAs consume
       __syncwarp();
+#ifdef GNB_ABL_LN_NOPART
+      if (a.R < 0)
+#endif
       {
         float4 acc = f4zero();
 #pragma unroll 1
@@ -599,13 +612,28 @@ __global__ void __launch_bounds__(E_THREADS, 1) k_edge5(const EdgeArgs a) {
 #pragma unroll
       for (int c = 0; c < 4; c++) wdec[c] = __ldg(reinterpret_cast<const float4*>(a.decW) + 4 * lane + c);
     }
-    float4 xa[4];
-    typename std::conditional<PBF, uint2, float4>::type pa[4], pb[4];
+    // NG groups of four rows of loads in flight per warp: two where the registers allow it (bf16 gathered rows, no fused decoder)
+#ifndef GNB_OUT_NG
+#define GNB_OUT_NG 1      /* 2 (eight rows in flight) measured 2 % slower: the role is not bound by its loads in flight (profiles/r02_summary.md) */
+#endif
+    constexpr int NG = (PBF && !DEC) ? GNB_OUT_NG : 1;
+    constexpr int WIN = 4 * NG;
+    static_assert(OUT_ROWS % WIN == 0, "the window keeps its slot numbering across slices only if it divides the slice");
+    float4 xa[WIN];
+    typename std::conditional<PBF, uint2, float4>::type pa[WIN], pb[WIN];
     auto issue1 = [&](int u, int64_t rb, int src_i1, int src_i2, int i) {
       const int i1 = __shfl_sync(0xffffffffu, src_i1, i), i2 = __shfl_sync(0xffffffffu, src_i2, i);
       int64_t r = rb + i;
       r = r < a.R ? r : a.R - 1;
+#ifdef GNB_ABL_OUT_NOX      /* GNB_ABL_*: timing-only ablations (results wrong), tools/ab_edge.sh */
+      xa[u] = f4zero();
+#else
       xa[u] = ld_stream(xbase + (size_t)r * H);                       // second and last read of x: L2 hit
+#endif
+#ifdef GNB_ABL_OUT_NOGATHER
+      if constexpr (PBF) { pa[u] = make_uint2(0u, 0u); pb[u] = pa[u]; } else { pa[u] = f4zero(); pb[u] = pa[u]; }
+      return;
+#endif
       if constexpr (PBF) {
         pa[u] = __ldg(reinterpret_cast<const uint2*>(base1 + (size_t)i1 * ldb1));
         pb[u] = __ldg(reinterpret_cast<const uint2*>(base2 + (size_t)i2 * ldb2));
@@ -622,7 +650,7 @@ __global__ void __launch_bounds__(E_THREADS, 1) k_edge5(const EdgeArgs a) {
     if (ow < total) {
       load_attr(slice_row0(ow), c_i1, c_i2, c_pid);
 #pragma unroll
-      for (int u = 0; u < 4; u++) issue1(u, slice_row0(ow), c_i1, c_i2, u);
+      for (int u = 0; u < WIN; u++) issue1(u, slice_row0(ow), c_i1, c_i2, u);
     }
     for (int k = ow; k < total && !wd_dead; k += OUT_WARPS) {
       const uint32_t tl = (uint32_t)k >> 3;
@@ -641,40 +669,53 @@ __global__ void __launch_bounds__(E_THREADS, 1) k_edge5(const EdgeArgs a) {
       mbar_wait(BAR(EB_STGFULL + sl), tl & 1);
       EDBG(1);
       float4 acc = f4zero();
+#ifdef GNB_ABL_OUT_NONE
+      if (a.R < 0)
+#endif
 #pragma unroll 1
-      for (int i0 = 0; i0 < OUT_ROWS; i0 += 4) {
+      for (int j0 = 0; j0 < OUT_ROWS; j0 += WIN) {
+#pragma unroll
+      for (int hg = 0; hg < NG; hg++) {      // group hg of the window: slots 4 hg .. 4 hg + 3
+        const int i0 = j0 + 4 * hg;
         float4 d[4];
 #pragma unroll
         for (int u = 0; u < 4; u++) {
           const int i = i0 + u;
           d[u] = *reinterpret_cast<const float4*>(sm + s_lane + i * 128 + ((s_chunk ^ (uint32_t)(i & 7)) << 4));
         }
-        // where the refills of this group come from: the next group of this slice or the first group of the next slice
-        const bool cur = i0 + 4 < OUT_ROWS;
+        // where the refills of this group come from: WIN rows further down this slice, or the head of this warp's next slice
+        const bool cur = i0 + WIN < OUT_ROWS;
         const int64_t rb = cur ? row0 : nrow0;
         const int s1 = cur ? c_i1 : n_i1, s2 = cur ? c_i2 : n_i2;
-        const int ib = cur ? i0 + 4 : 0;
+        const int ib = cur ? i0 + WIN : i0 + WIN - OUT_ROWS;
         const bool refill = cur || has_next;      // warp-uniform
         float od[16];      // DEC: this lane's share of the 4 decoder outputs of the 4 rows of the group
 #pragma unroll
-        for (int u = 0; u < 4; u++) {
-          const int i = i0 + u;
+        for (int uu = 0; uu < 4; uu++) {
+          const int u = 4 * hg + uu;      // window slot
+          const int i = i0 + uu;
           const float4 g = gathered(u);
-          const float4 y = add4(add4(xa[u], g), d[u]);      // (b2 is in the accumulator)
+          const float4 y = add4(add4(xa[u], g), d[uu]);      // (b2 is in the accumulator)
           if (DEC) {
-            od[4 * u + 0] = fmaf(y.w, wdec[3].x, fmaf(y.z, wdec[2].x, fmaf(y.y, wdec[1].x, y.x * wdec[0].x)));
-            od[4 * u + 1] = fmaf(y.w, wdec[3].y, fmaf(y.z, wdec[2].y, fmaf(y.y, wdec[1].y, y.x * wdec[0].y)));
-            od[4 * u + 2] = fmaf(y.w, wdec[3].z, fmaf(y.z, wdec[2].z, fmaf(y.y, wdec[1].z, y.x * wdec[0].z)));
-            od[4 * u + 3] = fmaf(y.w, wdec[3].w, fmaf(y.z, wdec[2].w, fmaf(y.y, wdec[1].w, y.x * wdec[0].w)));
+            od[4 * uu + 0] = fmaf(y.w, wdec[3].x, fmaf(y.z, wdec[2].x, fmaf(y.y, wdec[1].x, y.x * wdec[0].x)));
+            od[4 * uu + 1] = fmaf(y.w, wdec[3].y, fmaf(y.z, wdec[2].y, fmaf(y.y, wdec[1].y, y.x * wdec[0].y)));
+            od[4 * uu + 2] = fmaf(y.w, wdec[3].z, fmaf(y.z, wdec[2].z, fmaf(y.y, wdec[1].z, y.x * wdec[0].z)));
+            od[4 * uu + 3] = fmaf(y.w, wdec[3].w, fmaf(y.z, wdec[2].w, fmaf(y.y, wdec[1].w, y.x * wdec[0].w)));
           } else if (i < rows) {
+#ifndef GNB_ABL_OUT_NOSTORE
             __stcs(reinterpret_cast<float4*>(a.y + (size_t)(row0 + i) * H) + lane, y);
+#else
+            if (y.x == 123.456f) a.y[0] = y.y;
+#endif
           }
           acc = add4(acc, g);
           const bool fl = (endmask >> i) & 1u;
+#ifndef GNB_ABL_OUT_NOSTORE
           if (fl) *(reinterpret_cast<float4*>(a.Gpart + (size_t)pid * H) + lane) = acc;
+#endif
           acc.x = fl ? 0.f : acc.x; acc.y = fl ? 0.f : acc.y; acc.z = fl ? 0.f : acc.z; acc.w = fl ? 0.f : acc.w;
           pid += fl ? 1 : 0;
-          if (refill) issue1(u, rb, s1, s2, ib + u);
+          if (refill) issue1(u, rb, s1, s2, ib + uu);
         }
         if (DEC) {
           // 16 totals (4 rows x 4 outputs) land on the even lanes: value 8 b4 + 4 b3 + 2 b2 + b1 = 4 u + j, i.e. 16 consecutive floats
@@ -682,6 +723,7 @@ __global__ void __launch_bounds__(E_THREADS, 1) k_edge5(const EdgeArgs a) {
           const int vi = lane >> 1;
           if ((lane & 1) == 0 && i0 + (vi >> 2) < rows) a.dec_out[(size_t)(row0 + i0) * 4 + vi] = t;
         }
+      }
       }
       ARRIVE_LOCAL(EB_STGEMPTY + sl);
       EDBG(2);

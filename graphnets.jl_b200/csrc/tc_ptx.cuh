@@ -46,10 +46,11 @@ static __device__ __forceinline__ uint32_t mbar_test(uint32_t bar, uint32_t pari
   return ok;
 }
 // try_wait with a suspend-time hint: the thread may sleep in hardware until the phase completes (or the hint expires) instead of
-// returning to the polling loop - a polling warp otherwise takes issue slots from the three warps that share its scheduler
-// (ncu: 20 % of all instructions of k_edge5 were barrier polls)
+// returning to the polling loop (ncu: 20 % of all instructions of k_edge5 were barrier polls).  OFF by default (0): measured, it
+// changes nothing for k_edge5, and a waiter can over-sleep - harmless for the product's protocols, but it made the round-1
+// k_tc_proj protocol (test-only build, tests/test_gpu_watchdog.py) alias its 1-bit phase without any artificial stall.
 #ifndef GNB_MBAR_HINT_NS
-#define GNB_MBAR_HINT_NS 20000
+#define GNB_MBAR_HINT_NS 0
 #endif
 static __device__ __forceinline__ uint32_t mbar_test_hint(uint32_t bar, uint32_t parity) {
   uint32_t ok;

@@ -4,7 +4,9 @@ Round 1's two-context mode dead-locked (bounded spin -> __trap -> dead CUDA cont
 k_tc_proj waited on AFULL, a barrier whose producers do not wait for them, with a 1-bit phase parity; a drain warp delayed by
 more than one tile found the barrier two phases ahead and waited forever (csrc/tc.cu, protocol comment).  These tests
   (a) reproduce that dead-lock deterministically with the round-1 protocol (test-only build libgnb200_oldproj.so) by stalling
-      the drain warps, and show that the watchdog turns it into GNB_ERR_TIMEOUT with the CUDA context still usable;
+      the drain warps, and show that the watchdog turns it into GNB_ERR_TIMEOUT with the CUDA context still usable (since the
+      round-2 kernels changed the relative speed of the roles, the old protocol dead-locks even WITHOUT the stall - it was a
+      race, not a corner case - so the usability check of that mode runs on the fp32 path);
   (b) show that the product protocol computes bit-identical results under the same stall."""
 import json
 import os
@@ -43,10 +45,3 @@ def test_round1_protocol_deadlock_is_reproduced_and_caught():
     res = _probe("oldproj", 2048, 40000, 1500)
     assert res["timeout"], "the round-1 protocol was expected to dead-lock under a stalled drain: %s" % res
     assert res["usable"], "the CUDA context must stay usable after a fired watchdog: %s" % res
-
-
-def test_round1_protocol_without_stall_still_passes():
-    if not os.path.exists(os.path.join(ROOT, "graphnets.jl_b200", "libgnb200_oldproj.so")):
-        pytest.skip("test-only variant library not built")
-    res = _probe("oldproj", 2048, 0, 20000)
-    assert res == {"timeout": False, "equal": True, "usable": True}, res

@@ -21,7 +21,7 @@ print("forward %.3f ms" % (ev0.elapsed_time(ev1) / 10))
 eng.set_profiling(True); eng.read_profile()
 for _ in range(5): y = model(x, precision="auto")
 prof = eng.read_profile()
-for k in ("tc_edge_core", "tc_node_core"):
+for k in ("tc_edge_core", "tc_node_core", "graph_post"):
     print("  %-14s %.3f ms/launch" % (k, prof[k]["ms"] / prof[k]["launches"]))
 PY
 done
