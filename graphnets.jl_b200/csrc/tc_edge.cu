@@ -155,7 +155,7 @@ __device__ __forceinline__ float warp_sum16(const float (&v)[16], int lane) {
 // DEC: fused narrow decoder - the OUT warps do not store y but y . decW (EdgeArgs::decW)
 // PBF: the gathered addend rows are bf16 (EdgeArgs::add_bf16: the edges' P_s | P_r'), else fp32 (the nodes' P_agg, P_un)
 template <bool CL2, bool DEC, bool PBF>
-__global__ void __launch_bounds__(E_THREADS, 1) k_edge5(const EdgeArgs a) {
+__global__ void __launch_bounds__(E_THREADS, 1) k_edge5(const __grid_constant__ EdgeArgs a) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
@@ -646,6 +646,8 @@ __global__ void __launch_bounds__(E_THREADS, 1) k_edge5(const EdgeArgs a) {
       if constexpr (PBF) return add4(bf4(pa[u]), bf4(pb[u]));
       else return add4(pa[u], pb[u]);
     };
+    uint64_t pol_ef = 0;      // L2 evict-first policy of the TMA stores (y is not read again by this kernel)
+    if (!DEC) asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_ef));
     int c_i1 = 0, c_i2 = 0, c_pid = -1, n_i1 = 0, n_i2 = 0, n_pid = -1;
     if (ow < total) {
       load_attr(slice_row0(ow), c_i1, c_i2, c_pid);
@@ -702,16 +704,19 @@ __global__ void __launch_bounds__(E_THREADS, 1) k_edge5(const EdgeArgs a) {
             od[4 * uu + 2] = fmaf(y.w, wdec[3].z, fmaf(y.z, wdec[2].z, fmaf(y.y, wdec[1].z, y.x * wdec[0].z)));
             od[4 * uu + 3] = fmaf(y.w, wdec[3].w, fmaf(y.z, wdec[2].w, fmaf(y.y, wdec[1].w, y.x * wdec[0].w)));
           } else if (i < rows) {
-#ifndef GNB_ABL_OUT_NOSTORE
-            __stcs(reinterpret_cast<float4*>(a.y + (size_t)(row0 + i) * H) + lane, y);
+#if !defined(GNB_ABL_OUT_NOSTORE) && !defined(GNB_ABL_OUT_NOY)
+            if (a.y_tma) *reinterpret_cast<float4*>(sm + s_lane + i * 128 + ((s_chunk ^ (uint32_t)(i & 7)) << 4)) = y;      // in place of d
+            else __stcs(reinterpret_cast<float4*>(a.y + (size_t)(row0 + i) * H) + lane, y);
 #else
             if (y.x == 123.456f) a.y[0] = y.y;
 #endif
           }
           acc = add4(acc, g);
           const bool fl = (endmask >> i) & 1u;
-#ifndef GNB_ABL_OUT_NOSTORE
+#if !defined(GNB_ABL_OUT_NOSTORE) && !defined(GNB_ABL_OUT_NOGP)
           if (fl) *(reinterpret_cast<float4*>(a.Gpart + (size_t)pid * H) + lane) = acc;
+#elif defined(GNB_ABL_OUT_NOGP)
+          if (fl && acc.x == 123.456f) a.Gpart[0] = acc.y;
 #endif
           acc.x = fl ? 0.f : acc.x; acc.y = fl ? 0.f : acc.y; acc.z = fl ? 0.f : acc.z; acc.w = fl ? 0.f : acc.w;
           pid += fl ? 1 : 0;
@@ -724,6 +729,22 @@ __global__ void __launch_bounds__(E_THREADS, 1) k_edge5(const EdgeArgs a) {
           if ((lane & 1) == 0 && i0 + (vi >> 2) < rows) a.dec_out[(size_t)(row0 + i0) * 4 + vi] = t;
         }
       }
+      }
+      if (!DEC && a.y_tma) {
+        // the slice now holds y in the staging layout = four 16 x 128 B boxes in the 128B-swizzle pattern of the tensor map
+        fence_async_smem();      // this thread's generic-proxy writes -> visible to the TMA engine (async proxy)
+        __syncwarp();
+        if (lane == 0 && rows > 0) {
+          const uint32_t s0 = base + (uint32_t)(E_OFF_STG + (OUT_ROWS * sl) * 128);
+#pragma unroll
+          for (int g = 0; g < 4; g++)
+            asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group.L2::cache_hint [%0, {%1, %2}], [%3], %4;"
+                         ::"l"(reinterpret_cast<uint64_t>(&a.ymap)), "r"(32 * g), "r"((int)row0), "r"(s0 + (uint32_t)g * 16384u), "l"(pol_ef)
+                         : "memory");
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");      // the slice may be refilled once the engine has read it
+        }
+        __syncwarp();
       }
       ARRIVE_LOCAL(EB_STGEMPTY + sl);
       EDBG(2);
@@ -763,8 +784,37 @@ int edge5_smem_attr() {
 }
 }  // namespace
 
-int launch_edge5(gnb_ctx* ctx, const EdgeArgs& a, const char* name, double flops, double bytes) {
-  if (a.num_tiles <= 0) return GNB_OK;
+// cuTensorMapEncodeTiled through the runtime's driver entry point (the library does not link libcuda)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) p = nullptr;
+    cudaGetLastError();
+    return (EncodeTiledFn)p;
+  }();
+  return fn;
+}
+
+int launch_edge5(gnb_ctx* ctx, const EdgeArgs& a_in, const char* name, double flops, double bytes) {
+  if (a_in.num_tiles <= 0) return GNB_OK;
+  EdgeArgs a = a_in;
+  a.y_tma = 0;
+  static const bool tma_env = getenv("GNB_EDGE_NO_TMA_STORE") == nullptr;      // A/B toggle
+  if (a.decW == nullptr && a.y != nullptr && tma_env && encode_tiled_fn()) {
+    // y [R][128] fp32: box = 32 columns x 16 rows (one column group of one OUT slice), 128 B swizzle == the staging layout
+    const cuuint64_t dims[2] = {128, (cuuint64_t)a.R};
+    const cuuint64_t strides[1] = {512};
+    const cuuint32_t box[2] = {32, (cuuint32_t)OUT_ROWS};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult r = encode_tiled_fn()(&a.ymap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, a.y, dims, strides, box, estr,
+                                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                         CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    a.y_tma = r == CUDA_SUCCESS ? 1 : 0;
+  }
   // GNB_EDGE_CTA_PAIR=0: one CTA per tile stream (cta_group::1).  Read per launch so that a test can run both instantiations.
   const char* pair_env = getenv("GNB_EDGE_CTA_PAIR");
   const bool cl2 = (pair_env ? atoi(pair_env) : 1) && ctx->sm_count >= 2;

@@ -1,5 +1,6 @@
 // Fused GNCore edge kernel (tcgen05, generation 5); internal interface.
 #pragma once
+#include <cuda.h>      // CUtensorMap (types only: the driver entry point is resolved at run time, no -lcuda)
 #include <cuda_bf16.h>
 #include "common.cuh"
 
@@ -30,6 +31,10 @@ struct EdgeArgs {
   // outputs) - y itself is consumed by nothing else, so 2 x R x 512 B of HBM traffic and one full streaming pass disappear.
   const float* decW;     // [128][4] k-major, nullptr: store y as usual
   float* dec_out;        // [R][4]
+  // y as a 2-D tensor map (launch_edge5 fills it): the OUT warps write the finished rows back into the staging tile and one lane
+  // stores a 16-row slice with four cp.async.bulk.tensor (TMA) stores - 8 KB bursts instead of 512 B per-row stores
+  int y_tma;
+  alignas(64) CUtensorMap ymap;
 };
 
 int launch_edge5(gnb_ctx* ctx, const EdgeArgs& a, const char* name, double flops, double bytes);
