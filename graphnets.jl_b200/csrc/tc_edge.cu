@@ -123,6 +123,33 @@ __device__ __forceinline__ float4 ld_stream(const float* p) {   // read-once dat
   asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
   return v;
 }
+// x is read twice by a CTA, two to three tile periods apart (LayerNorm warps, then the residual of the OUT warps).  ncu showed
+// 45 % of the second reads missing L2 (0.48 GB of DRAM reads per launch): the first read (and the prefetch) mark the lines
+// evict_last, the second one evict_first.
+#ifndef GNB_X_L2_HINTS
+#define GNB_X_L2_HINTS 1
+#endif
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ float4 ld_hint(const float4* p, uint64_t pol) {
+  float4 v;
+  asm volatile("ld.global.nc.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p), "l"(pol));
+  return v;
+}
+__device__ __forceinline__ float4 ld_stream_hint(const float* p, uint64_t pol) {
+  float4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p), "l"(pol));
+  return v;
+}
 
 // CL2: the two CTAs of a cluster (an SM pair) run one 256-row MMA stream (cta_group::2): each CTA holds half of every weight
 // block (N split) - half the weight bytes per SM and a ring twice as deep in blocks - and its own 128-row tile otherwise.
@@ -264,7 +291,10 @@ __global__ void __launch_bounds__(E_THREADS, 1) k_edge5(const __grid_constant__ 
       const int64_t pre0 = ((int64_t)tile + 2 * (int64_t)grid) * TM;
       if (pre0 < a.R && elect_one()) {
         const int64_t prows = a.R - pre0 < TM ? a.R - pre0 : TM;
-        bulk_prefetch_l2(a.x + (size_t)pre0 * H, (uint32_t)(prows * H * sizeof(float)));
+        if (GNB_X_L2_HINTS)
+          asm volatile("cp.async.bulk.prefetch.L2.global.L2::cache_hint [%0], %1, %2;" ::"l"(a.x + (size_t)pre0 * H),
+                       "r"((uint32_t)(prows * H * sizeof(float))), "l"(l2_policy_evict_last()) : "memory");
+        else bulk_prefetch_l2(a.x + (size_t)pre0 * H, (uint32_t)(prows * H * sizeof(float)));
       }
       __syncwarp();
 #pragma unroll 1
@@ -459,6 +489,7 @@ __global__ void __launch_bounds__(E_THREADS, 1) k_edge5(const __grid_constant__ 
     const uint32_t p_chunk = (uint32_t)((lane & 15) >> 1);
     const float e_add = a.eps_mode == GNB_EPS_SQRT_VAR_EPS2 ? a.eps * a.eps : (a.eps_mode == GNB_EPS_STD_PLUS_EPS ? 0.f : a.eps);
     const float e_plus = a.eps_mode == GNB_EPS_STD_PLUS_EPS ? a.eps : 0.f;
+    const uint64_t pol_last = l2_policy_evict_last();
     uint32_t tl = 0;
     for (int tile = blockIdx.x; TILE_OK(tile); tile += grid, tl++) {
       const uint32_t stage = tl & 1, aph = (tl >> 1) & 1;
@@ -479,7 +510,7 @@ __global__ void __launch_bounds__(E_THREADS, 1) k_edge5(const __grid_constant__ 
           r = r < a.R ? r : a.R - 1;      // rows past the end re-read the last row; masked below
           const float4* p = reinterpret_cast<const float4*>(xbase + (size_t)r * H);
 #pragma unroll
-          for (int j = 0; j < 4; j++) xa[h][j] = __ldg(p + 8 * j);
+          for (int j = 0; j < 4; j++) xa[h][j] = GNB_X_L2_HINTS ? ld_hint(p + 8 * j, pol_last) : __ldg(p + 8 * j);
         }
       };
 #ifndef GNB_ABL_LN_NONE
@@ -584,6 +615,7 @@ __global__ void __launch_bounds__(E_THREADS, 1) k_edge5(const __grid_constant__ 
     constexpr int DEPTH = GNB_OUT_DEPTH;
     static_assert(OUT_ROWS % DEPTH == 0, "the rolling window keeps its slot numbering across slices only if DEPTH divides the slice");
     const int ow = warp < 8 ? warp - 4 : warp - 8;
+    const uint64_t pol_xf = l2_policy_evict_first();
     const float* xbase = a.x + 4 * lane;
     // this lane's 4 columns of a gathered row: 16 B of an fp32 row, 8 B of a bf16 row
     const uint8_t* base1 = reinterpret_cast<const uint8_t*>(a.add1) + (PBF ? 8 : 16) * lane;
@@ -628,7 +660,7 @@ __global__ void __launch_bounds__(E_THREADS, 1) k_edge5(const __grid_constant__ 
 #ifdef GNB_ABL_OUT_NOX      /* GNB_ABL_*: timing-only ablations (results wrong), tools/ab_edge.sh */
       xa[u] = f4zero();
 #else
-      xa[u] = ld_stream(xbase + (size_t)r * H);                       // second and last read of x: L2 hit
+      xa[u] = GNB_X_L2_HINTS ? ld_stream_hint(xbase + (size_t)r * H, pol_xf) : ld_stream(xbase + (size_t)r * H);      // second and last read of x
 #endif
 #ifdef GNB_ABL_OUT_NOGATHER
       if constexpr (PBF) { pa[u] = make_uint2(0u, 0u); pb[u] = pa[u]; } else { pa[u] = f4zero(); pb[u] = pa[u]; }
