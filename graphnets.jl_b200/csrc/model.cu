@@ -1007,8 +1007,8 @@ static int graphs_enabled() {
   return on;
 }
 static int env_signature() {      // environment toggles that are read per launch (tests flip them between calls)
-  const char* p = getenv("GNB_EDGE_CTA_PAIR");
-  return p ? 1 + atoi(p) : 0;
+  const char *p = getenv("GNB_EDGE_CTA_PAIR"), *q = getenv("GNB_FFN_CTA_PAIR"), *r = getenv("GNB_FUSE_DECODER");
+  return (p ? 1 + atoi(p) : 0) | ((q ? 1 + atoi(q) : 0) << 4) | ((r ? 1 + atoi(r) : 0) << 8);
 }
 static int forward_graphed(gnb_ctx* ctx, const gnb_model* m, const gnb_graph* g, const float* ef, const float* nf,
                            const float* gf, float* out_ef, float* out_nf, float* out_gf, int precision) {

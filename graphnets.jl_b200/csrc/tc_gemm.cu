@@ -416,9 +416,14 @@ struct PackCache { std::map<PackKey, __nv_bfloat16*> m; };
 // 14 warps: 0-3 DRAIN (conversion), 4-7 A producers (LayerNorm -> bf16 slabs, next tile), 8-11 EPI (D + b2 + x + h -> y,
 // fragment layout), 12 MMA issuer (two slabs = 8 UMMAs per iteration), 13 weight loader (16 KB slabs, 5-stage ring: W1 slabs of chunk c, then W2 slabs of chunk c-1).
 // =====================================================================================================
-constexpr int F_NW = 5;                                   // weight ring: 5 x 16 KB, consumed two slabs at a time
+// CL2 (default): the two CTAs of a cluster (an SM pair) run ONE 256-row cta_group::2 UMMA stream; each CTA holds its own 128-row A
+// tile and the N half (64 of 128 rows, 8 KB) of every weight slab - half the weight bytes per SM (the kernel streams 1 MB of
+// slabs per 128-row tile, which bound it at ~13 TB/s of L2 -> SM traffic: profiles/r01_wide_ncu.json) and a ring twice as deep
+// in slabs.  Only the leader CTA issues UMMAs; its barriers collect the arrivals of both CTAs, tcgen05.commit multicasts the
+// completions to both (same protocol as k_edge5, tc_edge.cu).
+constexpr int F_RING_BYTES = 5 * SLAB;                    // weight ring: 5 x 16 KB slabs, or 10 x 8 KB half slabs (CL2); consumed two slabs at a time
 constexpr int F_THREADS = 14 * 32;
-enum { FB_WFULL = 0, FB_WEMPTY = 5, FB_AFULL = 10, FB_AEMPTY = 12, FB_HIDFULL = 14, FB_HSREADY = 16, FB_ACCFULL = 18, FB_ACCFREE = 19 };
+enum { FB_WFULL = 0, FB_WEMPTY = 10, FB_AFULL = 20, FB_AEMPTY = 22, FB_HIDFULL = 24, FB_HSREADY = 26, FB_ACCFULL = 28, FB_ACCFREE = 29 };
 template <int FH> struct FfnCfg {
   static constexpr int KS = FH / 64;               // K slabs of the up projection
   static constexpr int CH = 4 * FH / 128;          // hidden chunks
@@ -427,7 +432,7 @@ template <int FH> struct FfnCfg {
   static constexpr int NAS = FH <= 256 ? 2 : 1;    // A tile stages in shared memory
   static constexpr int OFF_A = 0;
   static constexpr int OFF_W = NAS * KS * SLAB;
-  static constexpr int OFF_STAT = OFF_W + F_NW * SLAB;      // float2 stats[128]
+  static constexpr int OFF_STAT = OFF_W + F_RING_BYTES;     // float2 stats[128]
   static constexpr int OFF_B1 = OFF_STAT + 128 * 8;         // float b1[4 FH]
   static constexpr int OFF_BAR = OFF_B1 + 4 * FH * 4;
   static constexpr int SMEM = OFF_BAR + 32 * 8 + 16 + 1024;
@@ -446,9 +451,12 @@ struct FfnArgs {
   WatchArgs wd;                 // kernel watchdog (tc_ptx.cuh)
 };
 
-template <int FH>
+template <int FH, bool CL2>
 __global__ void __launch_bounds__(F_THREADS, 1) k_tc_ffn(const FfnArgs a) {
   using Cfg = FfnCfg<FH>;
+  constexpr int F_NW = CL2 ? 10 : 5;                       // ring stages
+  constexpr uint32_t WST = CL2 ? SLAB / 2 : SLAB;          // bytes per stage: this CTA's share of one slab
+  constexpr uint32_t NARR = CL2 ? 8u : 4u;                 // arrivals of a 4-warp role on a leader barrier
   constexpr int F_H = FH, F_KS = Cfg::KS, F_CH = Cfg::CH, F_NB = Cfg::NB, NHD = Cfg::NHD, NAS = Cfg::NAS;
   constexpr int F_OFF_A = Cfg::OFF_A, F_OFF_W = Cfg::OFF_W, F_OFF_STAT = Cfg::OFF_STAT, F_OFF_B1 = Cfg::OFF_B1, F_OFF_BAR = Cfg::OFF_BAR;
   extern __shared__ uint8_t smem_raw[];
@@ -463,28 +471,45 @@ __global__ void __launch_bounds__(F_THREADS, 1) k_tc_ffn(const FfnArgs a) {
   auto BAR = [&](int i) { return bar0 + 8u * (uint32_t)i; };
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   bool wd_dead = false;      // kernel watchdog (tc_ptx.cuh)
+  const uint32_t rank = CL2 ? cluster_ctarank() : 0u;      // == blockIdx.x & 1
   if (tid == 0) {
-    for (int i = 0; i < F_NW; i++) { mbar_init(BAR(FB_WFULL + i), 1); mbar_init(BAR(FB_WEMPTY + i), 1); }
+    // pair leader: WFULL[st] also counts the peer's "my half has landed" relay, so the MMA warp waits on ONE barrier per slab
+    for (int i = 0; i < F_NW; i++) { mbar_init(BAR(FB_WFULL + i), (CL2 && rank == 0) ? 2 : 1); mbar_init(BAR(FB_WEMPTY + i), 1); }
     for (int i = 0; i < 2; i++) {
-      mbar_init(BAR(FB_AFULL + i), 4); mbar_init(BAR(FB_AEMPTY + i), 1);
-      mbar_init(BAR(FB_HIDFULL + i), 1); mbar_init(BAR(FB_HSREADY + i), 4);
+      mbar_init(BAR(FB_AFULL + i), NARR); mbar_init(BAR(FB_AEMPTY + i), 1);
+      mbar_init(BAR(FB_HIDFULL + i), 1); mbar_init(BAR(FB_HSREADY + i), NARR);
     }
-    mbar_init(BAR(FB_ACCFULL), 1); mbar_init(BAR(FB_ACCFREE), 4);
+    mbar_init(BAR(FB_ACCFULL), 1); mbar_init(BAR(FB_ACCFREE), NARR);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 12) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (CL2) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   for (int i = tid; i < 4 * F_H; i += F_THREADS) sB1[i] = a.b1[i];
   tc_fence_before();
   __syncthreads();
+  if (CL2) cluster_sync_all();      // the peer's barriers are initialised before any remote arrive / multicast commit
   tc_fence_after();
+  // a 4-warp role's arrival on a barrier the MMA warp (leader CTA) waits on
+  auto ARRIVE_LEADER = [&](int i) {
+    __syncwarp();
+    if (lane == 0) {
+      if (CL2) mbar_arrive_cluster(map_to_cta(BAR(i), 0));
+      else mbar_arrive(BAR(i));
+    }
+  };
+#define TILE_OK(t) ((t) - (int)rank < a.num_tiles && !wd_dead)   /* both CTAs of a pair run the same number of passes */
   const uint32_t tmem = *tmem_slot;
   const uint32_t Dt = tmem, Hd0 = tmem + F_H;      // D: columns [0, FH); Hd[b]: [FH + 128 b, +128)
   // the hidden chunks are independent terms of the down projection: every CTA starts at a different one, so that the
   // lock-stepped CTAs do not stream the same weight slab from the same L2 slice at the same time
-  const int crot = (int)(blockIdx.x % F_CH);
+  const int crot = (int)((CL2 ? blockIdx.x >> 1 : blockIdx.x) % F_CH);      // (the same for both CTAs of a pair)
   auto rotc = [&](int c) { const int t = c + crot; return t < F_CH ? t : t - F_CH; };
 
   if (warp == 13) {
@@ -495,12 +520,13 @@ __global__ void __launch_bounds__(F_THREADS, 1) k_tc_ffn(const FfnArgs a) {
       it++;
       mbar_wait(BAR(FB_WEMPTY + st), ph ^ 1);
       if (elect_one()) {
-        mbar_expect_tx(BAR(FB_WFULL + st), SLAB);
-        bulk_g2s(base + F_OFF_W + st * SLAB, src, SLAB, BAR(FB_WFULL + st));
+        // CL2: this CTA's N half of the slab = rows [64 rank, 64 rank + 64), 8 KB contiguous in the swizzled slab image
+        mbar_expect_tx(BAR(FB_WFULL + st), WST);
+        bulk_g2s(base + F_OFF_W + st * WST, reinterpret_cast<const uint8_t*>(src) + (CL2 ? rank * WST : 0u), WST, BAR(FB_WFULL + st));
       }
       __syncwarp();
     };
-    for (int tile = blockIdx.x; tile < a.num_tiles && !wd_dead; tile += gridDim.x) {
+    for (int tile = blockIdx.x; TILE_OK(tile); tile += gridDim.x) {
 #pragma unroll 1
       for (int c = 0; c < F_CH + NHD - 1; c++) {
         if (c < F_CH)
@@ -521,12 +547,38 @@ __global__ void __launch_bounds__(F_THREADS, 1) k_tc_ffn(const FfnArgs a) {
       ws0 = it % F_NW; ws1 = (it + 1) % F_NW;
       const uint32_t p0 = (it / F_NW) & 1, p1 = ((it + 1) / F_NW) & 1;
       it += 2;
-      mbar_wait(BAR(FB_WFULL + ws0), p0);
+      mbar_wait(BAR(FB_WFULL + ws0), p0);      // CL2: own half (expect_tx) + the peer's relay arrive
       mbar_wait(BAR(FB_WFULL + ws1), p1);
-      wd0 = umma_desc(base + F_OFF_W + ws0 * SLAB);
-      wd1 = umma_desc(base + F_OFF_W + ws1 * SLAB);
+      wd0 = umma_desc(base + F_OFF_W + ws0 * WST);
+      wd1 = umma_desc(base + F_OFF_W + ws1 * WST);
     };
-    for (int tile = blockIdx.x; tile < a.num_tiles && !wd_dead; tile += gridDim.x, tl++) {
+    auto COMMIT = [&](int i) {
+      if (CL2) tc_commit2(BAR(i));
+      else tc_commit(BAR(i));
+    };
+    constexpr uint32_t ID = CL2 ? IDESC2 : IDESC;
+    auto MMA_SS = [&](uint32_t d, uint64_t ad, uint64_t bd, uint32_t acc) {
+      if (CL2) mma_ss2(d, ad, bd, ID, acc);
+      else mma_ss(d, ad, bd, ID, acc);
+    };
+    auto MMA_TS = [&](uint32_t d, uint32_t at, uint64_t bd, uint32_t acc) {
+      if (CL2) mma_ts2(d, at, bd, ID, acc);
+      else mma_ts(d, at, bd, ID, acc);
+    };
+    if (CL2 && rank != 0) {
+      // peer CTA: relay "my half of the slab has landed" to the leader, in ring order
+      constexpr int SLABS_PER_TILE = F_CH * (F_KS + 2 * F_NB);
+      for (int tile = blockIdx.x; TILE_OK(tile); tile += gridDim.x) {
+#pragma unroll 1
+        for (int s2 = 0; s2 < SLABS_PER_TILE; s2++, it++) {
+          const uint32_t st = it % F_NW, ph = (it / F_NW) & 1;
+          mbar_wait(BAR(FB_WFULL + st), ph);
+          if (lane == 0) mbar_arrive_cluster(map_to_cta(BAR(FB_WFULL + st), 0));
+          __syncwarp();
+        }
+      }
+    } else
+    for (int tile = blockIdx.x; TILE_OK(tile); tile += gridDim.x, tl++) {
       const uint32_t st = tl % NAS;
       mbar_wait(BAR(FB_AFULL + st), (tl / NAS) & 1);
 #pragma unroll 1
@@ -540,14 +592,14 @@ __global__ void __launch_bounds__(F_THREADS, 1) k_tc_ffn(const FfnArgs a) {
             if (elect_one()) {
               const uint64_t ad = umma_desc(base + F_OFF_A + (st * F_KS + 2 * kp) * SLAB);
 #pragma unroll
-              for (int k4 = 0; k4 < 4; k4++) mma_ss(Hd, ad + 2 * k4, wd0 + 2 * k4, IDESC, (kp > 0 || k4 > 0) ? 1u : 0u);
+              for (int k4 = 0; k4 < 4; k4++) MMA_SS(Hd, ad + 2 * k4, wd0 + 2 * k4, (kp > 0 || k4 > 0) ? 1u : 0u);
 #pragma unroll
-              for (int k4 = 0; k4 < 4; k4++) mma_ss(Hd, ad + (SLAB >> 4) + 2 * k4, wd1 + 2 * k4, IDESC, 1u);
-              tc_commit(BAR(FB_WEMPTY + ws0));
-              tc_commit(BAR(FB_WEMPTY + ws1));
+              for (int k4 = 0; k4 < 4; k4++) MMA_SS(Hd, ad + (SLAB >> 4) + 2 * k4, wd1 + 2 * k4, 1u);
+              COMMIT(FB_WEMPTY + ws0);
+              COMMIT(FB_WEMPTY + ws1);
               if (kp == F_KS / 2 - 1) {
-                tc_commit(BAR(FB_HIDFULL + (c % NHD)));
-                if (c == F_CH - 1) tc_commit(BAR(FB_AEMPTY + st));
+                COMMIT(FB_HIDFULL + (c % NHD));
+                if (c == F_CH - 1) COMMIT(FB_AEMPTY + st);
               }
             }
             __syncwarp();
@@ -565,12 +617,12 @@ __global__ void __launch_bounds__(F_THREADS, 1) k_tc_ffn(const FfnArgs a) {
             tc_fence_after();
             if (elect_one()) {
 #pragma unroll
-              for (int k4 = 0; k4 < 4; k4++) mma_ts(Dt + 128 * nb, Hd + 8 * k4, wd0 + 2 * k4, IDESC, (cc > 0 || k4 > 0) ? 1u : 0u);
+              for (int k4 = 0; k4 < 4; k4++) MMA_TS(Dt + 128 * nb, Hd + 8 * k4, wd0 + 2 * k4, (cc > 0 || k4 > 0) ? 1u : 0u);
 #pragma unroll
-              for (int k4 = 0; k4 < 4; k4++) mma_ts(Dt + 128 * nb, Hd + 32 + 8 * k4, wd1 + 2 * k4, IDESC, 1u);
-              tc_commit(BAR(FB_WEMPTY + ws0));
-              tc_commit(BAR(FB_WEMPTY + ws1));
-              if (cc == F_CH - 1 && nb == F_NB - 1) tc_commit(BAR(FB_ACCFULL));
+              for (int k4 = 0; k4 < 4; k4++) MMA_TS(Dt + 128 * nb, Hd + 32 + 8 * k4, wd1 + 2 * k4, 1u);
+              COMMIT(FB_WEMPTY + ws0);
+              COMMIT(FB_WEMPTY + ws1);
+              if (cc == F_CH - 1 && nb == F_NB - 1) COMMIT(FB_ACCFULL);
             }
             __syncwarp();
           }
@@ -592,7 +644,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) k_tc_ffn(const FfnArgs a) {
       TC_ST16(dst, p);
     };
     uint32_t nh[2] = {0, 0};
-    for (int tile = blockIdx.x; tile < a.num_tiles && !wd_dead; tile += gridDim.x) {
+    for (int tile = blockIdx.x; TILE_OK(tile); tile += gridDim.x) {
 #pragma unroll 1
       for (int c = 0; c < F_CH; c++) {
         const int hb = c % NHD;
@@ -614,8 +666,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) k_tc_ffn(const FfnArgs a) {
         cvt32(vb, bias + 96, t0 + 48);
         tc_wait_st();
         tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(BAR(FB_HSREADY + hb));
+        ARRIVE_LEADER(FB_HSREADY + hb);
       }
     }
   } else if (warp < 8) {
@@ -623,7 +674,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) k_tc_ffn(const FfnArgs a) {
     const int q = warp - 4;
     const int hr = lane >> 4, c16 = lane & 15;
     uint32_t tl = 0;
-    for (int tile = blockIdx.x; tile < a.num_tiles && !wd_dead; tile += gridDim.x, tl++) {
+    for (int tile = blockIdx.x; TILE_OK(tile); tile += gridDim.x, tl++) {
       const int64_t row0 = (int64_t)tile * TM + 32 * q;
       // two-pass statistics, 16 lanes per row, the row in registers (4 float4 per lane), 2 row pairs in flight
       const float* xs = a.x + 4 * c16;
@@ -705,8 +756,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) k_tc_ffn(const FfnArgs a) {
         }
       }
       fence_async_smem();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(BAR(FB_AFULL + st));
+      ARRIVE_LEADER(FB_AFULL + st);
     }
   } else if (warp < 12) {
     // ===================================================== EPI (TMEM lane quadrant = warp % 4): y = D + b2 + x + h
@@ -721,7 +771,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) k_tc_ffn(const FfnArgs a) {
 #pragma unroll
     for (int s2 = 0; s2 < F_NB; s2++) b2v[s2] = __ldg(reinterpret_cast<const float4*>(a.b2) + 32 * s2 + lane);
     uint32_t tl = 0;
-    for (int tile = blockIdx.x; tile < a.num_tiles && !wd_dead; tile += gridDim.x, tl++) {
+    for (int tile = blockIdx.x; TILE_OK(tile); tile += gridDim.x, tl++) {
       const int64_t row0 = (int64_t)tile * TM + 32 * dq;
       mbar_wait(BAR(FB_ACCFULL), tl & 1);
       tc_fence_after();
@@ -733,8 +783,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) k_tc_ffn(const FfnArgs a) {
         tc_wait_ld();
         if (st2 == 2 * (F_H / 64) - 1) {
           tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(BAR(FB_ACCFREE));
+          ARRIVE_LEADER(FB_ACCFREE);
         }
 #pragma unroll
         for (int h2 = 0; h2 < 2; h2++) {
@@ -780,7 +829,12 @@ __global__ void __launch_bounds__(F_THREADS, 1) k_tc_ffn(const FfnArgs a) {
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 12) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+  if (CL2) cluster_sync_all();      // the peer may still be reading this CTA's shared / tensor memory
+  if (warp == 12) {
+    if (CL2) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+  }
+#undef TILE_OK
 }
 
 // packed bf16 weight slabs of one Dense, built on first use and cached per (model, weight block, group size)
@@ -875,7 +929,10 @@ bool tc_ffn256_supported(int64_t R, int d) { return (d == 256 || d == 384) && R 
 
 template <int FH>
 static int launch_ffn_t(gnb_ctx* ctx, int once_key, int64_t R, const gnb_ffn_params& f, const gnb_ln_params& ln2, const float* x, const float* h, float* y) {
-  if (ctx_first(ctx, once_key)) GNB_CUDA(cudaFuncSetAttribute(k_tc_ffn<FH>, cudaFuncAttributeMaxDynamicSharedMemorySize, FfnCfg<FH>::SMEM));
+  if (ctx_first(ctx, once_key)) {
+    GNB_CUDA(cudaFuncSetAttribute(k_tc_ffn<FH, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FfnCfg<FH>::SMEM));
+    GNB_CUDA(cudaFuncSetAttribute(k_tc_ffn<FH, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FfnCfg<FH>::SMEM));
+  }
   FfnArgs a{};
   a.x = x; a.h = h; a.y = y; a.R = R; a.num_tiles = (int)ceil_div(R, TM);
   a.gamma = ln2.gamma; a.beta = ln2.beta; a.eps = ln2.eps; a.eps_mode = ln2.eps_mode;
@@ -894,8 +951,23 @@ static int launch_ffn_t(gnb_ctx* ctx, int once_key, int64_t R, const gnb_ffn_par
   GNB_TRY(get_pack(ctx, k2, p2, FH, 4 * FH, FH, 1, &a.w2));
   // canonical work of the reference FFN: 16 d^2 flop per row, x / h read and y written once
   Launch L(ctx, FH == 256 ? "tc_ffn256" : "tc_ffn384", 4.0 * 3 * FH * R, 16.0 * FH * FH * R);
-  const int grid = a.num_tiles < ctx->sm_count ? a.num_tiles : ctx->sm_count;
-  k_tc_ffn<FH><<<grid, F_THREADS, FfnCfg<FH>::SMEM, ctx->stream>>>(a);
+  // GNB_FFN_CTA_PAIR=0: one CTA per tile stream (cta_group::1).  Read per launch so that a test can run both instantiations.
+  const char* pair_env = getenv("GNB_FFN_CTA_PAIR");
+  const bool cl2 = (pair_env ? atoi(pair_env) : 1) && ctx->sm_count >= 2;
+  if (cl2) {
+    const int pairs = (a.num_tiles + 1) / 2, max_clusters = ctx->sm_count / 2;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * (pairs < max_clusters ? pairs : max_clusters)); cfg.blockDim = dim3(F_THREADS);
+    cfg.dynamicSmemBytes = FfnCfg<FH>::SMEM; cfg.stream = ctx->stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    GNB_CUDA(cudaLaunchKernelEx(&cfg, k_tc_ffn<FH, true>, a));
+  } else {
+    const int grid = a.num_tiles < ctx->sm_count ? a.num_tiles : ctx->sm_count;
+    k_tc_ffn<FH, false><<<grid, F_THREADS, FfnCfg<FH>::SMEM, ctx->stream>>>(a);
+  }
   GNB_CUDA(cudaGetLastError());
   return GNB_OK;
 }

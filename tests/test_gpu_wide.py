@@ -6,7 +6,7 @@ import pytest
 import torch
 
 import workloads as W
-from tests.gpu_util import BF16_TOL, FP32_TOL, assert_parity, run_oracle
+from tests.gpu_util import BF16_TOL, FP32_TOL, assert_parity, assert_wide_parity, run_oracle
 
 # the wide cores carry more bf16 operand error than the 128-wide ones (tests/gpu_util.py::assert_wide_parity): RMS bound = max-norm bound
 WIDE_RMS_TOL = 1.5e-2
@@ -46,6 +46,35 @@ def test_cfg5_shape_tensor_path(gn, B):
     got32, prof32 = _run(gn, layers, w, "fp32")
     assert_parity(got32, ref, FP32_TOL, "cfg5 fp32")
     assert "tc_linear" not in prof32
+
+
+@pytest.mark.parametrize("cfg,kw", [("cfg5", dict(B=40, n_nodes=37, n_edges=301)), ("cfg3", dict(B=24))])
+def test_ffn_cta_pair_equals_single_cta(gn, cfg, kw):
+    """k_tc_ffn<256 | 384> as CTA pairs (cta_group::2, default) and as single CTAs (GNB_FFN_CTA_PAIR=0) compute the same sums; only
+    the order in which a CTA walks the hidden chunks differs (per-CTA rotation), i.e. fp32 summation order: results agree to
+    a few 1e-4 of the tensor's range after four cores (an fp32 ulp flips bf16 roundings of the next layer's operands) - far
+    below the bf16 tolerance, which both variants meet against the oracle.  Ragged last tiles, odd number of tiles."""
+    import os
+    w = W.make_workload(cfg, **kw)
+    layers = W.model_params(cfg)
+    old = os.environ.get("GNB_FFN_CTA_PAIR")
+    try:
+        os.environ["GNB_FFN_CTA_PAIR"] = "1"
+        pair, prof = _run(gn, layers, w, "auto")
+        os.environ["GNB_FFN_CTA_PAIR"] = "0"
+        single, _ = _run(gn, layers, w, "auto")
+    finally:
+        if old is None:
+            os.environ.pop("GNB_FFN_CTA_PAIR", None)
+        else:
+            os.environ["GNB_FFN_CTA_PAIR"] = old
+    assert any(k.startswith("tc_ffn") for k in prof), list(prof)
+    for a_, b_ in zip(pair, single):
+        if a_ is not None:
+            assert np.max(np.abs(a_ - b_)) <= 2e-3 * np.max(np.abs(b_)), np.max(np.abs(a_ - b_)) / np.max(np.abs(b_))
+    # against the oracle: no worse than 2x ideal bf16-operand arithmetic (tests/gpu_util.py::assert_wide_parity)
+    assert_wide_parity(pair, layers, w, cfg + " ffn pairs")
+    assert_wide_parity(single, layers, w, cfg + " ffn single CTAs")
 
 
 def test_cfg5_many_small_graphs(gn):
