@@ -74,6 +74,10 @@ void Arena::release() {
 // Copies, the lowering and the host-side work of one context still overlap the forward of the other - which is what a
 // double-buffered input pipeline needs.
 static std::mutex g_chain_mu;
+// live contexts of the process: gnb_model_destroy drops a model's per-context state (packed-weight cache entries, captured
+// forward graphs) from every one of them
+static std::mutex g_ctx_mu;
+static std::vector<gnb_ctx*> g_ctxs;
 static cudaEvent_t g_chain_ev[64] = {};
 static gnb_ctx* g_chain_ctx[64] = {};
 
@@ -105,10 +109,15 @@ extern "C" gnb_ctx* gnb_ctx_create(int device, int* err) {
   }
   if (const char* e = getenv("GNB_DEBUG_PROJ_DRAIN_DELAY_NS")) c->dbg_proj_drain_delay_ns = (unsigned int)atoi(e);
   if (err) *err = GNB_OK;
+  { std::lock_guard<std::mutex> lk(g_ctx_mu); g_ctxs.push_back(c); }
   return c;
 }
 extern "C" int gnb_ctx_destroy(gnb_ctx* c) {
   if (!c) return GNB_OK;
+  {
+    std::lock_guard<std::mutex> lk(g_ctx_mu);
+    for (size_t i = 0; i < g_ctxs.size(); i++) if (g_ctxs[i] == c) { g_ctxs.erase(g_ctxs.begin() + i); break; }
+  }
   cudaSetDevice(c->device);
   c->arena.release();
   c->staging.release();
@@ -436,6 +445,20 @@ extern "C" int gnb_model_destroy(gnb_model* m) {
     if (w.decW4) cudaFree(w.decW4);
   }
   if (m->wbuf) cudaFree(m->wbuf);
+  {
+    // per-context state keyed by this model (the caller must not destroy a model while a forward with it is being enqueued)
+    std::lock_guard<std::mutex> lk(g_ctx_mu);
+    for (gnb_ctx* c : g_ctxs) {
+      if (c->device != m->device) continue;
+      tc_lin_cache_evict(c->lin_cache, m->id);
+      for (size_t i = 0; i < c->fwd_graphs.size();) {
+        if (c->fwd_graphs[i].model_id == m->id) {
+          if (c->fwd_graphs[i].exec) cudaGraphExecDestroy(c->fwd_graphs[i].exec);
+          c->fwd_graphs.erase(c->fwd_graphs.begin() + i);
+        } else i++;
+      }
+    }
+  }
   delete m;
   return GNB_OK;
 }

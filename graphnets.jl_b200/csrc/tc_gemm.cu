@@ -19,6 +19,7 @@
 #include "tc_ptx.cuh"
 #include "tc_gemm.cuh"
 #include <map>
+#include <mutex>
 #include <string>
 #include <stdlib.h>
 #include <tuple>
@@ -401,7 +402,7 @@ struct PackKey {
            std::tie(o.model, o.W[0], o.W[1], o.W[2], o.d[0], o.d[1], o.d[2], o.Nout, o.ldw, o.ng);
   }
 };
-struct PackCache { std::map<PackKey, __nv_bfloat16*> m; };
+struct PackCache { std::mutex mu; std::map<PackKey, __nv_bfloat16*> m; };      // mu: gnb_model_destroy evicts from any thread
 
 // =====================================================================================================
 // Fused GNFeedForward + residuals for hidden width FH = 256 or 384 (src/gnfeedforward.jl:27-31, src/gncore.jl:56-59):
@@ -841,6 +842,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) k_tc_ffn(const FfnArgs a) {
 static int get_pack(gnb_ctx* ctx, const PackKey& key, const PackSrc& ps, int ldw, int K, int Nout, int NG, const __nv_bfloat16** out) {
   if (!ctx->lin_cache) ctx->lin_cache = new PackCache();
   PackCache* cache = static_cast<PackCache*>(ctx->lin_cache);
+  std::lock_guard<std::mutex> lk(cache->mu);
   auto itc = cache->m.find(key);
   if (itc == cache->m.end()) {
     __nv_bfloat16* dst = nullptr;
@@ -860,6 +862,16 @@ static int get_pack(gnb_ctx* ctx, const PackKey& key, const PackSrc& ps, int ldw
 }
 
 }  // namespace
+
+void tc_lin_cache_evict(void* cache, uint64_t model_id) {
+  if (!cache) return;
+  PackCache* c = static_cast<PackCache*>(cache);
+  std::lock_guard<std::mutex> lk(c->mu);
+  for (auto it = c->m.begin(); it != c->m.end();) {
+    if (it->first.model == model_id) { cudaFree(it->second); it = c->m.erase(it); }
+    else ++it;
+  }
+}
 
 void tc_lin_cache_free(void* cache) {
   if (!cache) return;
@@ -914,10 +926,14 @@ int launch_linear_tc(gnb_ctx* ctx, const LinArgs& a) {
   double bytes = 2.0 * K * a.Nout + 4.0 * (double)a.R * a.Nout * a.nadd + (a.out_bf16 ? 2.0 : 4.0) * a.R * a.Nout;
   for (int s = 0; s < a.nsrc; s++) bytes += (a.src[s].x_bf16 ? 2.0 : 4.0) * a.R * a.src[s].d;
   // profile tag per layer shape (interned: Launch keeps the pointer)
-  static std::map<std::pair<int, int>, std::string> names;
+  static std::mutex names_mu;
+  static std::map<std::pair<int, int>, std::string> names;      // std::map: element addresses are stable
+  std::unique_lock<std::mutex> nlk(names_mu);
   auto nit = names.find({K, a.Nout});
   if (nit == names.end()) nit = names.emplace(std::make_pair(K, a.Nout), "tc_linear_k" + std::to_string(K) + "_n" + std::to_string(a.Nout)).first;
-  Launch L(ctx, ctx->profiling && getenv("GNB_PROFILE_SHAPES") ? nit->second.c_str() : "tc_linear", bytes, 2.0 * a.R * K * a.Nout);
+  const char* shape_name = nit->second.c_str();
+  nlk.unlock();
+  Launch L(ctx, ctx->profiling && getenv("GNB_PROFILE_SHAPES") ? shape_name : "tc_linear", bytes, 2.0 * a.R * K * a.Nout);
   const int grid = g.num_tiles < ctx->sm_count ? g.num_tiles : ctx->sm_count;
   g.wd = ctx_watch(ctx);
   k_tc_lin<<<grid, G_THREADS, G_SMEM, ctx->stream>>>(g);

@@ -7,6 +7,8 @@ bool tc_lin_supported(const LinArgs& a);
 // same contract as launch_linear_fp32, bf16 operands / fp32 accumulation on the tensor cores
 int launch_linear_tc(gnb_ctx* ctx, const LinArgs& a);
 void tc_lin_cache_free(void* cache);
+// drops (and frees) the packed weights of one model from a context's cache (gnb_model_destroy)
+void tc_lin_cache_evict(void* cache, uint64_t model_id);
 
 // fused GNFeedForward + residuals, y = x + h + W2 relu(W1 LN2(x) + b1) + b2, for hidden width 256 or 384 (hidden activation on chip)
 bool tc_ffn256_supported(int64_t R, int d);
