@@ -306,8 +306,9 @@ __global__ void __launch_bounds__(PJ_THREADS, NBLK == 1 ? 2 : 1) k_tc_proj(const
 // Barriers as k_tc_proj (no ASEEN: the drain warps read nothing the producers write).
 // =====================================================================================================
 struct Agg2Args {
-  const float* Epart;             // [n_parts][H]
+  const float* Epart;             // [n_parts][H]  (part_bf16: bf16 rows)
   const float* Gpart;             // [n_parts][H]
+  int part_bf16;
   const int32_t* part_ptr;        // [R+1] node -> its partial rows [part_ptr[v], part_ptr[v+1])
   const int32_t* gpart;           // [R]   node -> (16-node block, graph) run id (gnb_graph::node_gpart)
   float* SEpart;                  // out [n_nparts][H]
@@ -326,6 +327,7 @@ constexpr int AG_OFF_MISC = AG_OFF_W + 4 * BLK_BYTES;
 constexpr int AG_SMEM = AG_OFF_MISC + 256 + 1024;
 enum { AB_WFULL = 0, AB_AFULL = 1, AB_AEMPTY = 3, AB_OUTDONE = 5, AB_ACCFREE = 7 };
 
+template <bool PBF>      // PBF: the partial rows are bf16 (Agg2Args::part_bf16)
 __global__ void __launch_bounds__(AG_THREADS, 1) k_tc_agg2(const Agg2Args a) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
@@ -384,8 +386,15 @@ __global__ void __launch_bounds__(AG_THREADS, 1) k_tc_agg2(const Agg2Args a) {
   } else if (warp >= 4) {
     // ===================================================== producers: warp pw owns rows 16 pw .. 16 pw + 15 of the tile
     const int pw = warp - 4;
-    const float4* XE = reinterpret_cast<const float4*>(a.Epart) + lane;
-    const float4* XG = reinterpret_cast<const float4*>(a.Gpart) + lane;
+    // this lane's 4 columns of partial row p (fp32 rows of 512 B, or bf16 rows of 256 B)
+    auto ldE = [&](size_t p) {
+      if constexpr (PBF) { const uint2 v = __ldg(reinterpret_cast<const uint2*>(a.Epart) + p * (H / 4) + lane); return make_float4(__uint_as_float(v.x << 16), __uint_as_float(v.x & 0xffff0000u), __uint_as_float(v.y << 16), __uint_as_float(v.y & 0xffff0000u)); }
+      else return __ldg(reinterpret_cast<const float4*>(a.Epart) + p * (H / 4) + lane);
+    };
+    auto ldG = [&](size_t p) {
+      if constexpr (PBF) { const uint2 v = __ldg(reinterpret_cast<const uint2*>(a.Gpart) + p * (H / 4) + lane); return make_float4(__uint_as_float(v.x << 16), __uint_as_float(v.x & 0xffff0000u), __uint_as_float(v.y << 16), __uint_as_float(v.y & 0xffff0000u)); }
+      else return __ldg(reinterpret_cast<const float4*>(a.Gpart) + p * (H / 4) + lane);
+    };
     uint32_t tl = 0;
     for (int tile = blockIdx.x; tile < a.num_tiles && !wd_dead; tile += gridDim.x, tl++) {
       const int64_t row0 = (int64_t)tile * TM + 16 * pw;
@@ -415,10 +424,10 @@ __global__ void __launch_bounds__(AG_THREADS, 1) k_tc_agg2(const Agg2Args a) {
           q0[u] = __shfl_sync(0xffffffffu, p0, i0 + u);
           q1[u] = __shfl_sync(0xffffffffu, p1, i0 + u);
           const bool h0 = q0[u] < q1[u], h1 = q0[u] + 1 < q1[u];
-          s[u] = h0 ? __ldg(XE + (size_t)q0[u] * (H / 4)) : f4zero();
-          t[u] = h1 ? __ldg(XE + (size_t)(q0[u] + 1) * (H / 4)) : f4zero();
-          s2[u] = h0 ? __ldg(XG + (size_t)q0[u] * (H / 4)) : f4zero();
-          t2[u] = h1 ? __ldg(XG + (size_t)(q0[u] + 1) * (H / 4)) : f4zero();
+          s[u] = h0 ? ldE((size_t)q0[u]) : f4zero();
+          t[u] = h1 ? ldE((size_t)q0[u] + 1) : f4zero();
+          s2[u] = h0 ? ldG((size_t)q0[u]) : f4zero();
+          t2[u] = h1 ? ldG((size_t)q0[u] + 1) : f4zero();
         }
 #pragma unroll
         for (int u = 0; u < 4; u++) {
@@ -426,8 +435,8 @@ __global__ void __launch_bounds__(AG_THREADS, 1) k_tc_agg2(const Agg2Args a) {
           s[u] = f4add(s[u], t[u]);
           s2[u] = f4add(s2[u], t2[u]);
           for (int p = q0[u] + 2; p < q1[u]; p++) {
-            s[u] = f4add(s[u], __ldg(XE + (size_t)p * (H / 4)));
-            s2[u] = f4add(s2[u], __ldg(XG + (size_t)p * (H / 4)));
+            s[u] = f4add(s[u], ldE((size_t)p));
+            s2[u] = f4add(s2[u], ldG((size_t)p));
           }
           uint2 pk;
           pk.x = pack_bf16(s[u].x, s[u].y); pk.y = pack_bf16(s[u].z, s[u].w);
@@ -688,8 +697,12 @@ int tc_core_forward(gnb_ctx* ctx, const gnb_graph* g, const TcCorePack* pk, cons
   static const bool psr_bf16 = getenv("GNB_PSR_FP32") == nullptr || atoi(getenv("GNB_PSR_FP32")) == 0;
   const size_t psr_es = psr_bf16 ? 2 : 4;
   uint8_t* Psr = arena_ptr<uint8_t>(ctx->arena, (size_t)N * 2 * H * psr_es, &rc);
-  float* Epart = arena_ptr<float>(ctx->arena, nparts * H, &rc);
-  float* Gpart = arena_ptr<float>(ctx->arena, nparts * H, &rc);
+  // partial rows of the edge kernel (sums over <= 16 rows, written by k_edge5, read once by k_tc_agg2) in bf16: they are 0.33 GB
+  // of the kernel's 2.8 GB of DRAM traffic per launch in fp32; like P_s | P_r' the rounding is independent per row and element.
+  // (GNB_PART_FP32=1: fp32, A/B toggle)
+  static const bool part_bf16 = getenv("GNB_PART_FP32") == nullptr || atoi(getenv("GNB_PART_FP32")) == 0;
+  float* Epart = reinterpret_cast<float*>(arena_ptr<uint8_t>(ctx->arena, nparts * H * (part_bf16 ? 2 : 4), &rc));
+  float* Gpart = reinterpret_cast<float*>(arena_ptr<uint8_t>(ctx->arena, nparts * H * (part_bf16 ? 2 : 4), &rc));
   float* Pagg = arena_ptr<float>(ctx->arena, (size_t)N * H, &rc);
   const size_t nnparts = (size_t)(g->n_nparts > 0 ? g->n_nparts : 1);
   float* SEpart = arena_ptr<float>(ctx->arena, nnparts * H, &rc);
@@ -719,7 +732,7 @@ int tc_core_forward(gnb_ctx* ctx, const gnb_graph* g, const TcCorePack* pk, cons
     a.x = xe; a.y = ye; a.R = E; a.num_tiles = ceil_div(E, TM); a.wpack = pk->w_edge;
     a.bias_pack = pk->bias_e; a.eps = ln1[0].eps; a.eps_mode = ln1[0].eps_mode;
     a.add1 = Psr; a.idx1 = g->edge_src; a.ld1 = 2 * H; a.add2 = Psr + H * psr_es; a.idx2 = g->edge_dst; a.ld2 = 2 * H; a.add_bf16 = psr_bf16;
-    a.part = g->edge_part; a.Epart = Epart; a.Gpart = Gpart; a.dbg = g_tc_dbg; a.wd = ctx_watch(ctx);
+    a.part = g->edge_part; a.Epart = Epart; a.Gpart = Gpart; a.part_bf16 = part_bf16; a.dbg = g_tc_dbg; a.wd = ctx_watch(ctx);
     a.decW = dec.W4; a.dec_out = dec.partial;      // fused narrow decoder: y_e is not stored (ye may be nullptr)
     // canonical work of the reference's edge update + edge FFN: 24 H^2 flops and
     // 8H bytes of features + 12 B of index per edge
@@ -730,14 +743,18 @@ int tc_core_forward(gnb_ctx* ctx, const gnb_graph* g, const TcCorePack* pk, cons
   // k_graph_post (agg itself is never materialised)
   {
     Agg2Args a{};
-    a.Epart = Epart; a.Gpart = Gpart; a.part_ptr = g->node_part_ptr; a.gpart = g->node_gpart;
+    a.Epart = Epart; a.Gpart = Gpart; a.part_bf16 = part_bf16; a.part_ptr = g->node_part_ptr; a.gpart = g->node_gpart;
     a.SEpart = SEpart; a.SGpart = SGpart; a.out = Pagg; a.R = N; a.num_tiles = ceil_div(N, TM); a.wpack = pk->w_agg;
     a.wd = ctx_watch(ctx);
     if (a.num_tiles > 0) {
-      if (ctx_first(ctx, ONCE_AGG2)) GNB_CUDA(cudaFuncSetAttribute(k_tc_agg2, cudaFuncAttributeMaxDynamicSharedMemorySize, AG_SMEM));
+      if (ctx_first(ctx, ONCE_AGG2)) {
+        GNB_CUDA(cudaFuncSetAttribute(k_tc_agg2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, AG_SMEM));
+        GNB_CUDA(cudaFuncSetAttribute(k_tc_agg2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, AG_SMEM));
+      }
       const int grid = a.num_tiles < ctx->sm_count ? a.num_tiles : ctx->sm_count;
       Launch L(ctx, "tc_agg", 4.0 * (2.0 * nparts + N) * H, 2.0 * N * 2 * HH);
-      k_tc_agg2<<<grid, AG_THREADS, AG_SMEM, ctx->stream>>>(a);
+      if (part_bf16) k_tc_agg2<true><<<grid, AG_THREADS, AG_SMEM, ctx->stream>>>(a);
+      else k_tc_agg2<false><<<grid, AG_THREADS, AG_SMEM, ctx->stream>>>(a);
       GNB_CUDA(cudaGetLastError());
     }
   }
@@ -747,7 +764,7 @@ int tc_core_forward(gnb_ctx* ctx, const gnb_graph* g, const TcCorePack* pk, cons
     a.x = xn; a.y = yn; a.R = N; a.num_tiles = ceil_div(N, TM); a.wpack = pk->w_node;
     a.bias_pack = pk->bias_n; a.eps = ln1[1].eps; a.eps_mode = ln1[1].eps_mode;
     a.add1 = Pagg; a.idx1 = nullptr; a.ld1 = H; a.add2 = Pun; a.idx2 = g->node_graph; a.ld2 = H; a.add_bf16 = 0;
-    a.part = g->node_gpart; a.Epart = Vpart; a.Gpart = Npart; a.dbg = nullptr; a.wd = ctx_watch(ctx);
+    a.part = g->node_gpart; a.Epart = Vpart; a.Gpart = Npart; a.part_bf16 = 0; a.dbg = nullptr; a.wd = ctx_watch(ctx);
     GNB_TRY(launch_edge5(ctx, a, "tc_node_core", 20.0 * HH * N, (8.0 * H + 8.0) * N));
   }
   // graphs (B rows, fp32 CUDA cores): sums over the graph's nodes, graph update, graph FFN + residual

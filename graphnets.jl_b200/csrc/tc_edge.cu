@@ -593,7 +593,10 @@ __global__ void __launch_bounds__(E_THREADS, 1) k_edge5(const __grid_constant__ 
             acc = add4(acc, make_float4(__uint_as_float(v[u].x << 16), __uint_as_float(v[u].x & 0xffff0000u),
                                         __uint_as_float(v[u].y << 16), __uint_as_float(v[u].y & 0xffff0000u)));
             const bool fl = (endmask >> i) & 1u;
-            if (fl) *(reinterpret_cast<float4*>(a.Epart + (size_t)pid * H) + lane) = acc;
+            if (fl) {
+              if (a.part_bf16) *(reinterpret_cast<uint2*>(a.Epart) + (size_t)pid * (H / 4) + lane) = make_uint2(pack_bf16(acc.x, acc.y), pack_bf16(acc.z, acc.w));
+              else *(reinterpret_cast<float4*>(a.Epart + (size_t)pid * H) + lane) = acc;
+            }
             acc.x = fl ? 0.f : acc.x; acc.y = fl ? 0.f : acc.y; acc.z = fl ? 0.f : acc.z; acc.w = fl ? 0.f : acc.w;
             pid += fl ? 1 : 0;
           }
@@ -746,7 +749,10 @@ __global__ void __launch_bounds__(E_THREADS, 1) k_edge5(const __grid_constant__ 
           acc = add4(acc, g);
           const bool fl = (endmask >> i) & 1u;
 #if !defined(GNB_ABL_OUT_NOSTORE) && !defined(GNB_ABL_OUT_NOGP)
-          if (fl) *(reinterpret_cast<float4*>(a.Gpart + (size_t)pid * H) + lane) = acc;
+          if (fl) {
+            if (a.part_bf16) *(reinterpret_cast<uint2*>(a.Gpart) + (size_t)pid * (H / 4) + lane) = make_uint2(pack_bf16(acc.x, acc.y), pack_bf16(acc.z, acc.w));
+            else *(reinterpret_cast<float4*>(a.Gpart + (size_t)pid * H) + lane) = acc;
+          }
 #elif defined(GNB_ABL_OUT_NOGP)
           if (fl && acc.x == 123.456f) a.Gpart[0] = acc.y;
 #endif

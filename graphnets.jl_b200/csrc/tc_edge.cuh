@@ -24,6 +24,7 @@ struct EdgeArgs {
   const int32_t* part;   // partial-row id per edge (32-row blocks, receiver runs)
   float* Epart;          // out [n_parts][128] partial sums of the normalised edge rows
   float* Gpart;          // out [n_parts][128] partial sums of the gathered addends
+  int part_bf16;         // both stored as bf16 rows (256 B) instead of fp32
   unsigned long long* dbg;
   WatchArgs wd;          // kernel watchdog (tc_ptx.cuh)
   // Fused narrow decoder (last core of a model followed by a GNBlock with out_e <= 4, src/gnblock.jl:65): instead of storing y

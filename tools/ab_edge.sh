@@ -21,7 +21,6 @@ print("forward %.3f ms" % (ev0.elapsed_time(ev1) / 10))
 eng.set_profiling(True); eng.read_profile()
 for _ in range(5): y = model(x, precision="auto")
 prof = eng.read_profile()
-for k in ("tc_edge_core", "tc_node_core", "graph_post"):
-    print("  %-14s %.3f ms/launch" % (k, prof[k]["ms"] / prof[k]["launches"]))
+print("  " + "  ".join("%s %.3f" % (k, v["ms"] / v["launches"]) for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])[:8]) + "   (ms/launch)")
 PY
 done
