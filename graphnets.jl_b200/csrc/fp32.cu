@@ -46,6 +46,34 @@ k_linear(const LinArgs a) {
   for (int s = 0; s < a.nsrc; s++) {
     const LinSrc& S = a.src[s];
     if (S.gamma == nullptr || S.d == 0) continue;
+    if (S.d <= 32) {
+      // narrow rows (config 1 / 2 widths): one row per THREAD, the row in registers - one round trip to memory for the whole
+      // tile.  (A warp per row costs TM / NW dependent round trips x 2 passes: 16 us of a 27 us launch at config 2.)
+      for (int r = tid; r < TM; r += NT) {
+        const int64_t row = row0 + r;
+        float mu = 0.f, rs = 0.f;
+        if (row < a.R) {
+          const float* xr = S.x + (size_t)row * S.ldx;
+          float v[32];
+#pragma unroll
+          for (int k = 0; k < 32; k++) v[k] = k < S.d ? xr[k] : 0.f;
+          float sum = 0.f;
+#pragma unroll
+          for (int k = 0; k < 32; k++) sum += v[k];
+          mu = sum / (float)S.d;
+          float sq = 0.f;
+#pragma unroll
+          for (int k = 0; k < 32; k++) {
+            const float t = k < S.d ? v[k] - mu : 0.f;
+            sq += t * t;
+          }
+          rs = ln_rstd(sq / (float)S.d, S.eps, S.eps_mode);
+        }
+        s_mu[s][r] = mu;
+        s_rs[s][r] = rs;
+      }
+      continue;
+    }
     for (int r = warp; r < TM; r += NW) {
       int64_t row = row0 + r;
       float mu = 0.f, rs = 0.f;
