@@ -425,6 +425,15 @@ struct PackCache { std::mutex mu; std::map<PackKey, __nv_bfloat16*> m; };      /
 constexpr int F_RING_BYTES = 5 * SLAB;                    // weight ring: 5 x 16 KB slabs, or 10 x 8 KB half slabs (CL2); consumed two slabs at a time
 constexpr int F_THREADS = 14 * 32;
 enum { FB_WFULL = 0, FB_WEMPTY = 10, FB_AFULL = 20, FB_AEMPTY = 22, FB_HIDFULL = 24, FB_HSREADY = 26, FB_ACCFULL = 28, FB_ACCFREE = 29 };
+// Block order of a tile, step s -> 2 * chunk + (0: up projection, 1: down projection).  Two hidden buffers: up and down blocks
+// go in PAIRS  up(2p) up(2p+1) down(2p) down(2p+1): conv(2p) runs under up(2p+1), conv(2p+1) under down(2p), and the tensor pipe
+// switches between SS and TS operand mode 8 times per tile instead of 16 (~435 cycles each, tools/micro/hwprobe.cu T5).
+// One hidden buffer (FH = 384): up(c) down(c) in sequence.
+template <int NHD>
+__device__ __forceinline__ int ffn_step(int s) {
+  if (NHD == 2) { const int p = s >> 2, r = s & 3; return 2 * (2 * p + (r & 1)) + (r >> 1); }
+  return s;      // 2 c + {0, 1}
+}
 template <int FH> struct FfnCfg {
   static constexpr int KS = FH / 64;               // K slabs of the up projection
   static constexpr int CH = 4 * FH / 128;          // hidden chunks
@@ -529,13 +538,14 @@ __global__ void __launch_bounds__(F_THREADS, 1) k_tc_ffn(const FfnArgs a) {
     };
     for (int tile = blockIdx.x; TILE_OK(tile); tile += gridDim.x) {
 #pragma unroll 1
-      for (int c = 0; c < F_CH + NHD - 1; c++) {
-        if (c < F_CH)
+      for (int s2 = 0; s2 < F_CH * 2; s2++) {      // the MMA warp's block order (ffn_step below)
+        const int c = ffn_step<NHD>(s2) >> 1;
+        if ((ffn_step<NHD>(s2) & 1) == 0) {
           for (int ks = 0; ks < F_KS; ks++) load(a.w1 + (size_t)(rotc(c) * F_KS + ks) * 8192);
-        const int cc = c - (NHD - 1);
-        if (cc >= 0)
+        } else {
           for (int nb = 0; nb < F_NB; nb++)
-            for (int kh = 0; kh < 2; kh++) load(a.w2 + (size_t)(nb * (4 * F_H / 64) + 2 * rotc(cc) + kh) * 8192);
+            for (int kh = 0; kh < 2; kh++) load(a.w2 + (size_t)(nb * (4 * F_H / 64) + 2 * rotc(c) + kh) * 8192);
+        }
       }
     }
   } else if (warp == 12) {
@@ -583,8 +593,10 @@ __global__ void __launch_bounds__(F_THREADS, 1) k_tc_ffn(const FfnArgs a) {
       const uint32_t st = tl % NAS;
       mbar_wait(BAR(FB_AFULL + st), (tl / NAS) & 1);
 #pragma unroll 1
-      for (int c = 0; c < F_CH + NHD - 1; c++) {
-        if (c < F_CH) {      // up projection of chunk c: K slabs two at a time
+      for (int s2 = 0; s2 < F_CH * 2; s2++) {
+        const int c = ffn_step<NHD>(s2) >> 1;
+        const bool is_up = (ffn_step<NHD>(s2) & 1) == 0;
+        if (is_up) {      // up projection of chunk c: K slabs two at a time
           const uint32_t Hd = Hd0 + 128 * (c % NHD);
 #pragma unroll 1
           for (int kp = 0; kp < F_KS / 2; kp++) {
@@ -606,8 +618,8 @@ __global__ void __launch_bounds__(F_THREADS, 1) k_tc_ffn(const FfnArgs a) {
             __syncwarp();
           }
         }
-        if (c >= NHD - 1) {  // down projection of chunk c - (NHD - 1): one output block (both K halves) per iteration
-          const int cc = c - (NHD - 1), hb = cc % NHD;
+        if (!is_up) {  // down projection of chunk c: one output block (both K halves) per iteration
+          const int cc = c, hb = cc % NHD;
           const uint32_t Hd = Hd0 + 128 * hb;
           mbar_wait(BAR(FB_HSREADY + hb), nhid[hb] & 1);      // conversion of this chunk done
           nhid[hb]++;
