@@ -10,9 +10,10 @@ from .api import (GNData, GNGraphBatch, Padded, batch, batch_compact, batch_coo,
 from .layers import (GNBlock, GNCore, GNCoreList, GNSequential, GNFeedForward, GNGraphNorm, Dense, Chain,
                      LayerNorm, Dropout, set_precision, get_precision)
 from .shard import shard_ranges, shard_batch
+from .train import Trainer
 
 __all__ = [
     "GNGraphBatch", "batch", "batch_compact", "batch_coo", "pack_adjacency_bits", "unbatch", "GNBlock", "GNCore", "GNCoreList", "GNSequential", "efview", "nfview",
     "gfview", "flatunpaddednf", "flatunpaddedef", "logitcrossentropy", "collapsef", "unpaddedcollapsedef", "flatunpaddedcollapsedef",
-    "GNData", "Padded", "set_precision", "get_precision", "get_engine", "shard_ranges", "shard_batch",
+    "GNData", "Padded", "set_precision", "get_precision", "get_engine", "shard_ranges", "shard_batch", "Trainer",
 ]

@@ -79,6 +79,34 @@ SIGNATURES = {
 SIGNATURES["gnb_logit_cross_entropy"] = (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_void_p, C.c_void_p])
 
 
+class LinSrc(C.Structure):
+    _fields_ = [("x", C.c_void_p), ("d", C.c_int), ("ldx", C.c_int), ("W", C.c_void_p), ("gamma", C.c_void_p), ("beta", C.c_void_p),
+                ("eps", C.c_float), ("eps_mode", C.c_int)]
+
+
+class LinAdd(C.Structure):
+    _fields_ = [("a", C.c_void_p), ("idx", C.c_void_p), ("lda", C.c_int)]
+
+
+class LinArgs(C.Structure):
+    _fields_ = [("R", C.c_int64), ("Nout", C.c_int), ("ldw", C.c_int), ("nsrc", C.c_int), ("src", LinSrc * 3), ("bias", C.c_void_p),
+                ("nadd", C.c_int), ("add", LinAdd * 4), ("relu", C.c_int), ("out", C.c_void_p), ("ldo", C.c_int)]
+
+
+_vp, _i, _i64, _f = C.c_void_p, C.c_int, C.c_int64, C.c_float
+SIGNATURES["gnb_op_linear"] = (C.c_int, [_vp, C.POINTER(LinArgs)])
+SIGNATURES["gnb_op_segsum"] = (C.c_int, [_vp, _vp, _i, _vp, _i64, _vp, _vp])
+SIGNATURES["gnb_op_layernorm"] = (C.c_int, [_vp, _vp, _i64, _i, _vp, _vp, _f, _i, _vp])
+SIGNATURES["gnb_op_layernorm_bwd"] = (C.c_int, [_vp, _vp, _vp, _i64, _i, _vp, _f, _i, _vp, _vp])
+SIGNATURES["gnb_op_wgrad"] = (C.c_int, [_vp, _vp, _i, _i, _vp, _vp, _i, _i, _i64, _vp, _i])
+SIGNATURES["gnb_op_colsum"] = (C.c_int, [_vp, _vp, _i, _i, _i64, _vp])
+SIGNATURES["gnb_op_relu_mask"] = (C.c_int, [_vp, _vp, _vp, _i64])
+SIGNATURES["gnb_op_gather_add"] = (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i])
+SIGNATURES["gnb_op_transpose"] = (C.c_int, [_vp, _vp, _i, _i, _i, _vp])
+SIGNATURES["gnb_op_adamw"] = (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i64, _f, _f, _f, _f, _f, _i])
+SIGNATURES["gnb_graph_device_index"] = (C.c_int, [_vp] + [C.POINTER(C.c_void_p)] * 7)
+
+
 class ProfEntry(C.Structure):
     _fields_ = [("name", C.c_char * 48), ("launches", C.c_int64), ("ms", C.c_double),
                 ("alg_bytes", C.c_double), ("alg_flops", C.c_double)]

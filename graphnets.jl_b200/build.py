@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libgnb200.so")
 BUILD = os.path.join(HERE, "build")
-SOURCES = ["model.cu", "lower.cu", "fp32.cu", "tc.cu", "graphrows.cu", "smallk.cu", "tc_edge.cu", "tc_gemm.cu", "loss.cu"]
+SOURCES = ["model.cu", "lower.cu", "fp32.cu", "tc.cu", "graphrows.cu", "smallk.cu", "tc_edge.cu", "tc_gemm.cu", "loss.cu", "train.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
          "-Xcompiler", "-fPIC", "-Xptxas=-v"] + os.environ.get("GNB_EXTRA_NVCC_FLAGS", "").split()

@@ -72,6 +72,8 @@ struct FwdGraph {
 struct gnb_ctx {
   int device = 0;
   bool profiling = false;
+  void* train_ws = nullptr;      // scratch of the two-stage reductions of the training operators (train.cu), grown on demand
+  size_t train_ws_bytes = 0;
   std::vector<FwdGraph> fwd_graphs;
   uint64_t fwd_tick = 0;
   // the legacy default stream cannot be captured: forwards bound to it are captured / replayed on this side stream, forked from

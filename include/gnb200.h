@@ -171,6 +171,43 @@ int gnb_corelist_forward(gnb_ctx*, const gnb_graph*, const gnb_core_params* core
 int gnb_logit_cross_entropy(gnb_ctx*, const float* logits, const float* targets, int D, int64_t R,
                             float* loss, float* per_row);
 
+/* ---------------------------------------------------------------- training step ---------------- */
+/* Primitive operators of the backward pass of the GNBlock / GNCore forward (the reference differentiates it with Zygote inside
+ * Flux.withgradient, examples/sort/sort.jl:122-132; forward: src/gnblock.jl:63-69, src/gncore.jl:56-68).  fp32, device pointers,
+ * deterministic (no atomics).  The host side (graphnets.jl_b200/train.py) composes them into the adjoint of each layer; the
+ * flat gradient buffer is all-reduced over NCCL by the caller (torch.distributed) and applied with gnb_op_adamw. */
+typedef struct { const float* x; int d, ldx; const float* W; const float* gamma; const float* beta; float eps; int eps_mode; } gnb_lin_src;
+typedef struct { const float* a; const int32_t* idx; int lda; } gnb_lin_add;
+typedef struct {
+  int64_t R; int Nout, ldw, nsrc;      /* out = act( sum_s LN_s(x_s) W_s + bias + sum_j add_j[idx_j] ),  W_s: [d_s][ldw] */
+  gnb_lin_src src[3];
+  const float* bias;
+  int nadd; gnb_lin_add add[4];
+  int relu;
+  float* out; int ldo;
+} gnb_lin_args;
+int gnb_op_linear(gnb_ctx*, const gnb_lin_args*);      /* the forward's fused linear kernel (csrc/fp32.cu) */
+/* out[s] = sum over p in [ptr[s], ptr[s+1]) of x[perm ? perm[p] : p], ascending p */
+int gnb_op_segsum(gnb_ctx*, const float* x, int D, const int32_t* ptr, int64_t S, const int32_t* perm, float* out);
+int gnb_op_layernorm(gnb_ctx*, const float* x, int64_t R, int D, const float* gamma, const float* beta, float eps, int eps_mode, float* y);
+/* dx += adjoint of LayerNorm at x applied to g;  gxhat = g * xhat (column sums: d gamma; column sums of g: d beta) */
+int gnb_op_layernorm_bwd(gnb_ctx*, const float* x, const float* g, int64_t R, int D, const float* gamma, float eps, int eps_mode,
+                         float* dx, float* gxhat);
+/* dW[k][n] += sum_r X[idx ? idx[r] : r][k] * dY[r][n]      (dW: [K][ldw], the layout of a Flux Dense.weight block) */
+int gnb_op_wgrad(gnb_ctx*, const float* X, int ldx, int K, const int32_t* idx, const float* dY, int ldy, int N, int64_t R, float* dW, int ldw);
+int gnb_op_colsum(gnb_ctx*, const float* X, int ldx, int D, int64_t R, float* out /* += */);
+int gnb_op_relu_mask(gnb_ctx*, float* t, const float* h, int64_t n);      /* t[i] = h[i] > 0 ? t[i] : 0 */
+/* out[r] = a[r] + b1[idx1 ? idx1[r] : r] + b2[idx2 ? idx2[r] : r]   (a, b1, b2 optional; rows of width D) */
+int gnb_op_gather_add(gnb_ctx*, float* out, const float* a, const float* b1, const int32_t* idx1, const float* b2, const int32_t* idx2,
+                      int64_t R, int D);
+int gnb_op_transpose(gnb_ctx*, const float* in, int rows, int cols, int ld_in, float* out /* [cols][rows] */);
+int gnb_op_adamw(gnb_ctx*, float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,
+                 float weight_decay, int step);
+/* device pointers of the lowered index (owned by the graph) */
+int gnb_graph_device_index(const gnb_graph*, const int32_t** edge_src, const int32_t** edge_dst, const int32_t** edge_graph,
+                           const int32_t** node_graph, const int32_t** graph_edge_ptr, const int32_t** graph_node_ptr,
+                           const int32_t** node_in_ptr);
+
 #ifdef __cplusplus
 }
 #endif
