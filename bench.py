@@ -254,6 +254,13 @@ def extra_legs(gn, args, T, rank, world, local_rank, peaks):
         torch.cuda.empty_cache()
     except Exception as e:      # noqa: BLE001
         out["cfg5_shard_8192"] = {"error": repr(e)[:300]}
+    # ---- config 5's TRAINING step (every rank: the gradient all-reduce is a collective), bounded size
+    try:
+        torch.cuda.set_device(local_rank)
+        out["cfg5_train_step"] = train_leg(torch, gn, W, T.dist, world, 256)
+        torch.cuda.empty_cache()
+    except Exception as e:      # noqa: BLE001
+        out["cfg5_train_step"] = {"error": repr(e)[:300]}
     if rank != 0:
         return out
     # ---- the headline model on the fp32 CUDA-core path (1e-5 parity): what the default precision of the drop-in costs
@@ -318,6 +325,48 @@ def extra_legs(gn, args, T, rank, world, local_rank, peaks):
     except Exception as e:      # noqa: BLE001
         out["cfg3_full"] = {"error": repr(e)[:300]}
     return out
+
+
+def train_leg(torch, gn, W, dist, world, graphs, steps=3, lr=2e-5):
+    """Config 5's training step (BASELINE configs[4]: hidden 256, gradient all-reduce) on the fp32 path, at a bounded number of
+    graphs per GPU: forward with kept activations + cross-entropy on node and edge outputs + backward + all-reduce of the flat
+    gradient buffer (NCCL) + AdamW (graphnets.jl_b200/train.py; gradients checked against torch float64 autograd in
+    tests/test_gpu_train.py)."""
+    adj, ef, nf = synth("cfg5", graphs, 77)
+    x = gn.batch_compact(adj, ef, nf, device=torch.cuda.current_device())
+    tr = gn.Trainer(W.model_params("cfg5"), engine=x.graphs.engine)
+    dev = tr.eng.torch_device
+    g = x.graphs
+    rng = np.random.default_rng(5)
+    te = torch.from_numpy(np.eye(3, dtype=np.float32)[rng.integers(0, 3, g.E)]).to(dev)
+    tn = torch.from_numpy(np.eye(4, dtype=np.float32)[rng.integers(0, 4, g.N)]).to(dev)
+
+    def step():
+        y = tr.forward(x)
+        le, de = tr.cross_entropy(y[0], te)
+        ln, dn = tr.cross_entropy(y[1], tn)
+        tr.backward(de, dn, None)
+        tr.step(lr=lr)
+        return le + ln
+    l0 = float(step().cpu())      # warm-up (workspace growth, index upload)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(steps):
+        l = step()
+    ev1.record()
+    torch.cuda.synchronize()
+    ms = ev0.elapsed_time(ev1) / steps
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t[0])
+    return {"ms_per_step": ms, "graphs_per_gpu": graphs, "edges_per_gpu": int(g.E), "edges_per_sec": world * g.E / (ms * 1e-3),
+            "parameters": int(tr.params.numel()), "allreduce_bytes_per_step": int(tr.params.numel()) * 4 if world > 1 else 0,
+            "world": world, "precision": "fp32", "loss_first": l0, "loss_last": float(l.cpu()), "steps": steps,
+            "workload": "cfg5 training step: enc -> 4x GNCore(256) -> dec, forward + cross-entropy + backward + gradient all-reduce + AdamW, fp32 CUDA-core path"}
 
 
 def cuda_graph_leg(torch, T1, model, x, prec, steps):

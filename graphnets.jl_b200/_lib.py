@@ -77,6 +77,7 @@ SIGNATURES = {
 
 
 SIGNATURES["gnb_logit_cross_entropy"] = (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_void_p, C.c_void_p])
+SIGNATURES["gnb_logit_cross_entropy_bwd"] = (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_void_p])
 
 
 class LinSrc(C.Structure):

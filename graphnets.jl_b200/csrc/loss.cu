@@ -54,7 +54,37 @@ __global__ void k_xent_finish(const double* __restrict__ block_part, int nb, int
   }
 }
 
+// d loss / d logits of the mean cross-entropy:  (sum_d t[r][d]) softmax(x[r]) - t[r], scaled by scale / R; one warp per row
+__global__ void __launch_bounds__(LOSS_THREADS) k_xent_bwd(const float* __restrict__ x, const float* __restrict__ t, int D, int64_t R, float scale,
+                                                         float* __restrict__ dx) {
+  const int lane = threadIdx.x & 31;
+  const int64_t r = ((int64_t)blockIdx.x * LOSS_THREADS + threadIdx.x) >> 5;
+  if (r >= R) return;
+  const float* xr = x + (size_t)r * D;
+  const float* tr = t + (size_t)r * D;
+  float mx = -INFINITY;
+  for (int d = lane; d < D; d += 32) mx = fmaxf(mx, xr[d]);
+  for (int o = 16; o; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  float se = 0.f, ts = 0.f;
+  for (int d = lane; d < D; d += 32) { se += expf(xr[d] - mx); ts += tr[d]; }
+  for (int o = 16; o; o >>= 1) { se += __shfl_xor_sync(0xffffffffu, se, o); ts += __shfl_xor_sync(0xffffffffu, ts, o); }
+  const float c = scale / (float)R;
+  for (int d = lane; d < D; d += 32) dx[(size_t)r * D + d] = c * (ts * expf(xr[d] - mx) / se - tr[d]);
+}
+
 }  // namespace
+
+extern "C" int gnb_logit_cross_entropy_bwd(gnb_ctx* ctx, const float* logits, const float* targets, int D, int64_t R, float scale,
+                                           float* dlogits) {
+  GNB_CHECK(ctx && D > 0 && R >= 0, "gnb_logit_cross_entropy_bwd: bad arguments");
+  if (R == 0) return GNB_OK;
+  GNB_CHECK(logits && targets && dlogits, "gnb_logit_cross_entropy_bwd: null matrix");
+  GNB_CUDA(cudaSetDevice(ctx->device));
+  Launch L(ctx, "xent_bwd", 12.0 * R * D, 0);
+  k_xent_bwd<<<ceil_div(R * 32, LOSS_THREADS), LOSS_THREADS, 0, ctx->stream>>>(logits, targets, D, R, scale, dlogits);
+  GNB_CUDA(cudaGetLastError());
+  return GNB_OK;
+}
 
 extern "C" int gnb_logit_cross_entropy(gnb_ctx* ctx, const float* logits, const float* targets, int D, int64_t R, float* loss,
                                        float* per_row) {

@@ -93,6 +93,18 @@ class _Ops:
         return out
 
 
+def allreduce_flat(grads, average=True):
+    """One all-reduce of the flat gradient buffer over the default process group (NCCL for device tensors, gloo on the CPU in the
+    tests); a no-op without an initialised group.  Data-parallel training over graph shards: every rank holds the gradient of ITS
+    shard's loss, the sum (or mean) is the gradient of the whole batch (weights are replicated)."""
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(grads, op=dist.ReduceOp.SUM)
+        if average:
+            grads.div_(dist.get_world_size())
+    return grads
+
+
 class _Index:
     """Device index arrays of a lowered batch (owned by the graph handle) + the sender-sorted permutation of the edges."""
 
@@ -222,9 +234,12 @@ class Trainer:
     def forward(self, x):
         """x: the batched NamedTuple of gn.batch (compact torch tensors inside).  Returns (ef, nf, gf) compact device tensors."""
         self.eng.bind_stream()
-        ix = _Index(x.graphs)
-        zeros_idx = torch.zeros(max(ix.E, ix.N, ix.B, 1), dtype=torch.int32, device=self.eng.torch_device)
-        ix.zeros = lambda n: zeros_idx
+        if getattr(self, "_ix", None) is None or self._ix[0] is not x.graphs:      # index tensors + sender permutation: once per batch
+            ix = _Index(x.graphs)
+            zeros_idx = torch.zeros(max(ix.E, ix.N, ix.B, 1), dtype=torch.int32, device=self.eng.torch_device)
+            ix.zeros = lambda n: zeros_idx
+            self._ix = (x.graphs, ix)
+        ix = self._ix[1]
         o = self.ops
         cur = [None if f is None else f.compact for f in (x.ef, x.nf, x.gf)]
         R = (ix.E, ix.N, ix.B)
@@ -359,14 +374,20 @@ class Trainer:
             d = dx
         return tuple(d)
 
+    # ------------------------------------------------------------------ loss of the reference's training example
+    def cross_entropy(self, logits, targets, scale=1.0):
+        """Flux.logitcrossentropy over compact rows (examples/sort/sort.jl:76-78): returns (loss: device scalar tensor, dlogits)."""
+        R, D = logits.shape
+        loss = torch.empty(1, dtype=torch.float32, device=logits.device)
+        dl = torch.empty_like(logits)
+        check(lib.gnb_logit_cross_entropy(self.eng.ctx, _P(logits), _P(targets), D, R, _P(loss), None))
+        check(lib.gnb_logit_cross_entropy_bwd(self.eng.ctx, _P(logits), _P(targets), D, R, float(scale), _P(dl)))
+        return loss, dl
+
     # ------------------------------------------------------------------ optimiser step
     def step(self, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, average=True):
         """Gradient all-reduce over the process group (when torch.distributed is initialised; NCCL on GPUs) + AdamW."""
-        import torch.distributed as dist
-        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-            dist.all_reduce(self.grads, op=dist.ReduceOp.SUM)
-            if average:
-                self.grads.div_(dist.get_world_size())
+        allreduce_flat(self.grads, average)
         self.t += 1
         check(lib.gnb_op_adamw(self.eng.ctx, _P(self.params), _P(self.grads), _P(self.m), _P(self.v), self.params.numel(), lr, betas[0], betas[1],
                                eps, weight_decay, self.t))

@@ -170,6 +170,8 @@ int gnb_corelist_forward(gnb_ctx*, const gnb_graph*, const gnb_core_params* core
  * [R] (NULL: not written).  Deterministic (fixed-order sums). */
 int gnb_logit_cross_entropy(gnb_ctx*, const float* logits, const float* targets, int D, int64_t R,
                             float* loss, float* per_row);
+/* dlogits = scale * d loss / d logits of the mean cross-entropy above (the cotangent the backward pass starts from) */
+int gnb_logit_cross_entropy_bwd(gnb_ctx*, const float* logits, const float* targets, int D, int64_t R, float scale, float* dlogits);
 
 /* ---------------------------------------------------------------- training step ---------------- */
 /* Primitive operators of the backward pass of the GNBlock / GNCore forward (the reference differentiates it with Zygote inside

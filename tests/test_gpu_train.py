@@ -120,3 +120,19 @@ def test_adamw_and_descent(gn):
             ref = p - 1e-2 * ((m / 0.1) / (np.sqrt(v / 0.001) + 1e-8) + 1e-2 * p)
             assert _rel(tr.params.cpu().numpy().astype(np.float64), ref) <= 1e-5
     assert losses[-1] < losses[0], losses
+
+
+def test_cross_entropy_gradient(gn):
+    """d logitcrossentropy / d logits against torch autograd (examples/sort/sort.jl:76-78)."""
+    rng = np.random.default_rng(5)
+    R, D = 1000, 7
+    x = rng.standard_normal((R, D)).astype(np.float32)
+    t = np.eye(D, dtype=np.float32)[rng.integers(0, D, R)]
+    tr = gn.Trainer(W.model_params("cfg1"))
+    dev = tr.eng.torch_device
+    loss, dl = tr.cross_entropy(torch.from_numpy(x).to(dev), torch.from_numpy(t).to(dev))
+    xt = torch.tensor(x, dtype=torch.float64, requires_grad=True)
+    ref = -(torch.tensor(t, dtype=torch.float64) * torch.log_softmax(xt, dim=1)).sum(dim=1).mean()
+    ref.backward()
+    assert abs(float(loss.cpu()) - float(ref)) <= 1e-5 * abs(float(ref))
+    assert _rel(dl.cpu().numpy().astype(np.float64), xt.grad.numpy()) <= 1e-5
