@@ -327,7 +327,7 @@ def extra_legs(gn, args, T, rank, world, local_rank, peaks):
     return out
 
 
-def train_leg(torch, gn, W, dist, world, graphs, steps=3, lr=2e-5):
+def train_leg(torch, gn, W, dist, world, graphs, steps=3, lr=5e-6):
     """Config 5's training step (BASELINE configs[4]: hidden 256, gradient all-reduce) on the fp32 path, at a bounded number of
     graphs per GPU: forward with kept activations + cross-entropy on node and edge outputs + backward + all-reduce of the flat
     gradient buffer (NCCL) + AdamW (graphnets.jl_b200/train.py; gradients checked against torch float64 autograd in
