@@ -79,44 +79,56 @@ __global__ void k_ln_bwd(const float* __restrict__ x, const float* __restrict__ 
 }
 
 // ---- dW[k][n] (+)= sum_r X[idx ? idx[r] : r][k] dY[r][n]: stage 1 = partial sums per row chunk (grid.z), stage 2 = ordered reduction
-constexpr int WG_T = 32;
+// 64 x 64 output tile per CTA, 4 x 4 per thread, 16 rows per step (LDS.128 : FFMA = 2 : 16)
+constexpr int WG_T = 64, WG_R = 16;
 __global__ void __launch_bounds__(256) k_wgrad_part(const float* __restrict__ X, int ldx, int K, const int32_t* __restrict__ idx,
                                                     const float* __restrict__ dY, int ldy, int N, int64_t R, int64_t rows_per_chunk,
                                                     float* __restrict__ part /*[chunks][K][N]*/) {
-  __shared__ float Xs[WG_T][WG_T + 1];
-  __shared__ float Ys[WG_T][WG_T + 1];
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;      // 32 x 8
+  __shared__ __align__(16) float Xs[WG_R][WG_T];
+  __shared__ __align__(16) float Ys[WG_R][WG_T];
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;      // 16 x 16: k = k0 + 4 ty + i, n = n0 + 4 tx + j
   const int k0 = blockIdx.x * WG_T, n0 = blockIdx.y * WG_T;
   const int64_t r_begin = (int64_t)blockIdx.z * rows_per_chunk;
   const int64_t r_end = r_begin + rows_per_chunk < R ? r_begin + rows_per_chunk : R;
-  float acc[4] = {0.f, 0.f, 0.f, 0.f};      // k = k0 + 4 ty + i, n = n0 + tx
-  for (int64_t rb = r_begin; rb < r_end; rb += WG_T) {
-    // tiles: thread (tx, ty) loads rows ty, ty + 8, ... column tx
-    for (int rr = ty; rr < WG_T; rr += 8) {
+  const int lc = threadIdx.x & 63, lr = threadIdx.x >> 6;      // loader: column lc, rows lr, lr + 4, ...
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; i++)
+#pragma unroll
+    for (int j = 0; j < 4; j++) acc[i][j] = 0.f;
+  for (int64_t rb = r_begin; rb < r_end; rb += WG_R) {
+#pragma unroll
+    for (int rr = lr; rr < WG_R; rr += 4) {
       const int64_t r = rb + rr;
       float xv = 0.f, yv = 0.f;
       if (r < r_end) {
         const int64_t xr = idx ? (int64_t)idx[r] : r;
-        if (k0 + tx < K) xv = X[(size_t)xr * ldx + k0 + tx];
-        if (n0 + tx < N) yv = dY[(size_t)r * ldy + n0 + tx];
+        if (k0 + lc < K) xv = X[(size_t)xr * ldx + k0 + lc];
+        if (n0 + lc < N) yv = dY[(size_t)r * ldy + n0 + lc];
       }
-      Xs[rr][tx] = xv;
-      Ys[rr][tx] = yv;
+      Xs[rr][lc] = xv;
+      Ys[rr][lc] = yv;
     }
     __syncthreads();
-#pragma unroll 8
-    for (int rr = 0; rr < WG_T; rr++) {
-      const float yv = Ys[rr][tx];
 #pragma unroll
-      for (int i = 0; i < 4; i++) acc[i] = fmaf(Xs[rr][4 * ty + i], yv, acc[i]);
+    for (int rr = 0; rr < WG_R; rr++) {
+      const float4 a4 = *reinterpret_cast<const float4*>(&Xs[rr][4 * ty]);
+      const float4 b4 = *reinterpret_cast<const float4*>(&Ys[rr][4 * tx]);
+      const float av[4] = {a4.x, a4.y, a4.z, a4.w}, bv[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+      for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
     }
     __syncthreads();
   }
 #pragma unroll
-  for (int i = 0; i < 4; i++) {
-    const int k = k0 + 4 * ty + i, n = n0 + tx;
-    if (k < K && n < N) part[((size_t)blockIdx.z * K + k) * N + n] = acc[i];
-  }
+  for (int i = 0; i < 4; i++)
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      const int k = k0 + 4 * ty + i, n = n0 + 4 * tx + j;
+      if (k < K && n < N) part[((size_t)blockIdx.z * K + k) * N + n] = acc[i][j];
+    }
 }
 __global__ void k_reduce_parts(const float* __restrict__ part, int chunks, int K, int N, float* __restrict__ out, int ldo) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
