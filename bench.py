@@ -332,7 +332,8 @@ def train_leg(torch, gn, W, dist, world, graphs, steps=3, lr=5e-6):
     graphs per GPU: forward with kept activations + cross-entropy on node and edge outputs + backward + all-reduce of the flat
     gradient buffer (NCCL) + AdamW (graphnets.jl_b200/train.py; gradients checked against torch float64 autograd in
     tests/test_gpu_train.py)."""
-    adj, ef, nf = synth("cfg5", graphs, 77)
+    rank_ = dist.get_rank() if (dist is not None and world > 1) else 0
+    adj, ef, nf = synth("cfg5", graphs, 77 + rank_)      # every rank its own shard (weak scaling); weights replicated
     x = gn.batch_compact(adj, ef, nf, device=torch.cuda.current_device())
     tr = gn.Trainer(W.model_params("cfg5"), engine=x.graphs.engine)
     dev = tr.eng.torch_device
