@@ -12,7 +12,7 @@
 
 namespace {
 
-constexpr int TK = 32;
+constexpr int TK = 16;      // K tile; two shared-memory buffers of TK rows
 
 __device__ __forceinline__ float ln_rstd(float var, float eps, int mode) {
   if (mode == GNB_EPS_SQRT_VAR_EPS2) return 1.0f / sqrtf(var + eps * eps);
@@ -22,16 +22,19 @@ __device__ __forceinline__ float ln_rstd(float var, float eps, int mode) {
 
 // Thread tile: QM x QN quads of 4x4; quads are strided by TM/QM rows and TN/QN columns so
 // every shared-memory read is a conflict-free LDS.128.
+#ifndef GNB_LIN_MINB
+#define GNB_LIN_MINB 2      /* <= 128 registers: two CTAs per SM (one CTA of 153 registers measured 40 % slower) */
+#endif
 template <int TM, int TN, int QM, int QN>
-__global__ void __launch_bounds__((TM / (4 * QM)) * (TN / (4 * QN)))
+__global__ void __launch_bounds__((TM / (4 * QM)) * (TN / (4 * QN)), GNB_LIN_MINB)
 k_linear(const LinArgs a) {
   constexpr int TXN = TN / (4 * QN);
   constexpr int TYN = TM / (4 * QM);
   constexpr int NT = TXN * TYN;
   constexpr int LDA = TM + 4;
   constexpr int LDB = TN + 4;
-  __shared__ __align__(16) float As[TK * LDA];
-  __shared__ __align__(16) float Ws[TK * LDB];
+  __shared__ __align__(16) float As[2 * TK * LDA];
+  __shared__ __align__(16) float Ws[2 * TK * LDB];
   __shared__ float s_mu[3][TM];
   __shared__ float s_rs[3][TM];
 
@@ -74,6 +77,45 @@ k_linear(const LinArgs a) {
       }
       continue;
     }
+    if ((S.d & 3) == 0 && S.d <= 512 && (S.ldx & 3) == 0 && ((((uintptr_t)S.x) & 15) == 0)) {
+      // wide rows: 8 lanes per row, FOUR rows of a warp in flight, the row in registers (float4 chunks c = 8 i + l8), one pass
+      // over memory and 3 shuffle levels per statistic.  (A warp per row with two dependent passes cost 2 TM / NW round trips:
+      // 19 k cycles per CTA at 128-wide layers - more than the whole K loop.)
+      const int rr = lane >> 3, l8 = lane & 7;
+      const int nchunk = S.d >> 2;
+      for (int r4 = warp * 4; r4 < TM; r4 += NW * 4) {
+        const int r = r4 + rr;
+        const int64_t row = row0 + r;
+        const bool ok = r < TM && row < a.R;
+        const float4* xr = reinterpret_cast<const float4*>(S.x + (size_t)(ok ? row : row0) * S.ldx);
+        float4 v[16];
+        float sum = 0.f;
+#pragma unroll
+        for (int i = 0; i < 16; i++) {
+          const int c = 8 * i + l8;
+          v[i] = (ok && c < nchunk) ? xr[c] : make_float4(0.f, 0.f, 0.f, 0.f);
+          sum += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+        }
+#pragma unroll
+        for (int o = 1; o < 8; o <<= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        const float mu = sum / (float)S.d;
+        float sq = 0.f;
+#pragma unroll
+        for (int i = 0; i < 16; i++) {
+          if (8 * i + l8 < nchunk) {
+            const float dx = v[i].x - mu, dy = v[i].y - mu, dz = v[i].z - mu, dw = v[i].w - mu;
+            sq += (dx * dx + dy * dy) + (dz * dz + dw * dw);
+          }
+        }
+#pragma unroll
+        for (int o = 1; o < 8; o <<= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+        if (l8 == 0 && r < TM) {
+          s_mu[s][r] = ok ? mu : 0.f;
+          s_rs[s][r] = ok ? ln_rstd(sq / (float)S.d, S.eps, S.eps_mode) : 0.f;
+        }
+      }
+      continue;
+    }
     for (int r = warp; r < TM; r += NW) {
       int64_t row = row0 + r;
       float mu = 0.f, rs = 0.f;
@@ -105,79 +147,123 @@ k_linear(const LinArgs a) {
 #pragma unroll
     for (int j = 0; j < QN * 4; j++) acc[i][j] = 0.f;
 
-  for (int s = 0; s < a.nsrc; s++) {
+  // ---- main loop over K tiles of all sources, software pipelined: the global loads of tile t+1 (into registers, LayerNorm
+  // applied on the way) are in flight while tile t is multiplied out of shared memory; two shared-memory buffers, one
+  // __syncthreads per tile.  (The un-pipelined loop ran at 22 TFLOP/s = 30 % of the fp32 FMA peak at 128-wide layers.)
+  int ntile[3] = {0, 0, 0}, T = 0;
+  for (int s = 0; s < a.nsrc; s++) { ntile[s] = (a.src[s].d + TK - 1) / TK; T += ntile[s]; }
+  constexpr int A_PER = (TM * (TK / 4) + NT - 1) / NT;
+  constexpr int W_PER = (TK * (TN / 4) + NT - 1) / NT;
+  float4 ra[A_PER], rw[W_PER];
+  auto gload = [&](int t) {
+    int s = 0;
+    while (t >= ntile[s]) { t -= ntile[s]; s++; }
+    const int k0 = t * TK;
     const LinSrc& S = a.src[s];
     const bool has_ln = S.gamma != nullptr;
     const bool xvec = ((S.ldx & 3) == 0) && ((((uintptr_t)S.x) & 15) == 0);
     const bool wvec = ((a.ldw & 3) == 0) && ((((uintptr_t)S.W) & 15) == 0) && ((col0 & 3) == 0);
-    for (int k0 = 0; k0 < S.d; k0 += TK) {
-      // A tile: TM rows x TK k, stored transposed As[k][r]
-      for (int idx = tid; idx < TM * (TK / 4); idx += NT) {
-        int r = idx / (TK / 4);
-        int k = k0 + (idx % (TK / 4)) * 4;
-        int64_t row = row0 + r;
-        float v[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int i = 0; i < A_PER; i++) {
+      const int idx = tid + i * NT;
+      float v[4] = {0.f, 0.f, 0.f, 0.f};
+      if (idx < TM * (TK / 4)) {
+        const int r = idx / (TK / 4);
+        const int k = k0 + (idx % (TK / 4)) * 4;
+        const int64_t row = row0 + r;
         if (row < a.R && k < S.d) {
           const float* p = S.x + (size_t)row * S.ldx + k;
           if (xvec && k + 3 < S.d) {
-            float4 t = *reinterpret_cast<const float4*>(p);
-            v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+            const float4 t4 = *reinterpret_cast<const float4*>(p);
+            v[0] = t4.x; v[1] = t4.y; v[2] = t4.z; v[3] = t4.w;
           } else {
 #pragma unroll
-            for (int i = 0; i < 4; i++)
-              if (k + i < S.d) v[i] = p[i];
+            for (int q = 0; q < 4; q++)
+              if (k + q < S.d) v[q] = p[q];
           }
           if (has_ln) {
-            float mu = s_mu[s][r], rs = s_rs[s][r];
+            const float mu = s_mu[s][r], rs = s_rs[s][r];
 #pragma unroll
-            for (int i = 0; i < 4; i++)
-              if (k + i < S.d) v[i] = (v[i] - mu) * rs * S.gamma[k + i] + S.beta[k + i];
+            for (int q = 0; q < 4; q++)
+              if (k + q < S.d) v[q] = (v[q] - mu) * rs * S.gamma[k + q] + S.beta[k + q];
           }
         }
-        int kk = k - k0;
-#pragma unroll
-        for (int i = 0; i < 4; i++) As[(kk + i) * LDA + r] = v[i];
       }
-      // W tile: TK k x TN n
-      for (int idx = tid; idx < TK * (TN / 4); idx += NT) {
-        int kk = idx / (TN / 4);
-        int n = (idx % (TN / 4)) * 4;
-        int k = k0 + kk;
-        float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+      ra[i] = make_float4(v[0], v[1], v[2], v[3]);
+    }
+#pragma unroll
+    for (int i = 0; i < W_PER; i++) {
+      const int idx = tid + i * NT;
+      float4 t4 = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (idx < TK * (TN / 4)) {
+        const int kk = idx / (TN / 4);
+        const int n = (idx % (TN / 4)) * 4;
+        const int k = k0 + kk;
         if (k < S.d) {
           const float* p = S.W + (size_t)k * a.ldw + col0 + n;
           if (wvec && col0 + n + 3 < a.Nout) {
-            t = *reinterpret_cast<const float4*>(p);
+            t4 = *reinterpret_cast<const float4*>(p);
           } else {
-            if (col0 + n + 0 < a.Nout) t.x = p[0];
-            if (col0 + n + 1 < a.Nout) t.y = p[1];
-            if (col0 + n + 2 < a.Nout) t.z = p[2];
-            if (col0 + n + 3 < a.Nout) t.w = p[3];
+            if (col0 + n + 0 < a.Nout) t4.x = p[0];
+            if (col0 + n + 1 < a.Nout) t4.y = p[1];
+            if (col0 + n + 2 < a.Nout) t4.z = p[2];
+            if (col0 + n + 3 < a.Nout) t4.w = p[3];
           }
         }
-        *reinterpret_cast<float4*>(&Ws[kk * LDB + n]) = t;
       }
-      __syncthreads();
-#pragma unroll 8
-      for (int kk = 0; kk < TK; kk++) {
-        float av[QM * 4], bv[QN * 4];
-#pragma unroll
-        for (int q = 0; q < QM; q++) {
-          float4 t = *reinterpret_cast<const float4*>(&As[kk * LDA + q * (TM / QM) + ty * 4]);
-          av[q * 4 + 0] = t.x; av[q * 4 + 1] = t.y; av[q * 4 + 2] = t.z; av[q * 4 + 3] = t.w;
-        }
-#pragma unroll
-        for (int q = 0; q < QN; q++) {
-          float4 t = *reinterpret_cast<const float4*>(&Ws[kk * LDB + q * (TN / QN) + tx * 4]);
-          bv[q * 4 + 0] = t.x; bv[q * 4 + 1] = t.y; bv[q * 4 + 2] = t.z; bv[q * 4 + 3] = t.w;
-        }
-#pragma unroll
-        for (int i = 0; i < QM * 4; i++)
-#pragma unroll
-          for (int j = 0; j < QN * 4; j++) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
-      }
-      __syncthreads();
+      rw[i] = t4;
     }
+  };
+  auto sstore = [&](int buf) {
+    float* Ab = As + buf * (TK * LDA);
+    float* Wb = Ws + buf * (TK * LDB);
+#pragma unroll
+    for (int i = 0; i < A_PER; i++) {
+      const int idx = tid + i * NT;
+      if (idx < TM * (TK / 4)) {
+        const int r = idx / (TK / 4), kk = (idx % (TK / 4)) * 4;      // stored transposed: As[k][r]
+        Ab[(kk + 0) * LDA + r] = ra[i].x; Ab[(kk + 1) * LDA + r] = ra[i].y;
+        Ab[(kk + 2) * LDA + r] = ra[i].z; Ab[(kk + 3) * LDA + r] = ra[i].w;
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < W_PER; i++) {
+      const int idx = tid + i * NT;
+      if (idx < TK * (TN / 4)) {
+        const int kk = idx / (TN / 4), n = (idx % (TN / 4)) * 4;
+        *reinterpret_cast<float4*>(&Wb[kk * LDB + n]) = rw[i];
+      }
+    }
+  };
+  if (T > 0) {
+    gload(0);
+    sstore(0);
+  }
+  __syncthreads();
+  for (int t = 0; t < T; t++) {
+    if (t + 1 < T) gload(t + 1);
+    const float* Ab = As + (t & 1) * (TK * LDA);
+    const float* Wb = Ws + (t & 1) * (TK * LDB);
+#pragma unroll
+    for (int kk = 0; kk < TK; kk++) {
+      float av[QM * 4], bv[QN * 4];
+#pragma unroll
+      for (int q = 0; q < QM; q++) {
+        const float4 t4 = *reinterpret_cast<const float4*>(&Ab[kk * LDA + q * (TM / QM) + ty * 4]);
+        av[q * 4 + 0] = t4.x; av[q * 4 + 1] = t4.y; av[q * 4 + 2] = t4.z; av[q * 4 + 3] = t4.w;
+      }
+#pragma unroll
+      for (int q = 0; q < QN; q++) {
+        const float4 t4 = *reinterpret_cast<const float4*>(&Wb[kk * LDB + q * (TN / QN) + tx * 4]);
+        bv[q * 4 + 0] = t4.x; bv[q * 4 + 1] = t4.y; bv[q * 4 + 2] = t4.z; bv[q * 4 + 3] = t4.w;
+      }
+#pragma unroll
+      for (int i = 0; i < QM * 4; i++)
+#pragma unroll
+        for (int j = 0; j < QN * 4; j++) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+    if (t + 1 < T) sstore((t + 1) & 1);
+    __syncthreads();
   }
 
   // ---- epilogue: bias + gathered addends + activation + store ---------------------------
