@@ -84,8 +84,8 @@ constexpr int WG_T = 64, WG_R = 16;
 __global__ void __launch_bounds__(256) k_wgrad_part(const float* __restrict__ X, int ldx, int K, const int32_t* __restrict__ idx,
                                                     const float* __restrict__ dY, int ldy, int N, int64_t R, int64_t rows_per_chunk,
                                                     float* __restrict__ part /*[chunks][K][N]*/) {
-  __shared__ __align__(16) float Xs[WG_R][WG_T];
-  __shared__ __align__(16) float Ys[WG_R][WG_T];
+  __shared__ __align__(16) float Xs[2][WG_R][WG_T];
+  __shared__ __align__(16) float Ys[2][WG_R][WG_T];
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;      // 16 x 16: k = k0 + 4 ty + i, n = n0 + 4 tx + j
   const int k0 = blockIdx.x * WG_T, n0 = blockIdx.y * WG_T;
   const int64_t r_begin = (int64_t)blockIdx.z * rows_per_chunk;
@@ -96,30 +96,43 @@ __global__ void __launch_bounds__(256) k_wgrad_part(const float* __restrict__ X,
   for (int i = 0; i < 4; i++)
 #pragma unroll
     for (int j = 0; j < 4; j++) acc[i][j] = 0.f;
-  for (int64_t rb = r_begin; rb < r_end; rb += WG_R) {
+  // software pipelined: the rows of step s+1 are fetched into registers while step s is multiplied out of shared memory
+  float px[WG_R / 4], py[WG_R / 4];
+  auto gload = [&](int64_t rb) {
 #pragma unroll
-    for (int rr = lr; rr < WG_R; rr += 4) {
-      const int64_t r = rb + rr;
+    for (int q = 0; q < WG_R / 4; q++) {
+      const int64_t r = rb + lr + 4 * q;
       float xv = 0.f, yv = 0.f;
       if (r < r_end) {
         const int64_t xr = idx ? (int64_t)idx[r] : r;
         if (k0 + lc < K) xv = X[(size_t)xr * ldx + k0 + lc];
         if (n0 + lc < N) yv = dY[(size_t)r * ldy + n0 + lc];
       }
-      Xs[rr][lc] = xv;
-      Ys[rr][lc] = yv;
+      px[q] = xv; py[q] = yv;
     }
-    __syncthreads();
+  };
+  auto sstore = [&](int buf) {
+#pragma unroll
+    for (int q = 0; q < WG_R / 4; q++) { Xs[buf][lr + 4 * q][lc] = px[q]; Ys[buf][lr + 4 * q][lc] = py[q]; }
+  };
+  gload(r_begin);
+  sstore(0);
+  __syncthreads();
+  int buf = 0;
+  for (int64_t rb = r_begin; rb < r_end; rb += WG_R, buf ^= 1) {
+    const bool more = rb + WG_R < r_end;
+    if (more) gload(rb + WG_R);
 #pragma unroll
     for (int rr = 0; rr < WG_R; rr++) {
-      const float4 a4 = *reinterpret_cast<const float4*>(&Xs[rr][4 * ty]);
-      const float4 b4 = *reinterpret_cast<const float4*>(&Ys[rr][4 * tx]);
+      const float4 a4 = *reinterpret_cast<const float4*>(&Xs[buf][rr][4 * ty]);
+      const float4 b4 = *reinterpret_cast<const float4*>(&Ys[buf][rr][4 * tx]);
       const float av[4] = {a4.x, a4.y, a4.z, a4.w}, bv[4] = {b4.x, b4.y, b4.z, b4.w};
 #pragma unroll
       for (int i = 0; i < 4; i++)
 #pragma unroll
         for (int j = 0; j < 4; j++) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
     }
+    if (more) sstore(buf ^ 1);
     __syncthreads();
   }
 #pragma unroll
