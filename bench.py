@@ -350,6 +350,7 @@ def train_leg(torch, gn, W, dist, world, graphs, steps=3, lr=5e-6):
         tr.step(lr=lr)
         return le + ln
     l0 = float(step().cpu())      # warm-up (workspace growth, index upload)
+    step()                        # second warm-up: the caching allocator of the tensors the step allocates settles
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
