@@ -311,6 +311,53 @@ function logitcrossentropy(yhat, y)
     loss
 end
 
+# gradient of the loss above w.r.t. the logits (the cotangent a backward pass starts from)
+function logitcrossentropy_grad(yhat, y; scale::Real=1)
+    a, b = compact(yhat), compact(y)
+    d = similar(a)
+    check(ccall((:gnb_logit_cross_entropy_bwd, LIB), Cint,
+                (Ptr{Cvoid}, CuPtr{Float32}, CuPtr{Float32}, Cint, Int64, Cfloat, CuPtr{Float32}),
+                ctx(), pointer(a), pointer(b), size(a, 1), size(a, 2), Float32(scale), pointer(d)))
+    d
+end
+
+# ---------------------------------------------------------------- training step (examples/sort/sort.jl:118-132), fp32
+# Thin wrappers of the backward operators (include/gnb200.h, "training step"): an `rrule` per layer composes them exactly as
+# graphnets.jl_b200/train.py::Trainer does (INTEGRATION.md).  All arrays are compact (D, rows) CuMatrices.
+struct LinSrc;  x::CuPtr{Float32}; d::Cint; ldx::Cint; W::CuPtr{Float32}; gamma::CuPtr{Float32}; beta::CuPtr{Float32}; eps::Cfloat; eps_mode::Cint; end
+struct LinAdd;  a::CuPtr{Float32}; idx::CuPtr{Int32}; lda::Cint; end
+struct LinArgs
+    R::Int64; Nout::Cint; ldw::Cint; nsrc::Cint
+    src::NTuple{3,LinSrc}
+    bias::CuPtr{Float32}
+    nadd::Cint; add::NTuple{4,LinAdd}
+    relu::Cint
+    out::CuPtr{Float32}; ldo::Cint
+end
+op_linear(a::LinArgs) = check(ccall((:gnb_op_linear, LIB), Cint, (Ptr{Cvoid}, Ref{LinArgs}), ctx(), Ref(a)))
+op_segsum!(out, x, ptr, S; perm=CU_NULL) = check(ccall((:gnb_op_segsum, LIB), Cint,
+    (Ptr{Cvoid}, CuPtr{Float32}, Cint, CuPtr{Int32}, Int64, CuPtr{Int32}, CuPtr{Float32}), ctx(), pointer(x), size(x, 1), pointer(ptr), S, perm, pointer(out)))
+op_layernorm!(y, x, gamma, beta, eps, mode) = check(ccall((:gnb_op_layernorm, LIB), Cint,
+    (Ptr{Cvoid}, CuPtr{Float32}, Int64, Cint, CuPtr{Float32}, CuPtr{Float32}, Cfloat, Cint, CuPtr{Float32}),
+    ctx(), pointer(x), size(x, 2), size(x, 1), pointer(gamma), pointer(beta), eps, mode, pointer(y)))
+op_layernorm_bwd!(dx, gxhat, x, g, gamma, eps, mode) = check(ccall((:gnb_op_layernorm_bwd, LIB), Cint,
+    (Ptr{Cvoid}, CuPtr{Float32}, CuPtr{Float32}, Int64, Cint, CuPtr{Float32}, Cfloat, Cint, CuPtr{Float32}, CuPtr{Float32}),
+    ctx(), pointer(x), pointer(g), size(x, 2), size(x, 1), pointer(gamma), eps, mode, pointer(dx), pointer(gxhat)))
+op_wgrad!(dW, ldw, X, dY; idx=CU_NULL) = check(ccall((:gnb_op_wgrad, LIB), Cint,
+    (Ptr{Cvoid}, CuPtr{Float32}, Cint, Cint, CuPtr{Int32}, CuPtr{Float32}, Cint, Cint, Int64, CuPtr{Float32}, Cint),
+    ctx(), pointer(X), size(X, 1), size(X, 1), idx, pointer(dY), size(dY, 1), size(dY, 1), size(dY, 2), dW, ldw))
+op_colsum!(out, X) = check(ccall((:gnb_op_colsum, LIB), Cint, (Ptr{Cvoid}, CuPtr{Float32}, Cint, Cint, Int64, CuPtr{Float32}),
+    ctx(), pointer(X), size(X, 1), size(X, 1), size(X, 2), out))
+op_relu_mask!(t, h) = check(ccall((:gnb_op_relu_mask, LIB), Cint, (Ptr{Cvoid}, CuPtr{Float32}, CuPtr{Float32}, Int64), ctx(), pointer(t), pointer(h), length(t)))
+op_gather_add!(out, a, b1, idx1, b2, idx2) = check(ccall((:gnb_op_gather_add, LIB), Cint,
+    (Ptr{Cvoid}, CuPtr{Float32}, CuPtr{Float32}, CuPtr{Float32}, CuPtr{Int32}, CuPtr{Float32}, CuPtr{Int32}, Int64, Cint),
+    ctx(), pointer(out), a, b1, idx1, b2, idx2, size(out, 2), size(out, 1)))
+op_transpose!(out, W, rows, cols, ld) = check(ccall((:gnb_op_transpose, LIB), Cint, (Ptr{Cvoid}, CuPtr{Float32}, Cint, Cint, Cint, CuPtr{Float32}),
+    ctx(), W, rows, cols, ld, pointer(out)))
+op_adamw!(p, g, m, v, step; lr=1f-3, beta1=0.9f0, beta2=0.999f0, eps=1f-8, weight_decay=0f0) = check(ccall((:gnb_op_adamw, LIB), Cint,
+    (Ptr{Cvoid}, CuPtr{Float32}, CuPtr{Float32}, CuPtr{Float32}, CuPtr{Float32}, Int64, Cfloat, Cfloat, Cfloat, Cfloat, Cfloat, Cint),
+    ctx(), pointer(p), pointer(g), pointer(m), pointer(v), length(p), lr, beta1, beta2, eps, weight_decay, step))
+
 # ---------------------------------------------------------------- edge collapsing (src/gngraphbatch.jl:56-111)
 function collapsef(t::NamedTuple)
     g = t.graphs
