@@ -259,6 +259,8 @@ def extra_legs(gn, args, T, rank, world, local_rank, peaks):
         torch.cuda.set_device(local_rank)
         out["cfg5_train_step"] = train_leg(torch, gn, W, T.dist, world, 256)
         torch.cuda.empty_cache()
+        out["cfg5_train_step_bf16"] = train_leg(torch, gn, W, T.dist, world, 256, precision="bf16")
+        torch.cuda.empty_cache()
     except Exception as e:      # noqa: BLE001
         out["cfg5_train_step"] = {"error": repr(e)[:300]}
     if rank != 0:
@@ -327,7 +329,7 @@ def extra_legs(gn, args, T, rank, world, local_rank, peaks):
     return out
 
 
-def train_leg(torch, gn, W, dist, world, graphs, steps=3, lr=5e-6):
+def train_leg(torch, gn, W, dist, world, graphs, steps=3, lr=5e-6, precision="fp32"):
     """Config 5's training step (BASELINE configs[4]: hidden 256, gradient all-reduce) on the fp32 path, at a bounded number of
     graphs per GPU: forward with kept activations + cross-entropy on node and edge outputs + backward + all-reduce of the flat
     gradient buffer (NCCL) + AdamW (graphnets.jl_b200/train.py; gradients checked against torch float64 autograd in
@@ -335,7 +337,7 @@ def train_leg(torch, gn, W, dist, world, graphs, steps=3, lr=5e-6):
     rank_ = dist.get_rank() if (dist is not None and world > 1) else 0
     adj, ef, nf = synth("cfg5", graphs, 77 + rank_)      # every rank its own shard (weak scaling); weights replicated
     x = gn.batch_compact(adj, ef, nf, device=torch.cuda.current_device())
-    tr = gn.Trainer(W.model_params("cfg5"), engine=x.graphs.engine)
+    tr = gn.Trainer(W.model_params("cfg5"), engine=x.graphs.engine, precision=precision)
     dev = tr.eng.torch_device
     g = x.graphs
     rng = np.random.default_rng(5)
@@ -367,8 +369,9 @@ def train_leg(torch, gn, W, dist, world, graphs, steps=3, lr=5e-6):
         ms = float(t[0])
     return {"ms_per_step": ms, "graphs_per_gpu": graphs, "edges_per_gpu": int(g.E), "edges_per_sec": world * g.E / (ms * 1e-3),
             "parameters": int(tr.params.numel()), "allreduce_bytes_per_step": int(tr.params.numel()) * 4 if world > 1 else 0,
-            "world": world, "precision": "fp32", "loss_first": l0, "loss_last": float(l.cpu()), "steps": steps,
-            "workload": "cfg5 training step: enc -> 4x GNCore(256) -> dec, forward + cross-entropy + backward + gradient all-reduce + AdamW, fp32 CUDA-core path"}
+            "world": world, "precision": precision, "loss_first": l0, "loss_last": float(l.cpu()), "steps": steps,
+            "workload": "cfg5 training step: enc -> 4x GNCore(256) -> dec, forward + cross-entropy + backward + gradient all-reduce + AdamW; " +
+                        ("fp32 CUDA-core path" if precision == "fp32" else "GEMMs with bf16 operands on the tensor cores (k_tc_lin), weight gradients / LayerNorm / optimiser fp32")}
 
 
 def cuda_graph_leg(torch, T1, model, x, prec, steps):

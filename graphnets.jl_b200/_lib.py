@@ -91,7 +91,7 @@ class LinAdd(C.Structure):
 
 class LinArgs(C.Structure):
     _fields_ = [("R", C.c_int64), ("Nout", C.c_int), ("ldw", C.c_int), ("nsrc", C.c_int), ("src", LinSrc * 3), ("bias", C.c_void_p),
-                ("nadd", C.c_int), ("add", LinAdd * 4), ("relu", C.c_int), ("out", C.c_void_p), ("ldo", C.c_int)]
+                ("nadd", C.c_int), ("add", LinAdd * 4), ("relu", C.c_int), ("out", C.c_void_p), ("ldo", C.c_int), ("precision", C.c_int)]
 
 
 _vp, _i, _i64, _f = C.c_void_p, C.c_int, C.c_int64, C.c_float

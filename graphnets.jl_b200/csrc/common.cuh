@@ -74,6 +74,11 @@ struct gnb_ctx {
   bool profiling = false;
   void* train_ws = nullptr;      // scratch of the two-stage reductions of the training operators (train.cu), grown on demand
   size_t train_ws_bytes = 0;
+  // training: weights change every step, so the tensor-core linear layer packs its bf16 weight slabs per call into this
+  // stream-ordered scratch instead of the per-model cache (tc_gemm.cu::get_pack)
+  bool tc_lin_nocache = false;
+  void* pack_ws = nullptr;
+  size_t pack_ws_bytes = 0;
   std::vector<FwdGraph> fwd_graphs;
   uint64_t fwd_tick = 0;
   // the legacy default stream cannot be captured: forwards bound to it are captured / replayed on this side stream, forked from

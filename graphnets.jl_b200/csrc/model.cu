@@ -130,6 +130,7 @@ extern "C" int gnb_ctx_destroy(gnb_ctx* c) {
   if (c->h_abort) cudaFreeHost(c->h_abort);
   for (auto& fg : c->fwd_graphs) if (fg.exec) cudaGraphExecDestroy(fg.exec);
   if (c->train_ws) cudaFree(c->train_ws);
+  if (c->pack_ws) cudaFree(c->pack_ws);
   if (c->gstream) cudaStreamDestroy(c->gstream);
   if (c->g_fork) cudaEventDestroy(c->g_fork);
   if (c->g_join) cudaEventDestroy(c->g_join);

@@ -852,6 +852,25 @@ __global__ void __launch_bounds__(F_THREADS, 1) k_tc_ffn(const FfnArgs a) {
 
 // packed bf16 weight slabs of one Dense, built on first use and cached per (model, weight block, group size)
 static int get_pack(gnb_ctx* ctx, const PackKey& key, const PackSrc& ps, int ldw, int K, int Nout, int NG, const __nv_bfloat16** out) {
+  if (ctx->tc_lin_nocache) {
+    // per-call pack (training step): the slabs live in a grow-only scratch of the context; the next call overwrites them in stream
+    // order, after the GEMM that reads them
+    const size_t bytes = (size_t)K * Nout * sizeof(__nv_bfloat16);
+    if (ctx->pack_ws_bytes < bytes) {
+      if (ctx->pack_ws) { cudaStreamSynchronize(ctx->stream); cudaFree(ctx->pack_ws); ctx->pack_ws = nullptr; ctx->pack_ws_bytes = 0; }
+      if (cudaMalloc(&ctx->pack_ws, bytes) != cudaSuccess) {
+        cudaGetLastError();
+        gnb_set_error("tc_gemm: cudaMalloc(%zu) for the per-call weight pack failed", bytes);
+        return GNB_ERR_OOM;
+      }
+      ctx->pack_ws_bytes = bytes;
+    }
+    k_pack_lin<<<(unsigned)ceil_div((int64_t)K * Nout, 256), 256, 0, ctx->stream>>>(ps, ldw, K / 64, NG, Nout / 128 / NG, (__nv_bfloat16*)ctx->pack_ws);
+    GNB_CUDA(cudaGetLastError());
+    ctx->launches++;
+    *out = (const __nv_bfloat16*)ctx->pack_ws;
+    return GNB_OK;
+  }
   if (!ctx->lin_cache) ctx->lin_cache = new PackCache();
   PackCache* cache = static_cast<PackCache*>(ctx->lin_cache);
   std::lock_guard<std::mutex> lk(cache->mu);

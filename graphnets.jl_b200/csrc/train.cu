@@ -10,6 +10,7 @@
 //   * relu mask, gather-add, transpose, AdamW                                                                  small element-wise kernels
 // host-side orchestration: graphnets.jl_b200/train.py; oracle: torch float64 autograd of oracle/gn_oracle.py's formulation.
 #include "kernels.cuh"
+#include "tc_gemm.cuh"
 #include <stdlib.h>
 
 namespace {
@@ -254,6 +255,13 @@ extern "C" int gnb_op_linear(gnb_ctx* ctx, const gnb_lin_args* p) {
     a.src[s].gamma = p->src[s].gamma; a.src[s].beta = p->src[s].beta; a.src[s].eps = p->src[s].eps; a.src[s].eps_mode = p->src[s].eps_mode;
   }
   for (int j = 0; j < p->nadd; j++) { a.add[j].a = p->add[j].a; a.add[j].idx = p->add[j].idx; a.add[j].lda = p->add[j].lda; }
+  if ((p->precision == GNB_PREC_BF16 || p->precision == GNB_PREC_AUTO) && tc_lin_supported(a)) {
+    // bf16 operands / fp32 accumulation on the tensor cores (csrc/tc_gemm.cu), weights packed per call (they change every step)
+    ctx->tc_lin_nocache = true;
+    const int rc = launch_linear_tc(ctx, a);
+    ctx->tc_lin_nocache = false;
+    return rc;
+  }
   return launch_linear_fp32(ctx, a);
 }
 extern "C" int gnb_op_segsum(gnb_ctx* ctx, const float* x, int D, const int32_t* ptr, int64_t S, const int32_t* perm, float* out) {

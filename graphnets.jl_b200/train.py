@@ -27,8 +27,9 @@ _P = lambda t: None if t is None else C.c_void_p(t.data_ptr())
 class _Ops:
     """ctypes wrappers of the gnb_op_* entry points on torch device tensors (fp32, contiguous)."""
 
-    def __init__(self, eng):
+    def __init__(self, eng, precision="fp32"):
         self.eng, self.ctx, self.dev = eng, eng.ctx, eng.torch_device
+        self.prec = _lib.PRECISIONS[precision]
 
     def empty(self, *shape):
         return torch.empty(*shape, dtype=torch.float32, device=self.dev)
@@ -50,7 +51,7 @@ class _Ops:
         a.nadd = len(adds)
         for j, (t, idx) in enumerate(adds):
             a.add[j].a, a.add[j].idx, a.add[j].lda = t.data_ptr(), (None if idx is None else idx.data_ptr()), t.stride(0)
-        a.relu, a.out, a.ldo = int(relu), out.data_ptr(), out.stride(0)
+        a.relu, a.out, a.ldo, a.precision = int(relu), out.data_ptr(), out.stride(0), self.prec
         check(lib.gnb_op_linear(self.ctx, C.byref(a)))
         return out
 
@@ -127,10 +128,13 @@ class _Index:
 
 
 class Trainer:
-    def __init__(self, layers, eps_mode=0, engine=None):
+    def __init__(self, layers, eps_mode=0, engine=None, precision="fp32"):
+        """precision: "fp32" (default: gradients to 2e-4 of float64 autograd) or "bf16" / "auto": every GEMM of the step with
+        enough rows and tensor-core friendly widths (forward, recomputation, dX = dY W^T) runs with bf16 operands and fp32
+        accumulation on the generic tcgen05 linear kernel; weight gradients, LayerNorm, reductions and the optimiser stay fp32."""
         from .engine import get_engine
         self.eng = engine or get_engine()
-        self.ops = _Ops(self.eng)
+        self.ops = _Ops(self.eng, precision)
         self.eps_mode = int(eps_mode)
         # ---- flat parameter buffer; every weight in the ABI layout [in][out] (== Flux (out, in) column-major)
         self.spec, chunks, off = [], [], 0

@@ -187,6 +187,8 @@ typedef struct {
   int nadd; gnb_lin_add add[4];
   int relu;
   float* out; int ldo;
+  int precision;                       /* GNB_PREC_FP32 | GNB_PREC_BF16 / GNB_PREC_AUTO: bf16 operands on the tensor cores where the shape allows
+                                          (rows >= 256, widths multiples of 64 / 128), fp32 accumulation */
 } gnb_lin_args;
 int gnb_op_linear(gnb_ctx*, const gnb_lin_args*);      /* the forward's fused linear kernel (csrc/fp32.cu) */
 /* out[s] = sum over p in [ptr[s], ptr[s+1]) of x[perm ? perm[p] : p], ascending p */

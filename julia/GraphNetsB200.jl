@@ -333,6 +333,7 @@ struct LinArgs
     nadd::Cint; add::NTuple{4,LinAdd}
     relu::Cint
     out::CuPtr{Float32}; ldo::Cint
+    precision::Cint
 end
 op_linear(a::LinArgs) = check(ccall((:gnb_op_linear, LIB), Cint, (Ptr{Cvoid}, Ref{LinArgs}), ctx(), Ref(a)))
 op_segsum!(out, x, ptr, S; perm=CU_NULL) = check(ccall((:gnb_op_segsum, LIB), Cint,

@@ -136,3 +136,50 @@ def test_cross_entropy_gradient(gn):
     ref.backward()
     assert abs(float(loss.cpu()) - float(ref)) <= 1e-5 * abs(float(ref))
     assert _rel(dl.cpu().numpy().astype(np.float64), xt.grad.numpy()) <= 1e-5
+
+
+def test_bf16_gemm_training_step(gn):
+    """Trainer(precision="bf16"): the GEMMs of the step with >= 256 rows and 128-multiple widths run with bf16 operands on the
+    tensor cores (k_tc_lin, weights packed per call); gradients stay within bf16-operand distance of float64 autograd."""
+    rng = np.random.default_rng(9)
+    dims = (128, 128, 128)
+    layers = [("block", W.block_params(rng, (10, 5, 0), dims)), ("core", W.core_params(rng, dims)), ("block", W.block_params(rng, dims, (3, 4, 5)))]
+    adjs = [(rng.random((16, 16)) < 0.4).astype(np.uint8) for _ in range(40)]
+    ef = [rng.random((10, int(a.sum())), dtype=np.float32) for a in adjs]
+    nf = [rng.random((5, 16), dtype=np.float32) for a in adjs]
+    w = dict(mode="vector", graphs=adjs, ef=ef, nf=nf, gf=None)
+    x = gn.batch(W.as_batch_input(w))
+    tr = gn.Trainer(layers, precision="bf16")
+    eng = tr.eng
+    eng.set_profiling(True); eng.read_profile()
+    y = tr.forward(x)
+    g = O.lower(adjs)
+    cef, cnf, cgf = W.compact_inputs(w)
+    cot = [rng.standard_normal(tuple(t.shape)).astype(np.float32) for t in y]
+    outs, pgrads, igrads = G.forward_and_grads(layers, g, cef, cnf, cgf, cot)
+    dev = eng.torch_device
+    tr.backward(*[torch.from_numpy(c).to(dev) for c in cot])
+    prof = eng.read_profile()
+    eng.set_profiling(False)
+    assert prof.get("tc_linear", {}).get("launches", 0) >= 10, list(prof)      # forward + backward GEMMs on the tensor cores
+    for a, b in zip(y, outs):
+        assert _rel(a.cpu().numpy().astype(np.float64), b) <= 1e-2
+    worst = 0.0
+    got = [p for _, p in tr.param_grads()]
+    ref = [p for _, p in pgrads]
+
+    def walk(a, b, path):
+        nonlocal worst
+        if isinstance(b, dict):
+            for k, v in b.items():
+                if k not in ("din", "dout", "dims", "eps"):
+                    walk(a[k], v, path + "/" + k)
+        elif isinstance(b, list):
+            for i, v in enumerate(b):
+                walk(a[i], v, path + "/%d" % i)
+        elif isinstance(b, np.ndarray) and b.size:
+            err = _rel(np.asarray(a, np.float64), b)
+            assert err <= 3e-2, "%s: bf16 gradient rel err %.3e" % (path, err)
+            worst = max(worst, err)
+    walk(got, ref, "params")
+    assert worst > 1e-5      # (it really ran in reduced precision)
