@@ -99,7 +99,7 @@ SIGNATURES["gnb_op_linear"] = (C.c_int, [_vp, C.POINTER(LinArgs)])
 SIGNATURES["gnb_op_segsum"] = (C.c_int, [_vp, _vp, _i, _vp, _i64, _vp, _vp])
 SIGNATURES["gnb_op_layernorm"] = (C.c_int, [_vp, _vp, _i64, _i, _vp, _vp, _f, _i, _vp])
 SIGNATURES["gnb_op_layernorm_bwd"] = (C.c_int, [_vp, _vp, _vp, _i64, _i, _vp, _f, _i, _vp, _vp])
-SIGNATURES["gnb_op_wgrad"] = (C.c_int, [_vp, _vp, _i, _i, _vp, _vp, _i, _i, _i64, _vp, _i])
+SIGNATURES["gnb_op_wgrad"] = (C.c_int, [_vp, _vp, _i, _i, _vp, _vp, _i, _i, _i64, _vp, _i, _i])
 SIGNATURES["gnb_op_colsum"] = (C.c_int, [_vp, _vp, _i, _i, _i64, _vp])
 SIGNATURES["gnb_op_relu_mask"] = (C.c_int, [_vp, _vp, _vp, _i64])
 SIGNATURES["gnb_op_gather_add"] = (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i])

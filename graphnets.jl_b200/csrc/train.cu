@@ -11,6 +11,7 @@
 // host-side orchestration: graphnets.jl_b200/train.py; oracle: torch float64 autograd of oracle/gn_oracle.py's formulation.
 #include "kernels.cuh"
 #include "tc_gemm.cuh"
+#include "tc_ptx.cuh"
 #include <stdlib.h>
 
 namespace {
@@ -225,6 +226,122 @@ __global__ void k_adamw(float* __restrict__ p, const float* __restrict__ g, floa
   p[i] = p[i] - lr * ((mi / c1) / (sqrtf(vi / c2) + eps) + wd * p[i]);
 }
 
+// ---- dW = X^T dY on the tensor cores (bf16 operands, fp32 accumulation in TMEM): one 128 x 128 output tile per CTA, the
+// reduction (rows) split over grid.z chunks; per 64-row slab eight producer warps transpose X[rows][k0 .. k0+128) and
+// dY[rows][n0 .. n0+128) into K-major 128B-swizzled bf16 operand slabs (lane = operand row m, eight consecutive reduction rows
+// -> one 16 B chunk: the global loads of a warp are 128 B coalesced, the shared stores conflict-free), warp 8 issues 4 UMMAs per
+// slab through a 3-stage ring, warps 0-3 drain the accumulator into the partial-sum buffer (summed in a fixed order afterwards).
+constexpr int TW_STAGES = 3, TW_SLAB = 16384;
+constexpr int TW_SMEM = TW_STAGES * 2 * TW_SLAB + 16 * 8 + 16 + 1024;
+constexpr int TW_THREADS = 9 * 32;
+__global__ void __launch_bounds__(TW_THREADS, 2) k_tc_wgrad(const float* __restrict__ X, int ldx, int K, const int32_t* __restrict__ idx,
+                                                           const float* __restrict__ dY, int ldy, int N, int64_t R, int64_t rows_per_chunk,
+                                                           float* __restrict__ part, WatchArgs wd) {
+  using namespace tcx;
+  extern __shared__ uint8_t tw_raw[];
+  const uint32_t raw = smem_u32(tw_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* sm = tw_raw + (base - raw);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sm + TW_STAGES * 2 * TW_SLAB);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
+  const uint32_t bar0 = smem_u32(bars);
+  auto BAR = [&](int i) { return bar0 + 8u * (uint32_t)i; };      // FULL[s] = s, EMPTY[s] = 3 + s, DONE = 6
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  bool wd_dead = false;
+  if (tid == 0) {
+    for (int s2 = 0; s2 < TW_STAGES; s2++) { mbar_init(BAR(s2), 8); mbar_init(BAR(3 + s2), 1); }
+    mbar_init(BAR(6), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 8) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(128u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const int k0 = blockIdx.x * 128, n0 = blockIdx.y * 128;
+  const int64_t r_begin = (int64_t)blockIdx.z * rows_per_chunk;
+  const int64_t r_end = r_begin + rows_per_chunk < R ? r_begin + rows_per_chunk : R;
+  const int nslab = r_end > r_begin ? (int)((r_end - r_begin + 63) / 64) : 0;
+  if (warp < 8) {
+    // ---- producers: warp w builds chunks (8 reduction rows each) w of both slabs: items (operand, m group of 32) x 4
+    for (int sl = 0; sl < nslab && !wd_dead; sl++) {
+      const int st = sl % TW_STAGES;
+      mbar_wait_w(BAR(3 + st), ((sl / TW_STAGES) & 1) ^ 1, wd_dead, wd);
+      uint8_t* A = sm + st * 2 * TW_SLAB;
+      uint8_t* Bm = A + TW_SLAB;
+      const int64_t rb = r_begin + (int64_t)sl * 64 + 8 * warp;      // this warp's 8 reduction rows (chunk `warp` of the slab)
+      int64_t xr[8];
+#pragma unroll
+      for (int j = 0; j < 8; j++) {
+        const int64_t r = rb + j;
+        xr[j] = r < r_end ? (idx ? (int64_t)__ldg(idx + r) : r) : -1;
+      }
+#pragma unroll
+      for (int mg = 0; mg < 4; mg++) {
+        const int m = 32 * mg + lane;      // operand row: column k0 + m of X, column n0 + m of dY
+        float xv[8], yv[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+          const bool ok = xr[j] >= 0;
+          xv[j] = (ok && k0 + m < K) ? __ldg(X + (size_t)xr[j] * ldx + k0 + m) : 0.f;
+          yv[j] = (ok && n0 + m < N) ? __ldg(dY + (size_t)(rb + j) * ldy + n0 + m) : 0.f;
+        }
+        const uint32_t off = (uint32_t)(m * 128 + ((warp ^ (m & 7)) << 4));      // sw_off(m, 8 warp): chunk `warp` of row m
+        *reinterpret_cast<uint4*>(A + off) = make_uint4(pack_bf16(xv[0], xv[1]), pack_bf16(xv[2], xv[3]), pack_bf16(xv[4], xv[5]), pack_bf16(xv[6], xv[7]));
+        *reinterpret_cast<uint4*>(Bm + off) = make_uint4(pack_bf16(yv[0], yv[1]), pack_bf16(yv[2], yv[3]), pack_bf16(yv[4], yv[5]), pack_bf16(yv[6], yv[7]));
+      }
+      fence_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(BAR(st));
+    }
+    // ---- epilogue (warps 0-3, TMEM lane quadrant = warp): accumulator -> part[chunk][k][n]
+    if (warp < 4 && nslab > 0) {
+      mbar_wait_w(BAR(6), 0, wd_dead, wd);
+      tc_fence_after();
+      const int m = 32 * warp + lane;
+      const uint32_t lane_base = ((uint32_t)(32 * warp)) << 16;
+#pragma unroll 1
+      for (int c = 0; c < 4; c++) {
+        uint32_t v[32];
+        TC_LD32(tmem + lane_base + 32 * c, v);
+        tc_wait_ld();
+        if (k0 + m < K) {
+          float* o = part + ((size_t)blockIdx.z * K + k0 + m) * N + n0 + 32 * c;
+#pragma unroll
+          for (int j = 0; j < 32; j++)
+            if (n0 + 32 * c + j < N) o[j] = __uint_as_float(v[j]);
+        }
+      }
+    } else if (warp < 4) {      // empty chunk: zeros
+      const int m = 32 * warp + lane;
+      if (k0 + m < K)
+        for (int j = 0; j < 128; j++)
+          if (n0 + j < N) part[((size_t)blockIdx.z * K + k0 + m) * N + n0 + j] = 0.f;
+    }
+  } else {
+    // ---- MMA issuer
+    for (int sl = 0; sl < nslab && !wd_dead; sl++) {
+      const int st = sl % TW_STAGES;
+      mbar_wait_w(BAR(st), (sl / TW_STAGES) & 1, wd_dead, wd);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint64_t ad = umma_desc(base + st * 2 * TW_SLAB), bd = umma_desc(base + st * 2 * TW_SLAB + TW_SLAB);
+#pragma unroll
+        for (int k4 = 0; k4 < 4; k4++) mma_ss(tmem, ad + 2 * k4, bd + 2 * k4, IDESC, (sl > 0 || k4 > 0) ? 1u : 0u);
+        tc_commit(BAR(3 + st));
+        if (sl == nslab - 1) tc_commit(BAR(6));
+      }
+      __syncwarp();
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 8) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(128u) : "memory");
+}
+
 int chunks_for(int64_t R) {
   int64_t c = (R + 2047) / 2048;
   return (int)(c < 1 ? 1 : (c > 256 ? 256 : c));
@@ -295,10 +412,33 @@ extern "C" int gnb_op_layernorm_bwd(gnb_ctx* ctx, const float* x, const float* g
   return GNB_OK;
 }
 extern "C" int gnb_op_wgrad(gnb_ctx* ctx, const float* X, int ldx, int K, const int32_t* idx, const float* dY, int ldy, int N, int64_t R,
-                            float* dW, int ldw) {
+                            float* dW, int ldw, int precision) {
   GNB_CHECK(ctx && X && dY && dW && K > 0 && N > 0, "gnb_op_wgrad: bad arguments");
   if (R <= 0) return GNB_OK;
   GNB_CUDA(cudaSetDevice(ctx->device));
+  if ((precision == GNB_PREC_BF16 || precision == GNB_PREC_AUTO) && R >= 4096 && K >= 64 && N >= 64) {
+    // tensor cores: enough row chunks to fill the GPU with (K / 128) x (N / 128) x chunks CTAs, two CTAs per SM
+    const int tiles = ceil_div(K, 128) * ceil_div(N, 128);
+    int64_t chunks = (2 * (int64_t)ctx->sm_count + tiles - 1) / tiles;
+    const int64_t max_chunks = (R + 511) / 512;      // at least 512 rows (8 slabs) per chunk
+    chunks = chunks < 1 ? 1 : (chunks > max_chunks ? max_chunks : chunks);
+    int64_t rpc = (R + chunks - 1) / chunks;
+    rpc = (rpc + 63) / 64 * 64;
+    chunks = (R + rpc - 1) / rpc;
+    float* part = nullptr;
+    GNB_TRY(train_ws(ctx, (size_t)chunks * K * N * sizeof(float), &part));
+    if (ctx_first(ctx, ONCE_TC_WGRAD)) GNB_CUDA(cudaFuncSetAttribute(k_tc_wgrad, cudaFuncAttributeMaxDynamicSharedMemorySize, TW_SMEM));
+    {
+      Launch L(ctx, "train_wgrad_tc", 4.0 * R * (K + N), 2.0 * R * K * N);
+      k_tc_wgrad<<<dim3((unsigned)ceil_div(K, 128), (unsigned)ceil_div(N, 128), (unsigned)chunks), TW_THREADS, TW_SMEM, ctx->stream>>>(
+          X, ldx, K, idx, dY, ldy, N, R, rpc, part, ctx_watch(ctx));
+      GNB_CUDA(cudaGetLastError());
+    }
+    Launch L2(ctx, "train_reduce");
+    k_reduce_parts<<<ceil_div((int64_t)K * N, 256), 256, 0, ctx->stream>>>(part, (int)chunks, K, N, dW, ldw);
+    GNB_CUDA(cudaGetLastError());
+    return GNB_OK;
+  }
   const int chunks = chunks_for(R);
   const int64_t rpc = (R + chunks - 1) / chunks;
   float* part = nullptr;

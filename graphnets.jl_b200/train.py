@@ -74,7 +74,7 @@ class _Ops:
         """dW[k][n] += sum_r X[idx[r]][k] dY[r][n]   (dW: pointer view into the flat gradient buffer, rows of ldw floats)"""
         if X is None or X.shape[1] == 0 or dY.shape[1] == 0:
             return
-        check(lib.gnb_op_wgrad(self.ctx, _P(X), X.stride(0), X.shape[1], _P(idx), _P(dY), dY.stride(0), dY.shape[1], dY.shape[0], _P(dW), ldw))
+        check(lib.gnb_op_wgrad(self.ctx, _P(X), X.stride(0), X.shape[1], _P(idx), _P(dY), dY.stride(0), dY.shape[1], dY.shape[0], _P(dW), ldw, self.prec))
 
     def colsum(self, X, out):
         check(lib.gnb_op_colsum(self.ctx, _P(X), X.stride(0), X.shape[1], X.shape[0], _P(out)))

@@ -198,7 +198,9 @@ int gnb_op_layernorm(gnb_ctx*, const float* x, int64_t R, int D, const float* ga
 int gnb_op_layernorm_bwd(gnb_ctx*, const float* x, const float* g, int64_t R, int D, const float* gamma, float eps, int eps_mode,
                          float* dx, float* gxhat);
 /* dW[k][n] += sum_r X[idx ? idx[r] : r][k] * dY[r][n]      (dW: [K][ldw], the layout of a Flux Dense.weight block) */
-int gnb_op_wgrad(gnb_ctx*, const float* X, int ldx, int K, const int32_t* idx, const float* dY, int ldy, int N, int64_t R, float* dW, int ldw);
+/* precision GNB_PREC_BF16 / AUTO: bf16 operands on the tensor cores (split over row chunks, fp32 accumulation) when R >= 4096 */
+int gnb_op_wgrad(gnb_ctx*, const float* X, int ldx, int K, const int32_t* idx, const float* dY, int ldy, int N, int64_t R, float* dW, int ldw,
+                 int precision);
 int gnb_op_colsum(gnb_ctx*, const float* X, int ldx, int D, int64_t R, float* out /* += */);
 int gnb_op_relu_mask(gnb_ctx*, float* t, const float* h, int64_t n);      /* t[i] = h[i] > 0 ? t[i] : 0 */
 /* out[r] = a[r] + b1[idx1 ? idx1[r] : r] + b2[idx2 ? idx2[r] : r]   (a, b1, b2 optional; rows of width D) */

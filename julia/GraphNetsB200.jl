@@ -344,9 +344,9 @@ op_layernorm!(y, x, gamma, beta, eps, mode) = check(ccall((:gnb_op_layernorm, LI
 op_layernorm_bwd!(dx, gxhat, x, g, gamma, eps, mode) = check(ccall((:gnb_op_layernorm_bwd, LIB), Cint,
     (Ptr{Cvoid}, CuPtr{Float32}, CuPtr{Float32}, Int64, Cint, CuPtr{Float32}, Cfloat, Cint, CuPtr{Float32}, CuPtr{Float32}),
     ctx(), pointer(x), pointer(g), size(x, 2), size(x, 1), pointer(gamma), eps, mode, pointer(dx), pointer(gxhat)))
-op_wgrad!(dW, ldw, X, dY; idx=CU_NULL) = check(ccall((:gnb_op_wgrad, LIB), Cint,
-    (Ptr{Cvoid}, CuPtr{Float32}, Cint, Cint, CuPtr{Int32}, CuPtr{Float32}, Cint, Cint, Int64, CuPtr{Float32}, Cint),
-    ctx(), pointer(X), size(X, 1), size(X, 1), idx, pointer(dY), size(dY, 1), size(dY, 1), size(dY, 2), dW, ldw))
+op_wgrad!(dW, ldw, X, dY; idx=CU_NULL, precision=0) = check(ccall((:gnb_op_wgrad, LIB), Cint,
+    (Ptr{Cvoid}, CuPtr{Float32}, Cint, Cint, CuPtr{Int32}, CuPtr{Float32}, Cint, Cint, Int64, CuPtr{Float32}, Cint, Cint),
+    ctx(), pointer(X), size(X, 1), size(X, 1), idx, pointer(dY), size(dY, 1), size(dY, 1), size(dY, 2), dW, ldw, precision))
 op_colsum!(out, X) = check(ccall((:gnb_op_colsum, LIB), Cint, (Ptr{Cvoid}, CuPtr{Float32}, Cint, Cint, Int64, CuPtr{Float32}),
     ctx(), pointer(X), size(X, 1), size(X, 1), size(X, 2), out))
 op_relu_mask!(t, h) = check(ccall((:gnb_op_relu_mask, LIB), Cint, (Ptr{Cvoid}, CuPtr{Float32}, CuPtr{Float32}, Int64), ctx(), pointer(t), pointer(h), length(t)))

@@ -144,7 +144,7 @@ def test_bf16_gemm_training_step(gn):
     rng = np.random.default_rng(9)
     dims = (128, 128, 128)
     layers = [("block", W.block_params(rng, (10, 5, 0), dims)), ("core", W.core_params(rng, dims)), ("block", W.block_params(rng, dims, (3, 4, 5)))]
-    adjs = [(rng.random((16, 16)) < 0.4).astype(np.uint8) for _ in range(40)]
+    adjs = [(rng.random((16, 16)) < 0.4).astype(np.uint8) for _ in range(64)]      # E ~ 6500 >= 4096: tensor-core wgrad on the edges
     ef = [rng.random((10, int(a.sum())), dtype=np.float32) for a in adjs]
     nf = [rng.random((5, 16), dtype=np.float32) for a in adjs]
     w = dict(mode="vector", graphs=adjs, ef=ef, nf=nf, gf=None)
@@ -162,6 +162,7 @@ def test_bf16_gemm_training_step(gn):
     prof = eng.read_profile()
     eng.set_profiling(False)
     assert prof.get("tc_linear", {}).get("launches", 0) >= 10, list(prof)      # forward + backward GEMMs on the tensor cores
+    assert prof.get("train_wgrad_tc", {}).get("launches", 0) >= 3, list(prof)   # edge-row weight gradients on the tensor cores
     for a, b in zip(y, outs):
         assert _rel(a.cpu().numpy().astype(np.float64), b) <= 1e-2
     worst = 0.0
@@ -183,3 +184,30 @@ def test_bf16_gemm_training_step(gn):
             worst = max(worst, err)
     walk(got, ref, "params")
     assert worst > 1e-5      # (it really ran in reduced precision)
+
+
+@pytest.mark.parametrize("R,K,N,gather", [(5000, 200, 136, True), (4096, 128, 128, False), (70001, 64, 320, False)])
+def test_tensor_core_wgrad_operator(gn, R, K, N, gather):
+    """gnb_op_wgrad on the tensor cores (k_tc_wgrad: bf16 operands, fp32 accumulation, split over row chunks) against the exact
+    product of the bf16-rounded operands; ragged K / N tiles, a ragged last slab, gathered rows, accumulation into dW."""
+    import ctypes as C
+    from oracle.gn_oracle import round_bf16
+    rng = np.random.default_rng(R)
+    nx = 3000 if gather else R
+    X = rng.standard_normal((nx, K)).astype(np.float32)
+    dY = rng.standard_normal((R, N)).astype(np.float32)
+    idx = rng.integers(0, nx, R).astype(np.int32) if gather else None
+    dW0 = rng.standard_normal((K, N)).astype(np.float32)
+    eng = gn.get_engine()
+    eng.bind_stream()
+    dev = eng.torch_device
+    tX, tY, tW = (torch.from_numpy(a).to(dev) for a in (X, dY, dW0))
+    tI = None if idx is None else torch.from_numpy(idx).to(dev)
+    P = lambda t: None if t is None else C.c_void_p(t.data_ptr())
+    L = gn.pkg._lib
+    L.check(gn.lib.gnb_op_wgrad(eng.ctx, P(tX), K, K, P(tI), P(tY), N, N, R, P(tW), N, L.PRECISIONS["bf16"]))
+    eng.sync()
+    Xg = X if idx is None else X[idx]
+    ref = dW0.astype(np.float64) + round_bf16(Xg).T @ round_bf16(dY)
+    err = _rel(tW.cpu().numpy().astype(np.float64), ref)
+    assert err <= 2e-5, err
