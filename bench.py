@@ -257,9 +257,10 @@ def extra_legs(gn, args, T, rank, world, local_rank, peaks):
     # ---- config 5's TRAINING step (every rank: the gradient all-reduce is a collective), bounded size
     try:
         torch.cuda.set_device(local_rank)
-        out["cfg5_train_step"] = train_leg(torch, gn, W, T.dist, world, 256)
+        # 1024 graphs per GPU = an eighth of config 5's per-GPU shard (8192): one micro-batch of the step (activations are kept)
+        out["cfg5_train_step"] = train_leg(torch, gn, W, T.dist, world, 1024)
         torch.cuda.empty_cache()
-        out["cfg5_train_step_bf16"] = train_leg(torch, gn, W, T.dist, world, 256, precision="bf16")
+        out["cfg5_train_step_bf16"] = train_leg(torch, gn, W, T.dist, world, 1024, precision="bf16")
         torch.cuda.empty_cache()
     except Exception as e:      # noqa: BLE001
         out["cfg5_train_step"] = {"error": repr(e)[:300]}
