@@ -859,7 +859,8 @@ int launch_edge5(gnb_ctx* ctx, const EdgeArgs& a_in, const char* name, double fl
   const bool dec = a.decW != nullptr, pbf = a.add_bf16 != 0;
   int grid;
   if (cl2) {
-    const int pairs = (a.num_tiles + 1) / 2, max_clusters = ctx->sm_count / 2;
+    static const int cap_env = getenv("GNB_EDGE_MAX_PAIRS") ? atoi(getenv("GNB_EDGE_MAX_PAIRS")) : 0;      // experiment: fewer SMs
+    const int pairs = (a.num_tiles + 1) / 2, max_clusters = (cap_env > 0 && cap_env < ctx->sm_count / 2) ? cap_env : ctx->sm_count / 2;
     grid = 2 * (pairs < max_clusters ? pairs : max_clusters);
   } else {
     grid = a.num_tiles < ctx->sm_count ? a.num_tiles : ctx->sm_count;
