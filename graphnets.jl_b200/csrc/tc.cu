@@ -732,6 +732,8 @@ int tc_core_forward(gnb_ctx* ctx, const gnb_graph* g, const TcCorePack* pk, cons
     a.x = xe; a.y = ye; a.R = E; a.num_tiles = ceil_div(E, TM); a.wpack = pk->w_edge;
     a.bias_pack = pk->bias_e; a.eps = ln1[0].eps; a.eps_mode = ln1[0].eps_mode;
     a.add1 = Psr; a.idx1 = g->edge_src; a.ld1 = 2 * H; a.add2 = Psr + H * psr_es; a.idx2 = g->edge_dst; a.ld2 = 2 * H; a.add_bf16 = psr_bf16;
+    static const bool pf = getenv("GNB_EDGE_PPREFETCH") != nullptr && atoi(getenv("GNB_EDGE_PPREFETCH")) != 0;      // experiment toggle
+    if (pf) { a.pf_row_graph = g->edge_graph; a.pf_graph_ptr = g->graph_node_ptr; }
     a.part = g->edge_part; a.Epart = Epart; a.Gpart = Gpart; a.part_bf16 = part_bf16; a.dbg = g_tc_dbg; a.wd = ctx_watch(ctx);
     a.decW = dec.W4; a.dec_out = dec.partial;      // fused narrow decoder: y_e is not stored (ye may be nullptr)
     // canonical work of the reference's edge update + edge FFN: 24 H^2 flops and

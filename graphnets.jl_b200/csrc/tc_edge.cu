@@ -502,6 +502,21 @@ __global__ void __launch_bounds__(E_THREADS, 1) k_edge5(const __grid_constant__ 
       const uint32_t endmask = __ballot_sync(0xffffffffu, lane < rows && (lane == rows - 1 || nxt != my_pid));
       int pid = __shfl_sync(0xffffffffu, my_pid, 0);
       EDBG(0);
+      if (q == 0 && a.pf_row_graph != nullptr && left > 0) {
+        // the OUT warps gather P_s[src] / P_r'[dst] of this tile two tile periods from now; every sender / receiver lies in the
+        // contiguous node range of the graphs the tile touches: pull that range into L2 now (this warp idles at AEMPTY anyway;
+        // issued from the weight loader warp instead, the dependent index loads delayed the weight ring: profiles/r02_summary.md)
+        const int64_t t0 = (int64_t)tile * TM, tl_ = a.R - t0 < TM ? a.R - t0 : TM;
+        if (lane == 0) {
+          const int g0 = __ldg(a.pf_row_graph + t0), g1 = __ldg(a.pf_row_graph + t0 + tl_ - 1);
+          const int64_t n0 = __ldg(a.pf_graph_ptr + g0), n1 = __ldg(a.pf_graph_ptr + g1 + 1);
+          const int64_t rowb = (int64_t)a.ld1 * (a.add_bf16 ? 2 : 4);
+          int64_t nb = (n1 - n0) * rowb;
+          nb = nb > 131072 ? 131072 : nb;
+          if (nb > 0) bulk_prefetch_l2(reinterpret_cast<const uint8_t*>(a.add1) + (size_t)n0 * rowb, (uint32_t)nb);
+        }
+        __syncwarp();
+      }
       float4 xa[2][4];   // two 4-row steps in flight
       auto issue = [&](int i0) {
 #pragma unroll

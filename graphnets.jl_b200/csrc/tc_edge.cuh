@@ -21,6 +21,9 @@ struct EdgeArgs {
   const void* add1; const int32_t* idx1; int ld1;   // idx1 == nullptr: the row itself
   const void* add2; const int32_t* idx2; int ld2;
   int add_bf16;
+  // optional L2 prefetch of the rows the OUT warps will gather (edges): graph of every row + the graphs' row ranges in add1
+  // (graph_node_ptr); add1 / add2 are then the two halves of ONE row-interleaved matrix (P_s | P_r'), one range covers both
+  const int32_t* pf_row_graph; const int32_t* pf_graph_ptr;
   const int32_t* part;   // partial-row id per edge (32-row blocks, receiver runs)
   float* Epart;          // out [n_parts][128] partial sums of the normalised edge rows
   float* Gpart;          // out [n_parts][128] partial sums of the gathered addends
