@@ -127,7 +127,72 @@ class _Index:
         self.src_perm, self.node_out_ptr32 = t(perm), t(out_ptr)      # t() stores int32
 
 
+def layers_of(model):
+    """The oracle-format parameter list [("block" | "core", params)] of a model built from the layer objects of layers.py
+    (GNBlock, GNCore, GNCoreList / GNSequential): weights as numpy (out, in) arrays, like Flux's Dense.weight."""
+    from .layers import GNBlock, GNCore, GNCoreList
+
+    def blk(b):
+        return dict(din=tuple(b.in_dims), dout=tuple(b.out_dims), We=np.asarray(b.edgefn[0].weight), be=np.asarray(b.edgefn[0].bias),
+                    Wn=np.asarray(b.nodefn[0].weight), bn=np.asarray(b.nodefn[0].bias), Wg=np.asarray(b.graphfn[0].weight), bg=np.asarray(b.graphfn[0].bias))
+
+    def one(m):
+        if isinstance(m, GNBlock):
+            return [("block", blk(m))]
+        if isinstance(m, GNCore):
+            ffn = [dict(W1=np.asarray(ch[0].weight), b1=np.asarray(ch[0].bias), W2=np.asarray(ch[1].weight), b2=np.asarray(ch[1].bias))
+                   for ch in (m.ffwd.eff, m.ffwd.nff, m.ffwd.gff)]
+            ln = lambda g: [dict(gamma=np.asarray(l.scale), beta=np.asarray(l.bias), eps=float(l.eps)) for l in (g.edgeln, g.nodeln, g.graphln)]
+            return [("core", dict(dims=tuple(m.dims), block=blk(m.block), ffn=ffn, ln1=ln(m.gn1), ln2=ln(m.gn2)))]
+        if isinstance(m, GNCoreList):
+            return [l for c in m.list for l in one(c)]
+        raise TypeError("Trainer: unsupported layer %r" % type(m).__name__)
+    return one(model)
+
+
 class Trainer:
+    @classmethod
+    def from_model(cls, model, **kw):
+        """Trainer over the parameters of a GNBlock / GNCore / GNCoreList / GNSequential built with the layer objects; the
+        LayerNorm convention (eps_mode) is taken from the model's first GNCore."""
+        from .layers import GNCore, GNCoreList
+        cores = [c for c in (model.list if isinstance(model, GNCoreList) else [model]) if isinstance(c, GNCore)]
+        kw.setdefault("eps_mode", cores[0].gn1.edgeln.eps_mode if cores else 0)
+        return cls(layers_of(model), **kw)
+
+    def write_back(self, model):
+        """Copies the (trained) parameters back into the layer objects `from_model` was given (and re-syncs their device copies)."""
+        from .layers import GNBlock, GNCore, GNCoreList
+        p = self.params.cpu().numpy()
+        mods = model.list if isinstance(model, GNCoreList) else [model]
+
+        def W(off, rows_in, cols_out):
+            return p[off:off + rows_in * cols_out].reshape(rows_in, cols_out).T.copy()
+
+        def put_block(b, s):
+            (a, bb, c), (pp, q, r) = s["din"], s["dout"]
+            b.edgefn[0].set(W(s["We"], a + 2 * bb + c, pp), p[s["be"]:s["be"] + pp])
+            b.nodefn[0].set(W(s["Wn"], pp + bb + c, q), p[s["bn"]:s["bn"] + q])
+            b.graphfn[0].set(W(s["Wg"], pp + q + c, r), p[s["bg"]:s["bg"] + r])
+        flat = [c for m in mods for c in (m.list if isinstance(m, GNCoreList) else [m])]
+        assert len(flat) == len(self.spec)
+        for m, (kind, s) in zip(flat, self.spec):
+            if kind == "block":
+                assert isinstance(m, GNBlock)
+                put_block(m, s)
+            else:
+                assert isinstance(m, GNCore)
+                put_block(m.block, s["block"])
+                for ch, f, d in zip((m.ffwd.eff, m.ffwd.nff, m.ffwd.gff), s["ffn"], s["dims"]):
+                    ch[0].set(W(f["W1"], d, 4 * d), p[f["b1"]:f["b1"] + 4 * d])
+                    ch[1].set(W(f["W2"], 4 * d, d), p[f["b2"]:f["b2"] + d])
+                for g, key in ((m.gn1, "ln1"), (m.gn2, "ln2")):
+                    for l, ls, d in zip((g.edgeln, g.nodeln, g.graphln), s[key], s["dims"]):
+                        l.set(p[ls["gamma"]:ls["gamma"] + d], p[ls["beta"]:ls["beta"] + d])
+        if hasattr(model, "sync"):
+            model.sync()
+        return model
+
     def __init__(self, layers, eps_mode=0, engine=None, precision="fp32"):
         """precision: "fp32" (default: gradients to 2e-4 of float64 autograd) or "bf16" / "auto": every GEMM of the step with
         enough rows and tensor-core friendly widths (forward, recomputation, dX = dY W^T) runs with bf16 operands and fp32

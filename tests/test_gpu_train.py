@@ -211,3 +211,20 @@ def test_tensor_core_wgrad_operator(gn, R, K, N, gather):
     ref = dW0.astype(np.float64) + round_bf16(Xg).T @ round_bf16(dY)
     err = _rel(tW.cpu().numpy().astype(np.float64), ref)
     assert err <= 2e-5, err
+
+
+def test_trainer_from_model_and_write_back(gn):
+    """Trainer.from_model over layer objects; after a step the parameters written back make the product forward equal the
+    Trainer's own forward (fp32 path, same kernels)."""
+    w = W.make_workload("cfg2", B=8)
+    model = W.to_gn_model(gn, W.model_params("cfg2"))
+    x = gn.batch(W.as_batch_input(w))
+    tr = gn.Trainer.from_model(model)
+    y = tr.forward(x)
+    tr.backward(*y)
+    tr.step(lr=1e-3)
+    tr.write_back(model)
+    y_tr = tr.forward(x)
+    y_model = model(x, precision="fp32")
+    for a, b in zip(y_tr, (y_model.ef, y_model.nf, y_model.gf)):
+        assert _rel(a.cpu().numpy().astype(np.float64), b.compact.cpu().numpy().astype(np.float64)) <= 1e-5

@@ -144,3 +144,29 @@ def test_julia_shim_binds_only_declared_symbols_and_defines_the_reference_export
     for pat in (r"struct GNBlock\s+edgefn; nodefn; graphfn; dropout", r"struct GNCore\s+block; ffwd; gn1; gn2",
                 r"struct GNCoreList\s+list", r"struct GNFeedForward\s+eff; nff; gff", r"struct GNGraphNorm\s+edgeln; nodeln; graphln"):
         assert re.search(pat, code), pat
+
+
+def test_trainer_layer_conversion_roundtrip(gn):
+    """train.layers_of: layer objects -> the oracle-format parameter list the Trainer (and the oracle) consume (no GPU needed)."""
+    import workloads as W
+    from oracle import gn_oracle as O
+    layers = W.model_params("cfg2")
+    model = W.to_gn_model(gn, layers)
+    back = gn.pkg.train.layers_of(model)
+    assert [k for k, _ in back] == [k for k, _ in layers]
+    for (_, a), (_, b) in zip(back, layers):
+        if "We" in a:
+            for k in ("We", "be", "Wn", "bn", "Wg", "bg"):
+                assert np.array_equal(a[k], b[k])
+        else:
+            assert np.array_equal(a["block"]["We"], b["block"]["We"])
+            for i in range(3):
+                for k in ("W1", "b1", "W2", "b2"):
+                    assert np.array_equal(a["ffn"][i][k], b["ffn"][i][k])
+                assert np.array_equal(a["ln1"][i]["gamma"], b["ln1"][i]["gamma"]) and np.array_equal(a["ln2"][i]["beta"], b["ln2"][i]["beta"])
+    # the converted list drives the oracle to the same result as the original one
+    w = W.make_workload("cfg2", B=3)
+    g = O.lower(W.adj_list(w))
+    ef, nf, gf = W.compact_inputs(w)
+    y0, y1 = O.forward_sparse(layers, g, ef, nf, gf), O.forward_sparse(back, g, ef, nf, gf)
+    assert all(np.allclose(p, q, rtol=1e-12, atol=1e-12) for p, q in zip(y0, y1))      # (the weights' memory order differs: BLAS blocking)
