@@ -124,7 +124,7 @@ static inline WatchArgs ctx_watch(const gnb_ctx* c) { return WatchArgs{c->d_abor
 // Returns GNB_ERR_TIMEOUT (and clears the flag) if a kernel watchdog fired; call after the stream has been synchronised.
 int ctx_check_watchdog(gnb_ctx* c);
 
-enum { ONCE_EDGE5 = 0, ONCE_PROJ_LN2, ONCE_PROJ_AGG1, ONCE_PROJ_OTHER, ONCE_TC_LIN, ONCE_TC_FFN, ONCE_TC_FFN384, ONCE_WIDE, ONCE_NARROW2, ONCE_POOL, ONCE_AGG2, ONCE_TC_WGRAD };
+enum { ONCE_EDGE5 = 0, ONCE_PROJ_LN2, ONCE_PROJ_AGG1, ONCE_PROJ_OTHER, ONCE_TC_LIN, ONCE_TC_FFN, ONCE_TC_FFN384, ONCE_WIDE, ONCE_NARROW2, ONCE_POOL, ONCE_AGG2, ONCE_TC_WGRAD, ONCE_GRAPH_POST };
 // true exactly once per (context, key)
 static inline bool ctx_first(gnb_ctx* c, int key) {
   const uint64_t b = 1ull << key;

@@ -12,6 +12,7 @@
 //                  y_u = (u + h_u) + W2 relu(W1 LN2(u) + b1) + b2                       (src/gncore.jl:56-68)
 #include "kernels.cuh"
 #include "graphrows.cuh"
+#include <stdlib.h>
 
 namespace {
 
@@ -91,7 +92,7 @@ __global__ void __launch_bounds__(128) k_graph_pre(const GraphPreArgs a) {
 }
 
 // K-slice of gemv_rows: acc[r] += sum_{k in [k0, k0 + KS)} xs[r][k] * W[k*ldw + n]     (xs rows have stride LD floats)
-template <int KS, int LD>
+template <int KS, int LD, int RT>
 __device__ __forceinline__ void gemv_slice(const float* xs, int k0, const float* __restrict__ W, int ldw, int n, float* acc) {
 #pragma unroll 4
   for (int k = k0; k < k0 + KS; k += 4) {
@@ -130,20 +131,23 @@ __device__ __forceinline__ void ln_row(const float* xs, float* out, const float*
 // split 4 ways along K (partials combined in a fixed order through shared memory: deterministic) and the node sums 4 ways over
 // the graphs of the CTA.
 constexpr int GP_THREADS = 512;
-__global__ void __launch_bounds__(GP_THREADS) k_graph_post(const GraphPostArgs a) {
-  __shared__ __align__(16) float xs[RT][H];        // u
-  __shared__ __align__(16) float cat[RT][3 * H];   // [s_e | s_v | LN1(u)]   (s_v slot first holds gamma . sum v^)
-  __shared__ __align__(16) float xb[RT][H];        // LN2(u); later y_u, LN1'(y_u)
-  __shared__ __align__(16) float svg[RT][H];       // sum of the node addends
-  __shared__ __align__(16) float seg[RT][H];       // sum of the edge addends
-  __shared__ __align__(16) float hid[RT][4 * H];   // FFN hidden; before that the scratch of the K-split reductions
+template <int RT>
+__global__ void __launch_bounds__(GP_THREADS, 2) k_graph_post(const GraphPostArgs a) {
+  // dynamic shared memory (RT x 11 H floats: 45 KB at RT = 8, 90 KB at RT = 16)
+  extern __shared__ __align__(16) float gp_sm[];
+  float(*xs)[H] = reinterpret_cast<float(*)[H]>(gp_sm);                          // u
+  float(*cat)[3 * H] = reinterpret_cast<float(*)[3 * H]>(gp_sm + RT * H);        // [s_e | s_v | LN1(u)]   (s_v slot first holds gamma . sum v^)
+  float(*xb)[H] = reinterpret_cast<float(*)[H]>(gp_sm + RT * 4 * H);             // LN2(u); later y_u, LN1'(y_u)
+  float(*svg)[H] = reinterpret_cast<float(*)[H]>(gp_sm + RT * 5 * H);            // sum of the node addends
+  float(*seg)[H] = reinterpret_cast<float(*)[H]>(gp_sm + RT * 6 * H);            // sum of the edge addends
+  float(*hid)[4 * H] = reinterpret_cast<float(*)[4 * H]>(gp_sm + RT * 7 * H);    // FFN hidden; before that the scratch of the K-split reductions
   float(*red)[RT][H] = reinterpret_cast<float(*)[RT][H]>(&hid[0][0]);      // [4][RT][H] == sizeof(hid)
   const int tid = threadIdx.x, n = tid & (H - 1), ks = tid >> 7, warp = tid >> 5, lane = tid & 31;
   const int64_t g0 = (int64_t)blockIdx.x * RT;
   // ---- ordered sums of the graph's partial rows (per (16-node block, graph) run: a handful per graph): deterministic, no
-  // atomics; group ks owns graphs 2 ks, 2 ks + 1 of the CTA
+  // atomics; group ks owns RT / 4 graphs of the CTA
 #pragma unroll 1
-  for (int r = 2 * ks; r < 2 * ks + 2; r++) {
+  for (int r = ks * (RT / 4); r < (ks + 1) * (RT / 4); r++) {
     const int64_t g = g0 + r < a.B ? g0 + r : a.B - 1;
     xs[r][n] = a.xg[(size_t)g * H + n];
     const int p0 = a.graph_npart_ptr[g], p1 = a.graph_npart_ptr[g + 1];
@@ -159,15 +163,17 @@ __global__ void __launch_bounds__(GP_THREADS) k_graph_post(const GraphPostArgs a
     svg[r][n] = sn;
   }
   __syncthreads();
-  if (warp < RT) ln_row(xs[warp], &cat[warp][2 * H], a.g1, a.b1ln, a.eps1, a.eps_mode1, lane);
-  else ln_row(xs[warp - RT], xb[warp - RT], a.g2, a.b2ln, a.eps2, a.eps_mode2, lane);
+  for (int i = warp; i < 2 * RT; i += GP_THREADS / 32) {
+    if (i < RT) ln_row(xs[i], &cat[i][2 * H], a.g1, a.b1ln, a.eps1, a.eps_mode1, lane);
+    else ln_row(xs[i - RT], xb[i - RT], a.g2, a.b2ln, a.eps2, a.eps_mode2, lane);
+  }
   // ---- s_e = W_ee (gamma_e . sum ê) + sum of the edge addends;  s_v = W_nv (gamma_n . sum v^) + sum of the node addends
   {
     float t[RT], te[RT];
 #pragma unroll
     for (int r = 0; r < RT; r++) { t[r] = 0.f; te[r] = 0.f; }
-    gemv_slice<H / 4, 3 * H>(&cat[0][0], ks * (H / 4), a.Wee, H, n, te);
-    gemv_slice<H / 4, 3 * H>(&cat[0][H], ks * (H / 4), a.Wnv, H, n, t);
+    gemv_slice<H / 4, 3 * H, RT>(&cat[0][0], ks * (H / 4), a.Wee, H, n, te);
+    gemv_slice<H / 4, 3 * H, RT>(&cat[0][H], ks * (H / 4), a.Wnv, H, n, t);
 #pragma unroll
     for (int r = 0; r < RT; r++) red[ks][r][n] = t[r];
     __syncthreads();      // also publishes the LayerNorm rows
@@ -191,7 +197,7 @@ __global__ void __launch_bounds__(GP_THREADS) k_graph_post(const GraphPostArgs a
     float t[RT];
 #pragma unroll
     for (int r = 0; r < RT; r++) t[r] = 0.f;
-    gemv_slice<3 * H / 4, 3 * H>(&cat[0][0], ks * (3 * H / 4), a.Wg, H, n, t);
+    gemv_slice<3 * H / 4, 3 * H, RT>(&cat[0][0], ks * (3 * H / 4), a.Wg, H, n, t);
 #pragma unroll
     for (int r = 0; r < RT; r++) red[ks][r][n] = t[r];
     __syncthreads();
@@ -206,7 +212,7 @@ __global__ void __launch_bounds__(GP_THREADS) k_graph_post(const GraphPostArgs a
     const float b1 = a.b1[ks * H + n];
 #pragma unroll
     for (int r = 0; r < RT; r++) hc[r] = b1;
-    gemv_slice<H, H>(&xb[0][0], 0, a.W1 + ks * H, 4 * H, n, hc);
+    gemv_slice<H, H, RT>(&xb[0][0], 0, a.W1 + ks * H, 4 * H, n, hc);
 #pragma unroll
     for (int r = 0; r < RT; r++) hid[r][ks * H + n] = fmaxf(hc[r], 0.f);
   }
@@ -215,7 +221,7 @@ __global__ void __launch_bounds__(GP_THREADS) k_graph_post(const GraphPostArgs a
     float t[RT];
 #pragma unroll
     for (int r = 0; r < RT; r++) t[r] = 0.f;
-    gemv_slice<H, 4 * H>(&hid[0][0], ks * H, a.W2, H, n, t);
+    gemv_slice<H, 4 * H, RT>(&hid[0][0], ks * H, a.W2, H, n, t);
     float(*red2)[RT][H] = reinterpret_cast<float(*)[RT][H]>(&cat[0][0]);      // [3][RT][H] == sizeof(cat): slices 1..3
     if (ks > 0) {
 #pragma unroll
@@ -236,7 +242,7 @@ __global__ void __launch_bounds__(GP_THREADS) k_graph_post(const GraphPostArgs a
   if (a.next_Pue == nullptr) return;      // uniform
   // ---- per-graph rows of the NEXT core (k_graph_pre fused): P_ue = LN1'(y_u) W_eu' + c_e', P_un likewise
   __syncthreads();
-  if (warp < RT) ln_row(xb[warp], xs[warp], a.next_gamma, a.next_beta, a.next_eps, a.next_eps_mode, lane);
+  for (int i = warp; i < RT; i += GP_THREADS / 32) ln_row(xb[i], xs[i], a.next_gamma, a.next_beta, a.next_eps, a.next_eps_mode, lane);
   __syncthreads();
   {
     float te[RT];
@@ -244,7 +250,7 @@ __global__ void __launch_bounds__(GP_THREADS) k_graph_post(const GraphPostArgs a
     for (int r = 0; r < RT; r++) te[r] = 0.f;
     // groups 0, 1: the two K halves of P_ue; groups 2, 3: of P_un
     const float* W = ks < 2 ? a.next_Weu : a.next_Wnu;
-    gemv_slice<H / 2, H>(&xs[0][0], (ks & 1) * (H / 2), W, H, n, te);
+    gemv_slice<H / 2, H, RT>(&xs[0][0], (ks & 1) * (H / 2), W, H, n, te);
 #pragma unroll
     for (int r = 0; r < RT; r++) red[ks][r][n] = te[r];
     __syncthreads();
@@ -272,7 +278,16 @@ int launch_graph_post(gnb_ctx* ctx, const GraphPostArgs& a, int64_t N) {
   if (a.B <= 0) return GNB_OK;
   (void)N;
   Launch L(ctx, "graph_post", 8.0 * a.B * H + 4.0 * 12 * H * H, 24.0 * a.B * H * H);
-  k_graph_post<<<ceil_div(a.B, RT), GP_THREADS, 0, ctx->stream>>>(a);
+  // 16 graphs per CTA: 256 CTAs for 4096 graphs = ONE wave at two resident CTAs per SM and half the weight traffic from L2
+  // (8 graphs per CTA: 512 CTAs = 1.7 waves); small batches keep 8 so that every SM has work
+  static const int rt_env = getenv("GNB_GRAPH_RT") ? atoi(getenv("GNB_GRAPH_RT")) : 0;
+  const int rt = rt_env ? rt_env : (a.B >= 16 * ctx->sm_count ? 16 : 8);
+  if (ctx_first(ctx, ONCE_GRAPH_POST)) {
+    GNB_CUDA(cudaFuncSetAttribute(k_graph_post<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 16 * 11 * H * 4));
+    GNB_CUDA(cudaFuncSetAttribute(k_graph_post<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 11 * H * 4));
+  }
+  if (rt == 16) k_graph_post<16><<<ceil_div(a.B, 16), GP_THREADS, 16 * 11 * H * 4, ctx->stream>>>(a);
+  else k_graph_post<8><<<ceil_div(a.B, 8), GP_THREADS, 8 * 11 * H * 4, ctx->stream>>>(a);
   GNB_CUDA(cudaGetLastError());
   return GNB_OK;
 }

@@ -20,6 +20,7 @@ namespace {
 constexpr int WK_MAX = 32;      // max concatenated input width of k_wide
 constexpr int WIDE_ROWS = 32;   // rows staged per warp step
 constexpr int WIDE_WARPS = 8;
+constexpr int WIDE_MAXP = 5;    // == the size of WideArgs::pc
 
 __global__ void __launch_bounds__(WIDE_WARPS * 32) k_wide(const WideArgs a) {
   extern __shared__ __align__(16) float sm_w[];
@@ -56,21 +57,47 @@ __global__ void __launch_bounds__(WIDE_WARPS * 32) k_wide(const WideArgs a) {
   for (int64_t blk = (int64_t)blockIdx.x * WIDE_WARPS + warp; blk < nblocks; blk += (int64_t)gridDim.x * WIDE_WARPS) {
     const int64_t row0 = blk * WIDE_ROWS;
     const int rows = (int)((a.R - row0) < WIDE_ROWS ? (a.R - row0) : WIDE_ROWS);
-    // ---- assemble the concat rows of this block in shared memory: lane r gathers the pieces of row r
+    // ---- assemble the concat rows of this block in shared memory: lane r gathers the pieces of row r.  All index loads are
+    // issued together, then the first 8 values of EVERY piece, before anything is stored: two dependent memory round trips per
+    // block (a load -> store loop over k costs one round trip per k: the loop bounds are run-time values, nothing is hoisted).
+    // Lanes past the end of the batch gather a valid row (the last one); their outputs are never stored.
     __syncwarp();
     {
       float* zr = zin + lane * K4;
-      int koff = 0;
-      for (int p = 0; p < a.np; p++) {
-        const WidePiece& P = a.pc[p];
-        if (lane < rows) {
-          const int64_t g = P.idx ? (int64_t)__ldg(P.idx + row0 + lane) : row0 + lane;
-          const float* src = P.x + (size_t)g * P.ldx;
-          for (int k = 0; k < P.d; k++) zr[koff + k] = __ldg(src + k);
-        } else {
-          for (int k = 0; k < P.d; k++) zr[koff + k] = 0.f;
+      int64_t rr = row0 + lane;
+      rr = rr < a.R ? rr : a.R - 1;
+      const float* sp[WIDE_MAXP];
+#pragma unroll
+      for (int p = 0; p < WIDE_MAXP; p++) {
+        sp[p] = nullptr;
+        if (p < a.np) {
+          const int64_t g = a.pc[p].idx ? (int64_t)__ldg(a.pc[p].idx + rr) : rr;
+          sp[p] = a.pc[p].x + (size_t)g * a.pc[p].ldx;
         }
-        koff += P.d;
+      }
+      float t[WIDE_MAXP][8];
+#pragma unroll
+      for (int p = 0; p < WIDE_MAXP; p++)
+#pragma unroll
+        for (int j = 0; j < 8; j++) t[p][j] = (p < a.np && j < a.pc[p].d) ? __ldg(sp[p] + j) : 0.f;
+      int koff = 0;
+#pragma unroll
+      for (int p = 0; p < WIDE_MAXP; p++) {
+        if (p < a.np) {
+          const int d = a.pc[p].d;
+#pragma unroll
+          for (int j = 0; j < 8; j++)
+            if (j < d) zr[koff + j] = t[p][j];
+          for (int k0 = 8; k0 < d; k0 += 8) {      // pieces wider than 8: further batches of 8
+            float u[8];
+#pragma unroll
+            for (int j = 0; j < 8; j++) u[j] = k0 + j < d ? __ldg(sp[p] + k0 + j) : 0.f;
+#pragma unroll
+            for (int j = 0; j < 8; j++)
+              if (k0 + j < d) zr[koff + k0 + j] = u[j];
+          }
+          koff += d;
+        }
       }
       for (int k = koff; k < K4; k++) zr[k] = 0.f;
     }
@@ -121,15 +148,17 @@ __global__ void __launch_bounds__(WIDE_WARPS * 32) k_wide(const WideArgs a) {
   }
 }
 
-// One warp per node; lane k owns column k of Z (Kz <= 32).
+// One thread per (node, column of Z), nodes packed back to back along the thread index (Kz <= 32 columns per node: with one
+// WARP per node a third of the lanes idled at Kz = 21); the sums run over the node's receiver-sorted edges in order.
 __global__ void k_zsum(const ZsumArgs a) {
-  const int64_t v = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
+  const int o_s = a.de, o_v = a.de + a.dn, o_u = a.de + 2 * a.dn, o_d = a.de + 2 * a.dn + a.dg;
+  const int kz = o_d + 1;
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t v = t / kz;
+  const int k = (int)(t - v * kz);
   if (v >= a.N) return;
   const int e0 = a.node_in_ptr[v], e1 = a.node_in_ptr[v + 1];
   const float deg = (float)(e1 - e0);
-  const int k = lane;
-  const int o_s = a.de, o_v = a.de + a.dn, o_u = a.de + 2 * a.dn, o_d = a.de + 2 * a.dn + a.dg;
   float s = 0.f;
   if (k < o_s) {
     for (int e = e0; e < e1; e++) s += a.ef[(size_t)e * a.de + k];
@@ -139,10 +168,10 @@ __global__ void k_zsum(const ZsumArgs a) {
     s = deg * a.nf[(size_t)v * a.dn + (k - o_v)];
   } else if (k < o_d) {
     s = deg * a.gf[(size_t)a.node_graph[v] * a.dg + (k - o_u)];
-  } else if (k == o_d) {
+  } else {
     s = deg;
   }
-  if (k <= o_d) a.Z[(size_t)v * (o_d + 1) + k] = s;
+  a.Z[(size_t)v * kz + k] = s;
 }
 
 // lane owns k = 4*lane + 128*c (+0..3); one row per warp step, 4 rows in flight.
@@ -350,19 +379,24 @@ int launch_zsum(gnb_ctx* ctx, const ZsumArgs& a) {
   if (a.N <= 0) return GNB_OK;
   GNB_CHECK(a.de + 2 * a.dn + a.dg + 1 <= 32, "launch_zsum: aggregated input width > 32");
   Launch L(ctx, "zsum_fp32", 0, 0);
-  k_zsum<<<ceil_div(a.N * 32, 256), 256, 0, ctx->stream>>>(a);
+  k_zsum<<<ceil_div(a.N * (a.de + 2 * a.dn + a.dg + 1), 256), 256, 0, ctx->stream>>>(a);
   GNB_CUDA(cudaGetLastError());
   return GNB_OK;
 }
 
-int launch_narrow(gnb_ctx* ctx, const NarrowArgs& a) {
+int launch_narrow(gnb_ctx* ctx, const NarrowArgs& a_in) {
+  NarrowArgs a = a_in;
   if (a.R <= 0 || a.No <= 0) return GNB_OK;
   int K = 0;
   for (int s = 0; s < a.nsrc; s++) K += a.src[s].d;
   GNB_CHECK(a.No <= 8 && K <= NARROW_KMAX, "launch_narrow: No %d > 8 or K %d > %d", a.No, K, NARROW_KMAX);
   double bytes = 4.0 * a.R * (K + a.No * (1 + a.nadd));
   Launch L(ctx, "narrow_fp32", bytes, 2.0 * a.R * K * a.No);
-  // wide first source: thread-per-row through a swizzled staging tile; otherwise the lane-per-k kernel
+  // wide first source: thread-per-row through a swizzled staging tile; otherwise the lane-per-k kernel.  Every source carries
+  // its own weight rows, so the order of the sources is free: the widest goes first (the node decoder lists its 3-wide edge
+  // aggregate before the 128-wide node rows)
+  for (int s = 1; s < a.nsrc; s++)
+    if (a.src[s].d > a.src[0].d) { const NarrowSrc t = a.src[0]; a.src[0] = a.src[s]; a.src[s] = t; }
   bool small_rest = true;
   for (int s = 1; s < a.nsrc; s++) small_rest = small_rest && a.src[s].d <= 16;
   const NarrowSrc& S0 = a.src[0];

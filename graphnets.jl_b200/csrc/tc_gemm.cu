@@ -59,6 +59,59 @@ struct GemmArgs {
   WatchArgs wd;                   // kernel watchdog (tc_ptx.cuh)
 };
 
+// LayerNorm statistics of the 16 rows of one producer warp, two-pass in fp32 (src/gngraphnorm.jl:19-26): 16 lanes per row, the
+// row stays in registers for both passes; NP row pairs (= 2 NP rows) of NV float4 per lane are loaded before anything is reduced.
+template <int NP, int NV>
+__device__ __forceinline__ void tile_stats(const float* xs, int ldx, int nv, float inv_d, int64_t row0, int64_t R, int hr, int c16,
+                                           float2* st, float eps, int eps_mode) {
+#pragma unroll 1
+  for (int r0 = 0; r0 < 16; r0 += 2 * NP) {
+    float4 v[NP][NV];
+#pragma unroll
+    for (int p = 0; p < NP; p++) {
+      int64_t row = row0 + r0 + 2 * p + hr;
+      row = row < R ? row : R - 1;
+      const float* xr = xs + (size_t)row * ldx;
+#pragma unroll
+      for (int j = 0; j < NV; j++) v[p][j] = j < nv ? __ldg(reinterpret_cast<const float4*>(xr + 64 * j)) : f4zero();
+    }
+    float sum[NP], sq[NP];
+#pragma unroll
+    for (int p = 0; p < NP; p++) {
+      float t = 0.f;
+#pragma unroll
+      for (int j = 0; j < NV; j++) t += (v[p][j].x + v[p][j].y) + (v[p][j].z + v[p][j].w);
+      sum[p] = t;
+    }
+#pragma unroll
+    for (int o = 1; o < 16; o <<= 1)
+#pragma unroll
+      for (int p = 0; p < NP; p++) sum[p] += __shfl_xor_sync(0xffffffffu, sum[p], o);
+#pragma unroll
+    for (int p = 0; p < NP; p++) {
+      const float mu = sum[p] * inv_d;
+      float t = 0.f;
+#pragma unroll
+      for (int j = 0; j < NV; j++) {
+        if (j < nv) {
+          const float dx = v[p][j].x - mu, dy = v[p][j].y - mu, dz = v[p][j].z - mu, dw = v[p][j].w - mu;
+          t += (dx * dx + dy * dy) + (dz * dz + dw * dw);
+        }
+      }
+      sq[p] = t;
+      sum[p] = mu;
+    }
+#pragma unroll
+    for (int o = 1; o < 16; o <<= 1)
+#pragma unroll
+      for (int p = 0; p < NP; p++) sq[p] += __shfl_xor_sync(0xffffffffu, sq[p], o);
+    if (c16 == 0) {
+#pragma unroll
+      for (int p = 0; p < NP; p++) st[r0 + 2 * p + hr] = make_float2(sum[p], ln_rstd(sq[p] * inv_d, eps, eps_mode));
+    }
+  }
+}
+
 __global__ void __launch_bounds__(G_THREADS, 1) k_tc_lin(const GemmArgs a) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
@@ -150,59 +203,14 @@ __global__ void __launch_bounds__(G_THREADS, 1) k_tc_lin(const GemmArgs a) {
     for (int tile = blockIdx.x; tile < a.num_tiles && !wd_dead; tile += gridDim.x) {
       const int64_t row0 = (int64_t)tile * TM + 16 * pw;
       // ---- LayerNorm statistics of this warp's rows, two-pass in fp32 (src/gngraphnorm.jl:19-26), kept for all column groups
-      // (16 lanes per row, the row stays in registers for both passes; 2 row pairs = 4 rows of loads in flight)
+      // (tile_stats above)
       for (int s = 0; s < a.nsrc; s++) {
         if (a.gamma[s] == nullptr) continue;
         const int d = a.d[s], nv = d >> 6;      // float4 per lane and row (d <= 512: nv <= 8)
-        const float* xs = a.x[s] + 4 * c16;
-        const float inv_d = 1.0f / (float)d;
-#pragma unroll 1
-        for (int r0 = 0; r0 < 16; r0 += 4) {
-          float4 v[2][8];
-#pragma unroll
-          for (int p = 0; p < 2; p++) {
-            int64_t row = row0 + r0 + 2 * p + hr;
-            row = row < a.R ? row : a.R - 1;
-            const float* xr = xs + (size_t)row * a.ldx[s];
-#pragma unroll
-            for (int j = 0; j < 8; j++) v[p][j] = j < nv ? __ldg(reinterpret_cast<const float4*>(xr + 64 * j)) : f4zero();
-          }
-          float sum[2], sq[2];
-#pragma unroll
-          for (int p = 0; p < 2; p++) {
-            float t = 0.f;
-#pragma unroll
-            for (int j = 0; j < 8; j++) t += (v[p][j].x + v[p][j].y) + (v[p][j].z + v[p][j].w);
-            sum[p] = t;
-          }
-#pragma unroll
-          for (int o = 1; o < 16; o <<= 1)
-#pragma unroll
-            for (int p = 0; p < 2; p++) sum[p] += __shfl_xor_sync(0xffffffffu, sum[p], o);
-#pragma unroll
-          for (int p = 0; p < 2; p++) {
-            const float mu = sum[p] * inv_d;
-            float t = 0.f;
-#pragma unroll
-            for (int j = 0; j < 8; j++) {
-              if (j < nv) {
-                const float dx = v[p][j].x - mu, dy = v[p][j].y - mu, dz = v[p][j].z - mu, dw = v[p][j].w - mu;
-                t += (dx * dx + dy * dy) + (dz * dz + dw * dw);
-              }
-            }
-            sq[p] = t;
-            sum[p] = mu;
-          }
-#pragma unroll
-          for (int o = 1; o < 16; o <<= 1)
-#pragma unroll
-            for (int p = 0; p < 2; p++) sq[p] += __shfl_xor_sync(0xffffffffu, sq[p], o);
-          if (c16 == 0) {
-#pragma unroll
-            for (int p = 0; p < 2; p++)
-              stats[s * 128 + 16 * pw + r0 + 2 * p + hr] = make_float2(sum[p], ln_rstd(sq[p] * inv_d, a.eps[s], a.eps_mode[s]));
-          }
-        }
+        float2* st = stats + s * 128 + 16 * pw;
+        // rows up to 256 wide: 8 rows of loads in flight per warp, wider: 4 (the same 64 registers)
+        if (nv <= 4) tile_stats<4, 4>(a.x[s] + 4 * c16, a.ldx[s], nv, 1.0f / (float)d, row0, a.R, hr, c16, st, a.eps[s], a.eps_mode[s]);
+        else tile_stats<2, 8>(a.x[s] + 4 * c16, a.ldx[s], nv, 1.0f / (float)d, row0, a.R, hr, c16, st, a.eps[s], a.eps_mode[s]);
       }
       __syncwarp();
       const int npass = a.resident ? 1 : a.ngroups;
