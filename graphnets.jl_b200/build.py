@@ -43,7 +43,7 @@ VARIANTS = {"oldproj": (["tc.cu"], ["-DGNB_OLD_PROJ_PROTOCOL"]),
 if os.environ.get("GNB_AB_FLAGS"):
     for i, spec in enumerate(os.environ["GNB_AB_FLAGS"].split(";")):
         name, _, flags = spec.partition(":") if ":" in spec else ("ab" if i == 0 else "ab%d" % i, "", spec)
-        VARIANTS[name.strip()] = (["tc_edge.cu", "tc.cu", "tc_gemm.cu", "fp32.cu"], flags.split())
+        VARIANTS[name.strip()] = (["tc_edge.cu", "tc.cu", "tc_gemm.cu", "fp32.cu", "smallk.cu", "graphrows.cu"], flags.split())
 
 
 def variant_path(name):

@@ -711,7 +711,7 @@ static bool block_narrow_ok(const LayerW& w) {
 }
 // Edge update of a narrow decoder whose edge-feature term was already computed by the previous core's edge kernel
 // (partial[e][0..4) = y_e . We[0:128, :]):  h_e = partial + Ps[src] + Pr[dst] + (Pu[graph] | be)      (src/gnblock.jl:65)
-__global__ void k_dec_finish(const float* __restrict__ partial, const float* __restrict__ Ps, const float* __restrict__ Pr,
+__global__ void k_dec_finish(const float* __restrict__ partial, const float* __restrict__ Ps, const float* __restrict__ Pr, int ldP,
                              const float* __restrict__ Pu, const float* __restrict__ be, const int32_t* __restrict__ src,
                              const int32_t* __restrict__ dst, const int32_t* __restrict__ eg, int64_t E, int p, float* __restrict__ out) {
   const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -721,7 +721,7 @@ __global__ void k_dec_finish(const float* __restrict__ partial, const float* __r
   const int s_ = Ps ? src[e] : 0, d_ = Pr ? dst[e] : 0, g_ = Pu ? eg[e] : 0;
   for (int j = 0; j < p; j++) {
     float t = v[j];
-    if (Ps) t += __ldg(Ps + (size_t)s_ * p + j) + __ldg(Pr + (size_t)d_ * p + j);
+    if (Ps) t += __ldg(Ps + (size_t)s_ * ldP + j) + __ldg(Pr + (size_t)d_ * ldP + j);
     t += Pu ? __ldg(Pu + (size_t)g_ * p + j) : be[j];
     out[(size_t)e * p + j] = t;
   }
@@ -737,18 +737,29 @@ static int run_block_narrow(gnb_ctx* ctx, const gnb_graph* g, const LayerW& w, F
   const int64_t E = g->E, N = g->N, B = g->B;
   int rc = GNB_OK;
   float *Ps = nullptr, *Pr = nullptr, *Pu = nullptr;
+  int ldP = p;      // row stride of P_s / P_r
   if (bn_ > 0) {
-    Ps = arena_ptr<float>(ctx->arena, (size_t)N * p, &rc);
-    Pr = arena_ptr<float>(ctx->arena, (size_t)N * p, &rc);
+    // P_s | P_r interleaved per node ([N][2p]): both projections in ONE pass over the node rows
+    Ps = arena_ptr<float>(ctx->arena, (size_t)N * 2 * p, &rc);
     if (rc != GNB_OK) return rc;
-    NarrowArgs na{};
-    na.R = N; na.No = p; na.ldw = p; na.nsrc = 1; na.ldo = p;
-    na.src[0] = NarrowSrc{x.n, bn_, bn_, b.We + (size_t)a * p};
-    na.out = Ps;
-    GNB_TRY(launch_narrow(ctx, na));
-    na.src[0].W = b.We + (size_t)(a + bn_) * p;
-    na.out = Pr;
-    GNB_TRY(launch_narrow(ctx, na));
+    Pr = Ps + p;
+    ldP = 2 * p;
+    if (2 * p <= 8) {
+      NarrowArgs na{};
+      na.R = N; na.No = 2 * p; na.ldw = p; na.nsrc = 1; na.ldo = 2 * p;
+      na.src[0] = NarrowSrc{x.n, bn_, bn_, b.We + (size_t)a * p, b.We + (size_t)(a + bn_) * p, p};
+      na.out = Ps;
+      GNB_TRY(launch_narrow(ctx, na));
+    } else {
+      NarrowArgs na{};
+      na.R = N; na.No = p; na.ldw = p; na.nsrc = 1; na.ldo = 2 * p;
+      na.src[0] = NarrowSrc{x.n, bn_, bn_, b.We + (size_t)a * p};
+      na.out = Ps;
+      GNB_TRY(launch_narrow(ctx, na));
+      na.src[0].W = b.We + (size_t)(a + bn_) * p;
+      na.out = Pr;
+      GNB_TRY(launch_narrow(ctx, na));
+    }
   }
   if (c > 0) {
     Pu = arena_ptr<float>(ctx->arena, (size_t)B * p, &rc);
@@ -763,14 +774,14 @@ static int run_block_narrow(gnb_ctx* ctx, const gnb_graph* g, const LayerW& w, F
     if (edge_partial) {      // the edge-feature term came out of the previous core's edge kernel
       if (E > 0) {
         Launch L(ctx, "dec_finish", 4.0 * E * (4 + p + 3), 0);
-        k_dec_finish<<<ceil_div(E, 256), 256, 0, ctx->stream>>>(edge_partial, Ps, Pr, Pu, b.be, g->edge_src, g->edge_dst, g->edge_graph, E, p, h.e);
+        k_dec_finish<<<ceil_div(E, 256), 256, 0, ctx->stream>>>(edge_partial, Ps, Pr, ldP, Pu, b.be, g->edge_src, g->edge_dst, g->edge_graph, E, p, h.e);
         GNB_CUDA(cudaGetLastError());
       }
     } else {
       NarrowArgs na{};
       na.R = E; na.No = p; na.ldw = p; na.nsrc = 1; na.ldo = p; na.out = h.e;
       na.src[0] = NarrowSrc{x.e, a, a, b.We};
-      if (Ps) { na.add[na.nadd++] = NarrowAdd{Ps, g->edge_src, p}; na.add[na.nadd++] = NarrowAdd{Pr, g->edge_dst, p}; }
+      if (Ps) { na.add[na.nadd++] = NarrowAdd{Ps, g->edge_src, ldP}; na.add[na.nadd++] = NarrowAdd{Pr, g->edge_dst, ldP}; }
       if (Pu) na.add[na.nadd++] = NarrowAdd{Pu, g->edge_graph, p};
       else na.bias = b.be;
       GNB_TRY(launch_narrow(ctx, na));

@@ -22,26 +22,39 @@ constexpr int WIDE_ROWS = 32;   // rows staged per warp step
 constexpr int WIDE_WARPS = 8;
 constexpr int WIDE_MAXP = 5;    // == the size of WideArgs::pc
 
-__global__ void __launch_bounds__(WIDE_WARPS * 32) k_wide(const WideArgs a) {
+constexpr int WIDE_MINB = 3;      // resident CTAs per SM (<= 85 registers per thread; measured: 2 and 4 are slower)
+__global__ void __launch_bounds__(WIDE_WARPS * 32, WIDE_MINB) k_wide(const WideArgs a) {
   extern __shared__ __align__(16) float sm_w[];
-  // layout: Ws2[K4/2][128][2] (column block of this CTA, k-pair interleaved for packed FFMA2) | per-warp zin[WIDE_ROWS][K4]
+  // layout: Ws[K4/2][2][32][4] (column block of this CTA, k pairs interleaved) | per-warp zin[WIDE_ROWS][K4]
   const int K4 = a.K4;                       // total input width rounded up to a multiple of 4
   float* Ws = sm_w;
   float* zin_all = sm_w + (size_t)K4 * 128;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int col0 = blockIdx.y * 128;
-  // ---- weight block: rows = concatenated k, zero padded
-  for (int i = tid; i < K4 * 128; i += blockDim.x) {
-    const int k = i >> 7, n = i & 127;
-    float w = 0.f;
-    if (col0 + n < a.Nout) {
-      int kk = k;
-      for (int p = 0; p < a.np; p++) {
-        if (kk < a.pc[p].d) { w = a.pc[p].W[(size_t)kk * a.ldw + col0 + n]; break; }
-        kk -= a.pc[p].d;
+  // ---- weight block: rows = concatenated k, zero padded; four independent loads in flight per thread
+  for (int i0 = tid; i0 < K4 * 128; i0 += 4 * blockDim.x) {
+    float w[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      const int i = i0 + u * blockDim.x;
+      const int k = i >> 7, n = i & 127;
+      w[u] = 0.f;
+      if (i < K4 * 128 && col0 + n < a.Nout) {
+        int kk = k;
+        for (int p = 0; p < a.np; p++) {
+          if (kk < a.pc[p].d) { w[u] = __ldg(a.pc[p].W + (size_t)kk * a.ldw + col0 + n); break; }
+          kk -= a.pc[p].d;
+        }
       }
     }
-    Ws[((k >> 1) * 128 + n) * 2 + (k & 1)] = w;
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      const int i = i0 + u * blockDim.x;
+      const int k = i >> 7, n = i & 127;
+      // per k pair two planes of [lane][4]: plane c/2 holds (col c, k) (col c, k+1) (col c+1, k) (col c+1, k+1) of the lane's
+      // column quad - every 16 B weight load of the loop below is contiguous across the lanes (conflict-free)
+      if (i < K4 * 128) Ws[((((k >> 1) * 2 + ((n & 3) >> 1)) * 32 + (n >> 2)) << 2) + ((n & 1) << 1) + (k & 1)] = w[u];
+    }
   }
   __syncthreads();
   float* zin = zin_all + (size_t)warp * WIDE_ROWS * K4;
@@ -102,39 +115,36 @@ __global__ void __launch_bounds__(WIDE_WARPS * 32) k_wide(const WideArgs a) {
       for (int k = koff; k < K4; k++) zr[k] = 0.f;
     }
     __syncwarp();
-    // ---- 8 rows x (4 columns per lane) per step; k pairs on the two halves of packed FFMA2
+    // ---- 8 rows x (4 columns per lane) per step
 #pragma unroll 1
     for (int r0 = 0; r0 < rows; r0 += 8) {
-      float2 acc[8][4];
+      // plain FFMA: a packed FFMA2 occupies the FMA pipe for two cycles, so it only saves issue slots, and its k-pair
+      // accumulators cost 32 more registers (measured: 178 us per launch with FFMA2 at two CTAs per SM, 172 us this way)
+      float acc[8][4];
 #pragma unroll
       for (int j = 0; j < 8; j++)
 #pragma unroll
-        for (int c = 0; c < 4; c++) acc[j][c] = make_float2(0.f, 0.f);
+        for (int c = 0; c < 4; c++) acc[j][c] = 0.f;
       for (int k = 0; k < K4; k += 4) {
-        const float4 wa = *reinterpret_cast<const float4*>(Ws + ((k >> 1) * 128 + 4 * lane) * 2);        // pair k,k+1: cols 0,1
-        const float4 wb = *reinterpret_cast<const float4*>(Ws + ((k >> 1) * 128 + 4 * lane) * 2 + 4);    //             cols 2,3
-        const float4 wc = *reinterpret_cast<const float4*>(Ws + (((k >> 1) + 1) * 128 + 4 * lane) * 2);  // pair k+2,k+3
-        const float4 wd = *reinterpret_cast<const float4*>(Ws + (((k >> 1) + 1) * 128 + 4 * lane) * 2 + 4);
+        const float* wp = Ws + (k >> 1) * 256 + 4 * lane;
+        const float4 wa = *reinterpret_cast<const float4*>(wp);            // (c0: k, k+1) (c1: k, k+1)
+        const float4 wb = *reinterpret_cast<const float4*>(wp + 128);      // (c2: k, k+1) (c3: k, k+1)
+        const float4 wc = *reinterpret_cast<const float4*>(wp + 256);      // (c0: k+2, k+3) (c1: k+2, k+3)
+        const float4 wd = *reinterpret_cast<const float4*>(wp + 384);
 #pragma unroll
         for (int j = 0; j < 8; j++) {
           const float4 z = *reinterpret_cast<const float4*>(zin + (r0 + j) * K4 + k);   // broadcast
-          const float2 z01 = make_float2(z.x, z.y), z23 = make_float2(z.z, z.w);
-          acc[j][0] = __ffma2_rn(z01, make_float2(wa.x, wa.y), acc[j][0]);
-          acc[j][1] = __ffma2_rn(z01, make_float2(wa.z, wa.w), acc[j][1]);
-          acc[j][2] = __ffma2_rn(z01, make_float2(wb.x, wb.y), acc[j][2]);
-          acc[j][3] = __ffma2_rn(z01, make_float2(wb.z, wb.w), acc[j][3]);
-          acc[j][0] = __ffma2_rn(z23, make_float2(wc.x, wc.y), acc[j][0]);
-          acc[j][1] = __ffma2_rn(z23, make_float2(wc.z, wc.w), acc[j][1]);
-          acc[j][2] = __ffma2_rn(z23, make_float2(wd.x, wd.y), acc[j][2]);
-          acc[j][3] = __ffma2_rn(z23, make_float2(wd.z, wd.w), acc[j][3]);
+          acc[j][0] = fmaf(z.w, wc.y, fmaf(z.z, wc.x, fmaf(z.y, wa.y, fmaf(z.x, wa.x, acc[j][0]))));
+          acc[j][1] = fmaf(z.w, wc.w, fmaf(z.z, wc.z, fmaf(z.y, wa.w, fmaf(z.x, wa.z, acc[j][1]))));
+          acc[j][2] = fmaf(z.w, wd.y, fmaf(z.z, wd.x, fmaf(z.y, wb.y, fmaf(z.x, wb.x, acc[j][2]))));
+          acc[j][3] = fmaf(z.w, wd.w, fmaf(z.z, wd.z, fmaf(z.y, wb.w, fmaf(z.x, wb.z, acc[j][3]))));
         }
       }
 #pragma unroll
       for (int j = 0; j < 8; j++) {
         if (r0 + j < rows) {
           float* o = a.out + (size_t)(row0 + r0 + j) * a.ldo + n;
-          const float4 v = make_float4((acc[j][0].x + acc[j][0].y) + bias.x, (acc[j][1].x + acc[j][1].y) + bias.y,
-                                       (acc[j][2].x + acc[j][2].y) + bias.z, (acc[j][3].x + acc[j][3].y) + bias.w);
+          const float4 v = make_float4(acc[j][0] + bias.x, acc[j][1] + bias.y, acc[j][2] + bias.z, acc[j][3] + bias.w);
           if (n + 3 < a.Nout) {
             *reinterpret_cast<float4*>(o) = v;
           } else {
@@ -184,7 +194,9 @@ __global__ void __launch_bounds__(256) k_narrow(const NarrowArgs a) {
     const int d = a.src[s].d;
     for (int i = tid; i < d * NO; i += blockDim.x) {
       const int k = i / NO, j = i % NO;
-      Wsm[(ktot + k) * NO + j] = j < a.No ? a.src[s].W[(size_t)k * a.ldw + j] : 0.f;
+      float w = 0.f;
+      if (j < a.No) w = (a.src[s].W2 && j >= a.src[s].n1) ? a.src[s].W2[(size_t)k * a.ldw + (j - a.src[s].n1)] : a.src[s].W[(size_t)k * a.ldw + j];
+      Wsm[(ktot + k) * NO + j] = w;
     }
     ktot += d;
   }
@@ -269,7 +281,9 @@ __global__ void __launch_bounds__(N2_WARPS * 32) k_narrow2(const NarrowArgs a) {
     const int d = a.src[s].d;
     for (int i = tid; i < d * NO; i += blockDim.x) {
       const int k = i / NO, j = i % NO;
-      Wsm[(ktot + k) * NO + j] = j < a.No ? a.src[s].W[(size_t)k * a.ldw + j] : 0.f;
+      float w = 0.f;
+      if (j < a.No) w = (a.src[s].W2 && j >= a.src[s].n1) ? a.src[s].W2[(size_t)k * a.ldw + (j - a.src[s].n1)] : a.src[s].W[(size_t)k * a.ldw + j];
+      Wsm[(ktot + k) * NO + j] = w;
     }
     ktot += d;
   }
@@ -364,7 +378,7 @@ int launch_wide(gnb_ctx* ctx, const WideArgs& a0) {
   }
   const int64_t nblocks = (a.R + WIDE_ROWS - 1) / WIDE_ROWS;
   int64_t gx = (nblocks + WIDE_WARPS - 1) / WIDE_WARPS;
-  const int64_t cap = (int64_t)ctx->sm_count * 4;     // persistent over row blocks: the weight block is loaded once per CTA
+  const int64_t cap = (int64_t)ctx->sm_count * WIDE_MINB;     // persistent over row blocks, one wave of resident CTAs: the weight block is loaded once per CTA
   if (gx > cap) gx = cap;
   dim3 grid((unsigned)gx, (unsigned)ceil_div(a.Nout, 128));
   double bytes = 4.0 * a.R * (K + a.Nout) + 4.0 * K * a.Nout;

@@ -31,7 +31,9 @@ struct ZsumArgs {
 int launch_zsum(gnb_ctx* ctx, const ZsumArgs& a);
 
 constexpr int NARROW_KMAX = 544;
-struct NarrowSrc { const float* x; int d, ldx; const float* W; };      // W: [d][ldw]
+// W: [d][ldw]; optional second weight block W2 [d][ldw]: output columns j >= n1 take W2[k][j - n1] (two narrow projections of the
+// same rows in one pass, e.g. the decoder's P_s | P_r)
+struct NarrowSrc { const float* x; int d, ldx; const float* W; const float* W2 = nullptr; int n1 = 0; };
 struct NarrowAdd { const float* a; const int32_t* idx; int lda; };
 struct NarrowArgs {
   int64_t R;
