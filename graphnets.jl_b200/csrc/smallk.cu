@@ -158,30 +158,51 @@ __global__ void __launch_bounds__(WIDE_WARPS * 32, WIDE_MINB) k_wide(const WideA
   }
 }
 
-// One thread per (node, column of Z), nodes packed back to back along the thread index (Kz <= 32 columns per node: with one
-// WARP per node a third of the lanes idled at Kz = 21); the sums run over the node's receiver-sorted edges in order.
-__global__ void k_zsum(const ZsumArgs a) {
+// One thread per (group of ZS_NPT consecutive nodes, column of Z), groups packed back to back along the thread index.  The in-edges
+// of consecutive nodes are one contiguous edge range (receiver-sorted), so a thread walks that range ONCE with independent
+// loads and adds every value to the node that owns the edge - rows in ascending order per node (deterministic); the kernel is
+// a chain of dependent memory round trips per thread (offsets -> [sender index ->] values), so fewer, longer threads with more
+// loads in flight take fewer waves (one node per thread: 99 us at N = 262 144).
+constexpr int ZS_NPT = 4;
+__global__ void __launch_bounds__(256) k_zsum(const ZsumArgs a) {
   const int o_s = a.de, o_v = a.de + a.dn, o_u = a.de + 2 * a.dn, o_d = a.de + 2 * a.dn + a.dg;
   const int kz = o_d + 1;
   const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int64_t v = t / kz;
-  const int k = (int)(t - v * kz);
-  if (v >= a.N) return;
-  const int e0 = a.node_in_ptr[v], e1 = a.node_in_ptr[v + 1];
-  const float deg = (float)(e1 - e0);
-  float s = 0.f;
-  if (k < o_s) {
-    for (int e = e0; e < e1; e++) s += a.ef[(size_t)e * a.de + k];
-  } else if (k < o_v) {
-    for (int e = e0; e < e1; e++) s += a.nf[(size_t)a.edge_src[e] * a.dn + (k - o_s)];
-  } else if (k < o_u) {
-    s = deg * a.nf[(size_t)v * a.dn + (k - o_v)];
-  } else if (k < o_d) {
-    s = deg * a.gf[(size_t)a.node_graph[v] * a.dg + (k - o_u)];
+  const int64_t vq = t / kz;
+  const int k = (int)(t - vq * kz);
+  const int64_t v0 = vq * ZS_NPT;
+  if (v0 >= a.N) return;
+  int b[ZS_NPT + 1];
+#pragma unroll
+  for (int i = 0; i <= ZS_NPT; i++) b[i] = a.node_in_ptr[v0 + i < a.N ? v0 + i : a.N];
+  float s[ZS_NPT];
+#pragma unroll
+  for (int i = 0; i < ZS_NPT; i++) s[i] = 0.f;
+  if (k < o_v) {
+    const bool gathered = k >= o_s;
+    const float* base = gathered ? a.nf + (k - o_s) : a.ef + k;
+    const int ld = gathered ? a.dn : a.de;
+#pragma unroll 4
+    for (int e = b[0]; e < b[ZS_NPT]; e++) {
+      const int64_t row = gathered ? (int64_t)__ldg(a.edge_src + e) : (int64_t)e;
+      const float val = __ldg(base + (size_t)row * ld);
+#pragma unroll
+      for (int i = 0; i < ZS_NPT; i++) s[i] += (e >= b[i] && e < b[i + 1]) ? val : 0.f;
+    }
   } else {
-    s = deg;
+#pragma unroll
+    for (int i = 0; i < ZS_NPT; i++) {
+      if (v0 + i < a.N) {
+        const float deg = (float)(b[i + 1] - b[i]);
+        if (k < o_u) s[i] = deg * a.nf[(size_t)(v0 + i) * a.dn + (k - o_v)];
+        else if (k < o_d) s[i] = deg * a.gf[(size_t)a.node_graph[v0 + i] * a.dg + (k - o_u)];
+        else s[i] = deg;
+      }
+    }
   }
-  a.Z[(size_t)v * kz + k] = s;
+#pragma unroll
+  for (int i = 0; i < ZS_NPT; i++)
+    if (v0 + i < a.N) a.Z[(size_t)(v0 + i) * kz + k] = s[i];
 }
 
 // lane owns k = 4*lane + 128*c (+0..3); one row per warp step, 4 rows in flight.
@@ -393,7 +414,7 @@ int launch_zsum(gnb_ctx* ctx, const ZsumArgs& a) {
   if (a.N <= 0) return GNB_OK;
   GNB_CHECK(a.de + 2 * a.dn + a.dg + 1 <= 32, "launch_zsum: aggregated input width > 32");
   Launch L(ctx, "zsum_fp32", 0, 0);
-  k_zsum<<<ceil_div(a.N * (a.de + 2 * a.dn + a.dg + 1), 256), 256, 0, ctx->stream>>>(a);
+  k_zsum<<<ceil_div(ceil_div(a.N, ZS_NPT) * (a.de + 2 * a.dn + a.dg + 1), 256), 256, 0, ctx->stream>>>(a);
   GNB_CUDA(cudaGetLastError());
   return GNB_OK;
 }
