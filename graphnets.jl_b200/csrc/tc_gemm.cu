@@ -30,6 +30,9 @@ namespace {
 
 #define mbar_wait(b, p) mbar_wait_w((b), (p), wd_dead, a.wd)      /* `wd`: the kernel's Watch (tc_ptx.cuh) */
 
+#ifndef GNB_LIN_PREFETCH
+#define GNB_LIN_PREFETCH 0      /* 1: k_tc_lin producers prefetch the rows of their next tile into L2.  Measured SLOWER (cfg5: 541 vs 518 us per launch, profiles/r02_summary.md): the kernel is bound by memory throughput, not by load latency */
+#endif
 constexpr int SLAB = KB_BYTES;            // 128 rows x 64 k bf16
 constexpr int NA = 6, NW = 3;             // ring depths (A: 6 x 16 KB, W: 3 x 32 KB)
 constexpr int G_OFF_A = 0;
@@ -200,8 +203,24 @@ __global__ void __launch_bounds__(G_THREADS, 1) k_tc_lin(const GemmArgs a) {
     const int pw = warp - 4;
     const int hr = lane >> 4, c16 = lane & 15;      // two rows per load instruction, 16 lanes x 16 B per row slab
     uint32_t it = 0;
+    // Experiment (GNB_LIN_PREFETCH=1, off: measured slower): the rows of this warp's NEXT tile -> L2 (one bulk prefetch per
+    // contiguous source), so that the statistics pass below loads at L2 instead of HBM latency
+    auto prefetch_rows = [&](int t) {
+      const int64_t r0 = (int64_t)t * TM + 16 * pw;
+      if (t < a.num_tiles && r0 < a.R && elect_one()) {
+        const int64_t nr = a.R - r0 < 16 ? a.R - r0 : 16;
+        for (int s = 0; s < a.nsrc; s++) {
+          const size_t esz = a.xbf[s] ? 2 : 4;
+          if (a.ldx[s] != a.d[s] || ((a.d[s] * esz) & 15)) continue;      // rows not contiguous (a column slice of a wider buffer)
+          bulk_prefetch_l2(reinterpret_cast<const uint8_t*>(a.x[s]) + (size_t)r0 * a.ldx[s] * esz, (uint32_t)(nr * a.d[s] * esz));
+        }
+      }
+      __syncwarp();
+    };
+    if (GNB_LIN_PREFETCH) prefetch_rows(blockIdx.x);
     for (int tile = blockIdx.x; tile < a.num_tiles && !wd_dead; tile += gridDim.x) {
       const int64_t row0 = (int64_t)tile * TM + 16 * pw;
+      if (GNB_LIN_PREFETCH) prefetch_rows(tile + gridDim.x);
       // ---- LayerNorm statistics of this warp's rows, two-pass in fp32 (src/gngraphnorm.jl:19-26), kept for all column groups
       // (tile_stats above)
       for (int s = 0; s < a.nsrc; s++) {
@@ -432,6 +451,12 @@ struct PackCache { std::mutex mu; std::map<PackKey, __nv_bfloat16*> m; };      /
 // completions to both (same protocol as k_edge5, tc_edge.cu).
 constexpr int F_RING_BYTES = 5 * SLAB;                    // weight ring: 5 x 16 KB slabs, or 10 x 8 KB half slabs (CL2); consumed two slabs at a time
 constexpr int F_THREADS = 14 * 32;
+#ifndef GNB_FFN_EPI_PREFETCH
+#define GNB_FFN_EPI_PREFETCH 0      /* 1: EPI warps prefetch the x / h rows of their next tile into L2.  Measured SLOWER (cfg5: 1175 vs 1129 us per launch) */
+#endif
+#ifndef GNB_FFN_EPI_ROWS
+#define GNB_FFN_EPI_ROWS 2          /* rows in flight per EPI warp in phase 2 at hidden 256 (4 measured slower still: 1232 us; hidden 384 always 2) */
+#endif
 enum { FB_WFULL = 0, FB_WEMPTY = 10, FB_AFULL = 20, FB_AEMPTY = 22, FB_HIDFULL = 24, FB_HSREADY = 26, FB_ACCFULL = 28, FB_ACCFREE = 29 };
 // Block order of a tile, step s -> 2 * chunk + (0: up projection, 1: down projection).  Two hidden buffers: up and down blocks
 // go in PAIRS  up(2p) up(2p+1) down(2p) down(2p+1): conv(2p) runs under up(2p+1), conv(2p+1) under down(2p), and the tensor pipe
@@ -792,8 +817,23 @@ __global__ void __launch_bounds__(F_THREADS, 1) k_tc_ffn(const FfnArgs a) {
 #pragma unroll
     for (int s2 = 0; s2 < F_NB; s2++) b2v[s2] = __ldg(reinterpret_cast<const float4*>(a.b2) + 32 * s2 + lane);
     uint32_t tl = 0;
+    // Experiment (GNB_FFN_EPI_PREFETCH=1, off): phase 2 is a chain of dependent memory round trips per group of rows (ncu: x is no
+    // longer in L2 by then and h has not been touched at all), so an elected lane asks for the x and h rows of this warp's NEXT
+    // tile as two bulk L2 prefetches while the current tile is drained.  It made the kernel 4 % slower: the memory system, not
+    // the latency of these loads, is what bounds it (the extra requests only add contention / early evictions).
+    auto prefetch_rows = [&](int t) {
+      const int64_t r0 = (int64_t)t * TM + 32 * dq;
+      if (t - (int)rank < a.num_tiles && r0 < a.R && elect_one()) {
+        const int64_t nr = a.R - r0 < 32 ? a.R - r0 : 32;
+        bulk_prefetch_l2(a.x + (size_t)r0 * F_H, (uint32_t)(nr * F_H * sizeof(float)));
+        bulk_prefetch_l2(a.h + (size_t)r0 * F_H, (uint32_t)(nr * F_H * sizeof(float)));
+      }
+      __syncwarp();
+    };
+    if (GNB_FFN_EPI_PREFETCH) prefetch_rows(blockIdx.x);
     for (int tile = blockIdx.x; TILE_OK(tile); tile += gridDim.x, tl++) {
       const int64_t row0 = (int64_t)tile * TM + 32 * dq;
+      if (GNB_FFN_EPI_PREFETCH) prefetch_rows(tile + gridDim.x);
       mbar_wait(BAR(FB_ACCFULL), tl & 1);
       tc_fence_after();
 #pragma unroll 1
@@ -819,11 +859,12 @@ __global__ void __launch_bounds__(F_THREADS, 1) k_tc_ffn(const FfnArgs a) {
       __syncwarp();      // the rows below were written by other lanes of this warp
       const int64_t left = a.R - row0;
       const int rows = left < 0 ? 0 : (left > 32 ? 32 : (int)left);
+      constexpr int ER = F_NB == 2 ? GNB_FFN_EPI_ROWS : 2;      // rows in flight per warp
 #pragma unroll 1
-      for (int i0 = 0; i0 < rows; i0 += 2) {
-        float4 yy[2][F_NB], xx[2][F_NB], hh2[2][F_NB];      // 2 rows x F_NB 512-byte segments in flight
+      for (int i0 = 0; i0 < rows; i0 += ER) {
+        float4 yy[ER][F_NB], xx[ER][F_NB], hh2[ER][F_NB];      // ER rows x F_NB 512-byte segments in flight
 #pragma unroll
-        for (int u = 0; u < 2; u++) {
+        for (int u = 0; u < ER; u++) {
           const int64_t r = row0 + (i0 + u < rows ? i0 + u : rows - 1);
           const size_t o = (size_t)r * F_H + 4 * lane;
 #pragma unroll
@@ -834,7 +875,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) k_tc_ffn(const FfnArgs a) {
           }
         }
 #pragma unroll
-        for (int u = 0; u < 2; u++) {
+        for (int u = 0; u < ER; u++) {
           if (i0 + u < rows) {
             const size_t o = (size_t)(row0 + i0 + u) * F_H + 4 * lane;
 #pragma unroll
