@@ -118,38 +118,12 @@ __device__ __forceinline__ float rstd_nb(float var, float e_add, float plus) {
   return plus > 0.f ? __frcp_rn(fmaf(t, r, plus)) : r;      // sqrt(t) = t * rsqrt(t)
 }
 
-__device__ __forceinline__ float4 ld_stream(const float* p) {   // read-once data: do not keep it in L1
-  float4 v;
-  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
-  return v;
-}
 // x is read twice by a CTA, two to three tile periods apart (LayerNorm warps, then the residual of the OUT warps).  ncu showed
 // 45 % of the second reads missing L2 (0.48 GB of DRAM reads per launch): the first read (and the prefetch) mark the lines
 // evict_last, the second one evict_first.
 #ifndef GNB_X_L2_HINTS
 #define GNB_X_L2_HINTS 1
 #endif
-__device__ __forceinline__ uint64_t l2_policy_evict_last() {
-  uint64_t p;
-  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
-  return p;
-}
-__device__ __forceinline__ uint64_t l2_policy_evict_first() {
-  uint64_t p;
-  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
-  return p;
-}
-__device__ __forceinline__ float4 ld_hint(const float4* p, uint64_t pol) {
-  float4 v;
-  asm volatile("ld.global.nc.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p), "l"(pol));
-  return v;
-}
-__device__ __forceinline__ float4 ld_stream_hint(const float* p, uint64_t pol) {
-  float4 v;
-  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;"
-               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p), "l"(pol));
-  return v;
-}
 
 // CL2: the two CTAs of a cluster (an SM pair) run one 256-row MMA stream (cta_group::2): each CTA holds half of every weight
 // block (N split) - half the weight bytes per SM and a ring twice as deep in blocks - and its own 128-row tile otherwise.

@@ -30,6 +30,9 @@ namespace {
 
 #define mbar_wait(b, p) mbar_wait_w((b), (p), wd_dead, a.wd)      /* `wd`: the kernel's Watch (tc_ptx.cuh) */
 
+#ifndef GNB_LIN_L2_HINTS
+#define GNB_LIN_L2_HINTS 0      /* 1: k_tc_lin with gathered addend tables evict_last, streamed rows evict_first after their last read, fp32 output stored streaming.  Measured neutral at hidden 256 (523 vs 523 us per launch) and 5 % slower at 384: off */
+#endif
 #ifndef GNB_LIN_PREFETCH
 #define GNB_LIN_PREFETCH 0      /* 1: k_tc_lin producers prefetch the rows of their next tile into L2.  Measured SLOWER (cfg5: 541 vs 518 us per launch, profiles/r02_summary.md): the kernel is bound by memory throughput, not by load latency */
 #endif
@@ -66,7 +69,7 @@ struct GemmArgs {
 // row stays in registers for both passes; NP row pairs (= 2 NP rows) of NV float4 per lane are loaded before anything is reduced.
 template <int NP, int NV>
 __device__ __forceinline__ void tile_stats(const float* xs, int ldx, int nv, float inv_d, int64_t row0, int64_t R, int hr, int c16,
-                                           float2* st, float eps, int eps_mode) {
+                                           float2* st, float eps, int eps_mode, uint64_t pol) {
 #pragma unroll 1
   for (int r0 = 0; r0 < 16; r0 += 2 * NP) {
     float4 v[NP][NV];
@@ -76,7 +79,7 @@ __device__ __forceinline__ void tile_stats(const float* xs, int ldx, int nv, flo
       row = row < R ? row : R - 1;
       const float* xr = xs + (size_t)row * ldx;
 #pragma unroll
-      for (int j = 0; j < NV; j++) v[p][j] = j < nv ? __ldg(reinterpret_cast<const float4*>(xr + 64 * j)) : f4zero();
+      for (int j = 0; j < NV; j++) v[p][j] = j < nv ? (GNB_LIN_L2_HINTS ? ld_hint(reinterpret_cast<const float4*>(xr + 64 * j), pol) : __ldg(reinterpret_cast<const float4*>(xr + 64 * j))) : f4zero();
     }
     float sum[NP], sq[NP];
 #pragma unroll
@@ -202,6 +205,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) k_tc_lin(const GemmArgs a) {
     // ===================================================== A producers: warp pw owns rows 16 pw .. 16 pw + 15 of the tile
     const int pw = warp - 4;
     const int hr = lane >> 4, c16 = lane & 15;      // two rows per load instruction, 16 lanes x 16 B per row slab
+    const uint64_t pol_last = l2_policy_evict_last(), pol_first = l2_policy_evict_first();      // statistics pass, then the last read
     uint32_t it = 0;
     // Experiment (GNB_LIN_PREFETCH=1, off: measured slower): the rows of this warp's NEXT tile -> L2 (one bulk prefetch per
     // contiguous source), so that the statistics pass below loads at L2 instead of HBM latency
@@ -228,8 +232,8 @@ __global__ void __launch_bounds__(G_THREADS, 1) k_tc_lin(const GemmArgs a) {
         const int d = a.d[s], nv = d >> 6;      // float4 per lane and row (d <= 512: nv <= 8)
         float2* st = stats + s * 128 + 16 * pw;
         // rows up to 256 wide: 8 rows of loads in flight per warp, wider: 4 (the same 64 registers)
-        if (nv <= 4) tile_stats<4, 4>(a.x[s] + 4 * c16, a.ldx[s], nv, 1.0f / (float)d, row0, a.R, hr, c16, st, a.eps[s], a.eps_mode[s]);
-        else tile_stats<2, 8>(a.x[s] + 4 * c16, a.ldx[s], nv, 1.0f / (float)d, row0, a.R, hr, c16, st, a.eps[s], a.eps_mode[s]);
+        if (nv <= 4) tile_stats<4, 4>(a.x[s] + 4 * c16, a.ldx[s], nv, 1.0f / (float)d, row0, a.R, hr, c16, st, a.eps[s], a.eps_mode[s], pol_last);
+        else tile_stats<2, 8>(a.x[s] + 4 * c16, a.ldx[s], nv, 1.0f / (float)d, row0, a.R, hr, c16, st, a.eps[s], a.eps_mode[s], pol_last);
       }
       __syncwarp();
       const int npass = a.resident ? 1 : a.ngroups;
@@ -248,7 +252,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) k_tc_lin(const GemmArgs a) {
             for (int u = 0; u < 4; u++) {
               int64_t row = row0 + 4 * u + (lane >> 3);
               row = row < a.R ? row : a.R - 1;
-              vn[u] = __ldg(reinterpret_cast<const float4*>(xs + (size_t)row * a.ldx[ss]));
+              vn[u] = GNB_LIN_L2_HINTS ? ld_hint(reinterpret_cast<const float4*>(xs + (size_t)row * a.ldx[ss]), pol_first) : __ldg(reinterpret_cast<const float4*>(xs + (size_t)row * a.ldx[ss]));
             }
           } else {
             const float* xs = a.x[ss] + kk + 4 * c16;
@@ -256,7 +260,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) k_tc_lin(const GemmArgs a) {
             for (int u = 0; u < 8; u++) {
               int64_t row = row0 + 2 * u + hr;
               row = row < a.R ? row : a.R - 1;
-              vn[u] = __ldg(reinterpret_cast<const float4*>(xs + (size_t)row * a.ldx[ss]));
+              vn[u] = GNB_LIN_L2_HINTS ? ld_hint(reinterpret_cast<const float4*>(xs + (size_t)row * a.ldx[ss]), pol_first) : __ldg(reinterpret_cast<const float4*>(xs + (size_t)row * a.ldx[ss]));
             }
           }
         };
@@ -320,6 +324,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) k_tc_lin(const GemmArgs a) {
     // ===================================================== drain (TMEM lane quadrant = warp % 4; the two warps of a quadrant
     // split the 64-column chunks of the column group), accumulator-fragment layout: every 4 lanes own one 32 B sector of a row
     const int dq = warp & 3, dh = warp >= 12 ? 1 : 0;
+    const uint64_t pol_add = l2_policy_evict_last();      // the gathered node / graph tables are re-read by every edge of the node / graph
     const uint32_t lane_base = ((uint32_t)(dq * 32)) << 16;
     const int qr = lane >> 2, cq = 2 * (lane & 3);
     uint32_t item = 0;
@@ -370,7 +375,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) k_tc_lin(const GemmArgs a) {
                 const float* ap = a.add[j] + (size_t)(uint32_t)arow[j][k] * a.lda[j] + col;
 #pragma unroll
                 for (int n = 0; n < 8; n++) {
-                  const float2 t = __ldg(reinterpret_cast<const float2*>(ap + 8 * n));
+                  const float2 t = GNB_LIN_L2_HINTS ? ld_hint2(reinterpret_cast<const float2*>(ap + 8 * n), pol_add) : __ldg(reinterpret_cast<const float2*>(ap + 8 * n));
                   v[n].x += t.x; v[n].y += t.y;
                 }
               }
@@ -386,7 +391,10 @@ __global__ void __launch_bounds__(G_THREADS, 1) k_tc_lin(const GemmArgs a) {
                 } else {
                   float* o = a.out + (size_t)row * a.ldo + col;
 #pragma unroll
-                  for (int n = 0; n < 8; n++) *reinterpret_cast<float2*>(o + 8 * n) = v[n];
+                  for (int n = 0; n < 8; n++) {
+                    if (GNB_LIN_L2_HINTS) __stcs(reinterpret_cast<float2*>(o + 8 * n), v[n]);
+                    else *reinterpret_cast<float2*>(o + 8 * n) = v[n];
+                  }
                 }
               }
             }
@@ -451,6 +459,13 @@ struct PackCache { std::mutex mu; std::map<PackKey, __nv_bfloat16*> m; };      /
 // completions to both (same protocol as k_edge5, tc_edge.cu).
 constexpr int F_RING_BYTES = 5 * SLAB;                    // weight ring: 5 x 16 KB slabs, or 10 x 8 KB half slabs (CL2); consumed two slabs at a time
 constexpr int F_THREADS = 14 * 32;
+#ifndef GNB_FFN_L2_HINTS
+#define GNB_FFN_L2_HINTS 1      /* L2 eviction priorities for the two reads of x (ncu: the second one missed L2: 2.2 GB of DRAM reads per edge launch) */
+#endif
+#ifndef GNB_FFN_Y_STREAM
+#define GNB_FFN_Y_STREAM 0      /* 1: final y rows stored streaming (evict-first); measured neutral (1047 vs 1051 us per launch) */
+#endif
+#define FFN_LDX(p) (GNB_FFN_L2_HINTS ? ld_hint((p), pol_last) : __ldg(p))
 #ifndef GNB_FFN_EPI_PREFETCH
 #define GNB_FFN_EPI_PREFETCH 0      /* 1: EPI warps prefetch the x / h rows of their next tile into L2.  Measured SLOWER (cfg5: 1175 vs 1129 us per launch) */
 #endif
@@ -719,9 +734,11 @@ __global__ void __launch_bounds__(F_THREADS, 1) k_tc_ffn(const FfnArgs a) {
     // ===================================================== A producers (next tile): LayerNorm -> bf16 slabs, warp q rows 32 q .. + 31
     const int q = warp - 4;
     const int hr = lane >> 4, c16 = lane & 15;
+    const uint64_t pol_last = l2_policy_evict_last();
     uint32_t tl = 0;
     for (int tile = blockIdx.x; TILE_OK(tile); tile += gridDim.x, tl++) {
       const int64_t row0 = (int64_t)tile * TM + 32 * q;
+      // (x is read again by the EPI warps one to two tile periods later: evict_last here, evict_first there)
       // two-pass statistics, 16 lanes per row, the row in registers (4 float4 per lane), 2 row pairs in flight
       const float* xs = a.x + 4 * c16;
 #pragma unroll 1
@@ -732,7 +749,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) k_tc_ffn(const FfnArgs a) {
           int64_t row = row0 + r0 + 2 * p + hr;
           row = row < a.R ? row : a.R - 1;
 #pragma unroll
-          for (int j = 0; j < F_KS; j++) v[p][j] = __ldg(reinterpret_cast<const float4*>(xs + (size_t)row * F_H + 64 * j));
+          for (int j = 0; j < F_KS; j++) v[p][j] = FFN_LDX(reinterpret_cast<const float4*>(xs + (size_t)row * F_H + 64 * j));
         }
         float sum[2], sq[2];
 #pragma unroll
@@ -782,7 +799,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) k_tc_ffn(const FfnArgs a) {
           for (int u = 0; u < 8; u++) {
             int64_t row = row0 + i0 + 2 * u + hr;
             row = row < a.R ? row : a.R - 1;
-            v[u] = __ldg(reinterpret_cast<const float4*>(xs + (size_t)row * F_H + 64 * ks));
+            v[u] = FFN_LDX(reinterpret_cast<const float4*>(xs + (size_t)row * F_H + 64 * ks));
           }
 #pragma unroll
           for (int u = 0; u < 8; u++) {
@@ -813,6 +830,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) k_tc_ffn(const FfnArgs a) {
     const int dq = warp & 3;
     const uint32_t lane_base = ((uint32_t)(dq * 32)) << 16;
     const int qr = lane >> 2, cq = 2 * (lane & 3);
+    const uint64_t pol_first = l2_policy_evict_first();
     float4 b2v[F_NB];
 #pragma unroll
     for (int s2 = 0; s2 < F_NB; s2++) b2v[s2] = __ldg(reinterpret_cast<const float4*>(a.b2) + 32 * s2 + lane);
@@ -870,8 +888,8 @@ __global__ void __launch_bounds__(F_THREADS, 1) k_tc_ffn(const FfnArgs a) {
 #pragma unroll
           for (int s2 = 0; s2 < F_NB; s2++) {
             yy[u][s2] = __ldcg(reinterpret_cast<const float4*>(a.y + o + 128 * s2));
-            xx[u][s2] = __ldg(reinterpret_cast<const float4*>(a.x + o + 128 * s2));
-            hh2[u][s2] = __ldg(reinterpret_cast<const float4*>(a.h + o + 128 * s2));
+            xx[u][s2] = GNB_FFN_L2_HINTS ? ld_stream_hint(a.x + o + 128 * s2, pol_first) : __ldg(reinterpret_cast<const float4*>(a.x + o + 128 * s2));      // last read of x
+            hh2[u][s2] = GNB_FFN_L2_HINTS ? ld_stream_hint(a.h + o + 128 * s2, pol_first) : __ldg(reinterpret_cast<const float4*>(a.h + o + 128 * s2));     // only read of h
           }
         }
 #pragma unroll
@@ -881,8 +899,9 @@ __global__ void __launch_bounds__(F_THREADS, 1) k_tc_ffn(const FfnArgs a) {
 #pragma unroll
             for (int s2 = 0; s2 < F_NB; s2++) {
               const float4 X = xx[u][s2], Hh = hh2[u][s2], Y = yy[u][s2], Bv = b2v[s2];
-              *reinterpret_cast<float4*>(a.y + o + 128 * s2) = make_float4(((X.x + Hh.x) + Y.x) + Bv.x, ((X.y + Hh.y) + Y.y) + Bv.y,
-                                                                         ((X.z + Hh.z) + Y.z) + Bv.z, ((X.w + Hh.w) + Y.w) + Bv.w);
+              const float4 out4 = make_float4(((X.x + Hh.x) + Y.x) + Bv.x, ((X.y + Hh.y) + Y.y) + Bv.y, ((X.z + Hh.z) + Y.z) + Bv.z, ((X.w + Hh.w) + Y.w) + Bv.w);
+              if (GNB_FFN_Y_STREAM) __stcs(reinterpret_cast<float4*>(a.y + o + 128 * s2), out4);
+              else *reinterpret_cast<float4*>(a.y + o + 128 * s2) = out4;
             }
           }
         }
