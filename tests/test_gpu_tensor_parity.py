@@ -163,3 +163,19 @@ def test_fused_narrow_decoder_equals_unfused(gn):
         assert np.abs(a - b).max() <= 1e-5 * np.abs(b).max(), "fused and unfused decoder differ by more than fp32 rounding"
     _, ref = run_oracle(layers, w)
     assert_parity(res["1"][0], ref, BF16_TOL, "fused decoder, variable graphs")
+
+
+def test_many_small_graphs_graph_rows_16_per_cta(gn):
+    """2500 tiny graphs (1-6 nodes): B >= 16 x 148, so the graph-level rows of every core run on k_graph_post<16> (16 graphs per
+    CTA; below that batch size every other test runs the 8-graph instantiation), with a ragged last CTA (2500 = 156 x 16 + 4)."""
+    rng = np.random.default_rng(31)
+    adjs = []
+    while len(adjs) < 2500:
+        n = int(rng.integers(1, 7))
+        adjs.append((rng.random((n, n)) < 0.6).astype(np.uint8))
+    layers, w = _stack128(rng, adjs)
+    x, got, prof = _run(gn, layers, w, "auto")
+    assert x.graphs.B == 2500 and x.graphs.B >= 16 * torch.cuda.get_device_properties(0).multi_processor_count
+    assert prof["graph_post"]["launches"] == 2, list(prof)
+    _, ref = run_oracle(layers, w)
+    assert_parity(got, ref, BF16_TOL, "2500 tiny graphs (k_graph_post<16>)")
