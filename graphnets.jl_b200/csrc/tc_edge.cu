@@ -124,6 +124,9 @@ __device__ __forceinline__ float rstd_nb(float var, float e_add, float plus) {
 #ifndef GNB_X_L2_HINTS
 #define GNB_X_L2_HINTS 1
 #endif
+#ifndef GNB_EDGE_XPREFETCH
+#define GNB_EDGE_XPREFETCH 1      /* the weight loader's bulk L2 prefetch of the x rows two passes ahead; without it 851 vs 842 us per edge launch, forward 6.14 vs 6.03 ms (same box) */
+#endif
 
 // CL2: the two CTAs of a cluster (an SM pair) run one 256-row MMA stream (cta_group::2): each CTA holds half of every weight
 // block (N split) - half the weight bytes per SM and a ring twice as deep in blocks - and its own 128-row tile otherwise.
@@ -263,7 +266,7 @@ __global__ void __launch_bounds__(E_THREADS, 1) k_edge5(const __grid_constant__ 
       // the x rows of the pass after next -> L2: the LayerNorm warps (one pass ahead of the MMAs) then load at L2 latency
       // instead of HBM latency
       const int64_t pre0 = ((int64_t)tile + 2 * (int64_t)grid) * TM;
-      if (pre0 < a.R && elect_one()) {
+      if (GNB_EDGE_XPREFETCH && pre0 < a.R && elect_one()) {
         const int64_t prows = a.R - pre0 < TM ? a.R - pre0 : TM;
         if (GNB_X_L2_HINTS)
           asm volatile("cp.async.bulk.prefetch.L2.global.L2::cache_hint [%0], %1, %2;" ::"l"(a.x + (size_t)pre0 * H),
